@@ -1,0 +1,230 @@
+"""Pin the oracle against the REAL reference and write the golden fixtures under tests/golden/.
+
+Run in the build container only (needs /root/reference):  python -m oracle.make_golden
+
+1. loss / metric functions: reference src/util.py vs oracle/losses.py, bit-for-bit in fp32, on seeded
+   full-size inputs (values stored, inputs regenerated from the seed) and on small odd-shaped inputs
+   with exact zeros (inputs stored).
+2. modules: reference src/network classes vs oracle/model.py with identical deterministic weights;
+   outputs, input grads, parameter grads and BN buffers must agree to fp32 round-off; the
+   reference's results are stored (sub-sampled) in tests/golden/model_golden.npz.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import cases, fixtures as fx, losses as ol, ref_import  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def loss_cases():
+    """name -> (pred, target, rgb) generators; the big ones are regenerated from seeds in the tests."""
+    out = {}
+
+    def survey():
+        torch.manual_seed(0)
+        p = torch.rand(4, 1, 448, 576) * 9 + 0.5
+        t = torch.rand(4, 1, 448, 576) * 9 + 0.5
+        rgb = torch.rand(4, 3, 448, 576)
+        return p, t, rgb
+
+    def bench_like():
+        g = torch.Generator().manual_seed(1234)
+        rgb = torch.randn(3, 3, 448, 576, generator=g)
+        t = torch.rand(3, 1, 448, 576, generator=g) * 9.9 + 0.1
+        p = t * torch.exp(0.1 * torch.randn(3, 1, 448, 576, generator=g)) * 1.3
+        p[:, :, 100:140, 200:300] = 0.0          # exact zeros as the final ReLU produces
+        return p, t, rgb
+
+    def small_zeros():
+        g = torch.Generator().manual_seed(99)
+        rgb = torch.randn(3, 3, 37, 53, generator=g)
+        t = torch.rand(3, 1, 37, 53, generator=g) * 5 + 0.2
+        p = torch.rand(3, 1, 37, 53, generator=g) * 5
+        p[p < 1.0] = 0.0
+        t[:, :, 5:9, 7:19] = 0.0                 # invalid target pixels (masked only by SiLog)
+        return p, t, rgb
+
+    def tiny():
+        g = torch.Generator().manual_seed(5)
+        return (torch.rand(1, 1, 2, 3, generator=g) + 0.5, torch.rand(1, 1, 2, 3, generator=g) + 0.5,
+                torch.rand(1, 3, 2, 3, generator=g))
+
+    out["survey"] = survey
+    out["bench_like"] = bench_like
+    out["small_zeros"] = small_zeros
+    out["tiny"] = tiny
+    return out
+
+
+THRESH = [1.05, 1.05 ** 2, 1.05 ** 3, 1.25]
+
+
+def eval_all(mod, p, t, rgb):
+    r = {
+        "si": mod.scale_invariant_loss(p, t).item(),
+        "si_sqrt": mod.scale_invariant_loss(p, t, sqroot=True).item(),
+        "silog": mod.silog_loss(p, t, mask=(t > 0)).item(),
+        "grad": mod.gradient_loss(p, t).item(),
+        "edge": mod.edge_aware_loss(p, t, rgb, 0.5).item(),
+        "absrel": mod.absolute_relative_error(p, t).item(),
+    }
+    for i, th in enumerate(THRESH):
+        r[f"delta{i}"] = mod.delta_thres(p, t, thres=th).item()
+    return r
+
+
+def grads_all(mod, p, t, rgb):
+    out = {}
+    for name, fn in [("si", lambda q: mod.scale_invariant_loss(q, t)),
+                     ("silog", lambda q: mod.silog_loss(q, t, mask=(t > 0))),
+                     ("grad", lambda q: mod.gradient_loss(q, t)),
+                     ("edge", lambda q: mod.edge_aware_loss(q, t, rgb, 0.5))]:
+        q = p.clone().requires_grad_(True)
+        fn(q).backward()
+        out[name] = q.grad
+    return out
+
+
+def do_losses(ref_util):
+    gold = {}
+    small_store = {}
+    for name, gen in loss_cases().items():
+        p, t, rgb = gen()
+        r_ref = eval_all(ref_util, p, t, rgb)
+        r_ora = eval_all(ol, p, t, rgb)
+        for k in r_ref:
+            a, b = r_ref[k], r_ora[k]
+            assert (a == b) or (np.isnan(a) and np.isnan(b)), f"oracle != reference for {name}/{k}: {a} vs {b}"
+        r64 = eval_all(ol, p.double(), t.double(), rgb.double())
+        counts = ol.delta_counts(p, t, THRESH)
+        g_ref = grads_all(ref_util, p, t, rgb)
+        g_ora = grads_all(ol, p, t, rgb)
+        for k in g_ref:
+            a_, b_ = torch.nan_to_num(g_ref[k], 0.0, 0.0, 0.0), torch.nan_to_num(g_ora[k], 0.0, 0.0, 0.0)
+            assert float((a_ - b_).abs().max()) <= 1e-6 * float(a_.abs().max()), f"grad mismatch {name}/{k}"
+        gold[name] = {"fp32": r_ref, "fp64": r64, "delta_counts": counts.tolist(),
+                      "grad_abs_sum": {k: float(torch.nan_to_num(v, 0.0, 0.0, 0.0).abs().double().sum())
+                                       for k, v in g_ref.items()}}
+        if p.numel() < 10000:
+            small_store[f"{name}.pred"] = p.numpy()
+            small_store[f"{name}.target"] = t.numpy()
+            small_store[f"{name}.rgb"] = rgb.numpy()
+            for k, v in g_ref.items():
+                small_store[f"{name}.grad_{k}"] = v.numpy()
+        print("loss case", name, {k: round(v, 6) for k, v in r_ref.items()})
+    # main.evaluate_model metric set is inline code in the reference loop (main.py:254-392); record the oracle's
+    # restatement on the small case as a regression vector (checked by hand against the formulae).
+    p, t, rgb = loss_cases()["small_zeros"]()
+    gold["small_zeros"]["evaluate_model_sums"] = ol.evaluate_metric_sums(p, t)
+    with open(os.path.join(GOLD, "loss_metric_golden.json"), "w") as f:
+        json.dump(gold, f, indent=1, sort_keys=True)
+    np.savez_compressed(os.path.join(GOLD, "loss_small_inputs.npz"), **small_store)
+
+
+def build_reference(kind, kw, ref_blocks, ref_dpt, ref_sem):
+    if kind == "rcu":
+        return ref_blocks.ResidualConvUnit_custom(kw["features"], nn.ReLU(False), False)
+    if kind == "fusion":
+        return ref_blocks.FeatureFusionBlock_custom(kw["features"], nn.ReLU(False), deconv=False, bn=False,
+                                                    expand=kw["expand"], align_corners=True)
+    if kind == "resblock":
+        return ref_sem.ResidualBlock(kw["cin"], kw["cout"])
+    if kind == "dinohead":
+        return ref_dpt.Dinov2Head(1, 384, 128, use_bn=False, out_channels=[128, 256, 512, 512], use_clstoken=False)
+    if kind == "xattn":
+        return ref_sem.CrossAttention(kw["dim"], window_size=16)
+    raise KeyError(kind)
+
+
+def compare(a, b, what, tol=2e-5):
+    assert set(a) == set(b), (what, set(a) ^ set(b))
+    worst = 0.0
+    for k in a:
+        scale = max(float(a[k].abs().max()), 1e-6)
+        err = float((a[k] - b[k]).abs().max()) / scale
+        worst = max(worst, err)
+        assert err < tol, f"{what}: {k} rel err {err}"
+    return worst
+
+
+def do_modules(ref_blocks, ref_dpt, ref_sem, ref_small):
+    store = {}
+    for name, (kind, kw, shapes, fkw) in cases.CASES.items():
+        ref = fx.fill_deterministic(build_reference(kind, kw, ref_blocks, ref_dpt, ref_sem))
+        ora = fx.fill_deterministic(cases.build_oracle(kind, kw))
+        assert list(ref.state_dict().keys()) == list(ora.state_dict().keys()), name
+        ora.load_state_dict(ref.state_dict(), strict=True)
+        r = cases.run_case(ref, name)
+        o = cases.run_case(ora, name)
+        w = compare(r, o, name)
+        print(f"module case {name}: oracle vs reference worst rel err {w:.2e} ({len(r)} tensors)")
+        for k, v in r.items():
+            store[f"{name}/{k}"] = fx.subsample(v).numpy()
+    # full models
+    standins = fx.load_standins()
+    x, t = cases.full_batch()
+    for tag, ref_ctor, ora_ctor in [
+        ("semantics", lambda: ref_sem.MidasNetSemantics(None, features=64, backbone="efficientnet_lite3",
+                                                        exportable=True, non_negative=True, cfg=fx.model_cfg(),
+                                                        blocks={"expand": True}, dinov2_type="dinov2_vits14"),
+         cases.build_oracle_semantics),
+        ("small", lambda: ref_small.MidasNet_small(None, features=64, backbone="efficientnet_lite3", exportable=True,
+                                                   non_negative=True, cfg=fx.model_cfg(), blocks={"expand": True}),
+         cases.build_oracle_small),
+    ]:
+        with ref_import.offline_hub(standins.hub_load_standin):
+            ref = ref_ctor()
+        ora = ora_ctor(standins)
+        kr = [k for k in ref.state_dict().keys()]
+        ko = [k for k in ora.state_dict().keys()]
+        assert kr == ko, (tag, set(kr) ^ set(ko))
+        cases.prepare_full(ref)
+        ora.load_state_dict(ref.state_dict(), strict=True)
+        res = {}
+        for m, slot in ((ref, "ref"), (ora, "ora")):
+            m.train()
+            out = m(x)
+            loss = ol.scale_invariant_loss(out.unsqueeze(1), t)
+            loss.backward()
+            d = {"out": out.detach(), "loss": loss.detach().reshape(1)}
+            for k, p in m.named_parameters():
+                if p.grad is not None and not k.startswith(("pretrained.", "dinov2.")):
+                    d[f"gp.{k}"] = p.grad.detach()
+            for k, b in m.named_buffers():
+                if not k.startswith(("pretrained.", "dinov2.")):
+                    d[f"buf.{k}"] = b.detach().float()
+            m.eval()
+            with torch.no_grad():
+                d["out_eval"] = m(x).detach()
+            res[slot] = d
+        none_grad = sorted(k for k, p in ref.named_parameters() if p.requires_grad and p.grad is None)
+        w = compare(res["ref"], res["ora"], f"full/{tag}", tol=5e-4)
+        print(f"full model {tag}: oracle vs reference worst rel err {w:.2e}; loss {float(res['ref']['loss']):.6f}; "
+              f"zero fraction {float((res['ref']['out'] == 0).float().mean()):.3f}; params without grad: {len(none_grad)}")
+        for k, v in res["ref"].items():
+            store[f"full_{tag}/{k}"] = fx.subsample(v, 30000).numpy()
+        store[f"full_{tag}/nograd_keys"] = np.array(none_grad)
+        store[f"full_{tag}/state_keys"] = np.array(kr)
+    np.savez_compressed(os.path.join(GOLD, "model_golden.npz"), **store)
+
+
+def main():
+    torch.set_num_threads(os.cpu_count())
+    os.makedirs(GOLD, exist_ok=True)
+    ref_util, ref_blocks, ref_dpt, ref_sem, ref_small, ref_large = ref_import.import_reference()
+    do_losses(ref_util)
+    do_modules(ref_blocks, ref_dpt, ref_sem, ref_small)
+    print("golden fixtures written to", GOLD)
+
+
+if __name__ == "__main__":
+    main()
