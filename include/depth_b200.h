@@ -1,0 +1,119 @@
+/* depth_b200.h - C ABI of libdepth_b200.so (hand-written sm_100a kernels for the dense-prediction hot path).
+ *
+ * The reference (HairongLuo/monocular-depth-estimation-cil) is pure Python/PyTorch and has no FFI; its seam is
+ * the Python call signatures in src/util.py, src/main.py:51-89 and the nn.Module classes in src/network/.
+ * Every entry point below names the reference arithmetic it replaces.  The Python host side
+ * (monocular-depth-estimation-cil_b200/) binds these with ctypes and mirrors the reference signatures.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the comment says "host";
+ *   - the caller owns all memory including workspaces (query the *_workspace() functions);
+ *   - nothing allocates, synchronises or keeps mutable global state; work is enqueued on `stream`;
+ *   - return 0 on success, a negative DP_ERR_* code otherwise; dp_last_error() gives the thread-local message;
+ *   - re-entrant across host threads and streams (autograd's backward thread calls in concurrently).
+ * Activations handled by the conv/BN/resize entry points are NHWC bf16; loss/metric inputs are the
+ * reference's NCHW fp32 (B,1,H,W) tensors.
+ */
+#ifndef DEPTH_B200_H
+#define DEPTH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define DP_ABI_VERSION 1
+
+int dp_abi_version(void);
+const char* dp_last_error(void);
+/* number of kernel launches issued through this library by the calling process (bench.py's gpu_launches) */
+unsigned long long dp_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Loss / metric reductions
+ * ---------------------------------------------------------------------------------------------- */
+/* per-sample raw moments, double[B][DP_NMOM] */
+#define DP_NMOM 16
+#define DP_M_S1 0  /* sum d,   d = log(p+eps)-log(t+eps)              util.py:143-150 */
+#define DP_M_S2 1  /* sum d^2                                                          */
+#define DP_M_M0 2  /* #pixels with t>0                                 util.py:108     */
+#define DP_M_M1 3  /* sum d over t>0                                   util.py:114-121 */
+#define DP_M_M2 4  /* sum d^2 over t>0                                                 */
+#define DP_M_GX 5  /* sum ||dx p|-|dx t||  over (H, W-1)               util.py:35-41   */
+#define DP_M_GY 6  /* sum ||dy p|-|dy t||  over (H-1, W)               util.py:36-42   */
+#define DP_M_EX 7  /* sum g*||dx p|-|dx t||, g = normalised RGB grad   util.py:85      */
+#define DP_M_EY 8  /*                                                   util.py:86      */
+#define DP_M_AR 9  /* sum |t-p|/(t+1e-6)                               util.py:218     */
+#define DP_M_AB 10 /* sum |p-t|                                        main.py:291     */
+#define DP_M_SQ 11 /* sum (p-t)^2                                      main.py:292     */
+#define DP_M_V0 12 /* #pixels with t>1e-6                              main.py:304     */
+#define DP_M_V1 13 /* sum dv, dv = log(max(p,1e-6)) - log(t) over t>1e-6  main.py:311-318 */
+#define DP_M_V2 14 /* sum dv^2                                                          */
+
+/* which terms a pass evaluates */
+#define DP_F_SI 1u
+#define DP_F_SILOG 2u
+#define DP_F_GRAD 4u
+#define DP_F_EDGE 8u
+#define DP_F_ABSREL 16u
+#define DP_F_M4 32u
+
+/* dp_loss_combine output slots, float[DP_NLOSS] */
+#define DP_NLOSS 8
+#define DP_L_TOTAL 0     /* main.py:82   */
+#define DP_L_SI 1        /* si * alpha   */
+#define DP_L_SILOG 2
+#define DP_L_GRAD 3
+#define DP_L_EDGE 4
+#define DP_L_ABSREL 5    /* util.py:218  */
+#define DP_L_SI_RAW 6    /* unweighted (sqroot applied if requested: evaluation.py:157) */
+#define DP_L_SILOG_RAW 7
+
+#define DP_MAX_THR 8
+
+size_t dp_depth_moments_workspace(int B, int H, int W);
+size_t dp_rgb_minmax_bytes(void);
+
+/* util.py:58-70: per-block (min,max) of the RGB gradient magnitude; rgb is (B,3,H,W) fp32; out is dp_rgb_minmax_bytes() */
+int dp_rgb_gradmag_minmax(const float* rgb, int B, int H, int W, float* minmax_partials, cudaStream_t stream);
+
+/* One pass over pred/target (B,1,H,W fp32) [and rgb]: fills moments[B][DP_NMOM] for the terms in `flags`.
+ * Replaces the elementwise+reduction chains of util.py:24-156,210-219 and main.py:291-318. */
+int dp_depth_moments(const float* pred, const float* target, const float* rgb, const float* minmax_partials,
+                     int B, int H, int W, unsigned flags, float eps, double* moments,
+                     void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* moments -> scalars of main.py:66-82 (weights applied as there); per_sample (float[B], may be NULL) gets the
+ * per-sample SI terms (sqrt'ed when sqroot!=0, evaluation.py:157). */
+int dp_loss_combine(const double* moments, int B, int H, int W, unsigned flags, float w_si, float w_silog,
+                    float variance_focus, float w_grad, float beta, int sqroot, float* out, float* per_sample,
+                    cudaStream_t stream);
+
+/* d(total loss)/d(pred): what autograd derives from main.py:66-82; grad_out is a device scalar or NULL (=1);
+ * si_sample_scale (float[B] or NULL) multiplies the SI term per sample (1/(2*sqrt(v_b)) for sqroot=True). */
+int dp_loss_backward(const float* pred, const float* target, const float* rgb, const float* minmax_partials,
+                     const double* moments, const float* grad_out, const float* si_sample_scale,
+                     int B, int H, int W, unsigned flags, float eps,
+                     float w_si, float w_silog, float variance_focus, float w_grad, float beta, float* grad_pred,
+                     cudaStream_t stream);
+
+/* util.py:200-205 (aligned=1, eps_div=0: scale from moments[.][DP_M_S1]) or main.py:318-321 (aligned=0, eps_div=1e-6).
+ * thresholds: HOST pointer to nthr floats.  counts: device u64[B][nthr]. */
+int dp_delta_counts(const float* pred, const float* target, const double* moments, int B, int H, int W,
+                    const float* thresholds, int nthr, int aligned, float eps_div, unsigned long long* counts,
+                    void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* evaluation.py:157-166 for one batch: out[0]=SI-RMSE, out[1]=AbsRel, out[2+k]=delta_k */
+int dp_metrics_combine(const double* moments, const unsigned long long* counts, int B, int H, int W, int nthr,
+                       float* out, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEPTH_B200_H */

@@ -1,0 +1,94 @@
+"""ctypes binding of libdepth_b200.so (the C ABI declared in include/depth_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a call is made without a CUDA
+device, this module raises.  PyTorch is used only for device memory and streams.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdepth_b200.so")
+
+c_int, c_uint, c_float, c_size_t, c_void_p, c_u64 = (ctypes.c_int, ctypes.c_uint, ctypes.c_float, ctypes.c_size_t,
+                                                      ctypes.c_void_p, ctypes.c_uint64)
+
+
+class DepthB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DepthB200Error(
+                f"{LIB_PATH} not found: build it with `python __graft_entry__.py` (nvcc, sm_100a). "
+                "There is no CPU or PyTorch fallback for the hot path.")
+        _lib = ctypes.CDLL(LIB_PATH)
+        _declare(_lib)
+        if _lib.dp_abi_version() != 1:
+            raise DepthB200Error("libdepth_b200.so ABI version mismatch")
+    return _lib
+
+
+def _declare(L):
+    L.dp_abi_version.restype = c_int
+    L.dp_last_error.restype = ctypes.c_char_p
+    L.dp_launch_count.restype = c_u64
+    for name in dir(_Sig):
+        if name.startswith("dp_"):
+            fn = getattr(L, name)
+            res, args = getattr(_Sig, name)
+            fn.restype = res
+            fn.argtypes = args
+
+
+P = c_void_p
+
+
+class _Sig:
+    dp_depth_moments_workspace = (c_size_t, [c_int, c_int, c_int])
+    dp_rgb_minmax_bytes = (c_size_t, [])
+    dp_rgb_gradmag_minmax = (c_int, [P, c_int, c_int, c_int, P, P])
+    dp_depth_moments = (c_int, [P, P, P, P, c_int, c_int, c_int, c_uint, c_float, P, P, c_size_t, P])
+    dp_loss_combine = (c_int, [P, c_int, c_int, c_int, c_uint, c_float, c_float, c_float, c_float, c_float, c_int,
+                               P, P, P])
+    dp_loss_backward = (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_uint, c_float, c_float, c_float, c_float,
+                                c_float, c_float, P, P])
+    dp_delta_counts = (c_int, [P, P, P, c_int, c_int, c_int, ctypes.POINTER(c_float), c_int, c_int, c_float, P, P,
+                               c_size_t, P])
+    dp_metrics_combine = (c_int, [P, P, c_int, c_int, c_int, c_int, P, P])
+
+
+def check(code):
+    if code != 0:
+        raise DepthB200Error(f"libdepth_b200 error {code}: {lib().dp_last_error().decode()}")
+
+
+def ptr(t):
+    """device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise DepthB200Error("depth_b200 kernels need CUDA tensors (no CPU fallback)")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count():
+    return int(lib().dp_launch_count())
+
+
+# flags (include/depth_b200.h)
+F_SI, F_SILOG, F_GRAD, F_EDGE, F_ABSREL, F_M4 = 1, 2, 4, 8, 16, 32
+NMOM, NLOSS, MAX_THR = 16, 8, 8
+M_S1, M_S2, M_M0, M_M1, M_M2, M_GX, M_GY, M_EX, M_EY, M_AR, M_AB, M_SQ, M_V0, M_V1, M_V2 = range(15)
+L_TOTAL, L_SI, L_SILOG, L_GRAD, L_EDGE, L_ABSREL, L_SI_RAW, L_SILOG_RAW = range(8)

@@ -1,0 +1,24 @@
+// ABI version, thread-local error string and the launch counter.
+#include "common.cuh"
+#include "../../include/depth_b200.h"
+#include <atomic>
+#include <cstring>
+
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+int dp_set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+void dp_count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+extern "C" {
+int dp_abi_version(void) { return DP_ABI_VERSION; }
+const char* dp_last_error(void) { return g_err; }
+unsigned long long dp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+}

@@ -1,0 +1,574 @@
+// Fused, single-pass loss and metric reductions (HBM-bound by design).
+//
+// Reference arithmetic being replaced (all /root/reference/src):
+//   util.py:129-156  scale_invariant_loss      util.py:90-127   silog_loss
+//   util.py:24-44    gradient_loss             util.py:46-88    edge_aware_loss
+//   util.py:210-219  absolute_relative_error   util.py:183-207  delta_thres
+//   main.py:51-89    combined_loss             main.py:254-392  evaluate_model metric set
+//
+// One pass over (pred, target[, rgb]) produces per-sample raw moments in fp64 (dp_depth_moments);
+// tiny combine kernels turn moments into the reference's scalars; the backward is one stencil pass.
+// Algorithmic HBM bytes: 8 B/px forward (pred+target fp32 once), 12 B/px backward (re-read + grad
+// write); the edge term adds 12 B/px of RGB per pass plus a 12 B/px min/max pre-pass.
+#include "common.cuh"
+#include "../../include/depth_b200.h"
+
+namespace {
+
+using namespace dp;
+
+constexpr int NMOM = DP_NMOM;
+constexpr int TPB = 256;
+
+struct MomArgs {
+  const float* pred;
+  const float* target;
+  const float* rgb;
+  int B, H, W, chunks;
+  unsigned flags;
+  float eps;
+  const float* mm_partials;  // [mm_n][2] per-block (min,max) of the rgb gradient magnitude
+  int mm_n;
+  double* partials;  // [B][chunks][NMOM]
+};
+
+// RGB gradient magnitude at (y,x): sqrt(mean_c dx^2 + mean_c dy^2), right/bottom zero padded (util.py:58-67)
+__device__ __forceinline__ float grad_mag(const float* rgb_b, int H, int W, int y, int x) {
+  const size_t plane = (size_t)H * W;
+  float sx = 0.f, sy = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* r = rgb_b + c * plane + (size_t)y * W + x;
+    float v = __ldg(r);
+    float dx = (x + 1 < W) ? fabsf(v - __ldg(r + 1)) : 0.f;
+    float dy = (y + 1 < H) ? fabsf(v - __ldg(r + W)) : 0.f;
+    sx += dx * dx;
+    sy += dy * dy;
+  }
+  return sqrtf(sx / 3.0f + sy / 3.0f);
+}
+
+__global__ void __launch_bounds__(TPB) rgb_minmax_kernel(const float* __restrict__ rgb, int B, int H, int W,
+                                                         float* __restrict__ out /*[grid][2]*/) {
+  const size_t total = (size_t)B * H * W;
+  float mn = INFINITY, mx = -INFINITY;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int b = (int)(i / ((size_t)H * W));
+    int rem = (int)(i - (size_t)b * H * W);
+    int y = rem / W, x = rem - y * W;
+    float g = grad_mag(rgb + (size_t)b * 3 * H * W, H, W, y, x);
+    mn = fminf(mn, g);
+    mx = fmaxf(mx, g);
+  }
+  __shared__ float smn[32], smx[32];
+  mn = warp_min(mn);
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int nw = blockDim.x >> 5;
+    mn = threadIdx.x < nw ? smn[threadIdx.x] : INFINITY;
+    mx = threadIdx.x < nw ? smx[threadIdx.x] : -INFINITY;
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    if (threadIdx.x == 0) { out[2 * blockIdx.x] = mn; out[2 * blockIdx.x + 1] = mx; }
+  }
+}
+
+__device__ __forceinline__ void reduce_minmax(const float* parts, int n, float& gmin, float& gmax) {
+  __shared__ float s_mm[2];
+  float mn = INFINITY, mx = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    mn = fminf(mn, parts[2 * i]);
+    mx = fmaxf(mx, parts[2 * i + 1]);
+  }
+  __shared__ float smn[32], smx[32];
+  mn = warp_min(mn);
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int nw = blockDim.x >> 5;
+    for (int i = 0; i < nw; ++i) { mn = fminf(mn, smn[i]); mx = fmaxf(mx, smx[i]); }
+    s_mm[0] = mn; s_mm[1] = mx;
+  }
+  __syncthreads();
+  gmin = s_mm[0];
+  gmax = s_mm[1];
+}
+
+// One thread handles VEC consecutive pixels of one row.  Moments accumulate in fp64 per thread.
+template <int VEC, bool STENCIL, bool EDGE>
+__global__ void __launch_bounds__(TPB) moments_kernel(MomArgs a) {
+  const int b = blockIdx.y;
+  const int H = a.H, W = a.W;
+  const int rows_per = (H + a.chunks - 1) / a.chunks;
+  const int r0 = blockIdx.x * rows_per;
+  const int r1 = min(H, r0 + rows_per);
+  const float* __restrict__ P = a.pred + (size_t)b * H * W;
+  const float* __restrict__ T = a.target + (size_t)b * H * W;
+  const float* __restrict__ RGB = EDGE ? a.rgb + (size_t)b * 3 * H * W : nullptr;
+  const unsigned flags = a.flags;
+  const float eps = a.eps;
+
+  float gmin = 0.f, ginv = 0.f;
+  if (EDGE) {
+    float gmax;
+    reduce_minmax(a.mm_partials, a.mm_n, gmin, gmax);
+    ginv = gmax - gmin + 1e-6f;  // util.py:70 (divide, not multiply-by-reciprocal, to match rounding)
+  }
+
+  double acc[NMOM];
+#pragma unroll
+  for (int k = 0; k < NMOM; ++k) acc[k] = 0.0;
+
+  const int WV = (W + VEC - 1) / VEC;
+  const int nitems = (r1 > r0) ? (r1 - r0) * WV : 0;
+  for (int it = threadIdx.x; it < nitems; it += TPB) {
+    const int y = r0 + it / WV;
+    const int x0 = (it % WV) * VEC;
+    float pv[VEC + 1], tv[VEC + 1], pd[VEC], td[VEC];
+    const size_t off = (size_t)y * W + x0;
+    if (VEC == 4) {
+      float4 p4 = ldg4(P + off), t4 = ldg4(T + off);
+      pv[0] = p4.x; pv[1] = p4.y; pv[2] = p4.z; pv[3] = p4.w;
+      tv[0] = t4.x; tv[1] = t4.y; tv[2] = t4.z; tv[3] = t4.w;
+    } else {
+      pv[0] = __ldg(P + off);
+      tv[0] = __ldg(T + off);
+    }
+    if (STENCIL) {
+      const bool has_r = x0 + VEC < W;
+      pv[VEC] = has_r ? __ldg(P + off + VEC) : 0.f;
+      tv[VEC] = has_r ? __ldg(T + off + VEC) : 0.f;
+      if (y + 1 < H) {
+        if (VEC == 4) {
+          float4 p4 = ldg4(P + off + W), t4 = ldg4(T + off + W);
+          pd[0] = p4.x; pd[1] = p4.y; pd[2] = p4.z; pd[3] = p4.w;
+          td[0] = t4.x; td[1] = t4.y; td[2] = t4.z; td[3] = t4.w;
+        } else {
+          pd[0] = __ldg(P + off + W);
+          td[0] = __ldg(T + off + W);
+        }
+      }
+    }
+    // fp32 partial sums over the VEC pixels of this item, promoted to fp64 once per item
+    float s1 = 0.f, s2 = 0.f, m0 = 0.f, m1 = 0.f, m2 = 0.f, gx = 0.f, gy = 0.f, ex = 0.f, ey = 0.f, ar = 0.f,
+          ab = 0.f, sq = 0.f, v0 = 0.f, v1 = 0.f, v2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int x = x0 + j;
+      if (VEC == 1 || x < W) {
+        const float p = pv[j], t = tv[j];
+        if (flags & (DP_F_SI | DP_F_SILOG)) {
+          const float d = logf(p + eps) - logf(t + eps);
+          s1 += d;
+          s2 += d * d;
+          if (t > 0.f) { m0 += 1.f; m1 += d; m2 += d * d; }
+        }
+        if (flags & DP_F_ABSREL) ar += fabsf(t - p) / (t + 1e-6f);
+        if (flags & DP_F_M4) {
+          const float e = fabsf(p - t);
+          ab += e;
+          sq += e * e;
+          if (t > 1e-6f) {
+            const float dv = logf(p > 1e-6f ? p : 1e-6f) - logf(t);
+            v0 += 1.f; v1 += dv; v2 += dv * dv;
+          }
+        }
+        if (STENCIL) {
+          float e_x = 0.f, e_y = 0.f;
+          if (x + 1 < W) e_x = fabsf(fabsf(p - pv[j + 1]) - fabsf(t - tv[j + 1]));
+          if (y + 1 < H) e_y = fabsf(fabsf(p - pd[j]) - fabsf(t - td[j]));
+          gx += e_x;
+          gy += e_y;
+          if (EDGE) {
+            const float g = (grad_mag(RGB, H, W, y, x) - gmin) / ginv;
+            ex += g * e_x;
+            ey += g * e_y;
+          }
+        }
+      }
+    }
+    acc[DP_M_S1] += s1; acc[DP_M_S2] += s2; acc[DP_M_M0] += m0; acc[DP_M_M1] += m1; acc[DP_M_M2] += m2;
+    acc[DP_M_GX] += gx; acc[DP_M_GY] += gy; acc[DP_M_EX] += ex; acc[DP_M_EY] += ey; acc[DP_M_AR] += ar;
+    acc[DP_M_AB] += ab; acc[DP_M_SQ] += sq; acc[DP_M_V0] += v0; acc[DP_M_V1] += v1; acc[DP_M_V2] += v2;
+  }
+  __shared__ double red[NMOM * 32];
+  block_sum<NMOM>(acc, red);
+  if (threadIdx.x == 0) {
+    double* o = a.partials + ((size_t)b * a.chunks + blockIdx.x) * NMOM;
+#pragma unroll
+    for (int k = 0; k < NMOM; ++k) o[k] = acc[k];
+  }
+}
+
+__global__ void moments_finalize_kernel(const double* __restrict__ partials, int chunks, double* __restrict__ out) {
+  const int b = blockIdx.x;
+  const int k = threadIdx.x;
+  if (k >= NMOM) return;
+  double s = 0.0;
+  for (int c = 0; c < chunks; ++c) s += partials[((size_t)b * chunks + c) * NMOM + k];
+  out[(size_t)b * NMOM + k] = s;
+}
+
+// ---- combine: moments -> the reference's scalars ------------------------------------------------
+struct LossW {
+  float w_si, w_silog, vf, w_grad, beta;
+  int sqroot;
+};
+
+__global__ void loss_combine_kernel(const double* __restrict__ mom, int B, int H, int W, LossW w, unsigned flags,
+                                    float* __restrict__ out /*[DP_NLOSS]*/, float* __restrict__ per_sample /*[B] or null*/) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double n = (double)H * W;
+  double si = 0.0, M0 = 0.0, M1 = 0.0, M2 = 0.0, GX = 0.0, GY = 0.0, EX = 0.0, EY = 0.0, AR = 0.0;
+  for (int b = 0; b < B; ++b) {
+    const double* m = mom + (size_t)b * NMOM;
+    double v = m[DP_M_S2] / n - (m[DP_M_S1] * m[DP_M_S1]) / (n * n);
+    float vf32 = (float)v;
+    if (w.sqroot) vf32 = sqrtf(vf32);
+    if (per_sample) per_sample[b] = vf32;
+    si += (double)vf32;
+    M0 += m[DP_M_M0]; M1 += m[DP_M_M1]; M2 += m[DP_M_M2];
+    GX += m[DP_M_GX]; GY += m[DP_M_GY]; EX += m[DP_M_EX]; EY += m[DP_M_EY]; AR += m[DP_M_AR];
+  }
+  const float si_loss = (float)(si / B);
+  const double md = M1 / M0;
+  const float silog = (float)(M2 / M0 - (double)w.vf * md * md);
+  const float grad = (float)(GX / ((double)B * H * (W - 1))) + (float)(GY / ((double)B * (H - 1) * W));
+  const float edge_raw = (float)(EX / ((double)B * n)) + (float)(EY / ((double)B * n));
+  const float absrel = (float)(AR / ((double)B * n));
+  const float t_si = si_loss * w.w_si;
+  const float t_silog = (flags & DP_F_SILOG) ? silog * w.w_silog : 0.f;
+  const float t_grad = (flags & DP_F_GRAD) ? grad * w.w_grad : 0.f;
+  const float t_edge = (flags & DP_F_EDGE) ? w.beta * edge_raw : 0.f;
+  out[DP_L_TOTAL] = t_si + t_silog + t_grad + t_edge;
+  out[DP_L_SI] = t_si;
+  out[DP_L_SILOG] = t_silog;
+  out[DP_L_GRAD] = t_grad;
+  out[DP_L_EDGE] = t_edge;
+  out[DP_L_ABSREL] = absrel;
+  out[DP_L_SI_RAW] = si_loss;
+  out[DP_L_SILOG_RAW] = silog;
+}
+
+// ---- backward of combined loss w.r.t. pred --------------------------------------------------------
+struct BwdArgs {
+  const float* pred;
+  const float* target;
+  const float* rgb;
+  const double* mom;       // [B][NMOM]
+  const float* mm_partials;
+  int mm_n;
+  const float* grad_out;   // device scalar (dL/dtotal) or null => 1
+  const float* si_scale;   // per-sample multiplier of the SI term or null
+  float* grad_pred;
+  int B, H, W;
+  unsigned flags;
+  float eps;
+  LossW w;
+};
+
+template <bool STENCIL, bool EDGE>
+__global__ void __launch_bounds__(TPB) loss_bwd_kernel(BwdArgs a) {
+  const int H = a.H, W = a.W, B = a.B;
+  const double n = (double)H * W;
+  float gmin = 0.f, ginv = 1.f;
+  if (EDGE) {
+    float gmax;
+    reduce_minmax(a.mm_partials, a.mm_n, gmin, gmax);
+    ginv = gmax - gmin + 1e-6f;
+  }
+  __shared__ double s_tot[3];
+  if (threadIdx.x == 0) {
+    double M0 = 0, M1 = 0;
+    for (int b = 0; b < B; ++b) { M0 += a.mom[(size_t)b * NMOM + DP_M_M0]; M1 += a.mom[(size_t)b * NMOM + DP_M_M1]; }
+    s_tot[0] = M0; s_tot[1] = M1;
+  }
+  __syncthreads();
+  const double M0 = s_tot[0], M1 = s_tot[1];
+  const float go = a.grad_out ? __ldg(a.grad_out) : 1.f;
+  const size_t total = (size_t)B * H * W;
+  const float inv_nx = (float)(1.0 / ((double)B * H * (W - 1)));
+  const float inv_ny = (float)(1.0 / ((double)B * (H - 1) * W));
+  const float inv_n = (float)(1.0 / ((double)B * n));
+  for (size_t i = (size_t)blockIdx.x * TPB + threadIdx.x; i < total; i += (size_t)gridDim.x * TPB) {
+    const int b = (int)(i / ((size_t)H * W));
+    const int rem = (int)(i - (size_t)b * H * W);
+    const int y = rem / W, x = rem - y * W;
+    const float* P = a.pred + (size_t)b * H * W;
+    const float* T = a.target + (size_t)b * H * W;
+    const float p = __ldg(P + rem), t = __ldg(T + rem);
+    float g = 0.f;
+    if (a.flags & (DP_F_SI | DP_F_SILOG)) {
+      const float d = logf(p + a.eps) - logf(t + a.eps);
+      double gd = 0.0;
+      if ((a.flags & DP_F_SI) && a.w.w_si != 0.f) {
+        const double S1 = a.mom[(size_t)b * NMOM + DP_M_S1];
+        const double sc = a.si_scale ? (double)__ldg(a.si_scale + b) : 1.0;
+        gd += sc * (double)a.w.w_si * (2.0 * d / n - 2.0 * S1 / (n * n)) / B;
+      }
+      if ((a.flags & DP_F_SILOG) && a.w.w_silog != 0.f && t > 0.f)
+        gd += (double)a.w.w_silog * (2.0 * d / M0 - 2.0 * (double)a.w.vf * M1 / (M0 * M0));
+      g += (float)(gd / (double)(p + a.eps));
+    }
+    if (STENCIL) {
+      const float wg = a.w.w_grad, wb = EDGE ? a.w.beta : 0.f;
+      const float* RGB = EDGE ? a.rgb + (size_t)b * 3 * H * W : nullptr;
+      float acc = 0.f;
+      // pair (x, x+1): this pixel is the left element
+      if (x + 1 < W) {
+        const float pr = __ldg(P + rem + 1), tr = __ldg(T + rem + 1);
+        const float e = fabsf(p - pr) - fabsf(t - tr);
+        float wgt = wg * inv_nx;
+        if (EDGE) wgt += wb * inv_n * ((grad_mag(RGB, H, W, y, x) - gmin) / ginv);
+        acc += wgt * sgnf(e) * sgnf(p - pr);
+      }
+      if (x > 0) {  // pair (x-1, x): this pixel is the right element
+        const float pl = __ldg(P + rem - 1), tl = __ldg(T + rem - 1);
+        const float e = fabsf(pl - p) - fabsf(tl - t);
+        float wgt = wg * inv_nx;
+        if (EDGE) wgt += wb * inv_n * ((grad_mag(RGB, H, W, y, x - 1) - gmin) / ginv);
+        acc -= wgt * sgnf(e) * sgnf(pl - p);
+      }
+      if (y + 1 < H) {
+        const float pdn = __ldg(P + rem + W), tdn = __ldg(T + rem + W);
+        const float e = fabsf(p - pdn) - fabsf(t - tdn);
+        float wgt = wg * inv_ny;
+        if (EDGE) wgt += wb * inv_n * ((grad_mag(RGB, H, W, y, x) - gmin) / ginv);
+        acc += wgt * sgnf(e) * sgnf(p - pdn);
+      }
+      if (y > 0) {
+        const float pu = __ldg(P + rem - W), tu = __ldg(T + rem - W);
+        const float e = fabsf(pu - p) - fabsf(tu - t);
+        float wgt = wg * inv_ny;
+        if (EDGE) wgt += wb * inv_n * ((grad_mag(RGB, H, W, y - 1, x) - gmin) / ginv);
+        acc -= wgt * sgnf(e) * sgnf(pu - p);
+      }
+      g += acc;
+    }
+    a.grad_pred[i] = go * g;
+  }
+}
+
+// ---- delta-threshold pixel counts -------------------------------------------------------------------
+struct CntArgs {
+  const float* pred;
+  const float* target;
+  const double* mom;  // S1 per sample (aligned mode)
+  int B, H, W, chunks, nthr, aligned;
+  float eps_div;
+  float thr[DP_MAX_THR];
+  unsigned long long* partials;  // [B][chunks][DP_MAX_THR]
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(TPB) delta_counts_kernel(CntArgs a) {
+  const int b = blockIdx.y;
+  const size_t n = (size_t)a.H * a.W;
+  const float* __restrict__ P = a.pred + (size_t)b * n;
+  const float* __restrict__ T = a.target + (size_t)b * n;
+  float s = 1.f;
+  if (a.aligned) s = expf((float)(-a.mom[(size_t)b * NMOM + DP_M_S1] / (double)n));  // util.py:200
+  const size_t nv = n / VEC;
+  const size_t per = (nv + a.chunks - 1) / a.chunks;
+  const size_t i0 = blockIdx.x * per, i1 = min(nv, i0 + per);
+  unsigned cnt[DP_MAX_THR];
+#pragma unroll
+  for (int k = 0; k < DP_MAX_THR; ++k) cnt[k] = 0;
+  for (size_t i = i0 + threadIdx.x; i < i1; i += TPB) {
+    float pv[VEC], tv[VEC];
+    if (VEC == 4) {
+      float4 p4 = ldg4(P + i * 4), t4 = ldg4(T + i * 4);
+      pv[0] = p4.x; pv[1] = p4.y; pv[2] = p4.z; pv[3] = p4.w;
+      tv[0] = t4.x; tv[1] = t4.y; tv[2] = t4.z; tv[3] = t4.w;
+    } else {
+      pv[0] = __ldg(P + i);
+      tv[0] = __ldg(T + i);
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float al = pv[j] * s;
+      const float r1 = al / (tv[j] + a.eps_div);   // util.py:204 (eps_div = 0) / main.py:318 (1e-6)
+      const float r2 = tv[j] / (al + a.eps_div);
+#pragma unroll
+      for (int k = 0; k < DP_MAX_THR; ++k)
+        if (k < a.nthr && r1 < a.thr[k] && r2 < a.thr[k]) cnt[k]++;   // NaN / inf compare false, as torch.max + lt
+    }
+  }
+  __shared__ unsigned sc[DP_MAX_THR][32];
+#pragma unroll
+  for (int k = 0; k < DP_MAX_THR; ++k) {
+    unsigned v = cnt[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sc[k][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < DP_MAX_THR) {
+    unsigned long long tot = 0;
+    for (int w = 0; w < TPB / 32; ++w) tot += sc[threadIdx.x][w];
+    a.partials[((size_t)b * a.chunks + blockIdx.x) * DP_MAX_THR + threadIdx.x] = tot;
+  }
+}
+
+__global__ void counts_finalize_kernel(const unsigned long long* __restrict__ partials, int chunks, int nthr,
+                                       unsigned long long* __restrict__ counts /*[B][nthr]*/) {
+  const int b = blockIdx.x, k = threadIdx.x;
+  if (k >= nthr) return;
+  unsigned long long s = 0;
+  for (int c = 0; c < chunks; ++c) s += partials[((size_t)b * chunks + c) * DP_MAX_THR + k];
+  counts[(size_t)b * nthr + k] = s;
+}
+
+// evaluation.py:157-166 scalars for one batch from moments + counts
+__global__ void metrics_combine_kernel(const double* __restrict__ mom, const unsigned long long* __restrict__ counts,
+                                       int B, int H, int W, int nthr, float* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double n = (double)H * W;
+  double si = 0.0, ar = 0.0;
+  for (int b = 0; b < B; ++b) {
+    const double* m = mom + (size_t)b * NMOM;
+    const float v = (float)(m[DP_M_S2] / n - (m[DP_M_S1] * m[DP_M_S1]) / (n * n));
+    si += (double)sqrtf(v);
+    ar += m[DP_M_AR];
+  }
+  out[0] = (float)(si / B);
+  out[1] = (float)(ar / ((double)B * n));
+  for (int k = 0; k < nthr; ++k) {
+    double acc = 0.0;
+    for (int b = 0; b < B; ++b) acc += (double)(float)((double)counts[(size_t)b * nthr + k] / n);
+    out[2 + k] = (float)(acc / B);
+  }
+}
+
+inline int pick_chunks(int B, int H) {
+  int c = (4 * kNumSMs + B - 1) / B;
+  if (c < 1) c = 1;
+  if (c > H) c = H;
+  return c;
+}
+constexpr int kMinMaxBlocks = 4 * kNumSMs;
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+size_t dp_depth_moments_workspace(int B, int H, int W) {
+  (void)W;
+  size_t mom = (size_t)B * pick_chunks(B, H) * NMOM * sizeof(double);
+  size_t cnt = (size_t)B * pick_chunks(B, H) * DP_MAX_THR * sizeof(unsigned long long);
+  return (mom > cnt ? mom : cnt) + 256;
+}
+
+size_t dp_rgb_minmax_bytes(void) { return (size_t)kMinMaxBlocks * 2 * sizeof(float); }
+
+int dp_rgb_gradmag_minmax(const float* rgb, int B, int H, int W, float* minmax_partials, cudaStream_t stream) {
+  DP_CHECK_ARG(rgb && minmax_partials && B > 0 && H > 0 && W > 0, "dp_rgb_gradmag_minmax: bad arguments");
+  rgb_minmax_kernel<<<kMinMaxBlocks, TPB, 0, stream>>>(rgb, B, H, W, minmax_partials);
+  DP_CHECK_LAUNCH("rgb_minmax_kernel");
+  return DP_OK;
+}
+
+int dp_depth_moments(const float* pred, const float* target, const float* rgb, const float* minmax_partials,
+                     int B, int H, int W, unsigned flags, float eps, double* moments, void* workspace,
+                     size_t workspace_bytes, cudaStream_t stream) {
+  DP_CHECK_ARG(pred && target && moments && workspace, "dp_depth_moments: null pointer");
+  DP_CHECK_ARG(B > 0 && H > 0 && W > 0, "dp_depth_moments: bad shape %d %d %d", B, H, W);
+  if (flags & DP_F_EDGE) DP_CHECK_ARG(rgb && minmax_partials, "dp_depth_moments: edge term needs rgb + minmax partials");
+  if (workspace_bytes < dp_depth_moments_workspace(B, H, W))
+    return dp_set_error(DP_ERR_WORKSPACE, "dp_depth_moments: workspace %zu < %zu", workspace_bytes,
+                        dp_depth_moments_workspace(B, H, W));
+  MomArgs a;
+  a.pred = pred; a.target = target; a.rgb = rgb; a.B = B; a.H = H; a.W = W;
+  a.chunks = pick_chunks(B, H);
+  a.flags = flags; a.eps = eps; a.mm_partials = minmax_partials; a.mm_n = kMinMaxBlocks;
+  a.partials = reinterpret_cast<double*>(workspace);
+  const bool vec = (W % 4 == 0) && aligned16(pred) && aligned16(target);
+  const bool edge = flags & DP_F_EDGE;
+  const bool stencil = edge || (flags & DP_F_GRAD);
+  dim3 grid(a.chunks, B);
+  if (vec) {
+    if (edge) moments_kernel<4, true, true><<<grid, TPB, 0, stream>>>(a);
+    else if (stencil) moments_kernel<4, true, false><<<grid, TPB, 0, stream>>>(a);
+    else moments_kernel<4, false, false><<<grid, TPB, 0, stream>>>(a);
+  } else {
+    if (edge) moments_kernel<1, true, true><<<grid, TPB, 0, stream>>>(a);
+    else if (stencil) moments_kernel<1, true, false><<<grid, TPB, 0, stream>>>(a);
+    else moments_kernel<1, false, false><<<grid, TPB, 0, stream>>>(a);
+  }
+  DP_CHECK_LAUNCH("moments_kernel");
+  moments_finalize_kernel<<<B, 32, 0, stream>>>(a.partials, a.chunks, moments);
+  DP_CHECK_LAUNCH("moments_finalize_kernel");
+  return DP_OK;
+}
+
+int dp_loss_combine(const double* moments, int B, int H, int W, unsigned flags, float w_si, float w_silog,
+                    float variance_focus, float w_grad, float beta, int sqroot, float* out, float* per_sample,
+                    cudaStream_t stream) {
+  DP_CHECK_ARG(moments && out && B > 0, "dp_loss_combine: bad arguments");
+  LossW w{w_si, w_silog, variance_focus, w_grad, beta, sqroot};
+  loss_combine_kernel<<<1, 32, 0, stream>>>(moments, B, H, W, w, flags, out, per_sample);
+  DP_CHECK_LAUNCH("loss_combine_kernel");
+  return DP_OK;
+}
+
+int dp_loss_backward(const float* pred, const float* target, const float* rgb, const float* minmax_partials,
+                     const double* moments, const float* grad_out, const float* si_sample_scale, int B, int H, int W,
+                     unsigned flags, float eps, float w_si, float w_silog, float variance_focus, float w_grad, float beta, float* grad_pred,
+                     cudaStream_t stream) {
+  DP_CHECK_ARG(pred && target && moments && grad_pred, "dp_loss_backward: null pointer");
+  BwdArgs a;
+  a.pred = pred; a.target = target; a.rgb = rgb; a.mom = moments; a.mm_partials = minmax_partials;
+  a.mm_n = kMinMaxBlocks; a.grad_out = grad_out; a.si_scale = si_sample_scale; a.grad_pred = grad_pred; a.B = B; a.H = H; a.W = W;
+  a.flags = flags; a.eps = eps;
+  a.w = LossW{w_si, w_silog, variance_focus, w_grad, beta, 0};
+  const bool edge = (flags & DP_F_EDGE) && beta != 0.f;
+  const bool stencil = edge || ((flags & DP_F_GRAD) && w_grad != 0.f);
+  if (edge) DP_CHECK_ARG(rgb && minmax_partials, "dp_loss_backward: edge term needs rgb + minmax partials");
+  if (!(flags & DP_F_GRAD)) a.w.w_grad = 0.f;
+  const size_t total = (size_t)B * H * W;
+  int blocks = (int)((total + TPB - 1) / TPB);
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  if (edge) loss_bwd_kernel<true, true><<<blocks, TPB, 0, stream>>>(a);
+  else if (stencil) loss_bwd_kernel<true, false><<<blocks, TPB, 0, stream>>>(a);
+  else loss_bwd_kernel<false, false><<<blocks, TPB, 0, stream>>>(a);
+  DP_CHECK_LAUNCH("loss_bwd_kernel");
+  return DP_OK;
+}
+
+int dp_delta_counts(const float* pred, const float* target, const double* moments, int B, int H, int W,
+                    const float* thresholds, int nthr, int aligned, float eps_div, unsigned long long* counts,
+                    void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  DP_CHECK_ARG(pred && target && counts && workspace && thresholds, "dp_delta_counts: null pointer");
+  DP_CHECK_ARG(nthr >= 1 && nthr <= DP_MAX_THR, "dp_delta_counts: nthr %d out of [1,%d]", nthr, DP_MAX_THR);
+  DP_CHECK_ARG(!aligned || moments, "dp_delta_counts: aligned mode needs moments");
+  if (workspace_bytes < dp_depth_moments_workspace(B, H, W))
+    return dp_set_error(DP_ERR_WORKSPACE, "dp_delta_counts: workspace too small");
+  CntArgs a;
+  a.pred = pred; a.target = target; a.mom = moments; a.B = B; a.H = H; a.W = W;
+  a.chunks = pick_chunks(B, H);
+  a.nthr = nthr; a.aligned = aligned; a.eps_div = eps_div;
+  for (int k = 0; k < DP_MAX_THR; ++k) a.thr[k] = k < nthr ? thresholds[k] : 0.f;
+  a.partials = reinterpret_cast<unsigned long long*>(workspace);
+  dim3 grid(a.chunks, B);
+  const bool vec = (((size_t)H * W) % 4 == 0) && aligned16(pred) && aligned16(target);
+  if (vec) delta_counts_kernel<4><<<grid, TPB, 0, stream>>>(a);
+  else delta_counts_kernel<1><<<grid, TPB, 0, stream>>>(a);
+  DP_CHECK_LAUNCH("delta_counts_kernel");
+  counts_finalize_kernel<<<B, 32, 0, stream>>>(a.partials, a.chunks, nthr, counts);
+  DP_CHECK_LAUNCH("counts_finalize_kernel");
+  return DP_OK;
+}
+
+int dp_metrics_combine(const double* moments, const unsigned long long* counts, int B, int H, int W, int nthr,
+                       float* out, cudaStream_t stream) {
+  DP_CHECK_ARG(moments && counts && out, "dp_metrics_combine: null pointer");
+  metrics_combine_kernel<<<1, 32, 0, stream>>>(moments, counts, B, H, W, nthr, out);
+  DP_CHECK_LAUNCH("metrics_combine_kernel");
+  return DP_OK;
+}
+
+}  // extern "C"

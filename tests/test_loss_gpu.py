@@ -1,0 +1,136 @@
+"""GPU parity of the fused loss / metric kernels (through the C ABI) against the oracle and the
+golden values computed by the reference's own util.py.  Tolerance: 1e-5 relative in fp32 (north star);
+delta pixel counts within 0.01 % of pixels."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fixtures as fx, losses as ol
+from oracle.make_golden import loss_cases, THRESH
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REL = 1e-5
+
+
+def _close(a, b, rel=REL, abs_=1e-7):
+    a, b = float(a), float(b)
+    if np.isnan(b):
+        return np.isnan(a)
+    return abs(a - b) <= rel * abs(b) + abs_
+
+
+@pytest.mark.parametrize("name", ["survey", "bench_like", "small_zeros", "tiny"])
+def test_forward_values_vs_reference_golden(pkg, golden_loss, name):
+    p, t, rgb = loss_cases()[name]()
+    pc, tc, rc = p.cuda(), t.cuda(), rgb.cuda()
+    exp = golden_loss[name]["fp32"]
+    exp64 = golden_loss[name]["fp64"]
+    got = {
+        "si": pkg.scale_invariant_loss(pc, tc).item(),
+        "si_sqrt": pkg.scale_invariant_loss(pc, tc, sqroot=True).item(),
+        "silog": pkg.silog_loss(pc, tc, mask=(tc > 0)).item(),
+        "grad": pkg.gradient_loss(pc, tc).item(),
+        "edge": pkg.edge_aware_loss(pc, tc, rc, 0.5).item(),
+        "absrel": pkg.absolute_relative_error(pc, tc).item(),
+    }
+    for i, th in enumerate(THRESH):
+        got[f"delta{i}"] = pkg.delta_thres(pc, tc, thres=th).item()
+    for k in exp:
+        # fp32 reference value, or the fp64 evaluation of the same formula: we must be within 1e-5 of the reference
+        assert _close(got[k], exp[k]) or _close(got[k], exp64[k]), (name, k, got[k], exp[k], exp64[k])
+    # integer counts: within 0.01 % of pixels per sample
+    cnt = pkg.delta_counts(pc, tc, THRESH).cpu().numpy()
+    ref = np.array(golden_loss[name]["delta_counts"])
+    npx = p[0].numel()
+    assert np.abs(cnt - ref).max() <= max(1, int(1e-4 * npx)), (cnt, ref)
+
+
+@pytest.mark.parametrize("name", ["small_zeros", "tiny"])
+def test_gradients_vs_reference_stored(pkg, name):
+    z = np.load(os.path.join(ROOT, "tests", "golden", "loss_small_inputs.npz"))
+    p, t, rgb = (torch.from_numpy(z[f"{name}.{k}"]).cuda() for k in ("pred", "target", "rgb"))
+    fns = {"si": lambda q: pkg.scale_invariant_loss(q, t), "silog": lambda q: pkg.silog_loss(q, t, mask=(t > 0)),
+           "grad": lambda q: pkg.gradient_loss(q, t), "edge": lambda q: pkg.edge_aware_loss(q, t, rgb, 0.5)}
+    for k, fn in fns.items():
+        q = p.clone().requires_grad_(True)
+        fn(q).backward()
+        ref = torch.from_numpy(z[f"{name}.grad_{k}"]).cuda()
+        scale = float(ref.abs().max())
+        assert float((q.grad - ref).abs().max()) <= 2e-5 * scale + 1e-9, (name, k)
+
+
+def test_gradients_vs_oracle_full_size(pkg):
+    p, t, rgb = loss_cases()["bench_like"]()
+    cfg = fx.loss_config(si=1.0, silog=1.0, vf=0.85, grad=0.2, edge=0.5)
+    q = p.clone().requires_grad_(True)
+    tot, d = ol.combined_loss(q, t, cfg, rgb=rgb)
+    tot.backward()
+    qc = p.cuda().requires_grad_(True)
+    totc, dc = pkg.combined_loss(qc, t.cuda(), cfg, rgb=rgb.cuda())
+    (totc * 1.0).backward()
+    assert _close(totc.item(), tot.item())
+    for k in d:
+        assert _close(dc[k], d[k]), (k, dc[k], d[k])
+    ref = q.grad
+    err = (qc.grad.cpu() - ref).abs()
+    # sign() terms of the stencil losses flip only where |a|-|b| is within rounding of 0: allow a vanishing fraction
+    tol = 2e-5 * ref.abs() + 1e-5 * float(ref.abs().mean())
+    assert float((err > tol).float().mean()) < 1e-5
+    cfg0 = fx.loss_config()           # config.yaml defaults 1/0/0/0
+    totc0, dc0 = pkg.combined_loss(p.cuda(), t.cuda(), cfg0, rgb=rgb.cuda())
+    tot0, d0 = ol.combined_loss(p, t, cfg0, rgb=rgb)
+    assert _close(totc0.item(), tot0.item()) and dc0["silog_loss"] == 0.0 and dc0["edge_loss"] == 0.0
+
+
+def test_evaluation_metrics_fused(pkg):
+    """the fused evaluation.py metric set equals the five separate reference calls."""
+    p, t, _ = loss_cases()["bench_like"]()
+    out = pkg.evaluation_metrics(p.cuda(), t.cuda(), thresholds=[1.05, 1.05 ** 2, 1.05 ** 3]).cpu()
+    exp = [ol.scale_invariant_loss(p, t, sqroot=True), ol.absolute_relative_error(p, t)] + \
+          [ol.delta_thres(p, t, 1.05 ** j) for j in (1, 2, 3)]
+    for a, b in zip(out.tolist(), exp):
+        assert _close(a, b.item(), rel=1e-5, abs_=2e-6)
+
+
+def test_evaluate_model_metric_set(pkg, golden_loss):
+    """main.evaluate_model sums (MAE/RMSE/REL/siRMSE/unaligned delta<1.25^k)."""
+    p, t, _ = loss_cases()["small_zeros"]()
+    got = pkg.evaluate_model_sums(p.cuda(), t.cuda())
+    exp = ol.evaluate_metric_sums(p, t)
+    for k in ("abs", "sq", "rel", "sirmse"):
+        assert _close(got[k], exp[k], rel=2e-5), (k, got[k], exp[k])
+    for k in ("d1", "d2", "d3"):
+        assert abs(got[k] - exp[k]) <= 1
+
+
+def test_properties_full_size(pkg):
+    """size-independent properties at bench size (B=32, 448x576): scale invariance of SI and of aligned delta,
+    SI(p,p)=0, delta(p,p)=1, sample-permutation invariance."""
+    g = torch.Generator(device="cuda").manual_seed(7)
+    B, H, W = 32, 448, 576
+    t = torch.rand(B, 1, H, W, device="cuda", generator=g) * 9.9 + 0.1
+    p = t * torch.exp(0.2 * torch.randn(B, 1, H, W, device="cuda", generator=g))
+    si = pkg.scale_invariant_loss(p, t).item()
+    si_scaled = pkg.scale_invariant_loss(p * 3.7, t).item()
+    assert abs(si - si_scaled) <= 2e-4 * abs(si)          # eps=1e-6 breaks exact invariance only slightly
+    assert abs(pkg.scale_invariant_loss(p, p).item()) < 1e-7
+    assert pkg.delta_thres(p, p, thres=1.05).item() == 1.0
+    d = pkg.delta_thres(p, t, thres=1.25).item()
+    d_scaled = pkg.delta_thres(p * 0.31, t, thres=1.25).item()
+    assert abs(d - d_scaled) < 1e-4
+    perm = torch.randperm(B, device="cuda")
+    assert abs(pkg.scale_invariant_loss(p[perm], t[perm]).item() - si) <= 1e-6 * abs(si)
+    # analytic check: d ~ N(0, 0.2^2) so SI ~ 0.04
+    assert abs(si - 0.04) < 1e-3
+
+
+def test_shape_assert(pkg):
+    a = torch.rand(2, 1, 8, 8, device="cuda")
+    b = torch.rand(2, 1, 8, 9, device="cuda")
+    with pytest.raises(AssertionError):
+        pkg.scale_invariant_loss(a, b)
+    with pytest.raises(AssertionError):
+        pkg.delta_thres(a, b)

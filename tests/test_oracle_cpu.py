@@ -1,0 +1,108 @@
+"""CPU suite: the oracle against the golden vectors produced from the real reference
+(oracle/make_golden.py), and the C-ABI surface of the built library."""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+from oracle import cases, fixtures as fx, losses as ol          # noqa: E402
+from oracle.make_golden import loss_cases, THRESH, eval_all    # noqa: E402
+
+
+@pytest.mark.parametrize("name", ["survey", "bench_like", "small_zeros", "tiny"])
+def test_oracle_losses_match_reference_golden(golden_loss, name):
+    p, t, rgb = loss_cases()[name]()
+    got = eval_all(ol, p, t, rgb)
+    exp = golden_loss[name]["fp32"]
+    for k, v in exp.items():
+        assert got[k] == pytest.approx(v, rel=1e-6, abs=1e-9), (name, k)
+    cnt = ol.delta_counts(p, t, THRESH).tolist()
+    assert cnt == golden_loss[name]["delta_counts"]
+
+
+def test_survey_known_answers(golden_loss):
+    """the values SURVEY.md section 8c lists, computed by the reference's util.py."""
+    g = golden_loss["survey"]["fp32"]
+    assert g["si"] == pytest.approx(0.982784748, rel=2e-6)
+    assert g["si_sqrt"] == pytest.approx(0.991354585, rel=2e-6)
+    assert g["silog"] == pytest.approx(0.982787371, rel=2e-6)
+    assert g["grad"] == pytest.approx(4.79985094, rel=2e-6)
+    assert g["edge"] == pytest.approx(1.06726217, rel=2e-6)
+    assert g["absrel"] == pytest.approx(1.08991563, rel=2e-6)
+    assert g["delta0"] == pytest.approx(0.0532449372, rel=2e-6)
+    assert g["delta3"] == pytest.approx(0.222841293, rel=2e-6)
+
+
+def test_small_stored_inputs_roundtrip(golden_loss):
+    z = np.load(os.path.join(ROOT, "tests", "golden", "loss_small_inputs.npz"))
+    p, t, rgb = (torch.from_numpy(z[f"small_zeros.{k}"]) for k in ("pred", "target", "rgb"))
+    got = eval_all(ol, p, t, rgb)
+    for k, v in golden_loss["small_zeros"]["fp32"].items():
+        assert got[k] == pytest.approx(v, rel=1e-6, abs=1e-9)
+
+
+@pytest.mark.parametrize("name", ["rcu64", "fusion128_expand", "resblock_64_32", "xattn_multi", "dinohead"])
+def test_oracle_modules_match_reference_golden(name):
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "model_golden.npz"))
+    kind, kw, shapes, fkw = cases.CASES[name]
+    m = fx.fill_deterministic(cases.build_oracle(kind, kw))
+    res = cases.run_case(m, name)
+    for k, v in res.items():
+        ref = torch.from_numpy(gold[f"{name}/{k}"])
+        got = fx.subsample(v)
+        scale = max(float(ref.abs().max()), 1e-6)
+        assert float((got - ref).abs().max()) / scale < 1e-4, (name, k)
+
+
+def test_cross_attention_last_writer_identity():
+    """The closed form the CUDA kernel uses: token i attends over the key range of the LAST window containing i."""
+    from oracle.model import CrossAttention
+    hr, wr, ws = 20, 24, 16
+    rng = CrossAttention.window_ranges(hr, wr, ws)
+    owner = np.full(hr * wr, -1)
+    for wi, (lo, hi) in enumerate(rng):
+        owner[lo:hi] = wi
+    assert (owner >= 0).all()
+    # default geometry (56x72): SURVEY section 8 A9 owner histogram
+    rng = CrossAttention.window_ranges(56, 72, 16)
+    owner = np.full(56 * 72, -1)
+    for wi, (lo, hi) in enumerate(rng):
+        owner[lo:hi] = wi
+    hist = np.bincount(owner, minlength=20)
+    assert hist.tolist() == [16, 16, 16, 16, 1088] * 3 + [16, 16, 16, 16, 512]
+    total_scores = sum(hist[w] * (rng[w][1] - rng[w][0]) for w in range(20))
+    assert total_scores < 4.4e6
+
+
+def test_library_exports_every_declared_symbol():
+    """every function include/depth_b200.h declares is exported by the built .so (no compute calls)."""
+    import depth_b200
+    hdr = open(os.path.join(ROOT, "include", "depth_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(dp_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 10
+    lib = ctypes.CDLL(depth_b200._lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    assert lib.dp_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    import depth_b200
+    p = torch.rand(1, 1, 4, 4) + 0.5
+    with pytest.raises(depth_b200._lib.DepthB200Error):
+        depth_b200.scale_invariant_loss(p, p)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "monocular-depth-estimation-cil_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+\.*oracle", src, re.M), f"{f} imports the oracle"
+                assert "oracle/" not in src and "oracle." not in src, f"{f} references the oracle"
