@@ -113,6 +113,36 @@ int dp_delta_counts(const float* pred, const float* target, const double* moment
 int dp_metrics_combine(const double* moments, const unsigned long long* counts, int B, int H, int W, int nthr,
                        float* out, cudaStream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Convolutions (NHWC bf16 activations, fp32 accumulation in TMEM)
+ * ---------------------------------------------------------------------------------------------- */
+/* 3x3/stride 1/pad 1 or 1x1 convolution as an implicit GEMM on tcgen05 tensor cores.
+ * Replaces nn.Conv2d forward at blocks.py:149-161,335-341,401; midas_net_custom.py:106-110;
+ * midas_semantics.py:132-143,195; dpt_depth.py:39-47,103-106 - and, called with the transposed+flipped
+ * weight pack, the data gradient autograd derives for them.
+ *   x         NHWC bf16, pixel stride x_ld elements (a channel slice of a wider buffer is fine)
+ *   w_packed  bf16 [KS*KS][Cout][Cin_p]  (tap = r*KS+s; Cin_p >= Cin, zero padded)
+ *   epilogue  y = acc (+ bias[c]) (+ residual[pixel][c]);  out  = relu ? max(y,0) : y   (may be NULL)
+ *                                                          out2 = relu2 ? max(y,0) : y  (may be NULL)
+ *   stats_partials  NULL or float[dp_conv2d_tc_grid()][2][Cout]: per-CTA sum / sum of squares of y over pixels
+ *                   (train-mode BatchNorm statistics, midas_semantics.py:133,136,142,196) */
+int dp_conv2d_tc_grid(int B, int H, int W, int Cin, int Cout, int KS);
+int dp_conv2d_tc(const void* x, long long x_ld, int B, int H, int W, int Cin, const void* w_packed, int Cin_p,
+                 int Cout, int KS, const float* bias, const void* residual, long long res_ld, int relu, void* out,
+                 long long out_ld, void* out2, long long out2_ld, int relu2, float* stats_partials,
+                 cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Diagnostics
+ * ---------------------------------------------------------------------------------------------- */
+/* One CTA, one tcgen05.mma chain with host-specified shared-memory descriptors; dumps TMEM lanes 0..127 x
+ * ncols_dump fp32 columns to `out`.  A / B are row-major bf16 matrices loaded by TMA in boxes of
+ * (box_rows x box_cols), boxes laid out consecutively along the column axis.  adesc / bdesc are HOST arrays
+ * {lbo_bytes, sbo_bytes, layout_type, k_advance_bytes, start_offset_bytes}.  Test-only (tests/test_umma_probe_gpu.py). */
+int dp_umma_probe(const void* A, int a_rows, int a_cols, int a_box_rows, int a_box_cols, const void* B, int b_rows,
+                  int b_cols, int b_box_rows, int b_box_cols, int M, int N, int nk, int a_mn_major, int b_mn_major,
+                  const uint32_t* adesc, const uint32_t* bdesc, float* out, int ncols_dump, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

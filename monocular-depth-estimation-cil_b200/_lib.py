@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libdepth_b200.so")
 
 c_int, c_uint, c_float, c_size_t, c_void_p, c_u64 = (ctypes.c_int, ctypes.c_uint, ctypes.c_float, ctypes.c_size_t,
                                                       ctypes.c_void_p, ctypes.c_uint64)
+c_ll = ctypes.c_longlong
 
 
 class DepthB200Error(RuntimeError):
@@ -63,6 +64,11 @@ class _Sig:
     dp_delta_counts = (c_int, [P, P, P, c_int, c_int, c_int, ctypes.POINTER(c_float), c_int, c_int, c_float, P, P,
                                c_size_t, P])
     dp_metrics_combine = (c_int, [P, P, c_int, c_int, c_int, c_int, P, P])
+    dp_conv2d_tc_grid = (c_int, [c_int, c_int, c_int, c_int, c_int, c_int])
+    dp_conv2d_tc = (c_int, [P, c_ll, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, P, P, c_ll, c_int, P, c_ll, P,
+                            c_ll, c_int, P, P])
+    dp_umma_probe = (c_int, [P, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                             c_int, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32), P, c_int, P])
 
 
 def check(code):
