@@ -132,6 +132,14 @@ int dp_conv2d_tc(const void* x, long long x_ld, int B, int H, int W, int Cin, co
                  long long out_ld, void* out2, long long out2_ld, int relu2, float* stats_partials,
                  cudaStream_t stream);
 
+/* Weight gradient of the same convolutions (autograd's convolution_backward w.r.t. weight), tcgen05 GEMM over
+ * pixels with split-K partials reduced deterministically.  x, dy: NHWC bf16; grad_oihw: fp32 [Cout][Cin][KS][KS]
+ * (overwritten, or added to when accumulate != 0). */
+size_t dp_conv2d_wgrad_tc_workspace(int B, int H, int W, int Cin, int Cout, int KS);
+int dp_conv2d_wgrad_tc(const void* x, long long x_ld, const void* dy, long long dy_ld, int B, int H, int W, int Cin,
+                       int Cout, int KS, float* grad_oihw, int accumulate, void* workspace, size_t workspace_bytes,
+                       cudaStream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Diagnostics
  * ---------------------------------------------------------------------------------------------- */

@@ -67,6 +67,8 @@ class _Sig:
     dp_conv2d_tc_grid = (c_int, [c_int, c_int, c_int, c_int, c_int, c_int])
     dp_conv2d_tc = (c_int, [P, c_ll, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, P, P, c_ll, c_int, P, c_ll, P,
                             c_ll, c_int, P, P])
+    dp_conv2d_wgrad_tc_workspace = (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int])
+    dp_conv2d_wgrad_tc = (c_int, [P, c_ll, P, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_size_t, P])
     dp_umma_probe = (c_int, [P, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                              c_int, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32), P, c_int, P])
 

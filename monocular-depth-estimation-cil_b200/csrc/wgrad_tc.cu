@@ -1,0 +1,256 @@
+// Weight gradient of the 3x3/s1/p1 and 1x1 convolutions on tcgen05 tensor cores.
+//
+// dW[tap][co][ci] = sum over pixels p of dY[p][co] * X[p + tap][ci]   (what autograd's
+// convolution_backward computes for the nn.Conv2d layers listed in conv_tc.cu).
+//
+// GEMM view: M = co, N = ci, K = pixels.  Both operands are NHWC, i.e. "MN-major" (the contracted
+// pixel index is the strided one), which UMMA consumes directly from 128B/64B/32B-swizzled TMA boxes
+// (tests/test_umma_probe_gpu.py pins the MN-major descriptor conventions).  One CTA owns one
+// horizontal tap s, one block of output channels and one <=64-wide chunk of input channels; it
+// walks its share of the 128-pixel patches, issuing for each patch 3 (vertical taps) x 8 (K=16
+// pixel slices) UMMAs into three TMEM accumulators that share the dY tile and read the same X halo
+// box at r*tw rows offset.  Split-K partials go to a workspace and are reduced deterministically
+// (no atomics) by wgrad_reduce_kernel, which also un-packs to the OIHW fp32 layout of param.grad.
+#include "common.cuh"
+#include "tc.cuh"
+#include "../../include/depth_b200.h"
+
+namespace {
+
+constexpr int kThreads = 192;  // warp 0 producer, warp 1 MMA (+TMEM alloc), warps 2..5 epilogue
+constexpr int kMaxStages = 8;
+
+struct WgArgs {
+  int B, H, W, Cout, Cin, KS, pad;
+  int th, tw, tiles_y, tiles_x;
+  int MC, m_chunks, M, co_blocks;   // M chunk width (<=64 channels), chunks per UMMA, UMMA M, blocks over Cout
+  int NC, ci_chunks;                // N chunk width (<=64 channels), chunks over Cin
+  int psplit, stages;
+  long long tiles_total;
+  uint32_t a_box_bytes, a_slot_bytes, x_box_bytes, x_slot_bytes, stage_bytes;
+  uint32_t rowA, rowB, layoutA, layoutB, idesc, a_lbo;
+  float* partial;  // [psplit][KS*KS][Cout][Cin]
+};
+
+struct __align__(8) WgBars {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t done;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const WgArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  WgBars* bars = reinterpret_cast<WgBars*>(smem + (size_t)a.stages * a.stage_bytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int id = blockIdx.x;
+  const int ps = id % a.psplit; id /= a.psplit;
+  const int cc = id % a.ci_chunks; id /= a.ci_chunks;
+  const int cb = id % a.co_blocks; id /= a.co_blocks;
+  const int s = id;  // horizontal tap
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < a.stages; ++i) { tc::mbar_init(&bars->full[i], 1); tc::mbar_init(&bars->empty[i], 1); }
+    tc::mbar_init(&bars->done, 1);
+    tc::fence_barrier_init();
+    tc::prefetch_tmap(&tmDY);
+    tc::prefetch_tmap(&tmX);
+  }
+  if (warp == 1) tc::tmem_alloc(&bars->tmem_base, 256);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = bars->tmem_base;
+  const int real_chunks = a.MC < 64 ? 1 : a.m_chunks;  // chunks actually loaded (narrow layers alias chunk 0)
+
+  if (warp == 0 && lane == 0) {
+    uint32_t stage = 0, phase = 0;
+    for (long long t = ps; t < a.tiles_total; t += a.psplit) {
+      long long m = t;
+      const int tx = (int)(m % a.tiles_x); m /= a.tiles_x;
+      const int ty = (int)(m % a.tiles_y);
+      const int n = (int)(m / a.tiles_y);
+      const int y0 = ty * a.th, x0 = tx * a.tw;
+      tc::mbar_wait(&bars->empty[stage], phase ^ 1);
+      uint8_t* sA = smem + (size_t)stage * a.stage_bytes;
+      uint8_t* sX = sA + (size_t)real_chunks * a.a_slot_bytes;
+      tc::mbar_expect_tx(&bars->full[stage], (uint32_t)real_chunks * a.a_box_bytes + a.x_box_bytes);
+      for (int j = 0; j < real_chunks; ++j)
+        tc::tma_load_4d(sA + (size_t)j * a.a_slot_bytes, &tmDY, &bars->full[stage], cb * a.M + j * a.MC, x0, y0, n);
+      tc::tma_load_4d(sX, &tmX, &bars->full[stage], cc * a.NC, x0 + s - a.pad, y0 - a.pad, n);
+      if (++stage == (uint32_t)a.stages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1 && lane == 0) {
+    uint32_t stage = 0, phase = 0;
+    uint32_t accumulate = 0;
+    for (long long t = ps; t < a.tiles_total; t += a.psplit) {
+      tc::mbar_wait(&bars->full[stage], phase);
+      tc::fence_after_sync();
+      const uint32_t a_base = tc::smem_u32(smem + (size_t)stage * a.stage_bytes);
+      const uint32_t x_base = a_base + (uint32_t)real_chunks * a.a_slot_bytes;
+      for (int r = 0; r < a.KS; ++r) {
+#pragma unroll 1
+        for (int k16 = 0; k16 < 8; ++k16) {
+          const uint64_t da = tc::make_smem_desc(a_base + (uint32_t)(k16 * 16) * a.rowA, a.a_lbo, 8 * a.rowA, a.layoutA);
+          const uint64_t db = tc::make_smem_desc(x_base + (uint32_t)(r * a.tw + k16 * 16) * a.rowB, 0, 8 * a.rowB,
+                                                 a.layoutB);
+          tc::umma_bf16(tmem + (uint32_t)(r * a.NC), da, db, a.idesc, (accumulate | (uint32_t)(k16 > 0)));
+        }
+      }
+      accumulate = 1;
+      tc::umma_commit(&bars->empty[stage]);
+      if (++stage == (uint32_t)a.stages) { stage = 0; phase ^= 1; }
+    }
+    tc::umma_commit(&bars->done);
+  } else if (warp >= 2) {
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    tc::mbar_wait(&bars->done, 0);
+    tc::fence_after_sync();
+    // accumulator row -> TMEM lane: M=128: lane = row; M=64: lane = (row/16)*32 + row%16
+    int row = -1;
+    if (a.M == 128) row = q * 32 + lane;
+    else if (lane < 16) row = q * 16 + lane;
+    const int co = cb * a.M + row;
+    const bool row_ok = row >= 0 && row < (a.MC < 64 ? a.MC : a.M) && co < a.Cout;
+    const bool has_work = ps < a.tiles_total;  // a split with no tiles left its TMEM untouched: write zeros
+    for (int r = 0; r < a.KS; ++r) {
+      const int tap = r * a.KS + s;
+      for (int c0 = 0; c0 < a.NC; c0 += 16) {
+        float v[16];
+        tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * a.NC + c0), v);
+        if (row_ok) {
+          float* dst = a.partial + (((size_t)ps * a.KS * a.KS + tap) * a.Cout + co) * a.Cin + cc * a.NC + c0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (cc * a.NC + c0 + j < a.Cin) dst[j] = has_work ? v[j] : 0.f;
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem, 256);
+}
+
+// sum the split-K partials and write OIHW fp32: grad[co][ci][r][s] (+)= sum_ps partial[ps][tap][co][ci]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int psplit, int taps, int Cout, int Cin,
+                                    float* __restrict__ grad, int accumulate) {
+  const long long total = (long long)taps * Cout * Cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int p = 0; p < psplit; ++p) s += partial[(size_t)p * total + i];
+    const int ci = (int)(i % Cin);
+    const int co = (int)((i / Cin) % Cout);
+    const int tap = (int)(i / ((long long)Cin * Cout));
+    const size_t o = ((size_t)co * Cin + ci) * taps + tap;
+    grad[o] = accumulate ? grad[o] + s : s;
+  }
+}
+
+struct WgPlan {
+  WgArgs a;
+  size_t smem;
+  int grid;
+};
+
+int wg_plan(WgPlan& p, int B, int H, int W, int Cin, int Cout, int KS) {
+  WgArgs& a = p.a;
+  a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.KS = KS; a.pad = KS / 2;
+  const int cand[5][2] = {{8, 16}, {16, 8}, {4, 32}, {2, 64}, {1, 128}};
+  long long best = -1;
+  for (int i = 0; i < 5; ++i) {
+    long long t = (long long)dp::ceil_div(H, cand[i][0]) * dp::ceil_div(W, cand[i][1]);
+    if (best < 0 || t < best) { best = t; a.th = cand[i][0]; a.tw = cand[i][1]; }
+  }
+  a.tiles_y = dp::ceil_div(H, a.th);
+  a.tiles_x = dp::ceil_div(W, a.tw);
+  a.tiles_total = (long long)B * a.tiles_y * a.tiles_x;
+  a.MC = Cout >= 64 ? 64 : (Cout > 16 ? 32 : 16);
+  a.M = Cout > 64 ? 128 : 64;
+  a.m_chunks = a.M / a.MC;
+  a.co_blocks = dp::ceil_div(Cout, a.M);
+  a.NC = Cin >= 64 ? 64 : (Cin > 16 ? 32 : 16);
+  a.ci_chunks = dp::ceil_div(Cin, a.NC);
+  a.rowA = a.MC * 2; a.rowB = a.NC * 2;
+  a.layoutA = tc::swizzle_for_row_bytes(a.rowA);
+  a.layoutB = tc::swizzle_for_row_bytes(a.rowB);
+  a.idesc = tc::make_idesc_bf16(a.M, a.NC, 1, 1);
+  a.a_box_bytes = 128u * a.rowA;
+  a.a_slot_bytes = (a.a_box_bytes + 1023u) & ~1023u;
+  a.x_box_bytes = (uint32_t)((a.th + 2 * a.pad) * a.tw) * a.rowB;
+  a.x_slot_bytes = (a.x_box_bytes + 1023u) & ~1023u;
+  const int real_chunks = a.MC < 64 ? 1 : a.m_chunks;
+  a.a_lbo = a.MC < 64 ? 0u : a.a_slot_bytes;
+  a.stage_bytes = real_chunks * a.a_slot_bytes + a.x_slot_bytes;
+  const int base_ctas = KS * a.co_blocks * a.ci_chunks;
+  int ps = (2 * dp::kNumSMs + base_ctas - 1) / base_ctas;
+  if (ps > a.tiles_total) ps = (int)a.tiles_total;
+  if (ps < 1) ps = 1;
+  if (ps > 64) ps = 64;
+  a.psplit = ps;
+  long long per = (a.tiles_total + ps - 1) / ps;
+  int st = (int)((200 * 1024) / a.stage_bytes);
+  if (st > kMaxStages) st = kMaxStages;
+  if (st > per) st = (int)per;
+  if (st < 1) st = 1;
+  a.stages = st;
+  p.smem = 1024 + (size_t)st * a.stage_bytes + sizeof(WgBars) + 64;
+  p.grid = base_ctas * ps;
+  return DP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t dp_conv2d_wgrad_tc_workspace(int B, int H, int W, int Cin, int Cout, int KS) {
+  WgPlan p;
+  wg_plan(p, B, H, W, Cin, Cout, KS);
+  return (size_t)p.a.psplit * KS * KS * Cout * Cin * sizeof(float);
+}
+
+int dp_conv2d_wgrad_tc(const void* x, long long x_ld, const void* dy, long long dy_ld, int B, int H, int W, int Cin,
+                       int Cout, int KS, float* grad_oihw, int accumulate, void* workspace, size_t workspace_bytes,
+                       cudaStream_t stream) {
+  DP_CHECK_ARG(x && dy && grad_oihw && workspace, "dp_conv2d_wgrad_tc: null pointer");
+  DP_CHECK_ARG(KS == 3 || KS == 1, "dp_conv2d_wgrad_tc: kernel size %d", KS);
+  DP_CHECK_ARG(Cin % 8 == 0 && Cout % 8 == 0 && x_ld % 8 == 0 && dy_ld % 8 == 0,
+               "dp_conv2d_wgrad_tc: channels / strides must be multiples of 8");
+  WgPlan p;
+  wg_plan(p, B, H, W, Cin, Cout, KS);
+  WgArgs& a = p.a;
+  const size_t need = (size_t)a.psplit * KS * KS * Cout * Cin * sizeof(float);
+  if (workspace_bytes < need) return dp_set_error(DP_ERR_WORKSPACE, "dp_conv2d_wgrad_tc: workspace %zu < %zu",
+                                                  workspace_bytes, need);
+  a.partial = reinterpret_cast<float*>(workspace);
+  CUtensorMap tmDY, tmX;
+  {
+    uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)dy_ld * 2, (uint64_t)W * dy_ld * 2, (uint64_t)H * W * dy_ld * 2};
+    uint32_t box[4] = {(uint32_t)a.MC, (uint32_t)a.tw, (uint32_t)a.th, 1};
+    int rc = dp_make_tmap_bf16(&tmDY, dy, 4, dims, str, box, nullptr, a.rowA);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)x_ld * 2, (uint64_t)W * x_ld * 2, (uint64_t)H * W * x_ld * 2};
+    uint32_t box[4] = {(uint32_t)a.NC, (uint32_t)a.tw, (uint32_t)(a.th + 2 * a.pad), 1};
+    int rc = dp_make_tmap_bf16(&tmX, x, 4, dims, str, box, nullptr, a.rowB);
+    if (rc) return rc;
+  }
+  cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+  if (e != cudaSuccess) return dp_set_error(DP_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  wgrad_tc_kernel<<<p.grid, kThreads, p.smem, stream>>>(tmDY, tmX, a);
+  DP_CHECK_LAUNCH("wgrad_tc_kernel");
+  const long long total = (long long)KS * KS * Cout * Cin;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4 * dp::kNumSMs) blocks = 4 * dp::kNumSMs;
+  wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(a.partial, a.psplit, KS * KS, Cout, Cin, grad_oihw, accumulate);
+  DP_CHECK_LAUNCH("wgrad_reduce_kernel");
+  return DP_OK;
+}
+
+}  // extern "C"

@@ -114,3 +114,33 @@ def test_conv_full_resolution_persistent(pkg):
     # linearity (size-independent property): conv(2x) == 2 conv(x) exactly in bf16
     out2, _, _ = run_conv(pkg, (x.float() * 2).to(torch.bfloat16), pack_w(w), Cout, 3)
     assert torch.equal(out2.float(), out.float() * 2)
+
+
+WG_CASES = [
+    (2, 16, 32, 64, 64, 3), (1, 14, 18, 512, 512, 3), (2, 28, 36, 256, 256, 3), (2, 31, 45, 64, 32, 3),
+    (2, 24, 40, 32, 32, 3), (1, 24, 40, 32, 16, 3), (1, 24, 40, 16, 16, 3), (1, 28, 36, 136, 256, 3),
+    (1, 56, 72, 48, 128, 3), (1, 14, 18, 384, 512, 3), (2, 20, 28, 512, 256, 1), (1, 24, 40, 64, 32, 1),
+    (1, 24, 40, 32, 16, 1), (1, 16, 20, 384, 128, 1), (2, 112, 144, 64, 64, 3),
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,KS", WG_CASES)
+def test_wgrad(pkg, B, H, W, Cin, Cout, KS):
+    L = pkg._lib
+    g = torch.Generator().manual_seed(H * 7 + Cin + Cout)
+    x = torch.randn(B, H, W, Cin, generator=g).to(torch.bfloat16).cuda()
+    dy = torch.randn(B, H, W, Cout, generator=g).to(torch.bfloat16).cuda()
+    grad = torch.full((Cout, Cin, KS, KS), float("nan"), device="cuda")
+    nb = L.lib().dp_conv2d_wgrad_tc_workspace(B, H, W, Cin, Cout, KS)
+    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    L.check(L.lib().dp_conv2d_wgrad_tc(L.ptr(x), Cin, L.ptr(dy), Cout, B, H, W, Cin, Cout, KS, L.ptr(grad), 0,
+                                       L.ptr(ws), nb, L.stream()))
+    torch.cuda.synchronize()
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(False)
+    w0 = torch.zeros(Cout, Cin, KS, KS, device="cuda", requires_grad=True)
+    y = F.conv2d(xr, w0, padding=KS // 2)
+    y.backward(dy.float().permute(0, 3, 1, 2))
+    ref = w0.grad
+    err = (grad - ref).abs()
+    tol = 1e-3 * ref.abs() + 1e-3 * float(ref.abs().max())
+    assert bool((err <= tol).all()), f"max err {float(err.max())} scale {float(ref.abs().max())}"

@@ -90,3 +90,28 @@ def test_m64_tmem_layout(pkg):
     print("M=64 row->lane map:", lanes)
     expect = [(i // 16) * 32 + (i % 16) for i in range(64)]
     assert lanes == expect or lanes == list(range(64)), lanes
+
+
+@pytest.mark.parametrize("mc", [32, 16])
+def test_mn_major_narrow_swizzles_and_aliasing(pkg, mc):
+    """narrow layers (16/32 channels): MN-major boxes with 64B/32B rows; M=64 built from aliased chunks (LBO=0)."""
+    K, N = 64, mc
+    At = _rand(K, mc, 12)       # [K][mc]  -> M=64 made of 64/mc aliases of the same chunk
+    Bt = _rand(K, N, 13)
+    rb = mc * 2
+    out = _probe(pkg, At, (K, mc), Bt, (K, N), 64, N, K // 16, 1, 1,
+                 [0, 8 * rb, SW[rb], 16 * rb, 0], [0, 8 * rb, SW[rb], 16 * rb, 0], ncols=max(16, N))
+    ref = At.float().t() @ Bt.float()       # [mc][N]
+    lanes = [(i // 16) * 32 + (i % 16) for i in range(mc)]
+    assert torch.equal(out[lanes, :N], ref)
+
+
+def test_mn_major_b_row_shift(pkg):
+    """wgrad vertical taps: the X halo box is read r*tw pixel-rows further down (multiple of 8 rows)."""
+    K, M, N = 128, 128, 64
+    At = _rand(K, M, 14)
+    Xt = _rand(K + 32, N, 15)
+    out = _probe(pkg, At, (K, 64), Xt, (K + 32, 64), M, N, K // 16, 1, 1,
+                 [K * 128, 1024, 2, 2048, 0], [0, 1024, 2, 2048, 16 * 128])
+    ref = At.float().t() @ Xt[16:16 + K].float()
+    assert torch.equal(out[:, :N], ref)
