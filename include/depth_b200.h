@@ -122,15 +122,16 @@ int dp_metrics_combine(const double* moments, const unsigned long long* counts, 
  * weight pack, the data gradient autograd derives for them.
  *   x         NHWC bf16, pixel stride x_ld elements (a channel slice of a wider buffer is fine)
  *   w_packed  bf16 [KS*KS][Cout][Cin_p]  (tap = r*KS+s; Cin_p >= Cin, zero padded)
- *   epilogue  y = acc (+ bias[c]) (+ residual[pixel][c]);  out  = relu ? max(y,0) : y   (may be NULL)
- *                                                          out2 = relu2 ? max(y,0) : y  (may be NULL)
+ *   epilogue  y = acc (+ bias[c]) (+ residual[pixel][c]) (+ residual2[pixel][c]);
+ *             out  = relu ? max(y,0) : y   (may be NULL)
+ *             out2 = relu2 ? max(y,0) : y  (may be NULL)
  *   stats_partials  NULL or float[dp_conv2d_tc_grid()][2][Cout]: per-CTA sum / sum of squares of y over pixels
  *                   (train-mode BatchNorm statistics, midas_semantics.py:133,136,142,196) */
 int dp_conv2d_tc_grid(int B, int H, int W, int Cin, int Cout, int KS);
 int dp_conv2d_tc(const void* x, long long x_ld, int B, int H, int W, int Cin, const void* w_packed, int Cin_p,
-                 int Cout, int KS, const float* bias, const void* residual, long long res_ld, int relu, void* out,
-                 long long out_ld, void* out2, long long out2_ld, int relu2, float* stats_partials,
-                 cudaStream_t stream);
+                 int Cout, int KS, const float* bias, const void* residual, long long res_ld, const void* residual2,
+                 long long res2_ld, int relu, void* out, long long out_ld, void* out2, long long out2_ld, int relu2,
+                 float* stats_partials, cudaStream_t stream);
 
 /* Weight gradient of the same convolutions (autograd's convolution_backward w.r.t. weight), tcgen05 GEMM over
  * pixels with split-K partials reduced deterministically.  x, dy: NHWC bf16; grad_oihw: fp32 [Cout][Cin][KS][KS]
@@ -139,6 +140,101 @@ size_t dp_conv2d_wgrad_tc_workspace(int B, int H, int W, int Cin, int Cout, int 
 int dp_conv2d_wgrad_tc(const void* x, long long x_ld, const void* dy, long long dy_ld, int B, int H, int W, int Cin,
                        int Cout, int KS, float* grad_oihw, int accumulate, void* workspace, size_t workspace_bytes,
                        cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Layout / dtype boundaries and weight packing (csrc/layout.cu)
+ * ---------------------------------------------------------------------------------------------- */
+/* reference modules speak NCHW fp32; (B,C,H,W) fp32 <-> (B,H,W,ld) bf16 */
+int dp_nchw_f32_to_nhwc_bf16(const float* src, int B, int C, int H, int W, void* dst, long long dst_ld, cudaStream_t stream);
+int dp_nhwc_bf16_to_nchw_f32(const void* src, long long src_ld, int B, int C, int H, int W, float* dst, cudaStream_t stream);
+int dp_cast_f32_to_bf16(const float* src, void* dst, size_t n, cudaStream_t stream);
+int dp_cast_bf16_to_f32(const void* src, float* dst, size_t n, cudaStream_t stream);
+/* fp32 weight [D0][D1][KH][KW] (nn.Conv2d: D0=out, D1=in; nn.ConvTranspose2d: D0=in, D1=out) -> bf16 [KH*KW][A][ld]
+ * with (A, b) = swap ? (D1, d0) : (D0, d1) and the tap order reversed when flip != 0.
+ *   conv forward operand:  swap 0 flip 0;   stride-1 data gradient (correlation with dY): swap 1 flip 1;
+ *   gather-form data gradient / transposed-conv forward: swap 1 flip 0;  transposed-conv data gradient: swap 0 flip 0 */
+int dp_pack_conv_weight(const float* w, int D0, int D1, int KH, int KW, int swap, int flip, void* dst, int ld,
+                        cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Bandwidth-bound NHWC bf16 kernels (csrc/elementwise.cu)
+ * ---------------------------------------------------------------------------------------------- */
+/* out = g_raw + g_relu * (y > 0): gradient of a tensor consumed both raw and through nn.ReLU (blocks.py:361-374) */
+int dp_add_relu_bwd(const void* g_raw, const void* g_relu, const void* y, void* out, size_t n, cudaStream_t stream);
+int dp_relu_bf16(const void* x, void* out, size_t n, cudaStream_t stream);
+int dp_add_bf16(const void* a, const void* b, const void* c, void* out, size_t n, cudaStream_t stream);
+/* dst[p][0..C) = src[p][0..C): channel concat (torch.cat dim=1, midas_semantics.py:250) and slice copies */
+int dp_copy_channels(const void* src, long long src_ld, void* dst, long long dst_ld, size_t npix, int C,
+                     cudaStream_t stream);
+/* F.interpolate(mode="bilinear") forward / backward (blocks.py:226-238,432-434; dpt_depth.py:147; midas_semantics.py:243) */
+int dp_resize_bilinear_nhwc(const void* src, long long src_ld, int B, int Hi, int Wi, int C, void* dst, long long dst_ld,
+                            int Ho, int Wo, int align_corners, cudaStream_t stream);
+int dp_resize_bilinear_nhwc_bwd(const void* gout, long long g_ld, int B, int Hi, int Wi, int C, void* gin,
+                                long long gin_ld, int Ho, int Wo, int align_corners, cudaStream_t stream);
+/* fp32 planes: the RGB->DINOv2 resize (midas_semantics.py:233) and the prediction resize (util.py:308-313) */
+int dp_resize_bilinear_planes_f32(const float* src, int planes, int Hi, int Wi, float* dst, int Ho, int Wo,
+                                  int align_corners, cudaStream_t stream);
+/* per-channel sums over pixels: mode 0 sum x; 1 sum x, sum x^2; 2 sum g, sum g*x with g = dy*(mask>0).
+ * partial: float[dp_chan_reduce_blocks()][2][C]; dp_sum_partials folds partials into out[rows][C] */
+int dp_chan_reduce_blocks(void);
+int dp_chan_reduce(int mode, const void* x, long long x_ld, const void* dy, long long dy_ld, const void* mask,
+                   long long m_ld, size_t npix, int C, float* partial, cudaStream_t stream);
+int dp_sum_partials(const float* partial, int nparts, int rows, int C, float* out, int accumulate, cudaStream_t stream);
+/* nn.BatchNorm2d (midas_semantics.py:40-61,133-151,196): train-mode finalize from (sum, sumsq) partials incl. running
+ * statistics update (momentum, unbiased variance, num_batches_tracked += 1); eval-mode coefficients; apply; backward */
+int dp_bn_finalize(const float* partial, int nparts, int C, double count, const float* gamma, const float* beta,
+                   float eps, float momentum, float* running_mean, float* running_var, long long* num_batches_tracked,
+                   float* scale_shift, float* save_mean_invstd, cudaStream_t stream);
+int dp_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                      float eps, int C, float* scale_shift, float* save_mean_invstd, cudaStream_t stream);
+int dp_bn_apply(const void* x, long long x_ld, const float* scale_shift, const void* x2, long long x2_ld,
+                const float* scale_shift2, const void* res, long long res_ld, size_t npix, int C, int relu, void* y,
+                long long y_ld, cudaStream_t stream);
+int dp_bn_bwd_apply(const void* dy, long long dy_ld, const void* mask, long long m_ld, const void* x, long long x_ld,
+                    const float* red, const float* save_mean_invstd, const float* gamma, double count, int train,
+                    size_t npix, int C, void* dx, long long dx_ld, void* gmask, long long gm_ld, float* dgamma,
+                    float* dbeta, int accumulate, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Direct convolutions for strided / transposed layers and the C->1 heads (csrc/conv_direct.cu)
+ * ---------------------------------------------------------------------------------------------- */
+/* gather-form conv: conv rule iy = oy*stride - pad + ky, or transposed rule iy = (oy + pad - ky)/stride.
+ * Serves nn.Conv2d(stride 2) and nn.ConvTranspose2d forward and both data gradients
+ * (midas_semantics.py:38-61; dpt_depth.py:49-69).  w_packed bf16 [KH*KW][Co][Ci]. */
+int dp_conv_gather(const void* in, long long in_ld, int B, int Hi, int Wi, int Ci, const void* w_packed,
+                   const float* bias, void* out, long long out_ld, int Ho, int Wo, int Co, int KH, int KW, int stride,
+                   int pad, int transposed, int relu, cudaStream_t stream);
+size_t dp_conv_wgrad_direct_workspace(int B, int Hp, int Wp, int Cp, int Ct, int KH, int KW);
+int dp_conv_wgrad_direct(const void* P, long long p_ld, int Hp, int Wp, int Cp, const void* T, long long t_ld, int Ht,
+                         int Wt, int Ct, int B, int KH, int KW, int stride, int pad, int perm, float* out,
+                         int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+/* C->1 conv (3x3 pad 1 or 1x1) + bias + optional ReLU, fp32 (B,H,W) output: midas_semantics.py:203-204,
+ * midas_net_custom.py:110-111, dpt_depth.py:282-283.  w fp32 [1][C][KS][KS]. */
+int dp_head_conv_fwd(const void* x, long long x_ld, int B, int H, int W, int C, int KS, const float* w,
+                     const float* bias, int relu, float* out, cudaStream_t stream);
+size_t dp_head_conv_bwd_workspace(int C, int KS);
+int dp_head_conv_bwd(const float* dout, const float* out, int relu, const void* x, long long x_ld, int B, int H, int W,
+                     int C, int KS, const float* w, void* dx, long long dx_ld, float* dw, float* db, int accumulate,
+                     void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * CrossAttention token path (csrc/attention.cu; midas_semantics.py:63-127), dim 32 = 8 heads x 4
+ * ---------------------------------------------------------------------------------------------- */
+int dp_lnl_blocks(void);
+int dp_lnl_partial_floats(void);
+int dp_ln_linear_fwd(const void* x, long long x_ld, int x_is_f32, size_t ntok, int dim, const float* gamma,
+                     const float* beta, float eps, const float* W, const float* bias, void* out, long long out_ld,
+                     int out_is_bf16, cudaStream_t stream);
+int dp_ln_linear_bwd(const void* x, long long x_ld, int x_is_f32, size_t ntok, int dim, const float* gamma,
+                     const float* beta, float eps, const float* W, const void* dout, long long do_ld, int dout_is_bf16,
+                     void* dx, long long dx_ld, float* partial, float* dW, float* dbias, float* dgamma, float* dbeta,
+                     int accumulate, cudaStream_t stream);
+/* window loop of midas_semantics.py:93-112 in last-writer form; items/segs: device int4 arrays (see attention.cu) */
+int dp_attn_fwd(const float* q, const float* k, const float* v, int B, int N, float scale, const void* items,
+                int nitems, float* out, float* lse, cudaStream_t stream);
+int dp_attn_bwd(const float* q, const float* k, const float* v, const float* out, const float* dout, const float* lse,
+                int B, int N, float scale, const void* items, int nitems, const void* segs, int nseg, float* dq,
+                float* dk, float* dv, float* delta, cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Diagnostics

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libdepth_b200.so")
 c_int, c_uint, c_float, c_size_t, c_void_p, c_u64 = (ctypes.c_int, ctypes.c_uint, ctypes.c_float, ctypes.c_size_t,
                                                       ctypes.c_void_p, ctypes.c_uint64)
 c_ll = ctypes.c_longlong
+c_double = ctypes.c_double
 
 
 class DepthB200Error(RuntimeError):
@@ -65,10 +66,46 @@ class _Sig:
                                c_size_t, P])
     dp_metrics_combine = (c_int, [P, P, c_int, c_int, c_int, c_int, P, P])
     dp_conv2d_tc_grid = (c_int, [c_int, c_int, c_int, c_int, c_int, c_int])
-    dp_conv2d_tc = (c_int, [P, c_ll, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, P, P, c_ll, c_int, P, c_ll, P,
-                            c_ll, c_int, P, P])
+    dp_conv2d_tc = (c_int, [P, c_ll, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, P, P, c_ll, P, c_ll, c_int, P,
+                            c_ll, P, c_ll, c_int, P, P])
     dp_conv2d_wgrad_tc_workspace = (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int])
     dp_conv2d_wgrad_tc = (c_int, [P, c_ll, P, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_size_t, P])
+    dp_nchw_f32_to_nhwc_bf16 = (c_int, [P, c_int, c_int, c_int, c_int, P, c_ll, P])
+    dp_nhwc_bf16_to_nchw_f32 = (c_int, [P, c_ll, c_int, c_int, c_int, c_int, P, P])
+    dp_cast_f32_to_bf16 = (c_int, [P, P, c_size_t, P])
+    dp_cast_bf16_to_f32 = (c_int, [P, P, c_size_t, P])
+    dp_pack_conv_weight = (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P])
+    dp_add_relu_bwd = (c_int, [P, P, P, P, c_size_t, P])
+    dp_add_bf16 = (c_int, [P, P, P, P, c_size_t, P])
+    dp_relu_bf16 = (c_int, [P, P, c_size_t, P])
+    dp_copy_channels = (c_int, [P, c_ll, P, c_ll, c_size_t, c_int, P])
+    dp_resize_bilinear_nhwc = (c_int, [P, c_ll, c_int, c_int, c_int, c_int, P, c_ll, c_int, c_int, c_int, P])
+    dp_resize_bilinear_nhwc_bwd = (c_int, [P, c_ll, c_int, c_int, c_int, c_int, P, c_ll, c_int, c_int, c_int, P])
+    dp_resize_bilinear_planes_f32 = (c_int, [P, c_int, c_int, c_int, P, c_int, c_int, c_int, P])
+    dp_chan_reduce_blocks = (c_int, [])
+    dp_chan_reduce = (c_int, [c_int, P, c_ll, P, c_ll, P, c_ll, c_size_t, c_int, P, P])
+    dp_sum_partials = (c_int, [P, c_int, c_int, c_int, P, c_int, P])
+    dp_bn_finalize = (c_int, [P, c_int, c_int, c_double, P, P, c_float, c_float, P, P, P, P, P, P])
+    dp_bn_eval_coeffs = (c_int, [P, P, P, P, c_float, c_int, P, P, P])
+    dp_bn_apply = (c_int, [P, c_ll, P, P, c_ll, P, P, c_ll, c_size_t, c_int, c_int, P, c_ll, P])
+    dp_bn_bwd_apply = (c_int, [P, c_ll, P, c_ll, P, c_ll, P, P, P, c_double, c_int, c_size_t, c_int, P, c_ll, P, c_ll,
+                               P, P, c_int, P])
+    dp_conv_gather = (c_int, [P, c_ll, c_int, c_int, c_int, c_int, P, P, P, c_ll, c_int, c_int, c_int, c_int, c_int,
+                              c_int, c_int, c_int, c_int, P])
+    dp_conv_wgrad_direct_workspace = (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int])
+    dp_conv_wgrad_direct = (c_int, [P, c_ll, c_int, c_int, c_int, P, c_ll, c_int, c_int, c_int, c_int, c_int, c_int,
+                                    c_int, c_int, c_int, P, c_int, P, c_size_t, P])
+    dp_head_conv_fwd = (c_int, [P, c_ll, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, P])
+    dp_head_conv_bwd_workspace = (c_size_t, [c_int, c_int])
+    dp_head_conv_bwd = (c_int, [P, P, c_int, P, c_ll, c_int, c_int, c_int, c_int, c_int, P, P, c_ll, P, P, c_int, P,
+                                c_size_t, P])
+    dp_lnl_blocks = (c_int, [])
+    dp_lnl_partial_floats = (c_int, [])
+    dp_ln_linear_fwd = (c_int, [P, c_ll, c_int, c_size_t, c_int, P, P, c_float, P, P, P, c_ll, c_int, P])
+    dp_ln_linear_bwd = (c_int, [P, c_ll, c_int, c_size_t, c_int, P, P, c_float, P, P, c_ll, c_int, P, c_ll, P, P, P, P,
+                                P, c_int, P])
+    dp_attn_fwd = (c_int, [P, P, P, c_int, c_int, c_float, P, c_int, P, P, P])
+    dp_attn_bwd = (c_int, [P, P, P, P, P, P, c_int, c_int, c_float, P, c_int, P, c_int, P, P, P, P, P])
     dp_umma_probe = (c_int, [P, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                              c_int, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32), P, c_int, P])
 

@@ -82,6 +82,6 @@ __device__ __forceinline__ float sgnf(float x) { return (x > 0.f) ? 1.f : ((x < 
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+__host__ __device__ static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace dp

@@ -1,0 +1,417 @@
+// CUDA-core direct convolutions for the few layers the tcgen05 implicit GEMM does not cover:
+//   * stride-2 3x3 convs and k4/s2/p1, k4/s4, k2/s2 transposed convs (CrossAttention.spatial_reduction /
+//     spatial_upsample, midas_semantics.py:38-61; Dinov2Head.resize_layers, dpt_depth.py:49-69), forward,
+//     data gradient and weight gradient;
+//   * the 16->1 (or C->1) 3x3 depth head with bias + ReLU (midas_semantics.py:203-204) and the
+//     1x1 32->1 head of MidasNet_small / DPT (midas_net_custom.py:110-111, dpt_depth.py:282-283).
+// One gather-form kernel serves conv forward, transposed-conv forward and both data gradients:
+//   out[b,oy,ox,co] = bias[co] + sum_{ky,kx,ci} in[b,iy,ix,ci] * Wg[ky*KW+kx][co][ci]
+//   conv rule:        iy = oy*stride - pad + ky
+//   transposed rule:  iy = (oy + pad - ky) / stride   when divisible
+#include "common.cuh"
+#include "../../include/depth_b200.h"
+
+namespace {
+
+using namespace dp;
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+    f[2 * i] = __low2float(h);
+    f[2 * i + 1] = __high2float(h);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+struct GatherArgs {
+  const bf16* in; long long in_ld; int Hi, Wi, Ci;
+  const bf16* w;   // [KH*KW][Co][Ci]
+  const float* bias;
+  bf16* out; long long out_ld; int B, Ho, Wo, Co;
+  int KH, KW, stride, pad, transposed, relu;
+};
+
+// thread = one output pixel x 8 output channels
+__global__ void __launch_bounds__(256) conv_gather_kernel(GatherArgs a) {
+  const int G = a.Co / 8;
+  const size_t total = (size_t)a.B * a.Ho * a.Wo * G;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    size_t p = i / G;
+    const int ox = (int)(p % a.Wo); p /= a.Wo;
+    const int oy = (int)(p % a.Ho);
+    const int b = (int)(p / a.Ho);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = a.bias ? __ldg(a.bias + g * 8 + j) : 0.f;
+    for (int ky = 0; ky < a.KH; ++ky) {
+      int iy;
+      if (a.transposed) {
+        const int t = oy + a.pad - ky;
+        if (t < 0 || (t % a.stride) != 0) continue;
+        iy = t / a.stride;
+      } else {
+        iy = oy * a.stride - a.pad + ky;
+      }
+      if (iy < 0 || iy >= a.Hi) continue;
+      for (int kx = 0; kx < a.KW; ++kx) {
+        int ix;
+        if (a.transposed) {
+          const int t = ox + a.pad - kx;
+          if (t < 0 || (t % a.stride) != 0) continue;
+          ix = t / a.stride;
+        } else {
+          ix = ox * a.stride - a.pad + kx;
+        }
+        if (ix < 0 || ix >= a.Wi) continue;
+        const bf16* xin = a.in + (((size_t)b * a.Hi + iy) * a.Wi + ix) * a.in_ld;
+        const bf16* wt = a.w + ((size_t)(ky * a.KW + kx) * a.Co + g * 8) * a.Ci;
+        for (int c = 0; c < a.Ci; c += 8) {
+          float xv[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(xin + c)), xv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float wv[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(wt + (size_t)j * a.Ci + c)), wv);
+            float s = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) s += xv[q] * wv[q];
+            acc[j] += s;
+          }
+        }
+      }
+    }
+    if (a.relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+    }
+    *reinterpret_cast<uint4*>(a.out + (((size_t)b * a.Ho + oy) * a.Wo + ox) * a.out_ld + g * 8) = pack8(acc);
+  }
+}
+
+// out[tap][cp][ct] (fp32 partials per pixel chunk) = sum over plain-grid pixels (b,y,x) of
+//     P[b,y,x,cp] * T[b, y*stride-pad+ky, x*stride-pad+kx, ct]
+// block: 32x32 tile of (cp, ct) for one tap and one pixel chunk; 256 threads, 4 ct per thread.
+struct WgDirectArgs {
+  const bf16* P; long long p_ld; int Hp, Wp, Cp;
+  const bf16* T; long long t_ld; int Ht, Wt, Ct;
+  int B, KH, KW, stride, pad, chunks;
+  float* partial;  // [chunks][KH*KW][Cp][Ct]
+};
+
+__global__ void __launch_bounds__(256) conv_wgrad_direct_kernel(WgDirectArgs a) {
+  __shared__ float sP[32][33];
+  __shared__ float sT[32][33];
+  const int tiles_t = ceil_div(a.Ct, 32);
+  const int cp0 = (blockIdx.y / tiles_t) * 32, ct0 = (blockIdx.y % tiles_t) * 32;
+  const int tap = blockIdx.z % (a.KH * a.KW), chunk = blockIdx.z / (a.KH * a.KW);
+  const int ky = tap / a.KW, kx = tap % a.KW;
+  const size_t npix = (size_t)a.B * a.Hp * a.Wp;
+  const size_t per = (npix + a.chunks - 1) / a.chunks;
+  const size_t p_begin = (size_t)chunk * per, p_end = min(npix, p_begin + per);
+  const int cp = threadIdx.x / 8, ctg = (threadIdx.x % 8) * 4;  // this thread: row cp, columns ctg..ctg+3
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (size_t base = p_begin; base < p_end; base += 32) {
+    // stage 32 pixels x 32 channels of each operand
+    for (int e = threadIdx.x; e < 32 * 32; e += 256) {
+      const int pi = e / 32, c = e % 32;
+      const size_t p = base + pi;
+      float pv = 0.f, tv = 0.f;
+      if (p < p_end) {
+        const int x = (int)(p % a.Wp);
+        const int y = (int)((p / a.Wp) % a.Hp);
+        const int b = (int)(p / ((size_t)a.Wp * a.Hp));
+        if (cp0 + c < a.Cp) pv = __bfloat162float(a.P[p * a.p_ld + cp0 + c]);
+        const int ty = y * a.stride - a.pad + ky, tx = x * a.stride - a.pad + kx;
+        if (ty >= 0 && ty < a.Ht && tx >= 0 && tx < a.Wt && ct0 + c < a.Ct)
+          tv = __bfloat162float(a.T[(((size_t)b * a.Ht + ty) * a.Wt + tx) * a.t_ld + ct0 + c]);
+      }
+      sP[pi][c] = pv;
+      sT[pi][c] = tv;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int pi = 0; pi < 32; ++pi) {
+      const float pv = sP[pi][cp];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] += pv * sT[pi][ctg + j];
+    }
+    __syncthreads();
+  }
+  if (cp0 + cp < a.Cp) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (ct0 + ctg + j < a.Ct)
+        a.partial[(((size_t)chunk * a.KH * a.KW + tap) * a.Cp + cp0 + cp) * a.Ct + ct0 + ctg + j] = acc[j];
+  }
+}
+
+// out[i] (+)= sum over chunks; optional permutation to OIHW / IOHW: src index (tap, cp, ct) ->
+// dst[(cp*Ct + ct)*taps + tap] when perm == 1, dst[(ct*Cp + cp)*taps + tap] when perm == 2, identity when 0
+__global__ void wgrad_direct_reduce_kernel(const float* __restrict__ partial, int chunks, int taps, int Cp, int Ct,
+                                           int perm, float* __restrict__ out, int accumulate) {
+  const long long total = (long long)taps * Cp * Ct;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int c = 0; c < chunks; ++c) s += partial[(size_t)c * total + i];
+    const int ct = (int)(i % Ct);
+    const int cp = (int)((i / Ct) % Cp);
+    const int tap = (int)(i / ((long long)Ct * Cp));
+    size_t o = (size_t)i;
+    if (perm == 1) o = ((size_t)cp * Ct + ct) * taps + tap;
+    if (perm == 2) o = ((size_t)ct * Cp + cp) * taps + tap;
+    out[o] = accumulate ? out[o] + s : s;
+  }
+}
+
+// ---- C -> 1 head convolution (3x3 pad 1 or 1x1), bias, optional ReLU; fp32 (B,H,W) output --------------------
+__global__ void __launch_bounds__(256) head_conv_fwd_kernel(const bf16* __restrict__ x, long long x_ld, int B, int H,
+                                                            int W, int C, int KS, const float* __restrict__ w /*[C][KS][KS]*/,
+                                                            const float* __restrict__ bias, int relu,
+                                                            float* __restrict__ out) {
+  extern __shared__ float sw[];  // [KS*KS][C]
+  for (int i = threadIdx.x; i < KS * KS * C; i += blockDim.x) {
+    const int tap = i / C, c = i % C;
+    sw[i] = w[(size_t)c * KS * KS + tap];
+  }
+  __syncthreads();
+  const int pad = KS / 2;
+  const size_t total = (size_t)B * H * W;
+  const float b0 = bias ? __ldg(bias) : 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % W);
+    const int yy = (int)((i / W) % H);
+    const int b = (int)(i / ((size_t)W * H));
+    float acc = b0;
+    for (int r = 0; r < KS; ++r) {
+      const int iy = yy + r - pad;
+      if (iy < 0 || iy >= H) continue;
+      for (int s = 0; s < KS; ++s) {
+        const int ix = xx + s - pad;
+        if (ix < 0 || ix >= W) continue;
+        const bf16* px = x + (((size_t)b * H + iy) * W + ix) * x_ld;
+        const float* wt = sw + (r * KS + s) * C;
+        for (int c = 0; c < C; c += 8) {
+          float v[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(px + c)), v);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc += v[q] * wt[c + q];
+        }
+      }
+    }
+    out[i] = relu ? fmaxf(acc, 0.f) : acc;
+  }
+}
+
+// data gradient: dx[b,y,x,c] = sum_taps g[b, y-(r-pad), x-(s-pad)] * w[c][r][s],  g = dout * (out > 0 if relu)
+__global__ void __launch_bounds__(256) head_conv_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                                                              int relu, int B, int H, int W, int C, int KS,
+                                                              const float* __restrict__ w, bf16* __restrict__ dx,
+                                                              long long dx_ld) {
+  extern __shared__ float sw[];  // [KS*KS][C]
+  for (int i = threadIdx.x; i < KS * KS * C; i += blockDim.x) {
+    const int tap = i / C, c = i % C;
+    sw[i] = w[(size_t)c * KS * KS + tap];
+  }
+  __syncthreads();
+  const int pad = KS / 2, C8 = C / 8;
+  const size_t total = (size_t)B * H * W * C8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    size_t p = i / C8;
+    const int xx = (int)(p % W);
+    const int yy = (int)((p / W) % H);
+    const int b = (int)(p / ((size_t)W * H));
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int r = 0; r < KS; ++r) {
+      const int oy = yy - (r - pad);
+      if (oy < 0 || oy >= H) continue;
+      for (int s = 0; s < KS; ++s) {
+        const int ox = xx - (s - pad);
+        if (ox < 0 || ox >= W) continue;
+        const size_t o = ((size_t)b * H + oy) * W + ox;
+        float g = __ldg(dout + o);
+        if (relu && !(__ldg(out + o) > 0.f)) g = 0.f;
+        const float* wt = sw + (r * KS + s) * C + c8 * 8;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] += g * wt[q];
+      }
+    }
+    *reinterpret_cast<uint4*>(dx + p * dx_ld + c8 * 8) = pack8(acc);
+  }
+}
+
+// weight + bias gradient partials: part[block][KS*KS*C + 1]
+__global__ void __launch_bounds__(256) head_conv_wgrad_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                                                              int relu, const bf16* __restrict__ x, long long x_ld, int B,
+                                                              int H, int W, int C, int KS, float* __restrict__ part) {
+  extern __shared__ float sacc[];  // [KS*KS*C + 1]
+  const int nacc = KS * KS * C + 1;
+  for (int i = threadIdx.x; i < nacc; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int pad = KS / 2;
+  const size_t total = (size_t)B * H * W;
+  // each warp walks output pixels; lane l owns accumulators l, l+32, ... (tap-major, channel-minor)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  float local[20];  // up to ceil(577/32) accumulators per lane for C=64, KS=3
+  const int per_lane = (nacc + 31) / 32;
+  for (int k = 0; k < per_lane && k < 20; ++k) local[k] = 0.f;
+  for (size_t o = (size_t)blockIdx.x * nwarp + warp; o < total; o += (size_t)gridDim.x * nwarp) {
+    float g = __ldg(dout + o);
+    if (relu && !(__ldg(out + o) > 0.f)) g = 0.f;
+    if (g == 0.f) continue;
+    const int xx = (int)(o % W);
+    const int yy = (int)((o / W) % H);
+    const int b = (int)(o / ((size_t)W * H));
+    for (int k = 0; k < per_lane && k < 20; ++k) {
+      const int idx = k * 32 + lane;
+      if (idx >= nacc) break;
+      if (idx == nacc - 1) { local[k] += g; continue; }
+      const int tap = idx / C, c = idx % C;
+      const int iy = yy + tap / KS - pad, ix = xx + tap % KS - pad;
+      if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+      local[k] += g * __bfloat162float(x[(((size_t)b * H + iy) * W + ix) * x_ld + c]);
+    }
+  }
+  for (int k = 0; k < per_lane && k < 20; ++k) {
+    const int idx = k * 32 + lane;
+    if (idx < nacc) atomicAdd(&sacc[idx], local[k]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nacc; i += blockDim.x) part[(size_t)blockIdx.x * nacc + i] = sacc[i];
+}
+
+__global__ void head_conv_wgrad_reduce_kernel(const float* __restrict__ part, int nblocks, int C, int KS,
+                                              float* __restrict__ dw /*[C][KS][KS]*/, float* __restrict__ db,
+                                              int accumulate) {
+  const int nacc = KS * KS * C + 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nacc) return;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += (double)part[(size_t)b * nacc + i];
+  if (i == nacc - 1) {
+    if (db) db[0] = accumulate ? db[0] + (float)s : (float)s;
+  } else {
+    const int tap = i / C, c = i % C;
+    const size_t o = (size_t)c * KS * KS + tap;
+    dw[o] = accumulate ? dw[o] + (float)s : (float)s;
+  }
+}
+
+constexpr int kHeadWgBlocks = 2 * kNumSMs;
+
+inline int grid_for(size_t items, int tpb = 256, int waves = 8) {
+  size_t b = (items + tpb - 1) / tpb, cap = (size_t)waves * kNumSMs;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+inline int wg_chunks(size_t npix, int tiles, int taps) {
+  long long want = (4LL * kNumSMs + (long long)tiles * taps - 1) / ((long long)tiles * taps);
+  long long maxc = (long long)((npix + 255) / 256);
+  if (want > maxc) want = maxc;
+  if (want < 1) want = 1;
+  if (want > 512) want = 512;
+  return (int)want;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dp_conv_gather(const void* in, long long in_ld, int B, int Hi, int Wi, int Ci, const void* w_packed,
+                   const float* bias, void* out, long long out_ld, int Ho, int Wo, int Co, int KH, int KW, int stride,
+                   int pad, int transposed, int relu, cudaStream_t stream) {
+  DP_CHECK_ARG(in && w_packed && out, "dp_conv_gather: null pointer");
+  DP_CHECK_ARG(Ci % 8 == 0 && Co % 8 == 0 && in_ld % 8 == 0 && out_ld % 8 == 0, "dp_conv_gather: channels %% 8");
+  DP_CHECK_ARG(stride >= 1 && KH >= 1 && KW >= 1, "dp_conv_gather: bad geometry");
+  GatherArgs a;
+  a.in = (const bf16*)in; a.in_ld = in_ld; a.Hi = Hi; a.Wi = Wi; a.Ci = Ci;
+  a.w = (const bf16*)w_packed; a.bias = bias;
+  a.out = (bf16*)out; a.out_ld = out_ld; a.B = B; a.Ho = Ho; a.Wo = Wo; a.Co = Co;
+  a.KH = KH; a.KW = KW; a.stride = stride; a.pad = pad; a.transposed = transposed; a.relu = relu;
+  conv_gather_kernel<<<grid_for((size_t)B * Ho * Wo * (Co / 8), 256, 16), 256, 0, stream>>>(a);
+  DP_CHECK_LAUNCH("conv_gather_kernel");
+  return DP_OK;
+}
+
+size_t dp_conv_wgrad_direct_workspace(int B, int Hp, int Wp, int Cp, int Ct, int KH, int KW) {
+  const int tiles = dp::ceil_div(Cp, 32) * dp::ceil_div(Ct, 32);
+  const int chunks = wg_chunks((size_t)B * Hp * Wp, tiles, KH * KW);
+  return (size_t)chunks * KH * KW * Cp * Ct * sizeof(float);
+}
+
+/* out[(tap,cp,ct) permuted] = sum_pixels P[pix][cp] * T[pix*stride - pad + tap][ct].
+ * perm 0: [tap][Cp][Ct]; 1: [Cp][Ct][tap] (OIHW when P = dY, T = X); 2: [Ct][Cp][tap] */
+int dp_conv_wgrad_direct(const void* P, long long p_ld, int Hp, int Wp, int Cp, const void* T, long long t_ld, int Ht,
+                         int Wt, int Ct, int B, int KH, int KW, int stride, int pad, int perm, float* out,
+                         int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  DP_CHECK_ARG(P && T && out && workspace, "dp_conv_wgrad_direct: null pointer");
+  const int tiles = dp::ceil_div(Cp, 32) * dp::ceil_div(Ct, 32);
+  WgDirectArgs a;
+  a.P = (const bf16*)P; a.p_ld = p_ld; a.Hp = Hp; a.Wp = Wp; a.Cp = Cp;
+  a.T = (const bf16*)T; a.t_ld = t_ld; a.Ht = Ht; a.Wt = Wt; a.Ct = Ct;
+  a.B = B; a.KH = KH; a.KW = KW; a.stride = stride; a.pad = pad;
+  a.chunks = wg_chunks((size_t)B * Hp * Wp, tiles, KH * KW);
+  const size_t need = (size_t)a.chunks * KH * KW * Cp * Ct * sizeof(float);
+  if (workspace_bytes < need) return dp_set_error(DP_ERR_WORKSPACE, "dp_conv_wgrad_direct: workspace %zu < %zu",
+                                                  workspace_bytes, need);
+  a.partial = (float*)workspace;
+  dim3 grid(1, tiles, a.chunks * KH * KW);
+  DP_CHECK_ARG(grid.z <= 65535, "dp_conv_wgrad_direct: grid too large");
+  conv_wgrad_direct_kernel<<<grid, 256, 0, stream>>>(a);
+  DP_CHECK_LAUNCH("conv_wgrad_direct_kernel");
+  const long long total = (long long)KH * KW * Cp * Ct;
+  wgrad_direct_reduce_kernel<<<grid_for((size_t)total), 256, 0, stream>>>(a.partial, a.chunks, KH * KW, Cp, Ct, perm, out,
+                                                                          accumulate);
+  DP_CHECK_LAUNCH("wgrad_direct_reduce_kernel");
+  return DP_OK;
+}
+
+int dp_head_conv_fwd(const void* x, long long x_ld, int B, int H, int W, int C, int KS, const float* w,
+                     const float* bias, int relu, float* out, cudaStream_t stream) {
+  DP_CHECK_ARG(x && w && out && C % 8 == 0 && (KS == 1 || KS == 3), "dp_head_conv_fwd: bad arguments");
+  head_conv_fwd_kernel<<<grid_for((size_t)B * H * W), 256, KS * KS * C * sizeof(float), stream>>>(
+      (const bf16*)x, x_ld, B, H, W, C, KS, w, bias, relu, out);
+  DP_CHECK_LAUNCH("head_conv_fwd_kernel");
+  return DP_OK;
+}
+
+size_t dp_head_conv_bwd_workspace(int C, int KS) { return (size_t)kHeadWgBlocks * (KS * KS * C + 1) * sizeof(float); }
+
+int dp_head_conv_bwd(const float* dout, const float* out, int relu, const void* x, long long x_ld, int B, int H, int W,
+                     int C, int KS, const float* w, void* dx, long long dx_ld, float* dw, float* db, int accumulate,
+                     void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  DP_CHECK_ARG(dout && x && w && workspace && C % 8 == 0 && (KS == 1 || KS == 3) && (!relu || out),
+               "dp_head_conv_bwd: bad arguments");
+  DP_CHECK_ARG(KS * KS * C + 1 <= 640, "dp_head_conv_bwd: C too large for the head kernel");
+  if (workspace_bytes < dp_head_conv_bwd_workspace(C, KS))
+    return dp_set_error(DP_ERR_WORKSPACE, "dp_head_conv_bwd: workspace too small");
+  if (dx) {
+    head_conv_dgrad_kernel<<<grid_for((size_t)B * H * W * (C / 8)), 256, KS * KS * C * sizeof(float), stream>>>(
+        dout, out, relu, B, H, W, C, KS, w, (bf16*)dx, dx_ld);
+    DP_CHECK_LAUNCH("head_conv_dgrad_kernel");
+  }
+  if (dw) {
+    const int nacc = KS * KS * C + 1;
+    head_conv_wgrad_kernel<<<kHeadWgBlocks, 256, nacc * sizeof(float), stream>>>(dout, out, relu, (const bf16*)x, x_ld, B,
+                                                                                 H, W, C, KS, (float*)workspace);
+    DP_CHECK_LAUNCH("head_conv_wgrad_kernel");
+    head_conv_wgrad_reduce_kernel<<<dp::ceil_div(nacc, 128), 128, 0, stream>>>((const float*)workspace, kHeadWgBlocks, C,
+                                                                               KS, dw, db, accumulate);
+    DP_CHECK_LAUNCH("head_conv_wgrad_reduce_kernel");
+  }
+  return DP_OK;
+}
+
+}  // extern "C"

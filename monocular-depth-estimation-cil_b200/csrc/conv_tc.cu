@@ -43,6 +43,7 @@ struct ConvArgs {
   bf16* out2; long long out2_ld;
   const float* bias;
   const bf16* res; long long res_ld;
+  const bf16* resb; long long resb_ld;
   int relu, relu2;
   float* stats;  // [gridDim.x][2][Cout] or null
 };
@@ -240,6 +241,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             v[2 * j + 1] += __high2float(h);
           }
         }
+        if (a.resb && valid) {
+          const uint4* rp = reinterpret_cast<const uint4*>(a.resb + pix * a.resb_ld + n0);
+          uint4 r0 = __ldg(rp);
+          uint4 r1 = nvalid > 8 ? __ldg(rp + 1) : make_uint4(0, 0, 0, 0);
+          const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
+            v[2 * j] += __low2float(h);
+            v[2 * j + 1] += __high2float(h);
+          }
+        }
         if (a.stats) {
           float sv[16], sq[16];
 #pragma unroll
@@ -367,15 +380,16 @@ int dp_conv2d_tc_grid(int B, int H, int W, int Cin, int Cout, int KS) {
 }
 
 int dp_conv2d_tc(const void* x, long long x_ld, int B, int H, int W, int Cin, const void* w_packed, int Cin_p,
-                 int Cout, int KS, const float* bias, const void* residual, long long res_ld, int relu, void* out,
-                 long long out_ld, void* out2, long long out2_ld, int relu2, float* stats_partials,
-                 cudaStream_t stream) {
+                 int Cout, int KS, const float* bias, const void* residual, long long res_ld, const void* residual2,
+                 long long res2_ld, int relu, void* out, long long out_ld, void* out2, long long out2_ld, int relu2,
+                 float* stats_partials, cudaStream_t stream) {
   DP_CHECK_ARG(x && w_packed && (out || out2), "dp_conv2d_tc: null pointer");
   DP_CHECK_ARG(KS == 3 || KS == 1, "dp_conv2d_tc: kernel size %d (only 1 and 3, stride 1)", KS);
   DP_CHECK_ARG(Cin % 8 == 0 && Cout % 8 == 0 && Cin_p % 8 == 0 && Cin_p >= Cin,
                "dp_conv2d_tc: channels must be multiples of 8 (Cin %d Cin_p %d Cout %d)", Cin, Cin_p, Cout);
   DP_CHECK_ARG(x_ld % 8 == 0 && (!out || out_ld % 8 == 0) && (!out2 || out2_ld % 8 == 0) &&
-               (!residual || res_ld % 8 == 0), "dp_conv2d_tc: pixel strides must be multiples of 8 elements");
+               (!residual || res_ld % 8 == 0) && (!residual2 || res2_ld % 8 == 0),
+               "dp_conv2d_tc: pixel strides must be multiples of 8 elements");
   DP_CHECK_ARG(B > 0 && H > 0 && W > 0, "dp_conv2d_tc: bad shape");
   Plan p;
   int rc = make_plan(p, B, H, W, Cin, Cout, KS, stats_partials != nullptr);
@@ -385,6 +399,7 @@ int dp_conv2d_tc(const void* x, long long x_ld, int B, int H, int W, int Cin, co
   a.out2 = reinterpret_cast<bf16*>(out2); a.out2_ld = out2_ld;
   a.bias = bias;
   a.res = reinterpret_cast<const bf16*>(residual); a.res_ld = res_ld;
+  a.resb = reinterpret_cast<const bf16*>(residual2); a.resb_ld = res2_ld;
   a.relu = relu; a.relu2 = relu2;
   a.stats = stats_partials;
 

@@ -1,0 +1,550 @@
+// Bandwidth-bound NHWC bf16 kernels around the tensor-core convolutions: ReLU backward masks, bilinear
+// resize (both align_corners conventions) forward/backward, train/eval BatchNorm finalize / apply /
+// backward, per-channel sums.  All vectorised 8 channels (16 bytes) per thread, coalesced along channels.
+//
+// Reference arithmetic: nn.ReLU / F.interpolate(mode="bilinear") (blocks.py:226-238, 432-434; dpt_depth.py:147;
+// midas_semantics.py:233,243), nn.BatchNorm2d in train and eval mode (midas_semantics.py:40-61,133-151,196).
+#include "common.cuh"
+#include "../../include/depth_b200.h"
+
+namespace {
+
+using namespace dp;
+
+struct bf8 { uint4 u; };
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+    f[2 * i] = __low2float(h);
+    f[2 * i + 1] = __high2float(h);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ uint4 ld8(const bf16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void st8(bf16* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+
+inline int grid_for(size_t items, int tpb = 256, int max_waves = 8) {
+  size_t b = (items + tpb - 1) / tpb;
+  size_t cap = (size_t)max_waves * kNumSMs;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// out = (ga ? ga : 0) + (gb ? gb * (y > 0) : 0)            (vectors of 8)
+__global__ void add_relu_bwd_kernel(const bf16* __restrict__ ga, const bf16* __restrict__ gb, const bf16* __restrict__ y,
+                                    bf16* __restrict__ out, size_t n8) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    float a[8], b[8], yy[8], o[8];
+    if (ga) unpack8(ld8(ga + i * 8), a);
+    if (gb) { unpack8(ld8(gb + i * 8), b); unpack8(ld8(y + i * 8), yy); }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (ga ? a[j] : 0.f) + (gb ? (yy[j] > 0.f ? b[j] : 0.f) : 0.f);
+    st8(out + i * 8, pack8(o));
+  }
+}
+
+__global__ void relu_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, size_t n8) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    float v[8];
+    unpack8(ld8(x + i * 8), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    st8(out + i * 8, pack8(v));
+  }
+}
+
+// out = a + b (+ c)
+__global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, const bf16* __restrict__ c,
+                           bf16* __restrict__ out, size_t n8) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    float x[8], y[8], z[8], o[8];
+    unpack8(ld8(a + i * 8), x);
+    unpack8(ld8(b + i * 8), y);
+    if (c) unpack8(ld8(c + i * 8), z);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = x[j] + y[j] + (c ? z[j] : 0.f);
+    st8(out + i * 8, pack8(o));
+  }
+}
+
+// dst[p][0..C) = src[p][0..C) with independent pixel strides (channel concat / slice copies)
+__global__ void copy_channels_kernel(const bf16* __restrict__ src, long long src_ld, bf16* __restrict__ dst,
+                                     long long dst_ld, size_t npix, int C8) {
+  const size_t total = npix * C8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    const size_t p = i / C8;
+    st8(dst + p * dst_ld + c8 * 8, ld8(src + p * src_ld + c8 * 8));
+  }
+}
+
+// ---- bilinear resize ------------------------------------------------------------------------------------
+// source coordinate of output index o (PyTorch upsample_bilinear2d semantics)
+__device__ __forceinline__ float src_coord(int o, float scale, int align) {
+  if (align) return scale * o;
+  float s = scale * (o + 0.5f) - 0.5f;
+  return s < 0.f ? 0.f : s;
+}
+__host__ __device__ inline float resize_scale(int in, int out, int align) {
+  if (align) return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+  return (float)in / (float)out;
+}
+
+__global__ void resize_fwd_kernel(const bf16* __restrict__ src, long long src_ld, int B, int Hi, int Wi, int C,
+                                  bf16* __restrict__ dst, long long dst_ld, int Ho, int Wo, int align) {
+  const int C8 = C / 8;
+  const size_t total = (size_t)B * Ho * Wo * C8;
+  const float sy = resize_scale(Hi, Ho, align), sx = resize_scale(Wi, Wo, align);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    size_t p = i / C8;
+    const int ox = (int)(p % Wo); p /= Wo;
+    const int oy = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    const float fy = src_coord(oy, sy, align), fx = src_coord(ox, sx, align);
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < Hi - 1 ? 1 : 0), x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
+    const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
+    const bf16* s = src + (size_t)b * Hi * Wi * src_ld + c8 * 8;
+    float a[8], bq[8], c[8], d[8], o[8];
+    unpack8(ld8(s + ((size_t)y0 * Wi + x0) * src_ld), a);
+    unpack8(ld8(s + ((size_t)y0 * Wi + x1) * src_ld), bq);
+    unpack8(ld8(s + ((size_t)y1 * Wi + x0) * src_ld), c);
+    unpack8(ld8(s + ((size_t)y1 * Wi + x1) * src_ld), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = hy * (hx * a[j] + lx * bq[j]) + ly * (hx * c[j] + lx * d[j]);
+    st8(dst + (((size_t)b * Ho + oy) * Wo + ox) * dst_ld + c8 * 8, pack8(o));
+  }
+}
+
+// fp32 variant for the (B,3,H,W) RGB -> DINOv2 input resize and the (B,1,H,W) prediction resize (NCHW planes)
+__global__ void resize_planes_f32_kernel(const float* __restrict__ src, int planes, int Hi, int Wi,
+                                         float* __restrict__ dst, int Ho, int Wo, int align) {
+  const size_t total = (size_t)planes * Ho * Wo;
+  const float sy = resize_scale(Hi, Ho, align), sx = resize_scale(Wi, Wo, align);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % Wo);
+    const int oy = (int)((i / Wo) % Ho);
+    const size_t pl = i / ((size_t)Wo * Ho);
+    const float fy = src_coord(oy, sy, align), fx = src_coord(ox, sx, align);
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < Hi - 1 ? 1 : 0), x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
+    const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
+    const float* s = src + pl * Hi * Wi;
+    dst[i] = hy * (hx * __ldg(s + (size_t)y0 * Wi + x0) + lx * __ldg(s + (size_t)y0 * Wi + x1)) +
+             ly * (hx * __ldg(s + (size_t)y1 * Wi + x0) + lx * __ldg(s + (size_t)y1 * Wi + x1));
+  }
+}
+
+// Backward as a gather: input pixel (iy,ix) collects from every output pixel whose 2x2 footprint touches it.
+// The candidate output range is found by inverting the coordinate map with one pixel of slack, then
+// each candidate re-derives its own (y0,y1,ly) exactly as the forward pass did - deterministic, no atomics.
+__device__ __forceinline__ void out_range(int i, int in, int out, float scale, int align, int& lo, int& hi) {
+  // outputs o with floor(src(o)) in {i-1, i}
+  float inv = scale > 0.f ? 1.f / scale : 0.f;
+  float a = align ? (i - 1) * inv : ((i - 1) + 0.5f) * inv - 0.5f;
+  float b = align ? (i + 1) * inv : ((i + 1) + 0.5f) * inv - 0.5f;
+  lo = (int)floorf(a) - 1;
+  hi = (int)ceilf(b) + 1;
+  if (scale <= 0.f) { lo = 0; hi = out - 1; }
+  if (lo < 0) lo = 0;
+  if (hi > out - 1) hi = out - 1;
+  (void)in;
+}
+
+__global__ void resize_bwd_kernel(const bf16* __restrict__ gout, long long g_ld, int B, int Hi, int Wi, int C,
+                                  bf16* __restrict__ gin, long long gin_ld, int Ho, int Wo, int align) {
+  const int C8 = C / 8;
+  const size_t total = (size_t)B * Hi * Wi * C8;
+  const float sy = resize_scale(Hi, Ho, align), sx = resize_scale(Wi, Wo, align);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    size_t p = i / C8;
+    const int ix = (int)(p % Wi); p /= Wi;
+    const int iy = (int)(p % Hi);
+    const int b = (int)(p / Hi);
+    int oy_lo, oy_hi, ox_lo, ox_hi;
+    out_range(iy, Hi, Ho, sy, align, oy_lo, oy_hi);
+    out_range(ix, Wi, Wo, sx, align, ox_lo, ox_hi);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const bf16* g = gout + (size_t)b * Ho * Wo * g_ld + c8 * 8;
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+      const float fy = src_coord(oy, sy, align);
+      const int y0 = (int)fy;
+      const int y1 = y0 + (y0 < Hi - 1 ? 1 : 0);
+      const float ly = fy - y0;
+      float wy = 0.f;
+      if (y0 == iy) wy += 1.f - ly;
+      if (y1 == iy) wy += ly;
+      if (wy == 0.f) continue;
+      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+        const float fx = src_coord(ox, sx, align);
+        const int x0 = (int)fx;
+        const int x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
+        const float lx = fx - x0;
+        float wx = 0.f;
+        if (x0 == ix) wx += 1.f - lx;
+        if (x1 == ix) wx += lx;
+        if (wx == 0.f) continue;
+        float v[8];
+        unpack8(ld8(g + ((size_t)oy * Wo + ox) * g_ld), v);
+        const float w = wy * wx;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += w * v[j];
+      }
+    }
+    st8(gin + (((size_t)b * Hi + iy) * Wi + ix) * gin_ld + c8 * 8, pack8(acc));
+  }
+}
+
+// ---- per-channel reductions over pixels --------------------------------------------------------------------
+// MODE 0: sum x                              -> out[0][C]
+// MODE 1: sum x, sum x^2                     -> out[0..1][C]                 (BN statistics from a stored tensor)
+// MODE 2: g = dy * (mask ? mask>0 : 1); sum g, sum g*x   -> out[0..1][C]     (BN backward)
+constexpr int RED_TPB = 256;
+template <int MODE>
+__global__ void __launch_bounds__(RED_TPB) chan_reduce_kernel(const bf16* __restrict__ x, long long x_ld,
+                                                              const bf16* __restrict__ dy, long long dy_ld,
+                                                              const bf16* __restrict__ mask, long long m_ld,
+                                                              size_t npix, int C, float* __restrict__ partial) {
+  extern __shared__ float sred[];  // [2][lanes][C]
+  const int C8 = C / 8;
+  const int lanes = RED_TPB / C8;  // pixel lanes per block (C8 <= 64 -> lanes >= 4); threads beyond lanes*C8 idle
+  const int c8 = threadIdx.x % C8, pl = threadIdx.x / C8;
+  float s0[8], s1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s0[j] = 0.f; s1[j] = 0.f; }
+  if (pl < lanes) {
+    for (size_t p = (size_t)blockIdx.x * lanes + pl; p < npix; p += (size_t)gridDim.x * lanes) {
+      float xv[8], g[8];
+      if (MODE != 2 || x) unpack8(ld8(x + p * x_ld + c8 * 8), xv);
+      if (MODE == 2) {
+        unpack8(ld8(dy + p * dy_ld + c8 * 8), g);
+        if (mask) {
+          float m[8];
+          unpack8(ld8(mask + p * m_ld + c8 * 8), m);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] = m[j] > 0.f ? g[j] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (MODE == 0) s0[j] += xv[j];
+        if (MODE == 1) { s0[j] += xv[j]; s1[j] += xv[j] * xv[j]; }
+        if (MODE == 2) { s0[j] += g[j]; s1[j] += g[j] * xv[j]; }
+      }
+    }
+  }
+  if (pl < lanes) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sred[(0 * lanes + pl) * C + c8 * 8 + j] = s0[j];
+      if (MODE != 0) sred[(1 * lanes + pl) * C + c8 * 8 + j] = s1[j];
+    }
+  }
+  __syncthreads();
+  const int nout = (MODE == 0 ? 1 : 2) * C;
+  for (int i = threadIdx.x; i < nout; i += RED_TPB) {
+    const int which = i / C, c = i - which * C;
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += sred[(which * lanes + l) * C + c];
+    partial[((size_t)blockIdx.x * 2 + which) * C + c] = s;
+  }
+}
+
+// BatchNorm2d finalize (train): partial[nparts][2][C] (sum, sumsq over `count` values per channel) ->
+//   scale_shift[0][C] = gamma*invstd, [1][C] = beta - mean*gamma*invstd, save[0][C]=mean, save[1][C]=invstd;
+//   running stats updated with momentum (unbiased variance), num_batches_tracked += 1.
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int nparts, int C, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   long long* __restrict__ num_batches, float* __restrict__ scale_shift,
+                                   float* __restrict__ save) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && num_batches) *num_batches += 1;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int p = 0; p < nparts; ++p) {
+    s += (double)partial[((size_t)p * 2 + 0) * C + c];
+    q += (double)partial[((size_t)p * 2 + 1) * C + c];
+  }
+  const double mean = s / count;
+  double var = q / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  scale_shift[c] = g * invstd;
+  scale_shift[C + c] = b - (float)mean * g * invstd;
+  save[c] = (float)mean;
+  save[C + c] = invstd;
+  if (running_mean) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// eval mode: scale/shift from running statistics
+__global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ rm, const float* __restrict__ rv, float eps, int C,
+                                      float* __restrict__ scale_shift, float* __restrict__ save) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float invstd = 1.f / sqrtf(rv[c] + eps);
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  scale_shift[c] = g * invstd;
+  scale_shift[C + c] = b - rm[c] * g * invstd;
+  save[c] = rm[c];
+  save[C + c] = invstd;
+}
+
+// y = act( x*scale + shift  [+ x2*scale2 + shift2 | + res] )
+__global__ void bn_apply_kernel(const bf16* __restrict__ x, long long x_ld, const float* __restrict__ ss,
+                                const bf16* __restrict__ x2, long long x2_ld, const float* __restrict__ ss2,
+                                const bf16* __restrict__ res, long long res_ld, size_t npix, int C, int relu,
+                                bf16* __restrict__ y, long long y_ld) {
+  const int C8 = C / 8;
+  const size_t total = npix * C8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    const size_t p = i / C8;
+    float v[8], o[8];
+    unpack8(ld8(x + p * x_ld + c8 * 8), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = v[j] * __ldg(ss + c8 * 8 + j) + __ldg(ss + C + c8 * 8 + j);
+    if (x2) {
+      unpack8(ld8(x2 + p * x2_ld + c8 * 8), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += v[j] * __ldg(ss2 + c8 * 8 + j) + __ldg(ss2 + C + c8 * 8 + j);
+    }
+    if (res) {
+      unpack8(ld8(res + p * res_ld + c8 * 8), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += v[j];
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+    }
+    st8(y + p * y_ld + c8 * 8, pack8(o));
+  }
+}
+
+// BN backward apply: g = dy*(mask>0);  train: dx = gamma*invstd*(g - sum_g/N - xhat*sum_gxhat/N);  eval: gamma*invstd*g
+// red[0][C] = sum g, red[1][C] = sum g*x (raw x): sum_gxhat = invstd*(red1 - mean*red0).
+// Also writes dgamma = sum_gxhat, dbeta = sum g (by block 0), and optionally gmask = g (the masked upstream grad,
+// which is also the gradient of an identity shortcut / residual).
+__global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dy, long long dy_ld, const bf16* __restrict__ mask,
+                                    long long m_ld, const bf16* __restrict__ x, long long x_ld,
+                                    const float* __restrict__ red, const float* __restrict__ save,
+                                    const float* __restrict__ gamma, double count, int train, size_t npix, int C,
+                                    bf16* __restrict__ dx, long long dx_ld, bf16* __restrict__ gmask, long long gm_ld,
+                                    float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
+  const int C8 = C / 8;
+  const size_t total = npix * C8;
+  if (blockIdx.x == 0 && dgamma) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const float mean = save[c], invstd = save[C + c];
+      const float dg = invstd * (red[C + c] - mean * red[c]);
+      dgamma[c] = accumulate ? dgamma[c] + dg : dg;
+      dbeta[c] = accumulate ? dbeta[c] + red[c] : red[c];
+    }
+  }
+  const float invN = (float)(1.0 / count);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    const size_t p = i / C8;
+    float g[8], xv[8], o[8];
+    unpack8(ld8(dy + p * dy_ld + c8 * 8), g);
+    if (mask) {
+      float m[8];
+      unpack8(ld8(mask + p * m_ld + c8 * 8), m);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = m[j] > 0.f ? g[j] : 0.f;
+    }
+    if (gmask) st8(gmask + p * gm_ld + c8 * 8, pack8(g));
+    if (dx) {
+      unpack8(ld8(x + p * x_ld + c8 * 8), xv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c8 * 8 + j;
+        const float mean = __ldg(save + c), invstd = __ldg(save + C + c);
+        const float gm = gamma ? __ldg(gamma + c) : 1.f;
+        if (train) {
+          const float sg = __ldg(red + c), sgx = __ldg(red + C + c);
+          const float xhat = (xv[j] - mean) * invstd;
+          const float sgxh = invstd * (sgx - mean * sg);
+          o[j] = gm * invstd * (g[j] - sg * invN - xhat * sgxh * invN);
+        } else {
+          o[j] = gm * invstd * g[j];
+        }
+      }
+      st8(dx + p * dx_ld + c8 * 8, pack8(o));
+    }
+  }
+}
+
+__global__ void sum_partials_kernel(const float* __restrict__ partial, int nparts, int rows, int C,
+                                    float* __restrict__ out, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  const int which = i / C, c = i - which * C;
+  double s = 0.0;
+  for (int p = 0; p < nparts; ++p) s += (double)partial[((size_t)p * 2 + which) * C + c];
+  out[i] = accumulate ? out[i] + (float)s : (float)s;
+}
+
+constexpr int kRedBlocks = 2 * kNumSMs;
+
+}  // namespace
+
+extern "C" {
+
+int dp_add_relu_bwd(const void* g_raw, const void* g_relu, const void* y, void* out, size_t n, cudaStream_t stream) {
+  DP_CHECK_ARG(out && (g_raw || g_relu) && (!g_relu || y) && n % 8 == 0, "dp_add_relu_bwd: bad arguments");
+  if (n == 0) return DP_OK;
+  add_relu_bwd_kernel<<<grid_for(n / 8), 256, 0, stream>>>((const bf16*)g_raw, (const bf16*)g_relu, (const bf16*)y,
+                                                           (bf16*)out, n / 8);
+  DP_CHECK_LAUNCH("add_relu_bwd_kernel");
+  return DP_OK;
+}
+
+int dp_relu_bf16(const void* x, void* out, size_t n, cudaStream_t stream) {
+  DP_CHECK_ARG(x && out && n % 8 == 0, "dp_relu_bf16: bad arguments");
+  if (n == 0) return DP_OK;
+  relu_kernel<<<grid_for(n / 8), 256, 0, stream>>>((const bf16*)x, (bf16*)out, n / 8);
+  DP_CHECK_LAUNCH("relu_kernel");
+  return DP_OK;
+}
+
+int dp_add_bf16(const void* a, const void* b, const void* c, void* out, size_t n, cudaStream_t stream) {
+  DP_CHECK_ARG(a && b && out && n % 8 == 0, "dp_add_bf16: bad arguments");
+  if (n == 0) return DP_OK;
+  add_kernel<<<grid_for(n / 8), 256, 0, stream>>>((const bf16*)a, (const bf16*)b, (const bf16*)c, (bf16*)out, n / 8);
+  DP_CHECK_LAUNCH("add_kernel");
+  return DP_OK;
+}
+
+int dp_copy_channels(const void* src, long long src_ld, void* dst, long long dst_ld, size_t npix, int C,
+                     cudaStream_t stream) {
+  DP_CHECK_ARG(src && dst && C % 8 == 0 && src_ld % 8 == 0 && dst_ld % 8 == 0, "dp_copy_channels: bad arguments");
+  if (npix == 0) return DP_OK;
+  copy_channels_kernel<<<grid_for(npix * (C / 8)), 256, 0, stream>>>((const bf16*)src, src_ld, (bf16*)dst, dst_ld, npix, C / 8);
+  DP_CHECK_LAUNCH("copy_channels_kernel");
+  return DP_OK;
+}
+
+int dp_resize_bilinear_nhwc(const void* src, long long src_ld, int B, int Hi, int Wi, int C, void* dst,
+                            long long dst_ld, int Ho, int Wo, int align_corners, cudaStream_t stream) {
+  DP_CHECK_ARG(src && dst && C % 8 == 0 && src_ld % 8 == 0 && dst_ld % 8 == 0, "dp_resize_bilinear_nhwc: bad arguments");
+  const size_t items = (size_t)B * Ho * Wo * (C / 8);
+  resize_fwd_kernel<<<grid_for(items), 256, 0, stream>>>((const bf16*)src, src_ld, B, Hi, Wi, C, (bf16*)dst, dst_ld, Ho,
+                                                         Wo, align_corners);
+  DP_CHECK_LAUNCH("resize_fwd_kernel");
+  return DP_OK;
+}
+
+int dp_resize_bilinear_nhwc_bwd(const void* gout, long long g_ld, int B, int Hi, int Wi, int C, void* gin,
+                                long long gin_ld, int Ho, int Wo, int align_corners, cudaStream_t stream) {
+  DP_CHECK_ARG(gout && gin && C % 8 == 0 && g_ld % 8 == 0 && gin_ld % 8 == 0, "dp_resize_bilinear_nhwc_bwd: bad arguments");
+  const size_t items = (size_t)B * Hi * Wi * (C / 8);
+  resize_bwd_kernel<<<grid_for(items), 256, 0, stream>>>((const bf16*)gout, g_ld, B, Hi, Wi, C, (bf16*)gin, gin_ld, Ho,
+                                                         Wo, align_corners);
+  DP_CHECK_LAUNCH("resize_bwd_kernel");
+  return DP_OK;
+}
+
+int dp_resize_bilinear_planes_f32(const float* src, int planes, int Hi, int Wi, float* dst, int Ho, int Wo,
+                                  int align_corners, cudaStream_t stream) {
+  DP_CHECK_ARG(src && dst && planes > 0, "dp_resize_bilinear_planes_f32: bad arguments");
+  const size_t items = (size_t)planes * Ho * Wo;
+  resize_planes_f32_kernel<<<grid_for(items), 256, 0, stream>>>(src, planes, Hi, Wi, dst, Ho, Wo, align_corners);
+  DP_CHECK_LAUNCH("resize_planes_f32_kernel");
+  return DP_OK;
+}
+
+int dp_chan_reduce_blocks(void) { return kRedBlocks; }
+
+/* mode 0: sum x; 1: sum x, sum x^2; 2: sum g, sum g*x with g = dy*(mask>0).  partial: float[dp_chan_reduce_blocks()][2][C] */
+int dp_chan_reduce(int mode, const void* x, long long x_ld, const void* dy, long long dy_ld, const void* mask,
+                   long long m_ld, size_t npix, int C, float* partial, cudaStream_t stream) {
+  DP_CHECK_ARG(partial && C % 8 == 0 && C <= 512 && mode >= 0 && mode <= 2, "dp_chan_reduce: bad arguments");
+  DP_CHECK_ARG(mode == 2 ? (dy != nullptr && x != nullptr) : (x != nullptr), "dp_chan_reduce: null input");
+  const int C8 = C / 8;
+  const int lanes = RED_TPB / C8;
+  const size_t smem = (size_t)2 * lanes * C * sizeof(float);
+  if (mode == 0)
+    chan_reduce_kernel<0><<<kRedBlocks, RED_TPB, smem, stream>>>((const bf16*)x, x_ld, nullptr, 0, nullptr, 0, npix, C, partial);
+  else if (mode == 1)
+    chan_reduce_kernel<1><<<kRedBlocks, RED_TPB, smem, stream>>>((const bf16*)x, x_ld, nullptr, 0, nullptr, 0, npix, C, partial);
+  else
+    chan_reduce_kernel<2><<<kRedBlocks, RED_TPB, smem, stream>>>((const bf16*)x, x_ld, (const bf16*)dy, dy_ld,
+                                                                 (const bf16*)mask, m_ld, npix, C, partial);
+  DP_CHECK_LAUNCH("chan_reduce_kernel");
+  return DP_OK;
+}
+
+int dp_sum_partials(const float* partial, int nparts, int rows, int C, float* out, int accumulate, cudaStream_t stream) {
+  DP_CHECK_ARG(partial && out && rows >= 1 && rows <= 2, "dp_sum_partials: bad arguments");
+  sum_partials_kernel<<<dp::ceil_div(rows * C, 128), 128, 0, stream>>>(partial, nparts, rows, C, out, accumulate);
+  DP_CHECK_LAUNCH("sum_partials_kernel");
+  return DP_OK;
+}
+
+int dp_bn_finalize(const float* partial, int nparts, int C, double count, const float* gamma, const float* beta,
+                   float eps, float momentum, float* running_mean, float* running_var, long long* num_batches_tracked,
+                   float* scale_shift, float* save_mean_invstd, cudaStream_t stream) {
+  DP_CHECK_ARG(partial && scale_shift && save_mean_invstd && C > 0 && count > 0, "dp_bn_finalize: bad arguments");
+  bn_finalize_kernel<<<dp::ceil_div(C, 128), 128, 0, stream>>>(partial, nparts, C, count, gamma, beta, eps, momentum,
+                                                               running_mean, running_var, num_batches_tracked,
+                                                               scale_shift, save_mean_invstd);
+  DP_CHECK_LAUNCH("bn_finalize_kernel");
+  return DP_OK;
+}
+
+int dp_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                      float eps, int C, float* scale_shift, float* save_mean_invstd, cudaStream_t stream) {
+  DP_CHECK_ARG(running_mean && running_var && scale_shift && save_mean_invstd, "dp_bn_eval_coeffs: null pointer");
+  bn_eval_coeffs_kernel<<<dp::ceil_div(C, 128), 128, 0, stream>>>(gamma, beta, running_mean, running_var, eps, C,
+                                                                  scale_shift, save_mean_invstd);
+  DP_CHECK_LAUNCH("bn_eval_coeffs_kernel");
+  return DP_OK;
+}
+
+int dp_bn_apply(const void* x, long long x_ld, const float* scale_shift, const void* x2, long long x2_ld,
+                const float* scale_shift2, const void* res, long long res_ld, size_t npix, int C, int relu, void* y,
+                long long y_ld, cudaStream_t stream) {
+  DP_CHECK_ARG(x && scale_shift && y && C % 8 == 0 && (!x2 || scale_shift2), "dp_bn_apply: bad arguments");
+  bn_apply_kernel<<<grid_for(npix * (C / 8)), 256, 0, stream>>>((const bf16*)x, x_ld, scale_shift, (const bf16*)x2, x2_ld,
+                                                                scale_shift2, (const bf16*)res, res_ld, npix, C, relu,
+                                                                (bf16*)y, y_ld);
+  DP_CHECK_LAUNCH("bn_apply_kernel");
+  return DP_OK;
+}
+
+int dp_bn_bwd_apply(const void* dy, long long dy_ld, const void* mask, long long m_ld, const void* x, long long x_ld,
+                    const float* red, const float* save_mean_invstd, const float* gamma, double count, int train,
+                    size_t npix, int C, void* dx, long long dx_ld, void* gmask, long long gm_ld, float* dgamma,
+                    float* dbeta, int accumulate, cudaStream_t stream) {
+  DP_CHECK_ARG(dy && C % 8 == 0 && (dx || gmask), "dp_bn_bwd_apply: bad arguments");
+  DP_CHECK_ARG(!dx || (x && save_mean_invstd && (!train || red)), "dp_bn_bwd_apply: missing statistics");
+  DP_CHECK_ARG(!dgamma || (dbeta && red && save_mean_invstd), "dp_bn_bwd_apply: dgamma needs dbeta, red and save");
+  bn_bwd_apply_kernel<<<grid_for(npix * (C / 8)), 256, 0, stream>>>(
+      (const bf16*)dy, dy_ld, (const bf16*)mask, m_ld, (const bf16*)x, x_ld, red, save_mean_invstd, gamma, count, train,
+      npix, C, (bf16*)dx, dx_ld, (bf16*)gmask, gm_ld, dgamma, dbeta, accumulate);
+  DP_CHECK_LAUNCH("bn_bwd_apply_kernel");
+  return DP_OK;
+}
+
+}  // extern "C"

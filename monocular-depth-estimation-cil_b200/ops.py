@@ -1,0 +1,692 @@
+"""Autograd-aware host wrappers over the C ABI (include/depth_b200.h).
+
+Activations on this path are NHWC bf16 torch tensors of shape (B, H, W, C) whose last dim is contiguous
+(a channel slice of a wider buffer is allowed: the pixel stride `ld` is taken from the tensor strides).
+Every function here launches hand-written sm_100a kernels; torch only owns memory, streams and the
+autograd tape.  Nothing falls back to ATen for the arithmetic.
+"""
+import weakref
+
+import torch
+
+from . import _lib as L
+
+BF16 = torch.bfloat16
+
+
+# --------------------------------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------------------------------
+def _ld(x):
+    """pixel stride (elements) of an NHWC view; validates the layout."""
+    B, H, W, C = x.shape
+    assert x.dtype == BF16 and x.is_cuda, "NHWC bf16 CUDA tensor expected"
+    assert x.stride(3) == 1, "channels must be contiguous"
+    ld = x.stride(2) if W > 1 else (x.stride(1) if H > 1 else max(x.stride(0), C))
+    if W > 1 and H > 1:
+        assert x.stride(1) == W * ld, "rows must be densely packed"
+    if B > 1 and H * W > 1:
+        assert x.stride(0) == H * W * ld, "images must be densely packed"
+    assert ld % 8 == 0 and x.data_ptr() % 16 == 0, "pixel stride / base must be 16-byte aligned"
+    return ld
+
+
+def _nhwc(B, H, W, C, dev):
+    return torch.empty(B, H, W, C, dtype=BF16, device=dev)
+
+
+def _dense(t):
+    """gradient tensors arrive with arbitrary strides: make them dense NHWC bf16."""
+    if t is None:
+        return None
+    if t.dtype != BF16:
+        t = t.to(BF16)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class _PackCache:
+    """bf16 kernel-layout copies of fp32 parameters, refreshed when the parameter changes in place."""
+
+    def __init__(self):
+        self.store = {}
+
+    def get(self, w, swap, flip):
+        key = (id(w), swap, flip)
+        ver = (w._version, w.data_ptr(), tuple(w.shape))
+        hit = self.store.get(key)
+        if hit is not None and hit[0] == ver and hit[2]() is w:
+            return hit[1]
+        D0, D1, KH, KW = w.shape
+        A, Bc = (D1, D0) if swap else (D0, D1)
+        dst = torch.empty(KH * KW, A, Bc, dtype=BF16, device=w.device)
+        src = w.detach()
+        if src.dtype != torch.float32 or not src.is_contiguous():
+            src = src.float().contiguous()
+        L.check(L.lib().dp_pack_conv_weight(L.ptr(src), D0, D1, KH, KW, int(swap), int(flip), L.ptr(dst), Bc, L.stream()))
+        self.store[key] = (ver, dst, weakref.ref(w))
+        if len(self.store) > 4096:
+            self.store.clear()
+        return dst
+
+
+PACKS = _PackCache()
+
+
+def _f32(p):
+    if p is None:
+        return None
+    d = p.detach()
+    return d if (d.dtype == torch.float32 and d.is_contiguous()) else d.float().contiguous()
+
+
+def _colsum(g):
+    """per-channel sum over pixels of a dense NHWC bf16 tensor -> fp32 [C]"""
+    C = g.shape[-1]
+    npix = g.numel() // C
+    nb = L.lib().dp_chan_reduce_blocks()
+    part = torch.empty(nb, 2, C, dtype=torch.float32, device=g.device)
+    L.check(L.lib().dp_chan_reduce(0, L.ptr(g), C, None, 0, None, 0, npix, C, L.ptr(part), L.stream()))
+    out = torch.empty(C, dtype=torch.float32, device=g.device)
+    L.check(L.lib().dp_sum_partials(L.ptr(part), nb, 1, C, L.ptr(out), 0, L.stream()))
+    return out
+
+
+def _mask_grad(g_raw, g_relu, y):
+    """g_raw + g_relu * (y > 0) (either may be None)."""
+    if g_relu is None:
+        return _dense(g_raw)
+    g_raw, g_relu = _dense(g_raw), _dense(g_relu)
+    out = torch.empty(y.shape, dtype=BF16, device=y.device)
+    yd = y if y.is_contiguous() else y.contiguous()
+    L.check(L.lib().dp_add_relu_bwd(L.ptr(g_raw), L.ptr(g_relu), L.ptr(yd), L.ptr(out), out.numel(), L.stream()))
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# layout boundaries
+# --------------------------------------------------------------------------------------------------
+class _ToNHWC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        B, C, H, W = x.shape
+        ctx.shape = x.shape
+        xs = x.detach()
+        if xs.dtype != torch.float32 or not xs.is_contiguous():
+            xs = xs.float().contiguous()
+        out = _nhwc(B, H, W, C, x.device)
+        L.check(L.lib().dp_nchw_f32_to_nhwc_bf16(L.ptr(xs), B, C, H, W, L.ptr(out), C, L.stream()))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, C, H, W = ctx.shape
+        g = _dense(g)
+        out = torch.empty(B, C, H, W, dtype=torch.float32, device=g.device)
+        L.check(L.lib().dp_nhwc_bf16_to_nchw_f32(L.ptr(g), C, B, C, H, W, L.ptr(out), L.stream()))
+        return out
+
+
+class _ToNCHW(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        B, H, W, C = x.shape
+        ld = _ld(x)
+        out = torch.empty(B, C, H, W, dtype=torch.float32, device=x.device)
+        L.check(L.lib().dp_nhwc_bf16_to_nchw_f32(L.ptr(x), ld, B, C, H, W, L.ptr(out), L.stream()))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, C, H, W = g.shape
+        gs = g if (g.dtype == torch.float32 and g.is_contiguous()) else g.float().contiguous()
+        out = _nhwc(B, H, W, C, g.device)
+        L.check(L.lib().dp_nchw_f32_to_nhwc_bf16(L.ptr(gs), B, C, H, W, L.ptr(out), C, L.stream()))
+        return out
+
+
+def to_nhwc(x):
+    """(B,C,H,W) fp32 -> (B,H,W,C) bf16"""
+    return _ToNHWC.apply(x)
+
+
+def to_nchw(x):
+    """(B,H,W,C) bf16 -> (B,C,H,W) fp32"""
+    return _ToNCHW.apply(x)
+
+
+def tokens_to_nhwc(tok, ph, pw):
+    """(B, ph*pw, C) fp32 tokens of the frozen ViT -> (B, ph, pw, C) bf16 (dpt_depth.py:122 without the permute)."""
+    B, N, C = tok.shape
+    assert N == ph * pw
+    src = tok.detach()
+    if src.dtype != torch.float32 or not src.is_contiguous():
+        src = src.float().contiguous()
+    out = _nhwc(B, ph, pw, C, tok.device)
+    L.check(L.lib().dp_cast_f32_to_bf16(L.ptr(src), L.ptr(out), src.numel(), L.stream()))
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# tensor-core convolution (3x3 s1 p1 / 1x1)
+# --------------------------------------------------------------------------------------------------
+def _conv_tc_launch(x, wp, Cout, KS, bias, res, res2, relu, out, out2, relu2, stats):
+    B, H, W, Cin = x.shape
+    L.check(L.lib().dp_conv2d_tc(
+        L.ptr(x), _ld(x), B, H, W, Cin, L.ptr(wp), wp.shape[2], Cout, KS, L.ptr(bias),
+        L.ptr(res), _ld(res) if res is not None else 0, L.ptr(res2), _ld(res2) if res2 is not None else 0,
+        int(relu), L.ptr(out), _ld(out) if out is not None else 0, L.ptr(out2), _ld(out2) if out2 is not None else 0,
+        int(relu2), L.ptr(stats), L.stream()))
+
+
+def _wgrad_tc(x, g, Cin, Cout, KS):
+    B, H, W, _ = x.shape
+    lib = L.lib()
+    nb = lib.dp_conv2d_wgrad_tc_workspace(B, H, W, Cin, Cout, KS)
+    ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
+    dw = torch.empty(Cout, Cin, KS, KS, dtype=torch.float32, device=x.device)
+    L.check(lib.dp_conv2d_wgrad_tc(L.ptr(x), _ld(x), L.ptr(g), _ld(g), B, H, W, Cin, Cout, KS, L.ptr(dw), 0, L.ptr(ws),
+                                   nb, L.stream()))
+    return dw
+
+
+class _ConvTC(torch.autograd.Function):
+    """y = conv(x, w) + b (+ res) (+ res2);  outputs: (relu ? relu(y) : y [, relu(y) copy when dual] [, BN partials])."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, res, res2, relu, dual, want_stats):
+        Cout, Cin, KS, _ = weight.shape
+        B, H, W, _ = x.shape
+        wp = PACKS.get(weight, 0, 0)
+        out = _nhwc(B, H, W, Cout, x.device)
+        out2 = _nhwc(B, H, W, Cout, x.device) if dual else None
+        stats = None
+        if want_stats:
+            g = L.lib().dp_conv2d_tc_grid(B, H, W, Cin, Cout, KS)
+            stats = torch.empty(g, 2, Cout, dtype=torch.float32, device=x.device)
+        _conv_tc_launch(x, wp, Cout, KS, _f32(bias), res, res2, relu, out, out2, True, stats)
+        ctx.relu, ctx.dual, ctx.KS = relu, dual, KS
+        ctx.save_for_backward(x, weight, out if relu else None, out2 if dual else None)
+        ctx.has = (bias is not None, res is not None, res2 is not None)
+        ctx.mark_non_differentiable(*([stats] if stats is not None else []))
+        return out, out2, stats
+
+    @staticmethod
+    def backward(ctx, gy, gy2, _gs):
+        x, weight, y_relu, y2 = ctx.saved_tensors
+        Cout, Cin, KS, _ = weight.shape
+        if ctx.relu:
+            g = _mask_grad(None, gy, y_relu)            # single ReLU'd output
+            if gy2 is not None:
+                raise RuntimeError("dual output is only defined for a raw primary output")
+        elif ctx.dual and gy2 is not None:
+            g = _mask_grad(gy, gy2, y2) if gy is not None else _mask_grad(None, gy2, y2)
+        else:
+            g = _dense(gy)
+        need = ctx.needs_input_grad
+        dx = dw = db = None
+        if need[0]:
+            wd = PACKS.get(weight, 1, 1)
+            B, H, W, _ = x.shape
+            dx = _nhwc(B, H, W, Cin, x.device)
+            _conv_tc_launch(g, wd, Cin, KS, None, None, None, False, dx, None, False, None)
+        if need[1]:
+            dw = _wgrad_tc(x, g, Cin, Cout, KS).to(weight.dtype)
+        if ctx.has[0] and need[2]:
+            db = _colsum(g)
+        dres = g if (ctx.has[1] and need[3]) else None
+        dres2 = g if (ctx.has[2] and need[4]) else None
+        return dx, dw, db, dres, dres2, None, None, None
+
+
+def conv_tc(x, weight, bias=None, res=None, res2=None, relu=False, dual=False, stats=False):
+    """3x3/s1/p1 or 1x1 conv on tcgen05.  Returns y, or (y, relu(y)) when dual, with BN partials appended when stats."""
+    y, y2, st = _ConvTC.apply(x, weight, bias, res, res2, relu, dual, stats)
+    r = (y,)
+    if dual:
+        r = r + (y2,)
+    if stats:
+        r = r + (st,)
+    return r if len(r) > 1 else y
+
+
+# --------------------------------------------------------------------------------------------------
+# strided / transposed convolutions (CUDA-core gather form)
+# --------------------------------------------------------------------------------------------------
+def _gather(inp, wp, bias, Ho, Wo, Co, KH, KW, stride, pad, transposed, relu=False):
+    B, Hi, Wi, Ci = inp.shape
+    out = _nhwc(B, Ho, Wo, Co, inp.device)
+    L.check(L.lib().dp_conv_gather(L.ptr(inp), _ld(inp), B, Hi, Wi, Ci, L.ptr(wp), L.ptr(bias), L.ptr(out), Co, Ho, Wo,
+                                   Co, KH, KW, stride, pad, int(transposed), int(relu), L.stream()))
+    return out
+
+
+def _wgrad_direct(P, T, KH, KW, stride, pad, perm):
+    B, Hp, Wp, Cp = P.shape
+    _, Ht, Wt, Ct = T.shape
+    lib = L.lib()
+    nb = lib.dp_conv_wgrad_direct_workspace(B, Hp, Wp, Cp, Ct, KH, KW)
+    ws = torch.empty(nb, dtype=torch.uint8, device=P.device)
+    out = torch.empty(Cp, Ct, KH, KW, dtype=torch.float32, device=P.device)
+    L.check(lib.dp_conv_wgrad_direct(L.ptr(P), _ld(P), Hp, Wp, Cp, L.ptr(T), _ld(T), Ht, Wt, Ct, B, KH, KW, stride, pad,
+                                     perm, L.ptr(out), 0, L.ptr(ws), nb, L.stream()))
+    return out
+
+
+class _ConvStrided(torch.autograd.Function):
+    """nn.Conv2d with stride > 1 (weight [O][I][KH][KW])."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, pad):
+        O, I, KH, KW = weight.shape
+        B, Hi, Wi, _ = x.shape
+        Ho = (Hi + 2 * pad - KH) // stride + 1
+        Wo = (Wi + 2 * pad - KW) // stride + 1
+        out = _gather(x, PACKS.get(weight, 0, 0), _f32(bias), Ho, Wo, O, KH, KW, stride, pad, False)
+        ctx.save_for_backward(x, weight)
+        ctx.geom = (stride, pad, bias is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        stride, pad, has_bias = ctx.geom
+        O, I, KH, KW = weight.shape
+        B, Hi, Wi, _ = x.shape
+        g = _dense(g)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = _gather(g, PACKS.get(weight, 1, 0), None, Hi, Wi, I, KH, KW, stride, pad, True)
+        if ctx.needs_input_grad[1]:
+            dw = _wgrad_direct(g, x, KH, KW, stride, pad, 1).to(weight.dtype)      # [O][I][KH][KW]
+        if has_bias and ctx.needs_input_grad[2]:
+            db = _colsum(g)
+        return dx, dw, db, None, None
+
+
+class _ConvTransposed(torch.autograd.Function):
+    """nn.ConvTranspose2d (weight [I][O][KH][KW], output_padding 0)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, pad):
+        I, O, KH, KW = weight.shape
+        B, Hi, Wi, _ = x.shape
+        Ho = (Hi - 1) * stride - 2 * pad + KH
+        Wo = (Wi - 1) * stride - 2 * pad + KW
+        out = _gather(x, PACKS.get(weight, 1, 0), _f32(bias), Ho, Wo, O, KH, KW, stride, pad, True)
+        ctx.save_for_backward(x, weight)
+        ctx.geom = (stride, pad, bias is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        stride, pad, has_bias = ctx.geom
+        I, O, KH, KW = weight.shape
+        B, Hi, Wi, _ = x.shape
+        g = _dense(g)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = _gather(g, PACKS.get(weight, 0, 0), None, Hi, Wi, I, KH, KW, stride, pad, False)
+        if ctx.needs_input_grad[1]:
+            dw = _wgrad_direct(x, g, KH, KW, stride, pad, 1).to(weight.dtype)      # [I][O][KH][KW]
+        if has_bias and ctx.needs_input_grad[2]:
+            db = _colsum(g)
+        return dx, dw, db, None, None
+
+
+def conv_strided(x, weight, bias, stride, pad):
+    return _ConvStrided.apply(x, weight, bias, stride, pad)
+
+
+def conv_transposed(x, weight, bias, stride, pad):
+    return _ConvTransposed.apply(x, weight, bias, stride, pad)
+
+
+# --------------------------------------------------------------------------------------------------
+# C -> 1 head conv (+bias, +ReLU) producing the fp32 (B,H,W) depth map
+# --------------------------------------------------------------------------------------------------
+class _HeadConv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        _, C, KS, _ = weight.shape
+        B, H, W, _ = x.shape
+        out = torch.empty(B, H, W, dtype=torch.float32, device=x.device)
+        L.check(L.lib().dp_head_conv_fwd(L.ptr(x), _ld(x), B, H, W, C, KS, L.ptr(_f32(weight)), L.ptr(_f32(bias)),
+                                         int(relu), L.ptr(out), L.stream()))
+        ctx.relu = relu
+        ctx.save_for_backward(x, weight, out)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight, out = ctx.saved_tensors
+        _, C, KS, _ = weight.shape
+        B, H, W, _ = x.shape
+        g = g if (g.dtype == torch.float32 and g.is_contiguous()) else g.float().contiguous()
+        lib = L.lib()
+        nb = lib.dp_head_conv_bwd_workspace(C, KS)
+        ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
+        dx = _nhwc(B, H, W, C, x.device) if ctx.needs_input_grad[0] else None
+        dw = torch.empty(1, C, KS, KS, dtype=torch.float32, device=x.device)
+        db = torch.empty(1, dtype=torch.float32, device=x.device)
+        L.check(lib.dp_head_conv_bwd(L.ptr(g), L.ptr(out), int(ctx.relu), L.ptr(x), _ld(x), B, H, W, C, KS,
+                                     L.ptr(_f32(weight)), L.ptr(dx), C, L.ptr(dw), L.ptr(db), 0, L.ptr(ws), nb, L.stream()))
+        return dx, dw.to(weight.dtype), (db if ctx.has_bias else None), None
+
+
+def head_conv(x, weight, bias, relu):
+    return _HeadConv.apply(x, weight, bias, relu)
+
+
+# --------------------------------------------------------------------------------------------------
+# bilinear resize
+# --------------------------------------------------------------------------------------------------
+class _Resize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, Ho, Wo, align):
+        B, Hi, Wi, C = x.shape
+        out = _nhwc(B, Ho, Wo, C, x.device)
+        L.check(L.lib().dp_resize_bilinear_nhwc(L.ptr(x), _ld(x), B, Hi, Wi, C, L.ptr(out), C, Ho, Wo, int(align),
+                                                L.stream()))
+        ctx.geom = (B, Hi, Wi, C, Ho, Wo, align)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, Hi, Wi, C, Ho, Wo, align = ctx.geom
+        g = _dense(g)
+        gin = _nhwc(B, Hi, Wi, C, g.device)
+        L.check(L.lib().dp_resize_bilinear_nhwc_bwd(L.ptr(g), C, B, Hi, Wi, C, L.ptr(gin), C, Ho, Wo, int(align),
+                                                    L.stream()))
+        return gin, None, None, None
+
+
+def resize(x, size, align_corners):
+    Ho, Wo = int(size[0]), int(size[1])
+    if (Ho, Wo) == tuple(x.shape[1:3]):
+        return x
+    return _Resize.apply(x, Ho, Wo, bool(align_corners))
+
+
+def resize_planes_f32(x, size, align_corners):
+    """(B,C,H,W) fp32 -> (B,C,Ho,Wo) fp32, no gradient (RGB -> frozen DINOv2 input; prediction resize in eval)."""
+    B, C, Hi, Wi = x.shape
+    Ho, Wo = int(size[0]), int(size[1])
+    src = x.detach()
+    if src.dtype != torch.float32 or not src.is_contiguous():
+        src = src.float().contiguous()
+    out = torch.empty(B, C, Ho, Wo, dtype=torch.float32, device=x.device)
+    L.check(L.lib().dp_resize_bilinear_planes_f32(L.ptr(src), B * C, Hi, Wi, L.ptr(out), Ho, Wo, int(align_corners),
+                                                  L.stream()))
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# BatchNorm2d (+ residual / second normalised branch) (+ ReLU)
+# --------------------------------------------------------------------------------------------------
+def _bn_coeffs(bn, c, stats, training):
+    """returns (scale_shift [2][C], save [2][C] = mean, invstd); updates running stats in train mode."""
+    C = c.shape[-1]
+    dev = c.device
+    lib = L.lib()
+    ss = torch.empty(2, C, dtype=torch.float32, device=dev)
+    save = torch.empty(2, C, dtype=torch.float32, device=dev)
+    gamma, beta = _f32(bn.weight), _f32(bn.bias)
+    use_batch = training or bn.running_mean is None
+    if use_batch:
+        if stats is None:
+            npix = c.numel() // C
+            nb = lib.dp_chan_reduce_blocks()
+            stats = torch.empty(nb, 2, C, dtype=torch.float32, device=dev)
+            cd = c if c.is_contiguous() else c.contiguous()
+            L.check(lib.dp_chan_reduce(1, L.ptr(cd), C, None, 0, None, 0, npix, C, L.ptr(stats), L.stream()))
+        count = float(c.numel() // C)
+        track = training and bn.track_running_stats and bn.running_mean is not None
+        mom = bn.momentum if bn.momentum is not None else 0.1
+        L.check(lib.dp_bn_finalize(L.ptr(stats), stats.shape[0], C, count, L.ptr(gamma), L.ptr(beta), bn.eps, mom,
+                                   L.ptr(bn.running_mean) if track else None, L.ptr(bn.running_var) if track else None,
+                                   L.ptr(bn.num_batches_tracked) if track else None, L.ptr(ss), L.ptr(save), L.stream()))
+    else:
+        L.check(lib.dp_bn_eval_coeffs(L.ptr(gamma), L.ptr(beta), L.ptr(bn.running_mean), L.ptr(bn.running_var), bn.eps,
+                                      C, L.ptr(ss), L.ptr(save), L.stream()))
+    return ss, save, use_batch
+
+
+class _BNAct(torch.autograd.Function):
+    """y = act( bn(c) [+ bn2(c2) | + res] ).  Parameters enter as tensors so autograd routes their grads."""
+
+    @staticmethod
+    def forward(ctx, c, gamma, beta, ss, save, c2, gamma2, beta2, ss2, save2, res, relu, train):
+        B, H, W, C = c.shape
+        npix = B * H * W
+        y = _nhwc(B, H, W, C, c.device)
+        L.check(L.lib().dp_bn_apply(L.ptr(c), _ld(c), L.ptr(ss), L.ptr(c2), _ld(c2) if c2 is not None else 0,
+                                    L.ptr(ss2), L.ptr(res), _ld(res) if res is not None else 0, npix, C, int(relu),
+                                    L.ptr(y), C, L.stream()))
+        ctx.save_for_backward(c, gamma, save, c2, gamma2, save2, y if relu else None)
+        ctx.cfg = (relu, train, res is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        c, gamma, save, c2, gamma2, save2, y = ctx.saved_tensors
+        relu, train, has_res = ctx.cfg
+        B, H, W, C = c.shape
+        npix = B * H * W
+        lib = L.lib()
+        gy = _dense(gy)
+        dev = c.device
+        nb = lib.dp_chan_reduce_blocks()
+
+        def branch(cx, gm, sv, want_gmask):
+            part = torch.empty(nb, 2, C, dtype=torch.float32, device=dev)
+            L.check(lib.dp_chan_reduce(2, L.ptr(cx), _ld(cx), L.ptr(gy), C, L.ptr(y), C, npix, C, L.ptr(part), L.stream()))
+            red = torch.empty(2, C, dtype=torch.float32, device=dev)
+            L.check(lib.dp_sum_partials(L.ptr(part), nb, 2, C, L.ptr(red), 0, L.stream()))
+            dx = _nhwc(B, H, W, C, dev)
+            gmask = _nhwc(B, H, W, C, dev) if want_gmask else None
+            dg = torch.empty(C, dtype=torch.float32, device=dev)
+            dbt = torch.empty(C, dtype=torch.float32, device=dev)
+            L.check(lib.dp_bn_bwd_apply(L.ptr(gy), C, L.ptr(y), C, L.ptr(cx), _ld(cx), L.ptr(red), L.ptr(sv),
+                                        L.ptr(_f32(gm)), float(npix), int(train), npix, C, L.ptr(dx), C, L.ptr(gmask), C,
+                                        L.ptr(dg), L.ptr(dbt), 0, L.stream()))
+            return dx, dg, dbt, gmask
+
+        dc, dg, db, gmask = branch(c, gamma, save, has_res)
+        dc2 = dg2 = db2 = None
+        if c2 is not None:
+            dc2, dg2, db2, _ = branch(c2, gamma2, save2, False)
+        return (dc, dg.to(gamma.dtype), db.to(gamma.dtype), None, None, dc2,
+                dg2.to(gamma2.dtype) if dg2 is not None else None, db2.to(gamma2.dtype) if db2 is not None else None,
+                None, None, gmask, None, None)
+
+
+def bn_act(bn, c, stats=None, relu=True, res=None, bn2=None, c2=None, stats2=None):
+    """train/eval nn.BatchNorm2d on NHWC bf16 `c` (+ residual, or + a second normalised branch), optional ReLU."""
+    training = bn.training
+    ss, save, used_batch = _bn_coeffs(bn, c, stats, training)
+    ss2 = save2 = g2 = b2 = None
+    if bn2 is not None:
+        ss2, save2, _ = _bn_coeffs(bn2, c2, stats2, bn2.training)
+        g2, b2 = bn2.weight, bn2.bias
+    return _BNAct.apply(c, bn.weight, bn.bias, ss, save, c2, g2, b2, ss2, save2, res, relu, used_batch)
+
+
+# --------------------------------------------------------------------------------------------------
+# LayerNorm + Linear, segmented attention
+# --------------------------------------------------------------------------------------------------
+class _LNLinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, W, bias, eps, out_bf16):
+        # x: (..., 32) bf16 NHWC tokens or fp32 [B][N][32]
+        dim = x.shape[-1]
+        x_f32 = x.dtype == torch.float32
+        xs = x if x.is_contiguous() else x.contiguous()
+        ntok = xs.numel() // dim
+        out = torch.empty(x.shape, dtype=BF16 if out_bf16 else torch.float32, device=x.device)
+        L.check(L.lib().dp_ln_linear_fwd(L.ptr(xs), dim, int(x_f32), ntok, dim, L.ptr(_f32(gamma)), L.ptr(_f32(beta)), eps,
+                                         L.ptr(_f32(W)), L.ptr(_f32(bias)), L.ptr(out), dim, int(out_bf16), L.stream()))
+        ctx.save_for_backward(xs, gamma, beta, W)
+        ctx.cfg = (eps, bias is not None, x_f32, out_bf16)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        xs, gamma, beta, W = ctx.saved_tensors
+        eps, has_bias, x_f32, out_bf16 = ctx.cfg
+        dim = xs.shape[-1]
+        ntok = xs.numel() // dim
+        lib = L.lib()
+        want = BF16 if out_bf16 else torch.float32
+        g = g if (g.dtype == want and g.is_contiguous()) else g.to(want).contiguous()
+        dev = xs.device
+        part = torch.empty(lib.dp_lnl_blocks(), lib.dp_lnl_partial_floats(), dtype=torch.float32, device=dev)
+        dx = torch.empty_like(xs) if ctx.needs_input_grad[0] else None
+        dW = torch.empty(dim, dim, dtype=torch.float32, device=dev)
+        dbias = torch.empty(dim, dtype=torch.float32, device=dev) if has_bias else None
+        dg = torch.empty(dim, dtype=torch.float32, device=dev)
+        db = torch.empty(dim, dtype=torch.float32, device=dev)
+        L.check(lib.dp_ln_linear_bwd(L.ptr(xs), dim, int(x_f32), ntok, dim, L.ptr(_f32(gamma)), L.ptr(_f32(beta)), eps,
+                                     L.ptr(_f32(W)), L.ptr(g), dim, int(out_bf16), L.ptr(dx), dim, L.ptr(part), L.ptr(dW),
+                                     L.ptr(dbias), L.ptr(dg), L.ptr(db), 0, L.stream()))
+        return dx, dg.to(gamma.dtype), db.to(beta.dtype), dW.to(W.dtype), dbias, None, None
+
+
+def ln_linear(x, ln, lin, out_bf16=False):
+    return _LNLinear.apply(x, ln.weight, ln.bias, lin.weight, lin.bias, ln.eps, out_bf16)
+
+
+_SEG_CACHE = {}
+
+
+def attention_segments(hr, wr, ws, device):
+    """The reference's window loop (midas_semantics.py:93-112) reduced to its last-writer form.
+    Returns (items int32 [n,4] {q0, nq<=32, k_lo, k_hi}, segs int32 [m,4] {q_lo, q_hi, k_lo, k_hi})."""
+    key = (hr, wr, ws, str(device))
+    if key in _SEG_CACHE:
+        return _SEG_CACHE[key]
+    N = hr * wr
+    ranges = []
+    for h in range((hr + ws - 1) // ws):
+        for w in range((wr + ws - 1) // ws):
+            lo = h * ws * wr + w * ws
+            hi = min(min(h * ws + ws, hr) * wr + min(w * ws + ws, wr), N)
+            ranges.append((lo, hi))
+    owner = [-1] * N
+    for wi, (lo, hi) in enumerate(ranges):
+        for i in range(lo, hi):
+            owner[i] = wi
+    segs = []
+    i = 0
+    while i < N:
+        j = i
+        while j < N and owner[j] == owner[i]:
+            j += 1
+        if owner[i] >= 0:
+            lo, hi = ranges[owner[i]]
+            segs.append((i, j, lo, hi))
+        i = j
+    items = []
+    for (a, b, lo, hi) in segs:
+        for q0 in range(a, b, 32):
+            items.append((q0, min(32, b - q0), lo, hi))
+    unowned = [i for i in range(N) if owner[i] < 0]
+    res = (torch.tensor(items, dtype=torch.int32, device=device), torch.tensor(segs, dtype=torch.int32, device=device),
+           unowned)
+    _SEG_CACHE[key] = res
+    return res
+
+
+class _Attention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, items, segs, scale):
+        B, N, D = q.shape
+        out = torch.zeros(B, N, D, dtype=torch.float32, device=q.device)
+        lse = torch.zeros(B, N, 8, dtype=torch.float32, device=q.device)
+        L.check(L.lib().dp_attn_fwd(L.ptr(q), L.ptr(k), L.ptr(v), B, N, scale, L.ptr(items), items.shape[0], L.ptr(out),
+                                    L.ptr(lse), L.stream()))
+        ctx.save_for_backward(q, k, v, out, lse, items, segs)
+        ctx.scale = scale
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        q, k, v, out, lse, items, segs = ctx.saved_tensors
+        B, N, D = q.shape
+        g = g if (g.dtype == torch.float32 and g.is_contiguous()) else g.float().contiguous()
+        dq = torch.zeros_like(q)
+        dk = torch.zeros_like(k)
+        dv = torch.zeros_like(v)
+        delta = torch.zeros(B, N, 8, dtype=torch.float32, device=q.device)
+        L.check(L.lib().dp_attn_bwd(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(out), L.ptr(g), L.ptr(lse), B, N, ctx.scale,
+                                    L.ptr(items), items.shape[0], L.ptr(segs), segs.shape[0], L.ptr(dq), L.ptr(dk),
+                                    L.ptr(dv), L.ptr(delta), L.stream()))
+        return dq, dk, dv, None, None, None
+
+
+def attention(q, k, v, hr, wr, ws, scale):
+    """q,k,v fp32 [B][N][32] -> fp32 [B][N][32]"""
+    items, segs, _ = attention_segments(hr, wr, ws, q.device)
+    return _Attention.apply(q.contiguous(), k.contiguous(), v.contiguous(), items, segs, float(scale))
+
+
+def add(a, b, c=None):
+    """elementwise a + b (+ c) on dense NHWC bf16 (autograd: plain fan-out)."""
+    return _Add.apply(a, b, c)
+
+
+class _Add(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, c):
+        a_, b_ = (a if a.is_contiguous() else a.contiguous()), (b if b.is_contiguous() else b.contiguous())
+        c_ = None if c is None else (c if c.is_contiguous() else c.contiguous())
+        out = torch.empty_like(a_)
+        L.check(L.lib().dp_add_bf16(L.ptr(a_), L.ptr(b_), L.ptr(c_), L.ptr(out), out.numel(), L.stream()))
+        ctx.has_c = c is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g, (g if ctx.has_c else None)
+
+
+class _Concat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        B, H, W, Ca = a.shape
+        Cb = b.shape[-1]
+        out = _nhwc(B, H, W, Ca + Cb, a.device)
+        npix = B * H * W
+        L.check(L.lib().dp_copy_channels(L.ptr(a), _ld(a), L.ptr(out), Ca + Cb, npix, Ca, L.stream()))
+        L.check(L.lib().dp_copy_channels(L.ptr(b), _ld(b), out.data_ptr() + 2 * Ca, Ca + Cb, npix, Cb, L.stream()))
+        ctx.split = Ca
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g[..., :ctx.split], g[..., ctx.split:]
+
+
+def concat_channels(a, b):
+    """torch.cat([a, b], dim=1) of the reference, in NHWC."""
+    return _Concat.apply(a, b)
+
+
+class _Relu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        xd = x if x.is_contiguous() else x.contiguous()
+        out = torch.empty_like(xd)
+        L.check(L.lib().dp_relu_bf16(L.ptr(xd), L.ptr(out), out.numel(), L.stream()))
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        return _mask_grad(None, g, y)
+
+
+def relu(x):
+    return _Relu.apply(x)

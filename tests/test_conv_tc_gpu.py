@@ -24,7 +24,7 @@ def run_conv(pkg, x_nhwc, wp, Cout, KS, bias=None, res=None, relu=False, out2=Fa
         g = L.lib().dp_conv2d_tc_grid(B, H, W, Cin, Cout, KS)
         st = torch.full((g, 2, Cout), float("nan"), device="cuda", dtype=torch.float32)
     L.check(L.lib().dp_conv2d_tc(L.ptr(x_nhwc), Cin, B, H, W, Cin, L.ptr(wp), wp.shape[2], Cout, KS, L.ptr(bias),
-                                 L.ptr(res), Cout, int(relu), L.ptr(out), Cout, L.ptr(o2), Cout, int(relu2),
+                                 L.ptr(res), Cout, None, 0, int(relu), L.ptr(out), Cout, L.ptr(o2), Cout, int(relu2),
                                  L.ptr(st), L.stream()))
     torch.cuda.synchronize()
     return out, o2, st
