@@ -89,13 +89,14 @@ def build_oracle_small(standins):
 
 
 def prepare_full(model):
-    """deterministic weights; lift the last bias so the ReLU'd depth is not mostly zero."""
+    """deterministic weights; lift the last bias so the ReLU'd depth stays clear of 0 (the SI loss gradient
+    ~ 1/(p+1e-6) makes near-zero predictions dominate and turns gradient comparisons chaotic)."""
     fx.fill_deterministic(model)
     with torch.no_grad():
         if hasattr(model, "depth_head"):
-            model.depth_head[1].bias.add_(0.75)
+            model.depth_head[1].bias.add_(4.0)
         else:
-            model.scratch.output_conv[4].bias.add_(0.75)
+            model.scratch.output_conv[4].bias.add_(8.0)
     return model
 
 

@@ -173,7 +173,7 @@ def test_batchnorm_act(pkg, C, mode):
     out.backward(nhwc(cot))
     ok, e, s = close(nchw(out.detach()), ref.detach())
     assert ok, ("fwd", e, s)
-    gscale = float(cot.abs().max()) * float(bn.weight.abs().max()) * 2
+    gscale = float(cot.abs().max()) * float(bn.weight.detach().abs().max()) * 2
     assert float((nchw(xp.grad) - xr.grad).abs().max()) < 2e-2 * gscale
     if mode in ("two", "res"):
         assert float((nchw(x2p.grad) - x2r.grad).abs().max()) < 2e-2 * gscale
