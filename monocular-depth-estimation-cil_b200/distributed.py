@@ -1,0 +1,88 @@
+"""Data-parallel plumbing for the training hot path: one process per GPU, NCCL over NVLink.
+
+The reference has no distributed code (only commented-out nn.DataParallel, main.py:660); SURVEY section 8(e) maps
+its batch-parallel intent to: shard the batch by sample, per-replica BatchNorm statistics (DataParallel
+semantics, no SyncBN), one gradient all-reduce(mean) per step over the parameters that actually receive
+gradients (the 8 never-used refinenet4.resConfUnit1 tensors keep grad=None so AdamW leaves them alone, as in
+the reference), and one all-reduce of a handful of scalars for evaluation metrics.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """torchrun-style env (RANK/LOCAL_RANK/WORLD_SIZE/MASTER_*).  Returns (rank, local_rank, world)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, local, world
+
+
+class GradientAllReducer:
+    """Flat-bucket gradient averaging.  After the first backward, the parameters that received a gradient are
+    re-pointed at views of one flat fp32 buffer, so each later step is a single in-place all-reduce (96 MB for the
+    default model: launch-latency bound on NVSwitch, so one bucket beats many) and `zero()` is one memset."""
+
+    def __init__(self, params, world=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.world = world if world is not None else (dist.get_world_size() if dist.is_initialized() else 1)
+        self.flat = None
+        self.live = None
+
+    def _build(self):
+        self.live = [p for p in self.params if p.grad is not None]
+        n = sum(p.numel() for p in self.live)
+        dev = self.live[0].device
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.live:
+            v = self.flat[off:off + p.numel()].view_as(p)
+            v.copy_(p.grad)
+            p.grad = v
+            off += p.numel()
+
+    def zero(self):
+        if self.flat is None:
+            for p in self.params:
+                p.grad = None
+        else:
+            self.flat.zero_()
+
+    def reduce(self):
+        """call after backward(); averages gradients over ranks (no-op for world 1)."""
+        if self.flat is None:
+            self._build()
+        if self.world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.mul_(1.0 / self.world)
+
+    def live_parameters(self):
+        return self.live
+
+
+def all_reduce_metric_sums(values, device=None):
+    """sum a small list of python/torch scalars over ranks in fp64 (evaluation partials: per-rank sums of per-sample
+    SI-RMSE, AbsRel, delta_k and the sample count; evaluation.py:157-176)."""
+    t = torch.tensor([float(v) for v in values], dtype=torch.float64, device=device)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.tolist()
+
+
+def shard_range(n_items, rank, world):
+    """contiguous shard [lo, hi) of n_items samples for this rank (evaluation / prediction passes)."""
+    per = (n_items + world - 1) // world
+    lo = min(n_items, rank * per)
+    return lo, min(n_items, lo + per)

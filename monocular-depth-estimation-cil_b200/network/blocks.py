@@ -30,6 +30,15 @@ def enter(x):
     return ops.to_nhwc(x), True
 
 
+def from_nchw(f):
+    """encoder feature map (B,C,H,W), fp32 or (autocast) bf16 -> NHWC bf16.  A channels_last bf16 map is already
+    NHWC in memory: its permuted view is used as is (autograd routes the gradient back through the view)."""
+    if f.dtype == torch.bfloat16:
+        t = f.permute(0, 2, 3, 1)
+        return t if t.is_contiguous() else t.contiguous()
+    return ops.to_nhwc(f)
+
+
 def leave(y, was_public):
     return ops.to_nchw(y) if was_public else y
 

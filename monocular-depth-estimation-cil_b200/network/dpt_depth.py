@@ -7,7 +7,7 @@ import torch.nn as nn
 from .. import ops
 from . import blocks as _blocks
 from .base_model import BaseModel
-from .blocks import FeatureFusionBlock_custom, Interpolate, _make_scratch, enter, leave
+from .blocks import FeatureFusionBlock_custom, Interpolate, _make_scratch, enter, leave, from_nchw
 
 
 def _make_fusion_block(features, use_bn, size=None):
@@ -107,7 +107,7 @@ class DPT(BaseModel):
         """the decoder + head from the four reassembled maps (NCHW fp32 in, (B,H,W) fp32 out)."""
         s = self.scratch
         feats = [layer_1, layer_2, layer_3, layer_4]
-        rn = [ops.conv_tc(enter(f)[0], getattr(s, f"layer{i + 1}_rn").weight, None, dual=True) for i, f in enumerate(feats)]
+        rn = [ops.conv_tc(from_nchw(f), getattr(s, f"layer{i + 1}_rn").weight, None, dual=True) for i, f in enumerate(feats)]
         p4 = s.refinenet4.fused(rn[3], None, size=rn[2][0].shape[1:3])
         p3 = s.refinenet3.fused(p4, rn[2], size=rn[1][0].shape[1:3])
         p2 = s.refinenet2.fused(p3, rn[1], size=rn[0][0].shape[1:3])

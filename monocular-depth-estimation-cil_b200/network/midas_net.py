@@ -6,7 +6,7 @@ import torch.nn as nn
 from .. import ops
 from . import blocks as _blocks
 from .base_model import BaseModel
-from .blocks import FeatureFusionBlock, Interpolate, _make_scratch, _make_resnet_backbone, enter
+from .blocks import FeatureFusionBlock, Interpolate, _make_scratch, _make_resnet_backbone, enter, from_nchw
 
 
 class MidasNet(BaseModel):
@@ -37,7 +37,7 @@ class MidasNet(BaseModel):
     def forward_features(self, layer_1, layer_2, layer_3, layer_4):
         s = self.scratch
         feats = [layer_1, layer_2, layer_3, layer_4]
-        rn = [ops.conv_tc(enter(f)[0], getattr(s, f"layer{i + 1}_rn").weight, None, dual=True) for i, f in enumerate(feats)]
+        rn = [ops.conv_tc(from_nchw(f), getattr(s, f"layer{i + 1}_rn").weight, None, dual=True) for i, f in enumerate(feats)]
         p4 = s.refinenet4.fused(rn[3][1], None)                 # single input: relu(x) feeds both conv1 and the skip
         p3 = s.refinenet3.fused(p4, rn[2][1])
         p2 = s.refinenet2.fused(p3, rn[1][1])

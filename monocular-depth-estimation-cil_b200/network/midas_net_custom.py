@@ -9,7 +9,7 @@ import torch.nn as nn
 
 from .. import ops
 from .base_model import BaseModel
-from .blocks import FeatureFusionBlock_custom, Interpolate, _make_encoder, enter
+from .blocks import FeatureFusionBlock_custom, Interpolate, _make_encoder, enter, from_nchw
 
 
 class MidasNet_small(BaseModel):
@@ -74,7 +74,7 @@ class MidasNet_small(BaseModel):
         rn = []
         for i, f in enumerate(feats):
             conv = getattr(s, f"layer{i + 1}_rn")
-            rn.append(ops.conv_tc(enter(f)[0], conv.weight, None, dual=True))      # (raw, relu) pairs
+            rn.append(ops.conv_tc(from_nchw(f), conv.weight, None, dual=True))      # (raw, relu) pairs
         p4 = s.refinenet4.fused(rn[3], None)
         p3 = s.refinenet3.fused(p4, rn[2])
         p2 = s.refinenet2.fused(p3, rn[1])
