@@ -133,6 +133,20 @@ int dp_conv2d_tc(const void* x, long long x_ld, int B, int H, int W, int Cin, co
                  long long res2_ld, int relu, void* out, long long out_ld, void* out2, long long out2_ld, int relu2,
                  float* stats_partials, cudaStream_t stream);
 
+/* Stride-2 convolution (conv rule i = 2*o - pad + k, K x K taps) on the tensor cores, reading the four parity planes
+ * of the input as strided TMA tensors: nn.Conv2d(k3,s2,p1) forward (midas_semantics.py:39-45, dpt_depth.py:63-68) and
+ * the data gradient of nn.ConvTranspose2d(k4,s2,p1) (midas_semantics.py:52-58).
+ * x (B,Hi,Wi,Cin) NHWC bf16; w_packed bf16 [K*K][Cout][Cin_p]; out (B,Ho,Wo,Cout); stats as in dp_conv2d_tc. */
+int dp_conv2d_tc_down2_grid(int B, int Ho, int Wo, int Cin, int Cout, int K, int pad);
+int dp_conv2d_tc_down2(const void* x, long long x_ld, int B, int Hi, int Wi, int Cin, const void* w_packed, int Cin_p,
+                       int Cout, int K, int pad, const float* bias, int relu, void* out, long long out_ld, int Ho,
+                       int Wo, float* stats_partials, cudaStream_t stream);
+/* Transposed stride-2 convolution (rule i = (o + pad - k)/2 when even) as four output-phase launches whose epilogue
+ * writes pixel (2y+a, 2x+b): nn.ConvTranspose2d(k4,s2,p1) forward and the data gradient of nn.Conv2d(k3,s2,p1). */
+int dp_conv2d_tc_up2(const void* x, long long x_ld, int B, int Hi, int Wi, int Cin, const void* w_packed, int Cin_p,
+                     int Cout, int K, int pad, const float* bias, int relu, void* out, long long out_ld, int Ho, int Wo,
+                     cudaStream_t stream);
+
 /* Weight gradient of the same convolutions (autograd's convolution_backward w.r.t. weight), tcgen05 GEMM over
  * pixels with split-K partials reduced deterministically.  x, dy: NHWC bf16; grad_oihw: fp32 [Cout][Cin][KS][KS]
  * (overwritten, or added to when accumulate != 0). */
@@ -140,6 +154,14 @@ size_t dp_conv2d_wgrad_tc_workspace(int B, int H, int W, int Cin, int Cout, int 
 int dp_conv2d_wgrad_tc(const void* x, long long x_ld, const void* dy, long long dy_ld, int B, int H, int W, int Cin,
                        int Cout, int KS, float* grad_oihw, int accumulate, void* workspace, size_t workspace_bytes,
                        cudaStream_t stream);
+
+/* grad[cp][ct][ky][kx] (+)= sum over plain-grid pixels p of P[p][cp] * T[2p - pad + k][ct]  (K x K taps, stride 2):
+ *   nn.Conv2d(k3,s2,p1):          P = dY (B,Ho,Wo,O), T = X  (B,Hi,Wi,I)  -> weight.grad [O][I][3][3]
+ *   nn.ConvTranspose2d(k4,s2,p1): P = X  (B,Hi,Wi,I), T = dY (B,Ho,Wo,O)  -> weight.grad [I][O][4][4] */
+size_t dp_conv2d_wgrad_tc_s2_workspace(int B, int Hp, int Wp, int Cp, int Ct, int K, int pad);
+int dp_conv2d_wgrad_tc_s2(const void* P, long long p_ld, int Hp, int Wp, int Cp, const void* T, long long t_ld, int Ht,
+                          int Wt, int Ct, int B, int K, int pad, float* grad, int accumulate, void* workspace,
+                          size_t workspace_bytes, cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Layout / dtype boundaries and weight packing (csrc/layout.cu)

@@ -68,6 +68,11 @@ class _Sig:
     dp_conv2d_tc_grid = (c_int, [c_int, c_int, c_int, c_int, c_int, c_int])
     dp_conv2d_tc = (c_int, [P, c_ll, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, P, P, c_ll, P, c_ll, c_int, P,
                             c_ll, P, c_ll, c_int, P, P])
+    dp_conv2d_tc_down2_grid = (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int])
+    dp_conv2d_tc_down2 = (c_int, [P, c_ll, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, P, c_int, P, c_ll,
+                                  c_int, c_int, P, P])
+    dp_conv2d_tc_up2 = (c_int, [P, c_ll, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, P, c_int, P, c_ll,
+                                c_int, c_int, P])
     dp_conv2d_wgrad_tc_workspace = (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int])
     dp_conv2d_wgrad_tc = (c_int, [P, c_ll, P, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_size_t, P])
     dp_nchw_f32_to_nhwc_bf16 = (c_int, [P, c_int, c_int, c_int, c_int, P, c_ll, P])
@@ -106,6 +111,9 @@ class _Sig:
                                 P, c_int, P])
     dp_attn_fwd = (c_int, [P, P, P, c_int, c_int, c_float, P, c_int, P, P, P])
     dp_attn_bwd = (c_int, [P, P, P, P, P, P, c_int, c_int, c_float, P, c_int, P, c_int, P, P, P, P, P])
+    dp_conv2d_wgrad_tc_s2_workspace = (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int])
+    dp_conv2d_wgrad_tc_s2 = (c_int, [P, c_ll, c_int, c_int, c_int, P, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, P,
+                                     c_int, P, c_size_t, P])
     dp_umma_probe = (c_int, [P, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                              c_int, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32), P, c_int, P])
 

@@ -16,6 +16,13 @@
 //     set resident in shared memory for the life of the persistent CTA; large ones stream it.
 //   * Accumulators live in TMEM, double buffered (2 x BN fp32 columns) so the epilogue of tile i
 //     overlaps the MMAs of tile i+1.
+//   * The k-loop is table driven (ColLoad): each entry is one TMA box (source plane, x/y offset, number of
+//     vertical taps that share it, weight tap ids).  The plain 3x3 conv has three entries (one per horizontal
+//     tap).  Stride-2 convolutions read the four (row parity, column parity) planes of the input as separate
+//     strided tensor maps, which turns them into sums of small stride-1 convolutions; transposed stride-2
+//     convolutions are four output-phase launches whose epilogue writes pixel (2y+a, 2x+b).  This puts
+//     CrossAttention.spatial_reduction / spatial_upsample (midas_semantics.py:38-61), Dinov2Head.resize_layers[3]
+//     (dpt_depth.py:63-68) and their data gradients on the tensor cores as well.
 //   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
 //     warps 4..7 = epilogue (TMEM -> registers -> bias / residual / ReLU / BN partial sums -> global).
 #include "common.cuh"
@@ -28,15 +35,33 @@ constexpr int kThreads = 256;
 constexpr int kMaxStages = 8;
 constexpr int kTmemCols = 512;
 
+constexpr int kMaxCols = 8;
+
+struct ColLoad {
+  int map;        // index of the A tensor map (source plane)
+  int dx, dy;     // box origin relative to the tile origin (x0, y0), in plane pixels
+  int nr;         // vertical taps sharing this box (box rows = th + nr - 1)
+  int wtap[3];    // weight-pack tap id of vertical tap r
+  int wslot[3];   // resident-weight slot of vertical tap r
+  uint32_t box_bytes;
+};
+
+struct Maps {
+  CUtensorMap a[kMaxCols];
+  CUtensorMap b;
+};
+
 struct ConvArgs {
-  int B, H, W, Cout;
-  int KS, pad;
+  int B, H, W, Cout;              // GEMM pixel grid (tile domain) and output channels
+  int Ho, Wo, osy, osx, oay, oax; // output tensor dims; GEMM pixel (y,x) -> output pixel (y*osy+oay, x*osx+oax)
   int th, tw, tiles_y, tiles_x;
   int KB, kchunks;
   int BN, n_blocks;
   int stages, resident;
-  uint32_t a_stage_bytes, b_tap_bytes, b_stage_bytes, row_bytes, layout, sbo, idesc;
-  uint32_t a_box_bytes, b_box_bytes;  // bytes TMA actually writes per box (slots are rounded up to 1024)
+  int ncols, max_nr, nslots;
+  ColLoad cols[kMaxCols];
+  uint32_t a_slot_bytes, b_tap_bytes, row_bytes, layout, sbo, idesc;
+  uint32_t b_box_bytes;  // bytes TMA actually writes per weight box (slots are rounded up to 1024)
   uint32_t resident_bytes;
   long long total_items;
   bf16* out;  long long out_ld;
@@ -109,13 +134,13 @@ __device__ __forceinline__ int transpose_reduce16_col(int lane) {
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs a) {
+conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // layout: [resident weights][stages x (A | B)][stats][barriers]
   uint8_t* s_res = smem;
   uint8_t* s_stage = smem + a.resident_bytes;
-  const uint32_t stage_bytes = a.a_stage_bytes + (a.resident ? 0u : a.b_stage_bytes);
+  const uint32_t stage_bytes = a.a_slot_bytes + (a.resident ? 0u : (uint32_t)a.max_nr * a.b_tap_bytes);
   float* s_stats = reinterpret_cast<float*>(s_stage + (size_t)a.stages * stage_bytes);
   const int stats_floats = a.stats ? 4 * 2 * a.Cout : 0;
   Barriers* bars = reinterpret_cast<Barriers*>(reinterpret_cast<uint8_t*>(s_stats) + ((stats_floats * 4 + 15) & ~15));
@@ -128,8 +153,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars->tmem_full[i], 1); tc::mbar_init(&bars->tmem_empty[i], 4); }
     tc::mbar_init(&bars->resident_full, 1);
     tc::fence_barrier_init();
-    tc::prefetch_tmap(&tmA);
-    tc::prefetch_tmap(&tmB);
+    tc::prefetch_tmap(&tm.a[0]);
+    tc::prefetch_tmap(&tm.b);
   }
   if (warp == 2) tc::tmem_alloc(&bars->tmem_base, kTmemCols);
   for (int i = threadIdx.x; i < stats_floats; i += kThreads) s_stats[i] = 0.f;
@@ -137,33 +162,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = bars->tmem_base;
-  const int ksteps = a.KS * a.kchunks;  // one k-step = (horizontal tap s, channel chunk kc)
 
   if (warp == 0 && lane == 0) {
     // ================= TMA producer =================
     if (a.resident) {
-      tc::mbar_expect_tx(&bars->resident_full, (uint32_t)(a.KS * a.KS * a.kchunks) * a.b_box_bytes);
-      for (int s = 0; s < a.KS; ++s)
-        for (int kc = 0; kc < a.kchunks; ++kc)
-          for (int r = 0; r < a.KS; ++r)
-            tc::tma_load_3d(s_res + (size_t)((s * a.kchunks + kc) * a.KS + r) * a.b_tap_bytes, &tmB,
-                            &bars->resident_full, kc * a.KB, 0, r * a.KS + s);
+      tc::mbar_expect_tx(&bars->resident_full, (uint32_t)(a.nslots * a.kchunks) * a.b_box_bytes);
+      for (int c = 0; c < a.ncols; ++c)
+        for (int r = 0; r < a.cols[c].nr; ++r)
+          for (int kc = 0; kc < a.kchunks; ++kc)
+            tc::tma_load_3d(s_res + (size_t)(a.cols[c].wslot[r] * a.kchunks + kc) * a.b_tap_bytes, &tm.b,
+                            &bars->resident_full, kc * a.KB, 0, a.cols[c].wtap[r]);
     }
     uint32_t stage = 0, phase = 0;
     for (long long item = blockIdx.x; item < a.total_items; item += gridDim.x) {
       int n, y0, x0, nb;
       decode_item(a, item, n, y0, x0, nb);
-      for (int s = 0; s < a.KS; ++s) {
+      for (int c = 0; c < a.ncols; ++c) {
+        const ColLoad& col = a.cols[c];
         for (int kc = 0; kc < a.kchunks; ++kc) {
           tc::mbar_wait(&bars->empty[stage], phase ^ 1);
           uint8_t* sA = s_stage + (size_t)stage * stage_bytes;
-          tc::mbar_expect_tx(&bars->full[stage], a.a_box_bytes + (a.resident ? 0u : (uint32_t)a.KS * a.b_box_bytes));
-          tc::tma_load_4d(sA, &tmA, &bars->full[stage], kc * a.KB, x0 + s - a.pad, y0 - a.pad, n);
+          tc::mbar_expect_tx(&bars->full[stage], col.box_bytes + (a.resident ? 0u : (uint32_t)col.nr * a.b_box_bytes));
+          tc::tma_load_4d(sA, &tm.a[col.map], &bars->full[stage], kc * a.KB, x0 + col.dx, y0 + col.dy, n);
           if (!a.resident) {
-            uint8_t* sB = sA + a.a_stage_bytes;
-            for (int r = 0; r < a.KS; ++r)
-              tc::tma_load_3d(sB + (size_t)r * a.b_tap_bytes, &tmB, &bars->full[stage], kc * a.KB, nb * a.BN,
-                              r * a.KS + s);
+            uint8_t* sB = sA + a.a_slot_bytes;
+            for (int r = 0; r < col.nr; ++r)
+              tc::tma_load_3d(sB + (size_t)r * a.b_tap_bytes, &tm.b, &bars->full[stage], kc * a.KB, nb * a.BN,
+                              col.wtap[r]);
           }
           if (++stage == (uint32_t)a.stages) { stage = 0; phase ^= 1; }
         }
@@ -181,24 +206,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc::fence_after_sync();
       const uint32_t d_tmem = tmem + (uint32_t)(buf * a.BN);
       uint32_t accumulate = 0;
-      for (int ks = 0; ks < ksteps; ++ks) {
-        tc::mbar_wait(&bars->full[stage], phase);
-        tc::fence_after_sync();
-        const uint32_t a_base = tc::smem_u32(s_stage + (size_t)stage * stage_bytes);
-        const uint32_t b_base = a.resident ? tc::smem_u32(s_res) + (uint32_t)(ks * a.KS) * a.b_tap_bytes
-                                           : a_base + a.a_stage_bytes;
-        for (int r = 0; r < a.KS; ++r) {
-          const uint32_t ar = a_base + (uint32_t)(r * a.tw) * a.row_bytes;
-          const uint32_t br = b_base + (uint32_t)r * a.b_tap_bytes;
-          for (int kk = 0; kk < kk_n; ++kk) {
-            const uint64_t da = tc::make_smem_desc(ar + kk * 32, 16, a.sbo, a.layout);
-            const uint64_t db = tc::make_smem_desc(br + kk * 32, 16, a.sbo, a.layout);
-            tc::umma_bf16(d_tmem, da, db, a.idesc, accumulate);
-            accumulate = 1;
+      for (int c = 0; c < a.ncols; ++c) {
+        const ColLoad& col = a.cols[c];
+        for (int kc = 0; kc < a.kchunks; ++kc) {
+          tc::mbar_wait(&bars->full[stage], phase);
+          tc::fence_after_sync();
+          const uint32_t a_base = tc::smem_u32(s_stage + (size_t)stage * stage_bytes);
+          for (int r = 0; r < col.nr; ++r) {
+            const uint32_t ar = a_base + (uint32_t)(r * a.tw) * a.row_bytes;
+            const uint32_t br = a.resident
+                                    ? tc::smem_u32(s_res) + (uint32_t)(col.wslot[r] * a.kchunks + kc) * a.b_tap_bytes
+                                    : a_base + a.a_slot_bytes + (uint32_t)r * a.b_tap_bytes;
+            for (int kk = 0; kk < kk_n; ++kk) {
+              const uint64_t da = tc::make_smem_desc(ar + kk * 32, 16, a.sbo, a.layout);
+              const uint64_t db = tc::make_smem_desc(br + kk * 32, 16, a.sbo, a.layout);
+              tc::umma_bf16(d_tmem, da, db, a.idesc, accumulate);
+              accumulate = 1;
+            }
           }
+          tc::umma_commit(&bars->empty[stage]);  // frees the smem slot when these MMAs have read it
+          if (++stage == (uint32_t)a.stages) { stage = 0; phase ^= 1; }
         }
-        tc::umma_commit(&bars->empty[stage]);  // frees the smem slot when these MMAs have read it
-        if (++stage == (uint32_t)a.stages) { stage = 0; phase ^= 1; }
       }
       tc::umma_commit(&bars->tmem_full[buf]);  // accumulator complete -> epilogue
     }
@@ -213,8 +241,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       decode_item(a, item, n, y0, x0, nb);
       const int buf = it & 1;
       const int y = y0 + py, x = x0 + px;
-      const bool valid = (y < a.H) && (x < a.W);
-      const long long pix = ((long long)n * a.H + y) * a.W + x;
+      const int oy = y * a.osy + a.oay, ox = x * a.osx + a.oax;
+      const bool valid = (y < a.H) && (x < a.W) && (oy < a.Ho) && (ox < a.Wo);
+      const long long pix = ((long long)n * a.Ho + oy) * a.Wo + ox;
       tc::mbar_wait(&bars->tmem_full[buf], (it >> 1) & 1);
       tc::fence_after_sync();
       const uint32_t t_base = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * a.BN);
@@ -320,24 +349,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 2) tc::tmem_dealloc(tmem, kTmemCols);
 }
 
+struct Plane {   // a (possibly strided) pixel-grid view of an NHWC bf16 tensor; strides in elements
+  const void* base;
+  long long ld_px, ld_row, ld_img;
+  int Hp, Wp;
+};
+struct ColSpec { int plane, dx, dy, nr, wtap[3]; };
+struct OutMap { int Ho, Wo, osy, osx, oay, oax; };
+struct Epilogue {
+  const float* bias;
+  const void* res; long long res_ld;
+  const void* res2; long long res2_ld;
+  int relu; void* out; long long out_ld; void* out2; long long out2_ld; int relu2;
+  float* stats;
+};
+
 struct Plan {
   ConvArgs a;
   size_t smem;
   int grid;
 };
 
-int make_plan(Plan& p, int B, int H, int W, int Cin, int Cout, int KS, int want_stats) {
+// geometry that does not depend on pointers: tile shape, K/N blocking, stages, grid
+int make_plan(Plan& p, int B, int Hg, int Wg, int Cin, int Cout, const ColSpec* cols, int ncols, int want_stats) {
   ConvArgs& a = p.a;
-  a.B = B; a.H = H; a.W = W; a.Cout = Cout; a.KS = KS; a.pad = KS / 2;
+  if (ncols < 1 || ncols > kMaxCols) return dp_set_error(DP_ERR_UNSUPPORTED, "conv_tc: %d column loads", ncols);
+  a.B = B; a.H = Hg; a.W = Wg; a.Cout = Cout;
   // patch shape: th*tw == 128, tw a multiple of 8 (swizzle-atom alignment of the vertical tap offsets)
   const int cand[5][2] = {{8, 16}, {16, 8}, {4, 32}, {2, 64}, {1, 128}};
   long long best = -1;
   for (int i = 0; i < 5; ++i) {
-    long long t = (long long)dp::ceil_div(H, cand[i][0]) * dp::ceil_div(W, cand[i][1]);
+    long long t = (long long)dp::ceil_div(Hg, cand[i][0]) * dp::ceil_div(Wg, cand[i][1]);
     if (best < 0 || t < best) { best = t; a.th = cand[i][0]; a.tw = cand[i][1]; }
   }
-  a.tiles_y = dp::ceil_div(H, a.th);
-  a.tiles_x = dp::ceil_div(W, a.tw);
+  a.tiles_y = dp::ceil_div(Hg, a.th);
+  a.tiles_x = dp::ceil_div(Wg, a.tw);
   a.KB = Cin > 32 ? 64 : (Cin > 16 ? 32 : 16);
   a.kchunks = dp::ceil_div(Cin, a.KB);
   a.n_blocks = dp::ceil_div(Cout, 160);
@@ -346,18 +392,29 @@ int make_plan(Plan& p, int B, int H, int W, int Cin, int Cout, int KS, int want_
   a.layout = tc::swizzle_for_row_bytes(a.row_bytes);
   a.sbo = 8 * a.row_bytes;
   a.idesc = tc::make_idesc_bf16(128, a.BN, 0, 0);
-  a.a_box_bytes = (uint32_t)((a.th + 2 * a.pad) * a.tw * a.row_bytes);
   a.b_box_bytes = (uint32_t)(a.BN * a.row_bytes);
-  a.a_stage_bytes = (a.a_box_bytes + 1023u) & ~1023u;
   a.b_tap_bytes = (a.b_box_bytes + 1023u) & ~1023u;
-  a.b_stage_bytes = a.b_tap_bytes * KS;
-  const size_t all_w = (size_t)KS * KS * a.kchunks * a.b_tap_bytes;
+  a.ncols = ncols;
+  a.max_nr = 0;
+  a.nslots = 0;
+  uint32_t max_box = 0;
+  for (int c = 0; c < ncols; ++c) {
+    ColLoad& d = a.cols[c];
+    d.map = c; d.dx = cols[c].dx; d.dy = cols[c].dy; d.nr = cols[c].nr;
+    if (d.nr < 1 || d.nr > 3) return dp_set_error(DP_ERR_UNSUPPORTED, "conv_tc: %d vertical taps in one box", d.nr);
+    for (int r = 0; r < 3; ++r) { d.wtap[r] = r < d.nr ? cols[c].wtap[r] : 0; d.wslot[r] = r < d.nr ? a.nslots++ : 0; }
+    d.box_bytes = (uint32_t)((a.th + d.nr - 1) * a.tw) * a.row_bytes;
+    if (d.box_bytes > max_box) max_box = d.box_bytes;
+    if (d.nr > a.max_nr) a.max_nr = d.nr;
+  }
+  a.a_slot_bytes = (max_box + 1023u) & ~1023u;
+  const size_t all_w = (size_t)a.nslots * a.kchunks * a.b_tap_bytes;
   a.resident = (a.n_blocks == 1 && all_w <= 100 * 1024) ? 1 : 0;
   a.resident_bytes = a.resident ? (uint32_t)all_w : 0u;
   const size_t stats_bytes = want_stats ? ((size_t)4 * 2 * Cout * 4 + 15) & ~size_t(15) : 0;
   const size_t fixed = 1024 + a.resident_bytes + stats_bytes + sizeof(Barriers) + 64;
   const size_t budget = 220 * 1024;
-  const size_t stage = a.a_stage_bytes + (a.resident ? 0 : a.b_stage_bytes);
+  const size_t stage = a.a_slot_bytes + (a.resident ? 0 : (size_t)a.max_nr * a.b_tap_bytes);
   if (fixed + 2 * stage > budget)
     return dp_set_error(DP_ERR_UNSUPPORTED, "conv_tc: shape needs %zu B of shared memory", fixed + 2 * stage);
   int st = (int)((budget - fixed) / stage);
@@ -368,6 +425,103 @@ int make_plan(Plan& p, int B, int H, int W, int Cin, int Cout, int KS, int want_
   return DP_OK;
 }
 
+int launch(const Plane* planes, const ColSpec* cols, int ncols, int B, int Hg, int Wg, int Cin, const void* w_packed,
+           int Cin_p, int ntaps, int Cout, const Epilogue& ep, const OutMap& om, cudaStream_t stream) {
+  Plan p;
+  int rc = make_plan(p, B, Hg, Wg, Cin, Cout, cols, ncols, ep.stats != nullptr);
+  if (rc) return rc;
+  ConvArgs& a = p.a;
+  a.Ho = om.Ho; a.Wo = om.Wo; a.osy = om.osy; a.osx = om.osx; a.oay = om.oay; a.oax = om.oax;
+  a.out = reinterpret_cast<bf16*>(ep.out); a.out_ld = ep.out_ld;
+  a.out2 = reinterpret_cast<bf16*>(ep.out2); a.out2_ld = ep.out2_ld;
+  a.bias = ep.bias;
+  a.res = reinterpret_cast<const bf16*>(ep.res); a.res_ld = ep.res_ld;
+  a.resb = reinterpret_cast<const bf16*>(ep.res2); a.resb_ld = ep.res2_ld;
+  a.relu = ep.relu; a.relu2 = ep.relu2;
+  a.stats = ep.stats;
+  Maps tm;
+  for (int c = 0; c < ncols; ++c) {
+    const Plane& pl = planes[cols[c].plane];
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)pl.Wp, (uint64_t)pl.Hp, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)pl.ld_px * 2, (uint64_t)pl.ld_row * 2, (uint64_t)pl.ld_img * 2};
+    uint32_t box[4] = {(uint32_t)a.KB, (uint32_t)a.tw, (uint32_t)(a.th + cols[c].nr - 1), 1};
+    rc = dp_make_tmap_bf16(&tm.a[c], pl.base, 4, dims, str, box, nullptr, a.row_bytes);
+    if (rc) return rc;
+  }
+  for (int c = ncols; c < kMaxCols; ++c) tm.a[c] = tm.a[0];
+  {
+    uint64_t dims[3] = {(uint64_t)Cin_p, (uint64_t)Cout, (uint64_t)ntaps};
+    uint64_t str[2] = {(uint64_t)Cin_p * 2, (uint64_t)Cout * Cin_p * 2};
+    uint32_t box[3] = {(uint32_t)a.KB, (uint32_t)a.BN, 1};
+    rc = dp_make_tmap_bf16(&tm.b, w_packed, 3, dims, str, box, nullptr, a.row_bytes);
+    if (rc) return rc;
+  }
+  cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+  if (e != cudaSuccess) return dp_set_error(DP_ERR_CUDA, "cudaFuncSetAttribute(%zu): %s", p.smem, cudaGetErrorString(e));
+  conv_tc_kernel<<<p.grid, kThreads, p.smem, stream>>>(tm, a);
+  DP_CHECK_LAUNCH("conv_tc_kernel");
+  return DP_OK;
+}
+
+int plain_cols(ColSpec* cols, int KS) {
+  const int pad = KS / 2;
+  for (int s = 0; s < KS; ++s) {
+    cols[s].plane = 0; cols[s].dx = s - pad; cols[s].dy = -pad; cols[s].nr = KS;
+    for (int r = 0; r < 3; ++r) cols[s].wtap[r] = r < KS ? r * KS + s : 0;
+  }
+  return KS;
+}
+
+inline int floordiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
+
+// stride-2 conv (conv rule i = 2*o - pad + k) as column loads over the four parity planes of the input
+int down2_cols(ColSpec* cols, int K, int pad) {
+  int n = 0;
+  for (int kx = 0; kx < K; ++kx) {
+    const int px = (kx - pad) & 1, dx = floordiv2(kx - pad);
+    for (int py = 0; py < 2; ++py) {
+      ColSpec c;
+      c.plane = py * 2 + px; c.dx = dx; c.nr = 0; c.dy = 0;
+      for (int ky = 0; ky < K; ++ky) {
+        if (((ky - pad) & 1) != py) continue;
+        const int dy = floordiv2(ky - pad);
+        if (c.nr == 0) c.dy = dy;
+        else if (dy != c.dy + c.nr) return -1;
+        if (c.nr >= 3) return -1;
+        c.wtap[c.nr++] = ky * K + kx;
+      }
+      if (c.nr == 0) continue;
+      for (int r = c.nr; r < 3; ++r) c.wtap[r] = 0;
+      if (n >= kMaxCols) return -1;
+      cols[n++] = c;
+    }
+  }
+  return n;
+}
+
+// one output phase (a, b) of a transposed stride-2 conv (rule i = (o + pad - k)/2): o = 2*y + a
+int up2_cols(ColSpec* cols, int K, int pad, int pa, int pb) {
+  int n = 0;
+  for (int kx = K - 1; kx >= 0; --kx) {
+    if (((pb + pad - kx) & 1) != 0) continue;
+    ColSpec c;
+    c.plane = 0; c.dx = floordiv2(pb + pad - kx); c.nr = 0; c.dy = 0;
+    for (int ky = K - 1; ky >= 0; --ky) {       // decreasing k -> increasing input row
+      if (((pa + pad - ky) & 1) != 0) continue;
+      const int dy = floordiv2(pa + pad - ky);
+      if (c.nr == 0) c.dy = dy;
+      else if (dy != c.dy + c.nr) return -1;
+      if (c.nr >= 3) return -1;
+      c.wtap[c.nr++] = ky * K + kx;
+    }
+    if (c.nr == 0) continue;
+    for (int r = c.nr; r < 3; ++r) c.wtap[r] = 0;
+    if (n >= kMaxCols) return -1;
+    cols[n++] = c;
+  }
+  return n;
+}
+
 }  // namespace
 
 extern "C" {
@@ -375,7 +529,9 @@ extern "C" {
 /* number of CTAs (= rows of the BN-statistics partials buffer) dp_conv2d_tc launches for this shape */
 int dp_conv2d_tc_grid(int B, int H, int W, int Cin, int Cout, int KS) {
   Plan p;
-  if (make_plan(p, B, H, W, Cin, Cout, KS, 0)) return -1;
+  ColSpec cols[kMaxCols];
+  const int n = plain_cols(cols, KS);
+  if (make_plan(p, B, H, W, Cin, Cout, cols, n, 0)) return -1;
   return p.grid;
 }
 
@@ -391,37 +547,73 @@ int dp_conv2d_tc(const void* x, long long x_ld, int B, int H, int W, int Cin, co
                (!residual || res_ld % 8 == 0) && (!residual2 || res2_ld % 8 == 0),
                "dp_conv2d_tc: pixel strides must be multiples of 8 elements");
   DP_CHECK_ARG(B > 0 && H > 0 && W > 0, "dp_conv2d_tc: bad shape");
-  Plan p;
-  int rc = make_plan(p, B, H, W, Cin, Cout, KS, stats_partials != nullptr);
-  if (rc) return rc;
-  ConvArgs& a = p.a;
-  a.out = reinterpret_cast<bf16*>(out); a.out_ld = out_ld;
-  a.out2 = reinterpret_cast<bf16*>(out2); a.out2_ld = out2_ld;
-  a.bias = bias;
-  a.res = reinterpret_cast<const bf16*>(residual); a.res_ld = res_ld;
-  a.resb = reinterpret_cast<const bf16*>(residual2); a.resb_ld = res2_ld;
-  a.relu = relu; a.relu2 = relu2;
-  a.stats = stats_partials;
+  Plane pl{x, x_ld, (long long)W * x_ld, (long long)H * W * x_ld, H, W};
+  ColSpec cols[kMaxCols];
+  const int n = plain_cols(cols, KS);
+  Epilogue ep{bias, residual, res_ld, residual2, res2_ld, relu, out, out_ld, out2, out2_ld, relu2, stats_partials};
+  OutMap om{H, W, 1, 1, 0, 0};
+  return launch(&pl, cols, n, B, H, W, Cin, w_packed, Cin_p, KS * KS, Cout, ep, om, stream);
+}
 
-  CUtensorMap tmA, tmB;
-  {
-    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-    uint64_t str[3] = {(uint64_t)x_ld * 2, (uint64_t)W * x_ld * 2, (uint64_t)H * W * x_ld * 2};
-    uint32_t box[4] = {(uint32_t)a.KB, (uint32_t)a.tw, (uint32_t)(a.th + 2 * a.pad), 1};
-    rc = dp_make_tmap_bf16(&tmA, x, 4, dims, str, box, nullptr, a.row_bytes);
-    if (rc) return rc;
-  }
-  {
-    uint64_t dims[3] = {(uint64_t)Cin_p, (uint64_t)Cout, (uint64_t)(KS * KS)};
-    uint64_t str[2] = {(uint64_t)Cin_p * 2, (uint64_t)Cout * Cin_p * 2};
-    uint32_t box[3] = {(uint32_t)a.KB, (uint32_t)a.BN, 1};
-    rc = dp_make_tmap_bf16(&tmB, w_packed, 3, dims, str, box, nullptr, a.row_bytes);
-    if (rc) return rc;
-  }
-  cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
-  if (e != cudaSuccess) return dp_set_error(DP_ERR_CUDA, "cudaFuncSetAttribute(%zu): %s", p.smem, cudaGetErrorString(e));
-  conv_tc_kernel<<<p.grid, kThreads, p.smem, stream>>>(tmA, tmB, a);
-  DP_CHECK_LAUNCH("conv_tc_kernel");
+/* Stride-2 convolution (conv rule i = 2*o - pad + k, K x K taps) on the tensor cores: nn.Conv2d(k3,s2,p1) forward
+ * (midas_semantics.py:39-45, dpt_depth.py:63-68) and the data gradient of nn.ConvTranspose2d(k4,s2,p1)
+ * (midas_semantics.py:52-58).  x: (B,Hi,Wi,Cin) NHWC bf16; w_packed bf16 [K*K][Cout][Cin_p]; out: (B,Ho,Wo,Cout). */
+int dp_conv2d_tc_down2(const void* x, long long x_ld, int B, int Hi, int Wi, int Cin, const void* w_packed, int Cin_p,
+                       int Cout, int K, int pad, const float* bias, int relu, void* out, long long out_ld, int Ho,
+                       int Wo, float* stats_partials, cudaStream_t stream) {
+  DP_CHECK_ARG(x && w_packed && out, "dp_conv2d_tc_down2: null pointer");
+  DP_CHECK_ARG(Cin % 8 == 0 && Cout % 8 == 0 && Cin_p >= Cin && x_ld % 8 == 0 && out_ld % 8 == 0,
+               "dp_conv2d_tc_down2: channels / strides must be multiples of 8");
+  ColSpec cols[kMaxCols];
+  const int n = down2_cols(cols, K, pad);
+  if (n <= 0) return dp_set_error(DP_ERR_UNSUPPORTED, "dp_conv2d_tc_down2: K %d pad %d not supported", K, pad);
+  Plane pl[4];
+  const bf16* xb = reinterpret_cast<const bf16*>(x);
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      Plane& q = pl[py * 2 + px];
+      q.base = xb + ((long long)py * Wi + px) * x_ld;
+      q.ld_px = 2 * x_ld; q.ld_row = 2LL * Wi * x_ld; q.ld_img = (long long)Hi * Wi * x_ld;
+      q.Hp = (Hi - py + 1) / 2; q.Wp = (Wi - px + 1) / 2;
+      if (q.Hp < 1) q.Hp = 1;
+      if (q.Wp < 1) q.Wp = 1;
+    }
+  Epilogue ep{bias, nullptr, 0, nullptr, 0, relu, out, out_ld, nullptr, 0, 0, stats_partials};
+  OutMap om{Ho, Wo, 1, 1, 0, 0};
+  return launch(pl, cols, n, B, Ho, Wo, Cin, w_packed, Cin_p, K * K, Cout, ep, om, stream);
+}
+
+int dp_conv2d_tc_down2_grid(int B, int Ho, int Wo, int Cin, int Cout, int K, int pad) {
+  Plan p;
+  ColSpec cols[kMaxCols];
+  const int n = down2_cols(cols, K, pad);
+  if (n <= 0 || make_plan(p, B, Ho, Wo, Cin, Cout, cols, n, 0)) return -1;
+  return p.grid;
+}
+
+/* Transposed stride-2 convolution (rule i = (o + pad - k)/2 when even) as four output-phase launches:
+ * nn.ConvTranspose2d(k4,s2,p1) forward (midas_semantics.py:52-58) and the data gradient of nn.Conv2d(k3,s2,p1).
+ * x: (B,Hi,Wi,Cin); w_packed bf16 [K*K][Cout][Cin_p]; out: (B,Ho,Wo,Cout). */
+int dp_conv2d_tc_up2(const void* x, long long x_ld, int B, int Hi, int Wi, int Cin, const void* w_packed, int Cin_p,
+                     int Cout, int K, int pad, const float* bias, int relu, void* out, long long out_ld, int Ho, int Wo,
+                     cudaStream_t stream) {
+  DP_CHECK_ARG(x && w_packed && out, "dp_conv2d_tc_up2: null pointer");
+  DP_CHECK_ARG(Cin % 8 == 0 && Cout % 8 == 0 && Cin_p >= Cin && x_ld % 8 == 0 && out_ld % 8 == 0,
+               "dp_conv2d_tc_up2: channels / strides must be multiples of 8");
+  Plane pl{x, x_ld, (long long)Wi * x_ld, (long long)Hi * Wi * x_ld, Hi, Wi};
+  for (int pa = 0; pa < 2; ++pa)
+    for (int pb = 0; pb < 2; ++pb) {
+      const int Hg = (Ho - pa + 1) / 2, Wg = (Wo - pb + 1) / 2;
+      if (Hg <= 0 || Wg <= 0) continue;
+      ColSpec cols[kMaxCols];
+      const int n = up2_cols(cols, K, pad, pa, pb);
+      if (n < 0) return dp_set_error(DP_ERR_UNSUPPORTED, "dp_conv2d_tc_up2: K %d pad %d not supported", K, pad);
+      if (n == 0) return dp_set_error(DP_ERR_UNSUPPORTED, "dp_conv2d_tc_up2: phase (%d,%d) has no taps", pa, pb);
+      Epilogue ep{bias, nullptr, 0, nullptr, 0, relu, out, out_ld, nullptr, 0, 0, nullptr};
+      OutMap om{Ho, Wo, 2, 2, pa, pb};
+      int rc = launch(&pl, cols, n, B, Hg, Wg, Cin, w_packed, Cin_p, K * K, Cout, ep, om, stream);
+      if (rc) return rc;
+    }
   return DP_OK;
 }
 

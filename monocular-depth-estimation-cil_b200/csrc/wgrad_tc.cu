@@ -20,16 +20,31 @@ namespace {
 constexpr int kThreads = 192;  // warp 0 producer, warp 1 MMA (+TMEM alloc), warps 2..5 epilogue
 constexpr int kMaxStages = 8;
 
+constexpr int kMaxKW = 4;
+
+struct WgGroup {      // one TMA box of the tapped operand: vertical taps ky[0..nr) share it
+  int map, dx, dy, nr;
+  int ky[3];
+  uint32_t box_bytes, slot_off;
+};
+
+struct WgMaps {
+  CUtensorMap p;                  // plain operand (M side)
+  CUtensorMap t[kMaxKW * 2];      // tapped operand boxes, one per (horizontal tap, group)
+};
+
 struct WgArgs {
-  int B, H, W, Cout, Cin, KS, pad;
+  int B, H, W, Cout, Cin, KH, KW;   // H, W: GEMM pixel grid = grid of the plain operand; Cout = its channels (M side)
   int th, tw, tiles_y, tiles_x;
   int MC, m_chunks, M, co_blocks;   // M chunk width (<=64 channels), chunks per UMMA, UMMA M, blocks over Cout
-  int NC, ci_chunks;                // N chunk width (<=64 channels), chunks over Cin
+  int NC, ci_chunks;                // N chunk width (<=64 channels), chunks over Cin (tapped operand channels)
   int psplit, stages;
+  int ngrp[kMaxKW];
+  WgGroup grp[kMaxKW][2];
   long long tiles_total;
-  uint32_t a_box_bytes, a_slot_bytes, x_box_bytes, x_slot_bytes, stage_bytes;
+  uint32_t a_box_bytes, a_slot_bytes, stage_bytes;
   uint32_t rowA, rowB, layoutA, layoutB, idesc, a_lbo;
-  float* partial;  // [psplit][KS*KS][Cout][Cin]
+  float* partial;  // [psplit][KH*KW][Cout][Cin]
 };
 
 struct __align__(8) WgBars {
@@ -40,7 +55,7 @@ struct __align__(8) WgBars {
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
-wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const WgArgs a) {
+wgrad_tc_kernel(const __grid_constant__ WgMaps tm, const __grid_constant__ WgArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   WgBars* bars = reinterpret_cast<WgBars*>(smem + (size_t)a.stages * a.stage_bytes);
@@ -56,8 +71,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
     for (int i = 0; i < a.stages; ++i) { tc::mbar_init(&bars->full[i], 1); tc::mbar_init(&bars->empty[i], 1); }
     tc::mbar_init(&bars->done, 1);
     tc::fence_barrier_init();
-    tc::prefetch_tmap(&tmDY);
-    tc::prefetch_tmap(&tmX);
+    tc::prefetch_tmap(&tm.p);
+    tc::prefetch_tmap(&tm.t[0]);
   }
   if (warp == 1) tc::tmem_alloc(&bars->tmem_base, 256);
   tc::fence_before_sync();
@@ -77,10 +92,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
       tc::mbar_wait(&bars->empty[stage], phase ^ 1);
       uint8_t* sA = smem + (size_t)stage * a.stage_bytes;
       uint8_t* sX = sA + (size_t)real_chunks * a.a_slot_bytes;
-      tc::mbar_expect_tx(&bars->full[stage], (uint32_t)real_chunks * a.a_box_bytes + a.x_box_bytes);
+      uint32_t txb = (uint32_t)real_chunks * a.a_box_bytes;
+      for (int g = 0; g < a.ngrp[s]; ++g) txb += a.grp[s][g].box_bytes;
+      tc::mbar_expect_tx(&bars->full[stage], txb);
       for (int j = 0; j < real_chunks; ++j)
-        tc::tma_load_4d(sA + (size_t)j * a.a_slot_bytes, &tmDY, &bars->full[stage], cb * a.M + j * a.MC, x0, y0, n);
-      tc::tma_load_4d(sX, &tmX, &bars->full[stage], cc * a.NC, x0 + s - a.pad, y0 - a.pad, n);
+        tc::tma_load_4d(sA + (size_t)j * a.a_slot_bytes, &tm.p, &bars->full[stage], cb * a.M + j * a.MC, x0, y0, n);
+      for (int g = 0; g < a.ngrp[s]; ++g) {
+        const WgGroup& G = a.grp[s][g];
+        tc::tma_load_4d(sX + G.slot_off, &tm.t[G.map], &bars->full[stage], cc * a.NC, x0 + G.dx, y0 + G.dy, n);
+      }
       if (++stage == (uint32_t)a.stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1 && lane == 0) {
@@ -91,13 +111,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
       tc::fence_after_sync();
       const uint32_t a_base = tc::smem_u32(smem + (size_t)stage * a.stage_bytes);
       const uint32_t x_base = a_base + (uint32_t)real_chunks * a.a_slot_bytes;
-      for (int r = 0; r < a.KS; ++r) {
+      for (int g = 0; g < a.ngrp[s]; ++g) {
+        const WgGroup& G = a.grp[s][g];
+        for (int r = 0; r < G.nr; ++r) {
 #pragma unroll 1
-        for (int k16 = 0; k16 < 8; ++k16) {
-          const uint64_t da = tc::make_smem_desc(a_base + (uint32_t)(k16 * 16) * a.rowA, a.a_lbo, 8 * a.rowA, a.layoutA);
-          const uint64_t db = tc::make_smem_desc(x_base + (uint32_t)(r * a.tw + k16 * 16) * a.rowB, 0, 8 * a.rowB,
-                                                 a.layoutB);
-          tc::umma_bf16(tmem + (uint32_t)(r * a.NC), da, db, a.idesc, (accumulate | (uint32_t)(k16 > 0)));
+          for (int k16 = 0; k16 < 8; ++k16) {
+            const uint64_t da = tc::make_smem_desc(a_base + (uint32_t)(k16 * 16) * a.rowA, a.a_lbo, 8 * a.rowA, a.layoutA);
+            const uint64_t db = tc::make_smem_desc(x_base + G.slot_off + (uint32_t)(r * a.tw + k16 * 16) * a.rowB, 0,
+                                                   8 * a.rowB, a.layoutB);
+            tc::umma_bf16(tmem + (uint32_t)(G.ky[r] * a.NC), da, db, a.idesc, (accumulate | (uint32_t)(k16 > 0)));
+          }
         }
       }
       accumulate = 1;
@@ -116,13 +139,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
     const int co = cb * a.M + row;
     const bool row_ok = row >= 0 && row < (a.MC < 64 ? a.MC : a.M) && co < a.Cout;
     const bool has_work = ps < a.tiles_total;  // a split with no tiles left its TMEM untouched: write zeros
-    for (int r = 0; r < a.KS; ++r) {
-      const int tap = r * a.KS + s;
+    for (int r = 0; r < a.KH; ++r) {
+      const int tap = r * a.KW + s;
       for (int c0 = 0; c0 < a.NC; c0 += 16) {
         float v[16];
         tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * a.NC + c0), v);
         if (row_ok) {
-          float* dst = a.partial + (((size_t)ps * a.KS * a.KS + tap) * a.Cout + co) * a.Cin + cc * a.NC + c0;
+          float* dst = a.partial + (((size_t)ps * a.KH * a.KW + tap) * a.Cout + co) * a.Cin + cc * a.NC + c0;
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             if (cc * a.NC + c0 + j < a.Cin) dst[j] = has_work ? v[j] : 0.f;
@@ -156,36 +179,81 @@ struct WgPlan {
   int grid;
 };
 
-int wg_plan(WgPlan& p, int B, int H, int W, int Cin, int Cout, int KS) {
+struct WgPlaneT {  // strided pixel-grid view of the tapped operand
+  const void* base;
+  long long ld_px, ld_row, ld_img;
+  int Hp, Wp;
+};
+
+inline int wg_floordiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
+
+// stride: 1 (plain conv: T index = p - pad + k) or 2 (T index = 2p - pad + k, through parity planes)
+int wg_plan(WgPlan& p, int B, int Hg, int Wg, int Cp, int Ct, int K, int pad, int stride) {
   WgArgs& a = p.a;
-  a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.KS = KS; a.pad = KS / 2;
+  if (K < 1 || K > kMaxKW || (stride != 1 && stride != 2))
+    return dp_set_error(DP_ERR_UNSUPPORTED, "wgrad_tc: K %d stride %d", K, stride);
+  a.B = B; a.H = Hg; a.W = Wg; a.Cin = Ct; a.Cout = Cp; a.KH = K; a.KW = K;
   const int cand[5][2] = {{8, 16}, {16, 8}, {4, 32}, {2, 64}, {1, 128}};
   long long best = -1;
   for (int i = 0; i < 5; ++i) {
-    long long t = (long long)dp::ceil_div(H, cand[i][0]) * dp::ceil_div(W, cand[i][1]);
+    long long t = (long long)dp::ceil_div(Hg, cand[i][0]) * dp::ceil_div(Wg, cand[i][1]);
     if (best < 0 || t < best) { best = t; a.th = cand[i][0]; a.tw = cand[i][1]; }
   }
-  a.tiles_y = dp::ceil_div(H, a.th);
-  a.tiles_x = dp::ceil_div(W, a.tw);
+  a.tiles_y = dp::ceil_div(Hg, a.th);
+  a.tiles_x = dp::ceil_div(Wg, a.tw);
   a.tiles_total = (long long)B * a.tiles_y * a.tiles_x;
-  a.MC = Cout >= 64 ? 64 : (Cout > 16 ? 32 : 16);
-  a.M = Cout > 64 ? 128 : 64;
+  a.MC = Cp >= 64 ? 64 : (Cp > 16 ? 32 : 16);
+  a.M = Cp > 64 ? 128 : 64;
   a.m_chunks = a.M / a.MC;
-  a.co_blocks = dp::ceil_div(Cout, a.M);
-  a.NC = Cin >= 64 ? 64 : (Cin > 16 ? 32 : 16);
-  a.ci_chunks = dp::ceil_div(Cin, a.NC);
+  a.co_blocks = dp::ceil_div(Cp, a.M);
+  a.NC = Ct >= 64 ? 64 : (Ct > 16 ? 32 : 16);
+  a.ci_chunks = dp::ceil_div(Ct, a.NC);
   a.rowA = a.MC * 2; a.rowB = a.NC * 2;
   a.layoutA = tc::swizzle_for_row_bytes(a.rowA);
   a.layoutB = tc::swizzle_for_row_bytes(a.rowB);
   a.idesc = tc::make_idesc_bf16(a.M, a.NC, 1, 1);
   a.a_box_bytes = 128u * a.rowA;
   a.a_slot_bytes = (a.a_box_bytes + 1023u) & ~1023u;
-  a.x_box_bytes = (uint32_t)((a.th + 2 * a.pad) * a.tw) * a.rowB;
-  a.x_slot_bytes = (a.x_box_bytes + 1023u) & ~1023u;
+  // tapped-operand groups per horizontal tap
+  uint32_t max_x = 0;
+  for (int kx = 0; kx < K; ++kx) {
+    a.ngrp[kx] = 0;
+    uint32_t off = 0;
+    if (stride == 1) {
+      WgGroup& G = a.grp[kx][0];
+      G.map = kx * 2; G.dx = kx - pad; G.dy = -pad; G.nr = K;
+      if (K > 3) return dp_set_error(DP_ERR_UNSUPPORTED, "wgrad_tc: stride-1 K %d", K);
+      for (int r = 0; r < 3; ++r) G.ky[r] = r < K ? r : 0;
+      G.box_bytes = (uint32_t)((a.th + K - 1) * a.tw) * a.rowB;
+      G.slot_off = 0;
+      off = (G.box_bytes + 1023u) & ~1023u;
+      a.ngrp[kx] = 1;
+    } else {
+      for (int py = 0; py < 2; ++py) {
+        WgGroup G;
+        G.nr = 0; G.dy = 0; G.dx = wg_floordiv2(kx - pad); G.map = kx * 2 + py;
+        for (int ky = 0; ky < K; ++ky) {
+          if (((ky - pad) & 1) != py) continue;
+          const int dy = wg_floordiv2(ky - pad);
+          if (G.nr == 0) G.dy = dy;
+          else if (dy != G.dy + G.nr) return dp_set_error(DP_ERR_UNSUPPORTED, "wgrad_tc: taps not contiguous");
+          if (G.nr >= 3) return dp_set_error(DP_ERR_UNSUPPORTED, "wgrad_tc: too many taps per group");
+          G.ky[G.nr++] = ky;
+        }
+        if (G.nr == 0) continue;
+        for (int r = G.nr; r < 3; ++r) G.ky[r] = 0;
+        G.box_bytes = (uint32_t)((a.th + G.nr - 1) * a.tw) * a.rowB;
+        G.slot_off = off;
+        off += (G.box_bytes + 1023u) & ~1023u;
+        a.grp[kx][a.ngrp[kx]++] = G;
+      }
+    }
+    if (off > max_x) max_x = off;
+  }
   const int real_chunks = a.MC < 64 ? 1 : a.m_chunks;
   a.a_lbo = a.MC < 64 ? 0u : a.a_slot_bytes;
-  a.stage_bytes = real_chunks * a.a_slot_bytes + a.x_slot_bytes;
-  const int base_ctas = KS * a.co_blocks * a.ci_chunks;
+  a.stage_bytes = real_chunks * a.a_slot_bytes + max_x;
+  const int base_ctas = K * a.co_blocks * a.ci_chunks;
   int ps = (2 * dp::kNumSMs + base_ctas - 1) / base_ctas;
   if (ps > a.tiles_total) ps = (int)a.tiles_total;
   if (ps < 1) ps = 1;
@@ -202,13 +270,59 @@ int wg_plan(WgPlan& p, int B, int H, int W, int Cin, int Cout, int KS) {
   return DP_OK;
 }
 
+int wg_launch(WgPlan& p, const void* P, long long p_ld, const WgPlaneT* planes /*[kMaxKW*2], indexed by map id*/, int B,
+              float* grad, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  WgArgs& a = p.a;
+  const int K = a.KH;
+  const size_t need = (size_t)a.psplit * K * K * a.Cout * a.Cin * sizeof(float);
+  if (workspace_bytes < need) return dp_set_error(DP_ERR_WORKSPACE, "wgrad_tc: workspace %zu < %zu", workspace_bytes, need);
+  a.partial = reinterpret_cast<float*>(workspace);
+  WgMaps tm;
+  {
+    uint64_t dims[4] = {(uint64_t)a.Cout, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)p_ld * 2, (uint64_t)a.W * p_ld * 2, (uint64_t)a.H * a.W * p_ld * 2};
+    uint32_t box[4] = {(uint32_t)a.MC, (uint32_t)a.tw, (uint32_t)a.th, 1};
+    int rc = dp_make_tmap_bf16(&tm.p, P, 4, dims, str, box, nullptr, a.rowA);
+    if (rc) return rc;
+  }
+  bool have_first = false;
+  CUtensorMap first;
+  for (int kx = 0; kx < K; ++kx)
+    for (int g = 0; g < a.ngrp[kx]; ++g) {
+      const WgGroup& G = a.grp[kx][g];
+      const WgPlaneT* pl = &planes[G.map];   // planes are indexed like the tensor maps: [kx*2 + group parity]
+      uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)pl->Wp, (uint64_t)pl->Hp, (uint64_t)B};
+      uint64_t str[3] = {(uint64_t)pl->ld_px * 2, (uint64_t)pl->ld_row * 2, (uint64_t)pl->ld_img * 2};
+      uint32_t box[4] = {(uint32_t)a.NC, (uint32_t)a.tw, (uint32_t)(a.th + G.nr - 1), 1};
+      int rc = dp_make_tmap_bf16(&tm.t[G.map], pl->base, 4, dims, str, box, nullptr, a.rowB);
+      if (rc) return rc;
+      if (!have_first) { first = tm.t[G.map]; have_first = true; }
+    }
+  for (int i = 0; i < kMaxKW * 2; ++i) {
+    bool used = false;
+    for (int kx = 0; kx < K; ++kx)
+      for (int g = 0; g < a.ngrp[kx]; ++g) used |= (a.grp[kx][g].map == i);
+    if (!used) tm.t[i] = first;
+  }
+  cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+  if (e != cudaSuccess) return dp_set_error(DP_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  wgrad_tc_kernel<<<p.grid, kThreads, p.smem, stream>>>(tm, a);
+  DP_CHECK_LAUNCH("wgrad_tc_kernel");
+  const long long total = (long long)K * K * a.Cout * a.Cin;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4 * dp::kNumSMs) blocks = 4 * dp::kNumSMs;
+  wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(a.partial, a.psplit, K * K, a.Cout, a.Cin, grad, accumulate);
+  DP_CHECK_LAUNCH("wgrad_reduce_kernel");
+  return DP_OK;
+}
+
 }  // namespace
 
 extern "C" {
 
 size_t dp_conv2d_wgrad_tc_workspace(int B, int H, int W, int Cin, int Cout, int KS) {
   WgPlan p;
-  wg_plan(p, B, H, W, Cin, Cout, KS);
+  if (wg_plan(p, B, H, W, Cout, Cin, KS, KS / 2, 1)) return 0;
   return (size_t)p.a.psplit * KS * KS * Cout * Cin * sizeof(float);
 }
 
@@ -220,37 +334,46 @@ int dp_conv2d_wgrad_tc(const void* x, long long x_ld, const void* dy, long long 
   DP_CHECK_ARG(Cin % 8 == 0 && Cout % 8 == 0 && x_ld % 8 == 0 && dy_ld % 8 == 0,
                "dp_conv2d_wgrad_tc: channels / strides must be multiples of 8");
   WgPlan p;
-  wg_plan(p, B, H, W, Cin, Cout, KS);
-  WgArgs& a = p.a;
-  const size_t need = (size_t)a.psplit * KS * KS * Cout * Cin * sizeof(float);
-  if (workspace_bytes < need) return dp_set_error(DP_ERR_WORKSPACE, "dp_conv2d_wgrad_tc: workspace %zu < %zu",
-                                                  workspace_bytes, need);
-  a.partial = reinterpret_cast<float*>(workspace);
-  CUtensorMap tmDY, tmX;
-  {
-    uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-    uint64_t str[3] = {(uint64_t)dy_ld * 2, (uint64_t)W * dy_ld * 2, (uint64_t)H * W * dy_ld * 2};
-    uint32_t box[4] = {(uint32_t)a.MC, (uint32_t)a.tw, (uint32_t)a.th, 1};
-    int rc = dp_make_tmap_bf16(&tmDY, dy, 4, dims, str, box, nullptr, a.rowA);
-    if (rc) return rc;
-  }
-  {
-    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-    uint64_t str[3] = {(uint64_t)x_ld * 2, (uint64_t)W * x_ld * 2, (uint64_t)H * W * x_ld * 2};
-    uint32_t box[4] = {(uint32_t)a.NC, (uint32_t)a.tw, (uint32_t)(a.th + 2 * a.pad), 1};
-    int rc = dp_make_tmap_bf16(&tmX, x, 4, dims, str, box, nullptr, a.rowB);
-    if (rc) return rc;
-  }
-  cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
-  if (e != cudaSuccess) return dp_set_error(DP_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  wgrad_tc_kernel<<<p.grid, kThreads, p.smem, stream>>>(tmDY, tmX, a);
-  DP_CHECK_LAUNCH("wgrad_tc_kernel");
-  const long long total = (long long)KS * KS * Cout * Cin;
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 4 * dp::kNumSMs) blocks = 4 * dp::kNumSMs;
-  wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(a.partial, a.psplit, KS * KS, Cout, Cin, grad_oihw, accumulate);
-  DP_CHECK_LAUNCH("wgrad_reduce_kernel");
-  return DP_OK;
+  int rc = wg_plan(p, B, H, W, Cout, Cin, KS, KS / 2, 1);
+  if (rc) return rc;
+  WgPlaneT planes[kMaxKW * 2];
+  for (int i = 0; i < kMaxKW * 2; ++i) planes[i] = WgPlaneT{x, x_ld, (long long)W * x_ld, (long long)H * W * x_ld, H, W};
+  return wg_launch(p, dy, dy_ld, planes, B, grad_oihw, accumulate, workspace, workspace_bytes, stream);
+}
+
+/* grad[cp][ct][ky][kx] (+)= sum over plain-grid pixels p of P[p][cp] * T[2p - pad + k][ct]  (K x K taps, stride 2):
+ *   nn.Conv2d(k3,s2,p1):          P = dY (B,Ho,Wo,O), T = X  (B,Hi,Wi,I)  -> weight.grad [O][I][3][3]
+ *   nn.ConvTranspose2d(k4,s2,p1): P = X  (B,Hi,Wi,I), T = dY (B,Ho,Wo,O)  -> weight.grad [I][O][4][4] */
+size_t dp_conv2d_wgrad_tc_s2_workspace(int B, int Hp, int Wp, int Cp, int Ct, int K, int pad) {
+  WgPlan p;
+  if (wg_plan(p, B, Hp, Wp, Cp, Ct, K, pad, 2)) return 0;
+  return (size_t)p.a.psplit * K * K * Cp * Ct * sizeof(float);
+}
+
+int dp_conv2d_wgrad_tc_s2(const void* P, long long p_ld, int Hp, int Wp, int Cp, const void* T, long long t_ld, int Ht,
+                          int Wt, int Ct, int B, int K, int pad, float* grad, int accumulate, void* workspace,
+                          size_t workspace_bytes, cudaStream_t stream) {
+  DP_CHECK_ARG(P && T && grad && workspace, "dp_conv2d_wgrad_tc_s2: null pointer");
+  DP_CHECK_ARG(Cp % 8 == 0 && Ct % 8 == 0 && p_ld % 8 == 0 && t_ld % 8 == 0,
+               "dp_conv2d_wgrad_tc_s2: channels / strides must be multiples of 8");
+  WgPlan p;
+  int rc = wg_plan(p, B, Hp, Wp, Cp, Ct, K, pad, 2);
+  if (rc) return rc;
+  // planes[kx*2 + py]: parity plane (py, px(kx)) of T
+  WgPlaneT planes[kMaxKW * 2];
+  for (int i = 0; i < kMaxKW * 2; ++i) planes[i] = WgPlaneT{T, t_ld, (long long)Wt * t_ld, (long long)Ht * Wt * t_ld, Ht, Wt};
+  const bf16* tb = reinterpret_cast<const bf16*>(T);
+  for (int kx = 0; kx < K; ++kx)
+    for (int py = 0; py < 2; ++py) {
+      const int px = (kx - pad) & 1;
+      WgPlaneT& q = planes[kx * 2 + py];
+      q.base = tb + ((long long)py * Wt + px) * t_ld;
+      q.ld_px = 2 * t_ld; q.ld_row = 2LL * Wt * t_ld; q.ld_img = (long long)Ht * Wt * t_ld;
+      q.Hp = (Ht - py + 1) / 2; q.Wp = (Wt - px + 1) / 2;
+      if (q.Hp < 1) q.Hp = 1;
+      if (q.Wp < 1) q.Wp = 1;
+    }
+  return wg_launch(p, P, p_ld, planes, B, grad, accumulate, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

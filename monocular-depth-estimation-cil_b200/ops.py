@@ -260,6 +260,45 @@ def _gather(inp, wp, bias, Ho, Wo, Co, KH, KW, stride, pad, transposed, relu=Fal
     return out
 
 
+def _tc_down2(inp, wp, bias, Ho, Wo, Co, K, pad, stats=False):
+    """stride-2 conv rule on tcgen05 (parity planes)"""
+    B, Hi, Wi, Ci = inp.shape
+    out = _nhwc(B, Ho, Wo, Co, inp.device)
+    st = None
+    if stats:
+        g = L.lib().dp_conv2d_tc_down2_grid(B, Ho, Wo, Ci, Co, K, pad)
+        st = torch.empty(g, 2, Co, dtype=torch.float32, device=inp.device)
+    L.check(L.lib().dp_conv2d_tc_down2(L.ptr(inp), _ld(inp), B, Hi, Wi, Ci, L.ptr(wp), wp.shape[2], Co, K, pad,
+                                       L.ptr(bias), 0, L.ptr(out), Co, Ho, Wo, L.ptr(st), L.stream()))
+    return out, st
+
+
+def _tc_up2(inp, wp, bias, Ho, Wo, Co, K, pad):
+    """transposed stride-2 rule on tcgen05 (four output phases)"""
+    B, Hi, Wi, Ci = inp.shape
+    out = _nhwc(B, Ho, Wo, Co, inp.device)
+    L.check(L.lib().dp_conv2d_tc_up2(L.ptr(inp), _ld(inp), B, Hi, Wi, Ci, L.ptr(wp), wp.shape[2], Co, K, pad,
+                                     L.ptr(bias), 0, L.ptr(out), Co, Ho, Wo, L.stream()))
+    return out
+
+
+def _wgrad_tc_s2(P, T, K, pad):
+    """grad[cp][ct][ky][kx] = sum_p P[p][cp] * T[2p - pad + k][ct] on tcgen05"""
+    B, Hp, Wp, Cp = P.shape
+    _, Ht, Wt, Ct = T.shape
+    lib = L.lib()
+    nb = lib.dp_conv2d_wgrad_tc_s2_workspace(B, Hp, Wp, Cp, Ct, K, pad)
+    ws = torch.empty(nb, dtype=torch.uint8, device=P.device)
+    out = torch.empty(Cp, Ct, K, K, dtype=torch.float32, device=P.device)
+    L.check(lib.dp_conv2d_wgrad_tc_s2(L.ptr(P), _ld(P), Hp, Wp, Cp, L.ptr(T), _ld(T), Ht, Wt, Ct, B, K, pad, L.ptr(out), 0,
+                                      L.ptr(ws), nb, L.stream()))
+    return out
+
+
+def _tc_stride2_ok(K, stride, pad, Ci, Co):
+    return stride == 2 and pad == 1 and K in (3, 4) and Ci % 8 == 0 and Co % 8 == 0
+
+
 def _wgrad_direct(P, T, KH, KW, stride, pad, perm):
     B, Hp, Wp, Cp = P.shape
     _, Ht, Wt, Ct = T.shape
@@ -281,7 +320,10 @@ class _ConvStrided(torch.autograd.Function):
         B, Hi, Wi, _ = x.shape
         Ho = (Hi + 2 * pad - KH) // stride + 1
         Wo = (Wi + 2 * pad - KW) // stride + 1
-        out = _gather(x, PACKS.get(weight, 0, 0), _f32(bias), Ho, Wo, O, KH, KW, stride, pad, False)
+        if KH == KW and _tc_stride2_ok(KH, stride, pad, I, O):
+            out, _ = _tc_down2(x, PACKS.get(weight, 0, 0), _f32(bias), Ho, Wo, O, KH, pad)
+        else:
+            out = _gather(x, PACKS.get(weight, 0, 0), _f32(bias), Ho, Wo, O, KH, KW, stride, pad, False)
         ctx.save_for_backward(x, weight)
         ctx.geom = (stride, pad, bias is not None)
         return out
@@ -295,9 +337,15 @@ class _ConvStrided(torch.autograd.Function):
         g = _dense(g)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = _gather(g, PACKS.get(weight, 1, 0), None, Hi, Wi, I, KH, KW, stride, pad, True)
+            if KH == KW and _tc_stride2_ok(KH, stride, pad, O, I):
+                dx = _tc_up2(g, PACKS.get(weight, 1, 0), None, Hi, Wi, I, KH, pad)
+            else:
+                dx = _gather(g, PACKS.get(weight, 1, 0), None, Hi, Wi, I, KH, KW, stride, pad, True)
         if ctx.needs_input_grad[1]:
-            dw = _wgrad_direct(g, x, KH, KW, stride, pad, 1).to(weight.dtype)      # [O][I][KH][KW]
+            if KH == KW and _tc_stride2_ok(KH, stride, pad, I, O):
+                dw = _wgrad_tc_s2(g, x, KH, pad).to(weight.dtype)
+            else:
+                dw = _wgrad_direct(g, x, KH, KW, stride, pad, 1).to(weight.dtype)      # [O][I][KH][KW]
         if has_bias and ctx.needs_input_grad[2]:
             db = _colsum(g)
         return dx, dw, db, None, None
@@ -312,7 +360,10 @@ class _ConvTransposed(torch.autograd.Function):
         B, Hi, Wi, _ = x.shape
         Ho = (Hi - 1) * stride - 2 * pad + KH
         Wo = (Wi - 1) * stride - 2 * pad + KW
-        out = _gather(x, PACKS.get(weight, 1, 0), _f32(bias), Ho, Wo, O, KH, KW, stride, pad, True)
+        if KH == KW and _tc_stride2_ok(KH, stride, pad, I, O):
+            out = _tc_up2(x, PACKS.get(weight, 1, 0), _f32(bias), Ho, Wo, O, KH, pad)
+        else:
+            out = _gather(x, PACKS.get(weight, 1, 0), _f32(bias), Ho, Wo, O, KH, KW, stride, pad, True)
         ctx.save_for_backward(x, weight)
         ctx.geom = (stride, pad, bias is not None)
         return out
@@ -326,9 +377,15 @@ class _ConvTransposed(torch.autograd.Function):
         g = _dense(g)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = _gather(g, PACKS.get(weight, 0, 0), None, Hi, Wi, I, KH, KW, stride, pad, False)
+            if KH == KW and _tc_stride2_ok(KH, stride, pad, O, I):
+                dx, _ = _tc_down2(g, PACKS.get(weight, 0, 0), None, Hi, Wi, I, KH, pad)
+            else:
+                dx = _gather(g, PACKS.get(weight, 0, 0), None, Hi, Wi, I, KH, KW, stride, pad, False)
         if ctx.needs_input_grad[1]:
-            dw = _wgrad_direct(x, g, KH, KW, stride, pad, 1).to(weight.dtype)      # [I][O][KH][KW]
+            if KH == KW and _tc_stride2_ok(KH, stride, pad, I, O):
+                dw = _wgrad_tc_s2(x, g, KH, pad).to(weight.dtype)
+            else:
+                dw = _wgrad_direct(x, g, KH, KW, stride, pad, 1).to(weight.dtype)      # [I][O][KH][KW]
         if has_bias and ctx.needs_input_grad[2]:
             db = _colsum(g)
         return dx, dw, db, None, None

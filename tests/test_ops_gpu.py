@@ -76,6 +76,8 @@ CONV_CASES = [
     # kind, Cin, Cout, k, stride, pad, B, H, W
     ("conv", 32, 32, 3, 2, 1, 2, 32, 48), ("conv", 32, 32, 3, 2, 1, 1, 17, 23), ("conv", 512, 512, 3, 2, 1, 1, 16, 20),
     ("convT", 32, 32, 4, 2, 1, 2, 8, 12), ("convT", 128, 128, 4, 4, 0, 1, 4, 5), ("convT", 256, 256, 2, 2, 0, 1, 4, 5),
+    ("conv", 32, 32, 3, 2, 1, 2, 224, 288), ("convT", 32, 32, 4, 2, 1, 2, 112, 144), ("conv", 64, 48, 3, 2, 1, 1, 18, 30),
+    ("convT", 64, 32, 4, 2, 1, 1, 9, 15), ("conv", 32, 32, 3, 2, 1, 1, 8, 8), ("convT", 16, 16, 4, 2, 1, 1, 7, 9),
 ]
 
 
