@@ -202,7 +202,7 @@ int wg_plan(WgPlan& p, int B, int Hg, int Wg, int Cp, int Ct, int K, int pad, in
   a.tiles_y = dp::ceil_div(Hg, a.th);
   a.tiles_x = dp::ceil_div(Wg, a.tw);
   a.tiles_total = (long long)B * a.tiles_y * a.tiles_x;
-  a.MC = Cp >= 64 ? 64 : (Cp > 16 ? 32 : 16);
+  a.MC = Cp > 32 ? 64 : (Cp > 16 ? 32 : 16);
   a.M = Cp > 64 ? 128 : 64;
   a.m_chunks = a.M / a.MC;
   a.co_blocks = dp::ceil_div(Cp, a.M);

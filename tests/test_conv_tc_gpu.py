@@ -120,7 +120,8 @@ WG_CASES = [
     (2, 16, 32, 64, 64, 3), (1, 14, 18, 512, 512, 3), (2, 28, 36, 256, 256, 3), (2, 31, 45, 64, 32, 3),
     (2, 24, 40, 32, 32, 3), (1, 24, 40, 32, 16, 3), (1, 24, 40, 16, 16, 3), (1, 28, 36, 136, 256, 3),
     (1, 56, 72, 48, 128, 3), (1, 14, 18, 384, 512, 3), (2, 20, 28, 512, 256, 1), (1, 24, 40, 64, 32, 1),
-    (1, 24, 40, 32, 16, 1), (1, 16, 20, 384, 128, 1), (2, 112, 144, 64, 64, 3),
+    (1, 24, 40, 32, 16, 1), (1, 16, 20, 384, 128, 1), (2, 112, 144, 64, 64, 3), (1, 20, 28, 64, 48, 3),
+    (1, 20, 28, 32, 64, 3), (1, 20, 28, 128, 136, 3), (1, 20, 28, 48, 48, 1),
 ]
 
 
