@@ -114,6 +114,7 @@ class _Sig:
     dp_conv2d_wgrad_tc_s2_workspace = (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int])
     dp_conv2d_wgrad_tc_s2 = (c_int, [P, c_ll, c_int, c_int, c_int, P, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, P,
                                      c_int, P, c_size_t, P])
+    dp_debug_set_buffer = (None, [P])
     dp_umma_probe = (c_int, [P, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                              c_int, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32), P, c_int, P])
 

@@ -252,44 +252,59 @@ __global__ void __launch_bounds__(256) head_conv_dgrad_kernel(const float* __res
   }
 }
 
-// weight + bias gradient partials: part[block][KS*KS*C + 1]
+// weight + bias gradient partials: part[block][KS*KS*C + 1].
+// Thread = (pixel lane, tap, 8-channel group): it walks its lane's pixels, multiplies the (ReLU-masked) upstream
+// gradient by the 8 input channels under its tap and keeps 8 fp32 accumulators; the pixel lanes are then folded
+// through shared memory.  x is re-read once per tap from L1/L2 (9 x 32 B per pixel for C=16), g is a broadcast load.
 __global__ void __launch_bounds__(256) head_conv_wgrad_kernel(const float* __restrict__ dout, const float* __restrict__ out,
                                                               int relu, const bf16* __restrict__ x, long long x_ld, int B,
                                                               int H, int W, int C, int KS, float* __restrict__ part) {
-  extern __shared__ float sacc[];  // [KS*KS*C + 1]
+  extern __shared__ float sacc[];  // [lanes][ncombo*8 + 1]
+  const int pad = KS / 2, C8 = C / 8;
+  const int ncombo = KS * KS * C8;            // (tap, channel group) pairs
+  const int lanes = 256 / ncombo;             // pixel lanes per block (>= 1 since ncombo <= 72 is enforced by the host)
+  const int combo = threadIdx.x % ncombo, pl = threadIdx.x / ncombo;
+  const int tap = combo / C8, c8 = combo % C8;
+  const int dy = tap / KS - pad, dx = tap % KS - pad;
   const int nacc = KS * KS * C + 1;
-  for (int i = threadIdx.x; i < nacc; i += blockDim.x) sacc[i] = 0.f;
-  __syncthreads();
-  const int pad = KS / 2;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float bsum = 0.f;
   const size_t total = (size_t)B * H * W;
-  // each warp walks output pixels; lane l owns accumulators l, l+32, ... (tap-major, channel-minor)
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  float local[20];  // up to ceil(577/32) accumulators per lane for C=64, KS=3
-  const int per_lane = (nacc + 31) / 32;
-  for (int k = 0; k < per_lane && k < 20; ++k) local[k] = 0.f;
-  for (size_t o = (size_t)blockIdx.x * nwarp + warp; o < total; o += (size_t)gridDim.x * nwarp) {
-    float g = __ldg(dout + o);
-    if (relu && !(__ldg(out + o) > 0.f)) g = 0.f;
-    if (g == 0.f) continue;
-    const int xx = (int)(o % W);
-    const int yy = (int)((o / W) % H);
-    const int b = (int)(o / ((size_t)W * H));
-    for (int k = 0; k < per_lane && k < 20; ++k) {
-      const int idx = k * 32 + lane;
-      if (idx >= nacc) break;
-      if (idx == nacc - 1) { local[k] += g; continue; }
-      const int tap = idx / C, c = idx % C;
-      const int iy = yy + tap / KS - pad, ix = xx + tap % KS - pad;
+  if (pl < lanes) {
+    for (size_t o = (size_t)blockIdx.x * lanes + pl; o < total; o += (size_t)gridDim.x * lanes) {
+      float g = __ldg(dout + o);
+      if (relu && !(__ldg(out + o) > 0.f)) g = 0.f;
+      if (g == 0.f) continue;
+      if (combo == 0) bsum += g;
+      const int xx = (int)(o % W);
+      const int yy = (int)((o / W) % H);
+      const int iy = yy + dy, ix = xx + dx;
       if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
-      local[k] += g * __bfloat162float(x[(((size_t)b * H + iy) * W + ix) * x_ld + c]);
+      const size_t b = o / ((size_t)W * H);
+      float v[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + ((b * H + iy) * W + ix) * x_ld + c8 * 8)), v);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] += g * v[q];
     }
   }
-  for (int k = 0; k < per_lane && k < 20; ++k) {
-    const int idx = k * 32 + lane;
-    if (idx < nacc) atomicAdd(&sacc[idx], local[k]);
+  const int stride = ncombo * 8 + 1;
+  if (pl < lanes) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) sacc[pl * stride + combo * 8 + q] = acc[q];
+    if (combo == 0) sacc[pl * stride + ncombo * 8] = bsum;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < nacc; i += blockDim.x) part[(size_t)blockIdx.x * nacc + i] = sacc[i];
+  for (int i = threadIdx.x; i < nacc; i += blockDim.x) {
+    float s = 0.f;
+    if (i == nacc - 1) {
+      for (int l = 0; l < lanes; ++l) s += sacc[l * stride + ncombo * 8];
+    } else {
+      const int t = i / C, c = i % C;                // output index order: tap-major, channel-minor
+      const int src = (t * C8 + c / 8) * 8 + (c % 8);
+      for (int l = 0; l < lanes; ++l) s += sacc[l * stride + src];
+    }
+    part[(size_t)blockIdx.x * nacc + i] = s;
+  }
 }
 
 __global__ void head_conv_wgrad_reduce_kernel(const float* __restrict__ part, int nblocks, int C, int KS,
@@ -394,7 +409,7 @@ int dp_head_conv_bwd(const float* dout, const float* out, int relu, const void* 
                      void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   DP_CHECK_ARG(dout && x && w && workspace && C % 8 == 0 && (KS == 1 || KS == 3) && (!relu || out),
                "dp_head_conv_bwd: bad arguments");
-  DP_CHECK_ARG(KS * KS * C + 1 <= 640, "dp_head_conv_bwd: C too large for the head kernel");
+  DP_CHECK_ARG(KS * KS * (C / 8) <= 72, "dp_head_conv_bwd: C too large for the head kernel");
   if (workspace_bytes < dp_head_conv_bwd_workspace(C, KS))
     return dp_set_error(DP_ERR_WORKSPACE, "dp_head_conv_bwd: workspace too small");
   if (dx) {
@@ -404,7 +419,9 @@ int dp_head_conv_bwd(const float* dout, const float* out, int relu, const void* 
   }
   if (dw) {
     const int nacc = KS * KS * C + 1;
-    head_conv_wgrad_kernel<<<kHeadWgBlocks, 256, nacc * sizeof(float), stream>>>(dout, out, relu, (const bf16*)x, x_ld, B,
+    const int ncombo = KS * KS * (C / 8);
+    const size_t wg_smem = (size_t)(256 / ncombo) * (ncombo * 8 + 1) * sizeof(float);
+    head_conv_wgrad_kernel<<<kHeadWgBlocks, 256, wg_smem, stream>>>(dout, out, relu, (const bf16*)x, x_ld, B,
                                                                                  H, W, C, KS, (float*)workspace);
     DP_CHECK_LAUNCH("head_conv_wgrad_kernel");
     head_conv_wgrad_reduce_kernel<<<dp::ceil_div(nacc, 128), 128, 0, stream>>>((const float*)workspace, kHeadWgBlocks, C,

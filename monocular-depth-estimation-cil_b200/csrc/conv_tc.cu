@@ -59,6 +59,7 @@ struct ConvArgs {
   int BN, n_blocks;
   int stages, resident;
   int ncols, max_nr, nslots;
+  int halo, pitch;                // halo mode: one (th+2) x (tw+2) box per channel chunk serves all nine taps
   ColLoad cols[kMaxCols];
   uint32_t a_slot_bytes, b_tap_bytes, row_bytes, layout, sbo, idesc;
   uint32_t b_box_bytes;  // bytes TMA actually writes per weight box (slots are rounded up to 1024)
@@ -167,11 +168,18 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
     // ================= TMA producer =================
     if (a.resident) {
       tc::mbar_expect_tx(&bars->resident_full, (uint32_t)(a.nslots * a.kchunks) * a.b_box_bytes);
-      for (int c = 0; c < a.ncols; ++c)
-        for (int r = 0; r < a.cols[c].nr; ++r)
+      if (a.halo) {
+        for (int tap = 0; tap < 9; ++tap)
           for (int kc = 0; kc < a.kchunks; ++kc)
-            tc::tma_load_3d(s_res + (size_t)(a.cols[c].wslot[r] * a.kchunks + kc) * a.b_tap_bytes, &tm.b,
-                            &bars->resident_full, kc * a.KB, 0, a.cols[c].wtap[r]);
+            tc::tma_load_3d(s_res + (size_t)(tap * a.kchunks + kc) * a.b_tap_bytes, &tm.b, &bars->resident_full,
+                            kc * a.KB, 0, tap);
+      } else {
+        for (int c = 0; c < a.ncols; ++c)
+          for (int r = 0; r < a.cols[c].nr; ++r)
+            for (int kc = 0; kc < a.kchunks; ++kc)
+              tc::tma_load_3d(s_res + (size_t)(a.cols[c].wslot[r] * a.kchunks + kc) * a.b_tap_bytes, &tm.b,
+                              &bars->resident_full, kc * a.KB, 0, a.cols[c].wtap[r]);
+      }
     }
     uint32_t stage = 0, phase = 0;
     for (long long item = blockIdx.x; item < a.total_items; item += gridDim.x) {
@@ -200,6 +208,9 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
     uint32_t stage = 0, phase = 0;
     int it = 0;
     const int kk_n = a.KB / 16;
+    const uint32_t b_hi = tc::desc_hi(a.sbo, a.layout);                                   // also A's hi outside halo mode
+    const uint32_t a_hi_halo = tc::desc_hi((uint32_t)a.pitch * a.row_bytes, a.layout);
+    const uint32_t res_base = tc::smem_u32(s_res);
     for (long long item = blockIdx.x; item < a.total_items; item += gridDim.x, ++it) {
       const int buf = it & 1;
       tc::mbar_wait(&bars->tmem_empty[buf], ((it >> 1) & 1) ^ 1);
@@ -212,16 +223,41 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
           tc::mbar_wait(&bars->full[stage], phase);
           tc::fence_after_sync();
           const uint32_t a_base = tc::smem_u32(s_stage + (size_t)stage * stage_bytes);
-          for (int r = 0; r < col.nr; ++r) {
-            const uint32_t ar = a_base + (uint32_t)(r * a.tw) * a.row_bytes;
-            const uint32_t br = a.resident
-                                    ? tc::smem_u32(s_res) + (uint32_t)(col.wslot[r] * a.kchunks + kc) * a.b_tap_bytes
-                                    : a_base + a.a_slot_bytes + (uint32_t)r * a.b_tap_bytes;
-            for (int kk = 0; kk < kk_n; ++kk) {
-              const uint64_t da = tc::make_smem_desc(ar + kk * 32, 16, a.sbo, a.layout);
-              const uint64_t db = tc::make_smem_desc(br + kk * 32, 16, a.sbo, a.layout);
-              tc::umma_bf16(d_tmem, da, db, a.idesc, accumulate);
+          if (a.halo) {
+            // all nine taps read the same halo box: tap (r,s) starts (r*pitch + s) pixel rows in; the 8-pixel patch
+            // rows are `pitch` rows apart (SBO).  The swizzle is a function of the absolute smem address, so neither
+            // offset needs to be atom aligned (tests/test_umma_probe_gpu.py::test_k_major_halo_addressing).
+            const uint32_t a_lo0 = tc::desc_lo(a_base, 16);
+            const uint32_t b_lo0 = tc::desc_lo(res_base + (uint32_t)kc * a.b_tap_bytes, 16);
+            const uint32_t row16 = a.row_bytes >> 4, btap16 = (a.b_tap_bytes * (uint32_t)a.kchunks) >> 4;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+              for (int s3 = 0; s3 < 3; ++s3) {
+                const uint32_t al = a_lo0 + (uint32_t)(r * a.pitch + s3) * row16;
+                const uint32_t bl = b_lo0 + (uint32_t)(r * 3 + s3) * btap16;
+                tc::umma_bf16_lohi(d_tmem, al, a_hi_halo, bl, b_hi, a.idesc, accumulate);
+                accumulate = 1;
+                if (kk_n > 1) tc::umma_bf16_lohi(d_tmem, al + 2, a_hi_halo, bl + 2, b_hi, a.idesc, 1);
+                if (kk_n > 2) {
+                  tc::umma_bf16_lohi(d_tmem, al + 4, a_hi_halo, bl + 4, b_hi, a.idesc, 1);
+                  tc::umma_bf16_lohi(d_tmem, al + 6, a_hi_halo, bl + 6, b_hi, a.idesc, 1);
+                }
+              }
+            }
+          } else {
+            const uint32_t b_base = a.resident ? res_base + (uint32_t)kc * a.b_tap_bytes : a_base + a.a_slot_bytes;
+            for (int r = 0; r < col.nr; ++r) {
+              const uint32_t al = tc::desc_lo(a_base + (uint32_t)(r * a.tw) * a.row_bytes, 16);
+              const uint32_t bl = tc::desc_lo(a.resident ? b_base + (uint32_t)(col.wslot[r] * a.kchunks) * a.b_tap_bytes
+                                                         : b_base + (uint32_t)r * a.b_tap_bytes, 16);
+              tc::umma_bf16_lohi(d_tmem, al, b_hi, bl, b_hi, a.idesc, accumulate);
               accumulate = 1;
+              if (kk_n > 1) tc::umma_bf16_lohi(d_tmem, al + 2, b_hi, bl + 2, b_hi, a.idesc, 1);
+              if (kk_n > 2) {
+                tc::umma_bf16_lohi(d_tmem, al + 4, b_hi, bl + 4, b_hi, a.idesc, 1);
+                tc::umma_bf16_lohi(d_tmem, al + 6, b_hi, bl + 6, b_hi, a.idesc, 1);
+              }
             }
           }
           tc::umma_commit(&bars->empty[stage]);  // frees the smem slot when these MMAs have read it
@@ -371,7 +407,8 @@ struct Plan {
 };
 
 // geometry that does not depend on pointers: tile shape, K/N blocking, stages, grid
-int make_plan(Plan& p, int B, int Hg, int Wg, int Cin, int Cout, const ColSpec* cols, int ncols, int want_stats) {
+int make_plan(Plan& p, int B, int Hg, int Wg, int Cin, int Cout, const ColSpec* cols, int ncols, int want_stats,
+              int allow_halo = 0) {
   ConvArgs& a = p.a;
   if (ncols < 1 || ncols > kMaxCols) return dp_set_error(DP_ERR_UNSUPPORTED, "conv_tc: %d column loads", ncols);
   a.B = B; a.H = Hg; a.W = Wg; a.Cout = Cout;
@@ -382,13 +419,20 @@ int make_plan(Plan& p, int B, int Hg, int Wg, int Cin, int Cout, const ColSpec* 
     long long t = (long long)dp::ceil_div(Hg, cand[i][0]) * dp::ceil_div(Wg, cand[i][1]);
     if (best < 0 || t < best) { best = t; a.th = cand[i][0]; a.tw = cand[i][1]; }
   }
-  a.tiles_y = dp::ceil_div(Hg, a.th);
-  a.tiles_x = dp::ceil_div(Wg, a.tw);
   a.KB = Cin > 32 ? 64 : (Cin > 16 ? 32 : 16);
   a.kchunks = dp::ceil_div(Cin, a.KB);
   a.n_blocks = dp::ceil_div(Cout, 160);
   a.BN = ((dp::ceil_div(Cout, a.n_blocks) + 15) / 16) * 16;
   a.row_bytes = a.KB * 2;
+  // halo mode (plain 3x3, whole weight set resident): 16x8 patches, one 18x10-pixel box per channel chunk
+  a.halo = 0;
+  a.pitch = 0;
+  if (allow_halo && a.n_blocks == 1) {
+    const size_t w9 = (size_t)9 * a.kchunks * (((size_t)a.BN * a.row_bytes + 1023) & ~size_t(1023));
+    if (w9 <= 100 * 1024) { a.halo = 1; a.th = 16; a.tw = 8; a.pitch = a.tw + 2; }
+  }
+  a.tiles_y = dp::ceil_div(Hg, a.th);
+  a.tiles_x = dp::ceil_div(Wg, a.tw);
   a.layout = tc::swizzle_for_row_bytes(a.row_bytes);
   a.sbo = 8 * a.row_bytes;
   a.idesc = tc::make_idesc_bf16(128, a.BN, 0, 0);
@@ -398,6 +442,16 @@ int make_plan(Plan& p, int B, int Hg, int Wg, int Cin, int Cout, const ColSpec* 
   a.max_nr = 0;
   a.nslots = 0;
   uint32_t max_box = 0;
+  if (a.halo) {
+    a.ncols = ncols = 1;
+    ColLoad& d = a.cols[0];
+    d.map = 0; d.dx = -1; d.dy = -1; d.nr = 3;
+    for (int r = 0; r < 3; ++r) { d.wtap[r] = 0; d.wslot[r] = 0; }
+    d.box_bytes = (uint32_t)((a.th + 2) * (a.tw + 2)) * a.row_bytes;
+    max_box = d.box_bytes;
+    a.max_nr = 3;
+    a.nslots = 9;
+  } else
   for (int c = 0; c < ncols; ++c) {
     ColLoad& d = a.cols[c];
     d.map = c; d.dx = cols[c].dx; d.dy = cols[c].dy; d.nr = cols[c].nr;
@@ -426,10 +480,11 @@ int make_plan(Plan& p, int B, int Hg, int Wg, int Cin, int Cout, const ColSpec* 
 }
 
 int launch(const Plane* planes, const ColSpec* cols, int ncols, int B, int Hg, int Wg, int Cin, const void* w_packed,
-           int Cin_p, int ntaps, int Cout, const Epilogue& ep, const OutMap& om, cudaStream_t stream) {
+           int Cin_p, int ntaps, int Cout, const Epilogue& ep, const OutMap& om, cudaStream_t stream, int allow_halo = 0) {
   Plan p;
-  int rc = make_plan(p, B, Hg, Wg, Cin, Cout, cols, ncols, ep.stats != nullptr);
+  int rc = make_plan(p, B, Hg, Wg, Cin, Cout, cols, ncols, ep.stats != nullptr, allow_halo);
   if (rc) return rc;
+  if (p.a.halo) ncols = 1;
   ConvArgs& a = p.a;
   a.Ho = om.Ho; a.Wo = om.Wo; a.osy = om.osy; a.osx = om.osx; a.oay = om.oay; a.oax = om.oax;
   a.out = reinterpret_cast<bf16*>(ep.out); a.out_ld = ep.out_ld;
@@ -445,6 +500,7 @@ int launch(const Plane* planes, const ColSpec* cols, int ncols, int B, int Hg, i
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)pl.Wp, (uint64_t)pl.Hp, (uint64_t)B};
     uint64_t str[3] = {(uint64_t)pl.ld_px * 2, (uint64_t)pl.ld_row * 2, (uint64_t)pl.ld_img * 2};
     uint32_t box[4] = {(uint32_t)a.KB, (uint32_t)a.tw, (uint32_t)(a.th + cols[c].nr - 1), 1};
+    if (a.halo) { box[1] = (uint32_t)(a.tw + 2); box[2] = (uint32_t)(a.th + 2); }
     rc = dp_make_tmap_bf16(&tm.a[c], pl.base, 4, dims, str, box, nullptr, a.row_bytes);
     if (rc) return rc;
   }
@@ -531,7 +587,7 @@ int dp_conv2d_tc_grid(int B, int H, int W, int Cin, int Cout, int KS) {
   Plan p;
   ColSpec cols[kMaxCols];
   const int n = plain_cols(cols, KS);
-  if (make_plan(p, B, H, W, Cin, Cout, cols, n, 0)) return -1;
+  if (make_plan(p, B, H, W, Cin, Cout, cols, n, 0, KS == 3)) return -1;
   return p.grid;
 }
 
@@ -552,7 +608,7 @@ int dp_conv2d_tc(const void* x, long long x_ld, int B, int H, int W, int Cin, co
   const int n = plain_cols(cols, KS);
   Epilogue ep{bias, residual, res_ld, residual2, res2_ld, relu, out, out_ld, out2, out2_ld, relu2, stats_partials};
   OutMap om{H, W, 1, 1, 0, 0};
-  return launch(&pl, cols, n, B, H, W, Cin, w_packed, Cin_p, KS * KS, Cout, ep, om, stream);
+  return launch(&pl, cols, n, B, H, W, Cin, w_packed, Cin_p, KS * KS, Cout, ep, om, stream, KS == 3);
 }
 
 /* Stride-2 convolution (conv rule i = 2*o - pad + k, K x K taps) on the tensor cores: nn.Conv2d(k3,s2,p1) forward

@@ -12,7 +12,7 @@ struct ProbeArgs {
   int a_nbox, a_box_bytes, a_box_cols, b_nbox, b_box_bytes, b_box_cols;
   int M, N, nk;
   uint32_t idesc;
-  uint32_t a_lbo, a_sbo, a_layout, a_kadv, a_off;
+  uint32_t a_lbo, a_sbo, a_layout, a_kadv, a_off, a_boff;
   uint32_t b_lbo, b_sbo, b_layout, b_kadv, b_off;
   float* out;  // [128][ncols_dump]
   int ncols_dump;
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(128) umma_probe_kernel(const __grid_constant__
     tc::mbar_wait(&bar_full, 0);
     tc::fence_after_sync();
     for (int k = 0; k < p.nk; ++k) {
-      uint64_t da = tc::make_smem_desc(tc::smem_u32(sA) + p.a_off + k * p.a_kadv, p.a_lbo, p.a_sbo, p.a_layout);
+      uint64_t da = tc::make_smem_desc(tc::smem_u32(sA) + p.a_off + k * p.a_kadv, p.a_lbo, p.a_sbo, p.a_layout, p.a_boff);
       uint64_t db = tc::make_smem_desc(tc::smem_u32(sB) + p.b_off + k * p.b_kadv, p.b_lbo, p.b_sbo, p.b_layout);
       tc::umma_bf16(tmem, da, db, p.idesc, k > 0 ? 1u : 0u);
     }
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(128) umma_probe_kernel(const __grid_constant__
 
 extern "C" int dp_umma_probe(const void* A, int a_rows, int a_cols, int a_box_rows, int a_box_cols, const void* B,
                              int b_rows, int b_cols, int b_box_rows, int b_box_cols, int M, int N, int nk, int a_mn,
-                             int b_mn, const uint32_t* adesc /*host: lbo,sbo,layout,kadv,off*/,
+                             int b_mn, const uint32_t* adesc /*host: lbo,sbo,layout,kadv,off,base_offset*/,
                              const uint32_t* bdesc /*host*/, float* out, int ncols_dump, cudaStream_t stream) {
   DP_CHECK_ARG(A && B && out && adesc && bdesc, "dp_umma_probe: null pointer");
   DP_CHECK_ARG(ncols_dump % 16 == 0 && ncols_dump <= 512, "dp_umma_probe: ncols_dump");
@@ -89,7 +89,7 @@ extern "C" int dp_umma_probe(const void* A, int a_rows, int a_cols, int a_box_ro
   p.b_nbox = b_cols / b_box_cols; p.b_box_bytes = b_box_rows * b_box_cols * 2; p.b_box_cols = b_box_cols;
   p.M = M; p.N = N; p.nk = nk;
   p.idesc = tc::make_idesc_bf16(M, N, a_mn, b_mn);
-  p.a_lbo = adesc[0]; p.a_sbo = adesc[1]; p.a_layout = adesc[2]; p.a_kadv = adesc[3]; p.a_off = adesc[4];
+  p.a_lbo = adesc[0]; p.a_sbo = adesc[1]; p.a_layout = adesc[2]; p.a_kadv = adesc[3]; p.a_off = adesc[4]; p.a_boff = adesc[5];
   p.b_lbo = bdesc[0]; p.b_sbo = bdesc[1]; p.b_layout = bdesc[2]; p.b_kadv = bdesc[3]; p.b_off = bdesc[4];
   p.out = out; p.ncols_dump = ncols_dump;
   size_t smem = 1024 + ((p.a_nbox * p.a_box_bytes + 1023) & ~1023) + ((p.b_nbox * p.b_box_bytes + 1023) & ~1023);

@@ -26,6 +26,7 @@ struct WgGroup {      // one TMA box of the tapped operand: vertical taps ky[0..
   int map, dx, dy, nr;
   int ky[3];
   uint32_t box_bytes, slot_off;
+  uint32_t idesc, tmem_col;   // one UMMA covers all nr taps: N = nr*NC, columns start at tmem_col
 };
 
 struct WgMaps {
@@ -45,6 +46,7 @@ struct WgArgs {
   uint32_t a_box_bytes, a_slot_bytes, stage_bytes;
   uint32_t rowA, rowB, layoutA, layoutB, idesc, a_lbo;
   float* partial;  // [psplit][KH*KW][Cout][Cin]
+  unsigned long long* dbg;  // optional cycle counters (diagnostics): [0]=producer wait, [1]=mma wait, [2]=mma issue, [3]=total, [4]=tiles
 };
 
 struct __align__(8) WgBars {
@@ -81,15 +83,19 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps tm, const __grid_constant__ WgArg
   const uint32_t tmem = bars->tmem_base;
   const int real_chunks = a.MC < 64 ? 1 : a.m_chunks;  // chunks actually loaded (narrow layers alias chunk 0)
 
+  const long long t_start = clock64();
   if (warp == 0 && lane == 0) {
     uint32_t stage = 0, phase = 0;
+    long long w_acc = 0;
     for (long long t = ps; t < a.tiles_total; t += a.psplit) {
       long long m = t;
       const int tx = (int)(m % a.tiles_x); m /= a.tiles_x;
       const int ty = (int)(m % a.tiles_y);
       const int n = (int)(m / a.tiles_y);
       const int y0 = ty * a.th, x0 = tx * a.tw;
+      const long long c0 = clock64();
       tc::mbar_wait(&bars->empty[stage], phase ^ 1);
+      w_acc += clock64() - c0;
       uint8_t* sA = smem + (size_t)stage * a.stage_bytes;
       uint8_t* sX = sA + (size_t)real_chunks * a.a_slot_bytes;
       uint32_t txb = (uint32_t)real_chunks * a.a_box_bytes;
@@ -103,31 +109,41 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps tm, const __grid_constant__ WgArg
       }
       if (++stage == (uint32_t)a.stages) { stage = 0; phase ^= 1; }
     }
+    if (a.dbg && blockIdx.x == 0) a.dbg[0] = (unsigned long long)w_acc;
   } else if (warp == 1 && lane == 0) {
     uint32_t stage = 0, phase = 0;
     uint32_t accumulate = 0;
+    long long w_acc = 0, i_acc = 0, ntile = 0;
+    const uint32_t a_hi = tc::desc_hi(8 * a.rowA, a.layoutA), b_hi = tc::desc_hi(8 * a.rowB, a.layoutB);
+    const uint32_t a_step = (16u * a.rowA) >> 4, b_step = (16u * a.rowB) >> 4;   // 16 pixel rows per UMMA K-step
     for (long long t = ps; t < a.tiles_total; t += a.psplit) {
+      const long long c0 = clock64();
       tc::mbar_wait(&bars->full[stage], phase);
       tc::fence_after_sync();
+      const long long c1 = clock64();
+      w_acc += c1 - c0;
+      ++ntile;
       const uint32_t a_base = tc::smem_u32(smem + (size_t)stage * a.stage_bytes);
       const uint32_t x_base = a_base + (uint32_t)real_chunks * a.a_slot_bytes;
       for (int g = 0; g < a.ngrp[s]; ++g) {
         const WgGroup& G = a.grp[s][g];
-        for (int r = 0; r < G.nr; ++r) {
-#pragma unroll 1
-          for (int k16 = 0; k16 < 8; ++k16) {
-            const uint64_t da = tc::make_smem_desc(a_base + (uint32_t)(k16 * 16) * a.rowA, a.a_lbo, 8 * a.rowA, a.layoutA);
-            const uint64_t db = tc::make_smem_desc(x_base + G.slot_off + (uint32_t)(r * a.tw + k16 * 16) * a.rowB, 0,
-                                                   8 * a.rowB, a.layoutB);
-            tc::umma_bf16(tmem + (uint32_t)(G.ky[r] * a.NC), da, db, a.idesc, (accumulate | (uint32_t)(k16 > 0)));
-          }
-        }
+        // the nr vertical taps of a group are the same box read r*tw pixel rows further down: with the MN-major
+        // descriptor's LBO = tw*rowB they become nr consecutive N-chunks of ONE UMMA (N = nr*NC), whose
+        // accumulator columns [ky0*NC, (ky0+nr)*NC) are exactly the per-tap accumulators (contiguous ky).
+        const uint32_t al0 = tc::desc_lo(a_base, a.a_lbo), bl0 = tc::desc_lo(x_base + G.slot_off, (uint32_t)a.tw * a.rowB);
+        const uint32_t d_col = tmem + G.tmem_col;
+#pragma unroll
+        for (int k16 = 0; k16 < 8; ++k16)
+          tc::umma_bf16_lohi(d_col, al0 + (uint32_t)k16 * a_step, a_hi, bl0 + (uint32_t)k16 * b_step, b_hi, G.idesc,
+                             k16 > 0 ? 1u : accumulate);
       }
       accumulate = 1;
       tc::umma_commit(&bars->empty[stage]);
+      i_acc += clock64() - c1;
       if (++stage == (uint32_t)a.stages) { stage = 0; phase ^= 1; }
     }
     tc::umma_commit(&bars->done);
+    if (a.dbg && blockIdx.x == 0) { a.dbg[1] = (unsigned long long)w_acc; a.dbg[2] = (unsigned long long)i_acc; a.dbg[4] = (unsigned long long)ntile; }
   } else if (warp >= 2) {
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     tc::mbar_wait(&bars->done, 0);
@@ -139,11 +155,14 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps tm, const __grid_constant__ WgArg
     const int co = cb * a.M + row;
     const bool row_ok = row >= 0 && row < (a.MC < 64 ? a.MC : a.M) && co < a.Cout;
     const bool has_work = ps < a.tiles_total;  // a split with no tiles left its TMEM untouched: write zeros
-    for (int r = 0; r < a.KH; ++r) {
-      const int tap = r * a.KW + s;
+    for (int gr = 0; gr < a.ngrp[s] * 3; ++gr) {
+      const WgGroup& G = a.grp[s][gr / 3];
+      const int r = gr % 3;
+      if (r >= G.nr) continue;  // warp-uniform
+      const int tap = G.ky[r] * a.KW + s;
       for (int c0 = 0; c0 < a.NC; c0 += 16) {
         float v[16];
-        tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * a.NC + c0), v);
+        tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + G.tmem_col + (uint32_t)(r * a.NC + c0), v);
         if (row_ok) {
           float* dst = a.partial + (((size_t)ps * a.KH * a.KW + tap) * a.Cout + co) * a.Cin + cc * a.NC + c0;
 #pragma unroll
@@ -155,6 +174,7 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps tm, const __grid_constant__ WgArg
   }
   tc::fence_before_sync();
   __syncthreads();
+  if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[3] = (unsigned long long)(clock64() - t_start);
   if (warp == 1) tc::tmem_dealloc(tmem, 256);
 }
 
@@ -172,6 +192,8 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int pspli
     grad[o] = accumulate ? grad[o] + s : s;
   }
 }
+
+unsigned long long* g_wg_dbg = nullptr;   // diagnostics only (dp_debug_set_buffer); never set on the product path
 
 struct WgPlan {
   WgArgs a;
@@ -250,14 +272,29 @@ int wg_plan(WgPlan& p, int B, int Hg, int Wg, int Cp, int Ct, int K, int pad, in
     }
     if (off > max_x) max_x = off;
   }
+  for (int kx = 0; kx < K; ++kx) {
+    int slot = 0;
+    for (int g = 0; g < a.ngrp[kx]; ++g) {
+      WgGroup& G = a.grp[kx][g];
+      G.tmem_col = (uint32_t)(slot * a.NC);
+      G.idesc = tc::make_idesc_bf16(a.M, G.nr * a.NC, 1, 1);
+      slot += G.nr;
+    }
+    if (slot * a.NC > 256) return dp_set_error(DP_ERR_UNSUPPORTED, "wgrad_tc: accumulators exceed TMEM allocation");
+  }
   const int real_chunks = a.MC < 64 ? 1 : a.m_chunks;
   a.a_lbo = a.MC < 64 ? 0u : a.a_slot_bytes;
   a.stage_bytes = real_chunks * a.a_slot_bytes + max_x;
   const int base_ctas = K * a.co_blocks * a.ci_chunks;
-  int ps = (2 * dp::kNumSMs + base_ctas - 1) / base_ctas;
-  if (ps > a.tiles_total) ps = (int)a.tiles_total;
-  if (ps < 1) ps = 1;
-  if (ps > 64) ps = 64;
+  // split-K factor: minimise (waves / psplit), i.e. keep the last wave full (one CTA per SM)
+  int ps = 1;
+  double best_cost = 1e30;
+  const int ps_max = (int)(a.tiles_total < dp::kNumSMs ? a.tiles_total : dp::kNumSMs);
+  for (int c = 1; c <= ps_max; ++c) {
+    const int waves = (base_ctas * c + dp::kNumSMs - 1) / dp::kNumSMs;
+    const double cost = (double)waves / c + 1e-5 * c;
+    if (cost < best_cost) { best_cost = cost; ps = c; }
+  }
   a.psplit = ps;
   long long per = (a.tiles_total + ps - 1) / ps;
   int st = (int)((200 * 1024) / a.stage_bytes);
@@ -277,6 +314,7 @@ int wg_launch(WgPlan& p, const void* P, long long p_ld, const WgPlaneT* planes /
   const size_t need = (size_t)a.psplit * K * K * a.Cout * a.Cin * sizeof(float);
   if (workspace_bytes < need) return dp_set_error(DP_ERR_WORKSPACE, "wgrad_tc: workspace %zu < %zu", workspace_bytes, need);
   a.partial = reinterpret_cast<float*>(workspace);
+  a.dbg = g_wg_dbg;
   WgMaps tm;
   {
     uint64_t dims[4] = {(uint64_t)a.Cout, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)B};
@@ -319,6 +357,9 @@ int wg_launch(WgPlan& p, const void* P, long long p_ld, const WgPlaneT* planes /
 }  // namespace
 
 extern "C" {
+
+/* diagnostics: device buffer of >= 8 u64 that block 0 of the next wgrad launches fills with cycle counters; NULL = off */
+void dp_debug_set_buffer(void* p) { g_wg_dbg = reinterpret_cast<unsigned long long*>(p); }
 
 size_t dp_conv2d_wgrad_tc_workspace(int B, int H, int W, int Cin, int Cout, int KS) {
   WgPlan p;

@@ -12,7 +12,7 @@ def _probe(pkg, A, a_box, B, b_box, M, N, nk, a_mn, b_mn, adesc, bdesc, ncols=No
     L = pkg._lib
     ncols = ncols or max(16, N)
     out = torch.full((128, ncols), float("nan"), device="cuda", dtype=torch.float32)
-    ad = (ctypes.c_uint32 * 5)(*adesc)
+    ad = (ctypes.c_uint32 * 6)(*(list(adesc) + [0] * (6 - len(adesc))))
     bd = (ctypes.c_uint32 * 5)(*bdesc)
     L.check(L.lib().dp_umma_probe(L.ptr(A), A.shape[0], A.shape[1], a_box[0], a_box[1], L.ptr(B), B.shape[0],
                                   B.shape[1], b_box[0], b_box[1], M, N, nk, a_mn, b_mn, ad, bd, L.ptr(out), ncols,
@@ -115,3 +115,66 @@ def test_mn_major_b_row_shift(pkg):
                  [K * 128, 1024, 2, 2048, 0], [0, 1024, 2, 2048, 16 * 128])
     ref = At.float().t() @ Xt[16:16 + K].float()
     assert torch.equal(out[:, :N], ref)
+
+
+@pytest.mark.parametrize("kb", [64, 32, 16])
+@pytest.mark.parametrize("shift", [1, 2, 11, 21, 22])
+def test_k_major_halo_addressing(pkg, kb, shift):
+    """single-halo-load conv: the swizzle is a function of the absolute shared-memory address, so an A descriptor may
+    start ANY whole row into a swizzled TMA box and step between its 8-row groups with a stride (SBO) that is the halo
+    row pitch (tw+2 = 10 rows), not a multiple of the swizzle atom.  One box then serves all nine 3x3 taps."""
+    A = _rand(256, kb, 41)
+    B = _rand(64, kb, 42)
+    rb = kb * 2
+    out = _probe(pkg, A, (256, kb), B, (64, kb), 128, 64, kb // 16, 0, 0,
+                 [16, 10 * rb, SW[rb], 32, shift * rb, 0], [16, 8 * rb, SW[rb], 32, 0])
+    rows = torch.cat([A[g * 10 + shift: g * 10 + shift + 8] for g in range(16)])
+    ref = rows.float() @ B.float().t()
+    assert torch.equal(out[:, :64], ref)
+
+
+@pytest.mark.parametrize("nc", [64, 32, 16])
+@pytest.mark.parametrize("shift", [0, 1, 12])
+def test_mn_major_halo_addressing(pkg, nc, shift):
+    """wgrad from one halo box: MN-major B operand whose K (pixel) groups of 8 rows are a halo pitch (10 rows) apart and
+    whose N chunks (vertical taps) are LBO = one halo row pitch apart; start shifted by whole rows."""
+    K, M = 64, 128                                  # 64 pixels = 8 patch rows of 8
+    At = _rand(K, M, 43)
+    Xt = _rand(140, nc, 44)                         # halo box rows
+    rbB = nc * 2
+    out = _probe(pkg, At, (K, 64), Xt, (140, nc), M, 3 * nc, K // 16, 1, 1,
+                 [K * 128, 1024, 2, 2048, 0], [10 * rbB, 10 * rbB, SW[rbB], 20 * rbB, shift * rbB], ncols=max(16, 3 * nc))
+    ref = torch.zeros(M, 3 * nc, device="cuda")
+    for r in range(3):
+        rows = torch.cat([Xt[(g + r) * 10 + shift: (g + r) * 10 + shift + 8] for g in range(8)])   # [64][nc]
+        ref[:, r * nc:(r + 1) * nc] = At.float().t() @ rows.float()
+    assert torch.equal(out[:, :3 * nc], ref)
+
+
+def test_explore_unaligned_row_shift(pkg):
+    """exploration (prints, asserts nothing about the outcome): can the A descriptor start a non-multiple-of-8 rows
+    into a 128B-swizzled box (horizontal conv tap = +1 pixel)?  Tries base_offset = 0 and = shift."""
+    A = _rand(256, 64, 41)
+    B = _rand(64, 64, 42)
+    res = {}
+    for shift in (1, 2, 3, 9):
+        for boff in (0, shift & 7):
+            out = _probe(pkg, A, (256, 64), B, (64, 64), 128, 64, 4, 0, 0,
+                         [16, 1024, 2, 32, shift * 128, boff], [16, 1024, 2, 32, 0])
+            ref = A[shift:shift + 128].float() @ B.float().t()
+            res[(shift, boff)] = bool(torch.equal(out[:, :64], ref))
+    # 8-pixel-wide patch inside a 16-pixel-pitch halo box: group stride (SBO) = 2048, start shifted by s rows
+    for shift in (1, 2):
+        for boff in (0, shift):
+            out = _probe(pkg, A, (256, 64), B, (64, 64), 128, 64, 4, 0, 0,
+                         [16, 2048, 2, 32, shift * 128, boff], [16, 1024, 2, 32, 0])
+            rows = torch.cat([A[g * 16 + shift: g * 16 + shift + 8] for g in range(16)])[:128]
+            ref = rows.float() @ B.float().t()
+            res[("pitch16", shift, boff)] = bool(torch.equal(out[:, :64], ref))
+    for shift in (0, 1, 2):
+        out = _probe(pkg, A, (256, 64), B, (64, 64), 128, 64, 4, 0, 0,
+                     [16, 1280, 2, 32, shift * 128, 0], [16, 1024, 2, 32, 0])
+        rows = torch.cat([A[g * 10 + shift: g * 10 + shift + 8] for g in range(16)])[:128]
+        ref = rows.float() @ B.float().t()
+        res[("pitch10", shift)] = bool(torch.equal(out[:, :64], ref))
+    print("UNALIGNED-SHIFT EXPLORATION:", res)
