@@ -123,13 +123,17 @@ def run_ours(a):
     B = a.batch
     model = build_model(dev)
     cfg = fx.loss_config()                                # config.yaml:34-42 -> 1 / 0 / 0 / 0
-    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=1e-4, fused=True)
-    red = D.GradientAllReducer(model.parameters(), world)
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=1e-4, fused=True,
+                            capturable=True)
     xh, th = synthetic_batch(B, 1234 + rank)
     xh, th = xh.pin_memory(), th.pin_memory()
     xd, td = xh.to(dev), th.to(dev)
+    # The whole step (forward, combined_loss, backward, NCCL gradient all-reduce, AdamW) is one CUDA graph.
+    gstep = depth_b200.GraphedTrainStep(model, opt, cfg, xd, td, use_rgb=True, world=world, warmup=max(a.warmup, 3))
+    red = gstep.red
 
     def step(x, t, read_loss):
+        """the same step issued eagerly through the reference-shaped API (model(x), combined_loss, backward, step)"""
         red.zero()
         out = model(x).unsqueeze(1)
         loss, parts = depth_b200.combined_loss(out, t, cfg, rgb=x)      # one fused pass + one D2H read of 8 floats
@@ -143,18 +147,13 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(nsteps, from_host):
+    def timed(nsteps, from_host, fn):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         last = None
         for _ in range(nsteps):
-            if from_host:
-                x = xh.to(dev, non_blocking=True)
-                t = th.to(dev, non_blocking=True)
-            else:
-                x, t = xd, td
-            last = step(x, t, True)
+            last = fn(from_host)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -164,18 +163,37 @@ def run_ours(a):
             ms = float(tt.item())
         return ms, last
 
+    def graph_step(from_host):
+        if from_host:
+            gstep(xh, th)                       # H2D of this step's batch from pinned memory into the static buffers
+            return gstep.loss_dict()["si_loss"]  # D2H read of the step's loss scalars
+        gstep()
+        return None
+
+    def eager_step(from_host):
+        if from_host:
+            return step(xh.to(dev, non_blocking=True), th.to(dev, non_blocking=True), True)
+        return step(xd, td, True)
+
     for _ in range(max(a.warmup, 3)):
-        step(xd, td, True)
+        gstep()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     n0 = depth_b200._lib.launch_count()
-    ms, last_loss = timed(a.steps, False)
-    launches = depth_b200._lib.launch_count() - n0
+    ms, _ = timed(a.steps, False, graph_step)
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e, _ = timed(a.steps, True)
+    ms_e2e, last_loss = timed(a.steps, True, graph_step)
     value = world * B * a.steps / (ms / 1e3)
     e2e = world * B * a.steps / (ms_e2e / 1e3)
+    # eager dispatch of the same step (what main.py's loop does call by call), for reference
+    gstep.finish()
+    for _ in range(2):
+        step(xd, td, True)
+    n0 = depth_b200._lib.launch_count()
+    ms_eager, _ = timed(min(a.steps, 3), False, eager_step)
+    launches = (depth_b200._lib.launch_count() - n0) // min(a.steps, 3)
+    ms_eager /= min(a.steps, 3)
 
     # ---- roofline of the tcgen05 conv kernels: CUDA events around every launch, on the launching stream --------
     hbm, tf_burst, tf_sus, src = peaks()
@@ -274,7 +292,9 @@ def run_ours(a):
                                    "heads/loss on libdepth_b200.so"},
             "e2e": {"value": round(e2e, 2), "unit": "images/s", "h2d_bytes_per_step": int(xh.numel() * 4 + th.numel() * 4),
                     "d2h_bytes_per_step": 32, "ms_per_step": round(ms_e2e / a.steps, 3)},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "eval": ev,
+            "gpu_launches": int(launches) * a.steps, "gpu_launches_per_step": int(launches),
+            "execution": "whole train step captured once in a CUDA graph and replayed (depth_b200.GraphedTrainStep)",
+            "eager_ms_per_step": round(ms_eager, 3), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "eval": ev,
             "loss": last_loss,
             "train_tflops_algorithmic": round(3 * FWD_GFLOP_PER_IMG * value / 1e3, 1),
         }

@@ -1,0 +1,65 @@
+"""Whole-step CUDA graph for the training hot loop (reference main.py:125-156).
+
+The reference's loop body - zero_grad, forward, combined_loss, backward, optimizer.step - launches a few thousand
+kernels per step; on B200 the eager Python/autograd dispatch of those launches (about 130 ms) is slower than the
+kernels themselves.  `GraphedTrainStep` captures one full step (our kernels, the PyTorch-run encoders, the NCCL
+gradient all-reduce and the fused AdamW update) into a single CUDA graph and replays it: the host submits one
+graph launch per step, copies the batch into static buffers and reads back eight floats.
+"""
+import torch
+
+from . import ops, util
+from . import distributed as D
+
+
+class GraphedTrainStep:
+    def __init__(self, model, optimizer, config, example_inputs, example_targets, use_rgb=True, world=None,
+                 warmup=3):
+        assert example_inputs.is_cuda and example_targets.is_cuda
+        self.model, self.opt, self.cfg, self.use_rgb = model, optimizer, config, use_rgb
+        self.x = example_inputs.clone()
+        self.t = example_targets.clone()
+        self.red = D.GradientAllReducer(model.parameters(), world)
+        self.out = None
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(max(warmup, 2)):          # builds the flat gradient bucket, optimizer state, caches
+                self._body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        ops.PACKS.store.clear()                      # weight re-packs must be part of the captured step
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._body()
+        torch.cuda.synchronize()
+
+    def _body(self):
+        self.red.zero()
+        pred = self.model(self.x).unsqueeze(1)
+        total, out = util.combined_loss_device(pred, self.t, self.cfg, rgb=self.x if self.use_rgb else None)
+        total.backward()
+        self.red.reduce()
+        self.opt.step()
+        self.out = out
+
+    def __call__(self, inputs=None, targets=None):
+        """one optimisation step; inputs/targets may be (pinned) host or device tensors, or None to reuse the static
+        batch.  Returns the device tensor of loss scalars (index with depth_b200._lib.L_*); no host sync."""
+        if inputs is not None:
+            self.x.copy_(inputs, non_blocking=True)
+        if targets is not None:
+            self.t.copy_(targets, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+    def loss_dict(self):
+        """one device->host read of the eight loss scalars of the last step (main.py:85-88 needs four of them)."""
+        from . import _lib as L
+        h = self.out.tolist()
+        return {"total": h[L.L_TOTAL], "si_loss": h[L.L_SI], "silog_loss": h[L.L_SILOG], "grad_loss": h[L.L_GRAD],
+                "edge_loss": h[L.L_EDGE]}
+
+    def finish(self):
+        """call before going back to eager use of the model: the eager weight-pack cache must not trust versions."""
+        ops.PACKS.store.clear()

@@ -149,6 +149,19 @@ def edge_aware_loss(pred, target, rgb, beta=0.5):
     return val
 
 
+def combined_loss_device(pred, target, config, rgb=None):
+    """combined_loss without the host read: returns (total, device tensor of the DP_NLOSS scalars).  Capturable in a
+    CUDA graph (no synchronisation)."""
+    _check_cuda(pred, target, rgb)
+    assert pred.shape[-2:] == target.shape[-2:], \
+        "Pred and target must have the same spatial dimensions, got {} and {}".format(pred.shape[-2:], target.shape[-2:])
+    lf = config.model.loss_function
+    flags = L.F_SI | L.F_SILOG | L.F_GRAD | (L.F_EDGE if rgb is not None else 0)
+    return _LossFn.apply(pred, target, rgb, flags, 1e-6, float(lf.si_loss_alpha), float(lf.silog_loss.alpha),
+                         float(lf.silog_loss.variance_focus), float(lf.grad_loss_alpha),
+                         float(lf.edge_loss_alpha) if rgb is not None else 0.0, False, L.L_TOTAL)
+
+
 def combined_loss(pred, target, config, rgb=None):
     """reference main.py:51-89: returns (total, {'si_loss','silog_loss','grad_loss','edge_loss'}) - one fused
     pass and ONE device->host read instead of four `.item()` syncs."""
