@@ -29,6 +29,8 @@
 #include "tc.cuh"
 #include "../../include/depth_b200.h"
 
+extern unsigned long long* g_wg_dbg;
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -59,6 +61,7 @@ struct ConvArgs {
   int BN, n_blocks;
   int stages, resident;
   int ncols, max_nr, nslots;
+  int nbuf, niss;                 // TMEM accumulator buffers (2 or 4) and MMA-issuing warps (1 or 2)
   int halo, pitch;                // halo mode: one (th+2) x (tw+2) box per channel chunk serves all nine taps
   ColLoad cols[kMaxCols];
   uint32_t a_slot_bytes, b_tap_bytes, row_bytes, layout, sbo, idesc;
@@ -72,13 +75,14 @@ struct ConvArgs {
   const bf16* resb; long long resb_ld;
   int relu, relu2;
   float* stats;  // [gridDim.x][2][Cout] or null
+  unsigned long long* dbg;
 };
 
 struct __align__(8) Barriers {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
-  uint64_t tmem_full[2];
-  uint64_t tmem_empty[2];
+  uint64_t tmem_full[4];
+  uint64_t tmem_empty[4];
   uint64_t resident_full;
   uint32_t tmem_base;
 };
@@ -151,7 +155,7 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < a.stages; ++i) { tc::mbar_init(&bars->full[i], 1); tc::mbar_init(&bars->empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars->tmem_full[i], 1); tc::mbar_init(&bars->tmem_empty[i], 4); }
+    for (int i = 0; i < 4; ++i) { tc::mbar_init(&bars->tmem_full[i], 1); tc::mbar_init(&bars->tmem_empty[i], 4); }
     tc::mbar_init(&bars->resident_full, 1);
     tc::fence_barrier_init();
     tc::prefetch_tmap(&tm.a[0]);
@@ -163,6 +167,7 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = bars->tmem_base;
+  const long long t_start = clock64();
 
   if (warp == 0 && lane == 0) {
     // ================= TMA producer =================
@@ -202,26 +207,38 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ================= MMA issuer (single thread) =================
+  } else if ((warp == 1 || (warp == 3 && a.niss == 2)) && lane == 0) {
+    // ================= MMA issuers (one thread each; two warps alternate tiles) =================
+    // A lone thread needs ~50 cycles of scalar work per tcgen05.mma, more than a 128xNx16 UMMA with N <= 64 takes on
+    // the tensor pipe, so two issuers work on alternate tiles with their own TMEM accumulators.
     if (a.resident) { tc::mbar_wait(&bars->resident_full, 0); tc::fence_after_sync(); }
-    uint32_t stage = 0, phase = 0;
-    int it = 0;
+    const int wiss = warp == 1 ? 0 : 1;
     const int kk_n = a.KB / 16;
     const uint32_t b_hi = tc::desc_hi(a.sbo, a.layout);                                   // also A's hi outside halo mode
     const uint32_t a_hi_halo = tc::desc_hi((uint32_t)a.pitch * a.row_bytes, a.layout);
     const uint32_t res_base = tc::smem_u32(s_res);
-    for (long long item = blockIdx.x; item < a.total_items; item += gridDim.x, ++it) {
-      const int buf = it & 1;
-      tc::mbar_wait(&bars->tmem_empty[buf], ((it >> 1) & 1) ^ 1);
+    const int ksteps = a.ncols * a.kchunks;
+    long long dbg_te = 0, dbg_wf = 0, dbg_is = 0;
+    int it = wiss;
+    for (long long item = blockIdx.x + (long long)wiss * gridDim.x; item < a.total_items;
+         item += (long long)a.niss * gridDim.x, it += a.niss) {
+      const int buf = it % a.nbuf;
+      const long long q0 = clock64();
+      tc::mbar_wait(&bars->tmem_empty[buf], ((it / a.nbuf) & 1) ^ 1);
       tc::fence_after_sync();
+      dbg_te += clock64() - q0;
       const uint32_t d_tmem = tmem + (uint32_t)(buf * a.BN);
       uint32_t accumulate = 0;
+      const long long g0 = (long long)it * ksteps;      // global k-step counter: stage ring position of this tile
+      uint32_t stage = (uint32_t)(g0 % a.stages), phase = (uint32_t)((g0 / a.stages) & 1);
       for (int c = 0; c < a.ncols; ++c) {
         const ColLoad& col = a.cols[c];
         for (int kc = 0; kc < a.kchunks; ++kc) {
+          const long long q1 = clock64();
           tc::mbar_wait(&bars->full[stage], phase);
           tc::fence_after_sync();
+          const long long q2 = clock64();
+          dbg_wf += q2 - q1;
           const uint32_t a_base = tc::smem_u32(s_stage + (size_t)stage * stage_bytes);
           if (a.halo) {
             // all nine taps read the same halo box: tap (r,s) starts (r*pitch + s) pixel rows in; the 8-pixel patch
@@ -261,27 +278,33 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
             }
           }
           tc::umma_commit(&bars->empty[stage]);  // frees the smem slot when these MMAs have read it
+          dbg_is += clock64() - q2;
           if (++stage == (uint32_t)a.stages) { stage = 0; phase ^= 1; }
         }
       }
       tc::umma_commit(&bars->tmem_full[buf]);  // accumulator complete -> epilogue
     }
+    if (a.dbg && blockIdx.x == 0 && wiss == 0) { a.dbg[0] = dbg_te; a.dbg[1] = dbg_wf; a.dbg[2] = dbg_is; a.dbg[4] = it; }
   } else if (warp >= 4) {
     // ================= epilogue: TMEM -> registers -> global =================
     const int ew = warp - 4;  // == warp % 4: TMEM lanes [32*ew, 32*ew+32)
     const int m = ew * 32 + lane;
     const int py = m / a.tw, px = m - py * a.tw;
+    long long dbg_ew = 0, dbg_ek = 0;
     int it = 0;
     for (long long item = blockIdx.x; item < a.total_items; item += gridDim.x, ++it) {
       int n, y0, x0, nb;
       decode_item(a, item, n, y0, x0, nb);
-      const int buf = it & 1;
+      const int buf = it % a.nbuf;
       const int y = y0 + py, x = x0 + px;
       const int oy = y * a.osy + a.oay, ox = x * a.osx + a.oax;
       const bool valid = (y < a.H) && (x < a.W) && (oy < a.Ho) && (ox < a.Wo);
       const long long pix = ((long long)n * a.Ho + oy) * a.Wo + ox;
-      tc::mbar_wait(&bars->tmem_full[buf], (it >> 1) & 1);
+      const long long e0 = clock64();
+      tc::mbar_wait(&bars->tmem_full[buf], (it / a.nbuf) & 1);
       tc::fence_after_sync();
+      const long long e1 = clock64();
+      dbg_ew += e1 - e0;
       const uint32_t t_base = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * a.BN);
       for (int c0 = 0; c0 < a.BN; c0 += 16) {
         const int n0 = nb * a.BN + c0;
@@ -367,7 +390,9 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&bars->tmem_empty[buf]);
+      dbg_ek += clock64() - e1;
     }
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 128) { a.dbg[5] = dbg_ew; a.dbg[6] = dbg_ek; a.dbg[7] = it; }
     if (a.stats) {
       asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
       float* dst = a.stats + (size_t)blockIdx.x * 2 * a.Cout;
@@ -382,6 +407,7 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
   }
   tc::fence_before_sync();
   __syncthreads();
+  if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[3] = (unsigned long long)(clock64() - t_start);
   if (warp == 2) tc::tmem_dealloc(tmem, kTmemCols);
 }
 
@@ -436,6 +462,8 @@ int make_plan(Plan& p, int B, int Hg, int Wg, int Cin, int Cout, const ColSpec* 
   a.layout = tc::swizzle_for_row_bytes(a.row_bytes);
   a.sbo = 8 * a.row_bytes;
   a.idesc = tc::make_idesc_bf16(128, a.BN, 0, 0);
+  a.nbuf = 4 * a.BN <= kTmemCols ? 4 : 2;
+  a.niss = a.nbuf == 4 ? 2 : 1;
   a.b_box_bytes = (uint32_t)(a.BN * a.row_bytes);
   a.b_tap_bytes = (a.b_box_bytes + 1023u) & ~1023u;
   a.ncols = ncols;
@@ -473,6 +501,9 @@ int make_plan(Plan& p, int B, int Hg, int Wg, int Cin, int Cout, const ColSpec* 
     return dp_set_error(DP_ERR_UNSUPPORTED, "conv_tc: shape needs %zu B of shared memory", fixed + 2 * stage);
   int st = (int)((budget - fixed) / stage);
   a.stages = st > kMaxStages ? kMaxStages : st;
+  // Two issuers work one tile apart in the stage ring.  A parity wait on full[stage] for lap L is only meaningful once
+  // lap L-1 of that stage has completed, which is guaranteed when both tiles fit in the ring: 2 * k-steps <= stages.
+  if (2 * a.ncols * a.kchunks > a.stages) a.niss = 1;
   p.smem = fixed + (size_t)a.stages * stage;
   a.total_items = (long long)B * a.tiles_y * a.tiles_x * a.n_blocks;
   p.grid = (int)(a.total_items < dp::kNumSMs ? a.total_items : dp::kNumSMs);
@@ -494,6 +525,7 @@ int launch(const Plane* planes, const ColSpec* cols, int ncols, int B, int Hg, i
   a.resb = reinterpret_cast<const bf16*>(ep.res2); a.resb_ld = ep.res2_ld;
   a.relu = ep.relu; a.relu2 = ep.relu2;
   a.stats = ep.stats;
+  a.dbg = g_wg_dbg;
   Maps tm;
   for (int c = 0; c < ncols; ++c) {
     const Plane& pl = planes[cols[c].plane];

@@ -193,7 +193,9 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int pspli
   }
 }
 
+}  // namespace
 unsigned long long* g_wg_dbg = nullptr;   // diagnostics only (dp_debug_set_buffer); never set on the product path
+namespace {
 
 struct WgPlan {
   WgArgs a;
