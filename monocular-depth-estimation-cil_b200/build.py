@@ -11,7 +11,7 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libdepth_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("DP_EXTRA_FLAGS", "").split()
 
 
 def _newer(src, dst, extra=()):

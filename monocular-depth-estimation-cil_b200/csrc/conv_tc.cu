@@ -31,9 +31,20 @@
 
 extern unsigned long long* g_wg_dbg;
 
+// Per-role cycle counters (tools/dbg_conv.py).  Compiled out by default: a clock read costs the single-thread MMA
+// issuer a dependent-issue slot per use.
+#ifdef DP_CONV_TIMING
+#define DP_T(x) x
+#else
+#define DP_T(x)
+#endif
+
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kRoleThreads = 128;   // warp 0 TMA producer, warps 1/3 MMA issuers, warp 2 TMEM allocator
+constexpr int kEpiWarps = 8;        // warps 4..11: two per scheduler, splitting the tile's columns
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = kRoleThreads + kEpiThreads;
 constexpr int kMaxStages = 8;
 constexpr int kTmemCols = 512;
 
@@ -51,6 +62,7 @@ struct ColLoad {
 struct Maps {
   CUtensorMap a[kMaxCols];
   CUtensorMap b;
+  CUtensorMap o, o2;   // output tiles (TMA-store epilogue)
 };
 
 struct ConvArgs {
@@ -63,6 +75,10 @@ struct ConvArgs {
   int ncols, max_nr, nslots;
   int nbuf, niss;                 // TMEM accumulator buffers (2 or 4) and MMA-issuing warps (1 or 2)
   int halo, pitch;                // halo mode: one (th+2) x (tw+2) box per channel chunk serves all nine taps
+  int step_nb, step_tx, step_ty, step_n;   // mixed-radix digits of the item stride (gridDim.x)
+  int epi_tma;                    // 1: registers -> swizzled smem tile -> TMA store (BN in {16,32,64}); 0: direct stores
+  uint32_t out_tile_bytes;        // bytes of one staged output tile (128 pixels x BN bf16)
+  int nob;                        // staging ring depth (per output): nob - 2 TMA stores may still be reading smem
   ColLoad cols[kMaxCols];
   uint32_t a_slot_bytes, b_tap_bytes, row_bytes, layout, sbo, idesc;
   uint32_t b_box_bytes;  // bytes TMA actually writes per weight box (slots are rounded up to 1024)
@@ -87,21 +103,36 @@ struct __align__(8) Barriers {
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void decode_item(const ConvArgs& a, long long item, int& n, int& y0, int& x0, int& nb) {
-  nb = (int)(item % a.n_blocks);
-  long long m = item / a.n_blocks;
-  int tx = (int)(m % a.tiles_x);
-  m /= a.tiles_x;
-  int ty = (int)(m % a.tiles_y);
-  n = (int)(m / a.tiles_y);
-  y0 = ty * a.th;
-  x0 = tx * a.tw;
-}
+// Work items (image, tile row, tile column, N block) are walked with a fixed stride of gridDim.x.  Decoding an item
+// index costs three 64-bit divisions (hundreds of cycles on the critical path of every role, every tile), so each
+// role decodes once and then advances the mixed-radix digits by the precomputed digits of the stride.
+struct TileIter {
+  int nb, tx, ty, n;
+  __device__ __forceinline__ void init(const ConvArgs& a, unsigned item) {
+    nb = (int)(item % (unsigned)a.n_blocks);
+    unsigned m = item / (unsigned)a.n_blocks;
+    tx = (int)(m % (unsigned)a.tiles_x);
+    m /= (unsigned)a.tiles_x;
+    ty = (int)(m % (unsigned)a.tiles_y);
+    n = (int)(m / (unsigned)a.tiles_y);
+  }
+  __device__ __forceinline__ void step(const ConvArgs& a) {
+    nb += a.step_nb;
+    tx += a.step_tx;
+    ty += a.step_ty;
+    n += a.step_n;
+    if (nb >= a.n_blocks) { nb -= a.n_blocks; ++tx; }
+    if (tx >= a.tiles_x) { tx -= a.tiles_x; ++ty; }
+    if (ty >= a.tiles_y) { ty -= a.tiles_y; ++n; }
+  }
+};
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
 // column sums of a 32 (lanes) x 16 (registers) tile: after the call, lane L holds the sum of column col_of(L)
 // (lanes L and L^1 hold the same column).  16 shuffles instead of 80.
@@ -138,13 +169,258 @@ __device__ __forceinline__ int transpose_reduce16_col(int lane) {
   return ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
 }
 
+// ---- epilogue A: BN = 2*CW in {16, 32, 64}.  Each of the eight warps owns 32 pixels x CW columns of the tile: one
+// tcgen05.ld, TMEM released at once, math in registers, bf16 rows written to a swizzled shared-memory tile that one
+// thread hands to TMA (the store clips tile overhang, so no per-pixel predicates and fully coalesced HBM writes).
+// BatchNorm partial sums stay in registers across all tiles of the persistent CTA (thread = fixed pixel slot and
+// column slice) and are reduced once at the end.
+template <int CW>
+__device__ __forceinline__ void epilogue_tma(const Maps& tm, const ConvArgs& a, Barriers* bars, uint8_t* s_out,
+                                             float* s_stats, uint32_t tmem, int warp, int lane) {
+  const int e = warp - 4, ew = e & 3, half = e >> 2;
+  const int m = ew * 32 + lane;
+  const int py = m / a.tw, px = m - py * a.tw;
+  const int col0 = half * CW;
+  constexpr uint32_t kRowBytes = 4u * CW;                  // BN * 2
+  constexpr uint32_t kSwz = kRowBytes == 128 ? 7u : (kRowBytes == 64 ? 3u : 1u);
+  const bool store_thread = threadIdx.x == kRoleThreads;
+  const bool dual = a.out2 != nullptr;
+  const bool want_stats = a.stats != nullptr;
+  float acc_s[CW], acc_q[CW];
+#pragma unroll
+  for (int j = 0; j < CW; ++j) { acc_s[j] = 0.f; acc_q[j] = 0.f; }
+  uint32_t soff[CW / 8];                                   // swizzled byte offsets of this thread's 16-byte chunks
+#pragma unroll
+  for (int j = 0; j < CW / 8; ++j) {
+    const uint32_t off = (uint32_t)m * kRowBytes + (uint32_t)(col0 * 2 + j * 16);
+    soff[j] = off ^ (((off >> 7) & kSwz) << 4);
+  }
+  const uint32_t s_base = tc::smem_u32(s_out);
+  DP_T(long long dbg_ew = 0; long long dbg_ek = 0;)
+  int it = 0, ring = 0;
+  TileIter ti;
+  ti.init(a, blockIdx.x);
+  for (long long item = blockIdx.x; item < a.total_items; item += gridDim.x, ++it, ti.step(a)) {
+    const int n = ti.n, y0 = ti.ty * a.th, x0 = ti.tx * a.tw;
+    const int buf = it & (a.nbuf - 1);
+    const int y = y0 + py, x = x0 + px;
+    const int oy = y * a.osy + a.oay, ox = x * a.osx + a.oax;
+    const bool valid = (y < a.H) && (x < a.W) && (oy < a.Ho) && (ox < a.Wo);
+    const long long pix = ((long long)n * a.Ho + oy) * a.Wo + ox;
+    // residual operands do not depend on the accumulator: fetch them before waiting for the MMAs
+    uint4 r1[CW / 8], r2[CW / 8];
+    if (a.res) {
+      const uint4* rp = reinterpret_cast<const uint4*>(a.res + pix * a.res_ld + col0);
+#pragma unroll
+      for (int j = 0; j < CW / 8; ++j) r1[j] = (valid && col0 + j * 8 < a.Cout) ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
+    }
+    if (a.resb) {
+      const uint4* rp = reinterpret_cast<const uint4*>(a.resb + pix * a.resb_ld + col0);
+#pragma unroll
+      for (int j = 0; j < CW / 8; ++j) r2[j] = (valid && col0 + j * 8 < a.Cout) ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
+    }
+    DP_T(const long long e0 = clock64();)
+    tc::mbar_wait(&bars->tmem_full[buf], (it >> (a.nbuf == 4 ? 2 : 1)) & 1);
+    tc::fence_after_sync();
+    DP_T(const long long e1 = clock64(); dbg_ew += e1 - e0;)
+    uint32_t raw[CW];
+    tc::tmem_ld_issue<CW>(tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * a.BN + col0), raw);
+    tc::tmem_ld_wait();
+    tc::fence_before_sync();
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(&bars->tmem_empty[buf]);   // accumulator is in registers: free it for the next tile
+    float v[CW];
+#pragma unroll
+    for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(raw[j]);
+    if (a.bias) {
+#pragma unroll
+      for (int j = 0; j < CW; j += 4) {
+        if (col0 + j < a.Cout) {   // Cout is a multiple of 8
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + col0 + j));
+          v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+        }
+      }
+    }
+    if (a.res) {
+#pragma unroll
+      for (int j = 0; j < CW / 8; ++j) {
+        const uint32_t rr[4] = {r1[j].x, r1[j].y, r1[j].z, r1[j].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { v[j * 8 + 2 * k] += bf16_lo(rr[k]); v[j * 8 + 2 * k + 1] += bf16_hi(rr[k]); }
+      }
+    }
+    if (a.resb) {
+#pragma unroll
+      for (int j = 0; j < CW / 8; ++j) {
+        const uint32_t rr[4] = {r2[j].x, r2[j].y, r2[j].z, r2[j].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { v[j * 8 + 2 * k] += bf16_lo(rr[k]); v[j * 8 + 2 * k + 1] += bf16_hi(rr[k]); }
+      }
+    }
+    const uint32_t ring_off = (uint32_t)ring * (dual ? 2u : 1u) * a.out_tile_bytes;
+    const uint32_t st = s_base + ring_off;
+#pragma unroll
+    for (int j = 0; j < CW / 8; ++j) {
+      uint32_t q[4], q2[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float x0v = v[j * 8 + 2 * k], x1v = v[j * 8 + 2 * k + 1];
+        const uint32_t plain = pack_bf16x2(x0v, x1v);
+        const uint32_t act = pack_bf16x2(fmaxf(x0v, 0.f), fmaxf(x1v, 0.f));
+        q[k] = a.relu ? act : plain;
+        q2[k] = a.relu2 ? act : plain;
+        if (want_stats) {
+          // statistics of the value as stored (bf16-rounded), so mean/var describe the tensor the consumer reads
+          const float f0 = valid ? bf16_lo(plain) : 0.f, f1 = valid ? bf16_hi(plain) : 0.f;
+          acc_s[j * 8 + 2 * k] += f0;
+          acc_q[j * 8 + 2 * k] = fmaf(f0, f0, acc_q[j * 8 + 2 * k]);
+          acc_s[j * 8 + 2 * k + 1] += f1;
+          acc_q[j * 8 + 2 * k + 1] = fmaf(f1, f1, acc_q[j * 8 + 2 * k + 1]);
+        }
+      }
+      tc::st_shared_v4(st + soff[j], q[0], q[1], q[2], q[3]);
+      if (dual) tc::st_shared_v4(st + a.out_tile_bytes + soff[j], q2[0], q2[1], q2[2], q2[3]);
+    }
+    tc::fence_proxy_async();                                  // generic-proxy smem writes -> visible to the TMA engine
+    // ring of nob staging tiles, one barrier per tile: before the barrier the store thread makes sure at most
+    // nob - 2 earlier stores are still reading shared memory, so the buffer the NEXT tile writes is free.
+    if (store_thread) {
+      if (a.nob == 2) tc::bulk_wait_read<0>();
+      else if (a.nob == 3) tc::bulk_wait_read<1>();
+      else tc::bulk_wait_read<2>();
+    }
+    tc::named_bar_sync(1, kEpiThreads);
+    if (store_thread) {
+      tc::tma_store_4d(&tm.o, s_out + ring_off, 0, x0, y0, n);
+      if (dual) tc::tma_store_4d(&tm.o2, s_out + ring_off + a.out_tile_bytes, 0, x0, y0, n);
+      tc::bulk_commit();
+    }
+    if (++ring == a.nob) ring = 0;
+    DP_T(dbg_ek += clock64() - e1;)
+  }
+  if (store_thread) tc::bulk_wait_read<0>();
+  DP_T(if (a.dbg && blockIdx.x == 0 && threadIdx.x == kRoleThreads) { a.dbg[5] = dbg_ew; a.dbg[6] = dbg_ek; a.dbg[7] = it; })
+  if (want_stats) {
+#pragma unroll
+    for (int j = 0; j < CW; ++j) {
+      const float s = dp::warp_sum(acc_s[j]);
+      const float q = dp::warp_sum(acc_q[j]);
+      if (lane == 0 && col0 + j < a.Cout) {
+        s_stats[(ew * 2 + 0) * a.Cout + col0 + j] = s;
+        s_stats[(ew * 2 + 1) * a.Cout + col0 + j] = q;
+      }
+    }
+  }
+}
+
+// ---- epilogue B (any BN): 16-column chunks alternate between the two warps that share a TMEM lane quarter; each
+// thread writes its pixel's 32 bytes straight to global memory.
+__device__ __forceinline__ void epilogue_direct(const ConvArgs& a, Barriers* bars, float* s_stats, uint32_t tmem,
+                                                int warp, int lane) {
+  const int e = warp - 4, ew = e & 3, half = e >> 2;
+  const int m = ew * 32 + lane;
+  const int py = m / a.tw, px = m - py * a.tw;
+  int it = 0;
+  TileIter ti;
+  ti.init(a, blockIdx.x);
+  for (long long item = blockIdx.x; item < a.total_items; item += gridDim.x, ++it, ti.step(a)) {
+    const int n = ti.n, y0 = ti.ty * a.th, x0 = ti.tx * a.tw, nb = ti.nb;
+    const int buf = it & (a.nbuf - 1);
+    const int y = y0 + py, x = x0 + px;
+    const int oy = y * a.osy + a.oay, ox = x * a.osx + a.oax;
+    const bool valid = (y < a.H) && (x < a.W) && (oy < a.Ho) && (ox < a.Wo);
+    const long long pix = ((long long)n * a.Ho + oy) * a.Wo + ox;
+    tc::mbar_wait(&bars->tmem_full[buf], (it >> (a.nbuf == 4 ? 2 : 1)) & 1);
+    tc::fence_after_sync();
+    const uint32_t t_base = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * a.BN);
+    for (int c0 = half * 16; c0 < a.BN; c0 += 32) {
+      const int n0 = nb * a.BN + c0;
+      if (n0 >= a.Cout) break;  // warp-uniform
+      const int nvalid = min(16, a.Cout - n0);
+      float v[16];
+      tc::tmem_ld16(t_base + c0, v);
+      if (a.bias) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < nvalid) v[j] += __ldg(a.bias + n0 + j);
+      }
+      if (a.res && valid) {
+        const uint4* rp = reinterpret_cast<const uint4*>(a.res + pix * a.res_ld + n0);
+        uint4 r0 = __ldg(rp);
+        uint4 r1 = nvalid > 8 ? __ldg(rp + 1) : make_uint4(0, 0, 0, 0);
+        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { v[2 * j] += bf16_lo(rr[j]); v[2 * j + 1] += bf16_hi(rr[j]); }
+      }
+      if (a.resb && valid) {
+        const uint4* rp = reinterpret_cast<const uint4*>(a.resb + pix * a.resb_ld + n0);
+        uint4 r0 = __ldg(rp);
+        uint4 r1 = nvalid > 8 ? __ldg(rp + 1) : make_uint4(0, 0, 0, 0);
+        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { v[2 * j] += bf16_lo(rr[j]); v[2 * j + 1] += bf16_hi(rr[j]); }
+      }
+      if (a.stats) {
+        float sv[16], sq[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          // statistics of the value as stored (bf16-rounded), so mean/var describe the tensor the consumer reads
+          const float q = valid ? __bfloat162float(__float2bfloat16_rn(v[j])) : 0.f;
+          sv[j] = q;
+          sq[j] = q * q;
+        }
+        const float cs = transpose_reduce16(sv, lane);
+        const float cq = transpose_reduce16(sq, lane);
+        if ((lane & 1) == 0) {
+          const int col = n0 + transpose_reduce16_col(lane);
+          if (col < a.Cout) {
+            s_stats[(ew * 2 + 0) * a.Cout + col] += cs;
+            s_stats[(ew * 2 + 1) * a.Cout + col] += cq;
+          }
+        }
+      }
+      if (valid) {
+        if (a.out2) {
+          uint32_t q[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float x0v = v[2 * j], x1v = v[2 * j + 1];
+            if (a.relu2) { x0v = fmaxf(x0v, 0.f); x1v = fmaxf(x1v, 0.f); }
+            q[j] = pack_bf16x2(x0v, x1v);
+          }
+          uint4* op = reinterpret_cast<uint4*>(a.out2 + pix * a.out2_ld + n0);
+          op[0] = make_uint4(q[0], q[1], q[2], q[3]);
+          if (nvalid > 8) op[1] = make_uint4(q[4], q[5], q[6], q[7]);
+        }
+        if (a.out) {
+          uint32_t q[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float x0v = v[2 * j], x1v = v[2 * j + 1];
+            if (a.relu) { x0v = fmaxf(x0v, 0.f); x1v = fmaxf(x1v, 0.f); }
+            q[j] = pack_bf16x2(x0v, x1v);
+          }
+          uint4* op = reinterpret_cast<uint4*>(a.out + pix * a.out_ld + n0);
+          op[0] = make_uint4(q[0], q[1], q[2], q[3]);
+          if (nvalid > 8) op[1] = make_uint4(q[4], q[5], q[6], q[7]);
+        }
+      }
+    }
+    tc::fence_before_sync();
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(&bars->tmem_empty[buf]);
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // layout: [resident weights][stages x (A | B)][stats][barriers]
+  // layout: [resident weights][output staging tiles][stages x (A | B)][stats][barriers]
   uint8_t* s_res = smem;
-  uint8_t* s_stage = smem + a.resident_bytes;
+  uint8_t* s_out = smem + a.resident_bytes;
+  const uint32_t out_bytes = a.epi_tma ? (uint32_t)a.nob * (a.out2 ? 2u : 1u) * a.out_tile_bytes : 0u;
+  uint8_t* s_stage = s_out + out_bytes;
   const uint32_t stage_bytes = a.a_slot_bytes + (a.resident ? 0u : (uint32_t)a.max_nr * a.b_tap_bytes);
   float* s_stats = reinterpret_cast<float*>(s_stage + (size_t)a.stages * stage_bytes);
   const int stats_floats = a.stats ? 4 * 2 * a.Cout : 0;
@@ -155,11 +431,12 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < a.stages; ++i) { tc::mbar_init(&bars->full[i], 1); tc::mbar_init(&bars->empty[i], 1); }
-    for (int i = 0; i < 4; ++i) { tc::mbar_init(&bars->tmem_full[i], 1); tc::mbar_init(&bars->tmem_empty[i], 4); }
+    for (int i = 0; i < 4; ++i) { tc::mbar_init(&bars->tmem_full[i], 1); tc::mbar_init(&bars->tmem_empty[i], kEpiWarps); }
     tc::mbar_init(&bars->resident_full, 1);
     tc::fence_barrier_init();
     tc::prefetch_tmap(&tm.a[0]);
     tc::prefetch_tmap(&tm.b);
+    if (a.epi_tma) tc::prefetch_tmap(&tm.o);
   }
   if (warp == 2) tc::tmem_alloc(&bars->tmem_base, kTmemCols);
   for (int i = threadIdx.x; i < stats_floats; i += kThreads) s_stats[i] = 0.f;
@@ -167,7 +444,7 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = bars->tmem_base;
-  const long long t_start = clock64();
+  DP_T(const long long t_start = clock64();)
 
   if (warp == 0 && lane == 0) {
     // ================= TMA producer =================
@@ -187,9 +464,10 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
       }
     }
     uint32_t stage = 0, phase = 0;
-    for (long long item = blockIdx.x; item < a.total_items; item += gridDim.x) {
-      int n, y0, x0, nb;
-      decode_item(a, item, n, y0, x0, nb);
+    TileIter ti;
+    ti.init(a, blockIdx.x);
+    for (long long item = blockIdx.x; item < a.total_items; item += gridDim.x, ti.step(a)) {
+      const int n = ti.n, y0 = ti.ty * a.th, x0 = ti.tx * a.tw, nb = ti.nb;
       for (int c = 0; c < a.ncols; ++c) {
         const ColLoad& col = a.cols[c];
         for (int kc = 0; kc < a.kchunks; ++kc) {
@@ -218,27 +496,29 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
     const uint32_t a_hi_halo = tc::desc_hi((uint32_t)a.pitch * a.row_bytes, a.layout);
     const uint32_t res_base = tc::smem_u32(s_res);
     const int ksteps = a.ncols * a.kchunks;
-    long long dbg_te = 0, dbg_wf = 0, dbg_is = 0;
+    DP_T(long long dbg_te = 0; long long dbg_wf = 0; long long dbg_is = 0;)
     int it = wiss;
+    // stage ring position of this issuer's next tile: tile `it` starts at global k-step it * ksteps
+    uint32_t stage = 0, phase = 0;
+    for (int k = 0; k < wiss * ksteps; ++k)
+      if (++stage == (uint32_t)a.stages) { stage = 0; phase ^= 1; }
+    const int nbuf_mask = a.nbuf - 1, nbuf_shift = a.nbuf == 4 ? 2 : 1;
     for (long long item = blockIdx.x + (long long)wiss * gridDim.x; item < a.total_items;
          item += (long long)a.niss * gridDim.x, it += a.niss) {
-      const int buf = it % a.nbuf;
-      const long long q0 = clock64();
-      tc::mbar_wait(&bars->tmem_empty[buf], ((it / a.nbuf) & 1) ^ 1);
+      const int buf = it & nbuf_mask;
+      DP_T(const long long q0 = clock64();)
+      tc::mbar_wait(&bars->tmem_empty[buf], ((it >> nbuf_shift) & 1) ^ 1);
       tc::fence_after_sync();
-      dbg_te += clock64() - q0;
+      DP_T(dbg_te += clock64() - q0;)
       const uint32_t d_tmem = tmem + (uint32_t)(buf * a.BN);
       uint32_t accumulate = 0;
-      const long long g0 = (long long)it * ksteps;      // global k-step counter: stage ring position of this tile
-      uint32_t stage = (uint32_t)(g0 % a.stages), phase = (uint32_t)((g0 / a.stages) & 1);
       for (int c = 0; c < a.ncols; ++c) {
         const ColLoad& col = a.cols[c];
         for (int kc = 0; kc < a.kchunks; ++kc) {
-          const long long q1 = clock64();
+          DP_T(const long long q1 = clock64();)
           tc::mbar_wait(&bars->full[stage], phase);
           tc::fence_after_sync();
-          const long long q2 = clock64();
-          dbg_wf += q2 - q1;
+          DP_T(const long long q2 = clock64(); dbg_wf += q2 - q1;)
           const uint32_t a_base = tc::smem_u32(s_stage + (size_t)stage * stage_bytes);
           if (a.halo) {
             // all nine taps read the same halo box: tap (r,s) starts (r*pitch + s) pixel rows in; the 8-pixel patch
@@ -278,125 +558,28 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
             }
           }
           tc::umma_commit(&bars->empty[stage]);  // frees the smem slot when these MMAs have read it
-          dbg_is += clock64() - q2;
+          DP_T(dbg_is += clock64() - q2;)
           if (++stage == (uint32_t)a.stages) { stage = 0; phase ^= 1; }
         }
       }
       tc::umma_commit(&bars->tmem_full[buf]);  // accumulator complete -> epilogue
+      for (int k = 0; k < (a.niss - 1) * ksteps; ++k)   // skip the other issuer's tile in the stage ring
+        if (++stage == (uint32_t)a.stages) { stage = 0; phase ^= 1; }
     }
-    if (a.dbg && blockIdx.x == 0 && wiss == 0) { a.dbg[0] = dbg_te; a.dbg[1] = dbg_wf; a.dbg[2] = dbg_is; a.dbg[4] = it; }
+    DP_T(if (a.dbg && blockIdx.x == 0 && wiss == 0) { a.dbg[0] = dbg_te; a.dbg[1] = dbg_wf; a.dbg[2] = dbg_is; a.dbg[4] = it; })
   } else if (warp >= 4) {
-    // ================= epilogue: TMEM -> registers -> global =================
-    const int ew = warp - 4;  // == warp % 4: TMEM lanes [32*ew, 32*ew+32)
-    const int m = ew * 32 + lane;
-    const int py = m / a.tw, px = m - py * a.tw;
-    long long dbg_ew = 0, dbg_ek = 0;
-    int it = 0;
-    for (long long item = blockIdx.x; item < a.total_items; item += gridDim.x, ++it) {
-      int n, y0, x0, nb;
-      decode_item(a, item, n, y0, x0, nb);
-      const int buf = it % a.nbuf;
-      const int y = y0 + py, x = x0 + px;
-      const int oy = y * a.osy + a.oay, ox = x * a.osx + a.oax;
-      const bool valid = (y < a.H) && (x < a.W) && (oy < a.Ho) && (ox < a.Wo);
-      const long long pix = ((long long)n * a.Ho + oy) * a.Wo + ox;
-      const long long e0 = clock64();
-      tc::mbar_wait(&bars->tmem_full[buf], (it / a.nbuf) & 1);
-      tc::fence_after_sync();
-      const long long e1 = clock64();
-      dbg_ew += e1 - e0;
-      const uint32_t t_base = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * a.BN);
-      for (int c0 = 0; c0 < a.BN; c0 += 16) {
-        const int n0 = nb * a.BN + c0;
-        if (n0 >= a.Cout) break;  // warp-uniform
-        const int nvalid = min(16, a.Cout - n0);
-        float v[16];
-        tc::tmem_ld16(t_base + c0, v);
-        if (a.bias) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < nvalid) v[j] += __ldg(a.bias + n0 + j);
-        }
-        if (a.res && valid) {
-          const uint4* rp = reinterpret_cast<const uint4*>(a.res + pix * a.res_ld + n0);
-          uint4 r0 = __ldg(rp);
-          uint4 r1 = nvalid > 8 ? __ldg(rp + 1) : make_uint4(0, 0, 0, 0);
-          const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
-            v[2 * j] += __low2float(h);
-            v[2 * j + 1] += __high2float(h);
-          }
-        }
-        if (a.resb && valid) {
-          const uint4* rp = reinterpret_cast<const uint4*>(a.resb + pix * a.resb_ld + n0);
-          uint4 r0 = __ldg(rp);
-          uint4 r1 = nvalid > 8 ? __ldg(rp + 1) : make_uint4(0, 0, 0, 0);
-          const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
-            v[2 * j] += __low2float(h);
-            v[2 * j + 1] += __high2float(h);
-          }
-        }
-        if (a.stats) {
-          float sv[16], sq[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            // statistics of the value as stored (bf16-rounded), so mean/var describe the tensor the consumer reads
-            const float q = valid ? __bfloat162float(__float2bfloat16_rn(v[j])) : 0.f;
-            sv[j] = q;
-            sq[j] = q * q;
-          }
-          const float cs = transpose_reduce16(sv, lane);
-          const float cq = transpose_reduce16(sq, lane);
-          if ((lane & 1) == 0) {
-            const int col = n0 + transpose_reduce16_col(lane);
-            if (col < a.Cout) {
-              s_stats[(ew * 2 + 0) * a.Cout + col] += cs;
-              s_stats[(ew * 2 + 1) * a.Cout + col] += cq;
-            }
-          }
-        }
-        if (valid) {
-          if (a.out2) {
-            uint32_t q[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float x0v = v[2 * j], x1v = v[2 * j + 1];
-              if (a.relu2) { x0v = fmaxf(x0v, 0.f); x1v = fmaxf(x1v, 0.f); }
-              q[j] = pack_bf16x2(x0v, x1v);
-            }
-            uint4* op = reinterpret_cast<uint4*>(a.out2 + pix * a.out2_ld + n0);
-            op[0] = make_uint4(q[0], q[1], q[2], q[3]);
-            if (nvalid > 8) op[1] = make_uint4(q[4], q[5], q[6], q[7]);
-          }
-          if (a.out) {
-            uint32_t q[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float x0v = v[2 * j], x1v = v[2 * j + 1];
-              if (a.relu) { x0v = fmaxf(x0v, 0.f); x1v = fmaxf(x1v, 0.f); }
-              q[j] = pack_bf16x2(x0v, x1v);
-            }
-            uint4* op = reinterpret_cast<uint4*>(a.out + pix * a.out_ld + n0);
-            op[0] = make_uint4(q[0], q[1], q[2], q[3]);
-            if (nvalid > 8) op[1] = make_uint4(q[4], q[5], q[6], q[7]);
-          }
-        }
-      }
-      tc::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&bars->tmem_empty[buf]);
-      dbg_ek += clock64() - e1;
+    // ================= epilogue: TMEM -> registers -> (smem -> TMA store | global) =================
+    if (a.epi_tma) {
+      if (a.BN == 64) epilogue_tma<32>(tm, a, bars, s_out, s_stats, tmem, warp, lane);
+      else if (a.BN == 32) epilogue_tma<16>(tm, a, bars, s_out, s_stats, tmem, warp, lane);
+      else epilogue_tma<8>(tm, a, bars, s_out, s_stats, tmem, warp, lane);
+    } else {
+      epilogue_direct(a, bars, s_stats, tmem, warp, lane);
     }
-    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 128) { a.dbg[5] = dbg_ew; a.dbg[6] = dbg_ek; a.dbg[7] = it; }
     if (a.stats) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+      tc::named_bar_sync(1, kEpiThreads);  // the epilogue warps only
       float* dst = a.stats + (size_t)blockIdx.x * 2 * a.Cout;
-      for (int i = threadIdx.x - 128; i < 2 * a.Cout; i += 128) {
+      for (int i = threadIdx.x - kRoleThreads; i < 2 * a.Cout; i += kEpiThreads) {
         const int which = i / a.Cout, col = i - which * a.Cout;
         float s = 0.f;
 #pragma unroll
@@ -407,7 +590,7 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[3] = (unsigned long long)(clock64() - t_start);
+  DP_T(if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[3] = (unsigned long long)(clock64() - t_start);)
   if (warp == 2) tc::tmem_dealloc(tmem, kTmemCols);
 }
 
@@ -434,7 +617,7 @@ struct Plan {
 
 // geometry that does not depend on pointers: tile shape, K/N blocking, stages, grid
 int make_plan(Plan& p, int B, int Hg, int Wg, int Cin, int Cout, const ColSpec* cols, int ncols, int want_stats,
-              int allow_halo = 0) {
+              int allow_halo = 0, int n_out = 1) {
   ConvArgs& a = p.a;
   if (ncols < 1 || ncols > kMaxCols) return dp_set_error(DP_ERR_UNSUPPORTED, "conv_tc: %d column loads", ncols);
   a.B = B; a.H = Hg; a.W = Wg; a.Cout = Cout;
@@ -494,7 +677,12 @@ int make_plan(Plan& p, int B, int Hg, int Wg, int Cin, int Cout, const ColSpec* 
   a.resident = (a.n_blocks == 1 && all_w <= 100 * 1024) ? 1 : 0;
   a.resident_bytes = a.resident ? (uint32_t)all_w : 0u;
   const size_t stats_bytes = want_stats ? ((size_t)4 * 2 * Cout * 4 + 15) & ~size_t(15) : 0;
-  const size_t fixed = 1024 + a.resident_bytes + stats_bytes + sizeof(Barriers) + 64;
+  // TMA-store epilogue: one N block of 16/32/64 columns; two staging tiles per output
+  a.epi_tma = (a.n_blocks == 1 && (a.BN == 16 || a.BN == 32 || a.BN == 64) && n_out >= 1) ? 1 : 0;
+  a.out_tile_bytes = (uint32_t)(128 * a.BN * 2);
+  a.nob = n_out >= 2 ? 2 : (a.BN == 64 ? 3 : 4);
+  const size_t out_bytes = a.epi_tma ? (size_t)a.nob * n_out * a.out_tile_bytes : 0;
+  const size_t fixed = 1024 + a.resident_bytes + out_bytes + stats_bytes + sizeof(Barriers) + 64;
   const size_t budget = 220 * 1024;
   const size_t stage = a.a_slot_bytes + (a.resident ? 0 : (size_t)a.max_nr * a.b_tap_bytes);
   if (fixed + 2 * stage > budget)
@@ -507,13 +695,22 @@ int make_plan(Plan& p, int B, int Hg, int Wg, int Cin, int Cout, const ColSpec* 
   p.smem = fixed + (size_t)a.stages * stage;
   a.total_items = (long long)B * a.tiles_y * a.tiles_x * a.n_blocks;
   p.grid = (int)(a.total_items < dp::kNumSMs ? a.total_items : dp::kNumSMs);
+  {
+    int g = p.grid;
+    a.step_nb = g % a.n_blocks; g /= a.n_blocks;
+    a.step_tx = g % a.tiles_x; g /= a.tiles_x;
+    a.step_ty = g % a.tiles_y; g /= a.tiles_y;
+    a.step_n = g;
+  }
+  if (a.total_items >= (1LL << 31)) return dp_set_error(DP_ERR_UNSUPPORTED, "conv_tc: %lld work items", a.total_items);
   return DP_OK;
 }
 
 int launch(const Plane* planes, const ColSpec* cols, int ncols, int B, int Hg, int Wg, int Cin, const void* w_packed,
            int Cin_p, int ntaps, int Cout, const Epilogue& ep, const OutMap& om, cudaStream_t stream, int allow_halo = 0) {
   Plan p;
-  int rc = make_plan(p, B, Hg, Wg, Cin, Cout, cols, ncols, ep.stats != nullptr, allow_halo);
+  int rc = make_plan(p, B, Hg, Wg, Cin, Cout, cols, ncols, ep.stats != nullptr, allow_halo,
+                     ep.out ? (ep.out2 ? 2 : 1) : 0);
   if (rc) return rc;
   if (p.a.halo) ncols = 1;
   ConvArgs& a = p.a;
@@ -543,6 +740,24 @@ int launch(const Plane* planes, const ColSpec* cols, int ncols, int B, int Hg, i
     uint32_t box[3] = {(uint32_t)a.KB, (uint32_t)a.BN, 1};
     rc = dp_make_tmap_bf16(&tm.b, w_packed, 3, dims, str, box, nullptr, a.row_bytes);
     if (rc) return rc;
+  }
+  tm.o = tm.a[0];
+  tm.o2 = tm.a[0];
+  if (a.epi_tma) {
+    // output tiles leave through TMA: the (possibly strided, for the transposed-conv output phases) pixel grid of the
+    // output tensor that GEMM pixel (y, x) maps to; overhanging pixels / channels are clipped by the store
+    const uint64_t Wv = (uint64_t)((om.Wo - om.oax + om.osx - 1) / om.osx), Hv = (uint64_t)((om.Ho - om.oay + om.osy - 1) / om.osy);
+    uint64_t dims[4] = {(uint64_t)Cout, Wv, Hv, (uint64_t)B};
+    uint32_t box[4] = {(uint32_t)a.BN, (uint32_t)a.tw, (uint32_t)a.th, 1};
+    for (int k = 0; k < 2; ++k) {
+      bf16* base = k == 0 ? a.out : a.out2;
+      const long long ld = k == 0 ? a.out_ld : a.out2_ld;
+      if (!base) continue;
+      uint64_t str[3] = {(uint64_t)om.osx * ld * 2, (uint64_t)om.osy * om.Wo * ld * 2, (uint64_t)om.Ho * om.Wo * ld * 2};
+      rc = dp_make_tmap_bf16(k == 0 ? &tm.o : &tm.o2, base + ((long long)om.oay * om.Wo + om.oax) * ld, 4, dims, str, box,
+                             nullptr, a.BN * 2);
+      if (rc) return rc;
+    }
   }
   cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
   if (e != cudaSuccess) return dp_set_error(DP_ERR_CUDA, "cudaFuncSetAttribute(%zu): %s", p.smem, cudaGetErrorString(e));

@@ -15,6 +15,12 @@
 #include "tc.cuh"
 #include "../../include/depth_b200.h"
 
+#ifdef DP_CONV_TIMING
+#define DP_T(x) x
+#else
+#define DP_T(x)
+#endif
+
 namespace {
 
 constexpr int kThreads = 192;  // warp 0 producer, warp 1 MMA (+TMEM alloc), warps 2..5 epilogue
@@ -40,6 +46,7 @@ struct WgArgs {
   int MC, m_chunks, M, co_blocks;   // M chunk width (<=64 channels), chunks per UMMA, UMMA M, blocks over Cout
   int NC, ci_chunks;                // N chunk width (<=64 channels), chunks over Cin (tapped operand channels)
   int psplit, stages;
+  int step_tx, step_ty, step_n;     // digits of the tile stride (psplit) in the (tiles_x, tiles_y, B) radix
   int ngrp[kMaxKW];
   WgGroup grp[kMaxKW][2];
   long long tiles_total;
@@ -83,19 +90,23 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps tm, const __grid_constant__ WgArg
   const uint32_t tmem = bars->tmem_base;
   const int real_chunks = a.MC < 64 ? 1 : a.m_chunks;  // chunks actually loaded (narrow layers alias chunk 0)
 
-  const long long t_start = clock64();
+  DP_T(const long long t_start = clock64();)
   if (warp == 0 && lane == 0) {
     uint32_t stage = 0, phase = 0;
-    long long w_acc = 0;
+    DP_T(long long w_acc = 0;)
+    // tile walk with stride psplit: decode once, then advance the (tx, ty, n) digits by the stride's digits
+    int tx, ty, n;
+    {
+      unsigned m = (unsigned)ps;
+      tx = (int)(m % (unsigned)a.tiles_x); m /= (unsigned)a.tiles_x;
+      ty = (int)(m % (unsigned)a.tiles_y);
+      n = (int)(m / (unsigned)a.tiles_y);
+    }
     for (long long t = ps; t < a.tiles_total; t += a.psplit) {
-      long long m = t;
-      const int tx = (int)(m % a.tiles_x); m /= a.tiles_x;
-      const int ty = (int)(m % a.tiles_y);
-      const int n = (int)(m / a.tiles_y);
       const int y0 = ty * a.th, x0 = tx * a.tw;
-      const long long c0 = clock64();
+      DP_T(const long long c0 = clock64();)
       tc::mbar_wait(&bars->empty[stage], phase ^ 1);
-      w_acc += clock64() - c0;
+      DP_T(w_acc += clock64() - c0;)
       uint8_t* sA = smem + (size_t)stage * a.stage_bytes;
       uint8_t* sX = sA + (size_t)real_chunks * a.a_slot_bytes;
       uint32_t txb = (uint32_t)real_chunks * a.a_box_bytes;
@@ -108,21 +119,22 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps tm, const __grid_constant__ WgArg
         tc::tma_load_4d(sX + G.slot_off, &tm.t[G.map], &bars->full[stage], cc * a.NC, x0 + G.dx, y0 + G.dy, n);
       }
       if (++stage == (uint32_t)a.stages) { stage = 0; phase ^= 1; }
+      tx += a.step_tx; ty += a.step_ty; n += a.step_n;
+      if (tx >= a.tiles_x) { tx -= a.tiles_x; ++ty; }
+      if (ty >= a.tiles_y) { ty -= a.tiles_y; ++n; }
     }
-    if (a.dbg && blockIdx.x == 0) a.dbg[0] = (unsigned long long)w_acc;
+    DP_T(if (a.dbg && blockIdx.x == 0) a.dbg[0] = (unsigned long long)w_acc;)
   } else if (warp == 1 && lane == 0) {
     uint32_t stage = 0, phase = 0;
     uint32_t accumulate = 0;
-    long long w_acc = 0, i_acc = 0, ntile = 0;
+    DP_T(long long w_acc = 0; long long i_acc = 0; long long ntile = 0;)
     const uint32_t a_hi = tc::desc_hi(8 * a.rowA, a.layoutA), b_hi = tc::desc_hi(8 * a.rowB, a.layoutB);
     const uint32_t a_step = (16u * a.rowA) >> 4, b_step = (16u * a.rowB) >> 4;   // 16 pixel rows per UMMA K-step
     for (long long t = ps; t < a.tiles_total; t += a.psplit) {
-      const long long c0 = clock64();
+      DP_T(const long long c0 = clock64();)
       tc::mbar_wait(&bars->full[stage], phase);
       tc::fence_after_sync();
-      const long long c1 = clock64();
-      w_acc += c1 - c0;
-      ++ntile;
+      DP_T(const long long c1 = clock64(); w_acc += c1 - c0; ++ntile;)
       const uint32_t a_base = tc::smem_u32(smem + (size_t)stage * a.stage_bytes);
       const uint32_t x_base = a_base + (uint32_t)real_chunks * a.a_slot_bytes;
       for (int g = 0; g < a.ngrp[s]; ++g) {
@@ -139,11 +151,11 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps tm, const __grid_constant__ WgArg
       }
       accumulate = 1;
       tc::umma_commit(&bars->empty[stage]);
-      i_acc += clock64() - c1;
+      DP_T(i_acc += clock64() - c1;)
       if (++stage == (uint32_t)a.stages) { stage = 0; phase ^= 1; }
     }
     tc::umma_commit(&bars->done);
-    if (a.dbg && blockIdx.x == 0) { a.dbg[1] = (unsigned long long)w_acc; a.dbg[2] = (unsigned long long)i_acc; a.dbg[4] = (unsigned long long)ntile; }
+    DP_T(if (a.dbg && blockIdx.x == 0) { a.dbg[1] = (unsigned long long)w_acc; a.dbg[2] = (unsigned long long)i_acc; a.dbg[4] = (unsigned long long)ntile; })
   } else if (warp >= 2) {
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     tc::mbar_wait(&bars->done, 0);
@@ -174,7 +186,7 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps tm, const __grid_constant__ WgArg
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[3] = (unsigned long long)(clock64() - t_start);
+  DP_T(if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[3] = (unsigned long long)(clock64() - t_start);)
   if (warp == 1) tc::tmem_dealloc(tmem, 256);
 }
 
@@ -298,6 +310,12 @@ int wg_plan(WgPlan& p, int B, int Hg, int Wg, int Cp, int Ct, int K, int pad, in
     if (cost < best_cost) { best_cost = cost; ps = c; }
   }
   a.psplit = ps;
+  {
+    int g = ps;
+    a.step_tx = g % a.tiles_x; g /= a.tiles_x;
+    a.step_ty = g % a.tiles_y; g /= a.tiles_y;
+    a.step_n = g;
+  }
   long long per = (a.tiles_total + ps - 1) / ps;
   int st = (int)((200 * 1024) / a.stage_bytes);
   if (st > kMaxStages) st = kMaxStages;

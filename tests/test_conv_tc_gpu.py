@@ -89,6 +89,51 @@ def test_conv_epilogue_bias_residual_relu_dual(pkg):
     assert bool(((out.float() - ref).abs() <= 2 ** -7 * ref.abs() + 2e-3).all())
 
 
+@pytest.mark.parametrize("Cin,Cout,KS", [(64, 64, 3), (32, 32, 3), (64, 32, 1), (32, 16, 3), (16, 16, 3), (16, 8, 1)])
+def test_conv_tma_store_epilogue_all_operands(pkg, Cin, Cout, KS):
+    """BN in {16,32,64}: registers -> swizzled smem tile -> TMA store.  Bias + two residuals + dual (raw / ReLU) outputs,
+    tile overhang in both directions, outputs and residuals living in channel slices of wider buffers."""
+    L = pkg._lib
+    B, H, W = 2, 37, 43
+    g = torch.Generator().manual_seed(Cin * 100 + Cout + KS)
+    x = torch.randn(B, H, W, Cin, generator=g).to(torch.bfloat16).cuda()
+    w = (torch.randn(Cout, Cin, KS, KS, generator=g) * (2.0 / (Cin * KS * KS)) ** 0.5).cuda()
+    bias = torch.randn(Cout, generator=g).cuda()
+    wide = Cout + 24
+    r1 = torch.randn(B, H, W, wide, generator=g).to(torch.bfloat16).cuda()
+    r2 = torch.randn(B, H, W, Cout, generator=g).to(torch.bfloat16).cuda()
+    ob = torch.full((B, H, W, wide), 7.0, device="cuda", dtype=torch.bfloat16)
+    o2 = torch.full((B, H, W, Cout), 7.0, device="cuda", dtype=torch.bfloat16)
+    res1 = r1[..., 8:8 + Cout]
+    out = ob[..., 16:16 + Cout]
+    L.check(L.lib().dp_conv2d_tc(L.ptr(x), Cin, B, H, W, Cin, L.ptr(pack_w(w)), Cin, Cout, KS, L.ptr(bias),
+                                 res1.data_ptr(), wide, L.ptr(r2), Cout, 0, out.data_ptr(), wide, L.ptr(o2), Cout, 1,
+                                 None, L.stream()))
+    torch.cuda.synchronize()
+    ref = ref_conv(x, w, bias, res1, KS) + r2.float()
+    tol = 2 ** -7 * ref.abs() + 4e-3
+    assert bool(((out.float() - ref).abs() <= tol).all()), float((out.float() - ref).abs().max())
+    assert bool(((o2.float() - ref.clamp_min(0)).abs() <= tol).all())
+    # the store must not touch the neighbouring channels of the wide buffer
+    assert bool((ob[..., :16] == 7.0).all()) and bool((ob[..., 16 + Cout:] == 7.0).all())
+
+
+@pytest.mark.parametrize("Cin,Cout,KS", [(32, 32, 3), (16, 16, 3), (64, 32, 1), (32, 16, 1)])
+def test_conv_bn_statistics_with_bias_small_n(pkg, Cin, Cout, KS):
+    B, H, W = 3, 45, 52
+    g = torch.Generator().manual_seed(Cin + 3 * Cout + KS)
+    x = torch.randn(B, H, W, Cin, generator=g).to(torch.bfloat16).cuda()
+    w = (torch.randn(Cout, Cin, KS, KS, generator=g) * 0.1).cuda()
+    bias = torch.randn(Cout, generator=g).cuda()
+    out, _, st = run_conv(pkg, x, pack_w(w), Cout, KS, bias=bias, stats=True)
+    ref = ref_conv(x, w, bias, None, KS)
+    assert bool(((out.float() - ref).abs() <= 2 ** -7 * ref.abs() + 2e-3).all())
+    s = st.double().sum(dim=0)
+    y = out.double().reshape(-1, Cout)
+    assert torch.allclose(s[0], y.sum(0), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(s[1], (y * y).sum(0), rtol=1e-4, atol=1e-2)
+
+
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 40, 48, 64, 64), (3, 24, 40, 64, 32), (1, 50, 70, 32, 16)])
 def test_conv_bn_statistics(pkg, B, H, W, Cin, Cout):
     g = torch.Generator().manual_seed(9)
