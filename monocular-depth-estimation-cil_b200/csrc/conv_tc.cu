@@ -426,7 +426,7 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
   const int stats_floats = a.stats ? 4 * 2 * a.Cout : 0;
   Barriers* bars = reinterpret_cast<Barriers*>(reinterpret_cast<uint8_t*>(s_stats) + ((stats_floats * 4 + 15) & ~15));
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = tc::warp_idx_uniform();
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -446,8 +446,9 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
   const uint32_t tmem = bars->tmem_base;
   DP_T(const long long t_start = clock64();)
 
-  if (warp == 0 && lane == 0) {
-    // ================= TMA producer =================
+  if (warp == 0) {
+    // ================= TMA producer (one elected lane) =================
+    if (tc::elect_one_sync()) {
     if (a.resident) {
       tc::mbar_expect_tx(&bars->resident_full, (uint32_t)(a.nslots * a.kchunks) * a.b_box_bytes);
       if (a.halo) {
@@ -485,7 +486,9 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
         }
       }
     }
-  } else if ((warp == 1 || (warp == 3 && a.niss == 2)) && lane == 0) {
+    }
+  } else if (warp == 1 || (warp == 3 && a.niss == 2)) {
+    if (tc::elect_one_sync()) {
     // ================= MMA issuers (one thread each; two warps alternate tiles) =================
     // A lone thread needs ~50 cycles of scalar work per tcgen05.mma, more than a 128xNx16 UMMA with N <= 64 takes on
     // the tensor pipe, so two issuers work on alternate tiles with their own TMEM accumulators.
@@ -567,6 +570,7 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
         if (++stage == (uint32_t)a.stages) { stage = 0; phase ^= 1; }
     }
     DP_T(if (a.dbg && blockIdx.x == 0 && wiss == 0) { a.dbg[0] = dbg_te; a.dbg[1] = dbg_wf; a.dbg[2] = dbg_is; a.dbg[4] = it; })
+    }
   } else if (warp >= 4) {
     // ================= epilogue: TMEM -> registers -> (smem -> TMA store | global) =================
     if (a.epi_tma) {

@@ -68,7 +68,7 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps tm, const __grid_constant__ WgArg
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   WgBars* bars = reinterpret_cast<WgBars*>(smem + (size_t)a.stages * a.stage_bytes);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tc::warp_idx_uniform(), lane = threadIdx.x & 31;
 
   int id = blockIdx.x;
   const int ps = id % a.psplit; id /= a.psplit;
@@ -91,7 +91,8 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps tm, const __grid_constant__ WgArg
   const int real_chunks = a.MC < 64 ? 1 : a.m_chunks;  // chunks actually loaded (narrow layers alias chunk 0)
 
   DP_T(const long long t_start = clock64();)
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
+    if (tc::elect_one_sync()) {
     uint32_t stage = 0, phase = 0;
     DP_T(long long w_acc = 0;)
     // tile walk with stride psplit: decode once, then advance the (tx, ty, n) digits by the stride's digits
@@ -124,7 +125,9 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps tm, const __grid_constant__ WgArg
       if (ty >= a.tiles_y) { ty -= a.tiles_y; ++n; }
     }
     DP_T(if (a.dbg && blockIdx.x == 0) a.dbg[0] = (unsigned long long)w_acc;)
-  } else if (warp == 1 && lane == 0) {
+    }
+  } else if (warp == 1) {
+    if (tc::elect_one_sync()) {
     uint32_t stage = 0, phase = 0;
     uint32_t accumulate = 0;
     DP_T(long long w_acc = 0; long long i_acc = 0; long long ntile = 0;)
@@ -156,6 +159,7 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps tm, const __grid_constant__ WgArg
     }
     tc::umma_commit(&bars->done);
     DP_T(if (a.dbg && blockIdx.x == 0) { a.dbg[1] = (unsigned long long)w_acc; a.dbg[2] = (unsigned long long)i_acc; a.dbg[4] = (unsigned long long)ntile; })
+    }
   } else if (warp >= 2) {
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     tc::mbar_wait(&bars->done, 0);
