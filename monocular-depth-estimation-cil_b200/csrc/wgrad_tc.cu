@@ -46,6 +46,7 @@ struct WgArgs {
   int MC, m_chunks, M, co_blocks;   // M chunk width (<=64 channels), chunks per UMMA, UMMA M, blocks over Cout
   int NC, ci_chunks;                // N chunk width (<=64 channels), chunks over Cin (tapped operand channels)
   int psplit, stages;
+  int halo, pitch;                  // halo mode: one (th+2) x (tw+2) box of the tapped operand serves all nine taps
   int step_tx, step_ty, step_n;     // digits of the tile stride (psplit) in the (tiles_x, tiles_y, B) radix
   int ngrp[kMaxKW];
   WgGroup grp[kMaxKW][2];
@@ -74,7 +75,7 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps tm, const __grid_constant__ WgArg
   const int ps = id % a.psplit; id /= a.psplit;
   const int cc = id % a.ci_chunks; id /= a.ci_chunks;
   const int cb = id % a.co_blocks; id /= a.co_blocks;
-  const int s = id;  // horizontal tap
+  const int s = id;  // horizontal tap (always 0 in halo mode: the CTA walks all three itself)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < a.stages; ++i) { tc::mbar_init(&bars->full[i], 1); tc::mbar_init(&bars->empty[i], 1); }
@@ -83,7 +84,7 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps tm, const __grid_constant__ WgArg
     tc::prefetch_tmap(&tm.p);
     tc::prefetch_tmap(&tm.t[0]);
   }
-  if (warp == 1) tc::tmem_alloc(&bars->tmem_base, 256);
+  if (warp == 1) tc::tmem_alloc(&bars->tmem_base, 512);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -140,6 +141,24 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps tm, const __grid_constant__ WgArg
       DP_T(const long long c1 = clock64(); w_acc += c1 - c0; ++ntile;)
       const uint32_t a_base = tc::smem_u32(smem + (size_t)stage * a.stage_bytes);
       const uint32_t x_base = a_base + (uint32_t)real_chunks * a.a_slot_bytes;
+      if (a.halo) {
+        // one halo box: horizontal tap sx starts sx pixel rows in, vertical taps are `pitch` rows apart (LBO), and one
+        // K=16 slice is one 16-pixel tile row, i.e. `pitch` box rows further down per step.  The swizzle is a function
+        // of the absolute shared-memory address, so none of these offsets needs to be atom aligned.
+        const WgGroup& G = a.grp[0][0];
+        const uint32_t al0 = tc::desc_lo(a_base, a.a_lbo);
+        const uint32_t row16 = a.rowB >> 4, b_row_step = ((uint32_t)a.pitch * a.rowB) >> 4;
+        const uint32_t bl00 = tc::desc_lo(x_base + G.slot_off, (uint32_t)a.pitch * a.rowB);
+#pragma unroll
+        for (int sx = 0; sx < 3; ++sx) {
+          const uint32_t d_col = tmem + (uint32_t)(sx * 3 * a.NC);
+          const uint32_t bl0 = bl00 + (uint32_t)sx * row16;
+#pragma unroll
+          for (int k16 = 0; k16 < 8; ++k16)
+            tc::umma_bf16_lohi(d_col, al0 + (uint32_t)k16 * a_step, a_hi, bl0 + (uint32_t)k16 * b_row_step, b_hi, G.idesc,
+                               k16 > 0 ? 1u : accumulate);
+        }
+      } else
       for (int g = 0; g < a.ngrp[s]; ++g) {
         const WgGroup& G = a.grp[s][g];
         // the nr vertical taps of a group are the same box read r*tw pixel rows further down: with the MN-major
@@ -171,14 +190,17 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps tm, const __grid_constant__ WgArg
     const int co = cb * a.M + row;
     const bool row_ok = row >= 0 && row < (a.MC < 64 ? a.MC : a.M) && co < a.Cout;
     const bool has_work = ps < a.tiles_total;  // a split with no tiles left its TMEM untouched: write zeros
+    const int ns = a.halo ? 3 : 1;
+    for (int sx = 0; sx < ns; ++sx)
     for (int gr = 0; gr < a.ngrp[s] * 3; ++gr) {
       const WgGroup& G = a.grp[s][gr / 3];
       const int r = gr % 3;
       if (r >= G.nr) continue;  // warp-uniform
-      const int tap = G.ky[r] * a.KW + s;
+      const int tap = G.ky[r] * a.KW + (a.halo ? sx : s);
+      const uint32_t col_base = G.tmem_col + (uint32_t)(sx * 3 * a.NC);
       for (int c0 = 0; c0 < a.NC; c0 += 16) {
         float v[16];
-        tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + G.tmem_col + (uint32_t)(r * a.NC + c0), v);
+        tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + col_base + (uint32_t)(r * a.NC + c0), v);
         if (row_ok) {
           float* dst = a.partial + (((size_t)ps * a.KH * a.KW + tap) * a.Cout + co) * a.Cin + cc * a.NC + c0;
 #pragma unroll
@@ -191,7 +213,7 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps tm, const __grid_constant__ WgArg
   tc::fence_before_sync();
   __syncthreads();
   DP_T(if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[3] = (unsigned long long)(clock64() - t_start);)
-  if (warp == 1) tc::tmem_dealloc(tmem, 256);
+  if (warp == 1) tc::tmem_dealloc(tmem, 512);
 }
 
 // sum the split-K partials and write OIHW fp32: grad[co][ci][r][s] (+)= sum_ps partial[ps][tap][co][ci]
@@ -239,6 +261,11 @@ int wg_plan(WgPlan& p, int B, int Hg, int Wg, int Cp, int Ct, int K, int pad, in
     long long t = (long long)dp::ceil_div(Hg, cand[i][0]) * dp::ceil_div(Wg, cand[i][1]);
     if (best < 0 || t < best) { best = t; a.th = cand[i][0]; a.tw = cand[i][1]; }
   }
+  // halo mode (plain 3x3 with few tapped-operand channels, i.e. the bandwidth-bound full-resolution layers): every
+  // operand tile is fetched once and all nine taps accumulate in one CTA (9 x NC <= 512 TMEM columns)
+  a.halo = (stride == 1 && K == 3 && pad == 1 && Ct <= 64) ? 1 : 0;
+  a.pitch = 0;
+  if (a.halo) { a.th = 8; a.tw = 16; a.pitch = a.tw + 2; }
   a.tiles_y = dp::ceil_div(Hg, a.th);
   a.tiles_x = dp::ceil_div(Wg, a.tw);
   a.tiles_total = (long long)B * a.tiles_y * a.tiles_x;
@@ -246,7 +273,7 @@ int wg_plan(WgPlan& p, int B, int Hg, int Wg, int Cp, int Ct, int K, int pad, in
   a.M = Cp > 64 ? 128 : 64;
   a.m_chunks = a.M / a.MC;
   a.co_blocks = dp::ceil_div(Cp, a.M);
-  a.NC = Ct >= 64 ? 64 : (Ct > 16 ? 32 : 16);
+  a.NC = (Ct >= 64 && !a.halo) ? 64 : (Ct > 16 ? 32 : 16);
   a.ci_chunks = dp::ceil_div(Ct, a.NC);
   a.rowA = a.MC * 2; a.rowB = a.NC * 2;
   a.layoutA = tc::swizzle_for_row_bytes(a.rowA);
@@ -265,6 +292,10 @@ int wg_plan(WgPlan& p, int B, int Hg, int Wg, int Cp, int Ct, int K, int pad, in
       if (K > 3) return dp_set_error(DP_ERR_UNSUPPORTED, "wgrad_tc: stride-1 K %d", K);
       for (int r = 0; r < 3; ++r) G.ky[r] = r < K ? r : 0;
       G.box_bytes = (uint32_t)((a.th + K - 1) * a.tw) * a.rowB;
+      if (a.halo) {
+        G.map = 0; G.dx = -pad;
+        G.box_bytes = (uint32_t)((a.th + 2) * a.pitch) * a.rowB;
+      }
       G.slot_off = 0;
       off = (G.box_bytes + 1023u) & ~1023u;
       a.ngrp[kx] = 1;
@@ -298,19 +329,32 @@ int wg_plan(WgPlan& p, int B, int Hg, int Wg, int Cp, int Ct, int K, int pad, in
       G.idesc = tc::make_idesc_bf16(a.M, G.nr * a.NC, 1, 1);
       slot += G.nr;
     }
-    if (slot * a.NC > 256) return dp_set_error(DP_ERR_UNSUPPORTED, "wgrad_tc: accumulators exceed TMEM allocation");
+    if (slot * a.NC * (a.halo ? 3 : 1) > 512)
+      return dp_set_error(DP_ERR_UNSUPPORTED, "wgrad_tc: accumulators exceed TMEM allocation");
   }
   const int real_chunks = a.MC < 64 ? 1 : a.m_chunks;
   a.a_lbo = a.MC < 64 ? 0u : a.a_slot_bytes;
   a.stage_bytes = real_chunks * a.a_slot_bytes + max_x;
-  const int base_ctas = K * a.co_blocks * a.ci_chunks;
-  // split-K factor: minimise (waves / psplit), i.e. keep the last wave full (one CTA per SM)
+  const int base_ctas = (a.halo ? 1 : K) * a.co_blocks * a.ci_chunks;
+  // split-K factor.  Cost model (cycles at ~1.9 GHz): every CTA pays a fixed price (launch, TMEM allocation, the
+  // epilogue that writes taps x M x NC fp32 partials) plus a per-tile price (UMMA time on the pipe, or the issue /
+  // barrier latency floor for narrow layers); the partials are written once and read once by the reduce kernel.
+  double tile_cyc = 0.0;
+  for (int g = 0; g < a.ngrp[0]; ++g) {
+    const double pipe = (a.M / 128.0) * (a.grp[0][g].nr * a.NC) / 2.0;   // cycles per K=16 UMMA
+    tile_cyc += 8.0 * (pipe > 20.0 ? pipe : 20.0);
+  }
+  if (a.halo) tile_cyc *= 3.0;
+  tile_cyc += 250.0;
+  const double fixed_cyc = 5000.0 + 0.5 * K * a.M * a.NC;
+  const double part_bytes = (double)K * K * Cp * Ct * 4.0;
   int ps = 1;
   double best_cost = 1e30;
-  const int ps_max = (int)(a.tiles_total < dp::kNumSMs ? a.tiles_total : dp::kNumSMs);
+  const int ps_max = (int)(a.tiles_total < 4 * dp::kNumSMs ? a.tiles_total : 4 * dp::kNumSMs);
   for (int c = 1; c <= ps_max; ++c) {
     const int waves = (base_ctas * c + dp::kNumSMs - 1) / dp::kNumSMs;
-    const double cost = (double)waves / c + 1e-5 * c;
+    const double per_cta = (double)((a.tiles_total + c - 1) / c) * tile_cyc + fixed_cyc;
+    const double cost = waves * per_cta / 1.9e9 + 2.0 * c * part_bytes / 5.0e12;
     if (cost < best_cost) { best_cost = cost; ps = c; }
   }
   a.psplit = ps;
@@ -355,8 +399,9 @@ int wg_launch(WgPlan& p, const void* P, long long p_ld, const WgPlaneT* planes /
       const WgPlaneT* pl = &planes[G.map];   // planes are indexed like the tensor maps: [kx*2 + group parity]
       uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)pl->Wp, (uint64_t)pl->Hp, (uint64_t)B};
       uint64_t str[3] = {(uint64_t)pl->ld_px * 2, (uint64_t)pl->ld_row * 2, (uint64_t)pl->ld_img * 2};
-      uint32_t box[4] = {(uint32_t)a.NC, (uint32_t)a.tw, (uint32_t)(a.th + G.nr - 1), 1};
+      uint32_t box[4] = {(uint32_t)a.NC, (uint32_t)(a.halo ? a.pitch : a.tw), (uint32_t)(a.th + G.nr - 1), 1};
       int rc = dp_make_tmap_bf16(&tm.t[G.map], pl->base, 4, dims, str, box, nullptr, a.rowB);
+      if (a.halo) { first = tm.t[G.map]; have_first = true; kx = K; break; }   // the single halo box serves every tap
       if (rc) return rc;
       if (!have_first) { first = tm.t[G.map]; have_first = true; }
     }
