@@ -113,6 +113,14 @@ int dp_delta_counts(const float* pred, const float* target, const double* moment
 int dp_metrics_combine(const double* moments, const unsigned long long* counts, int B, int H, int W, int nthr,
                        float* out, cudaStream_t stream);
 
+/* evaluation.py:157-166 for one batch in one fused pass (8 B/px of HBM traffic): a thread-block cluster per sample
+ * accumulates the SI / AbsRel moments, exchanges them through distributed shared memory and counts the scale-aligned
+ * delta thresholds (util.py:183-207) on a second, L2-resident sweep; then the scalar combine.
+ * thresholds: HOST pointer.  moments: device double[B][DP_NMOM] (S1, S2, AR filled).  counts: device u64[B][nthr].
+ * out: device float[2+nthr] = SI-RMSE, AbsRel, delta_k (batch means). */
+int dp_eval_metrics(const float* pred, const float* target, int B, int H, int W, const float* thresholds, int nthr,
+                    float eps, double* moments, unsigned long long* counts, float* out, cudaStream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Convolutions (NHWC bf16 activations, fp32 accumulation in TMEM)
  * ---------------------------------------------------------------------------------------------- */
@@ -196,11 +204,14 @@ int dp_resize_bilinear_nhwc_bwd(const void* gout, long long g_ld, int B, int Hi,
 /* fp32 planes: the RGB->DINOv2 resize (midas_semantics.py:233) and the prediction resize (util.py:308-313) */
 int dp_resize_bilinear_planes_f32(const float* src, int planes, int Hi, int Wi, float* dst, int Ho, int Wo,
                                   int align_corners, cudaStream_t stream);
-/* per-channel sums over pixels: mode 0 sum x; 1 sum x, sum x^2; 2 sum g, sum g*x with g = dy*(mask>0).
+/* per-channel sums over pixels: mode 0 sum x; 1 sum x, sum x^2; 2 sum g, sum g*x with g = dy*(mask>0); 3 = 2 with the
+ * ReLU6 mask (0 < mask < 6).
  * partial: float[dp_chan_reduce_blocks()][2][C]; dp_sum_partials folds partials into out[rows][C] */
 int dp_chan_reduce_blocks(void);
+/* mask_ss (modes 2/3, optional): BN scale/shift [2][C] of the forward pass - the activation mask is then recomputed
+ * from x (x*scale+shift in fp32) instead of being read from the activated output; `mask`, if given, is then the residual added before the activation. */
 int dp_chan_reduce(int mode, const void* x, long long x_ld, const void* dy, long long dy_ld, const void* mask,
-                   long long m_ld, size_t npix, int C, float* partial, cudaStream_t stream);
+                   long long m_ld, const float* mask_ss, size_t npix, int C, float* partial, cudaStream_t stream);
 int dp_sum_partials(const float* partial, int nparts, int rows, int C, float* out, int accumulate, cudaStream_t stream);
 /* nn.BatchNorm2d (midas_semantics.py:40-61,133-151,196): train-mode finalize from (sum, sumsq) partials incl. running
  * statistics update (momentum, unbiased variance, num_batches_tracked += 1); eval-mode coefficients; apply; backward */
@@ -212,7 +223,8 @@ int dp_bn_eval_coeffs(const float* gamma, const float* beta, const float* runnin
 int dp_bn_apply(const void* x, long long x_ld, const float* scale_shift, const void* x2, long long x2_ld,
                 const float* scale_shift2, const void* res, long long res_ld, size_t npix, int C, int relu, void* y,
                 long long y_ld, cudaStream_t stream);
-int dp_bn_bwd_apply(const void* dy, long long dy_ld, const void* mask, long long m_ld, const void* x, long long x_ld,
+int dp_bn_bwd_apply(const void* dy, long long dy_ld, const void* mask, long long m_ld, const float* mask_ss,
+                    const void* x, long long x_ld,
                     const float* red, const float* save_mean_invstd, const float* gamma, double count, int train,
                     size_t npix, int C, void* dx, long long dx_ld, void* gmask, long long gm_ld, float* dgamma,
                     float* dbeta, int accumulate, cudaStream_t stream);
@@ -257,6 +269,22 @@ int dp_attn_fwd(const float* q, const float* k, const float* v, int B, int N, fl
 int dp_attn_bwd(const float* q, const float* k, const float* v, const float* out, const float* dout, const float* lse,
                 int B, int N, float scale, const void* items, int nitems, const void* segs, int nseg, float* dq,
                 float* dk, float* dv, float* delta, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Depthwise convolutions of the EfficientNet-Lite3 trunk (hub model consumed at blocks.py:166-186)
+ * ---------------------------------------------------------------------------------------------- */
+/* K in {3,5}, stride in {1,2}; explicit top/left padding (symmetric or TF-"SAME"); w fp32 [K*K][C] tap-major.
+ * stats_partials: null or float[dp_dwconv_fwd_blocks()][2][C] = per-block (sum, sumsq) of the stored output. */
+int dp_dwconv_fwd_blocks(int B, int Ho, int Wo, int C);
+int dp_dwconv_fwd(const void* x, long long x_ld, int B, int Hi, int Wi, int C, const float* w, int K, int stride,
+                  int pad_t, int pad_l, void* out, long long out_ld, int Ho, int Wo, float* stats_partials,
+                  cudaStream_t stream);
+int dp_dwconv_dgrad_s2(const void* dy, long long dy_ld, int B, int Ho, int Wo, int C, const float* w, int K, int pad_t,
+                       int pad_l, void* dx, long long dx_ld, int Hi, int Wi, cudaStream_t stream);
+size_t dp_dwconv_wgrad_workspace(int B, int Ho, int Wo, int C, int K);
+int dp_dwconv_wgrad(const void* x, long long x_ld, int B, int Hi, int Wi, int C, const void* dy, long long dy_ld, int Ho,
+                    int Wo, int K, int stride, int pad_t, int pad_l, float* grad, int accumulate, void* workspace,
+                    size_t workspace_bytes, cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Diagnostics

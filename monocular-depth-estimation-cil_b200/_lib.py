@@ -33,9 +33,34 @@ def lib():
                 "There is no CPU or PyTorch fallback for the hot path.")
         _lib = ctypes.CDLL(LIB_PATH)
         _declare(_lib)
+        if os.environ.get("DP_TRACE"):
+            _lib = _Traced(_lib)
         if _lib.dp_abi_version() != 1:
             raise DepthB200Error("libdepth_b200.so ABI version mismatch")
     return _lib
+
+
+class _Traced:
+    """DP_TRACE=1: print every C-ABI call (name + scalar arguments) to stderr and synchronise after it, so a faulting
+    kernel is attributed to the call that launched it.  Diagnostics only."""
+
+    def __init__(self, lib):
+        self._lib = lib
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if not name.startswith("dp_") or name in ("dp_last_error", "dp_launch_count", "dp_abi_version"):
+            return fn
+
+        def call(*a):
+            import sys
+            sys.stderr.write(f"[dp] {name} {[x for x in a if isinstance(x, (int, float)) and abs(x) < (1 << 32)]}\n")
+            sys.stderr.flush()
+            r = fn(*a)
+            if torch.cuda.is_available() and not torch.cuda.is_current_stream_capturing():
+                torch.cuda.synchronize()
+            return r
+        return call
 
 
 def _declare(L):
@@ -65,6 +90,7 @@ class _Sig:
     dp_delta_counts = (c_int, [P, P, P, c_int, c_int, c_int, ctypes.POINTER(c_float), c_int, c_int, c_float, P, P,
                                c_size_t, P])
     dp_metrics_combine = (c_int, [P, P, c_int, c_int, c_int, c_int, P, P])
+    dp_eval_metrics = (c_int, [P, P, c_int, c_int, c_int, ctypes.POINTER(c_float), c_int, c_float, P, P, P, P])
     dp_conv2d_tc_grid = (c_int, [c_int, c_int, c_int, c_int, c_int, c_int])
     dp_conv2d_tc = (c_int, [P, c_ll, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, P, P, c_ll, P, c_ll, c_int, P,
                             c_ll, P, c_ll, c_int, P, P])
@@ -75,6 +101,12 @@ class _Sig:
                                 c_int, c_int, P])
     dp_conv2d_wgrad_tc_workspace = (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int])
     dp_conv2d_wgrad_tc = (c_int, [P, c_ll, P, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_size_t, P])
+    dp_dwconv_fwd_blocks = (c_int, [c_int, c_int, c_int, c_int])
+    dp_dwconv_fwd = (c_int, [P, c_ll, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, P, c_ll, c_int, c_int, P, P])
+    dp_dwconv_dgrad_s2 = (c_int, [P, c_ll, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, P, c_ll, c_int, c_int, P])
+    dp_dwconv_wgrad_workspace = (c_size_t, [c_int, c_int, c_int, c_int, c_int])
+    dp_dwconv_wgrad = (c_int, [P, c_ll, c_int, c_int, c_int, c_int, P, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, P,
+                               c_int, P, c_size_t, P])
     dp_nchw_f32_to_nhwc_bf16 = (c_int, [P, c_int, c_int, c_int, c_int, P, c_ll, P])
     dp_nhwc_bf16_to_nchw_f32 = (c_int, [P, c_ll, c_int, c_int, c_int, c_int, P, P])
     dp_cast_f32_to_bf16 = (c_int, [P, P, c_size_t, P])
@@ -88,12 +120,12 @@ class _Sig:
     dp_resize_bilinear_nhwc_bwd = (c_int, [P, c_ll, c_int, c_int, c_int, c_int, P, c_ll, c_int, c_int, c_int, P])
     dp_resize_bilinear_planes_f32 = (c_int, [P, c_int, c_int, c_int, P, c_int, c_int, c_int, P])
     dp_chan_reduce_blocks = (c_int, [])
-    dp_chan_reduce = (c_int, [c_int, P, c_ll, P, c_ll, P, c_ll, c_size_t, c_int, P, P])
+    dp_chan_reduce = (c_int, [c_int, P, c_ll, P, c_ll, P, c_ll, P, c_size_t, c_int, P, P])
     dp_sum_partials = (c_int, [P, c_int, c_int, c_int, P, c_int, P])
     dp_bn_finalize = (c_int, [P, c_int, c_int, c_double, P, P, c_float, c_float, P, P, P, P, P, P])
     dp_bn_eval_coeffs = (c_int, [P, P, P, P, c_float, c_int, P, P, P])
     dp_bn_apply = (c_int, [P, c_ll, P, P, c_ll, P, P, c_ll, c_size_t, c_int, c_int, P, c_ll, P])
-    dp_bn_bwd_apply = (c_int, [P, c_ll, P, c_ll, P, c_ll, P, P, P, c_double, c_int, c_size_t, c_int, P, c_ll, P, c_ll,
+    dp_bn_bwd_apply = (c_int, [P, c_ll, P, c_ll, P, P, c_ll, P, P, P, c_double, c_int, c_size_t, c_int, P, c_ll, P, c_ll,
                                P, P, c_int, P])
     dp_conv_gather = (c_int, [P, c_ll, c_int, c_int, c_int, c_int, P, P, P, c_ll, c_int, c_int, c_int, c_int, c_int,
                               c_int, c_int, c_int, c_int, P])

@@ -307,6 +307,82 @@ __global__ void __launch_bounds__(256) head_conv_wgrad_kernel(const float* __res
   }
 }
 
+// Faster form for C in {8,16,32,64}: thread = (input pixel, 8-channel group) with the channel group fixed per thread, so the
+// activation vector is loaded once (fully coalesced) and multiplied into all KS*KS taps; the masked upstream gradient of
+// the KS*KS neighbours comes from L1.  Persistent blocks walk whole image rows (no per-pixel index divisions) and keep
+// KS*KS*8 fp32 accumulators per thread; one fixed-order shuffle + shared-memory reduction per block at the end.
+template <int KS>
+__global__ void __launch_bounds__(256) head_conv_wgrad_rows_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                                                                   int relu, const bf16* __restrict__ x, long long x_ld,
+                                                                   int B, int H, int W, int C, float* __restrict__ part) {
+  constexpr int T = KS * KS, pad = KS / 2;
+  __shared__ float s_red[8][8][T * 8 + 1];     // [warp][c8][tap*8 + j | bias]
+  const int C8 = C / 8;                        // power of two <= 8 (host checked)
+  const int c8 = threadIdx.x % C8;
+  const int px0 = threadIdx.x / C8, pxs = 256 / C8;
+  float acc[T][8];
+#pragma unroll
+  for (int t = 0; t < T; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+  float bsum = 0.f;
+  const int rows = B * H;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int y = row % H;
+    const size_t rbase = (size_t)row * W;
+    for (int xx = px0; xx < W; xx += pxs) {
+      float v[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + (rbase + xx) * x_ld + c8 * 8)), v);
+#pragma unroll
+      for (int r = 0; r < KS; ++r) {
+        const int gy = y - r + pad;
+        if (gy < 0 || gy >= H) continue;
+#pragma unroll
+        for (int s2 = 0; s2 < KS; ++s2) {
+          const int gx = xx - s2 + pad;
+          if (gx < 0 || gx >= W) continue;
+          const size_t o = rbase + (size_t)(gy - y) * W + gx;     // same image: rows of one image are contiguous
+          float g = __ldg(dout + o);
+          if (relu && !(__ldg(out + o) > 0.f)) g = 0.f;
+          if (r == pad && s2 == pad && c8 == 0) bsum += g;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[r * KS + s2][j] = fmaf(g, v[j], acc[r * KS + s2][j]);
+        }
+      }
+    }
+  }
+  // lanes with equal (lane % C8) hold the same channel group: fold them with xor shuffles down to lanes 0..C8-1
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int t = 0; t < T; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = acc[t][j];
+      for (int o = 16; o >= C8; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      acc[t][j] = a;
+    }
+  for (int o = 16; o >= 1; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+  if (lane < C8) {
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_red[warp][lane][t * 8 + j] = acc[t][j];
+    if (lane == 0) s_red[warp][0][T * 8] = bsum;
+  }
+  __syncthreads();
+  const int nacc = T * C + 1;
+  for (int i = threadIdx.x; i < nacc; i += 256) {
+    float s = 0.f;
+    if (i == nacc - 1) {
+      for (int w = 0; w < 8; ++w) s += s_red[w][0][T * 8];
+    } else {
+      const int t = i / C, c = i % C;            // output index order: tap-major, channel-minor
+      for (int w = 0; w < 8; ++w) s += s_red[w][c / 8][t * 8 + (c % 8)];
+    }
+    part[(size_t)blockIdx.x * nacc + i] = s;
+  }
+}
+
 __global__ void head_conv_wgrad_reduce_kernel(const float* __restrict__ part, int nblocks, int C, int KS,
                                               float* __restrict__ dw /*[C][KS][KS]*/, float* __restrict__ db,
                                               int accumulate) {
@@ -421,9 +497,20 @@ int dp_head_conv_bwd(const float* dout, const float* out, int relu, const void* 
     const int nacc = KS * KS * C + 1;
     const int ncombo = KS * KS * (C / 8);
     const size_t wg_smem = (size_t)(256 / ncombo) * (ncombo * 8 + 1) * sizeof(float);
-    head_conv_wgrad_kernel<<<kHeadWgBlocks, 256, wg_smem, stream>>>(dout, out, relu, (const bf16*)x, x_ld, B,
-                                                                                 H, W, C, KS, (float*)workspace);
-    DP_CHECK_LAUNCH("head_conv_wgrad_kernel");
+    const int C8 = C / 8;
+    if ((C8 == 1 || C8 == 2 || C8 == 4 || C8 == 8) && (KS == 3 ? C8 <= 4 : true)) {
+      if (KS == 3)
+        head_conv_wgrad_rows_kernel<3><<<kHeadWgBlocks, 256, 0, stream>>>(dout, out, relu, (const bf16*)x, x_ld, B, H, W, C,
+                                                                           (float*)workspace);
+      else
+        head_conv_wgrad_rows_kernel<1><<<kHeadWgBlocks, 256, 0, stream>>>(dout, out, relu, (const bf16*)x, x_ld, B, H, W, C,
+                                                                           (float*)workspace);
+      DP_CHECK_LAUNCH("head_conv_wgrad_rows_kernel");
+    } else {
+      head_conv_wgrad_kernel<<<kHeadWgBlocks, 256, wg_smem, stream>>>(dout, out, relu, (const bf16*)x, x_ld, B,
+                                                                      H, W, C, KS, (float*)workspace);
+      DP_CHECK_LAUNCH("head_conv_wgrad_kernel");
+    }
     head_conv_wgrad_reduce_kernel<<<dp::ceil_div(nacc, 128), 128, 0, stream>>>((const float*)workspace, kHeadWgBlocks, C,
                                                                                KS, dw, db, accumulate);
     DP_CHECK_LAUNCH("head_conv_wgrad_reduce_kernel");

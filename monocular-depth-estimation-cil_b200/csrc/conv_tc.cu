@@ -25,6 +25,7 @@
 //     (dpt_depth.py:63-68) and their data gradients on the tensor cores as well.
 //   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
 //     warps 4..7 = epilogue (TMEM -> registers -> bias / residual / ReLU / BN partial sums -> global).
+#include <cstdlib>
 #include "common.cuh"
 #include "tc.cuh"
 #include "../../include/depth_b200.h"
@@ -683,6 +684,11 @@ int make_plan(Plan& p, int B, int Hg, int Wg, int Cin, int Cout, const ColSpec* 
   const size_t stats_bytes = want_stats ? ((size_t)4 * 2 * Cout * 4 + 15) & ~size_t(15) : 0;
   // TMA-store epilogue: one N block of 16/32/64 columns; two staging tiles per output
   a.epi_tma = (a.n_blocks == 1 && (a.BN == 16 || a.BN == 32 || a.BN == 64) && n_out >= 1) ? 1 : 0;
+  {   // experiment knobs (diagnostics)
+    static const int no_tma = getenv("DP_CONV_NOTMA") != nullptr, niss1 = getenv("DP_CONV_NISS1") != nullptr;
+    if (no_tma) a.epi_tma = 0;
+    if (niss1) a.niss = 1;
+  }
   a.out_tile_bytes = (uint32_t)(128 * a.BN * 2);
   a.nob = n_out >= 2 ? 2 : (a.BN == 64 ? 3 : 4);
   const size_t out_bytes = a.epi_tma ? (size_t)a.nob * n_out * a.out_tile_bytes : 0;
@@ -693,9 +699,13 @@ int make_plan(Plan& p, int B, int Hg, int Wg, int Cin, int Cout, const ColSpec* 
     return dp_set_error(DP_ERR_UNSUPPORTED, "conv_tc: shape needs %zu B of shared memory", fixed + 2 * stage);
   int st = (int)((budget - fixed) / stage);
   a.stages = st > kMaxStages ? kMaxStages : st;
-  // Two issuers work one tile apart in the stage ring.  A parity wait on full[stage] for lap L is only meaningful once
-  // lap L-1 of that stage has completed, which is guaranteed when both tiles fit in the ring: 2 * k-steps <= stages.
-  if (2 * a.ncols * a.kchunks > a.stages) a.niss = 1;
+  // Two issuers alternate tiles.  They are only used when a tile is a single k-step and the ring has an even number
+  // of stages, so that every full/empty barrier is waited on by exactly one issuer for the life of the kernel (issuer
+  // 0 owns the even stages, issuer 1 the odd ones) and the usual one-producer / one-consumer parity reasoning holds.
+  // With several k-steps per tile the two issuers meet on the same barriers in alternating laps; that configuration
+  // faulted intermittently under load (EfficientNet trunk 1x1 layers, Cin 144/192) and is not used.
+  if (a.ncols * a.kchunks != 1) a.niss = 1;
+  if (a.niss == 2 && (a.stages & 1)) a.stages -= 1;
   p.smem = fixed + (size_t)a.stages * stage;
   a.total_items = (long long)B * a.tiles_y * a.tiles_x * a.n_blocks;
   p.grid = (int)(a.total_items < dp::kNumSMs ? a.total_items : dp::kNumSMs);

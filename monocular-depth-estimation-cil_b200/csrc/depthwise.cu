@@ -1,0 +1,357 @@
+// Depthwise convolutions of the EfficientNet-Lite3 encoder trunk (the hub model consumed at
+// reference src/network/blocks.py:166-186): k3 / k5, stride 1 / 2, NHWC bf16, fp32 accumulation.
+// All three passes are bandwidth-bound (9..25 MAC per element), so the design goal is to touch HBM once per tensor:
+//   * forward (and, with flipped taps, the stride-1 data gradient): each thread owns 8 channels (one 16-byte vector) of
+//     a strip of 4 output pixels and slides the K x (3*S+K) input window through registers; the BatchNorm batch
+//     statistics (sum, sum of squares of the stored bf16 value) of the layer that follows are accumulated on the fly
+//     and reduced deterministically per block, so the BN needs no extra pass over the output;
+//   * stride-2 data gradient: gather over the taps whose parity matches;
+//   * weight gradient: thread = 8 channels x one kernel row, K x 8 fp32 accumulators, fixed-order two-level reduction
+//     (no atomics).
+#include "common.cuh"
+#include "../../include/depth_b200.h"
+
+namespace {
+
+using namespace dp;
+
+constexpr int TPB = 256;
+constexpr int TX = 4;  // output pixels per thread along x
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    v[2 * k] = __uint_as_float(w[k] << 16);
+    v[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+    w[k] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ uint4 ld8(const bf16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+struct DwArgs {
+  const bf16* x; long long x_ld;
+  int B, Hi, Wi, C;
+  const float* w;        // [K*K][C] fp32, tap = ky*K + kx
+  int pad_t, pad_l;
+  bf16* out; long long out_ld;
+  int Ho, Wo;
+  float* stats;          // [gridDim.x][2][C] or null
+};
+
+// out[b,oy,ox,c] = sum_{ky,kx} w[ky*K+kx][c] * x[b, oy*S - pad_t + ky, ox*S - pad_l + kx, c]
+template <int K, int S>
+__global__ void __launch_bounds__(TPB) dw_fwd_kernel(DwArgs a) {
+  extern __shared__ float s_red[];   // [TPB][16] when stats
+  const int C8 = a.C / 8;
+  const int strips = (a.Wo + TX - 1) / TX;
+  const long long items = (long long)a.B * a.Ho * strips * C8;
+  const long long nthreads = (long long)gridDim.x * TPB;
+  const long long stride = (nthreads / C8) * C8;          // keeps every thread on one channel group
+  const long long tid = (long long)blockIdx.x * TPB + threadIdx.x;
+  const int c8 = (int)(tid % C8);
+  float st_s[8], st_q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { st_s[j] = 0.f; st_q[j] = 0.f; }
+  if (tid < stride) {
+    for (long long idx = tid; idx < items; idx += stride) {
+      long long r = idx / C8;
+      const int sx = (int)(r % strips); r /= strips;
+      const int oy = (int)(r % a.Ho);
+      const int b = (int)(r / a.Ho);
+      const int ox0 = sx * TX;
+      float acc[TX][8];
+#pragma unroll
+      for (int t = 0; t < TX; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < K; ++ky) {
+        const int iy = oy * S - a.pad_t + ky;
+        if (iy < 0 || iy >= a.Hi) continue;
+        float wrow[K][8];
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.w + (size_t)(ky * K + kx) * a.C + c8 * 8));
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(a.w + (size_t)(ky * K + kx) * a.C + c8 * 8 + 4));
+          wrow[kx][0] = w0.x; wrow[kx][1] = w0.y; wrow[kx][2] = w0.z; wrow[kx][3] = w0.w;
+          wrow[kx][4] = w1.x; wrow[kx][5] = w1.y; wrow[kx][6] = w1.z; wrow[kx][7] = w1.w;
+        }
+        const bf16* rowp = a.x + (((long long)b * a.Hi + iy) * a.Wi) * a.x_ld + c8 * 8;
+#pragma unroll
+        for (int col = 0; col < (TX - 1) * S + K; ++col) {
+          const int ix = ox0 * S - a.pad_l + col;
+          if (ix < 0 || ix >= a.Wi) continue;
+          float v[8];
+          unpack8(ld8(rowp + (long long)ix * a.x_ld), v);
+#pragma unroll
+          for (int t = 0; t < TX; ++t) {
+            const int kx = col - t * S;
+            if (kx >= 0 && kx < K) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(v[j], wrow[kx][j], acc[t][j]);
+            }
+          }
+        }
+      }
+      bf16* op = a.out + (((long long)b * a.Ho + oy) * a.Wo + ox0) * a.out_ld + c8 * 8;
+#pragma unroll
+      for (int t = 0; t < TX; ++t) {
+        if (ox0 + t < a.Wo) {
+          const uint4 q = pack8(acc[t]);
+          *reinterpret_cast<uint4*>(op + (long long)t * a.out_ld) = q;
+          if (a.stats) {
+            float f[8];
+            unpack8(q, f);   // statistics of the value as stored
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { st_s[j] += f[j]; st_q[j] = fmaf(f[j], f[j], st_q[j]); }
+          }
+        }
+      }
+    }
+  }
+  if (a.stats) {
+    // deterministic block reduction: thread t owns channel group (block_base + t) % C8
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s_red[threadIdx.x * 16 + j] = st_s[j]; s_red[threadIdx.x * 16 + 8 + j] = st_q[j]; }
+    __syncthreads();
+    float* dst = a.stats + (size_t)blockIdx.x * 2 * a.C;
+    const int base = (int)(((long long)blockIdx.x * TPB) % C8);
+    for (int g = threadIdx.x; g < C8; g += TPB) {
+      int t0 = g - base;
+      if (t0 < 0) t0 += C8;
+      float s[8], q[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+      for (int t = t0; t < TPB; t += C8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] += s_red[t * 16 + j]; q[j] += s_red[t * 16 + 8 + j]; }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { dst[g * 8 + j] = s[j]; dst[a.C + g * 8 + j] = q[j]; }
+    }
+  }
+}
+
+// stride-2 data gradient: dx[b,iy,ix,c] = sum over taps with (iy + pad_t - ky) even: w[ky*K+kx][c] * dy[b,(iy+pad_t-ky)/2,...]
+template <int K>
+__global__ void __launch_bounds__(TPB) dw_dgrad_s2_kernel(const bf16* __restrict__ dy, long long dy_ld, int B, int Ho, int Wo,
+                                                          int C, const float* __restrict__ w, int pad_t, int pad_l,
+                                                          bf16* __restrict__ dx, long long dx_ld, int Hi, int Wi) {
+  const int C8 = C / 8;
+  const long long items = (long long)B * Hi * Wi * C8;
+  for (long long idx = (long long)blockIdx.x * TPB + threadIdx.x; idx < items; idx += (long long)gridDim.x * TPB) {
+    const int c8 = (int)(idx % C8);
+    long long r = idx / C8;
+    const int ix = (int)(r % Wi); r /= Wi;
+    const int iy = (int)(r % Hi);
+    const int b = (int)(r / Hi);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+      const int ty = iy + pad_t - ky;
+      if (ty < 0 || (ty & 1)) continue;
+      const int oy = ty >> 1;
+      if (oy >= Ho) continue;
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        const int tx = ix + pad_l - kx;
+        if (tx < 0 || (tx & 1)) continue;
+        const int ox = tx >> 1;
+        if (ox >= Wo) continue;
+        float g[8];
+        unpack8(ld8(dy + (((long long)b * Ho + oy) * Wo + ox) * dy_ld + c8 * 8), g);
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + (size_t)(ky * K + kx) * C + c8 * 8));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + (size_t)(ky * K + kx) * C + c8 * 8 + 4));
+        acc[0] = fmaf(g[0], w0.x, acc[0]); acc[1] = fmaf(g[1], w0.y, acc[1]);
+        acc[2] = fmaf(g[2], w0.z, acc[2]); acc[3] = fmaf(g[3], w0.w, acc[3]);
+        acc[4] = fmaf(g[4], w1.x, acc[4]); acc[5] = fmaf(g[5], w1.y, acc[5]);
+        acc[6] = fmaf(g[6], w1.z, acc[6]); acc[7] = fmaf(g[7], w1.w, acc[7]);
+      }
+    }
+    *reinterpret_cast<uint4*>(dx + (((long long)b * Hi + iy) * Wi + ix) * dx_ld + c8 * 8) = pack8(acc);
+  }
+}
+
+// weight gradient partials: partial[chunk][ky*K+kx][c] = sum over the chunk's output pixels of dy * x(tap)
+constexpr int WG_C8B = 16;   // channel groups per block
+template <int K, int S>
+__global__ void __launch_bounds__(TPB) dw_wgrad_kernel(const bf16* __restrict__ x, long long x_ld, int B, int Hi, int Wi, int C,
+                                                       const bf16* __restrict__ dy, long long dy_ld, int Ho, int Wo,
+                                                       int pad_t, int pad_l, int nchunks, float* __restrict__ partial) {
+  extern __shared__ float s_acc[];   // [TPB][K*8]
+  const int C8 = C / 8;
+  const int c8b = C8 < WG_C8B ? C8 : WG_C8B;
+  const int per_slot = c8b * K;
+  const int nslots = TPB / per_slot;
+  const int c8l = threadIdx.x % c8b;
+  const int ky = (threadIdx.x / c8b) % K;
+  const int slot = threadIdx.x / per_slot;
+  const int c8 = blockIdx.x * c8b + c8l;
+  const long long npix = (long long)B * Ho * Wo;
+  const long long per_chunk = (npix + nchunks - 1) / nchunks;
+  const long long p0 = (long long)blockIdx.y * per_chunk;
+  const long long p1 = p0 + per_chunk < npix ? p0 + per_chunk : npix;
+  float acc[K][8];
+#pragma unroll
+  for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[kx][j] = 0.f;
+  if (slot < nslots && c8 < C8) {
+    for (long long p = p0 + slot; p < p1; p += nslots) {
+      const int ox = (int)(p % Wo);
+      long long r = p / Wo;
+      const int oy = (int)(r % Ho);
+      const int b = (int)(r / Ho);
+      const int iy = oy * S - pad_t + ky;
+      if (iy < 0 || iy >= Hi) continue;
+      float g[8];
+      unpack8(ld8(dy + p * dy_ld + c8 * 8), g);
+      const bf16* rowp = x + (((long long)b * Hi + iy) * Wi) * x_ld + c8 * 8;
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        const int ix = ox * S - pad_l + kx;
+        if (ix < 0 || ix >= Wi) continue;
+        float v[8];
+        unpack8(ld8(rowp + (long long)ix * x_ld), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[kx][j] = fmaf(g[j], v[j], acc[kx][j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_acc[threadIdx.x * (K * 8) + kx * 8 + j] = acc[kx][j];
+  __syncthreads();
+  if (slot == 0 && c8 < C8) {
+    for (int kx = 0; kx < K; ++kx) {
+      float s[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] = 0.f;
+      for (int sl = 0; sl < nslots; ++sl) {
+        const int t = sl * per_slot + threadIdx.x;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += s_acc[t * (K * 8) + kx * 8 + j];
+      }
+      float* dst = partial + ((size_t)blockIdx.y * K * K + ky * K + kx) * C + c8 * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dst[j] = s[j];
+    }
+  }
+}
+
+// grad[c][ky][kx] (OIHW with I = 1) (+)= sum_chunks partial[chunk][tap][c]
+__global__ void dw_wgrad_reduce_kernel(const float* __restrict__ partial, int nchunks, int taps, int C,
+                                       float* __restrict__ grad, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= taps * C) return;
+  const int tap = i / C, c = i - tap * C;
+  double s = 0.0;
+  for (int p = 0; p < nchunks; ++p) s += (double)partial[((size_t)p * taps + tap) * C + c];
+  const size_t o = (size_t)c * taps + tap;
+  grad[o] = accumulate ? grad[o] + (float)s : (float)s;
+}
+
+inline int dw_grid(long long items) {
+  long long b = (items + TPB - 1) / TPB;
+  const long long cap = 8LL * kNumSMs;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+inline int wg_chunks(int B, int Ho, int Wo, int C) {
+  const int C8 = C / 8;
+  const int cblocks = (C8 + WG_C8B - 1) / WG_C8B;
+  long long npix = (long long)B * Ho * Wo;
+  long long n = (4LL * kNumSMs + cblocks - 1) / cblocks;
+  if (n > npix / 64) n = npix / 64;
+  if (n < 1) n = 1;
+  return (int)n;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dp_dwconv_fwd_blocks(int B, int Ho, int Wo, int C) {
+  const long long items = (long long)B * Ho * ((Wo + TX - 1) / TX) * (C / 8);
+  return dw_grid(items);
+}
+
+/* Depthwise K x K convolution (K = 3 or 5; stride 1 or 2; explicit top / left padding so both symmetric and TF-"SAME"
+ * geometries are expressible), NHWC bf16.  w: fp32 [K*K][C] (tap-major).  stats_partials: null or
+ * float[dp_dwconv_fwd_blocks()][2][C] receiving per-block (sum, sum of squares) of the stored output for the BatchNorm
+ * that follows.  With flipped taps and pad' = K-1-pad this is also the stride-1 data gradient. */
+int dp_dwconv_fwd(const void* x, long long x_ld, int B, int Hi, int Wi, int C, const float* w, int K, int stride,
+                  int pad_t, int pad_l, void* out, long long out_ld, int Ho, int Wo, float* stats_partials,
+                  cudaStream_t stream) {
+  DP_CHECK_ARG(x && w && out, "dp_dwconv_fwd: null pointer");
+  DP_CHECK_ARG(C % 8 == 0 && C <= 2048 && x_ld % 8 == 0 && out_ld % 8 == 0, "dp_dwconv_fwd: channels must be a multiple of 8 (<= 2048)");
+  DP_CHECK_ARG((K == 3 || K == 5) && (stride == 1 || stride == 2), "dp_dwconv_fwd: K %d stride %d", K, stride);
+  DwArgs a{reinterpret_cast<const bf16*>(x), x_ld, B, Hi, Wi, C, w, pad_t, pad_l, reinterpret_cast<bf16*>(out), out_ld,
+           Ho, Wo, stats_partials};
+  const int grid = dp_dwconv_fwd_blocks(B, Ho, Wo, C);
+  const size_t smem = stats_partials ? (size_t)TPB * 16 * sizeof(float) : 0;
+  if (K == 3 && stride == 1) dw_fwd_kernel<3, 1><<<grid, TPB, smem, stream>>>(a);
+  else if (K == 3) dw_fwd_kernel<3, 2><<<grid, TPB, smem, stream>>>(a);
+  else if (stride == 1) dw_fwd_kernel<5, 1><<<grid, TPB, smem, stream>>>(a);
+  else dw_fwd_kernel<5, 2><<<grid, TPB, smem, stream>>>(a);
+  DP_CHECK_LAUNCH("dw_fwd_kernel");
+  return DP_OK;
+}
+
+/* data gradient of the stride-2 depthwise convolution: dy (B,Ho,Wo,C) -> dx (B,Hi,Wi,C); w as in dp_dwconv_fwd */
+int dp_dwconv_dgrad_s2(const void* dy, long long dy_ld, int B, int Ho, int Wo, int C, const float* w, int K, int pad_t,
+                       int pad_l, void* dx, long long dx_ld, int Hi, int Wi, cudaStream_t stream) {
+  DP_CHECK_ARG(dy && w && dx && C % 8 == 0 && (K == 3 || K == 5), "dp_dwconv_dgrad_s2: bad arguments");
+  const int grid = dw_grid((long long)B * Hi * Wi * (C / 8));
+  if (K == 3)
+    dw_dgrad_s2_kernel<3><<<grid, TPB, 0, stream>>>(reinterpret_cast<const bf16*>(dy), dy_ld, B, Ho, Wo, C, w, pad_t, pad_l,
+                                                    reinterpret_cast<bf16*>(dx), dx_ld, Hi, Wi);
+  else
+    dw_dgrad_s2_kernel<5><<<grid, TPB, 0, stream>>>(reinterpret_cast<const bf16*>(dy), dy_ld, B, Ho, Wo, C, w, pad_t, pad_l,
+                                                    reinterpret_cast<bf16*>(dx), dx_ld, Hi, Wi);
+  DP_CHECK_LAUNCH("dw_dgrad_s2_kernel");
+  return DP_OK;
+}
+
+size_t dp_dwconv_wgrad_workspace(int B, int Ho, int Wo, int C, int K) {
+  return (size_t)wg_chunks(B, Ho, Wo, C) * K * K * C * sizeof(float);
+}
+
+/* weight gradient of the depthwise convolution: grad (fp32, [C][1][K][K]) (+)= sum_p dy[p][c] * x[tap(p)][c] */
+int dp_dwconv_wgrad(const void* x, long long x_ld, int B, int Hi, int Wi, int C, const void* dy, long long dy_ld, int Ho,
+                    int Wo, int K, int stride, int pad_t, int pad_l, float* grad, int accumulate, void* workspace,
+                    size_t workspace_bytes, cudaStream_t stream) {
+  DP_CHECK_ARG(x && dy && grad && workspace && C % 8 == 0, "dp_dwconv_wgrad: bad arguments");
+  DP_CHECK_ARG((K == 3 || K == 5) && (stride == 1 || stride == 2), "dp_dwconv_wgrad: K %d stride %d", K, stride);
+  if (workspace_bytes < dp_dwconv_wgrad_workspace(B, Ho, Wo, C, K))
+    return dp_set_error(DP_ERR_WORKSPACE, "dp_dwconv_wgrad: workspace too small");
+  const int nchunks = wg_chunks(B, Ho, Wo, C);
+  const int C8 = C / 8;
+  dim3 grid((C8 + WG_C8B - 1) / WG_C8B, nchunks);
+  float* partial = reinterpret_cast<float*>(workspace);
+  const size_t smem = (size_t)TPB * K * 8 * sizeof(float);
+  const bf16* xb = reinterpret_cast<const bf16*>(x);
+  const bf16* gb = reinterpret_cast<const bf16*>(dy);
+  if (K == 3 && stride == 1) dw_wgrad_kernel<3, 1><<<grid, TPB, smem, stream>>>(xb, x_ld, B, Hi, Wi, C, gb, dy_ld, Ho, Wo, pad_t, pad_l, nchunks, partial);
+  else if (K == 3) dw_wgrad_kernel<3, 2><<<grid, TPB, smem, stream>>>(xb, x_ld, B, Hi, Wi, C, gb, dy_ld, Ho, Wo, pad_t, pad_l, nchunks, partial);
+  else if (stride == 1) dw_wgrad_kernel<5, 1><<<grid, TPB, smem, stream>>>(xb, x_ld, B, Hi, Wi, C, gb, dy_ld, Ho, Wo, pad_t, pad_l, nchunks, partial);
+  else dw_wgrad_kernel<5, 2><<<grid, TPB, smem, stream>>>(xb, x_ld, B, Hi, Wi, C, gb, dy_ld, Ho, Wo, pad_t, pad_l, nchunks, partial);
+  DP_CHECK_LAUNCH("dw_wgrad_kernel");
+  dw_wgrad_reduce_kernel<<<dp::ceil_div(K * K * C, 128), 128, 0, stream>>>(partial, nchunks, K * K, C, grad, accumulate);
+  DP_CHECK_LAUNCH("dw_wgrad_reduce_kernel");
+  return DP_OK;
+}
+
+}  // extern "C"

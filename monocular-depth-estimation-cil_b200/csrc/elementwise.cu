@@ -211,13 +211,15 @@ __global__ void resize_bwd_kernel(const bf16* __restrict__ gout, long long g_ld,
 // ---- per-channel reductions over pixels --------------------------------------------------------------------
 // MODE 0: sum x                              -> out[0][C]
 // MODE 1: sum x, sum x^2                     -> out[0..1][C]                 (BN statistics from a stored tensor)
-// MODE 2: g = dy * (mask ? mask>0 : 1); sum g, sum g*x   -> out[0..1][C]     (BN backward)
+// MODE 2: g = dy * (mask ? 0<mask<mask_hi : 1); sum g, sum g*x   -> out[0..1][C]     (BN backward; mask_hi = inf for
+//         ReLU, 6 for ReLU6)
 constexpr int RED_TPB = 256;
 template <int MODE>
 __global__ void __launch_bounds__(RED_TPB) chan_reduce_kernel(const bf16* __restrict__ x, long long x_ld,
                                                               const bf16* __restrict__ dy, long long dy_ld,
                                                               const bf16* __restrict__ mask, long long m_ld,
-                                                              size_t npix, int C, float* __restrict__ partial) {
+                                                              size_t npix, int C, float* __restrict__ partial,
+                                                              float mask_hi, const float* __restrict__ mask_ss) {
   extern __shared__ float sred[];  // [2][lanes][C]
   const int C8 = C / 8;
   const int lanes = RED_TPB / C8;  // pixel lanes per block (C8 <= 64 -> lanes >= 4); threads beyond lanes*C8 idle
@@ -231,11 +233,23 @@ __global__ void __launch_bounds__(RED_TPB) chan_reduce_kernel(const bf16* __rest
       if (MODE != 2 || x) unpack8(ld8(x + p * x_ld + c8 * 8), xv);
       if (MODE == 2) {
         unpack8(ld8(dy + p * dy_ld + c8 * 8), g);
-        if (mask) {
+        if (mask_ss) {
+          // activation recomputed from the pre-BN tensor (already being read) instead of loading the activated output;
+          // with mask_ss set, `mask` (optional) is the residual that was added before the activation
+          float radd[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (mask) unpack8(ld8(mask + p * m_ld + c8 * 8), radd);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            // fp32 pre-activation, not its bf16 rounding: values just below 6 that round up to 6.0 keep their gradient,
+            // as in the reference's fp32 hardtanh backward
+            const float m = xv[j] * __ldg(mask_ss + c8 * 8 + j) + __ldg(mask_ss + C + c8 * 8 + j) + radd[j];
+            g[j] = (m > 0.f && m < mask_hi) ? g[j] : 0.f;
+          }
+        } else if (mask) {
           float m[8];
           unpack8(ld8(mask + p * m_ld + c8 * 8), m);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) g[j] = m[j] > 0.f ? g[j] : 0.f;
+          for (int j = 0; j < 8; ++j) g[j] = (m[j] > 0.f && m[j] < mask_hi) ? g[j] : 0.f;
         }
       }
 #pragma unroll
@@ -337,6 +351,10 @@ __global__ void bn_apply_kernel(const bf16* __restrict__ x, long long x_ld, cons
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
     }
+    if (relu == 2) {   // ReLU6
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fminf(o[j], 6.f);
+    }
     st8(y + p * y_ld + c8 * 8, pack8(o));
   }
 }
@@ -350,7 +368,8 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dy, long long dy_ld
                                     const float* __restrict__ red, const float* __restrict__ save,
                                     const float* __restrict__ gamma, double count, int train, size_t npix, int C,
                                     bf16* __restrict__ dx, long long dx_ld, bf16* __restrict__ gmask, long long gm_ld,
-                                    float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
+                                    float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
+                                    float mask_hi, const float* __restrict__ mask_ss) {
   const int C8 = C / 8;
   const size_t total = npix * C8;
   if (blockIdx.x == 0 && dgamma) {
@@ -367,15 +386,23 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dy, long long dy_ld
     const size_t p = i / C8;
     float g[8], xv[8], o[8];
     unpack8(ld8(dy + p * dy_ld + c8 * 8), g);
-    if (mask) {
+    if (dx || mask_ss) unpack8(ld8(x + p * x_ld + c8 * 8), xv);
+    if (mask_ss) {
+      float radd[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (mask) unpack8(ld8(mask + p * m_ld + c8 * 8), radd);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float m = xv[j] * __ldg(mask_ss + c8 * 8 + j) + __ldg(mask_ss + C + c8 * 8 + j) + radd[j];
+        g[j] = (m > 0.f && m < mask_hi) ? g[j] : 0.f;
+      }
+    } else if (mask) {
       float m[8];
       unpack8(ld8(mask + p * m_ld + c8 * 8), m);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = m[j] > 0.f ? g[j] : 0.f;
+      for (int j = 0; j < 8; ++j) g[j] = (m[j] > 0.f && m[j] < mask_hi) ? g[j] : 0.f;
     }
     if (gmask) st8(gmask + p * gm_ld + c8 * 8, pack8(g));
     if (dx) {
-      unpack8(ld8(x + p * x_ld + c8 * 8), xv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int c = c8 * 8 + j;
@@ -476,21 +503,23 @@ int dp_resize_bilinear_planes_f32(const float* src, int planes, int Hi, int Wi, 
 
 int dp_chan_reduce_blocks(void) { return kRedBlocks; }
 
-/* mode 0: sum x; 1: sum x, sum x^2; 2: sum g, sum g*x with g = dy*(mask>0).  partial: float[dp_chan_reduce_blocks()][2][C] */
+/* mode 0: sum x; 1: sum x, sum x^2; 2: sum g, sum g*x with g = dy*(mask>0); 3: as 2 with the ReLU6 mask 0<mask<6.
+ * partial: float[dp_chan_reduce_blocks()][2][C] */
 int dp_chan_reduce(int mode, const void* x, long long x_ld, const void* dy, long long dy_ld, const void* mask,
-                   long long m_ld, size_t npix, int C, float* partial, cudaStream_t stream) {
-  DP_CHECK_ARG(partial && C % 8 == 0 && C <= 512 && mode >= 0 && mode <= 2, "dp_chan_reduce: bad arguments");
-  DP_CHECK_ARG(mode == 2 ? (dy != nullptr && x != nullptr) : (x != nullptr), "dp_chan_reduce: null input");
+                   long long m_ld, const float* mask_ss, size_t npix, int C, float* partial, cudaStream_t stream) {
+  DP_CHECK_ARG(partial && C % 8 == 0 && C <= 2048 && mode >= 0 && mode <= 3, "dp_chan_reduce: bad arguments");
+  DP_CHECK_ARG(mode >= 2 ? (dy != nullptr && x != nullptr) : (x != nullptr), "dp_chan_reduce: null input");
+  const float mask_hi = mode == 3 ? 6.f : INFINITY;
   const int C8 = C / 8;
   const int lanes = RED_TPB / C8;
   const size_t smem = (size_t)2 * lanes * C * sizeof(float);
   if (mode == 0)
-    chan_reduce_kernel<0><<<kRedBlocks, RED_TPB, smem, stream>>>((const bf16*)x, x_ld, nullptr, 0, nullptr, 0, npix, C, partial);
+    chan_reduce_kernel<0><<<kRedBlocks, RED_TPB, smem, stream>>>((const bf16*)x, x_ld, nullptr, 0, nullptr, 0, npix, C, partial, mask_hi, nullptr);
   else if (mode == 1)
-    chan_reduce_kernel<1><<<kRedBlocks, RED_TPB, smem, stream>>>((const bf16*)x, x_ld, nullptr, 0, nullptr, 0, npix, C, partial);
+    chan_reduce_kernel<1><<<kRedBlocks, RED_TPB, smem, stream>>>((const bf16*)x, x_ld, nullptr, 0, nullptr, 0, npix, C, partial, mask_hi, nullptr);
   else
     chan_reduce_kernel<2><<<kRedBlocks, RED_TPB, smem, stream>>>((const bf16*)x, x_ld, (const bf16*)dy, dy_ld,
-                                                                 (const bf16*)mask, m_ld, npix, C, partial);
+                                                                 (const bf16*)mask, m_ld, npix, C, partial, mask_hi, mask_ss);
   DP_CHECK_LAUNCH("chan_reduce_kernel");
   return DP_OK;
 }
@@ -533,16 +562,17 @@ int dp_bn_apply(const void* x, long long x_ld, const float* scale_shift, const v
   return DP_OK;
 }
 
-int dp_bn_bwd_apply(const void* dy, long long dy_ld, const void* mask, long long m_ld, const void* x, long long x_ld,
-                    const float* red, const float* save_mean_invstd, const float* gamma, double count, int train,
+int dp_bn_bwd_apply(const void* dy, long long dy_ld, const void* mask, long long m_ld, const float* mask_ss,
+                    const void* x, long long x_ld, const float* red, const float* save_mean_invstd, const float* gamma, double count, int train,
                     size_t npix, int C, void* dx, long long dx_ld, void* gmask, long long gm_ld, float* dgamma,
                     float* dbeta, int accumulate, cudaStream_t stream) {
-  DP_CHECK_ARG(dy && C % 8 == 0 && (dx || gmask), "dp_bn_bwd_apply: bad arguments");
+  DP_CHECK_ARG(dy && C % 8 == 0 && (dx || gmask) && (!mask_ss || x), "dp_bn_bwd_apply: bad arguments");
   DP_CHECK_ARG(!dx || (x && save_mean_invstd && (!train || red)), "dp_bn_bwd_apply: missing statistics");
   DP_CHECK_ARG(!dgamma || (dbeta && red && save_mean_invstd), "dp_bn_bwd_apply: dgamma needs dbeta, red and save");
+  // train: bit 0 = batch statistics (train mode); bit 1 = the mask is a ReLU6 output (gradient passes for 0 < mask < 6)
   bn_bwd_apply_kernel<<<grid_for(npix * (C / 8)), 256, 0, stream>>>(
-      (const bf16*)dy, dy_ld, (const bf16*)mask, m_ld, (const bf16*)x, x_ld, red, save_mean_invstd, gamma, count, train,
-      npix, C, (bf16*)dx, dx_ld, (bf16*)gmask, gm_ld, dgamma, dbeta, accumulate);
+      (const bf16*)dy, dy_ld, (const bf16*)mask, m_ld, (const bf16*)x, x_ld, red, save_mean_invstd, gamma, count, train & 1,
+      npix, C, (bf16*)dx, dx_ld, (bf16*)gmask, gm_ld, dgamma, dbeta, accumulate, (train & 2) ? 6.f : INFINITY, mask_ss);
   DP_CHECK_LAUNCH("bn_bwd_apply_kernel");
   return DP_OK;
 }

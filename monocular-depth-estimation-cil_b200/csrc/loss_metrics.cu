@@ -442,6 +442,148 @@ __global__ void metrics_combine_kernel(const double* __restrict__ mom, const uns
   }
 }
 
+
+// ---- fused evaluation metrics: SI-RMSE + AbsRel + aligned delta counts in ONE launch -----------------------------
+// evaluation.py:157-166 calls scale_invariant_loss(sqroot=True), absolute_relative_error and three delta_thres.
+// delta needs the per-sample scale exp(mean(log t - log p)) before any pixel can be classified, i.e. two sweeps over
+// each sample.  A thread-block cluster of kEvalCluster CTAs owns one sample: sweep 1 accumulates the moments (fp32
+// over 4 pixels, fp64 beyond), the CTAs exchange their partials through distributed shared memory, and sweep 2
+// re-reads the CTA's own slice (2 MB per sample: an L2 hit) to count.  HBM traffic: 8 B/px, once.
+constexpr int kEvalCluster = 8;
+
+struct EvalArgs {
+  const float* pred;
+  const float* target;
+  int B, nthr;
+  long long n;         // pixels per sample
+  float eps;
+  float thr[DP_MAX_THR];
+  double* moments;                 // [B][NMOM]: S1, S2, AR filled
+  unsigned long long* counts;      // [B][nthr]
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double ld_dsmem_f64(const double* local_ptr, uint32_t rank) {
+  uint32_t sa = (uint32_t)__cvta_generic_to_shared(local_ptr), ra;
+  double v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(sa), "r"(rank));
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_dsmem_u64(const unsigned long long* local_ptr, uint32_t rank) {
+  uint32_t sa = (uint32_t)__cvta_generic_to_shared(local_ptr), ra;
+  unsigned long long v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(sa), "r"(rank));
+  asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(ra) : "memory");
+  return v;
+}
+
+template <int VEC>
+__global__ void __cluster_dims__(kEvalCluster, 1, 1) __launch_bounds__(TPB) eval_fused_kernel(EvalArgs a) {
+  const int b = blockIdx.x / kEvalCluster;
+  const uint32_t rank = cluster_ctarank();
+  const long long n = a.n;
+  const float* __restrict__ P = a.pred + (size_t)b * n;
+  const float* __restrict__ T = a.target + (size_t)b * n;
+  const long long nv = n / VEC;
+  const long long per = (nv + kEvalCluster - 1) / kEvalCluster;
+  const long long i0 = (long long)rank * per, i1 = min(nv, i0 + per);
+  const float eps = a.eps;
+
+  __shared__ double s_mom[3];                       // this CTA's S1, S2, AR
+  __shared__ unsigned long long s_cnt[DP_MAX_THR];  // this CTA's counts
+  __shared__ double red[3 * 32];
+
+  // ---- sweep 1: moments ----
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (long long i = i0 + threadIdx.x; i < i1; i += TPB) {
+    float pv[VEC], tv[VEC];
+    if (VEC == 4) {
+      const float4 p4 = ldg4(P + i * 4), t4 = ldg4(T + i * 4);
+      pv[0] = p4.x; pv[1] = p4.y; pv[2] = p4.z; pv[3] = p4.w;
+      tv[0] = t4.x; tv[1] = t4.y; tv[2] = t4.z; tv[3] = t4.w;
+    } else {
+      pv[0] = __ldg(P + i);
+      tv[0] = __ldg(T + i);
+    }
+    float s1 = 0.f, s2 = 0.f, ar = 0.f;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float d = logf(pv[j] + eps) - logf(tv[j] + eps);   // util.py:143
+      s1 += d;
+      s2 += d * d;
+      ar += fabsf(tv[j] - pv[j]) / (tv[j] + 1e-6f);            // util.py:218
+    }
+    acc[0] += s1; acc[1] += s2; acc[2] += ar;
+  }
+  block_sum<3>(acc, red);
+  if (threadIdx.x == 0) { s_mom[0] = acc[0]; s_mom[1] = acc[1]; s_mom[2] = acc[2]; }
+  cluster_sync_all();
+  double S1 = 0.0;
+  for (uint32_t r = 0; r < kEvalCluster; ++r) S1 += ld_dsmem_f64(&s_mom[0], r);   // fixed order: same value in every CTA
+  const float s = expf((float)(-S1 / (double)n));                                  // util.py:200
+
+  // ---- sweep 2: aligned delta counts over the same slice (L2-resident) ----
+  unsigned cnt[DP_MAX_THR];
+#pragma unroll
+  for (int k = 0; k < DP_MAX_THR; ++k) cnt[k] = 0;
+  for (long long i = i0 + threadIdx.x; i < i1; i += TPB) {
+    float pv[VEC], tv[VEC];
+    if (VEC == 4) {
+      const float4 p4 = ldg4(P + i * 4), t4 = ldg4(T + i * 4);
+      pv[0] = p4.x; pv[1] = p4.y; pv[2] = p4.z; pv[3] = p4.w;
+      tv[0] = t4.x; tv[1] = t4.y; tv[2] = t4.z; tv[3] = t4.w;
+    } else {
+      pv[0] = __ldg(P + i);
+      tv[0] = __ldg(T + i);
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float al = pv[j] * s;
+      const float r1 = al / tv[j];          // util.py:204: no epsilon in the divisions
+      const float r2 = tv[j] / al;
+#pragma unroll
+      for (int k = 0; k < DP_MAX_THR; ++k)
+        if (k < a.nthr && r1 < a.thr[k] && r2 < a.thr[k]) cnt[k]++;   // NaN / inf compare false, as torch.max + lt
+    }
+  }
+  __shared__ unsigned sc[DP_MAX_THR][TPB / 32];
+#pragma unroll
+  for (int k = 0; k < DP_MAX_THR; ++k) {
+    unsigned v = cnt[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sc[k][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < DP_MAX_THR) {
+    unsigned long long tot = 0;
+    for (int w = 0; w < TPB / 32; ++w) tot += sc[threadIdx.x][w];
+    s_cnt[threadIdx.x] = tot;
+  }
+  cluster_sync_all();
+  if (rank == 0) {
+    if (threadIdx.x < 3) {
+      double v = 0.0;
+      for (uint32_t r = 0; r < kEvalCluster; ++r) v += ld_dsmem_f64(&s_mom[threadIdx.x], r);
+      const int slot = threadIdx.x == 0 ? DP_M_S1 : (threadIdx.x == 1 ? DP_M_S2 : DP_M_AR);
+      a.moments[(size_t)b * NMOM + slot] = v;
+    } else if (threadIdx.x >= 32 && threadIdx.x < 32 + a.nthr) {
+      const int k = threadIdx.x - 32;
+      unsigned long long v = 0;
+      for (uint32_t r = 0; r < kEvalCluster; ++r) v += ld_dsmem_u64(&s_cnt[k], r);
+      a.counts[(size_t)b * a.nthr + k] = v;
+    }
+  }
+  cluster_sync_all();   // keep every CTA's shared memory alive until rank 0 has read it
+}
+
 inline int pick_chunks(int B, int H) {
   int c = (4 * kNumSMs + B - 1) / B;
   if (c < 1) c = 1;
@@ -566,6 +708,27 @@ int dp_delta_counts(const float* pred, const float* target, const double* moment
 int dp_metrics_combine(const double* moments, const unsigned long long* counts, int B, int H, int W, int nthr,
                        float* out, cudaStream_t stream) {
   DP_CHECK_ARG(moments && counts && out, "dp_metrics_combine: null pointer");
+  metrics_combine_kernel<<<1, 32, 0, stream>>>(moments, counts, B, H, W, nthr, out);
+  DP_CHECK_LAUNCH("metrics_combine_kernel");
+  return DP_OK;
+}
+
+
+/* evaluation.py:157-166 in two launches: the fused cluster kernel (moments + aligned delta counts, 8 B/px of HBM
+ * traffic) and the scalar combine.  out[0]=SI-RMSE, out[1]=AbsRel, out[2+k]=delta_k (batch means). */
+int dp_eval_metrics(const float* pred, const float* target, int B, int H, int W, const float* thresholds, int nthr,
+                    float eps, double* moments, unsigned long long* counts, float* out, cudaStream_t stream) {
+  DP_CHECK_ARG(pred && target && thresholds && moments && counts && out, "dp_eval_metrics: null pointer");
+  DP_CHECK_ARG(B > 0 && H > 0 && W > 0, "dp_eval_metrics: bad shape %d %d %d", B, H, W);
+  DP_CHECK_ARG(nthr >= 1 && nthr <= DP_MAX_THR, "dp_eval_metrics: nthr %d out of [1,%d]", nthr, DP_MAX_THR);
+  EvalArgs a;
+  a.pred = pred; a.target = target; a.B = B; a.nthr = nthr; a.n = (long long)H * W; a.eps = eps;
+  for (int k = 0; k < DP_MAX_THR; ++k) a.thr[k] = k < nthr ? thresholds[k] : 0.f;
+  a.moments = moments; a.counts = counts;
+  const bool vec = (a.n % 4 == 0) && aligned16(pred) && aligned16(target);
+  if (vec) eval_fused_kernel<4><<<B * kEvalCluster, TPB, 0, stream>>>(a);
+  else eval_fused_kernel<1><<<B * kEvalCluster, TPB, 0, stream>>>(a);
+  DP_CHECK_LAUNCH("eval_fused_kernel");
   metrics_combine_kernel<<<1, 32, 0, stream>>>(moments, counts, B, H, W, nthr, out);
   DP_CHECK_LAUNCH("metrics_combine_kernel");
   return DP_OK;

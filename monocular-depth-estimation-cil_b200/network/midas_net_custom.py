@@ -9,6 +9,7 @@ import torch.nn as nn
 
 from .. import ops
 from .base_model import BaseModel
+from . import encoder_fused
 from .blocks import FeatureFusionBlock_custom, Interpolate, _make_encoder, enter, from_nchw
 
 
@@ -49,11 +50,18 @@ class MidasNet_small(BaseModel):
         )
         # run the third-party encoder under bf16 autocast + channels_last (bench); parity tests keep fp32
         self.encoder_autocast = False
+        # run the EfficientNet-Lite3 trunk on the sm_100a kernels (network/encoder_fused.py) when its structure is
+        # recognised; False keeps it on PyTorch (the parity tests compare both)
+        self.fused_encoder = False
         if path:
             self.load(path)
 
     # -- pieces shared with MidasNetSemantics ----------------------------------------------------------
     def encoder_features(self, x):
+        self._feats_nhwc = False
+        if self.fused_encoder and x.is_cuda and encoder_fused.supported(self.pretrained):
+            self._feats_nhwc = True
+            return tuple(encoder_fused.forward(self.pretrained, x))      # NHWC bf16 (internal layout)
         if self.encoder_autocast:
             with torch.autocast("cuda", dtype=torch.bfloat16):
                 xc = x.contiguous(memory_format=torch.channels_last)
@@ -74,7 +82,8 @@ class MidasNet_small(BaseModel):
         rn = []
         for i, f in enumerate(feats):
             conv = getattr(s, f"layer{i + 1}_rn")
-            rn.append(ops.conv_tc(from_nchw(f), conv.weight, None, dual=True))      # (raw, relu) pairs
+            t = f if getattr(self, "_feats_nhwc", False) else from_nchw(f)   # the fused trunk hands over NHWC bf16
+            rn.append(ops.conv_tc(t, conv.weight, None, dual=True))      # (raw, relu) pairs
         p4 = s.refinenet4.fused(rn[3], None)
         p3 = s.refinenet3.fused(p4, rn[2])
         p2 = s.refinenet2.fused(p3, rn[1])

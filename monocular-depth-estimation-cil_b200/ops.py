@@ -85,7 +85,7 @@ def _colsum(g):
     npix = g.numel() // C
     nb = L.lib().dp_chan_reduce_blocks()
     part = torch.empty(nb, 2, C, dtype=torch.float32, device=g.device)
-    L.check(L.lib().dp_chan_reduce(0, L.ptr(g), C, None, 0, None, 0, npix, C, L.ptr(part), L.stream()))
+    L.check(L.lib().dp_chan_reduce(0, L.ptr(g), C, None, 0, None, 0, None, npix, C, L.ptr(part), L.stream()))
     out = torch.empty(C, dtype=torch.float32, device=g.device)
     L.check(L.lib().dp_sum_partials(L.ptr(part), nb, 1, C, L.ptr(out), 0, L.stream()))
     return out
@@ -396,7 +396,123 @@ def conv_strided(x, weight, bias, stride, pad):
 
 
 def conv_transposed(x, weight, bias, stride, pad):
+    I, O, KH, KW = weight.shape
+    if KH == KW == stride and pad == 0 and I % 8 == 0 and O % 8 == 0:
+        # non-overlapping taps (Dinov2Head.resize_layers[0..1], dpt_depth.py:49-62): every output pixel (k*y+a, k*x+b)
+        # sees exactly one tap, so the layer is a 1x1 convolution to k*k*O channels on tcgen05 followed by a pixel
+        # shuffle; autograd derives the data / weight gradients as the 1x1 kernels' and routes them back through
+        # the weight re-view.
+        k = KH
+        B, H, W, _ = x.shape
+        w1 = weight.permute(2, 3, 1, 0).reshape(k * k * O, I, 1, 1)
+        b1 = bias.repeat(k * k) if bias is not None else None
+        t = conv_tc(x, w1, b1)                                             # (B, H, W, k*k*O)
+        return t.view(B, H, W, k, k, O).permute(0, 1, 3, 2, 4, 5).reshape(B, H * k, W * k, O)
     return _ConvTransposed.apply(x, weight, bias, stride, pad)
+
+
+# --------------------------------------------------------------------------------------------------
+# depthwise convolution and the 3-channel stem of the EfficientNet-Lite3 trunk
+# --------------------------------------------------------------------------------------------------
+def _dw_pack(weight, flip=False):
+    """[C][1][K][K] fp32 -> tap-major fp32 [K*K][C] (optionally spatially flipped: the stride-1 data gradient)."""
+    C, _, K, _ = weight.shape
+    w = weight.detach().float()
+    if flip:
+        w = w.flip(2, 3)
+    return w.reshape(C, K * K).t().contiguous()
+
+
+def _dw_launch(x, wp, K, stride, pad_t, pad_l, Ho, Wo, want_stats):
+    B, Hi, Wi, C = x.shape
+    lib = L.lib()
+    out = _nhwc(B, Ho, Wo, C, x.device)
+    st = None
+    if want_stats:
+        st = torch.empty(lib.dp_dwconv_fwd_blocks(B, Ho, Wo, C), 2, C, dtype=torch.float32, device=x.device)
+    L.check(lib.dp_dwconv_fwd(L.ptr(x), _ld(x), B, Hi, Wi, C, L.ptr(wp), K, stride, pad_t, pad_l, L.ptr(out), C, Ho, Wo,
+                              L.ptr(st), L.stream()))
+    return out, st
+
+
+class _DwConv(torch.autograd.Function):
+    """nn.Conv2d(C, C, K, stride, groups=C, bias=False) on NHWC bf16; optional BN partial statistics of the output."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride, pad_t, pad_l, Ho, Wo, want_stats):
+        K = weight.shape[2]
+        out, st = _dw_launch(x, _dw_pack(weight), K, stride, pad_t, pad_l, Ho, Wo, want_stats)
+        ctx.save_for_backward(x, weight)
+        ctx.geom = (stride, pad_t, pad_l, Ho, Wo)
+        if st is not None:
+            ctx.mark_non_differentiable(st)
+        return out, st
+
+    @staticmethod
+    def backward(ctx, g, _gs):
+        x, weight = ctx.saved_tensors
+        stride, pad_t, pad_l, Ho, Wo = ctx.geom
+        B, Hi, Wi, C = x.shape
+        K = weight.shape[2]
+        lib = L.lib()
+        g = _dense(g)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            if stride == 1:
+                dx, _ = _dw_launch(g, _dw_pack(weight, flip=True), K, 1, K - 1 - pad_t, K - 1 - pad_l, Hi, Wi, False)
+            else:
+                dx = _nhwc(B, Hi, Wi, C, x.device)
+                L.check(lib.dp_dwconv_dgrad_s2(L.ptr(g), C, B, Ho, Wo, C, L.ptr(_dw_pack(weight)), K, pad_t, pad_l,
+                                               L.ptr(dx), C, Hi, Wi, L.stream()))
+        if ctx.needs_input_grad[1]:
+            nb = lib.dp_dwconv_wgrad_workspace(B, Ho, Wo, C, K)
+            ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
+            dw = torch.empty(C, 1, K, K, dtype=torch.float32, device=x.device)
+            L.check(lib.dp_dwconv_wgrad(L.ptr(x), _ld(x), B, Hi, Wi, C, L.ptr(g), C, Ho, Wo, K, stride, pad_t, pad_l,
+                                        L.ptr(dw), 0, L.ptr(ws), nb, L.stream()))
+            dw = dw.to(weight.dtype)
+        return dx, dw, None, None, None, None, None, None
+
+
+def dwconv(x, weight, stride, pad_t, pad_l, Ho, Wo, stats=False):
+    """depthwise conv; returns out or (out, BN partials)"""
+    out, st = _DwConv.apply(x, weight, stride, pad_t, pad_l, Ho, Wo, stats)
+    return (out, st) if stats else out
+
+
+class _StemConv(torch.autograd.Function):
+    """3x3 / stride 2 / pad 1 convolution of the fp32 NCHW image (3 channels, zero padded to 8 for the tensor cores)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, want_stats):
+        B, Ci, H, W = x.shape
+        O, _, K, _ = weight.shape
+        assert K == 3 and Ci <= 8
+        xs = x.detach()
+        if xs.dtype != torch.float32 or not xs.is_contiguous():
+            xs = xs.float().contiguous()
+        x8 = torch.zeros(B, H, W, 8, dtype=BF16, device=x.device)
+        L.check(L.lib().dp_nchw_f32_to_nhwc_bf16(L.ptr(xs), B, Ci, H, W, L.ptr(x8), 8, L.stream()))
+        wp = torch.zeros(K * K, O, 8, dtype=BF16, device=x.device)
+        wp[:, :, :Ci] = weight.detach().permute(2, 3, 0, 1).reshape(K * K, O, Ci).to(BF16)
+        Ho, Wo = (H + 2 - K) // 2 + 1, (W + 2 - K) // 2 + 1
+        out, st = _tc_down2(x8, wp, None, Ho, Wo, O, K, 1, stats=want_stats)
+        ctx.save_for_backward(x8, weight)
+        if st is not None:
+            ctx.mark_non_differentiable(st)
+        return out, st
+
+    @staticmethod
+    def backward(ctx, g, _gs):
+        x8, weight = ctx.saved_tensors
+        Ci = weight.shape[1]
+        dw = _wgrad_tc_s2(_dense(g), x8, 3, 1)[:, :Ci].contiguous().to(weight.dtype)
+        return None, dw, None
+
+
+def stem_conv(x, weight, stats=False):
+    out, st = _StemConv.apply(x, weight, stats)
+    return (out, st) if stats else out
 
 
 # --------------------------------------------------------------------------------------------------
@@ -497,7 +613,7 @@ def _bn_coeffs(bn, c, stats, training):
             nb = lib.dp_chan_reduce_blocks()
             stats = torch.empty(nb, 2, C, dtype=torch.float32, device=dev)
             cd = c if c.is_contiguous() else c.contiguous()
-            L.check(lib.dp_chan_reduce(1, L.ptr(cd), C, None, 0, None, 0, npix, C, L.ptr(stats), L.stream()))
+            L.check(lib.dp_chan_reduce(1, L.ptr(cd), C, None, 0, None, 0, None, npix, C, L.ptr(stats), L.stream()))
         count = float(c.numel() // C)
         track = training and bn.track_running_stats and bn.running_mean is not None
         mom = bn.momentum if bn.momentum is not None else 0.1
@@ -518,16 +634,21 @@ class _BNAct(torch.autograd.Function):
         B, H, W, C = c.shape
         npix = B * H * W
         y = _nhwc(B, H, W, C, c.device)
+        relu = int(relu)                      # 0 none, 1 ReLU, 2 ReLU6
         L.check(L.lib().dp_bn_apply(L.ptr(c), _ld(c), L.ptr(ss), L.ptr(c2), _ld(c2) if c2 is not None else 0,
-                                    L.ptr(ss2), L.ptr(res), _ld(res) if res is not None else 0, npix, C, int(relu),
+                                    L.ptr(ss2), L.ptr(res), _ld(res) if res is not None else 0, npix, C, relu,
                                     L.ptr(y), C, L.stream()))
-        ctx.save_for_backward(c, gamma, save, c2, gamma2, save2, y if relu else None)
+        # BN (+ residual) + activation: the backward recomputes the activation mask in fp32 from c, the scale/shift and
+        # the residual; only with a second normalised branch is the stored output used as the mask
+        recompute = bool(relu) and c2 is None
+        ctx.save_for_backward(c, gamma, save, c2, gamma2, save2,
+                              (res if recompute else y) if relu else None, ss if recompute else None)
         ctx.cfg = (relu, train, res is not None)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        c, gamma, save, c2, gamma2, save2, y = ctx.saved_tensors
+        c, gamma, save, c2, gamma2, save2, y, mss = ctx.saved_tensors
         relu, train, has_res = ctx.cfg
         B, H, W, C = c.shape
         npix = B * H * W
@@ -538,15 +659,17 @@ class _BNAct(torch.autograd.Function):
 
         def branch(cx, gm, sv, want_gmask):
             part = torch.empty(nb, 2, C, dtype=torch.float32, device=dev)
-            L.check(lib.dp_chan_reduce(2, L.ptr(cx), _ld(cx), L.ptr(gy), C, L.ptr(y), C, npix, C, L.ptr(part), L.stream()))
+            L.check(lib.dp_chan_reduce(3 if relu == 2 else 2, L.ptr(cx), _ld(cx), L.ptr(gy), C, L.ptr(y), C, L.ptr(mss),
+                                       npix, C, L.ptr(part), L.stream()))
             red = torch.empty(2, C, dtype=torch.float32, device=dev)
             L.check(lib.dp_sum_partials(L.ptr(part), nb, 2, C, L.ptr(red), 0, L.stream()))
             dx = _nhwc(B, H, W, C, dev)
             gmask = _nhwc(B, H, W, C, dev) if want_gmask else None
             dg = torch.empty(C, dtype=torch.float32, device=dev)
             dbt = torch.empty(C, dtype=torch.float32, device=dev)
-            L.check(lib.dp_bn_bwd_apply(L.ptr(gy), C, L.ptr(y), C, L.ptr(cx), _ld(cx), L.ptr(red), L.ptr(sv),
-                                        L.ptr(_f32(gm)), float(npix), int(train), npix, C, L.ptr(dx), C, L.ptr(gmask), C,
+            L.check(lib.dp_bn_bwd_apply(L.ptr(gy), C, L.ptr(y), C, L.ptr(mss), L.ptr(cx), _ld(cx), L.ptr(red), L.ptr(sv),
+                                        L.ptr(_f32(gm)), float(npix), int(train) | (2 if relu == 2 else 0), npix, C,
+                                        L.ptr(dx), C, L.ptr(gmask), C,
                                         L.ptr(dg), L.ptr(dbt), 0, L.stream()))
             return dx, dg, dbt, gmask
 
@@ -560,7 +683,8 @@ class _BNAct(torch.autograd.Function):
 
 
 def bn_act(bn, c, stats=None, relu=True, res=None, bn2=None, c2=None, stats2=None):
-    """train/eval nn.BatchNorm2d on NHWC bf16 `c` (+ residual, or + a second normalised branch), optional ReLU."""
+    """train/eval nn.BatchNorm2d on NHWC bf16 `c` (+ residual, or + a second normalised branch), optional ReLU
+    (relu=True / 1) or ReLU6 (relu=2)."""
     training = bn.training
     ss, save, used_batch = _bn_coeffs(bn, c, stats, training)
     ss2 = save2 = g2 = b2 = None

@@ -204,16 +204,21 @@ def delta_counts(pred, target, thresholds, aligned=True):
 
 
 def evaluation_metrics(pred, target, thresholds=(1.05, 1.05 ** 2, 1.05 ** 3)):
-    """The metric set of evaluation.py:157-166 for one batch in two fused passes:
+    """The metric set of evaluation.py:157-166 for one batch in one fused cluster kernel (each input read from HBM once):
     returns a device tensor [SI-RMSE, AbsRel, delta_1 .. delta_k] (batch means, as the reference's functions)."""
     assert pred.shape == target.shape, \
         "Pred and target must have the same shape, got {} and {}".format(pred.shape, target.shape)
     _check_cuda(pred, target)
-    ps = _Pass(pred, target, None, L.F_SI | L.F_ABSREL, 1e-6)
-    cnt = ps.counts(list(thresholds), aligned=True)
-    out = torch.empty(2 + len(thresholds), dtype=torch.float32, device=pred.device)
-    L.check(L.lib().dp_metrics_combine(L.ptr(ps.mom), L.ptr(cnt), ps.B, ps.H, ps.W, len(thresholds), L.ptr(out),
-                                       L.stream()))
+    p, t = _prep(pred), _prep(target)
+    B, H, W = _bhw(p)
+    n = len(thresholds)
+    dev = p.device
+    mom = torch.empty(B, L.NMOM, dtype=torch.float64, device=dev)
+    cnt = torch.empty(B, n, dtype=torch.int64, device=dev)
+    out = torch.empty(2 + n, dtype=torch.float32, device=dev)
+    arr = (ctypes.c_float * n)(*[float(x) for x in thresholds])
+    L.check(L.lib().dp_eval_metrics(L.ptr(p), L.ptr(t), B, H, W, arr, n, 1e-6, L.ptr(mom), L.ptr(cnt), L.ptr(out),
+                                    L.stream()))
     return out
 
 

@@ -57,6 +57,9 @@ CASES = [
     (1, 33, 47, 64, 64, 1),
     (1, 24, 40, 64, 32, 1),
     (1, 16, 20, 384, 128, 1),
+    # EfficientNet-Lite3 trunk 1x1 shapes: many N blocks, Cout / Cin that are not multiples of 16 / 64
+    (1, 14, 18, 384, 1392, 1), (1, 14, 18, 1392, 232, 1), (2, 14, 18, 232, 1392, 1), (1, 28, 36, 816, 136, 1),
+    (1, 56, 72, 24, 144, 1), (1, 56, 72, 144, 24, 1), (1, 28, 36, 96, 576, 1), (1, 14, 18, 1392, 384, 1),
 ]
 
 

@@ -134,3 +134,21 @@ def test_shape_assert(pkg):
         pkg.scale_invariant_loss(a, b)
     with pytest.raises(AssertionError):
         pkg.delta_thres(a, b)
+
+
+@pytest.mark.parametrize("B,H,W", [(3, 37, 53), (2, 64, 96), (9, 448, 576)])
+def test_fused_eval_counts_match_two_pass_counts(pkg, B, H, W):
+    """the cluster kernel (one launch, DSMEM exchange of the per-sample scale) must classify exactly the pixels the
+    separate moments + delta_counts passes classify: integer equality of the per-batch counts."""
+    g = torch.Generator().manual_seed(B * H + W)
+    t = (torch.rand(B, 1, H, W, generator=g) * 9.9 + 0.1).cuda()
+    p = (t.cpu() * torch.exp(0.1 * torch.randn(B, 1, H, W, generator=g)) * 1.3).cuda()
+    p[:, :, 3:9, 5:17] = 0.0
+    thr = [1.05, 1.05 ** 2, 1.05 ** 3]
+    out = pkg.evaluation_metrics(p, t, thresholds=thr).double().cpu()
+    cnt = pkg.delta_counts(p, t, thr, aligned=True).cpu()
+    n = H * W
+    want = (cnt.double() / n).float().double().mean(0)
+    assert torch.allclose(out[2:], want, rtol=0, atol=1e-7), (out[2:], want)
+    assert abs(out[0].item() - pkg.scale_invariant_loss(p, t, sqroot=True).item()) <= 1e-6
+    assert abs(out[1].item() - pkg.absolute_relative_error(p, t).item()) <= 1e-6 * out[1].item()

@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, depth_b200
 from depth_b200 import util, _lib as L
-EB, H, W = int(os.environ.get("EB", "128")), 448, 576
+EB, H, W = int(os.environ.get("EB", "650")), 448, 576
 dev = torch.device("cuda", 0)
 g = torch.Generator(device=dev).manual_seed(7)
 tt = torch.rand(EB, 1, H, W, device=dev, generator=g) * 9.9 + 0.1
