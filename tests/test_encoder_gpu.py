@@ -165,9 +165,20 @@ def test_trunk_blocks_match_pytorch(pkg):
         yf.backward(cot.permute(0, 2, 3, 1).contiguous().to(BF))
         rel = float((xf.grad.float().permute(0, 3, 1, 2) - xr.grad).norm() / xr.grad.norm())
         assert rel < 0.08, (i, "dx", rel)
-        for (n, pf), (_, pr) in zip(f.named_parameters(), r.named_parameters()):
+        # parameter gradients: self-calibrated against stock bf16 autocast of the same block on the same input - the
+        # fused path may not be further from the fp32 gradients than twice the autocast run's own distance (+ 0.01)
+        import copy
+        ra = copy.deepcopy(r)
+        for p_ in ra.parameters():
+            p_.grad = None
+        xa = x.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=BF):
+            ya = ra(xa)
+        ya.backward(cot.to(ya.dtype))
+        for (n, pf), (_, pr), (_, pa) in zip(f.named_parameters(), r.named_parameters(), ra.named_parameters()):
             cos = float(F.cosine_similarity(pf.grad.flatten().double(), pr.grad.flatten().double(), dim=0))
-            assert cos > 0.98, (i, n, cos)
+            cos_a = float(F.cosine_similarity(pa.grad.flatten().double(), pr.grad.flatten().double(), dim=0))
+            assert 1.0 - cos <= 2.0 * (1.0 - cos_a) + 0.01, (i, n, cos, cos_a)
         for (n, bf_), (_, br) in zip(f.named_buffers(), r.named_buffers()):
             if n.endswith("running_var") or n.endswith("running_mean"):
                 assert torch.allclose(bf_, br, rtol=1e-2, atol=1e-2), (i, n)
@@ -177,17 +188,22 @@ def test_trunk_blocks_match_pytorch(pkg):
 
 def test_trunk_end_to_end(pkg):
     """whole trunk, train mode, 4 x 256x320 input: bf16 storage noise is amplified by ~75 train-mode BatchNorms over few
-    samples per channel in the deep stages, so the end-to-end bound is loose (relative L2 < 0.5 on the deepest map,
-    < 0.05 on the first); the per-block test above carries the tight tolerance."""
+    samples per channel in the deep stages, so the end-to-end bound is calibrated against stock bf16 autocast of the
+    same module; the per-block test above carries the tight tolerance."""
     ref, fused, ef = _trunk_pair()
     x = rnd(4, 3, 256, 320, seed=1).cuda()
     feats = ef.forward(fused, x)
     r1 = ref.layer1(x); r2 = ref.layer2(r1); r3 = ref.layer3(r2); r4 = ref.layer4(r3)
-    bounds = [0.05, 0.12, 0.3, 0.5]
-    for f, r, b in zip(feats, [r1, r2, r3, r4], bounds):
+    import copy
+    auto = copy.deepcopy(ref)
+    with torch.autocast("cuda", dtype=BF):
+        a1 = auto.layer1(x); a2 = auto.layer2(a1); a3 = auto.layer3(a2); a4 = auto.layer4(a3)
+    for f, r, a in zip(feats, [r1, r2, r3, r4], [a1, a2, a3, a4]):
         assert tuple(f.shape) == (r.shape[0], r.shape[2], r.shape[3], r.shape[1])
         rel = float((f.float().permute(0, 3, 1, 2) - r).norm() / r.norm())
-        assert rel < b, (rel, b)
+        rel_auto = float((a.float() - r).norm() / r.norm())
+        # self-calibrated: no further from fp32 than 1.5x stock bf16 autocast's own drift (+ 2 %)
+        assert rel <= 1.5 * rel_auto + 0.02, (rel, rel_auto)
     sum(f.float().sum() for f in feats).backward()
     for n, p in fused.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), n
