@@ -45,28 +45,37 @@ struct DwArgs {
   bf16* out; long long out_ld;
   int Ho, Wo;
   float* stats;          // [gridDim.x][2][C] or null
+  int G;                 // channel groups (of 8) per block column: min(C/8, 32)
 };
 
 // out[b,oy,ox,c] = sum_{ky,kx} w[ky*K+kx][c] * x[b, oy*S - pad_t + ky, ox*S - pad_l + kx, c]
+// grid = (pixel-strip blocks, channel chunks of G groups).  A block keeps its chunk's taps in shared memory; thread =
+// (channel group c8l = tid % G, strip slot = tid / G), so a warp touches G*16 contiguous bytes per pixel.
 template <int K, int S>
-__global__ void __launch_bounds__(TPB) dw_fwd_kernel(DwArgs a) {
-  extern __shared__ float s_red[];   // [TPB][16] when stats
-  const int C8 = a.C / 8;
+__global__ void __launch_bounds__(TPB, 2) dw_fwd_kernel(DwArgs a) {
+  extern __shared__ float smem[];            // [K*K][G*8] taps | [TPB][16] statistics scratch
+  const int G = a.G, C8 = a.C / 8;
+  float* s_w = smem;
+  float* s_red = smem + K * K * G * 8;
+  const int c8l = threadIdx.x % G, slot = threadIdx.x / G, nslots = TPB / G;
+  const int c8 = blockIdx.y * G + c8l;
+  const bool active = slot < nslots && c8 < C8;
+  for (int i = threadIdx.x; i < K * K * G * 8; i += TPB) {
+    const int tap = i / (G * 8), cc = i - tap * (G * 8);
+    const int ch = blockIdx.y * G * 8 + cc;
+    s_w[i] = ch < a.C ? __ldg(a.w + (size_t)tap * a.C + ch) : 0.f;
+  }
+  __syncthreads();
   const int strips = (a.Wo + TX - 1) / TX;
-  const long long items = (long long)a.B * a.Ho * strips * C8;
-  const long long nthreads = (long long)gridDim.x * TPB;
-  const long long stride = (nthreads / C8) * C8;          // keeps every thread on one channel group
-  const long long tid = (long long)blockIdx.x * TPB + threadIdx.x;
-  const int c8 = (int)(tid % C8);
+  const int nstrips = a.B * a.Ho * strips;
   float st_s[8], st_q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { st_s[j] = 0.f; st_q[j] = 0.f; }
-  if (tid < stride) {
-    for (long long idx = tid; idx < items; idx += stride) {
-      long long r = idx / C8;
-      const int sx = (int)(r % strips); r /= strips;
-      const int oy = (int)(r % a.Ho);
-      const int b = (int)(r / a.Ho);
+  if (active) {
+    for (int st = blockIdx.x * nslots + slot; st < nstrips; st += gridDim.x * nslots) {
+      const int sx = st % strips;
+      const int r = st / strips;
+      const int oy = r % a.Ho, b = r / a.Ho;
       const int ox0 = sx * TX;
       float acc[TX][8];
 #pragma unroll
@@ -77,28 +86,25 @@ __global__ void __launch_bounds__(TPB) dw_fwd_kernel(DwArgs a) {
       for (int ky = 0; ky < K; ++ky) {
         const int iy = oy * S - a.pad_t + ky;
         if (iy < 0 || iy >= a.Hi) continue;
-        float wrow[K][8];
+        const bf16* rowp = a.x + (((long long)b * a.Hi + iy) * a.Wi) * a.x_ld + c8 * 8;
+        constexpr int NCOL = (TX - 1) * S + K;
+        uint4 raw[NCOL];
+#pragma unroll
+        for (int col = 0; col < NCOL; ++col) {       // all loads of the row window first, then the FMAs
+          const int ix = ox0 * S - a.pad_l + col;
+          raw[col] = (ix >= 0 && ix < a.Wi) ? ld8(rowp + (long long)ix * a.x_ld) : make_uint4(0, 0, 0, 0);
+        }
 #pragma unroll
         for (int kx = 0; kx < K; ++kx) {
-          const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.w + (size_t)(ky * K + kx) * a.C + c8 * 8));
-          const float4 w1 = __ldg(reinterpret_cast<const float4*>(a.w + (size_t)(ky * K + kx) * a.C + c8 * 8 + 4));
-          wrow[kx][0] = w0.x; wrow[kx][1] = w0.y; wrow[kx][2] = w0.z; wrow[kx][3] = w0.w;
-          wrow[kx][4] = w1.x; wrow[kx][5] = w1.y; wrow[kx][6] = w1.z; wrow[kx][7] = w1.w;
-        }
-        const bf16* rowp = a.x + (((long long)b * a.Hi + iy) * a.Wi) * a.x_ld + c8 * 8;
-#pragma unroll
-        for (int col = 0; col < (TX - 1) * S + K; ++col) {
-          const int ix = ox0 * S - a.pad_l + col;
-          if (ix < 0 || ix >= a.Wi) continue;
-          float v[8];
-          unpack8(ld8(rowp + (long long)ix * a.x_ld), v);
+          const float4 w0 = *reinterpret_cast<const float4*>(s_w + (ky * K + kx) * G * 8 + c8l * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(s_w + (ky * K + kx) * G * 8 + c8l * 8 + 4);
+          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
           for (int t = 0; t < TX; ++t) {
-            const int kx = col - t * S;
-            if (kx >= 0 && kx < K) {
+            float v[8];
+            unpack8(raw[kx + t * S], v);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(v[j], wrow[kx][j], acc[t][j]);
-            }
+            for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(v[j], wv[j], acc[t][j]);
           }
         }
       }
@@ -119,24 +125,22 @@ __global__ void __launch_bounds__(TPB) dw_fwd_kernel(DwArgs a) {
     }
   }
   if (a.stats) {
-    // deterministic block reduction: thread t owns channel group (block_base + t) % C8
+    // deterministic block reduction over the strip slots of each channel group
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s_red[threadIdx.x * 16 + j] = st_s[j]; s_red[threadIdx.x * 16 + 8 + j] = st_q[j]; }
     __syncthreads();
-    float* dst = a.stats + (size_t)blockIdx.x * 2 * a.C;
-    const int base = (int)(((long long)blockIdx.x * TPB) % C8);
-    for (int g = threadIdx.x; g < C8; g += TPB) {
-      int t0 = g - base;
-      if (t0 < 0) t0 += C8;
-      float s[8], q[8];
+    if (threadIdx.x < G && blockIdx.y * G + threadIdx.x < C8) {
+      float sacc[8], qacc[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
-      for (int t = t0; t < TPB; t += C8) {
+      for (int j = 0; j < 8; ++j) { sacc[j] = 0.f; qacc[j] = 0.f; }
+      for (int sl = 0; sl < nslots; ++sl) {
+        const int t = sl * G + threadIdx.x;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { s[j] += s_red[t * 16 + j]; q[j] += s_red[t * 16 + 8 + j]; }
+        for (int j = 0; j < 8; ++j) { sacc[j] += s_red[t * 16 + j]; qacc[j] += s_red[t * 16 + 8 + j]; }
       }
+      float* dst = a.stats + (size_t)blockIdx.x * 2 * a.C + (size_t)(blockIdx.y * G + threadIdx.x) * 8;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { dst[g * 8 + j] = s[j]; dst[a.C + g * 8 + j] = q[j]; }
+      for (int j = 0; j < 8; ++j) { dst[j] = sacc[j]; dst[a.C + j] = qacc[j]; }
     }
   }
 }
@@ -184,6 +188,8 @@ __global__ void __launch_bounds__(TPB) dw_dgrad_s2_kernel(const bf16* __restrict
 }
 
 // weight gradient partials: partial[chunk][ky*K+kx][c] = sum over the chunk's output pixels of dy * x(tap)
+// thread = (channel group, kernel row ky, strip slot); each step takes a strip of TX output pixels of one row: TX dy
+// vectors and the (TX-1)*S+K input vectors under kernel row ky are loaded up front (independent loads), then multiplied.
 constexpr int WG_C8B = 16;   // channel groups per block
 template <int K, int S>
 __global__ void __launch_bounds__(TPB) dw_wgrad_kernel(const bf16* __restrict__ x, long long x_ld, int B, int Hi, int Wi, int C,
@@ -198,34 +204,46 @@ __global__ void __launch_bounds__(TPB) dw_wgrad_kernel(const bf16* __restrict__ 
   const int ky = (threadIdx.x / c8b) % K;
   const int slot = threadIdx.x / per_slot;
   const int c8 = blockIdx.x * c8b + c8l;
-  const long long npix = (long long)B * Ho * Wo;
-  const long long per_chunk = (npix + nchunks - 1) / nchunks;
-  const long long p0 = (long long)blockIdx.y * per_chunk;
-  const long long p1 = p0 + per_chunk < npix ? p0 + per_chunk : npix;
+  const int strips = (Wo + TX - 1) / TX;
+  const int nstrips = B * Ho * strips;
+  const int per_chunk = (nstrips + nchunks - 1) / nchunks;
+  const int s0 = blockIdx.y * per_chunk;
+  const int s1 = s0 + per_chunk < nstrips ? s0 + per_chunk : nstrips;
   float acc[K][8];
 #pragma unroll
   for (int kx = 0; kx < K; ++kx)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[kx][j] = 0.f;
   if (slot < nslots && c8 < C8) {
-    for (long long p = p0 + slot; p < p1; p += nslots) {
-      const int ox = (int)(p % Wo);
-      long long r = p / Wo;
-      const int oy = (int)(r % Ho);
-      const int b = (int)(r / Ho);
+    for (int st = s0 + slot; st < s1; st += nslots) {
+      const int sx = st % strips;
+      const int r = st / strips;
+      const int oy = r % Ho, b = r / Ho;
       const int iy = oy * S - pad_t + ky;
       if (iy < 0 || iy >= Hi) continue;
-      float g[8];
-      unpack8(ld8(dy + p * dy_ld + c8 * 8), g);
+      const int ox0 = sx * TX;
+      constexpr int NCOL = (TX - 1) * S + K;
+      uint4 graw[TX], xraw[NCOL];
+      const bf16* gp = dy + (((long long)b * Ho + oy) * Wo + ox0) * dy_ld + c8 * 8;
+#pragma unroll
+      for (int t = 0; t < TX; ++t) graw[t] = (ox0 + t < Wo) ? ld8(gp + (long long)t * dy_ld) : make_uint4(0, 0, 0, 0);
       const bf16* rowp = x + (((long long)b * Hi + iy) * Wi) * x_ld + c8 * 8;
 #pragma unroll
-      for (int kx = 0; kx < K; ++kx) {
-        const int ix = ox * S - pad_l + kx;
-        if (ix < 0 || ix >= Wi) continue;
-        float v[8];
-        unpack8(ld8(rowp + (long long)ix * x_ld), v);
+      for (int col = 0; col < NCOL; ++col) {
+        const int ix = ox0 * S - pad_l + col;
+        xraw[col] = (ix >= 0 && ix < Wi) ? ld8(rowp + (long long)ix * x_ld) : make_uint4(0, 0, 0, 0);
+      }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[kx][j] = fmaf(g[j], v[j], acc[kx][j]);
+      for (int t = 0; t < TX; ++t) {
+        float g[8];
+        unpack8(graw[t], g);
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+          float v[8];
+          unpack8(xraw[kx + t * S], v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[kx][j] = fmaf(g[j], v[j], acc[kx][j]);
+        }
       }
     }
   }
@@ -273,8 +291,8 @@ inline int wg_chunks(int B, int Ho, int Wo, int C) {
   const int C8 = C / 8;
   const int cblocks = (C8 + WG_C8B - 1) / WG_C8B;
   long long npix = (long long)B * Ho * Wo;
-  long long n = (4LL * kNumSMs + cblocks - 1) / cblocks;
-  if (n > npix / 64) n = npix / 64;
+  long long n = (6LL * kNumSMs + cblocks - 1) / cblocks;
+  if (n > npix / 128) n = npix / 128;
   if (n < 1) n = 1;
   return (int)n;
 }
@@ -283,9 +301,16 @@ inline int wg_chunks(int B, int Ho, int Wo, int C) {
 
 extern "C" {
 
+static inline int dw_G(int C) { return C / 8 < 32 ? C / 8 : 32; }
+
 int dp_dwconv_fwd_blocks(int B, int Ho, int Wo, int C) {
-  const long long items = (long long)B * Ho * ((Wo + TX - 1) / TX) * (C / 8);
-  return dw_grid(items);
+  const int G = dw_G(C), ny = (C / 8 + G - 1) / G, nslots = TPB / G;
+  const long long nstrips = (long long)B * Ho * ((Wo + TX - 1) / TX);
+  long long nx = (nstrips + nslots - 1) / nslots;
+  long long cap = (4LL * kNumSMs + ny - 1) / ny;
+  if (cap < 1) cap = 1;
+  if (nx > cap) nx = cap;
+  return (int)(nx < 1 ? 1 : nx);
 }
 
 /* Depthwise K x K convolution (K = 3 or 5; stride 1 or 2; explicit top / left padding so both symmetric and TF-"SAME"
@@ -298,10 +323,12 @@ int dp_dwconv_fwd(const void* x, long long x_ld, int B, int Hi, int Wi, int C, c
   DP_CHECK_ARG(x && w && out, "dp_dwconv_fwd: null pointer");
   DP_CHECK_ARG(C % 8 == 0 && C <= 2048 && x_ld % 8 == 0 && out_ld % 8 == 0, "dp_dwconv_fwd: channels must be a multiple of 8 (<= 2048)");
   DP_CHECK_ARG((K == 3 || K == 5) && (stride == 1 || stride == 2), "dp_dwconv_fwd: K %d stride %d", K, stride);
+  DP_CHECK_ARG((long long)B * Ho * ((Wo + TX - 1) / TX) < (1LL << 31), "dp_dwconv_fwd: too many pixel strips");
+  const int G = dw_G(C);
   DwArgs a{reinterpret_cast<const bf16*>(x), x_ld, B, Hi, Wi, C, w, pad_t, pad_l, reinterpret_cast<bf16*>(out), out_ld,
-           Ho, Wo, stats_partials};
-  const int grid = dp_dwconv_fwd_blocks(B, Ho, Wo, C);
-  const size_t smem = stats_partials ? (size_t)TPB * 16 * sizeof(float) : 0;
+           Ho, Wo, stats_partials, G};
+  dim3 grid(dp_dwconv_fwd_blocks(B, Ho, Wo, C), (C / 8 + G - 1) / G);
+  const size_t smem = ((size_t)K * K * G * 8 + (stats_partials ? (size_t)TPB * 16 : 0)) * sizeof(float);
   if (K == 3 && stride == 1) dw_fwd_kernel<3, 1><<<grid, TPB, smem, stream>>>(a);
   else if (K == 3) dw_fwd_kernel<3, 2><<<grid, TPB, smem, stream>>>(a);
   else if (stride == 1) dw_fwd_kernel<5, 1><<<grid, TPB, smem, stream>>>(a);

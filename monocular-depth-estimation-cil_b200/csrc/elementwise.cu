@@ -228,35 +228,57 @@ __global__ void __launch_bounds__(RED_TPB) chan_reduce_kernel(const bf16* __rest
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s0[j] = 0.f; s1[j] = 0.f; }
   if (pl < lanes) {
-    for (size_t p = (size_t)blockIdx.x * lanes + pl; p < npix; p += (size_t)gridDim.x * lanes) {
-      float xv[8], g[8];
-      if (MODE != 2 || x) unpack8(ld8(x + p * x_ld + c8 * 8), xv);
-      if (MODE == 2) {
-        unpack8(ld8(dy + p * dy_ld + c8 * 8), g);
-        if (mask_ss) {
-          // activation recomputed from the pre-BN tensor (already being read) instead of loading the activated output;
-          // with mask_ss set, `mask` (optional) is the residual that was added before the activation
-          float radd[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (mask) unpack8(ld8(mask + p * m_ld + c8 * 8), radd);
+    float msc[8], msh[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            // fp32 pre-activation, not its bf16 rounding: values just below 6 that round up to 6.0 keep their gradient,
-            // as in the reference's fp32 hardtanh backward
-            const float m = xv[j] * __ldg(mask_ss + c8 * 8 + j) + __ldg(mask_ss + C + c8 * 8 + j) + radd[j];
-            g[j] = (m > 0.f && m < mask_hi) ? g[j] : 0.f;
-          }
-        } else if (mask) {
-          float m[8];
-          unpack8(ld8(mask + p * m_ld + c8 * 8), m);
+    for (int j = 0; j < 8; ++j) {
+      msc[j] = (MODE == 2 && mask_ss) ? __ldg(mask_ss + c8 * 8 + j) : 0.f;
+      msh[j] = (MODE == 2 && mask_ss) ? __ldg(mask_ss + C + c8 * 8 + j) : 0.f;
+    }
+    const size_t pstep = (size_t)gridDim.x * lanes;
+    // two pixels per iteration: all loads of both are issued before any is consumed (bytes in flight, not occupancy,
+    // carry the bandwidth of this reduction)
+    for (size_t p = (size_t)blockIdx.x * lanes + pl; p < npix; p += 2 * pstep) {
+      const size_t pp[2] = {p, p + pstep};
+      uint4 rx[2], rg[2], rm[2];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) g[j] = (m[j] > 0.f && m[j] < mask_hi) ? g[j] : 0.f;
-        }
+      for (int u = 0; u < 2; ++u) {
+        const bool ok = pp[u] < npix;
+        rx[u] = (ok && (MODE != 2 || x)) ? ld8(x + pp[u] * x_ld + c8 * 8) : make_uint4(0, 0, 0, 0);
+        rg[u] = (ok && MODE == 2) ? ld8(dy + pp[u] * dy_ld + c8 * 8) : make_uint4(0, 0, 0, 0);
+        rm[u] = (ok && MODE == 2 && mask) ? ld8(mask + pp[u] * m_ld + c8 * 8) : make_uint4(0, 0, 0, 0);
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (MODE == 0) s0[j] += xv[j];
-        if (MODE == 1) { s0[j] += xv[j]; s1[j] += xv[j] * xv[j]; }
-        if (MODE == 2) { s0[j] += g[j]; s1[j] += g[j] * xv[j]; }
+      for (int u = 0; u < 2; ++u) {
+        if (pp[u] >= npix) continue;
+        float xv[8], g[8];
+        unpack8(rx[u], xv);
+        if (MODE == 2) {
+          unpack8(rg[u], g);
+          if (mask_ss) {
+            // activation recomputed from the pre-BN tensor (already being read) instead of loading the activated
+            // output; with mask_ss set, `mask` (optional) is the residual that was added before the activation
+            float radd[8];
+            unpack8(rm[u], radd);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              // fp32 pre-activation, not its bf16 rounding: values just below 6 that round up to 6.0 keep their
+              // gradient, as in the reference's fp32 hardtanh backward
+              const float m = xv[j] * msc[j] + msh[j] + radd[j];
+              g[j] = (m > 0.f && m < mask_hi) ? g[j] : 0.f;
+            }
+          } else if (mask) {
+            float m[8];
+            unpack8(rm[u], m);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] = (m[j] > 0.f && m[j] < mask_hi) ? g[j] : 0.f;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (MODE == 0) s0[j] += xv[j];
+          if (MODE == 1) { s0[j] += xv[j]; s1[j] += xv[j] * xv[j]; }
+          if (MODE == 2) { s0[j] += g[j]; s1[j] += g[j] * xv[j]; }
+        }
       }
     }
   }
@@ -280,19 +302,30 @@ __global__ void __launch_bounds__(RED_TPB) chan_reduce_kernel(const bf16* __rest
 // BatchNorm2d finalize (train): partial[nparts][2][C] (sum, sumsq over `count` values per channel) ->
 //   scale_shift[0][C] = gamma*invstd, [1][C] = beta - mean*gamma*invstd, save[0][C]=mean, save[1][C]=invstd;
 //   running stats updated with momentum (unbiased variance), num_batches_tracked += 1.
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, int nparts, int C, double count,
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partial, int nparts, int C, double count,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                                    long long* __restrict__ num_batches, float* __restrict__ scale_shift,
                                    float* __restrict__ save) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && num_batches) *num_batches += 1;
-  if (c >= C) return;
+  // block = 32 channels x 8 partial lanes: coalesced 128-byte rows of the partials, fixed-order fp64 folding
+  __shared__ double s_s[8][32], s_q[8][32];
+  const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches) *num_batches += 1;
   double s = 0.0, q = 0.0;
-  for (int p = 0; p < nparts; ++p) {
-    s += (double)partial[((size_t)p * 2 + 0) * C + c];
-    q += (double)partial[((size_t)p * 2 + 1) * C + c];
+  if (c < C) {
+    for (int p = pl; p < nparts; p += 8) {
+      s += (double)partial[((size_t)p * 2 + 0) * C + c];
+      q += (double)partial[((size_t)p * 2 + 1) * C + c];
+    }
   }
+  s_s[pl][cl] = s;
+  s_q[pl][cl] = q;
+  __syncthreads();
+  if (pl != 0 || c >= C) return;
+  s = 0.0; q = 0.0;
+#pragma unroll
+  for (int l = 0; l < 8; ++l) { s += s_s[l][cl]; q += s_q[l][cl]; }
   const double mean = s / count;
   double var = q / count - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -324,23 +357,37 @@ __global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const flo
 }
 
 // y = act( x*scale + shift  [+ x2*scale2 + shift2 | + res] )
-__global__ void bn_apply_kernel(const bf16* __restrict__ x, long long x_ld, const float* __restrict__ ss,
+// The grid-stride is rounded down to a multiple of C/8, so every thread stays on one 8-channel group and keeps its
+// scale / shift vectors in registers for its whole pixel walk.
+__global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ x, long long x_ld, const float* __restrict__ ss,
                                 const bf16* __restrict__ x2, long long x2_ld, const float* __restrict__ ss2,
                                 const bf16* __restrict__ res, long long res_ld, size_t npix, int C, int relu,
                                 bf16* __restrict__ y, long long y_ld) {
   const int C8 = C / 8;
   const size_t total = npix * C8;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % C8);
-    const size_t p = i / C8;
+  const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+  const size_t stride = (nthreads / C8) * C8;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= stride) return;
+  const int c8 = (int)(tid % C8);
+  float sc[8], sh[8], sc2[8], sh2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = __ldg(ss + c8 * 8 + j);
+    sh[j] = __ldg(ss + C + c8 * 8 + j);
+    sc2[j] = x2 ? __ldg(ss2 + c8 * 8 + j) : 0.f;
+    sh2[j] = x2 ? __ldg(ss2 + C + c8 * 8 + j) : 0.f;
+  }
+  const size_t pstep = stride / C8;
+  for (size_t p = tid / C8; p < npix; p += pstep) {
     float v[8], o[8];
     unpack8(ld8(x + p * x_ld + c8 * 8), v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = v[j] * __ldg(ss + c8 * 8 + j) + __ldg(ss + C + c8 * 8 + j);
+    for (int j = 0; j < 8; ++j) o[j] = v[j] * sc[j] + sh[j];
     if (x2) {
       unpack8(ld8(x2 + p * x2_ld + c8 * 8), v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] += v[j] * __ldg(ss2 + c8 * 8 + j) + __ldg(ss2 + C + c8 * 8 + j);
+      for (int j = 0; j < 8; ++j) o[j] += v[j] * sc2[j] + sh2[j];
     }
     if (res) {
       unpack8(ld8(res + p * res_ld + c8 * 8), v);
@@ -357,13 +404,14 @@ __global__ void bn_apply_kernel(const bf16* __restrict__ x, long long x_ld, cons
     }
     st8(y + p * y_ld + c8 * 8, pack8(o));
   }
+  (void)total;
 }
 
 // BN backward apply: g = dy*(mask>0);  train: dx = gamma*invstd*(g - sum_g/N - xhat*sum_gxhat/N);  eval: gamma*invstd*g
 // red[0][C] = sum g, red[1][C] = sum g*x (raw x): sum_gxhat = invstd*(red1 - mean*red0).
 // Also writes dgamma = sum_gxhat, dbeta = sum g (by block 0), and optionally gmask = g (the masked upstream grad,
 // which is also the gradient of an identity shortcut / residual).
-__global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dy, long long dy_ld, const bf16* __restrict__ mask,
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restrict__ dy, long long dy_ld, const bf16* __restrict__ mask,
                                     long long m_ld, const bf16* __restrict__ x, long long x_ld,
                                     const float* __restrict__ red, const float* __restrict__ save,
                                     const float* __restrict__ gamma, double count, int train, size_t npix, int C,
@@ -371,7 +419,6 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dy, long long dy_ld
                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
                                     float mask_hi, const float* __restrict__ mask_ss) {
   const int C8 = C / 8;
-  const size_t total = npix * C8;
   if (blockIdx.x == 0 && dgamma) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       const float mean = save[c], invstd = save[C + c];
@@ -380,59 +427,97 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dy, long long dy_ld
       dbeta[c] = accumulate ? dbeta[c] + red[c] : red[c];
     }
   }
+  // every thread stays on one 8-channel group (stride rounded to a multiple of C/8) and folds the per-channel
+  // statistics into three coefficients once:  dx = ca*g + cb*x + cd
+  const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+  const size_t stride = (nthreads / C8) * C8;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= stride) return;
+  const int c8 = (int)(tid % C8);
   const float invN = (float)(1.0 / count);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % C8);
-    const size_t p = i / C8;
-    float g[8], xv[8], o[8];
-    unpack8(ld8(dy + p * dy_ld + c8 * 8), g);
-    if (dx || mask_ss) unpack8(ld8(x + p * x_ld + c8 * 8), xv);
-    if (mask_ss) {
-      float radd[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (mask) unpack8(ld8(mask + p * m_ld + c8 * 8), radd);
+  float ca[8], cb[8], cd[8], msc[8], msh[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float m = xv[j] * __ldg(mask_ss + c8 * 8 + j) + __ldg(mask_ss + C + c8 * 8 + j) + radd[j];
-        g[j] = (m > 0.f && m < mask_hi) ? g[j] : 0.f;
-      }
-    } else if (mask) {
-      float m[8];
-      unpack8(ld8(mask + p * m_ld + c8 * 8), m);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = (m[j] > 0.f && m[j] < mask_hi) ? g[j] : 0.f;
-    }
-    if (gmask) st8(gmask + p * gm_ld + c8 * 8, pack8(g));
+  for (int j = 0; j < 8; ++j) {
+    const int c = c8 * 8 + j;
+    ca[j] = cb[j] = cd[j] = 0.f;
     if (dx) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = c8 * 8 + j;
-        const float mean = __ldg(save + c), invstd = __ldg(save + C + c);
-        const float gm = gamma ? __ldg(gamma + c) : 1.f;
-        if (train) {
-          const float sg = __ldg(red + c), sgx = __ldg(red + C + c);
-          const float xhat = (xv[j] - mean) * invstd;
-          const float sgxh = invstd * (sgx - mean * sg);
-          o[j] = gm * invstd * (g[j] - sg * invN - xhat * sgxh * invN);
-        } else {
-          o[j] = gm * invstd * g[j];
-        }
+      const float mean = __ldg(save + c), invstd = __ldg(save + C + c);
+      const float gm = gamma ? __ldg(gamma + c) : 1.f;
+      ca[j] = gm * invstd;
+      if (train) {
+        const float sg = __ldg(red + c), sgx = __ldg(red + C + c);
+        const float sgxh = invstd * (sgx - mean * sg);
+        // gm*invstd*(g - sg/N - (x-mean)*invstd*sgxh/N)
+        cb[j] = -gm * invstd * invstd * sgxh * invN;
+        cd[j] = -gm * invstd * sg * invN - cb[j] * mean;
       }
-      st8(dx + p * dx_ld + c8 * 8, pack8(o));
+    }
+    msc[j] = mask_ss ? __ldg(mask_ss + c) : 0.f;
+    msh[j] = mask_ss ? __ldg(mask_ss + C + c) : 0.f;
+  }
+  const size_t pstep = stride / C8;
+  for (size_t p0 = tid / C8; p0 < npix; p0 += 2 * pstep) {
+    const size_t pp[2] = {p0, p0 + pstep};
+    uint4 rg[2], rx[2], rm[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {     // both pixels' loads first
+      const bool ok = pp[u] < npix;
+      rg[u] = ok ? ld8(dy + pp[u] * dy_ld + c8 * 8) : make_uint4(0, 0, 0, 0);
+      rx[u] = (ok && (dx || mask_ss)) ? ld8(x + pp[u] * x_ld + c8 * 8) : make_uint4(0, 0, 0, 0);
+      rm[u] = (ok && mask) ? ld8(mask + pp[u] * m_ld + c8 * 8) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const size_t p = pp[u];
+      if (p >= npix) continue;
+      float g[8], xv[8], o[8];
+      unpack8(rg[u], g);
+      unpack8(rx[u], xv);
+      if (mask_ss) {
+        float radd[8];
+        unpack8(rm[u], radd);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float m = xv[j] * msc[j] + msh[j] + radd[j];
+          g[j] = (m > 0.f && m < mask_hi) ? g[j] : 0.f;
+        }
+      } else if (mask) {
+        float m[8];
+        unpack8(rm[u], m);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = (m[j] > 0.f && m[j] < mask_hi) ? g[j] : 0.f;
+      }
+      if (gmask) st8(gmask + p * gm_ld + c8 * 8, pack8(g));
+      if (dx) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(ca[j], g[j], fmaf(cb[j], xv[j], cd[j]));
+        st8(dx + p * dx_ld + c8 * 8, pack8(o));
+      }
     }
   }
 }
 
-__global__ void sum_partials_kernel(const float* __restrict__ partial, int nparts, int rows, int C,
+__global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ partial, int nparts, int rows, int C,
                                     float* __restrict__ out, int accumulate) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * C) return;
-  const int which = i / C, c = i - which * C;
+  // block = 32 columns x 8 partial lanes over the flattened [rows*C] vector; partial stride is 2*C per part
+  __shared__ double s_s[8][32];
+  const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + cl;
   double s = 0.0;
-  for (int p = 0; p < nparts; ++p) s += (double)partial[((size_t)p * 2 + which) * C + c];
+  if (i < rows * C) {
+    const int which = i / C, c = i - which * C;
+    for (int p = pl; p < nparts; p += 8) s += (double)partial[((size_t)p * 2 + which) * C + c];
+  }
+  s_s[pl][cl] = s;
+  __syncthreads();
+  if (pl != 0 || i >= rows * C) return;
+  s = 0.0;
+#pragma unroll
+  for (int l = 0; l < 8; ++l) s += s_s[l][cl];
   out[i] = accumulate ? out[i] + (float)s : (float)s;
 }
 
-constexpr int kRedBlocks = 2 * kNumSMs;
+constexpr int kRedBlocks = 4 * kNumSMs;
 
 }  // namespace
 
@@ -526,7 +611,7 @@ int dp_chan_reduce(int mode, const void* x, long long x_ld, const void* dy, long
 
 int dp_sum_partials(const float* partial, int nparts, int rows, int C, float* out, int accumulate, cudaStream_t stream) {
   DP_CHECK_ARG(partial && out && rows >= 1 && rows <= 2, "dp_sum_partials: bad arguments");
-  sum_partials_kernel<<<dp::ceil_div(rows * C, 128), 128, 0, stream>>>(partial, nparts, rows, C, out, accumulate);
+  sum_partials_kernel<<<dp::ceil_div(rows * C, 32), 256, 0, stream>>>(partial, nparts, rows, C, out, accumulate);
   DP_CHECK_LAUNCH("sum_partials_kernel");
   return DP_OK;
 }
@@ -535,7 +620,7 @@ int dp_bn_finalize(const float* partial, int nparts, int C, double count, const 
                    float eps, float momentum, float* running_mean, float* running_var, long long* num_batches_tracked,
                    float* scale_shift, float* save_mean_invstd, cudaStream_t stream) {
   DP_CHECK_ARG(partial && scale_shift && save_mean_invstd && C > 0 && count > 0, "dp_bn_finalize: bad arguments");
-  bn_finalize_kernel<<<dp::ceil_div(C, 128), 128, 0, stream>>>(partial, nparts, C, count, gamma, beta, eps, momentum,
+  bn_finalize_kernel<<<dp::ceil_div(C, 32), 256, 0, stream>>>(partial, nparts, C, count, gamma, beta, eps, momentum,
                                                                running_mean, running_var, num_batches_tracked,
                                                                scale_shift, save_mean_invstd);
   DP_CHECK_LAUNCH("bn_finalize_kernel");
