@@ -635,7 +635,11 @@ int make_plan(Plan& p, int B, int Hg, int Wg, int Cin, int Cout, const ColSpec* 
   }
   a.KB = Cin > 32 ? 64 : (Cin > 16 ? 32 : 16);
   a.kchunks = dp::ceil_div(Cin, a.KB);
-  a.n_blocks = dp::ceil_div(Cout, 160);
+  // N blocking: every N block re-reads the activation tile, so pointwise (1x1) layers - bandwidth-bound, small weight
+  // tiles - take up to 256 columns per block (two TMEM accumulators); 3x3 layers stream three weight taps per stage
+  // and stay at <= 160 columns so that the pipeline keeps several stages.
+  const int bn_cap = (ncols == 1 && cols[0].nr == 1) ? 256 : 160;
+  a.n_blocks = dp::ceil_div(Cout, bn_cap);
   a.BN = ((dp::ceil_div(Cout, a.n_blocks) + 15) / 16) * 16;
   a.row_bytes = a.KB * 2;
   // halo mode (plain 3x3, whole weight set resident): 16x8 patches, one 18x10-pixel box per channel chunk

@@ -503,6 +503,7 @@ __global__ void __cluster_dims__(kEvalCluster, 1, 1) __launch_bounds__(TPB) eval
 
   // ---- sweep 1: moments ----
   double acc[3] = {0.0, 0.0, 0.0};
+#pragma unroll 2
   for (long long i = i0 + threadIdx.x; i < i1; i += TPB) {
     float pv[VEC], tv[VEC];
     if (VEC == 4) {
@@ -534,6 +535,7 @@ __global__ void __cluster_dims__(kEvalCluster, 1, 1) __launch_bounds__(TPB) eval
   unsigned cnt[DP_MAX_THR];
 #pragma unroll
   for (int k = 0; k < DP_MAX_THR; ++k) cnt[k] = 0;
+#pragma unroll 2
   for (long long i = i0 + threadIdx.x; i < i1; i += TPB) {
     float pv[VEC], tv[VEC];
     if (VEC == 4) {

@@ -31,42 +31,53 @@ def init_from_env(backend=None):
 
 
 class GradientAllReducer:
-    """Flat-bucket gradient averaging.  After the first backward, the parameters that received a gradient are
-    re-pointed at views of one flat fp32 buffer, so each later step is a single in-place all-reduce (96 MB for the
-    default model: launch-latency bound on NVSwitch, so one bucket beats many) and `zero()` is one memset."""
+    """Flat-bucket gradient averaging.  `zero()` drops the gradients (grad=None), so autograd *assigns* each fresh
+    gradient instead of launching one accumulation kernel per parameter (~400 per step for the default model).
+    `reduce()` gathers the gradients that exist into one flat fp32 buffer with a multi-tensor copy, all-reduces it
+    once (96 MB for the default model: launch-latency bound on NVSwitch, so one bucket beats many) and re-points
+    `.grad` at the buffer's views for the optimizer.  With a single rank the gradients are left where autograd put
+    them.  Parameters that never receive a gradient keep grad=None (AdamW then skips them, as in the reference)."""
 
     def __init__(self, params, world=None):
         self.params = [p for p in params if p.requires_grad]
         self.world = world if world is not None else (dist.get_world_size() if dist.is_initialized() else 1)
         self.flat = None
         self.live = None
+        self.views = None
 
     def _build(self):
         self.live = [p for p in self.params if p.grad is not None]
         n = sum(p.numel() for p in self.live)
         dev = self.live[0].device
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.views = []
         off = 0
         for p in self.live:
-            v = self.flat[off:off + p.numel()].view_as(p)
-            v.copy_(p.grad)
-            p.grad = v
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
 
     def zero(self):
-        if self.flat is None:
-            for p in self.params:
-                p.grad = None
-        else:
-            self.flat.zero_()
+        for p in self.params:
+            p.grad = None
 
     def reduce(self):
         """call after backward(); averages gradients over ranks (no-op for world 1)."""
-        if self.flat is None:
+        if self.live is None:
             self._build()
-        if self.world > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-            self.flat.mul_(1.0 / self.world)
+        if self.world == 1:
+            return
+        grads, views = [], []
+        for p, v in zip(self.live, self.views):
+            if p.grad is None:
+                v.zero_()
+            else:
+                grads.append(p.grad if p.grad.dtype == torch.float32 else p.grad.float())
+                views.append(v)
+        torch._foreach_copy_(views, grads)
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+        self.flat.mul_(1.0 / self.world)
+        for p, v in zip(self.live, self.views):
+            p.grad = v
 
     def live_parameters(self):
         return self.live
