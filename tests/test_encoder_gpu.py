@@ -77,9 +77,10 @@ def test_batchnorm_relu6_fwd_bwd(pkg, C, res):
     x = rnd(B, C, H, W, seed=C, scale=3.0)
     r = rnd(B, C, H, W, seed=C + 1)
     bn = nn.BatchNorm2d(C, eps=1e-3)
+    gp = torch.Generator().manual_seed(1000 + C)
     with torch.no_grad():
-        bn.weight.copy_(torch.rand(C) + 0.5)
-        bn.bias.copy_(torch.randn(C) * 2 + 2)      # pushes a good share of the outputs above 6
+        bn.weight.copy_(torch.rand(C, generator=gp) + 0.5)
+        bn.bias.copy_(torch.randn(C, generator=gp) * 2 + 2)      # pushes a good share of the outputs above 6
     import copy
     bn_ref = copy.deepcopy(bn).train()
     xr = x.clone().requires_grad_(True)

@@ -1,5 +1,12 @@
-set -x
-python tools/ncu_conv.py > gpurun_out/plain_conv.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 6 -c 3 -o gpurun_out/prof_conv_r1_v7 python tools/ncu_conv.py > gpurun_out/ncu_conv.log 2>&1
-tail -3 gpurun_out/ncu_conv.log
-python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-eval > gpurun_out/plain_bench.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -s 3400 -c 1300 --csv --log-file gpurun_out/launches_r1_v7.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-eval > gpurun_out/ncu_bench.log 2>&1
-tail -2 gpurun_out/ncu_bench.log; wc -l gpurun_out/launches_r1_v7.csv
+python -m pytest tests -m gpu -q -x 2>&1 | tail -3
+python bench.py --steps 8 --warmup 3 --profile-layers > gpurun_out/bench_r1_v8.json 2> gpurun_out/bench_r1_v8_layers.txt
+tail -2 gpurun_out/bench_r1_v8_layers.txt
+python - <<'PY'
+import json
+for l in open('gpurun_out/bench_r1_v8.json'):
+    if l.startswith('{'):
+        d=json.loads(l)
+        print({k:d[k] for k in ['value','ms_per_step','e2e','eager_ms_per_step','clocks','gpu_launches_per_step']}); print(json.dumps(d['roofline'])[:1500]); print(d['eval']); print(d['cpu_baseline'])
+PY
+python tools/step_breakdown.py > gpurun_out/breakdown.txt 2>gpurun_out/breakdown.err
+head -24 gpurun_out/breakdown.txt | cut -c1-120
