@@ -307,11 +307,144 @@ __device__ __forceinline__ void epilogue_tma(const Maps& tm, const ConvArgs& a, 
       const float s = dp::warp_sum(acc_s[j]);
       const float q = dp::warp_sum(acc_q[j]);
       if (lane == 0 && col0 + j < a.Cout) {
-        s_stats[(ew * 2 + 0) * a.Cout + col0 + j] = s;
-        s_stats[(ew * 2 + 1) * a.Cout + col0 + j] = q;
+        s_stats[(e * 2 + 0) * a.Cout + col0 + j] = s;
+        s_stats[(e * 2 + 1) * a.Cout + col0 + j] = q;
       }
     }
   }
+}
+
+// ---- epilogue A2: BN a multiple of 64 (> 64), single output.  The tile leaves in 64-column sub-blocks: per
+// sub-block each of the eight warps takes 32 pixels x 32 columns (one tcgen05.ld), stages bf16 rows in a 128B-swizzled
+// [128 px][64 ch] tile and one thread TMA-stores it at channel offset nb*BN + sb*64 (channels >= Cout are clipped by the
+// store).  A thread's direct stores would touch 32 B out of every Cout*2-byte pixel row - the wide "expand" pointwise
+// layers of the encoder trunk ran at ~1.4 TB/s that way.  BN statistics use the shuffle transpose (columns are too
+// many to keep per-thread accumulators).
+__device__ __forceinline__ void epilogue_tma_wide(const Maps& tm, const ConvArgs& a, Barriers* bars, uint8_t* s_out,
+                                                  float* s_stats, uint32_t tmem, int warp, int lane) {
+  const int e = warp - 4, ew = e & 3, half = e >> 2;
+  const int m = ew * 32 + lane;
+  const int py = m / a.tw, px = m - py * a.tw;
+  const bool store_thread = threadIdx.x == kRoleThreads;
+  uint32_t soff[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t off = (uint32_t)m * 128u + (uint32_t)(half * 64 + j * 16);
+    soff[j] = off ^ (((off >> 7) & 7u) << 4);
+  }
+  const uint32_t s_base = tc::smem_u32(s_out);
+  const int nsub = a.BN / 64;
+  int it = 0, ring = 0;
+  TileIter ti;
+  ti.init(a, blockIdx.x);
+  for (long long item = blockIdx.x; item < a.total_items; item += gridDim.x, ++it, ti.step(a)) {
+    const int n = ti.n, y0 = ti.ty * a.th, x0 = ti.tx * a.tw, nb = ti.nb;
+    const int buf = it & (a.nbuf - 1);
+    const int y = y0 + py, x = x0 + px;
+    const int oy = y * a.osy + a.oay, ox = x * a.osx + a.oax;
+    const bool valid = (y < a.H) && (x < a.W) && (oy < a.Ho) && (ox < a.Wo);
+    const long long pix = ((long long)n * a.Ho + oy) * a.Wo + ox;
+    tc::mbar_wait(&bars->tmem_full[buf], (it >> (a.nbuf == 4 ? 2 : 1)) & 1);
+    tc::fence_after_sync();
+    for (int sb = 0; sb < nsub; ++sb) {
+      const int n0 = nb * a.BN + sb * 64 + half * 32;       // first output channel of this thread's 32 columns
+      uint32_t raw[32];
+      tc::tmem_ld_issue<32>(tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * a.BN + sb * 64 + half * 32), raw);
+      tc::tmem_ld_wait();
+      if (sb == nsub - 1) {
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bars->tmem_empty[buf]);
+      }
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+      if (n0 < a.Cout) {                                        // warp-uniform; Cout is a multiple of 8
+        if (a.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (n0 + j < a.Cout) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          }
+        }
+        if (a.res && valid) {
+          const uint4* rp = reinterpret_cast<const uint4*>(a.res + pix * a.res_ld + n0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (n0 + j * 8 < a.Cout) {
+              const uint4 r = __ldg(rp + j);
+              const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) { v[j * 8 + 2 * k] += bf16_lo(rr[k]); v[j * 8 + 2 * k + 1] += bf16_hi(rr[k]); }
+            }
+          }
+        }
+        if (a.resb && valid) {
+          const uint4* rp = reinterpret_cast<const uint4*>(a.resb + pix * a.resb_ld + n0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (n0 + j * 8 < a.Cout) {
+              const uint4 r = __ldg(rp + j);
+              const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) { v[j * 8 + 2 * k] += bf16_lo(rr[k]); v[j * 8 + 2 * k + 1] += bf16_hi(rr[k]); }
+            }
+          }
+        }
+      }
+      uint32_t q[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        float x0v = v[2 * k], x1v = v[2 * k + 1];
+        if (a.relu) { x0v = fmaxf(x0v, 0.f); x1v = fmaxf(x1v, 0.f); }
+        q[k] = pack_bf16x2(x0v, x1v);
+      }
+      if (a.stats && !valid) {        // overhanging pixels are clipped by the store; zero them for the column sums below
+#pragma unroll
+        for (int k = 0; k < 16; ++k) q[k] = 0u;
+      }
+      const uint32_t st = s_base + (uint32_t)ring * 16384u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tc::st_shared_v4(st + soff[j], q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
+      tc::fence_proxy_async();
+      if (store_thread) {
+        if (a.nob == 2) tc::bulk_wait_read<0>();
+        else tc::bulk_wait_read<1>();
+      }
+      tc::named_bar_sync(1, kEpiThreads);
+      if (store_thread) {
+        tc::tma_store_4d(&tm.o, s_out + (size_t)ring * 16384u, nb * a.BN + sb * 64, x0, y0, n);
+        tc::bulk_commit();
+      }
+      if (a.stats) {
+        // BatchNorm partial sums from the staged tile (the values as stored): warp e sums pixel rows [16e, 16e+16),
+        // lane l the channel pair (2l, 2l+1) - one conflict-free 128-byte row per load, no shuffles.  Slot (e, column)
+        // of s_stats has a single owner, so the += needs no atomics.
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const uint32_t r = (uint32_t)(e * 16 + i);
+          const uint32_t addr = st + r * 128u + ((((uint32_t)lane >> 2) ^ (r & 7u)) << 4) + ((uint32_t)lane & 3u) * 4u;
+          uint32_t u;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(addr));
+          const float f0 = bf16_lo(u), f1 = bf16_hi(u);
+          s0 += f0; s1 += f1;
+          q0 = fmaf(f0, f0, q0); q1 = fmaf(f1, f1, q1);
+        }
+        const int col = nb * a.BN + sb * 64 + 2 * lane;
+        if (col < a.Cout) {      // Cout is even
+          s_stats[(e * 2 + 0) * a.Cout + col] += s0;
+          s_stats[(e * 2 + 0) * a.Cout + col + 1] += s1;
+          s_stats[(e * 2 + 1) * a.Cout + col] += q0;
+          s_stats[(e * 2 + 1) * a.Cout + col + 1] += q1;
+        }
+      }
+      if (++ring == a.nob) ring = 0;
+    }
+  }
+  if (store_thread) tc::bulk_wait_read<0>();
 }
 
 // ---- epilogue B (any BN): 16-column chunks alternate between the two warps that share a TMEM lane quarter; each
@@ -375,8 +508,8 @@ __device__ __forceinline__ void epilogue_direct(const ConvArgs& a, Barriers* bar
         if ((lane & 1) == 0) {
           const int col = n0 + transpose_reduce16_col(lane);
           if (col < a.Cout) {
-            s_stats[(ew * 2 + 0) * a.Cout + col] += cs;
-            s_stats[(ew * 2 + 1) * a.Cout + col] += cq;
+            s_stats[(e * 2 + 0) * a.Cout + col] += cs;
+            s_stats[(e * 2 + 1) * a.Cout + col] += cq;
           }
         }
       }
@@ -420,11 +553,12 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
   // layout: [resident weights][output staging tiles][stages x (A | B)][stats][barriers]
   uint8_t* s_res = smem;
   uint8_t* s_out = smem + a.resident_bytes;
-  const uint32_t out_bytes = a.epi_tma ? (uint32_t)a.nob * (a.out2 ? 2u : 1u) * a.out_tile_bytes : 0u;
+  const uint32_t out_bytes = a.epi_tma == 2 ? (uint32_t)a.nob * 16384u
+                                             : (a.epi_tma ? (uint32_t)a.nob * (a.out2 ? 2u : 1u) * a.out_tile_bytes : 0u);
   uint8_t* s_stage = s_out + out_bytes;
   const uint32_t stage_bytes = a.a_slot_bytes + (a.resident ? 0u : (uint32_t)a.max_nr * a.b_tap_bytes);
   float* s_stats = reinterpret_cast<float*>(s_stage + (size_t)a.stages * stage_bytes);
-  const int stats_floats = a.stats ? 4 * 2 * a.Cout : 0;
+  const int stats_floats = a.stats ? kEpiWarps * 2 * a.Cout : 0;
   Barriers* bars = reinterpret_cast<Barriers*>(reinterpret_cast<uint8_t*>(s_stats) + ((stats_floats * 4 + 15) & ~15));
 
   const int warp = tc::warp_idx_uniform();
@@ -574,7 +708,9 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
     }
   } else if (warp >= 4) {
     // ================= epilogue: TMEM -> registers -> (smem -> TMA store | global) =================
-    if (a.epi_tma) {
+    if (a.epi_tma == 2) {
+      epilogue_tma_wide(tm, a, bars, s_out, s_stats, tmem, warp, lane);
+    } else if (a.epi_tma) {
       if (a.BN == 64) epilogue_tma<32>(tm, a, bars, s_out, s_stats, tmem, warp, lane);
       else if (a.BN == 32) epilogue_tma<16>(tm, a, bars, s_out, s_stats, tmem, warp, lane);
       else epilogue_tma<8>(tm, a, bars, s_out, s_stats, tmem, warp, lane);
@@ -588,7 +724,7 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
         const int which = i / a.Cout, col = i - which * a.Cout;
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) s += s_stats[(w * 2 + which) * a.Cout + col];
+        for (int w = 0; w < kEpiWarps; ++w) s += s_stats[(w * 2 + which) * a.Cout + col];
         dst[i] = s;
       }
     }
@@ -638,9 +774,11 @@ int make_plan(Plan& p, int B, int Hg, int Wg, int Cin, int Cout, const ColSpec* 
   // N blocking: every N block re-reads the activation tile, so pointwise (1x1) layers - bandwidth-bound, small weight
   // tiles - take up to 256 columns per block (two TMEM accumulators); 3x3 layers stream three weight taps per stage
   // and stay at <= 160 columns so that the pipeline keeps several stages.
-  const int bn_cap = (ncols == 1 && cols[0].nr == 1) ? 256 : 160;
+  const bool pointwise = (ncols == 1 && cols[0].nr == 1);
+  const int bn_cap = pointwise ? 256 : 160;
   a.n_blocks = dp::ceil_div(Cout, bn_cap);
   a.BN = ((dp::ceil_div(Cout, a.n_blocks) + 15) / 16) * 16;
+  if (pointwise && a.BN > 64) a.BN = ((a.BN + 63) / 64) * 64;     // wide TMA-store epilogue works in 64-column sub-blocks
   a.row_bytes = a.KB * 2;
   // halo mode (plain 3x3, whole weight set resident): 16x8 patches, one 18x10-pixel box per channel chunk
   a.halo = 0;
@@ -685,7 +823,7 @@ int make_plan(Plan& p, int B, int Hg, int Wg, int Cin, int Cout, const ColSpec* 
   const size_t all_w = (size_t)a.nslots * a.kchunks * a.b_tap_bytes;
   a.resident = (a.n_blocks == 1 && all_w <= 100 * 1024) ? 1 : 0;
   a.resident_bytes = a.resident ? (uint32_t)all_w : 0u;
-  const size_t stats_bytes = want_stats ? ((size_t)4 * 2 * Cout * 4 + 15) & ~size_t(15) : 0;
+  const size_t stats_bytes = want_stats ? ((size_t)kEpiWarps * 2 * Cout * 4 + 15) & ~size_t(15) : 0;
   // TMA-store epilogue: one N block of 16/32/64 columns; two staging tiles per output
   a.epi_tma = (a.n_blocks == 1 && (a.BN == 16 || a.BN == 32 || a.BN == 64) && n_out >= 1) ? 1 : 0;
   {   // experiment knobs (diagnostics)
@@ -695,7 +833,14 @@ int make_plan(Plan& p, int B, int Hg, int Wg, int Cin, int Cout, const ColSpec* 
   }
   a.out_tile_bytes = (uint32_t)(128 * a.BN * 2);
   a.nob = n_out >= 2 ? 2 : (a.BN == 64 ? 3 : 4);
-  const size_t out_bytes = a.epi_tma ? (size_t)a.nob * n_out * a.out_tile_bytes : 0;
+  size_t out_bytes = a.epi_tma ? (size_t)a.nob * n_out * a.out_tile_bytes : 0;
+  if (!a.epi_tma && n_out == 1 && a.BN > 64 && a.BN % 64 == 0 && getenv("DP_CONV_NOTMA") == nullptr) {
+    // wide TMA-store epilogue: three (or two) 16 KB staging tiles, as long as the load pipeline keeps >= 3 stages
+    const size_t stage_b = a.a_slot_bytes + (a.resident ? 0 : (size_t)a.max_nr * a.b_tap_bytes);
+    const size_t base_fixed = 1024 + a.resident_bytes + stats_bytes + sizeof(Barriers) + 64;
+    for (int nob = 3; nob >= 2 && !a.epi_tma; --nob)
+      if (base_fixed + (size_t)nob * 16384 + 3 * stage_b <= 220 * 1024) { a.epi_tma = 2; a.nob = nob; out_bytes = (size_t)nob * 16384; }
+  }
   const size_t fixed = 1024 + a.resident_bytes + out_bytes + stats_bytes + sizeof(Barriers) + 64;
   const size_t budget = 220 * 1024;
   const size_t stage = a.a_slot_bytes + (a.resident ? 0 : (size_t)a.max_nr * a.b_tap_bytes);
@@ -766,14 +911,14 @@ int launch(const Plane* planes, const ColSpec* cols, int ncols, int B, int Hg, i
     // output tensor that GEMM pixel (y, x) maps to; overhanging pixels / channels are clipped by the store
     const uint64_t Wv = (uint64_t)((om.Wo - om.oax + om.osx - 1) / om.osx), Hv = (uint64_t)((om.Ho - om.oay + om.osy - 1) / om.osy);
     uint64_t dims[4] = {(uint64_t)Cout, Wv, Hv, (uint64_t)B};
-    uint32_t box[4] = {(uint32_t)a.BN, (uint32_t)a.tw, (uint32_t)a.th, 1};
+    uint32_t box[4] = {(uint32_t)(a.epi_tma == 2 ? 64 : a.BN), (uint32_t)a.tw, (uint32_t)a.th, 1};
     for (int k = 0; k < 2; ++k) {
       bf16* base = k == 0 ? a.out : a.out2;
       const long long ld = k == 0 ? a.out_ld : a.out2_ld;
       if (!base) continue;
       uint64_t str[3] = {(uint64_t)om.osx * ld * 2, (uint64_t)om.osy * om.Wo * ld * 2, (uint64_t)om.Ho * om.Wo * ld * 2};
       rc = dp_make_tmap_bf16(k == 0 ? &tm.o : &tm.o2, base + ((long long)om.oay * om.Wo + om.oax) * ld, 4, dims, str, box,
-                             nullptr, a.BN * 2);
+                             nullptr, a.epi_tma == 2 ? 128 : a.BN * 2);
       if (rc) return rc;
     }
   }

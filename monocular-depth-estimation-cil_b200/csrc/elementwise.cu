@@ -235,20 +235,23 @@ __global__ void __launch_bounds__(RED_TPB) chan_reduce_kernel(const bf16* __rest
       msh[j] = (MODE == 2 && mask_ss) ? __ldg(mask_ss + C + c8 * 8 + j) : 0.f;
     }
     const size_t pstep = (size_t)gridDim.x * lanes;
-    // two pixels per iteration: all loads of both are issued before any is consumed (bytes in flight, not occupancy,
-    // carry the bandwidth of this reduction)
-    for (size_t p = (size_t)blockIdx.x * lanes + pl; p < npix; p += 2 * pstep) {
-      const size_t pp[2] = {p, p + pstep};
-      uint4 rx[2], rg[2], rm[2];
+    // four pixels per iteration: all loads are issued before any is consumed (bytes in flight, not occupancy, carry
+    // the bandwidth of this reduction; the grid stays at two blocks per SM so the partials stay few)
+    constexpr int U = 4;
+    for (size_t p = (size_t)blockIdx.x * lanes + pl; p < npix; p += U * pstep) {
+      size_t pp[U];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < U; ++u) pp[u] = p + u * pstep;
+      uint4 rx[U], rg[U], rm[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
         const bool ok = pp[u] < npix;
         rx[u] = (ok && (MODE != 2 || x)) ? ld8(x + pp[u] * x_ld + c8 * 8) : make_uint4(0, 0, 0, 0);
         rg[u] = (ok && MODE == 2) ? ld8(dy + pp[u] * dy_ld + c8 * 8) : make_uint4(0, 0, 0, 0);
         rm[u] = (ok && MODE == 2 && mask) ? ld8(mask + pp[u] * m_ld + c8 * 8) : make_uint4(0, 0, 0, 0);
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < U; ++u) {
         if (pp[u] >= npix) continue;
         float xv[8], g[8];
         unpack8(rx[u], xv);
@@ -517,7 +520,7 @@ __global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restri
   out[i] = accumulate ? out[i] + (float)s : (float)s;
 }
 
-constexpr int kRedBlocks = 4 * kNumSMs;
+constexpr int kRedBlocks = 2 * kNumSMs;
 
 }  // namespace
 

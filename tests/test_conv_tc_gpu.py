@@ -121,7 +121,8 @@ def test_conv_tma_store_epilogue_all_operands(pkg, Cin, Cout, KS):
     assert bool((ob[..., :16] == 7.0).all()) and bool((ob[..., 16 + Cout:] == 7.0).all())
 
 
-@pytest.mark.parametrize("Cin,Cout,KS", [(32, 32, 3), (16, 16, 3), (64, 32, 1), (32, 16, 1)])
+@pytest.mark.parametrize("Cin,Cout,KS", [(32, 32, 3), (16, 16, 3), (64, 32, 1), (32, 16, 1), (32, 192, 1), (96, 576, 1),
+                                         (48, 288, 1), (136, 816, 1), (24, 144, 1), (128, 128, 3), (64, 128, 3)])
 def test_conv_bn_statistics_with_bias_small_n(pkg, Cin, Cout, KS):
     B, H, W = 3, 45, 52
     g = torch.Generator().manual_seed(Cin + 3 * Cout + KS)
