@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--profile-layers", action="store_true", help="print per-shape conv timings to stderr")
+    ap.add_argument("--no-side-wgrad", action="store_true", help="keep weight gradients on the main stream")
     ap.add_argument("--torch-encoder", action="store_true", help="run the EfficientNet-Lite3 trunk through PyTorch/cuDNN")
     return ap.parse_args()
 
@@ -118,8 +119,8 @@ def run_ours(a):
     import depth_b200
     from depth_b200 import distributed as D, ops
     from oracle import fixtures as fx                     # config object only (no oracle arithmetic on this arm)
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
-        os.environ["NCCL_DEBUG"] = "WARN"       # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+        os.environ.pop("NCCL_DEBUG")            # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     rank, local, world = D.init_from_env()
     assert world == a.gpus or world == 1 and a.gpus == 1, f"launch with torchrun --nproc-per-node {a.gpus}"
     torch.cuda.set_device(local)
@@ -133,7 +134,8 @@ def run_ours(a):
     xh, th = xh.pin_memory(), th.pin_memory()
     xd, td = xh.to(dev), th.to(dev)
     # The whole step (forward, combined_loss, backward, NCCL gradient all-reduce, AdamW) is one CUDA graph.
-    gstep = depth_b200.GraphedTrainStep(model, opt, cfg, xd, td, use_rgb=True, world=world, warmup=max(a.warmup, 3))
+    gstep = depth_b200.GraphedTrainStep(model, opt, cfg, xd, td, use_rgb=True, world=world, warmup=max(a.warmup, 3),
+                                        side_wgrad=not a.no_side_wgrad)
     red = gstep.red
 
     def step(x, t, read_loss):

@@ -14,9 +14,10 @@ from . import distributed as D
 
 class GraphedTrainStep:
     def __init__(self, model, optimizer, config, example_inputs, example_targets, use_rgb=True, world=None,
-                 warmup=3):
+                 warmup=3, side_wgrad=True):
         assert example_inputs.is_cuda and example_targets.is_cuda
         self.model, self.opt, self.cfg, self.use_rgb = model, optimizer, config, use_rgb
+        self.side_wgrad = side_wgrad
         self.x = example_inputs.clone()
         self.t = example_targets.clone()
         self.red = D.GradientAllReducer(model.parameters(), world)
@@ -38,7 +39,12 @@ class GraphedTrainStep:
         self.red.zero()
         pred = self.model(self.x).unsqueeze(1)
         total, out = util.combined_loss_device(pred, self.t, self.cfg, rgb=self.x if self.use_rgb else None)
-        total.backward()
+        ops.side_enable(self.side_wgrad)          # weight gradients overlap the data-gradient chain on a second stream
+        try:
+            total.backward()
+            ops.side_join()
+        finally:
+            ops.side_enable(False)
         self.red.reduce()
         self.opt.step()
         self.out = out

@@ -72,6 +72,53 @@ class _PackCache:
 PACKS = _PackCache()
 
 
+# --------------------------------------------------------------------------------------------------
+# weight gradients on a side stream (opt-in: graphs.GraphedTrainStep)
+# --------------------------------------------------------------------------------------------------
+class _Side:
+    """Weight gradients feed nothing but the optimizer, so inside a captured train step they are issued on a second
+    stream and overlap the (mostly bandwidth-bound) kernels of the data-gradient chain.  The operands are kept alive
+    until the next join so the caching allocator cannot hand their memory to the main stream while the side stream
+    still reads it; joins happen when more than `limit` bytes are pending and once after backward."""
+    enabled = False
+    stream = None
+    pending = []
+    pending_bytes = 0
+    limit = 6 << 30
+
+
+def side_enable(flag):
+    _Side.enabled = bool(flag)
+    if flag and _Side.stream is None and torch.cuda.is_available():
+        _Side.stream = torch.cuda.Stream()
+
+
+def side_join():
+    """main stream waits for every weight-gradient kernel issued so far; call after backward()."""
+    if _Side.stream is not None and (_Side.pending or _Side.pending_bytes):
+        torch.cuda.current_stream().wait_stream(_Side.stream)
+    _Side.pending.clear()
+    _Side.pending_bytes = 0
+
+
+def _on_side(fn, keep):
+    if not _Side.enabled:
+        return fn()
+    cur = torch.cuda.current_stream()
+    side = _Side.stream
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        out = fn()
+    for t in keep:
+        if t is not None:
+            _Side.pending.append(t)
+            _Side.pending_bytes += t.numel() * t.element_size()
+    _Side.pending_bytes += 1
+    if _Side.pending_bytes > _Side.limit:
+        side_join()
+    return out
+
+
 def _f32(p):
     if p is None:
         return None
@@ -230,7 +277,7 @@ class _ConvTC(torch.autograd.Function):
             dx = _nhwc(B, H, W, Cin, x.device)
             _conv_tc_launch(g, wd, Cin, KS, None, None, None, False, dx, None, False, None)
         if need[1]:
-            dw = _wgrad_tc(x, g, Cin, Cout, KS).to(weight.dtype)
+            dw = _on_side(lambda: _wgrad_tc(x, g, Cin, Cout, KS).to(weight.dtype), (x, g))
         if ctx.has[0] and need[2]:
             db = _colsum(g)
         dres = g if (ctx.has[1] and need[3]) else None
@@ -343,9 +390,9 @@ class _ConvStrided(torch.autograd.Function):
                 dx = _gather(g, PACKS.get(weight, 1, 0), None, Hi, Wi, I, KH, KW, stride, pad, True)
         if ctx.needs_input_grad[1]:
             if KH == KW and _tc_stride2_ok(KH, stride, pad, I, O):
-                dw = _wgrad_tc_s2(g, x, KH, pad).to(weight.dtype)
+                dw = _on_side(lambda: _wgrad_tc_s2(g, x, KH, pad).to(weight.dtype), (x, g))
             else:
-                dw = _wgrad_direct(g, x, KH, KW, stride, pad, 1).to(weight.dtype)      # [O][I][KH][KW]
+                dw = _on_side(lambda: _wgrad_direct(g, x, KH, KW, stride, pad, 1).to(weight.dtype), (x, g))  # [O][I][KH][KW]
         if has_bias and ctx.needs_input_grad[2]:
             db = _colsum(g)
         return dx, dw, db, None, None
@@ -383,9 +430,9 @@ class _ConvTransposed(torch.autograd.Function):
                 dx = _gather(g, PACKS.get(weight, 0, 0), None, Hi, Wi, I, KH, KW, stride, pad, False)
         if ctx.needs_input_grad[1]:
             if KH == KW and _tc_stride2_ok(KH, stride, pad, I, O):
-                dw = _wgrad_tc_s2(x, g, KH, pad).to(weight.dtype)
+                dw = _on_side(lambda: _wgrad_tc_s2(x, g, KH, pad).to(weight.dtype), (x, g))
             else:
-                dw = _wgrad_direct(x, g, KH, KW, stride, pad, 1).to(weight.dtype)      # [I][O][KH][KW]
+                dw = _on_side(lambda: _wgrad_direct(x, g, KH, KW, stride, pad, 1).to(weight.dtype), (x, g))  # [I][O][KH][KW]
         if has_bias and ctx.needs_input_grad[2]:
             db = _colsum(g)
         return dx, dw, db, None, None
@@ -465,12 +512,14 @@ class _DwConv(torch.autograd.Function):
                 L.check(lib.dp_dwconv_dgrad_s2(L.ptr(g), C, B, Ho, Wo, C, L.ptr(_dw_pack(weight)), K, pad_t, pad_l,
                                                L.ptr(dx), C, Hi, Wi, L.stream()))
         if ctx.needs_input_grad[1]:
-            nb = lib.dp_dwconv_wgrad_workspace(B, Ho, Wo, C, K)
-            ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
-            dw = torch.empty(C, 1, K, K, dtype=torch.float32, device=x.device)
-            L.check(lib.dp_dwconv_wgrad(L.ptr(x), _ld(x), B, Hi, Wi, C, L.ptr(g), C, Ho, Wo, K, stride, pad_t, pad_l,
-                                        L.ptr(dw), 0, L.ptr(ws), nb, L.stream()))
-            dw = dw.to(weight.dtype)
+            def wgrad():
+                nb = lib.dp_dwconv_wgrad_workspace(B, Ho, Wo, C, K)
+                ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
+                out = torch.empty(C, 1, K, K, dtype=torch.float32, device=x.device)
+                L.check(lib.dp_dwconv_wgrad(L.ptr(x), _ld(x), B, Hi, Wi, C, L.ptr(g), C, Ho, Wo, K, stride, pad_t, pad_l,
+                                            L.ptr(out), 0, L.ptr(ws), nb, L.stream()))
+                return out.to(weight.dtype)
+            dw = _on_side(wgrad, (x, g))
         return dx, dw, None, None, None, None, None, None
 
 
