@@ -101,14 +101,22 @@ def side_join():
     _Side.pending_bytes = 0
 
 
-def _on_side(fn, keep):
-    if not _Side.enabled:
+def _on_side(weight, fn, keep):
+    """weight gradient `fn()` of leaf parameter `weight`: on the main stream it is returned to autograd as usual; with
+    the side stream enabled it is computed AND accumulated into weight.grad there (autograd's own accumulation kernels
+    would run on the main stream and race with the side stream - e.g. the spatial_reduction convs that are applied
+    twice), and autograd gets None for it."""
+    if not _Side.enabled or not (weight.is_leaf and weight.requires_grad):
         return fn()
     cur = torch.cuda.current_stream()
     side = _Side.stream
     side.wait_stream(cur)
     with torch.cuda.stream(side):
-        out = fn()
+        dw = fn()
+        if weight.grad is None:
+            weight.grad = dw
+        else:
+            weight.grad.add_(dw)
     for t in keep:
         if t is not None:
             _Side.pending.append(t)
@@ -116,7 +124,7 @@ def _on_side(fn, keep):
     _Side.pending_bytes += 1
     if _Side.pending_bytes > _Side.limit:
         side_join()
-    return out
+    return None
 
 
 def _f32(p):
@@ -277,7 +285,7 @@ class _ConvTC(torch.autograd.Function):
             dx = _nhwc(B, H, W, Cin, x.device)
             _conv_tc_launch(g, wd, Cin, KS, None, None, None, False, dx, None, False, None)
         if need[1]:
-            dw = _on_side(lambda: _wgrad_tc(x, g, Cin, Cout, KS).to(weight.dtype), (x, g))
+            dw = _on_side(weight, lambda: _wgrad_tc(x, g, Cin, Cout, KS).to(weight.dtype), (x, g))
         if ctx.has[0] and need[2]:
             db = _colsum(g)
         dres = g if (ctx.has[1] and need[3]) else None
@@ -390,9 +398,9 @@ class _ConvStrided(torch.autograd.Function):
                 dx = _gather(g, PACKS.get(weight, 1, 0), None, Hi, Wi, I, KH, KW, stride, pad, True)
         if ctx.needs_input_grad[1]:
             if KH == KW and _tc_stride2_ok(KH, stride, pad, I, O):
-                dw = _on_side(lambda: _wgrad_tc_s2(g, x, KH, pad).to(weight.dtype), (x, g))
+                dw = _on_side(weight, lambda: _wgrad_tc_s2(g, x, KH, pad).to(weight.dtype), (x, g))
             else:
-                dw = _on_side(lambda: _wgrad_direct(g, x, KH, KW, stride, pad, 1).to(weight.dtype), (x, g))  # [O][I][KH][KW]
+                dw = _on_side(weight, lambda: _wgrad_direct(g, x, KH, KW, stride, pad, 1).to(weight.dtype), (x, g))  # [O][I][KH][KW]
         if has_bias and ctx.needs_input_grad[2]:
             db = _colsum(g)
         return dx, dw, db, None, None
@@ -430,9 +438,9 @@ class _ConvTransposed(torch.autograd.Function):
                 dx = _gather(g, PACKS.get(weight, 0, 0), None, Hi, Wi, I, KH, KW, stride, pad, False)
         if ctx.needs_input_grad[1]:
             if KH == KW and _tc_stride2_ok(KH, stride, pad, I, O):
-                dw = _on_side(lambda: _wgrad_tc_s2(x, g, KH, pad).to(weight.dtype), (x, g))
+                dw = _on_side(weight, lambda: _wgrad_tc_s2(x, g, KH, pad).to(weight.dtype), (x, g))
             else:
-                dw = _on_side(lambda: _wgrad_direct(x, g, KH, KW, stride, pad, 1).to(weight.dtype), (x, g))  # [I][O][KH][KW]
+                dw = _on_side(weight, lambda: _wgrad_direct(x, g, KH, KW, stride, pad, 1).to(weight.dtype), (x, g))  # [I][O][KH][KW]
         if has_bias and ctx.needs_input_grad[2]:
             db = _colsum(g)
         return dx, dw, db, None, None
@@ -519,7 +527,7 @@ class _DwConv(torch.autograd.Function):
                 L.check(lib.dp_dwconv_wgrad(L.ptr(x), _ld(x), B, Hi, Wi, C, L.ptr(g), C, Ho, Wo, K, stride, pad_t, pad_l,
                                             L.ptr(out), 0, L.ptr(ws), nb, L.stream()))
                 return out.to(weight.dtype)
-            dw = _on_side(wgrad, (x, g))
+            dw = _on_side(weight, wgrad, (x, g))
         return dx, dw, None, None, None, None, None, None
 
 
