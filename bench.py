@@ -306,10 +306,43 @@ def run_ours(a):
             ems = float(q.item())
         gpx = world * EB * H * W / (ems / 1e3) / 1e9
         gbs = EB * H * W * 8 / (ems / 1e3) / 1e9
+        # the MUFU (fast-math) variant of the same kernel: within the 1e-5 / 0.01 % contract, bandwidth-bound
+        for _ in range(3):
+            depth_b200.evaluation_metrics(pp, tt, fast_math=True)
+        barrier()
+        e0.record()
+        for _ in range(reps):
+            depth_b200.evaluation_metrics(pp, tt, fast_math=True)
+        e1.record()
+        barrier()
+        fms = e0.elapsed_time(e1) / reps
+        if world > 1:
+            q = torch.tensor([fms], device=dev)
+            dist.all_reduce(q, op=dist.ReduceOp.MAX)
+            fms = float(q.item())
+        fgbs = EB * H * W * 8 / (fms / 1e3) / 1e9
+        ev_traffic = None
+        try:      # DRAM bytes per launch from the committed ncu --set full capture of this kernel at this shape
+            with open(os.path.join(ROOT, "profiles", "ncu_eval_full_r1_v10.json")) as f:
+                cap = json.load(f)["launches"][0]
+            if EB == 650:
+                ev_traffic = round(float(cap["dram__bytes_read.sum [Gbyte]"]) * 1e9 + float(cap["dram__bytes_write.sum [Mbyte]"]) * 1e6)
+        except Exception:
+            ev_traffic = None
         ev = {"metric": "eval Gpx/s (fused SI-RMSE + AbsRel + 3x delta, evaluation.py:157-166)", "value": round(gpx, 2),
               "unit": "Gpx/s", "batch_per_gpu": EB, "inputs": f"{EB * H * W * 8 / 1e6:.0f} MB per GPU per call (> 126 MB L2)",
+              "arithmetic": "IEEE logf / division (the reference's arithmetic): issue-bound (ncu: 86 % of issue slots "
+                            "active), not bandwidth-bound",
               "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": hbm, "unit": "GB/s",
-                           "frac": round(gbs / hbm, 4), "algorithmic_bytes_per_px": 8, "traffic": None}}
+                           "frac": round(gbs / hbm, 4), "algorithmic_bytes_per_px": 8,
+                           "algorithmic_bytes_per_launch": EB * H * W * 8, "traffic": ev_traffic,
+                           "traffic_source": "profiles/ncu_eval_full_r1_v10.json: the delta sweep misses L2 (86 clusters x "
+                                             "2 MB in flight), so DRAM traffic is 2x algorithmic"},
+              "fast_math": {"value": round(world * EB * H * W / (fms / 1e3) / 1e9, 2), "unit": "Gpx/s",
+                            "arithmetic": "MUFU lg2 / rcp variant (evaluation_metrics(fast_math=True)); within 1e-5 relative / "
+                                          "0.01 % of pixels of the exact path (tests/test_loss_gpu.py)",
+                            "roofline": {"bound": "hbm", "achieved": round(fgbs, 1), "peak": hbm, "unit": "GB/s",
+                                         "frac": round(fgbs / hbm, 4)}}}
 
     cpu = None
     if rank == 0 and not a.no_cpu_baseline:

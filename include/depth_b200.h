@@ -117,9 +117,12 @@ int dp_metrics_combine(const double* moments, const unsigned long long* counts, 
  * accumulates the SI / AbsRel moments, exchanges them through distributed shared memory and counts the scale-aligned
  * delta thresholds (util.py:183-207) on a second, L2-resident sweep; then the scalar combine.
  * thresholds: HOST pointer.  moments: device double[B][DP_NMOM] (S1, S2, AR filled).  counts: device u64[B][nthr].
- * out: device float[2+nthr] = SI-RMSE, AbsRel, delta_k (batch means). */
+ * out: device float[2+nthr] = SI-RMSE, AbsRel, delta_k (batch means).
+ * fast_math = 0: IEEE logf / division (the reference's arithmetic); 1: MUFU lg2 / rcp (within ~1e-6 relative of the exact
+ * path; bandwidth-bound instead of issue-bound). */
 int dp_eval_metrics(const float* pred, const float* target, int B, int H, int W, const float* thresholds, int nthr,
-                    float eps, double* moments, unsigned long long* counts, float* out, cudaStream_t stream);
+                    float eps, int fast_math, double* moments, unsigned long long* counts, float* out,
+                    cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Convolutions (NHWC bf16 activations, fp32 accumulation in TMEM)

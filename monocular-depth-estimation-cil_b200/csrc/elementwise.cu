@@ -179,6 +179,25 @@ __global__ void resize_bwd_kernel(const bf16* __restrict__ gout, long long g_ld,
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     const bf16* g = gout + (size_t)b * Ho * Wo * g_ld + c8 * 8;
+    // column weights once per input pixel (the candidate window is at most a few outputs wide); wide windows
+    // (strong down-scaling) fall back to recomputing them per row
+    constexpr int NW = 8;
+    float wxs[NW];
+    const bool small_win = ox_hi - ox_lo < NW;
+#pragma unroll
+    for (int k = 0; k < NW; ++k) {
+      const int ox = ox_lo + k;
+      float wx = 0.f;
+      if (small_win && ox <= ox_hi) {
+        const float fx = src_coord(ox, sx, align);
+        const int x0 = (int)fx;
+        const int x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
+        const float lx = fx - x0;
+        if (x0 == ix) wx += 1.f - lx;
+        if (x1 == ix) wx += lx;
+      }
+      wxs[k] = wx;
+    }
     for (int oy = oy_lo; oy <= oy_hi; ++oy) {
       const float fy = src_coord(oy, sy, align);
       const int y0 = (int)fy;
@@ -188,6 +207,18 @@ __global__ void resize_bwd_kernel(const bf16* __restrict__ gout, long long g_ld,
       if (y0 == iy) wy += 1.f - ly;
       if (y1 == iy) wy += ly;
       if (wy == 0.f) continue;
+      if (small_win) {
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+          if (wxs[k] == 0.f) continue;
+          float v[8];
+          unpack8(ld8(g + ((size_t)oy * Wo + ox_lo + k) * g_ld), v);
+          const float w = wy * wxs[k];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += w * v[j];
+        }
+        continue;
+      }
       for (int ox = ox_lo; ox <= ox_hi; ++ox) {
         const float fx = src_coord(ox, sx, align);
         const int x0 = (int)fx;

@@ -485,7 +485,10 @@ __device__ __forceinline__ unsigned long long ld_dsmem_u64(const unsigned long l
   return v;
 }
 
-template <int VEC>
+// FAST = false: IEEE logf / division, the arithmetic of the reference's torch ops (default).
+// FAST = true : MUFU lg2 / rcp (2^-22-class errors: SI-RMSE / AbsRel within ~1e-6 relative of the exact path, delta counts
+//               within a few pixels per million) - the variant that is bandwidth- rather than issue-bound.
+template <int VEC, bool FAST, int NT>      // NT: compile-time threshold count (3 = evaluation.py's set), 0 = a.nthr at run time
 __global__ void __cluster_dims__(kEvalCluster, 1, 1) __launch_bounds__(TPB) eval_fused_kernel(EvalArgs a) {
   const int b = blockIdx.x / kEvalCluster;
   const uint32_t rank = cluster_ctarank();
@@ -503,26 +506,43 @@ __global__ void __cluster_dims__(kEvalCluster, 1, 1) __launch_bounds__(TPB) eval
 
   // ---- sweep 1: moments ----
   double acc[3] = {0.0, 0.0, 0.0};
-#pragma unroll 2
-  for (long long i = i0 + threadIdx.x; i < i1; i += TPB) {
-    float pv[VEC], tv[VEC];
-    if (VEC == 4) {
-      const float4 p4 = ldg4(P + i * 4), t4 = ldg4(T + i * 4);
-      pv[0] = p4.x; pv[1] = p4.y; pv[2] = p4.z; pv[3] = p4.w;
-      tv[0] = t4.x; tv[1] = t4.y; tv[2] = t4.z; tv[3] = t4.w;
-    } else {
-      pv[0] = __ldg(P + i);
-      tv[0] = __ldg(T + i);
-    }
-    float s1 = 0.f, s2 = 0.f, ar = 0.f;
+  constexpr int U = 1;     // items per round (more in flight costs occupancy: measured slower)
+  for (long long i = i0 + threadIdx.x; i < i1; i += (long long)U * TPB) {
+    float pv[U][VEC], tv[U][VEC];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      const float d = logf(pv[j] + eps) - logf(tv[j] + eps);   // util.py:143
-      s1 += d;
-      s2 += d * d;
-      ar += fabsf(tv[j] - pv[j]) / (tv[j] + 1e-6f);            // util.py:218
+    for (int u = 0; u < U; ++u) {
+      const long long iu = i + (long long)u * TPB;
+      if (iu < i1) {
+        if (VEC == 4) {
+          const float4 p4 = ldg4(P + iu * 4), t4 = ldg4(T + iu * 4);
+          pv[u][0] = p4.x; pv[u][1] = p4.y; pv[u][2] = p4.z; pv[u][3] = p4.w;
+          tv[u][0] = t4.x; tv[u][1] = t4.y; tv[u][2] = t4.z; tv[u][3] = t4.w;
+        } else {
+          pv[u][0] = __ldg(P + iu);
+          tv[u][0] = __ldg(T + iu);
+        }
+      }
     }
-    acc[0] += s1; acc[1] += s2; acc[2] += ar;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i + (long long)u * TPB >= i1) continue;
+      float s1 = 0.f, s2 = 0.f, ar = 0.f;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        float d, q;
+        if (FAST) {
+          d = (__log2f(pv[u][j] + eps) - __log2f(tv[u][j] + eps)) * 0.69314718055994531f;
+          q = __fdividef(fabsf(tv[u][j] - pv[u][j]), tv[u][j] + 1e-6f);
+        } else {
+          d = logf(pv[u][j] + eps) - logf(tv[u][j] + eps);             // util.py:143
+          q = fabsf(tv[u][j] - pv[u][j]) / (tv[u][j] + 1e-6f);         // util.py:218
+        }
+        s1 += d;
+        s2 += d * d;
+        ar += q;
+      }
+      acc[0] += s1; acc[1] += s2; acc[2] += ar;
+    }
   }
   block_sum<3>(acc, red);
   if (threadIdx.x == 0) { s_mom[0] = acc[0]; s_mom[1] = acc[1]; s_mom[2] = acc[2]; }
@@ -535,25 +555,40 @@ __global__ void __cluster_dims__(kEvalCluster, 1, 1) __launch_bounds__(TPB) eval
   unsigned cnt[DP_MAX_THR];
 #pragma unroll
   for (int k = 0; k < DP_MAX_THR; ++k) cnt[k] = 0;
-#pragma unroll 2
-  for (long long i = i0 + threadIdx.x; i < i1; i += TPB) {
-    float pv[VEC], tv[VEC];
-    if (VEC == 4) {
-      const float4 p4 = ldg4(P + i * 4), t4 = ldg4(T + i * 4);
-      pv[0] = p4.x; pv[1] = p4.y; pv[2] = p4.z; pv[3] = p4.w;
-      tv[0] = t4.x; tv[1] = t4.y; tv[2] = t4.z; tv[3] = t4.w;
-    } else {
-      pv[0] = __ldg(P + i);
-      tv[0] = __ldg(T + i);
+  for (long long i = i0 + threadIdx.x; i < i1; i += (long long)U * TPB) {
+    float pv[U][VEC], tv[U][VEC];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long iu = i + (long long)u * TPB;
+      if (iu < i1) {
+        if (VEC == 4) {
+          const float4 p4 = ldg4(P + iu * 4), t4 = ldg4(T + iu * 4);
+          pv[u][0] = p4.x; pv[u][1] = p4.y; pv[u][2] = p4.z; pv[u][3] = p4.w;
+          tv[u][0] = t4.x; tv[u][1] = t4.y; tv[u][2] = t4.z; tv[u][3] = t4.w;
+        } else {
+          pv[u][0] = __ldg(P + iu);
+          tv[u][0] = __ldg(T + iu);
+        }
+      }
     }
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      const float al = pv[j] * s;
-      const float r1 = al / tv[j];          // util.py:204: no epsilon in the divisions
-      const float r2 = tv[j] / al;
+    for (int u = 0; u < U; ++u) {
+      if (i + (long long)u * TPB >= i1) continue;
 #pragma unroll
-      for (int k = 0; k < DP_MAX_THR; ++k)
-        if (k < a.nthr && r1 < a.thr[k] && r2 < a.thr[k]) cnt[k]++;   // NaN / inf compare false, as torch.max + lt
+      for (int j = 0; j < VEC; ++j) {
+        const float al = pv[u][j] * s;
+        float r1, r2;
+        if (FAST) {   // plain reciprocal-multiply: 0/0, x/0 and inf cases still compare false below
+          r1 = al * __frcp_rn(tv[u][j]);
+          r2 = tv[u][j] * __frcp_rn(al);
+        } else {
+          r1 = al / tv[u][j];          // util.py:204: no epsilon in the divisions
+          r2 = tv[u][j] / al;
+        }
+#pragma unroll
+        for (int k = 0; k < (NT ? NT : DP_MAX_THR); ++k)
+          if ((NT || k < a.nthr) && r1 < a.thr[k] && r2 < a.thr[k]) cnt[k]++;   // NaN / inf compare false, as torch.max + lt
+      }
     }
   }
   __shared__ unsigned sc[DP_MAX_THR][TPB / 32];
@@ -719,7 +754,8 @@ int dp_metrics_combine(const double* moments, const unsigned long long* counts, 
 /* evaluation.py:157-166 in two launches: the fused cluster kernel (moments + aligned delta counts, 8 B/px of HBM
  * traffic) and the scalar combine.  out[0]=SI-RMSE, out[1]=AbsRel, out[2+k]=delta_k (batch means). */
 int dp_eval_metrics(const float* pred, const float* target, int B, int H, int W, const float* thresholds, int nthr,
-                    float eps, double* moments, unsigned long long* counts, float* out, cudaStream_t stream) {
+                    float eps, int fast_math, double* moments, unsigned long long* counts, float* out,
+                    cudaStream_t stream) {
   DP_CHECK_ARG(pred && target && thresholds && moments && counts && out, "dp_eval_metrics: null pointer");
   DP_CHECK_ARG(B > 0 && H > 0 && W > 0, "dp_eval_metrics: bad shape %d %d %d", B, H, W);
   DP_CHECK_ARG(nthr >= 1 && nthr <= DP_MAX_THR, "dp_eval_metrics: nthr %d out of [1,%d]", nthr, DP_MAX_THR);
@@ -728,8 +764,18 @@ int dp_eval_metrics(const float* pred, const float* target, int B, int H, int W,
   for (int k = 0; k < DP_MAX_THR; ++k) a.thr[k] = k < nthr ? thresholds[k] : 0.f;
   a.moments = moments; a.counts = counts;
   const bool vec = (a.n % 4 == 0) && aligned16(pred) && aligned16(target);
-  if (vec) eval_fused_kernel<4><<<B * kEvalCluster, TPB, 0, stream>>>(a);
-  else eval_fused_kernel<1><<<B * kEvalCluster, TPB, 0, stream>>>(a);
+  const dim3 grid(B * kEvalCluster);
+#define DP_EVAL_LAUNCH(V, F)                                                        \
+  do {                                                                              \
+    if (nthr == 3) eval_fused_kernel<V, F, 3><<<grid, TPB, 0, stream>>>(a);         \
+    else if (nthr == 1) eval_fused_kernel<V, F, 1><<<grid, TPB, 0, stream>>>(a);    \
+    else eval_fused_kernel<V, F, 0><<<grid, TPB, 0, stream>>>(a);                   \
+  } while (0)
+  if (vec && fast_math) DP_EVAL_LAUNCH(4, true);
+  else if (vec) DP_EVAL_LAUNCH(4, false);
+  else if (fast_math) DP_EVAL_LAUNCH(1, true);
+  else DP_EVAL_LAUNCH(1, false);
+#undef DP_EVAL_LAUNCH
   DP_CHECK_LAUNCH("eval_fused_kernel");
   metrics_combine_kernel<<<1, 32, 0, stream>>>(moments, counts, B, H, W, nthr, out);
   DP_CHECK_LAUNCH("metrics_combine_kernel");

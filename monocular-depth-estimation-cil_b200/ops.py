@@ -262,6 +262,7 @@ class _ConvTC(torch.autograd.Function):
         ctx.relu, ctx.dual, ctx.KS = relu, dual, KS
         ctx.save_for_backward(x, weight, out if relu else None, out2 if dual else None)
         ctx.has = (bias is not None, res is not None, res2 is not None)
+        ctx.bias_ref = weakref.ref(bias) if (bias is not None and bias.is_leaf and bias.requires_grad) else None
         ctx.mark_non_differentiable(*([stats] if stats is not None else []))
         return out, out2, stats
 
@@ -287,7 +288,8 @@ class _ConvTC(torch.autograd.Function):
         if need[1]:
             dw = _on_side(weight, lambda: _wgrad_tc(x, g, Cin, Cout, KS).to(weight.dtype), (x, g))
         if ctx.has[0] and need[2]:
-            db = _colsum(g)
+            bias = ctx.bias_ref() if ctx.bias_ref is not None else None
+            db = _on_side(bias, lambda: _colsum(g), (g,)) if bias is not None else _colsum(g)
         dres = g if (ctx.has[1] and need[3]) else None
         dres2 = g if (ctx.has[2] and need[4]) else None
         return dx, dw, db, dres, dres2, None, None, None

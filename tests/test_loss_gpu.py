@@ -152,3 +152,19 @@ def test_fused_eval_counts_match_two_pass_counts(pkg, B, H, W):
     assert torch.allclose(out[2:], want, rtol=0, atol=1e-7), (out[2:], want)
     assert abs(out[0].item() - pkg.scale_invariant_loss(p, t, sqroot=True).item()) <= 1e-6
     assert abs(out[1].item() - pkg.absolute_relative_error(p, t).item()) <= 1e-6 * out[1].item()
+
+
+def test_fused_eval_fast_math_within_contract(pkg):
+    """MUFU variant of the fused evaluation kernel: SI-RMSE / AbsRel within 1e-5 relative of the exact path and the
+    delta fractions within 0.01 % of pixels (the north-star tolerances; measured differences are ~1e-7 / a few ppm)."""
+    B, H, W = 8, 448, 576
+    g = torch.Generator().manual_seed(77)
+    t = (torch.rand(B, 1, H, W, generator=g) * 9.9 + 0.1).cuda()
+    p = (t.cpu() * torch.exp(0.1 * torch.randn(B, 1, H, W, generator=g)) * 1.3).cuda()
+    p[:, :, 100:140, 200:300] = 0.0
+    thr = [1.05, 1.05 ** 2, 1.05 ** 3]
+    exact = pkg.evaluation_metrics(p, t, thresholds=thr).double().cpu()
+    fast = pkg.evaluation_metrics(p, t, thresholds=thr, fast_math=True).double().cpu()
+    assert abs(fast[0] - exact[0]) <= 1e-5 * abs(exact[0])
+    assert abs(fast[1] - exact[1]) <= 1e-5 * abs(exact[1])
+    assert float((fast[2:] - exact[2:]).abs().max()) <= 1e-4

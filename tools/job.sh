@@ -1,10 +1,2 @@
-for f in "--no-side-wgrad" "--no-side-wgrad" "" ""; do
-python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-eval $f > gpurun_out/b.json 2> gpurun_out/b.err || tail -5 gpurun_out/b.err
-python - <<PY
-import json
-for l in open('gpurun_out/b.json'):
-    if l.startswith('{'):
-        d=json.loads(l)
-        print("$f", {k:d[k] for k in ['value','ms_per_step','loss']})
-PY
-done
+python tools/ncu_eval.py > gpurun_out/plain_eval.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:eval_fused_kernel -s 4 -c 2 -o gpurun_out/prof_eval_r1_v10 python tools/ncu_eval.py > gpurun_out/ncu_eval.log 2>&1
+tail -2 gpurun_out/ncu_eval.log
