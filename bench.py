@@ -90,7 +90,7 @@ def build_model(device, fused_encoder=True):
     import depth_b200  # noqa: F401
     from depth_b200 import standins
     from depth_b200.network import blocks, midas_semantics
-    from oracle import fixtures as fx
+    from depth_b200 import config as fx
     blocks.hub_load = standins.hub_load_standin
     torch.manual_seed(0)
     import contextlib, io
@@ -118,7 +118,7 @@ def run_ours(a):
     import torch.distributed as dist
     import depth_b200
     from depth_b200 import distributed as D, ops
-    from oracle import fixtures as fx                     # config object only (no oracle arithmetic on this arm)
+    from depth_b200 import config as fx                   # the product arm never imports oracle/
     if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
         os.environ.pop("NCCL_DEBUG")            # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     rank, local, world = D.init_from_env()

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
 import depth_b200
-from oracle import fixtures as fx
+from depth_b200 import config as fx
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=32)
