@@ -155,7 +155,7 @@ def test_full_model_train_step_parity(pkg, which):
     gradient is zero-mean by construction) is ill-conditioned for ANY bf16 pipeline, so the tolerance is
     calibrated in the test itself: the same oracle modules are also run under PyTorch's stock bf16 autocast on
     the GPU, and our drift from fp32 must stay below that of stock autocast (measured: ~2x better; see
-    tools/calib_autocast.py).  Hard checks: the well-conditioned last layers within 8e-2, the unused-parameter
+    tests/calib_autocast.py).  Hard checks: the well-conditioned last layers within 8e-2, the unused-parameter
     grad=None pattern, BN buffers incl. the double update of the shared spatial_reduction BN, eval-mode forward."""
     import copy
     ora, prod = _full(pkg, which)
