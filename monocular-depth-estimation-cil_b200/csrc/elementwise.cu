@@ -336,19 +336,20 @@ __global__ void __launch_bounds__(RED_TPB) chan_reduce_kernel(const bf16* __rest
 // BatchNorm2d finalize (train): partial[nparts][2][C] (sum, sumsq over `count` values per channel) ->
 //   scale_shift[0][C] = gamma*invstd, [1][C] = beta - mean*gamma*invstd, save[0][C]=mean, save[1][C]=invstd;
 //   running stats updated with momentum (unbiased variance), num_batches_tracked += 1.
-__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partial, int nparts, int C, double count,
+constexpr int kPartLanes = 32;   // partial-sum lanes per channel in the finalize / fold kernels (block = 32 x kPartLanes)
+__global__ void __launch_bounds__(32 * kPartLanes) bn_finalize_kernel(const float* __restrict__ partial, int nparts, int C, double count,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                                    long long* __restrict__ num_batches, float* __restrict__ scale_shift,
                                    float* __restrict__ save) {
-  // block = 32 channels x 8 partial lanes: coalesced 128-byte rows of the partials, fixed-order fp64 folding
-  __shared__ double s_s[8][32], s_q[8][32];
+  // block = 32 channels x kPartLanes partial lanes: coalesced 128-byte rows of the partials, fixed-order fp64 folding
+  __shared__ double s_s[kPartLanes][32], s_q[kPartLanes][32];
   const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches) *num_batches += 1;
   double s = 0.0, q = 0.0;
   if (c < C) {
-    for (int p = pl; p < nparts; p += 8) {
+    for (int p = pl; p < nparts; p += kPartLanes) {
       s += (double)partial[((size_t)p * 2 + 0) * C + c];
       q += (double)partial[((size_t)p * 2 + 1) * C + c];
     }
@@ -359,7 +360,7 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
   if (pl != 0 || c >= C) return;
   s = 0.0; q = 0.0;
 #pragma unroll
-  for (int l = 0; l < 8; ++l) { s += s_s[l][cl]; q += s_q[l][cl]; }
+  for (int l = 0; l < kPartLanes; ++l) { s += s_s[l][cl]; q += s_q[l][cl]; }
   const double mean = s / count;
   double var = q / count - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -531,23 +532,23 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
   }
 }
 
-__global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ partial, int nparts, int rows, int C,
+__global__ void __launch_bounds__(32 * kPartLanes) sum_partials_kernel(const float* __restrict__ partial, int nparts, int rows, int C,
                                     float* __restrict__ out, int accumulate) {
-  // block = 32 columns x 8 partial lanes over the flattened [rows*C] vector; partial stride is 2*C per part
-  __shared__ double s_s[8][32];
+  // block = 32 columns x kPartLanes partial lanes over the flattened [rows*C] vector; partial stride is 2*C per part
+  __shared__ double s_s[kPartLanes][32];
   const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + cl;
   double s = 0.0;
   if (i < rows * C) {
     const int which = i / C, c = i - which * C;
-    for (int p = pl; p < nparts; p += 8) s += (double)partial[((size_t)p * 2 + which) * C + c];
+    for (int p = pl; p < nparts; p += kPartLanes) s += (double)partial[((size_t)p * 2 + which) * C + c];
   }
   s_s[pl][cl] = s;
   __syncthreads();
   if (pl != 0 || i >= rows * C) return;
   s = 0.0;
 #pragma unroll
-  for (int l = 0; l < 8; ++l) s += s_s[l][cl];
+  for (int l = 0; l < kPartLanes; ++l) s += s_s[l][cl];
   out[i] = accumulate ? out[i] + (float)s : (float)s;
 }
 
@@ -645,7 +646,7 @@ int dp_chan_reduce(int mode, const void* x, long long x_ld, const void* dy, long
 
 int dp_sum_partials(const float* partial, int nparts, int rows, int C, float* out, int accumulate, cudaStream_t stream) {
   DP_CHECK_ARG(partial && out && rows >= 1 && rows <= 2, "dp_sum_partials: bad arguments");
-  sum_partials_kernel<<<dp::ceil_div(rows * C, 32), 256, 0, stream>>>(partial, nparts, rows, C, out, accumulate);
+  sum_partials_kernel<<<dp::ceil_div(rows * C, 32), 32 * kPartLanes, 0, stream>>>(partial, nparts, rows, C, out, accumulate);
   DP_CHECK_LAUNCH("sum_partials_kernel");
   return DP_OK;
 }
@@ -654,7 +655,7 @@ int dp_bn_finalize(const float* partial, int nparts, int C, double count, const 
                    float eps, float momentum, float* running_mean, float* running_var, long long* num_batches_tracked,
                    float* scale_shift, float* save_mean_invstd, cudaStream_t stream) {
   DP_CHECK_ARG(partial && scale_shift && save_mean_invstd && C > 0 && count > 0, "dp_bn_finalize: bad arguments");
-  bn_finalize_kernel<<<dp::ceil_div(C, 32), 256, 0, stream>>>(partial, nparts, C, count, gamma, beta, eps, momentum,
+  bn_finalize_kernel<<<dp::ceil_div(C, 32), 32 * kPartLanes, 0, stream>>>(partial, nparts, C, count, gamma, beta, eps, momentum,
                                                                running_mean, running_var, num_batches_tracked,
                                                                scale_shift, save_mean_invstd);
   DP_CHECK_LAUNCH("bn_finalize_kernel");

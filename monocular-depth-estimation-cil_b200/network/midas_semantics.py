@@ -11,7 +11,7 @@ from .midas_net_custom import MidasNet_small
 
 class CrossAttention(nn.Module):
     """reference midas_semantics.py:14-127.  The window loop is evaluated in its exact last-writer closed form
-    (csrc/attention.cu); the strided / transposed convs run as gather-form kernels; BatchNorm is applied per call,
+    (csrc/attention.cu); the stride-2 / transposed convs run on tcgen05 (parity planes / output phases); BatchNorm is applied per call,
     so the shared spatial_reduction BN is updated twice per forward exactly as in the reference."""
 
     def __init__(self, dim, num_heads=8, qkv_bias=False, window_size=16):
@@ -91,15 +91,18 @@ class ResidualBlock(nn.Module):
 
     def fused(self, x):
         tr = self.training
-        r = ops.conv_tc(x, self.conv1.weight, None, stats=tr)
-        c1, st1 = r if tr else (r, None)
+        cs = sts = None
+        if len(self.shortcut) != 0:
+            # conv1 and the 1x1 shortcut read the same tensor: one op, so their data gradients are chained in backward
+            c1, st1, cs, sts = ops.conv_tc_pair(x, self.conv1.weight, self.shortcut[0].weight, stats=tr)
+        else:
+            r = ops.conv_tc(x, self.conv1.weight, None, stats=tr)
+            c1, st1 = r if tr else (r, None)
         a1 = ops.bn_act(self.bn1, c1, st1, relu=True)
         r = ops.conv_tc(a1, self.conv2.weight, None, stats=tr)
         c2, st2 = r if tr else (r, None)
         if len(self.shortcut) == 0:
             return ops.bn_act(self.bn2, c2, st2, relu=True, res=x)
-        r = ops.conv_tc(x, self.shortcut[0].weight, None, stats=tr)
-        cs, sts = r if tr else (r, None)
         return ops.bn_act(self.bn2, c2, st2, relu=True, bn2=self.shortcut[1], c2=cs, stats2=sts)
 
     def forward(self, x):

@@ -295,6 +295,52 @@ class _ConvTC(torch.autograd.Function):
         return dx, dw, db, dres, dres2, None, None, None
 
 
+class _ConvPair(torch.autograd.Function):
+    """Two bias-free convolutions of the SAME input (ResidualBlock conv1 + its 1x1 shortcut, midas_semantics.py:132-143):
+    y1 = conv(x, w1), y2 = conv(x, w2), each with optional BN partials.  The backward chains the two data gradients
+    through the epilogue's residual input (dx = dgrad2(g2) + dgrad1(g1) in one pass) instead of leaving the sum of two
+    full-resolution tensors to a separate elementwise kernel."""
+
+    @staticmethod
+    def forward(ctx, x, w1, w2, want_stats):
+        B, H, W, _ = x.shape
+        outs = []
+        for w in (w1, w2):
+            Cout, Cin, KS, _ = w.shape
+            out = _nhwc(B, H, W, Cout, x.device)
+            st = None
+            if want_stats:
+                st = torch.empty(L.lib().dp_conv2d_tc_grid(B, H, W, Cin, Cout, KS), 2, Cout, dtype=torch.float32,
+                                 device=x.device)
+            _conv_tc_launch(x, PACKS.get(w, 0, 0), Cout, KS, None, None, None, False, out, None, False, st)
+            outs += [out, st]
+        ctx.save_for_backward(x, w1, w2)
+        ctx.mark_non_differentiable(*[t for t in (outs[1], outs[3]) if t is not None])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, g1, _s1, g2, _s2):
+        x, w1, w2 = ctx.saved_tensors
+        B, H, W, Cin = x.shape
+        g1, g2 = _dense(g1), _dense(g2)
+        dx = dw1 = dw2 = None
+        if ctx.needs_input_grad[0]:
+            t = _nhwc(B, H, W, Cin, x.device)
+            _conv_tc_launch(g1, PACKS.get(w1, 1, 1), Cin, w1.shape[2], None, None, None, False, t, None, False, None)
+            dx = _nhwc(B, H, W, Cin, x.device)
+            _conv_tc_launch(g2, PACKS.get(w2, 1, 1), Cin, w2.shape[2], None, t, None, False, dx, None, False, None)
+        if ctx.needs_input_grad[1]:
+            dw1 = _on_side(w1, lambda: _wgrad_tc(x, g1, Cin, w1.shape[0], w1.shape[2]).to(w1.dtype), (x, g1))
+        if ctx.needs_input_grad[2]:
+            dw2 = _on_side(w2, lambda: _wgrad_tc(x, g2, Cin, w2.shape[0], w2.shape[2]).to(w2.dtype), (x, g2))
+        return dx, dw1, dw2, None
+
+
+def conv_tc_pair(x, w1, w2, stats=False):
+    """(y1, stats1, y2, stats2) of two bias-free convolutions sharing their input (stats are None unless requested)."""
+    return _ConvPair.apply(x, w1, w2, stats)
+
+
 def conv_tc(x, weight, bias=None, res=None, res2=None, relu=False, dual=False, stats=False):
     """3x3/s1/p1 or 1x1 conv on tcgen05.  Returns y, or (y, relu(y)) when dual, with BN partials appended when stats."""
     y, y2, st = _ConvTC.apply(x, weight, bias, res, res2, relu, dual, stats)
