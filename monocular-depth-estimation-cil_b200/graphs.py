@@ -22,6 +22,10 @@ class GraphedTrainStep:
         self.t = example_targets.clone()
         self.red = D.GradientAllReducer(model.parameters(), world)
         self.out = None
+        self._copy = self._sx = self._st = self._consumed = None
+        self._step = 0
+        self._hout = [torch.empty(8, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._done = [torch.cuda.Event(), torch.cuda.Event()]
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -51,18 +55,47 @@ class GraphedTrainStep:
 
     def __call__(self, inputs=None, targets=None):
         """one optimisation step; inputs/targets may be (pinned) host or device tensors, or None to reuse the static
-        batch.  Returns the device tensor of loss scalars (index with depth_b200._lib.L_*); no host sync."""
-        if inputs is not None:
-            self.x.copy_(inputs, non_blocking=True)
-        if targets is not None:
-            self.t.copy_(targets, non_blocking=True)
+        batch.  Returns the device tensor of loss scalars (index with depth_b200._lib.L_*); no host sync.
+
+        Host batches travel on a copy stream into a staging buffer, so the H2D transfer of step i overlaps the graph
+        replay of step i-1 (the caller is never blocked); a device-to-device copy then refreshes the graph's static
+        inputs.  The loss scalars of every step are copied to pinned host memory asynchronously (`loss_dict`)."""
+        main = torch.cuda.current_stream()
+        if inputs is not None or targets is not None:
+            if self._copy is None:
+                self._copy = torch.cuda.Stream()
+                self._sx, self._st = torch.empty_like(self.x), torch.empty_like(self.t)
+                self._consumed = torch.cuda.Event()
+                self._consumed.record(main)
+            cs = self._copy
+            cs.wait_event(self._consumed)                 # the previous step has finished reading the staging buffers
+            with torch.cuda.stream(cs):
+                if inputs is not None:
+                    self._sx.copy_(inputs, non_blocking=True)
+                if targets is not None:
+                    self._st.copy_(targets, non_blocking=True)
+            main.wait_stream(cs)
+            if inputs is not None:
+                self.x.copy_(self._sx, non_blocking=True)
+            if targets is not None:
+                self.t.copy_(self._st, non_blocking=True)
+            self._consumed.record(main)
         self.graph.replay()
+        slot = self._step & 1
+        self._hout[slot].copy_(self.out, non_blocking=True)
+        self._done[slot].record(main)
+        self._step += 1
         return self.out
 
-    def loss_dict(self):
-        """one device->host read of the eight loss scalars of the last step (main.py:85-88 needs four of them)."""
+    def loss_dict(self, lag=0):
+        """the loss scalars of the last step (lag=0) or of the one before it (lag=1: lets the host run one step ahead of
+        the device, which is what overlaps the next batch's H2D copy with the current replay); waits only for that
+        step's device->host copy (main.py:85-88 needs four of the scalars)."""
         from . import _lib as L
-        h = self.out.tolist()
+        assert lag in (0, 1) and self._step > lag
+        slot = (self._step - 1 - lag) & 1
+        self._done[slot].synchronize()
+        h = self._hout[slot].tolist()
         return {"total": h[L.L_TOTAL], "si_loss": h[L.L_SI], "silog_loss": h[L.L_SILOG], "grad_loss": h[L.L_GRAD],
                 "edge_loss": h[L.L_EDGE]}
 

@@ -96,8 +96,8 @@ class ResidualBlock(nn.Module):
             # conv1 and the 1x1 shortcut read the same tensor: one op, so their data gradients are chained in backward
             c1, st1, cs, sts = ops.conv_tc_pair(x, self.conv1.weight, self.shortcut[0].weight, stats=tr)
         else:
-            r = ops.conv_tc(x, self.conv1.weight, None, stats=tr)
-            c1, st1 = r if tr else (r, None)
+            # identity shortcut: x re-joins after bn2; its two gradients meet in conv1's backward node
+            c1, st1, x = ops.conv_tc_skip(x, self.conv1.weight, stats=tr)
         a1 = ops.bn_act(self.bn1, c1, st1, relu=True)
         r = ops.conv_tc(a1, self.conv2.weight, None, stats=tr)
         c2, st2 = r if tr else (r, None)

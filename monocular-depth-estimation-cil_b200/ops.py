@@ -336,6 +336,48 @@ class _ConvPair(torch.autograd.Function):
         return dx, dw1, dw2, None
 
 
+class _ConvSkip(torch.autograd.Function):
+    """y = conv(x, w) (bias-free, optional BN partials) plus a pass-through alias of x for a residual connection that
+    re-joins later (ResidualBlock / inverted-residual blocks).  Both gradients of x then arrive in ONE backward node:
+    the skip gradient enters the data-gradient conv as its epilogue residual, so no separate elementwise sum is needed."""
+
+    @staticmethod
+    def forward(ctx, x, w, want_stats):
+        B, H, W, _ = x.shape
+        Cout, Cin, KS, _ = w.shape
+        out = _nhwc(B, H, W, Cout, x.device)
+        st = None
+        if want_stats:
+            st = torch.empty(L.lib().dp_conv2d_tc_grid(B, H, W, Cin, Cout, KS), 2, Cout, dtype=torch.float32, device=x.device)
+        _conv_tc_launch(x, PACKS.get(w, 0, 0), Cout, KS, None, None, None, False, out, None, False, st)
+        ctx.save_for_backward(x, w)
+        if st is not None:
+            ctx.mark_non_differentiable(st)
+        return out, st, x.detach()
+
+    @staticmethod
+    def backward(ctx, g, _gs, gskip):
+        x, w = ctx.saved_tensors
+        B, H, W, Cin = x.shape
+        Cout, _, KS, _ = w.shape
+        dx = dw = None
+        if g is None:
+            return (_dense(gskip) if gskip is not None else None), None, None
+        g = _dense(g)
+        if ctx.needs_input_grad[0]:
+            gskip = _dense(gskip)
+            dx = _nhwc(B, H, W, Cin, x.device)
+            _conv_tc_launch(g, PACKS.get(w, 1, 1), Cin, KS, None, gskip, None, False, dx, None, False, None)
+        if ctx.needs_input_grad[1]:
+            dw = _on_side(w, lambda: _wgrad_tc(x, g, Cin, Cout, KS).to(w.dtype), (x, g))
+        return dx, dw, None
+
+
+def conv_tc_skip(x, weight, stats=False):
+    """(y, stats, x_skip): bias-free conv of x plus an alias of x to feed the residual add that follows"""
+    return _ConvSkip.apply(x, weight, stats)
+
+
 def conv_tc_pair(x, w1, w2, stats=False):
     """(y1, stats1, y2, stats2) of two bias-free convolutions sharing their input (stats are None unless requested)."""
     return _ConvPair.apply(x, w1, w2, stats)
