@@ -258,3 +258,57 @@ def remove_module_prefix(state_dict):
     for k, v in state_dict.items():
         out[k.replace("module.", "", 1) if k.startswith("module.") else k] = v
     return out
+
+
+def load_model(model_type, checkpoint_path, model_cfg=None):
+    """reference util.py:222-238 / evaluation.py:42-66: build the configured model and load a checkpoint written by
+    main.py (``{'model_state_dict': ...}``) or a bare / ``module.``-prefixed state_dict."""
+    from .network.midas_net_custom import MidasNet_small
+    from .network.midas_semantics import MidasNetSemantics
+    if model_type != 'MiDaS_small':
+        raise NotImplementedError(f"model_type {model_type!r}: the reference's load_model only builds 'MiDaS_small'")
+    if getattr(model_cfg, "dinov2_type", None) is not None:
+        model = MidasNetSemantics(None, features=64, backbone="efficientnet_lite3", exportable=True, non_negative=True,
+                                  cfg=model_cfg, blocks={'expand': True}, dinov2_type=model_cfg.dinov2_type)
+    else:
+        model = MidasNet_small(None, features=64, backbone="efficientnet_lite3", exportable=True, non_negative=True,
+                               cfg=model_cfg, blocks={'expand': True})
+    checkpoint = torch.load(checkpoint_path, map_location="cpu")
+    if 'model_state_dict' in checkpoint:
+        model.load_state_dict(checkpoint['model_state_dict'])
+    else:
+        model.load_state_dict(remove_module_prefix(checkpoint))
+    return model
+
+
+def ensure_dir(directory):
+    """reference util.py:288-290."""
+    import os
+    if not os.path.exists(directory):
+        os.makedirs(directory)
+
+
+def generate_test_predictions(model, test_loader, device, predictions_dir, size=(426, 560)):
+    """reference util.py:292-325: eval-mode forward, bilinear resize of the depth maps to the dataset's native 426x560
+    (align_corners=True) and one ``<name>.npy`` per sample.  The resize runs in the fp32 plane kernel
+    (dp_resize_bilinear_planes_f32) and each batch leaves the device in ONE asynchronous copy into pinned memory instead
+    of a ``.cpu()`` per sample; file names follow the reference (second token of the list entry)."""
+    import os
+    import numpy as np
+    from . import ops
+    model.eval()
+    ensure_dir(predictions_dir)
+    host = None
+    with torch.no_grad():
+        for inputs, filenames in test_loader:
+            inputs = inputs.to(device, non_blocking=True)
+            outputs = model(inputs).unsqueeze(1)                               # (B,1,H,W) fp32
+            outputs = ops.resize_planes_f32(outputs, size, True)               # (B,1,426,560)
+            if host is None or host.shape != outputs.shape:
+                host = torch.empty(outputs.shape, dtype=torch.float32).pin_memory()
+            host.copy_(outputs, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            arr = host.numpy()
+            for i in range(arr.shape[0]):
+                filename = filenames[i].split(' ')[1]
+                np.save(os.path.join(predictions_dir, f"{filename}"), arr[i, 0])

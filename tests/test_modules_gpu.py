@@ -265,3 +265,22 @@ def test_full_model_vs_reference_golden(pkg):
     for k, p in prod.named_parameters():
         if p.requires_grad:
             assert (p.grad is None) == (k in nograd), k
+
+
+def test_generate_test_predictions_matches_reference_recipe(pkg, tmp_path):
+    """util.generate_test_predictions (reference util.py:292-325): per-sample .npy files equal the reference recipe
+    (model(x).unsqueeze(1) -> F.interpolate(426x560, bilinear, align_corners=True)) applied to the same model output."""
+    import numpy as np
+    import torch.nn.functional as F
+    _, prod = _full(pkg, "semantics")
+    prod.eval()
+    x, _ = cases.full_batch()
+    names = [f"sample_{i:04d}_rgb.png sample_{i:04d}_depth.npy" for i in range(x.shape[0])]
+    loader = [(x, names)]
+    pkg.util.generate_test_predictions(prod, loader, torch.device("cuda"), str(tmp_path))
+    with torch.no_grad():
+        ref = F.interpolate(prod(x.cuda()).unsqueeze(1), size=(426, 560), mode="bilinear", align_corners=True).cpu()
+    for i, n in enumerate(names):
+        got = np.load(tmp_path / f"sample_{i:04d}_depth.npy")
+        assert got.shape == (426, 560)
+        assert np.allclose(got, ref[i, 0].numpy(), rtol=1e-5, atol=1e-5)

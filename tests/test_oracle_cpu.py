@@ -106,3 +106,27 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+\.*oracle", src, re.M), f"{f} imports the oracle"
                 assert "oracle/" not in src and "oracle." not in src, f"{f} references the oracle"
+
+
+def test_load_model_reads_reference_checkpoint_formats(tmp_path):
+    """util.load_model (reference util.py:222-238): both checkpoint layouts main.py / DataParallel runs produce load
+    into the drop-in model with identical keys (no CUDA needed: only parameter containers are touched)."""
+    import types
+    import torch
+    import depth_b200
+    from depth_b200 import standins
+    from depth_b200.network import blocks
+    blocks.hub_load = standins.hub_load_standin
+    cfg = types.SimpleNamespace(use_lb=False, use_dgr=False, dinov2_type="dinov2_vits14")
+    from depth_b200.network.midas_semantics import MidasNetSemantics
+    torch.manual_seed(0)
+    src = MidasNetSemantics(None, features=64, backbone="efficientnet_lite3", exportable=True, non_negative=True, cfg=cfg,
+                            blocks={'expand': True}, dinov2_type="dinov2_vits14")
+    p1, p2 = tmp_path / "a.pth", tmp_path / "b.pth"
+    torch.save({"epoch": 3, "model_state_dict": src.state_dict()}, p1)
+    torch.save({"module." + k: v for k, v in src.state_dict().items()}, p2)
+    for p in (p1, p2):
+        m = depth_b200.util.load_model("MiDaS_small", str(p), cfg)
+        sd = m.state_dict()
+        assert list(sd.keys()) == list(src.state_dict().keys())
+        assert all(torch.equal(sd[k], v) for k, v in src.state_dict().items())
