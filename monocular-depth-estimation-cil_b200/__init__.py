@@ -9,6 +9,7 @@ The directory name is not a Python identifier; import it through the repo-root s
 from . import _lib                      # noqa: F401
 from . import util                      # noqa: F401
 from . import config                    # noqa: F401
+from . import evaluation                # noqa: F401
 from .graphs import GraphedTrainStep    # noqa: F401
 from .util import (scale_invariant_loss, silog_loss, gradient_loss, edge_aware_loss, combined_loss,  # noqa: F401
                    absolute_relative_error, delta_thres, evaluation_metrics, evaluate_model_sums,

@@ -168,3 +168,35 @@ def test_fused_eval_fast_math_within_contract(pkg):
     assert abs(fast[0] - exact[0]) <= 1e-5 * abs(exact[0])
     assert abs(fast[1] - exact[1]) <= 1e-5 * abs(exact[1])
     assert float((fast[2:] - exact[2:]).abs().max()) <= 1e-4
+
+
+def test_evaluation_loop_matches_reference_arithmetic(pkg):
+    """depth_b200.evaluation.evaluate_batches vs the reference's loop (evaluation.py:138-186) re-enacted with the oracle
+    functions: batch-length weighting and the N_SAMPLES clip of the last batch."""
+    import torch.nn as nn
+
+    class Identity(nn.Module):
+        def forward(self, x):          # "model": the rgb tensor already is the prediction (B,1,H,W)
+            return x
+
+    g = torch.Generator().manual_seed(5)
+    batches = []
+    for b in (4, 4, 3):
+        t = torch.rand(b, 1, 48, 64, generator=g) * 9.9 + 0.1
+        p = t * torch.exp(0.1 * torch.randn(b, 1, 48, 64, generator=g)) * 1.2
+        batches.append((p, t, None))
+    n_samples = 10
+    got = pkg.evaluation.evaluate_batches(Identity(), batches, torch.device("cuda"), n_samples=n_samples)
+    tot = [0.0] * 5
+    seen = 0
+    for p, t, _ in batches:
+        b = p.shape[0]
+        take = max(0, min(b, n_samples - seen)); seen += b
+        vals = [ol.scale_invariant_loss(p, t, sqroot=True).item(), ol.absolute_relative_error(p, t).item()] + \
+               [ol.delta_thres(p, t, 1.05 ** j).item() for j in (1, 2, 3)]
+        tot = [a + v * take for a, v in zip(tot, vals)]
+    want = [v / n_samples for v in tot]
+    assert got["samples"] == n_samples
+    assert abs(got["si_rmse"] - want[0]) <= 1e-5 * abs(want[0])
+    assert abs(got["abs_rel"] - want[1]) <= 1e-5 * abs(want[1])
+    assert all(abs(a - b) <= 1e-4 for a, b in zip(got["delta"], want[2:]))
