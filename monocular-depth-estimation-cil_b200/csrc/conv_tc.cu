@@ -314,6 +314,135 @@ __device__ __forceinline__ void epilogue_tma(const Maps& tm, const ConvArgs& a, 
   }
 }
 
+// ---- epilogue A1: BN in {16, 32}, single output.  Small tiles are bound by the serial latency of one epilogue pass
+// (TMEM load -> math -> staging -> store), not by its work, so the eight warps form two independent groups that take
+// alternate tiles (group g <-> MMA issuer g <-> TMEM buffers g, g+2).  Each warp owns 32 pixels x all BN columns, stages
+// them in its own swizzled ring slot and issues its own TMA store of a (32 / tw) x tw pixel box: no inter-warp barrier.
+template <int BNT>
+__device__ __forceinline__ void epilogue_tma_warp(const Maps& tm, const ConvArgs& a, Barriers* bars, uint8_t* s_out,
+                                                  float* s_stats, uint32_t tmem, int warp, int lane) {
+  const int e = warp - 4, ew = e & 3, grp = e >> 2;
+  const int m = ew * 32 + lane;
+  const int py = m / a.tw, px = m - py * a.tw;
+  constexpr uint32_t kRowBytes = 2u * BNT;                  // 32 or 64
+  constexpr uint32_t kSwz = kRowBytes == 64 ? 3u : 1u;
+  constexpr uint32_t kSlotBytes = 32u * kRowBytes;          // one warp's 32-pixel sub-tile
+  constexpr int kRing = 4;
+  const bool want_stats = a.stats != nullptr;
+  float acc_s[BNT], acc_q[BNT];
+#pragma unroll
+  for (int j = 0; j < BNT; ++j) { acc_s[j] = 0.f; acc_q[j] = 0.f; }
+  uint32_t soff[BNT / 8];
+#pragma unroll
+  for (int j = 0; j < BNT / 8; ++j) {
+    const uint32_t off = (uint32_t)lane * kRowBytes + (uint32_t)(j * 16);
+    soff[j] = off ^ (((off >> 7) & kSwz) << 4);
+  }
+  uint8_t* my_ring = s_out + (size_t)e * kRing * kSlotBytes;
+  const uint32_t ring_base = tc::smem_u32(my_ring);
+  const int rows_per_warp = 32 / a.tw;                      // tw in {8, 16, 32}
+  int it = grp, ring = 0;
+  TileIter ti;
+  ti.init(a, blockIdx.x + (unsigned)grp * gridDim.x);
+  for (long long item = blockIdx.x + (long long)grp * gridDim.x; item < a.total_items;
+       item += 2LL * gridDim.x, it += 2, ti.step(a), ti.step(a)) {
+    const int n = ti.n, y0 = ti.ty * a.th, x0 = ti.tx * a.tw;
+    const int buf = it & (a.nbuf - 1);
+    const int y = y0 + py, x = x0 + px;
+    const int oy = y * a.osy + a.oay, ox = x * a.osx + a.oax;
+    const bool valid = (y < a.H) && (x < a.W) && (oy < a.Ho) && (ox < a.Wo);
+    const long long pix = ((long long)n * a.Ho + oy) * a.Wo + ox;
+    uint4 r1[BNT / 8], r2[BNT / 8];
+    if (a.res) {
+      const uint4* rp = reinterpret_cast<const uint4*>(a.res + pix * a.res_ld);
+#pragma unroll
+      for (int j = 0; j < BNT / 8; ++j) r1[j] = (valid && j * 8 < a.Cout) ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
+    }
+    if (a.resb) {
+      const uint4* rp = reinterpret_cast<const uint4*>(a.resb + pix * a.resb_ld);
+#pragma unroll
+      for (int j = 0; j < BNT / 8; ++j) r2[j] = (valid && j * 8 < a.Cout) ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
+    }
+    // the ring slot written below was handed to TMA four of this warp's tiles ago: make sure it has been read
+    if (lane == 0) tc::bulk_wait_read<kRing - 1>();
+    __syncwarp();
+    tc::mbar_wait(&bars->tmem_full[buf], (it >> (a.nbuf == 4 ? 2 : 1)) & 1);
+    tc::fence_after_sync();
+    uint32_t raw[BNT];
+    tc::tmem_ld_issue<BNT>(tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * a.BN), raw);
+    tc::tmem_ld_wait();
+    tc::fence_before_sync();
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(&bars->tmem_empty[buf]);
+    float v[BNT];
+#pragma unroll
+    for (int j = 0; j < BNT; ++j) v[j] = __uint_as_float(raw[j]);
+    if (a.bias) {
+#pragma unroll
+      for (int j = 0; j < BNT; j += 4) {
+        if (j < a.Cout) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + j));
+          v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+        }
+      }
+    }
+    if (a.res) {
+#pragma unroll
+      for (int j = 0; j < BNT / 8; ++j) {
+        const uint32_t rr[4] = {r1[j].x, r1[j].y, r1[j].z, r1[j].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { v[j * 8 + 2 * k] += bf16_lo(rr[k]); v[j * 8 + 2 * k + 1] += bf16_hi(rr[k]); }
+      }
+    }
+    if (a.resb) {
+#pragma unroll
+      for (int j = 0; j < BNT / 8; ++j) {
+        const uint32_t rr[4] = {r2[j].x, r2[j].y, r2[j].z, r2[j].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { v[j * 8 + 2 * k] += bf16_lo(rr[k]); v[j * 8 + 2 * k + 1] += bf16_hi(rr[k]); }
+      }
+    }
+    const uint32_t st = ring_base + (uint32_t)ring * kSlotBytes;
+#pragma unroll
+    for (int j = 0; j < BNT / 8; ++j) {
+      uint32_t q[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float x0v = v[j * 8 + 2 * k], x1v = v[j * 8 + 2 * k + 1];
+        const uint32_t plain = pack_bf16x2(x0v, x1v);
+        q[k] = a.relu ? pack_bf16x2(fmaxf(x0v, 0.f), fmaxf(x1v, 0.f)) : plain;
+        if (want_stats) {
+          const float f0 = valid ? bf16_lo(plain) : 0.f, f1 = valid ? bf16_hi(plain) : 0.f;
+          acc_s[j * 8 + 2 * k] += f0;
+          acc_q[j * 8 + 2 * k] = fmaf(f0, f0, acc_q[j * 8 + 2 * k]);
+          acc_s[j * 8 + 2 * k + 1] += f1;
+          acc_q[j * 8 + 2 * k + 1] = fmaf(f1, f1, acc_q[j * 8 + 2 * k + 1]);
+        }
+      }
+      tc::st_shared_v4(st + soff[j], q[0], q[1], q[2], q[3]);
+    }
+    tc::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      tc::tma_store_4d(&tm.o2, my_ring + (size_t)ring * kSlotBytes, 0, x0, y0 + ew * rows_per_warp, n);
+      tc::bulk_commit();
+    }
+    if (++ring == kRing) ring = 0;
+  }
+  if (lane == 0) tc::bulk_wait_read<0>();
+  if (want_stats) {
+#pragma unroll
+    for (int j = 0; j < BNT; ++j) {
+      const float s = dp::warp_sum(acc_s[j]);
+      const float q = dp::warp_sum(acc_q[j]);
+      if (lane == 0 && j < a.Cout) {
+        s_stats[(e * 2 + 0) * a.Cout + j] = s;
+        s_stats[(e * 2 + 1) * a.Cout + j] = q;
+      }
+    }
+  }
+}
+
 // ---- epilogue A2: BN a multiple of 64 (> 64), single output.  The tile leaves in 64-column sub-blocks: per
 // sub-block each of the eight warps takes 32 pixels x 32 columns (one tcgen05.ld), stages bf16 rows in a 128B-swizzled
 // [128 px][64 ch] tile and one thread TMA-stores it at channel offset nb*BN + sb*64 (channels >= Cout are clipped by the
@@ -553,7 +682,8 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
   // layout: [resident weights][output staging tiles][stages x (A | B)][stats][barriers]
   uint8_t* s_res = smem;
   uint8_t* s_out = smem + a.resident_bytes;
-  const uint32_t out_bytes = a.epi_tma == 2 ? (uint32_t)a.nob * 16384u
+  const uint32_t out_bytes = a.epi_tma == 3 ? (uint32_t)(kEpiWarps * 4 * 32 * a.BN * 2)
+                             : a.epi_tma == 2 ? (uint32_t)a.nob * 16384u
                                              : (a.epi_tma ? (uint32_t)a.nob * (a.out2 ? 2u : 1u) * a.out_tile_bytes : 0u);
   uint8_t* s_stage = s_out + out_bytes;
   const uint32_t stage_bytes = a.a_slot_bytes + (a.resident ? 0u : (uint32_t)a.max_nr * a.b_tap_bytes);
@@ -566,12 +696,15 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < a.stages; ++i) { tc::mbar_init(&bars->full[i], 1); tc::mbar_init(&bars->empty[i], 1); }
-    for (int i = 0; i < 4; ++i) { tc::mbar_init(&bars->tmem_full[i], 1); tc::mbar_init(&bars->tmem_empty[i], kEpiWarps); }
+    for (int i = 0; i < 4; ++i) {
+      tc::mbar_init(&bars->tmem_full[i], 1);
+      tc::mbar_init(&bars->tmem_empty[i], a.epi_tma == 3 ? kEpiWarps / 2 : kEpiWarps);   // per-warp mode: one group per buffer
+    }
     tc::mbar_init(&bars->resident_full, 1);
     tc::fence_barrier_init();
     tc::prefetch_tmap(&tm.a[0]);
     tc::prefetch_tmap(&tm.b);
-    if (a.epi_tma) tc::prefetch_tmap(&tm.o);
+    if (a.epi_tma) tc::prefetch_tmap(a.epi_tma == 3 ? &tm.o2 : &tm.o);
   }
   if (warp == 2) tc::tmem_alloc(&bars->tmem_base, kTmemCols);
   for (int i = threadIdx.x; i < stats_floats; i += kThreads) s_stats[i] = 0.f;
@@ -708,7 +841,10 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
     }
   } else if (warp >= 4) {
     // ================= epilogue: TMEM -> registers -> (smem -> TMA store | global) =================
-    if (a.epi_tma == 2) {
+    if (a.epi_tma == 3) {
+      if (a.BN == 32) epilogue_tma_warp<32>(tm, a, bars, s_out, s_stats, tmem, warp, lane);
+      else epilogue_tma_warp<16>(tm, a, bars, s_out, s_stats, tmem, warp, lane);
+    } else if (a.epi_tma == 2) {
       epilogue_tma_wide(tm, a, bars, s_out, s_stats, tmem, warp, lane);
     } else if (a.epi_tma) {
       if (a.BN == 64) epilogue_tma<32>(tm, a, bars, s_out, s_stats, tmem, warp, lane);
@@ -834,6 +970,13 @@ int make_plan(Plan& p, int B, int Hg, int Wg, int Cin, int Cout, const ColSpec* 
   a.out_tile_bytes = (uint32_t)(128 * a.BN * 2);
   a.nob = n_out >= 2 ? 2 : (a.BN == 64 ? 3 : 4);
   size_t out_bytes = a.epi_tma ? (size_t)a.nob * n_out * a.out_tile_bytes : 0;
+  // per-warp mode: two epilogue groups on alternate tiles (needs the two-issuer / four-buffer MMA side: single k-step
+  // tiles) and 32-pixel sub-tiles that are whole rows of the tile
+  if (a.epi_tma == 1 && n_out == 1 && (a.BN == 16 || a.BN == 32) && a.nbuf == 4 && a.ncols * a.kchunks == 1 && a.tw <= 32 &&
+      getenv("DP_CONV_NOWARP") == nullptr) {
+    a.epi_tma = 3;
+    out_bytes = (size_t)kEpiWarps * 4 * 32 * a.BN * 2;
+  }
   if (!a.epi_tma && n_out == 1 && a.BN > 64 && a.BN % 64 == 0 && getenv("DP_CONV_NOTMA") == nullptr) {
     // wide TMA-store epilogue: three (or two) 16 KB staging tiles, as long as the load pipeline keeps >= 3 stages
     const size_t stage_b = a.a_slot_bytes + (a.resident ? 0 : (size_t)a.max_nr * a.b_tap_bytes);
@@ -912,7 +1055,15 @@ int launch(const Plane* planes, const ColSpec* cols, int ncols, int B, int Hg, i
     const uint64_t Wv = (uint64_t)((om.Wo - om.oax + om.osx - 1) / om.osx), Hv = (uint64_t)((om.Ho - om.oay + om.osy - 1) / om.osy);
     uint64_t dims[4] = {(uint64_t)Cout, Wv, Hv, (uint64_t)B};
     uint32_t box[4] = {(uint32_t)(a.epi_tma == 2 ? 64 : a.BN), (uint32_t)a.tw, (uint32_t)a.th, 1};
-    for (int k = 0; k < 2; ++k) {
+    if (a.epi_tma == 3) {      // per-warp stores: (32 / tw) x tw pixel boxes of the single output, kept in tm.o2
+      uint32_t wbox[4] = {(uint32_t)a.BN, (uint32_t)a.tw, (uint32_t)(32 / a.tw), 1};
+      uint64_t str[3] = {(uint64_t)om.osx * a.out_ld * 2, (uint64_t)om.osy * om.Wo * a.out_ld * 2,
+                         (uint64_t)om.Ho * om.Wo * a.out_ld * 2};
+      rc = dp_make_tmap_bf16(&tm.o2, a.out + ((long long)om.oay * om.Wo + om.oax) * a.out_ld, 4, dims, str, wbox, nullptr,
+                             a.BN * 2);
+      if (rc) return rc;
+    }
+    for (int k = 0; k < 2 && a.epi_tma != 3; ++k) {
       bf16* base = k == 0 ? a.out : a.out2;
       const long long ld = k == 0 ? a.out_ld : a.out2_ld;
       if (!base) continue;
