@@ -77,11 +77,11 @@ __global__ void __launch_bounds__(TPB, 2) dw_fwd_kernel(DwArgs a) {
       const int r = st / strips;
       const int oy = r % a.Ho, b = r / a.Ho;
       const int ox0 = sx * TX;
-      float acc[TX][8];
+      float2 acc2[TX][4];            // packed f32x2 accumulators: one FFMA2 does two of the eight channels
 #pragma unroll
       for (int t = 0; t < TX; ++t)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc2[t][j] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int ky = 0; ky < K; ++ky) {
         const int iy = oy * S - a.pad_t + ky;
@@ -98,16 +98,25 @@ __global__ void __launch_bounds__(TPB, 2) dw_fwd_kernel(DwArgs a) {
         for (int kx = 0; kx < K; ++kx) {
           const float4 w0 = *reinterpret_cast<const float4*>(s_w + (ky * K + kx) * G * 8 + c8l * 8);
           const float4 w1 = *reinterpret_cast<const float4*>(s_w + (ky * K + kx) * G * 8 + c8l * 8 + 4);
-          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+          const float2 wv2[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y),
+                                 make_float2(w1.z, w1.w)};
 #pragma unroll
           for (int t = 0; t < TX; ++t) {
-            float v[8];
-            unpack8(raw[kx + t * S], v);
+            const uint4 u = raw[kx + t * S];
+            const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(v[j], wv[j], acc[t][j]);
+            for (int j = 0; j < 4; ++j) {
+              const float2 v2 = make_float2(__uint_as_float(uw[j] << 16), __uint_as_float(uw[j] & 0xffff0000u));
+              acc2[t][j] = __ffma2_rn(v2, wv2[j], acc2[t][j]);
+            }
           }
         }
       }
+      float acc[TX][8];
+#pragma unroll
+      for (int t = 0; t < TX; ++t)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[t][2 * j] = acc2[t][j].x; acc[t][2 * j + 1] = acc2[t][j].y; }
       bf16* op = a.out + (((long long)b * a.Ho + oy) * a.Wo + ox0) * a.out_ld + c8 * 8;
 #pragma unroll
       for (int t = 0; t < TX; ++t) {
@@ -270,13 +279,22 @@ __global__ void __launch_bounds__(TPB) dw_wgrad_kernel(const bf16* __restrict__ 
 }
 
 // grad[c][ky][kx] (OIHW with I = 1) (+)= sum_chunks partial[chunk][tap][c]
-__global__ void dw_wgrad_reduce_kernel(const float* __restrict__ partial, int nchunks, int taps, int C,
-                                       float* __restrict__ grad, int accumulate) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= taps * C) return;
-  const int tap = i / C, c = i - tap * C;
+// block = 32 consecutive (tap, c) columns x 32 chunk lanes: coalesced rows of the partials, fixed-order fp64 fold
+__global__ void __launch_bounds__(1024) dw_wgrad_reduce_kernel(const float* __restrict__ partial, int nchunks, int taps, int C,
+                                                               float* __restrict__ grad, int accumulate) {
+  __shared__ double s_s[32][32];
+  const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + cl;
   double s = 0.0;
-  for (int p = 0; p < nchunks; ++p) s += (double)partial[((size_t)p * taps + tap) * C + c];
+  if (i < taps * C)
+    for (int p = pl; p < nchunks; p += 32) s += (double)partial[(size_t)p * taps * C + i];
+  s_s[pl][cl] = s;
+  __syncthreads();
+  if (pl != 0 || i >= taps * C) return;
+  s = 0.0;
+#pragma unroll
+  for (int l = 0; l < 32; ++l) s += s_s[l][cl];
+  const int tap = i / C, c = i - tap * C;
   const size_t o = (size_t)c * taps + tap;
   grad[o] = accumulate ? grad[o] + (float)s : (float)s;
 }
@@ -376,7 +394,7 @@ int dp_dwconv_wgrad(const void* x, long long x_ld, int B, int Hi, int Wi, int C,
   else if (stride == 1) dw_wgrad_kernel<5, 1><<<grid, TPB, smem, stream>>>(xb, x_ld, B, Hi, Wi, C, gb, dy_ld, Ho, Wo, pad_t, pad_l, nchunks, partial);
   else dw_wgrad_kernel<5, 2><<<grid, TPB, smem, stream>>>(xb, x_ld, B, Hi, Wi, C, gb, dy_ld, Ho, Wo, pad_t, pad_l, nchunks, partial);
   DP_CHECK_LAUNCH("dw_wgrad_kernel");
-  dw_wgrad_reduce_kernel<<<dp::ceil_div(K * K * C, 128), 128, 0, stream>>>(partial, nchunks, K * K, C, grad, accumulate);
+  dw_wgrad_reduce_kernel<<<dp::ceil_div(K * K * C, 32), 1024, 0, stream>>>(partial, nchunks, K * K, C, grad, accumulate);
   DP_CHECK_LAUNCH("dw_wgrad_reduce_kernel");
   return DP_OK;
 }

@@ -106,13 +106,7 @@ def run_block(b, x):
     kind = _block_kind(b)
     skip = x if getattr(b, "has_residual", False) else None
     if kind == "ir":
-        if skip is not None:
-            # the skip gradient joins conv_pw's data gradient in one backward node (ops.conv_tc_skip)
-            tr = b.bn1.training
-            c, st, skip = ops.conv_tc_skip(x, b.conv_pw.weight, stats=tr)
-            y = ops.bn_act(b.bn1, c, st, relu=2)
-        else:
-            y = _pw(x, b.conv_pw, b.bn1, 2)
+        y = _pw(x, b.conv_pw, b.bn1, 2)
         y = _dw(y, b.conv_dw, b.bn2)
         return _pw(y, b.conv_pwl, b.bn3, 0, res=skip)
     y = _dw(x, b.conv_dw, b.bn1)

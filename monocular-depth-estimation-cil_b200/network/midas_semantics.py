@@ -91,18 +91,15 @@ class ResidualBlock(nn.Module):
 
     def fused(self, x):
         tr = self.training
-        cs = sts = None
-        if len(self.shortcut) != 0:
-            # conv1 and the 1x1 shortcut read the same tensor: one op, so their data gradients are chained in backward
-            c1, st1, cs, sts = ops.conv_tc_pair(x, self.conv1.weight, self.shortcut[0].weight, stats=tr)
-        else:
-            # identity shortcut: x re-joins after bn2; its two gradients meet in conv1's backward node
-            c1, st1, x = ops.conv_tc_skip(x, self.conv1.weight, stats=tr)
+        r = ops.conv_tc(x, self.conv1.weight, None, stats=tr)
+        c1, st1 = r if tr else (r, None)
         a1 = ops.bn_act(self.bn1, c1, st1, relu=True)
         r = ops.conv_tc(a1, self.conv2.weight, None, stats=tr)
         c2, st2 = r if tr else (r, None)
         if len(self.shortcut) == 0:
             return ops.bn_act(self.bn2, c2, st2, relu=True, res=x)
+        r = ops.conv_tc(x, self.shortcut[0].weight, None, stats=tr)
+        cs, sts = r if tr else (r, None)
         return ops.bn_act(self.bn2, c2, st2, relu=True, bn2=self.shortcut[1], c2=cs, stats2=sts)
 
     def forward(self, x):

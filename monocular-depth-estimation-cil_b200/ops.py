@@ -295,94 +295,6 @@ class _ConvTC(torch.autograd.Function):
         return dx, dw, db, dres, dres2, None, None, None
 
 
-class _ConvPair(torch.autograd.Function):
-    """Two bias-free convolutions of the SAME input (ResidualBlock conv1 + its 1x1 shortcut, midas_semantics.py:132-143):
-    y1 = conv(x, w1), y2 = conv(x, w2), each with optional BN partials.  The backward chains the two data gradients
-    through the epilogue's residual input (dx = dgrad2(g2) + dgrad1(g1) in one pass) instead of leaving the sum of two
-    full-resolution tensors to a separate elementwise kernel."""
-
-    @staticmethod
-    def forward(ctx, x, w1, w2, want_stats):
-        B, H, W, _ = x.shape
-        outs = []
-        for w in (w1, w2):
-            Cout, Cin, KS, _ = w.shape
-            out = _nhwc(B, H, W, Cout, x.device)
-            st = None
-            if want_stats:
-                st = torch.empty(L.lib().dp_conv2d_tc_grid(B, H, W, Cin, Cout, KS), 2, Cout, dtype=torch.float32,
-                                 device=x.device)
-            _conv_tc_launch(x, PACKS.get(w, 0, 0), Cout, KS, None, None, None, False, out, None, False, st)
-            outs += [out, st]
-        ctx.save_for_backward(x, w1, w2)
-        ctx.mark_non_differentiable(*[t for t in (outs[1], outs[3]) if t is not None])
-        return tuple(outs)
-
-    @staticmethod
-    def backward(ctx, g1, _s1, g2, _s2):
-        x, w1, w2 = ctx.saved_tensors
-        B, H, W, Cin = x.shape
-        g1, g2 = _dense(g1), _dense(g2)
-        dx = dw1 = dw2 = None
-        if ctx.needs_input_grad[0]:
-            t = _nhwc(B, H, W, Cin, x.device)
-            _conv_tc_launch(g1, PACKS.get(w1, 1, 1), Cin, w1.shape[2], None, None, None, False, t, None, False, None)
-            dx = _nhwc(B, H, W, Cin, x.device)
-            _conv_tc_launch(g2, PACKS.get(w2, 1, 1), Cin, w2.shape[2], None, t, None, False, dx, None, False, None)
-        if ctx.needs_input_grad[1]:
-            dw1 = _on_side(w1, lambda: _wgrad_tc(x, g1, Cin, w1.shape[0], w1.shape[2]).to(w1.dtype), (x, g1))
-        if ctx.needs_input_grad[2]:
-            dw2 = _on_side(w2, lambda: _wgrad_tc(x, g2, Cin, w2.shape[0], w2.shape[2]).to(w2.dtype), (x, g2))
-        return dx, dw1, dw2, None
-
-
-class _ConvSkip(torch.autograd.Function):
-    """y = conv(x, w) (bias-free, optional BN partials) plus a pass-through alias of x for a residual connection that
-    re-joins later (ResidualBlock / inverted-residual blocks).  Both gradients of x then arrive in ONE backward node:
-    the skip gradient enters the data-gradient conv as its epilogue residual, so no separate elementwise sum is needed."""
-
-    @staticmethod
-    def forward(ctx, x, w, want_stats):
-        B, H, W, _ = x.shape
-        Cout, Cin, KS, _ = w.shape
-        out = _nhwc(B, H, W, Cout, x.device)
-        st = None
-        if want_stats:
-            st = torch.empty(L.lib().dp_conv2d_tc_grid(B, H, W, Cin, Cout, KS), 2, Cout, dtype=torch.float32, device=x.device)
-        _conv_tc_launch(x, PACKS.get(w, 0, 0), Cout, KS, None, None, None, False, out, None, False, st)
-        ctx.save_for_backward(x, w)
-        if st is not None:
-            ctx.mark_non_differentiable(st)
-        return out, st, x.detach()
-
-    @staticmethod
-    def backward(ctx, g, _gs, gskip):
-        x, w = ctx.saved_tensors
-        B, H, W, Cin = x.shape
-        Cout, _, KS, _ = w.shape
-        dx = dw = None
-        if g is None:
-            return (_dense(gskip) if gskip is not None else None), None, None
-        g = _dense(g)
-        if ctx.needs_input_grad[0]:
-            gskip = _dense(gskip)
-            dx = _nhwc(B, H, W, Cin, x.device)
-            _conv_tc_launch(g, PACKS.get(w, 1, 1), Cin, KS, None, gskip, None, False, dx, None, False, None)
-        if ctx.needs_input_grad[1]:
-            dw = _on_side(w, lambda: _wgrad_tc(x, g, Cin, Cout, KS).to(w.dtype), (x, g))
-        return dx, dw, None
-
-
-def conv_tc_skip(x, weight, stats=False):
-    """(y, stats, x_skip): bias-free conv of x plus an alias of x to feed the residual add that follows"""
-    return _ConvSkip.apply(x, weight, stats)
-
-
-def conv_tc_pair(x, w1, w2, stats=False):
-    """(y1, stats1, y2, stats2) of two bias-free convolutions sharing their input (stats are None unless requested)."""
-    return _ConvPair.apply(x, w1, w2, stats)
-
-
 def conv_tc(x, weight, bias=None, res=None, res2=None, relu=False, dual=False, stats=False):
     """3x3/s1/p1 or 1x1 conv on tcgen05.  Returns y, or (y, relu(y)) when dual, with BN partials appended when stats."""
     y, y2, st = _ConvTC.apply(x, weight, bias, res, res2, relu, dual, stats)

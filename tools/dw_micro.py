@@ -1,0 +1,29 @@
+"""Depthwise conv kernels of the EfficientNet trunk against their HBM floors."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, depth_b200
+from depth_b200 import ops
+HBM = 6549.8e9
+for (B, H, W, C, K, S) in [(32, 56, 72, 288, 5, 1), (32, 28, 36, 816, 5, 1), (32, 14, 18, 1392, 5, 1), (32, 112, 144, 192, 3, 1),
+                           (32, 224, 288, 144, 3, 2), (32, 14, 18, 1392, 3, 1)]:
+    x = torch.randn(B, H, W, C, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    w = (torch.randn(C, 1, K, K, device="cuda") * 0.2).requires_grad_(True)
+    p = K // 2
+    Ho, Wo = (H + 2 * p - K) // S + 1, (W + 2 * p - K) // S + 1
+    def fwd():
+        return ops.dwconv(x, w, S, p, p, Ho, Wo, stats=True)[0]
+    y = fwd(); g = torch.randn_like(y)
+    def t(fn, reps=10):
+        for _ in range(3): fn()
+        torch.cuda._sleep(int(2e6))
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps): fn()
+        e.record(); torch.cuda.synchronize()
+        return s.elapsed_time(e) / reps * 1e3
+    tf = t(fwd)
+    def fb():
+        yy = fwd(); yy.backward(g)
+    tb = t(fb) - tf
+    by = 2.0 * B * (H * W + Ho * Wo) * C
+    print(f"dw k{K} s{S} {H}x{W}x{C}: fwd {tf:7.1f} us (floor {by / HBM * 1e6:5.1f})  bwd(dgrad+wgrad) {tb:7.1f} us (floor {2 * by / HBM * 1e6:5.1f})")
