@@ -152,15 +152,29 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__
       reinterpret_cast<float4*>(&sV[j][0])[c4] = __ldg(reinterpret_cast<const float4*>(v + (base + k0 + j) * D) + c4);
     }
     __syncthreads();
-    for (int j = 0; j < nk; ++j) {
-      const float4 kk = *reinterpret_cast<const float4*>(&sK[j][h * HD]);
-      const float4 vv = *reinterpret_cast<const float4*>(&sV[j][h * HD]);
-      const float s = qv.x * kk.x + qv.y * kk.y + qv.z * kk.z + qv.w * kk.w;
-      const float mn = fmaxf(m, s);
-      const float corr = __expf(m - mn), p = __expf(s - mn);
-      l = l * corr + p;
-      acc.x = acc.x * corr + p * vv.x; acc.y = acc.y * corr + p * vv.y;
-      acc.z = acc.z * corr + p * vv.z; acc.w = acc.w * corr + p * vv.w;
+    // online softmax over groups of four keys: one rescale (exp) per group instead of one per key - the loop is bound
+    // by the MUFU rate (two exponentials per score otherwise)
+    for (int j = 0; j < nk; j += 4) {
+      float sc[4];
+      float4 vv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int jj = j + u < nk ? j + u : nk - 1;
+        const float4 kk = *reinterpret_cast<const float4*>(&sK[jj][h * HD]);
+        vv[u] = *reinterpret_cast<const float4*>(&sV[jj][h * HD]);
+        const float s = qv.x * kk.x + qv.y * kk.y + qv.z * kk.z + qv.w * kk.w;
+        sc[u] = j + u < nk ? s : -INFINITY;
+      }
+      const float mn = fmaxf(fmaxf(m, fmaxf(sc[0], sc[1])), fmaxf(sc[2], sc[3]));
+      const float corr = __expf(m - mn);
+      l *= corr;
+      acc.x *= corr; acc.y *= corr; acc.z *= corr; acc.w *= corr;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float p = __expf(sc[u] - mn);
+        l += p;
+        acc.x += p * vv[u].x; acc.y += p * vv[u].y; acc.z += p * vv[u].z; acc.w += p * vv[u].w;
+      }
       m = mn;
     }
   }
