@@ -6,6 +6,8 @@ kernels themselves.  `GraphedTrainStep` captures one full step (our kernels, the
 gradient all-reduce and the fused AdamW update) into a single CUDA graph and replays it: the host submits one
 graph launch per step, copies the batch into static buffers and reads back eight floats.
 """
+import os
+
 import torch
 
 from . import ops, util
@@ -23,6 +25,10 @@ class GraphedTrainStep:
         self.red = D.GradientAllReducer(model.parameters(), world)
         self.out = None
         self._copy = self._sx = self._st = self._consumed = None
+        # The copy-stream overlap pays off on a single GPU (+3 % end to end).  With NCCL collectives captured in the graph
+        # (world > 1) the same scheme doubled the end-to-end step time at N = 4 (measured; H2D bandwidth itself was a full
+        # 55 GB/s per rank), so multi-rank steps copy on the main stream (+2 ms per step).
+        self._overlap_h2d = self.red.world == 1 and not os.environ.get("DP_NO_COPY_STREAM")
         self._step = 0
         self._hout = [torch.empty(8, dtype=torch.float32).pin_memory() for _ in range(2)]
         self._done = [torch.cuda.Event(), torch.cuda.Event()]
@@ -57,11 +63,16 @@ class GraphedTrainStep:
         """one optimisation step; inputs/targets may be (pinned) host or device tensors, or None to reuse the static
         batch.  Returns the device tensor of loss scalars (index with depth_b200._lib.L_*); no host sync.
 
-        Host batches travel on a copy stream into a staging buffer, so the H2D transfer of step i overlaps the graph
-        replay of step i-1 (the caller is never blocked); a device-to-device copy then refreshes the graph's static
-        inputs.  The loss scalars of every step are copied to pinned host memory asynchronously (`loss_dict`)."""
+        On a single GPU host batches travel on a copy stream into a staging buffer, so the H2D transfer of step i
+        overlaps the graph replay of step i-1 (the caller is never blocked); a device-to-device copy then refreshes the
+        graph's static inputs.  Multi-rank steps copy on the main stream.  The loss scalars of every step are copied to pinned host memory asynchronously (`loss_dict`)."""
         main = torch.cuda.current_stream()
-        if inputs is not None or targets is not None:
+        if (inputs is not None or targets is not None) and not self._overlap_h2d:
+            if inputs is not None:                 # copies on the main stream (no overlap with the previous replay)
+                self.x.copy_(inputs, non_blocking=True)
+            if targets is not None:
+                self.t.copy_(targets, non_blocking=True)
+        elif inputs is not None or targets is not None:
             if self._copy is None:
                 self._copy = torch.cuda.Stream()
                 self._sx, self._st = torch.empty_like(self.x), torch.empty_like(self.t)
