@@ -22,6 +22,13 @@ CASES = {
     "dinohead": ("dinohead", dict(), [(2, 20, 384)] * 4, dict(ph=4, pw=5)),
     "xattn_1win": ("xattn", dict(dim=32), [(2, 32, 64, 96), (2, 32, 64, 96)], {}),
     "xattn_multi": ("xattn", dict(dim=32), [(1, 32, 160, 192), (1, 32, 160, 192)], {}),
+    # MiDaS-large / DPT decoders: blocks.py:243-314, midas_net.py:12-76, dpt_depth.py:155-293
+    "rcu_large64": ("rcu_large", dict(features=64), [(2, 64, 10, 14)], {}),
+    "fusion_large64": ("fusion_large", dict(features=64), [(2, 64, 9, 12), (2, 64, 9, 12)], {}),
+    "fusion_large64_single": ("fusion_large", dict(features=64), [(1, 64, 7, 10)], {}),
+    "dpt_decoder64": ("dpt", dict(features=64), [(1, 256, 24, 32), (1, 512, 12, 16), (1, 768, 6, 8), (1, 768, 3, 4)], {}),
+    "midas_large_decoder64": ("midas_large", dict(features=64),
+                              [(1, 256, 16, 24), (1, 512, 8, 12), (1, 1024, 4, 6), (1, 2048, 2, 3)], {}),
 }
 
 
@@ -36,6 +43,14 @@ def build_oracle(kind, kw):
         return om.Dinov2Head(1, 384, 128, use_bn=False, out_channels=[128, 256, 512, 512], use_clstoken=False)
     if kind == "xattn":
         return om.CrossAttention(kw["dim"], window_size=16)
+    if kind == "rcu_large":
+        return om.RCUInplace(kw["features"])
+    if kind == "fusion_large":
+        return om.FusionBlockLarge(kw["features"])
+    if kind == "dpt":
+        return om.DPTDecoder(features=kw["features"])
+    if kind == "midas_large":
+        return om.MidasLargeDecoder(features=kw["features"])
     raise KeyError(kind)
 
 
@@ -51,7 +66,11 @@ def run_case(module, name, device="cpu", call=None):
     module = module.to(device)
     module.train()
     xs = [x.to(device).requires_grad_(True) for x in case_inputs(name)]
-    if call is not None:
+    if kind in ("rcu_large", "fusion_large"):
+        # these blocks apply an in-place ReLU to their input (blocks.py:263,274): feed non-leaf copies
+        fed = [x * 1.0 for x in xs]
+        out = call(module, fed, fkw) if call is not None else module(*fed)
+    elif call is not None:
         out = call(module, xs, fkw)
     elif kind == "dinohead":
         out = module(tuple(xs), fkw["ph"], fkw["pw"])

@@ -142,7 +142,61 @@ def build_reference(kind, kw, ref_blocks, ref_dpt, ref_sem):
         return ref_dpt.Dinov2Head(1, 384, 128, use_bn=False, out_channels=[128, 256, 512, 512], use_clstoken=False)
     if kind == "xattn":
         return ref_sem.CrossAttention(kw["dim"], window_size=16)
+    if kind == "rcu_large":
+        return ref_blocks.ResidualConvUnit(kw["features"])
+    if kind == "fusion_large":
+        return ref_blocks.FeatureFusionBlock(kw["features"])
+    if kind == "dpt":
+        # the real DPTDepthModel with an inert backbone object; its own forward() then runs on the four feature maps
+        # handed in as `x` (forward_transformer is an instance attribute set in DPT.__init__, dpt_depth.py:214-226)
+        real = ref_blocks._make_pretrained_vitb_rn50_384
+        ref_blocks._make_pretrained_vitb_rn50_384 = lambda *a, **k: nn.Module()
+        try:
+            m = ref_dpt.DPTDepthModel(path=None, backbone="vitb_rn50_384", features=kw["features"], non_negative=True)
+        finally:
+            ref_blocks._make_pretrained_vitb_rn50_384 = real
+        m.forward_transformer = lambda pretrained, feats: feats
+        return m
+    if kind == "midas_large":
+        import network.midas_net as ref_large
+        real = ref_blocks._make_pretrained_resnext101_wsl
+        ref_blocks._make_pretrained_resnext101_wsl = lambda *a, **k: _FeatureFeeder()
+        try:
+            m = ref_large.MidasNet(None, features=kw["features"], non_negative=True)
+        finally:
+            ref_blocks._make_pretrained_resnext101_wsl = real
+        return m
     raise KeyError(kind)
+
+
+class _Feed(nn.Module):
+    """stands in for one ResNeXt stage: ignores its input and returns the preset feature map"""
+
+    def __init__(self):
+        super().__init__()
+        self.value = None
+
+    def forward(self, _x):
+        return self.value
+
+
+class _FeatureFeeder(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.layer1, self.layer2, self.layer3, self.layer4 = _Feed(), _Feed(), _Feed(), _Feed()
+
+
+def reference_call(kind):
+    """how the REAL reference module is driven for the decoder-only cases"""
+    if kind == "dpt":
+        return lambda m, xs, fkw: m(tuple(xs))
+    if kind == "midas_large":
+        def call(m, xs, fkw):
+            for i, x in enumerate(xs):
+                getattr(m.pretrained, f"layer{i + 1}").value = x
+            return m(xs[0])
+        return call
+    return None
 
 
 def compare(a, b, what, tol=2e-5):
@@ -163,7 +217,7 @@ def do_modules(ref_blocks, ref_dpt, ref_sem, ref_small):
         ora = fx.fill_deterministic(cases.build_oracle(kind, kw))
         assert list(ref.state_dict().keys()) == list(ora.state_dict().keys()), name
         ora.load_state_dict(ref.state_dict(), strict=True)
-        r = cases.run_case(ref, name)
+        r = cases.run_case(ref, name, call=reference_call(kind))
         o = cases.run_case(ora, name)
         w = compare(r, o, name)
         print(f"module case {name}: oracle vs reference worst rel err {w:.2e} ({len(r)} tensors)")

@@ -351,7 +351,7 @@ class MidasLargeDecoder(nn.Module):
     def __init__(self, features=256, non_negative=True):
         super().__init__()
         self.scratch = make_scratch([256, 512, 1024, 2048], features, expand=False)
-        for i in (1, 2, 3, 4):
+        for i in (4, 3, 2, 1):        # registration order of midas_net.py:38-41 (state_dict key order)
             setattr(self.scratch, f"refinenet{i}", FusionBlockLarge(features))
         self.scratch.output_conv = nn.Sequential(
             nn.Conv2d(features, 128, 3, 1, 1),

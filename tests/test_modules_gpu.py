@@ -25,7 +25,8 @@ TOL_OUT, TOL_GRAD, TOL_BUF = 3e-2, 5e-2, 2e-3
 # cancellation amplifies rounding noise.  One BN level (ResidualBlock): 8e-2; CrossAttention stacks six BN levels
 # (three down, three up) around the attention: 0.25.  The kernels themselves are pinned tightly, op by op, in
 # tests/test_ops_gpu.py.
-TOL_GRAD_BY_KIND = {"rcu": 5e-2, "fusion": 5e-2, "dinohead": 0.1, "resblock": 0.1, "xattn": 0.25}
+TOL_GRAD_BY_KIND = {"rcu": 5e-2, "fusion": 5e-2, "dinohead": 0.1, "resblock": 0.1, "xattn": 0.25, "rcu_large": 5e-2,
+                    "fusion_large": 5e-2, "dpt": 0.1, "midas_large": 0.1}
 
 
 def build_product(pkg, kind, kw):
@@ -41,6 +42,15 @@ def build_product(pkg, kind, kw):
         return dpt_depth.Dinov2Head(1, 384, 128, use_bn=False, out_channels=[128, 256, 512, 512], use_clstoken=False)
     if kind == "xattn":
         return midas_semantics.CrossAttention(kw["dim"], window_size=16)
+    if kind == "rcu_large":
+        return blocks.ResidualConvUnit(kw["features"])
+    if kind == "fusion_large":
+        return blocks.FeatureFusionBlock(kw["features"])
+    if kind == "dpt":          # decoder + head of DPTDepthModel; the timm backbone is third-party (forward_features)
+        return dpt_depth.DPTDepthModel(path=None, backbone="vitb_rn50_384", features=kw["features"], non_negative=True)
+    if kind == "midas_large":
+        from depth_b200.network import midas_net
+        return midas_net.MidasNet(None, features=kw["features"], non_negative=True)
     raise KeyError(kind)
 
 
@@ -81,6 +91,10 @@ def run(module, name, device):
         out = module(tuple(xs), fkw["ph"], fkw["pw"])
     elif kind == "fusion":
         out = module(*xs, **fkw)
+    elif kind in ("rcu_large", "fusion_large"):
+        out = module(*[x * 1.0 for x in xs])          # in-place ReLU on the input (blocks.py:263,274): non-leaf copies
+    elif kind in ("dpt", "midas_large") and hasattr(module, "forward_features"):
+        out = module.forward_features(*xs)            # product: decoder + head from the four feature maps
     else:
         out = module(*xs)
     # positive cotangent: gradients are coherent sums instead of random-sign cancellations

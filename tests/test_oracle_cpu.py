@@ -46,7 +46,8 @@ def test_small_stored_inputs_roundtrip(golden_loss):
         assert got[k] == pytest.approx(v, rel=1e-6, abs=1e-9)
 
 
-@pytest.mark.parametrize("name", ["rcu64", "fusion128_expand", "resblock_64_32", "xattn_multi", "dinohead"])
+@pytest.mark.parametrize("name", ["rcu64", "fusion128_expand", "resblock_64_32", "xattn_multi", "dinohead", "rcu_large64",
+                                  "fusion_large64", "fusion_large64_single", "dpt_decoder64", "midas_large_decoder64"])
 def test_oracle_modules_match_reference_golden(name):
     gold = np.load(os.path.join(ROOT, "tests", "golden", "model_golden.npz"))
     kind, kw, shapes, fkw = cases.CASES[name]
