@@ -298,3 +298,34 @@ def test_generate_test_predictions_matches_reference_recipe(pkg, tmp_path):
         got = np.load(tmp_path / f"sample_{i:04d}_depth.npy")
         assert got.shape == (426, 560)
         assert np.allclose(got, ref[i, 0].numpy(), rtol=1e-5, atol=1e-5)
+
+
+def test_config5_dpt_decoder_at_2x_resolution(pkg):
+    """BASELINE config 5: the largest configured decoder (DPT, features=256) at 2x input resolution (896x1152), bf16.
+    Feature maps [256, 512, 768, 768] at strides 4..32; forward against the fp32 oracle run by PyTorch on the GPU
+    (max-norm 5e-2), backward finite with every decoder parameter receiving a gradient except refinenet4.resConfUnit1
+    (single-input fusion block: never used, as in the reference)."""
+    from depth_b200.network import dpt_depth
+    import oracle.model as om
+    torch.manual_seed(0)
+    ora = fx.fill_deterministic(om.DPTDecoder(features=256))
+    round_weights_bf16_(ora)
+    prod = dpt_depth.DPTDepthModel(path=None, backbone="vitb_rn50_384", features=256, non_negative=True)
+    prod.load_state_dict(ora.state_dict(), strict=True)
+    ora, prod = ora.cuda().eval(), prod.cuda().train()
+    H, W = 896, 1152
+    feats = [fx.seeded((1, c, H // s, W // s), 900 + i).to(torch.bfloat16).float().cuda()
+             for i, (c, s) in enumerate(zip((256, 512, 768, 768), (4, 8, 16, 32)))]
+    with torch.no_grad():
+        ref = ora(*feats)
+    fin = [f.clone().requires_grad_(True) for f in feats]
+    out = prod.forward_features(*fin)
+    assert tuple(out.shape) == (1, H, W) and out.dtype == torch.float32
+    assert rel_err(out.detach().cpu(), ref.cpu()) < 5e-2
+    out.sum().backward()
+    for k, p in prod.named_parameters():
+        if k.startswith("scratch.refinenet4.resConfUnit1."):
+            assert p.grad is None, k
+        else:
+            assert p.grad is not None and bool(torch.isfinite(p.grad).all()), k
+    assert all(f.grad is not None and bool(torch.isfinite(f.grad).all()) for f in fin)
