@@ -905,7 +905,18 @@ class _Concat(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        return g[..., :ctx.split], g[..., ctx.split:]
+        # dense halves (one strided-read copy kernel each): strided views would make every consumer - and autograd's
+        # own gradient accumulation - fall back to slow non-vectorised elementwise kernels
+        g = g if g.stride(3) == 1 else g.contiguous()
+        B, H, W, C = g.shape
+        ld = _ld(g)
+        npix = B * H * W
+        outs = []
+        for lo, hi in ((0, ctx.split), (ctx.split, C)):
+            t = _nhwc(B, H, W, hi - lo, g.device)
+            L.check(L.lib().dp_copy_channels(g.data_ptr() + 2 * lo, ld, L.ptr(t), hi - lo, npix, hi - lo, L.stream()))
+            outs.append(t)
+        return outs[0], outs[1]
 
 
 def concat_channels(a, b):
