@@ -16,7 +16,7 @@ from . import distributed as D
 
 class GraphedTrainStep:
     def __init__(self, model, optimizer, config, example_inputs, example_targets, use_rgb=True, world=None,
-                 warmup=3, side_wgrad=True):
+                 warmup=3, side_wgrad=True, overlap_h2d=False):
         assert example_inputs.is_cuda and example_targets.is_cuda
         self.model, self.opt, self.cfg, self.use_rgb = model, optimizer, config, use_rgb
         self.side_wgrad = side_wgrad
@@ -25,10 +25,11 @@ class GraphedTrainStep:
         self.red = D.GradientAllReducer(model.parameters(), world)
         self.out = None
         self._copy = self._sx = self._st = self._consumed = None
-        # The copy-stream overlap pays off on a single GPU (+3 % end to end).  With NCCL collectives captured in the graph
-        # (world > 1) the same scheme doubled the end-to-end step time at N = 4 (measured; H2D bandwidth itself was a full
-        # 55 GB/s per rank), so multi-rank steps copy on the main stream (+2 ms per step).
-        self._overlap_h2d = self.red.world == 1 and not os.environ.get("DP_NO_COPY_STREAM")
+        # Optional copy-stream overlap of the next batch's H2D with the current replay (overlap_h2d=True, single rank
+        # only).  Measured end to end it ranged from +2 % to -7 % against plain main-stream copies across runs on one
+        # GPU, and it doubled the step time at N = 4 with NCCL collectives captured in the graph (the H2D bandwidth
+        # itself was a full 55 GB/s per rank), so the default is the predictable main-stream copy (+2.6 ms per step).
+        self._overlap_h2d = bool(overlap_h2d) and self.red.world == 1
         self._step = 0
         self._hout = [torch.empty(8, dtype=torch.float32).pin_memory() for _ in range(2)]
         self._done = [torch.cuda.Event(), torch.cuda.Event()]
@@ -63,9 +64,9 @@ class GraphedTrainStep:
         """one optimisation step; inputs/targets may be (pinned) host or device tensors, or None to reuse the static
         batch.  Returns the device tensor of loss scalars (index with depth_b200._lib.L_*); no host sync.
 
-        On a single GPU host batches travel on a copy stream into a staging buffer, so the H2D transfer of step i
-        overlaps the graph replay of step i-1 (the caller is never blocked); a device-to-device copy then refreshes the
-        graph's static inputs.  Multi-rank steps copy on the main stream.  The loss scalars of every step are copied to pinned host memory asynchronously (`loss_dict`)."""
+        Host batches are copied into the graph's static inputs on the main stream (asynchronously from pinned memory);
+        with overlap_h2d=True (single rank) they travel on a copy stream into a staging buffer instead, so the H2D
+        transfer of step i can overlap the graph replay of step i-1.  The loss scalars of every step are copied to pinned host memory asynchronously (`loss_dict`)."""
         main = torch.cuda.current_stream()
         if (inputs is not None or targets is not None) and not self._overlap_h2d:
             if inputs is not None:                 # copies on the main stream (no overlap with the previous replay)
