@@ -131,3 +131,54 @@ def test_load_model_reads_reference_checkpoint_formats(tmp_path):
         sd = m.state_dict()
         assert list(sd.keys()) == list(src.state_dict().keys())
         assert all(torch.equal(sd[k], v) for k, v in src.state_dict().items())
+
+
+def test_attention_segments_match_window_loop():
+    """Host logic of the last-writer attention (ops.attention_segments): every token's key range equals the range of the
+    LAST window of the reference loop (midas_semantics.py:93-112) that contains it, and the 32-query work items tile the
+    query runs exactly."""
+    import depth_b200
+    from depth_b200 import ops
+    for hr, wr, ws in [(56, 72, 16), (8, 12, 16), (20, 24, 16), (7, 9, 4)]:
+        items, segs, unowned = ops.attention_segments(hr, wr, ws, "cpu")
+        N = hr * wr
+        owner = [None] * N
+        for h in range((hr + ws - 1) // ws):
+            for w in range((wr + ws - 1) // ws):
+                lo = h * ws * wr + w * ws
+                hi = min(min(h * ws + ws, hr) * wr + min(w * ws + ws, wr), N)
+                for i in range(lo, hi):
+                    owner[i] = (lo, hi)
+        got = [None] * N
+        for q0, nq, klo, khi in items.tolist():
+            assert 1 <= nq <= 32
+            for i in range(q0, q0 + nq):
+                assert got[i] is None, "work items must not overlap"
+                got[i] = (klo, khi)
+        assert got == owner
+        assert unowned == [i for i in range(N) if owner[i] is None]
+        covered = sorted(i for a, b, _, _ in segs.tolist() for i in range(a, b))
+        assert covered == [i for i in range(N) if owner[i] is not None]
+
+
+def test_fused_encoder_structure_recognition():
+    """network/encoder_fused.supported(): the gen-efficientnet-shaped trunk is accepted; anything it cannot execute
+    exactly (biased conv, squeeze-excite, unknown block) sends the caller back to the PyTorch path."""
+    import torch.nn as nn
+    import depth_b200
+    from depth_b200 import standins
+    from depth_b200.network import blocks, encoder_fused
+    blocks.hub_load = standins.hub_load_standin
+    p = blocks._make_pretrained_efficientnet_lite3(False)
+    assert encoder_fused.supported(p)
+    geo = encoder_fused._dw_geom(p.layer2[0][0].conv_dw, 112, 144)
+    assert geo == (2, 2, 2, 56, 72)
+    q = blocks._make_pretrained_efficientnet_lite3(False)
+    q.layer3[0][1].conv_pw = nn.Conv2d(96, 576, 1, bias=True)
+    assert not encoder_fused.supported(q)
+    r = blocks._make_pretrained_efficientnet_lite3(False)
+    r.layer2[0][0].se = nn.Sequential(nn.Conv2d(8, 8, 1))
+    assert not encoder_fused.supported(r)
+    s = blocks._make_pretrained_efficientnet_lite3(False)
+    s.layer4[0][0] = nn.Sequential(nn.Conv2d(136, 232, 3, 2, 1), nn.ReLU())
+    assert not encoder_fused.supported(s)
