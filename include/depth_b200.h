@@ -28,7 +28,7 @@ extern "C" {
 typedef struct CUstream_st* cudaStream_t;
 #endif
 
-#define DP_ABI_VERSION 1
+#define DP_ABI_VERSION 2
 
 int dp_abi_version(void);
 const char* dp_last_error(void);
@@ -113,16 +113,20 @@ int dp_delta_counts(const float* pred, const float* target, const double* moment
 int dp_metrics_combine(const double* moments, const unsigned long long* counts, int B, int H, int W, int nthr,
                        float* out, cudaStream_t stream);
 
-/* evaluation.py:157-166 for one batch in one fused pass (8 B/px of HBM traffic): a thread-block cluster per sample
- * accumulates the SI / AbsRel moments, exchanges them through distributed shared memory and counts the scale-aligned
- * delta thresholds (util.py:183-207) on a second, L2-resident sweep; then the scalar combine.
+/* evaluation.py:157-166 for one batch in one streaming pass (8 B/px of HBM traffic): groups of co-resident CTAs keep
+ * their slices of (pred, target) in shared memory (1-D bulk copies on mbarriers), accumulate the SI / AbsRel moments
+ * (util.py:129-156, 210-219), exchange the per-sample scale through `workspace` and count the scale-aligned delta
+ * thresholds (util.py:183-207) from shared memory; then a parallel combine.  Shapes the streaming kernel cannot take
+ * (H*W not a multiple of 4, bases not 16-byte aligned) run the thread-block-cluster kernel (second sweep from L2).
  * thresholds: HOST pointer.  moments: device double[B][DP_NMOM] (S1, S2, AR filled).  counts: device u64[B][nthr].
  * out: device float[2+nthr] = SI-RMSE, AbsRel, delta_k (batch means).
+ * workspace: device, >= dp_eval_metrics_workspace(B,H,W) bytes (contents irrelevant on entry).
  * fast_math = 0: IEEE logf / division (the reference's arithmetic); 1: MUFU lg2 / rcp (within ~1e-6 relative of the exact
- * path; bandwidth-bound instead of issue-bound). */
+ * path; HBM-bound instead of issue-bound). */
+size_t dp_eval_metrics_workspace(int B, int H, int W);
 int dp_eval_metrics(const float* pred, const float* target, int B, int H, int W, const float* thresholds, int nthr,
                     float eps, int fast_math, double* moments, unsigned long long* counts, float* out,
-                    cudaStream_t stream);
+                    void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Convolutions (NHWC bf16 activations, fp32 accumulation in TMEM)

@@ -35,7 +35,7 @@ def lib():
         _declare(_lib)
         if os.environ.get("DP_TRACE"):
             _lib = _Traced(_lib)
-        if _lib.dp_abi_version() != 1:
+        if _lib.dp_abi_version() != 2:
             raise DepthB200Error("libdepth_b200.so ABI version mismatch")
     return _lib
 
@@ -90,7 +90,8 @@ class _Sig:
     dp_delta_counts = (c_int, [P, P, P, c_int, c_int, c_int, ctypes.POINTER(c_float), c_int, c_int, c_float, P, P,
                                c_size_t, P])
     dp_metrics_combine = (c_int, [P, P, c_int, c_int, c_int, c_int, P, P])
-    dp_eval_metrics = (c_int, [P, P, c_int, c_int, c_int, ctypes.POINTER(c_float), c_int, c_float, c_int, P, P, P, P])
+    dp_eval_metrics_workspace = (c_size_t, [c_int, c_int, c_int])
+    dp_eval_metrics = (c_int, [P, P, c_int, c_int, c_int, ctypes.POINTER(c_float), c_int, c_float, c_int, P, P, P, P, c_size_t, P])
     dp_conv2d_tc_grid = (c_int, [c_int, c_int, c_int, c_int, c_int, c_int])
     dp_conv2d_tc = (c_int, [P, c_ll, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, P, P, c_ll, P, c_ll, c_int, P,
                             c_ll, P, c_ll, c_int, P, P])

@@ -11,6 +11,8 @@
 // Algorithmic HBM bytes: 8 B/px forward (pred+target fp32 once), 12 B/px backward (re-read + grad
 // write); the edge term adds 12 B/px of RGB per pass plus a 12 B/px min/max pre-pass.
 #include "common.cuh"
+#include "tc.cuh"
+#include <cstdlib>
 #include "../../include/depth_b200.h"
 
 namespace {
@@ -421,24 +423,28 @@ __global__ void counts_finalize_kernel(const unsigned long long* __restrict__ pa
   counts[(size_t)b * nthr + k] = s;
 }
 
-// evaluation.py:157-166 scalars for one batch from moments + counts
-__global__ void metrics_combine_kernel(const double* __restrict__ mom, const unsigned long long* __restrict__ counts,
-                                       int B, int H, int W, int nthr, float* __restrict__ out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// evaluation.py:157-166 scalars for one batch from moments + counts (one block; fixed summation order)
+__global__ void __launch_bounds__(256) metrics_combine_kernel(const double* __restrict__ mom,
+                                                              const unsigned long long* __restrict__ counts, int B, int H,
+                                                              int W, int nthr, float* __restrict__ out) {
+  __shared__ double red[(2 + DP_MAX_THR) * 32];
   const double n = (double)H * W;
-  double si = 0.0, ar = 0.0;
-  for (int b = 0; b < B; ++b) {
+  double v[2 + DP_MAX_THR];
+#pragma unroll
+  for (int k = 0; k < 2 + DP_MAX_THR; ++k) v[k] = 0.0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
     const double* m = mom + (size_t)b * NMOM;
-    const float v = (float)(m[DP_M_S2] / n - (m[DP_M_S1] * m[DP_M_S1]) / (n * n));
-    si += (double)sqrtf(v);
-    ar += m[DP_M_AR];
+    v[0] += (double)sqrtf((float)(m[DP_M_S2] / n - (m[DP_M_S1] * m[DP_M_S1]) / (n * n)));
+    v[1] += m[DP_M_AR];
+#pragma unroll
+    for (int k = 0; k < DP_MAX_THR; ++k)
+      if (k < nthr) v[2 + k] += (double)(float)((double)counts[(size_t)b * nthr + k] / n);
   }
-  out[0] = (float)(si / B);
-  out[1] = (float)(ar / ((double)B * n));
-  for (int k = 0; k < nthr; ++k) {
-    double acc = 0.0;
-    for (int b = 0; b < B; ++b) acc += (double)(float)((double)counts[(size_t)b * nthr + k] / n);
-    out[2 + k] = (float)(acc / B);
+  block_sum<2 + DP_MAX_THR>(v, red);
+  if (threadIdx.x == 0) {
+    out[0] = (float)(v[0] / B);
+    out[1] = (float)(v[1] / ((double)B * n));
+    for (int k = 0; k < nthr; ++k) out[2 + k] = (float)(v[2 + k] / B);
   }
 }
 
@@ -621,6 +627,383 @@ __global__ void __cluster_dims__(kEvalCluster, 1, 1) __launch_bounds__(TPB) eval
   cluster_sync_all();   // keep every CTA's shared memory alive until rank 0 has read it
 }
 
+// ---- streaming evaluation kernel (default path): each input byte crosses HBM once and is classified from shared memory ----
+// One CTA per SM.  A group of G co-resident CTAs owns one sample at a time (the launch is cooperative, so every CTA of
+// a group is resident); the groups walk the batch in parallel.  Each CTA keeps its slice of (pred, target) in one of
+// kEvSlots shared-memory slots, filled by 1-D bulk copies (cp.async.bulk, completion on mbarriers).  Roles, iteration i:
+//     consumers (28 warps) : sweep 1 of sample i (moments, as the chunks land)  ->  sweep 2 of sample i-1 (delta counts
+//                            from shared memory, releasing each chunk as soon as it has been classified)
+//     exchanger (1 warp)   : posts the CTA's moment partials of sample i to global memory, collects the S1 partials of
+//                            the other CTAs of the group, adds the G values in rank order and hands the per-sample scale
+//                            to the consumers - one sweep ahead of where they need it
+//     producer  (1 warp)   : refills every released chunk with the sample kEvSlots iterations ahead
+// DRAM traffic is the algorithmic 8 B/px (ncu: 1.344 GB for 1.342 GB of input); the second sweep touches neither HBM nor L2.
+constexpr int kEvCW = 28;                   // consumer warps
+constexpr int kEvCT = kEvCW * 32;           // consumer threads
+constexpr int kEvThreads = kEvCT + 64;      // + producer warp + exchange warp
+constexpr int kEvChunkPx = kEvCT * 4;       // pixels per chunk: one float4 of each operand per consumer thread
+constexpr int kEvMaxChunks = 8;             // chunks per slot
+constexpr int kEvSlots = 2;                 // shared-memory slots = samples in flight per CTA
+constexpr int kEvStaticAllowance = 3072;    // static shared memory the plan leaves room for
+
+struct EvsArgs {
+  const float* pred;
+  const float* target;
+  int B, nthr, G, ngroups, per;  // per: pixels per slice (multiple of 4)
+  long long n;
+  float eps;
+  float thr[DP_MAX_THR];
+  unsigned long long* ll;        // [B][G][2] flagged S1 words, zero before launch
+  double* mom_part;              // [B][G][4]: S1, S2, AR
+  unsigned long long* cnt_part;  // [B][G][DP_MAX_THR]
+};
+
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(tc::smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(tc::smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(kEvCT) : "memory"); }
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// The exchange warp of the streaming kernels.  Per sample: wait for the consumers' per-warp moment partials, post the CTA's
+// sums, collect the S1 partials of all G CTAs of the group, add them in rank order (the same value in every CTA) and
+// publish the per-sample scale exp(-S1/n) (util.py:200) to the consumers.
+// S1 travels as two 8-byte words {flag = 1 : 32 bits of the double}: an aligned 8-byte store is a single transaction, so
+// data and flag land together - no fence, no counter, one round trip to post and one polling read to collect.  The
+// words are zeroed by the entry point before the launch.
+template <bool LOG2_UNITS>
+__device__ __forceinline__ void exchange_loop(unsigned long long* ll, double* mom_part, int G, int ngroups, int group,
+                                              int rank, int nit, long long n, uint64_t* red_full, uint64_t* scale_full,
+                                              const double* s_red /*[2][3*kEvCW]*/, float* s_scale /*[2]*/) {
+  const int lane = threadIdx.x & 31;
+  for (int it = 0; it < nit; ++it) {
+    const int b = group + it * ngroups;
+    if (lane == 0) {
+      tc::mbar_wait(&red_full[it & 1], (it >> 1) & 1);
+      double m0 = 0.0, m1 = 0.0, m2 = 0.0;
+      const double* r = s_red + (it & 1) * 3 * kEvCW;
+      for (int w = 0; w < kEvCW; ++w) { m0 += r[w]; m1 += r[kEvCW + w]; m2 += r[2 * kEvCW + w]; }
+      if (LOG2_UNITS) { m0 *= 0.6931471805599453; m1 *= 0.6931471805599453 * 0.6931471805599453; }
+      unsigned long long* w = ll + ((size_t)b * G + rank) * 2;
+      const unsigned long long w0 = (1ull << 32) | (unsigned)__double2hiint(m0);
+      const unsigned long long w1 = (1ull << 32) | (unsigned)__double2loint(m0);
+      asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(w), "l"(w0), "l"(w1) : "memory");
+      double* mp = mom_part + ((size_t)b * G + rank) * 4;      // for eval_gather_kernel
+      __stcg(mp + 0, m0); __stcg(mp + 1, m1); __stcg(mp + 2, m2);
+    }
+    __syncwarp();
+    double S1 = 0.0;
+    const unsigned long long* gw = ll + (size_t)b * G * 2;
+    for (int g0 = 0; g0 < G; g0 += 32) {
+      const int g = g0 + lane;
+      unsigned long long w0 = 1ull << 32, w1 = 1ull << 32;
+      unsigned spins = 0;
+      long long t0 = 0;
+      for (;;) {
+        if (g < G)
+          asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(gw + (size_t)g * 2) : "memory");
+        const bool ok = (w0 >> 32) == 1ull && (w1 >> 32) == 1ull;
+        if (__all_sync(0xffffffffu, ok)) break;
+        if ((++spins & 255u) == 0) {        // bounded: a protocol bug traps instead of hanging
+          const long long now = clock64();
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > 4000000000LL) __trap();
+        }
+      }
+      const double v = g < G ? __hiloint2double((int)(unsigned)w0, (int)(unsigned)w1) : 0.0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) S1 += __shfl_sync(0xffffffffu, v, i);
+    }
+    if (lane == 0) {
+      s_scale[it & 1] = expf((float)(-S1 / (double)n));
+      tc::mbar_arrive(&scale_full[it & 1]);
+    }
+    __syncwarp();
+  }
+}
+
+// util.py:204-205 for one pixel, both quotients as written there
+template <int NTS, bool RT>
+__device__ __forceinline__ void delta_px_generic(float al, float t, const float* thr, int nthr, unsigned (&cnt)[NTS]) {
+  const float r1 = __fdiv_rn(al, t), r2 = __fdiv_rn(t, al);
+#pragma unroll
+  for (int k = 0; k < NTS; ++k)
+    if ((!RT || k < nthr) && r1 < thr[k] && r2 < thr[k]) cnt[k]++;
+}
+
+// FAST   : MUFU lg2 / rcp instead of IEEE logf / division (as eval_fused_kernel).
+// ONEDIV : every threshold is > 1, so of the two quotients al/t and t/al only the one with the larger numerator can
+//          reach a threshold (the other is <= 1 by monotonicity of rounding): one division per pixel, same counts.
+//          Needs both operands non-negative or of mixed sign; a pixel group with a negative pair takes the generic path.
+template <bool FAST, bool ONEDIV, int NT>
+__global__ void __launch_bounds__(kEvThreads, 1) eval_stream_kernel(EvsArgs a) {
+  constexpr int NS = kEvSlots;
+  constexpr int NTS = NT ? NT : DP_MAX_THR;
+  constexpr int CH = kEvChunkPx;
+  extern __shared__ __align__(128) unsigned char ev_smem[];
+  __shared__ uint64_t full[NS][kEvMaxChunks], empty[NS][kEvMaxChunks];
+  __shared__ uint64_t red_full[2], scale_full[2];
+  __shared__ double s_red[2][3 * kEvCW];
+  __shared__ unsigned s_cred[2][NTS * kEvCW];
+  __shared__ float s_scale[2];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int group = blockIdx.x / a.G, rank = blockIdx.x - group * a.G;
+  const long long n = a.n;
+  const long long px0 = (long long)rank * a.per;
+  const long long left = n - px0;
+  const int len = left <= 0 ? 0 : (left > a.per ? a.per : (int)left);   // multiple of 4 (n and per are)
+  const int nch = (len + CH - 1) / CH;
+  const int nit = group < a.B ? (a.B - group + a.ngroups - 1) / a.ngroups : 0;   // samples of this group
+  const size_t slot_floats = (size_t)a.per * 2;                                  // pred slice, then target slice
+
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s)
+      for (int c = 0; c < kEvMaxChunks; ++c) { tc::mbar_init(&full[s][c], 1); tc::mbar_init(&empty[s][c], kEvCW); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&red_full[i], kEvCW); tc::mbar_init(&scale_full[i], 1); }
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (warp == kEvCW) {   // ---- producer warp: one lane streams the slices in ----
+    if (lane == 0) {
+      int slot = 0, ph = 0;
+      for (int it = 0; it < nit; ++it) {
+        const int b = group + it * a.ngroups;
+        const float* P = a.pred + (size_t)b * n + px0;
+        const float* T = a.target + (size_t)b * n + px0;
+        float* Ps = reinterpret_cast<float*>(ev_smem) + slot * slot_floats;
+        float* Ts = Ps + a.per;
+        for (int c = 0; c < nch; ++c) {
+          if (it >= NS) tc::mbar_wait(&empty[slot][c], ph ^ 1);
+          const int cl = min(CH, len - c * CH);
+          tc::mbar_expect_tx(&full[slot][c], (uint32_t)cl * 8u);
+          bulk_g2s(Ps + c * CH, P + c * CH, (uint32_t)cl * 4u, &full[slot][c]);
+          bulk_g2s(Ts + c * CH, T + c * CH, (uint32_t)cl * 4u, &full[slot][c]);
+        }
+        if (++slot == NS) { slot = 0; ph ^= 1; }
+      }
+    }
+    return;
+  }
+
+  if (warp == kEvCW + 1) {   // ---- exchange warp: per-sample scale through global memory, off the consumers' path ----
+    exchange_loop<FAST>(a.ll, a.mom_part, a.G, a.ngroups, group, rank, nit, n, red_full, scale_full, &s_red[0][0], s_scale);
+    return;
+  }
+
+  // ---- consumer warps ----
+  const int len4 = len >> 2;
+  const float eps = a.eps;
+  int slot1 = 0, ph1 = 0, slot2 = 0;
+  for (int it = 0; it <= nit; ++it) {
+    if (it < nit) {
+      // sweep 1 of sample `it`: moments (fp32 over 4 pixels, fp64 beyond) as the slice lands
+      const float4* P4 = reinterpret_cast<const float4*>(reinterpret_cast<float*>(ev_smem) + slot1 * slot_floats) + tid;
+      const float4* T4 = reinterpret_cast<const float4*>(reinterpret_cast<float*>(ev_smem) + slot1 * slot_floats + a.per) + tid;
+      double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+      for (int c = 0; c < nch; ++c) {
+        tc::mbar_wait(&full[slot1][c], ph1);
+        if (c * kEvCT + tid < len4) {   // one float4 of each operand per thread per chunk
+          const float4 p4 = P4[c * kEvCT], t4 = T4[c * kEvCT];
+          const float pv[4] = {p4.x, p4.y, p4.z, p4.w}, tv[4] = {t4.x, t4.y, t4.z, t4.w};
+          float s1 = 0.f, s2 = 0.f, ar = 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float d, e;
+            if (FAST) {   // d in log2 units; scaled by ln 2 once per CTA
+              d = lg2_approx(pv[q] + eps) - lg2_approx(tv[q] + eps);
+              e = fabsf(tv[q] - pv[q]) * rcp_approx(tv[q] + 1e-6f);
+            } else {
+              d = logf(pv[q] + eps) - logf(tv[q] + eps);                 // util.py:143
+              e = __fdiv_rn(fabsf(tv[q] - pv[q]), tv[q] + 1e-6f);        // util.py:218
+            }
+            s1 += d;
+            s2 += d * d;
+            ar += e;
+          }
+          acc0 += s1; acc1 += s2; acc2 += ar;
+        }
+      }
+      acc0 = warp_sum(acc0); acc1 = warp_sum(acc1); acc2 = warp_sum(acc2);
+      if (lane == 0) {
+        double* r = s_red[it & 1];
+        r[warp] = acc0; r[kEvCW + warp] = acc1; r[2 * kEvCW + warp] = acc2;
+        tc::mbar_arrive(&red_full[it & 1]);
+      }
+      if (++slot1 == NS) { slot1 = 0; ph1 ^= 1; }
+    }
+    if (it >= 1) {
+      // sweep 2 of sample `it - 1`: scale-aligned delta counts from shared memory; finished chunks go back to the producer
+      const int j = it - 1;
+      const int b = group + j * a.ngroups;
+      tc::mbar_wait(&scale_full[j & 1], (j >> 1) & 1);
+      const float s = s_scale[j & 1];
+      const float4* P4 = reinterpret_cast<const float4*>(reinterpret_cast<float*>(ev_smem) + slot2 * slot_floats) + tid;
+      const float4* T4 = reinterpret_cast<const float4*>(reinterpret_cast<float*>(ev_smem) + slot2 * slot_floats + a.per) + tid;
+      unsigned cnt[NTS];
+#pragma unroll
+      for (int k = 0; k < NTS; ++k) cnt[k] = 0;
+      for (int c = 0; c < nch; ++c) {
+        if (c * kEvCT + tid < len4) {
+          const float4 p4 = P4[c * kEvCT], t4 = T4[c * kEvCT];
+          const float al[4] = {p4.x * s, p4.y * s, p4.z * s, p4.w * s}, tv[4] = {t4.x, t4.y, t4.z, t4.w};
+          bool generic = !ONEDIV;
+          if (ONEDIV) {
+            const float mx = fminf(fminf(fmaxf(al[0], tv[0]), fmaxf(al[1], tv[1])),
+                                   fminf(fmaxf(al[2], tv[2]), fmaxf(al[3], tv[3])));
+            generic = mx < 0.f;   // some pair is negative in both operands
+          }
+          if (generic) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) delta_px_generic<NTS, NT == 0>(al[q], tv[q], a.thr, a.nthr, cnt);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const bool sel = al[q] > tv[q];
+              const float num = sel ? al[q] : tv[q], den = sel ? tv[q] : al[q];
+              const float r = FAST ? num * rcp_approx(den) : __fdiv_rn(num, den);
+#pragma unroll
+              for (int k = 0; k < NTS; ++k)
+                if ((NT || k < a.nthr) && r < a.thr[k]) cnt[k]++;    // NaN / inf compare false, as torch.max + lt
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&empty[slot2][c]);
+      }
+      unsigned* cr = s_cred[j & 1];
+#pragma unroll
+      for (int k = 0; k < NTS; ++k) {
+        const unsigned v = __reduce_add_sync(0xffffffffu, cnt[k]);
+        if (lane == 0) cr[k * kEvCW + warp] = v;
+      }
+      bar_consumers();   // also orders the reuse of s_cred[j & 1] two samples later
+      if (tid < NTS && (NT || tid < a.nthr)) {
+        unsigned long long tot = 0;
+        for (int w = 0; w < kEvCW; ++w) tot += cr[tid * kEvCW + w];
+        a.cnt_part[((size_t)b * a.G + rank) * DP_MAX_THR + tid] = tot;
+      }
+      if (++slot2 == NS) slot2 = 0;
+    }
+  }
+}
+
+// partials of the streaming kernels -> per-sample moments / counts and the per-sample terms of evaluation.py:157-166.
+// One warp per sample: lanes take the CTAs of the group (all partial loads of a sample in flight at once), a butterfly
+// in a fixed pattern adds them.
+__global__ void __launch_bounds__(1024) eval_gather_kernel(const double* __restrict__ mom_part,
+                                                           const unsigned long long* __restrict__ cnt_part, int B, int G,
+                                                           double n, int nthr, double* __restrict__ moments,
+                                                           unsigned long long* __restrict__ counts,
+                                                           double* __restrict__ terms /*[B][2 + DP_MAX_THR]*/) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  double m0 = 0.0, m1 = 0.0, m2 = 0.0;
+  unsigned long long c[DP_MAX_THR];
+#pragma unroll
+  for (int k = 0; k < DP_MAX_THR; ++k) c[k] = 0;
+  for (int g = lane; g < G; g += 32) {
+    const double* mp = mom_part + ((size_t)b * G + g) * 4;
+    m0 += mp[0]; m1 += mp[1]; m2 += mp[2];
+#pragma unroll
+    for (int k = 0; k < DP_MAX_THR; ++k)
+      if (k < nthr) c[k] += cnt_part[((size_t)b * G + g) * DP_MAX_THR + k];
+  }
+  m0 = warp_sum(m0); m1 = warp_sum(m1); m2 = warp_sum(m2);
+#pragma unroll
+  for (int k = 0; k < DP_MAX_THR; ++k) {
+    if (k < nthr) {
+      c[k] = __reduce_add_sync(0xffffffffu, (unsigned)c[k]);   // a sample has < 2^32 pixels
+    }
+  }
+  if (lane == 0) {
+    moments[(size_t)b * NMOM + DP_M_S1] = m0;
+    moments[(size_t)b * NMOM + DP_M_S2] = m1;
+    moments[(size_t)b * NMOM + DP_M_AR] = m2;
+    double* t = terms + (size_t)b * (2 + DP_MAX_THR);
+    t[0] = (double)sqrtf((float)(m1 / n - (m0 * m0) / (n * n)));   // util.py:152-154 (sqroot=True)
+    t[1] = m2;
+    for (int k = 0; k < nthr; ++k) {
+      counts[(size_t)b * nthr + k] = c[k];
+      t[2 + k] = (double)(float)((double)c[k] / n);                // util.py:205 per-sample mean
+    }
+  }
+}
+
+// per-sample terms -> the batch means evaluation.py:157-166 reports (one block, fixed order)
+__global__ void __launch_bounds__(256) eval_means_kernel(const double* __restrict__ terms, int B, double n, int nthr,
+                                                         float* __restrict__ out) {
+  __shared__ double red[(2 + DP_MAX_THR) * 32];
+  double v[2 + DP_MAX_THR];
+#pragma unroll
+  for (int k = 0; k < 2 + DP_MAX_THR; ++k) v[k] = 0.0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const double* t = terms + (size_t)b * (2 + DP_MAX_THR);
+#pragma unroll
+    for (int k = 0; k < 2 + DP_MAX_THR; ++k)
+      if (k < 2 + nthr) v[k] += t[k];
+  }
+  block_sum<2 + DP_MAX_THR>(v, red);
+  if (threadIdx.x == 0) {
+    out[0] = (float)(v[0] / B);
+    out[1] = (float)(v[1] / ((double)B * n));
+    for (int k = 0; k < nthr; ++k) out[2 + k] = (float)(v[2 + k] / B);
+  }
+}
+
+struct EvalPlan {
+  bool ok;
+  int G, ngroups, per;
+  size_t dyn;
+};
+
+// Pure function of the shape (and the device's shared memory / SM count), shared by the workspace query and the launch:
+// one CTA per SM, kEvSlots slices resident per CTA, and the CTAs-per-sample count G that wastes the fewest thread
+// slots (slices that are whole chunks) and SMs (groups * G close to the SM count).
+inline EvalPlan eval_plan(long long n, int B) {
+  EvalPlan p{};
+  if (n % 4 != 0 || n <= 0) return p;
+  int smem_sm = 0, sms = 0, dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return p;
+  if (cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) != cudaSuccess) return p;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return p;
+  const long long budget = ((long long)smem_sm - 1024 - kEvStaticAllowance) / kEvSlots;   // bytes per slot
+  if (budget < 4096) return p;
+  const long long gmin = (n * 8 + budget - 1) / budget;
+  double best = -1.0;
+  for (long long G = gmin; G <= sms && G < gmin + 32; ++G) {
+    long long per = (n + G - 1) / G;
+    per = (per + 3) & ~3LL;
+    const long long nch = (per + kEvChunkPx - 1) / kEvChunkPx;
+    if (per * 8 > budget || nch > kEvMaxChunks) continue;
+    long long groups = sms / G;
+    if (groups > B) groups = B;
+    const double eff = (double)n / (double)(nch * kEvChunkPx * G) * (double)(groups * G) / (double)sms;
+    if (eff > best + 1e-9) {
+      best = eff;
+      p.G = (int)G; p.per = (int)per; p.ngroups = (int)groups;
+    }
+  }
+  if (best < 0.0) return p;
+  p.dyn = (size_t)p.per * 8 * kEvSlots;
+  p.ok = true;
+  return p;
+}
+
+inline size_t eval_ws_ll_bytes(int B, int G) { return (((size_t)B * G * 2 * sizeof(unsigned long long)) + 255) & ~(size_t)255; }
+
 inline int pick_chunks(int B, int H) {
   int c = (4 * kNumSMs + B - 1) / B;
   if (c < 1) c = 1;
@@ -745,25 +1128,86 @@ int dp_delta_counts(const float* pred, const float* target, const double* moment
 int dp_metrics_combine(const double* moments, const unsigned long long* counts, int B, int H, int W, int nthr,
                        float* out, cudaStream_t stream) {
   DP_CHECK_ARG(moments && counts && out, "dp_metrics_combine: null pointer");
-  metrics_combine_kernel<<<1, 32, 0, stream>>>(moments, counts, B, H, W, nthr, out);
+  metrics_combine_kernel<<<1, 256, 0, stream>>>(moments, counts, B, H, W, nthr, out);
   DP_CHECK_LAUNCH("metrics_combine_kernel");
   return DP_OK;
 }
 
 
-/* evaluation.py:157-166 in two launches: the fused cluster kernel (moments + aligned delta counts, 8 B/px of HBM
- * traffic) and the scalar combine.  out[0]=SI-RMSE, out[1]=AbsRel, out[2+k]=delta_k (batch means). */
+static size_t eval_ws_bytes(int B, const EvalPlan& p) {
+  return eval_ws_ll_bytes(B, p.G) + (size_t)B * p.G * 4 * sizeof(double) +
+         (size_t)B * p.G * DP_MAX_THR * sizeof(unsigned long long) + (size_t)B * (2 + DP_MAX_THR) * sizeof(double);
+}
+
+size_t dp_eval_metrics_workspace(int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) return 256;
+  const EvalPlan p = eval_plan((long long)H * W, B);
+  return p.ok ? eval_ws_bytes(B, p) : 256;
+}
+
+/* evaluation.py:157-166: a streaming kernel (8 B/px of HBM traffic, pixels classified from shared memory) and the
+ * parallel combine; shapes it cannot take (pixel count not a multiple of 4, unaligned bases, slices larger than the
+ * chip's shared memory) go through the cluster kernel.  out[0]=SI-RMSE, out[1]=AbsRel, out[2+k]=delta_k (batch means). */
 int dp_eval_metrics(const float* pred, const float* target, int B, int H, int W, const float* thresholds, int nthr,
                     float eps, int fast_math, double* moments, unsigned long long* counts, float* out,
-                    cudaStream_t stream) {
+                    void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   DP_CHECK_ARG(pred && target && thresholds && moments && counts && out, "dp_eval_metrics: null pointer");
   DP_CHECK_ARG(B > 0 && H > 0 && W > 0, "dp_eval_metrics: bad shape %d %d %d", B, H, W);
   DP_CHECK_ARG(nthr >= 1 && nthr <= DP_MAX_THR, "dp_eval_metrics: nthr %d out of [1,%d]", nthr, DP_MAX_THR);
+  const long long n = (long long)H * W;
+  const bool vec = (n % 4 == 0) && aligned16(pred) && aligned16(target);
+
+  const EvalPlan plan = vec ? eval_plan(n, B) : EvalPlan{};
+  if (plan.ok) {
+    DP_CHECK_ARG(workspace, "dp_eval_metrics: null workspace");
+    if (workspace_bytes < eval_ws_bytes(B, plan))
+      return dp_set_error(DP_ERR_WORKSPACE, "dp_eval_metrics: workspace %zu < %zu", workspace_bytes, eval_ws_bytes(B, plan));
+    unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+    unsigned long long* ll = reinterpret_cast<unsigned long long*>(ws);
+    double* mom_part = reinterpret_cast<double*>(ws + eval_ws_ll_bytes(B, plan.G));
+    unsigned long long* cnt_part =
+        reinterpret_cast<unsigned long long*>(ws + eval_ws_ll_bytes(B, plan.G) + (size_t)B * plan.G * 4 * sizeof(double));
+    EvsArgs a;
+    a.pred = pred; a.target = target; a.B = B; a.nthr = nthr; a.G = plan.G; a.ngroups = plan.ngroups; a.per = plan.per;
+    a.n = n; a.eps = eps; a.ll = ll; a.mom_part = mom_part; a.cnt_part = cnt_part;
+    bool onediv = true;
+    for (int k = 0; k < DP_MAX_THR; ++k) {
+      a.thr[k] = k < nthr ? thresholds[k] : 0.f;
+      if (k < nthr && !(thresholds[k] > 1.0f)) onediv = false;
+    }
+#define DP_EVS_PICK(F, O)                                                                       \
+  (nthr == 3 ? (const void*)eval_stream_kernel<F, O, 3>                                         \
+             : (nthr == 1 ? (const void*)eval_stream_kernel<F, O, 1> : (const void*)eval_stream_kernel<F, O, 0>))
+    const void* fn;
+    if (fast_math) fn = onediv ? DP_EVS_PICK(true, true) : DP_EVS_PICK(true, false);
+    else fn = onediv ? DP_EVS_PICK(false, true) : DP_EVS_PICK(false, false);
+#undef DP_EVS_PICK
+    void* kargs[1] = {&a};
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.dyn);
+    int resident = 0;
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, fn, kEvThreads, plan.dyn);
+    if (e != cudaSuccess)
+      return dp_set_error(DP_ERR_CUDA, "dp_eval_metrics: launch setup failed: %s", cudaGetErrorString(e));
+    if (resident < 1)
+      return dp_set_error(DP_ERR_UNSUPPORTED, "dp_eval_metrics: a CTA with %zu B of shared memory is not resident", plan.dyn);
+    e = cudaMemsetAsync(ll, 0, (size_t)B * plan.G * 2 * sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return dp_set_error(DP_ERR_CUDA, "dp_eval_metrics: memset failed: %s", cudaGetErrorString(e));
+    e = cudaLaunchCooperativeKernel(fn, dim3(plan.ngroups * plan.G), dim3(kEvThreads), kargs, plan.dyn, stream);
+    dp_count_launch(1);
+    if (e != cudaSuccess)
+      return dp_set_error(DP_ERR_CUDA, "eval_stream_kernel launch failed: %s", cudaGetErrorString(e));
+    double* terms = reinterpret_cast<double*>(cnt_part + (size_t)B * plan.G * DP_MAX_THR);
+    eval_gather_kernel<<<(B + 31) / 32, 1024, 0, stream>>>(mom_part, cnt_part, B, plan.G, (double)n, nthr, moments, counts, terms);
+    DP_CHECK_LAUNCH("eval_gather_kernel");
+    eval_means_kernel<<<1, 256, 0, stream>>>(terms, B, (double)n, nthr, out);
+    DP_CHECK_LAUNCH("eval_means_kernel");
+    return DP_OK;
+  }
+
   EvalArgs a;
-  a.pred = pred; a.target = target; a.B = B; a.nthr = nthr; a.n = (long long)H * W; a.eps = eps;
+  a.pred = pred; a.target = target; a.B = B; a.nthr = nthr; a.n = n; a.eps = eps;
   for (int k = 0; k < DP_MAX_THR; ++k) a.thr[k] = k < nthr ? thresholds[k] : 0.f;
   a.moments = moments; a.counts = counts;
-  const bool vec = (a.n % 4 == 0) && aligned16(pred) && aligned16(target);
   const dim3 grid(B * kEvalCluster);
 #define DP_EVAL_LAUNCH(V, F)                                                        \
   do {                                                                              \
@@ -777,7 +1221,7 @@ int dp_eval_metrics(const float* pred, const float* target, int B, int H, int W,
   else DP_EVAL_LAUNCH(1, false);
 #undef DP_EVAL_LAUNCH
   DP_CHECK_LAUNCH("eval_fused_kernel");
-  metrics_combine_kernel<<<1, 32, 0, stream>>>(moments, counts, B, H, W, nthr, out);
+  metrics_combine_kernel<<<1, 256, 0, stream>>>(moments, counts, B, H, W, nthr, out);
   DP_CHECK_LAUNCH("metrics_combine_kernel");
   return DP_OK;
 }

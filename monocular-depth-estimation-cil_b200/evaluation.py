@@ -3,7 +3,7 @@
 The reference walks a DataLoader, calls scale_invariant_loss(sqroot=True), absolute_relative_error and three
 delta_thres per batch (five passes over pred/target plus six `.item()`-style syncs), weights each by the batch length,
 clips to N_SAMPLES and prints the averages.  Here every batch costs ONE fused kernel launch
-(`util.evaluation_metrics`: a thread-block cluster per sample), the weighted sums stay on the device, and with
+(`util.evaluation_metrics`: the streaming kernel, each input byte read from HBM once), the weighted sums stay on the device, and with
 `torch.distributed` initialised the samples are sharded by rank and the partial sums meet in one all-reduce of
 2 + N_DELTA + 1 doubles.
 """

@@ -138,8 +138,9 @@ def test_shape_assert(pkg):
 
 @pytest.mark.parametrize("B,H,W", [(3, 37, 53), (2, 64, 96), (9, 448, 576)])
 def test_fused_eval_counts_match_two_pass_counts(pkg, B, H, W):
-    """the cluster kernel (one launch, DSMEM exchange of the per-sample scale) must classify exactly the pixels the
-    separate moments + delta_counts passes classify: integer equality of the per-batch counts."""
+    """the fused kernels (37x53: pixel count not a multiple of 4 -> the thread-block-cluster kernel with its DSMEM
+    exchange of the per-sample scale; the others -> the streaming kernel) must classify exactly the pixels the separate
+    moments + delta_counts passes classify: integer equality of the per-batch counts."""
     g = torch.Generator().manual_seed(B * H + W)
     t = (torch.rand(B, 1, H, W, generator=g) * 9.9 + 0.1).cuda()
     p = (t.cpu() * torch.exp(0.1 * torch.randn(B, 1, H, W, generator=g)) * 1.3).cuda()
@@ -152,6 +153,39 @@ def test_fused_eval_counts_match_two_pass_counts(pkg, B, H, W):
     assert torch.allclose(out[2:], want, rtol=0, atol=1e-7), (out[2:], want)
     assert abs(out[0].item() - pkg.scale_invariant_loss(p, t, sqroot=True).item()) <= 1e-6
     assert abs(out[1].item() - pkg.absolute_relative_error(p, t).item()) <= 1e-6 * out[1].item()
+
+
+@pytest.mark.parametrize("B,H,W,thr", [
+    (40, 448, 576, [1.05, 1.05 ** 2, 1.05 ** 3]),      # several samples per CTA group: mbarrier phases, chunk refill
+    (5, 426, 560, [1.25]),                             # raw test-set resolution, ragged last slice, one threshold
+    (3, 448, 576, [1.1, 1.3]),                         # run-time threshold count, one-division form
+    (3, 128, 160, [0.9, 1.0, 1.2, 1.5]),               # thresholds <= 1: both quotients as written in util.py:204
+    (2, 896, 1152, [1.05, 1.05 ** 2, 1.05 ** 3]),      # config-5 resolution: more CTAs per sample
+])
+def test_streaming_eval_counts_exact(pkg, B, H, W, thr):
+    """the streaming kernel (slices in shared memory, one IEEE division per pixel when every threshold is > 1) must
+    classify exactly the pixels the two-pass path (both quotients, util.py:204-205) classifies - integer equality -
+    including zero predictions, zero targets and fast_math staying inside the contract."""
+    g = torch.Generator().manual_seed(B * H + W)
+    t = (torch.rand(B, 1, H, W, generator=g) * 9.9 + 0.1)
+    p = t * torch.exp(0.1 * torch.randn(B, 1, H, W, generator=g)) * 1.3
+    p[:, :, 3:9, 5:17] = 0.0
+    t[:, :, 20:23, 40:47] = 0.0
+    p[0, :, 21, 41] = 0.0           # 0 / 0
+    p, t = p.cuda(), t.cuda()
+    out = pkg.evaluation_metrics(p, t, thresholds=thr).double().cpu()
+    cnt = pkg.delta_counts(p, t, thr, aligned=True).cpu()
+    n = H * W
+    want = (cnt.double() / n).float().double().mean(0)
+    assert torch.allclose(out[2:], want, rtol=0, atol=1e-7), (out[2:], want)
+    assert abs(out[0].item() - pkg.scale_invariant_loss(p, t, sqroot=True).item()) <= 1e-6
+    assert abs(out[1].item() - pkg.absolute_relative_error(p, t).item()) <= 1e-6 * abs(out[1].item())
+    fast = pkg.evaluation_metrics(p, t, thresholds=thr, fast_math=True).double().cpu()
+    assert abs(fast[0] - out[0]) <= 1e-5 * abs(out[0])
+    assert float((fast[2:] - out[2:]).abs().max()) <= 1e-4
+    # same call again: the arrival counters are reset by the entry point, results are deterministic
+    again = pkg.evaluation_metrics(p, t, thresholds=thr).double().cpu()
+    assert torch.equal(again, out)
 
 
 def test_fused_eval_fast_math_within_contract(pkg):

@@ -29,3 +29,6 @@ print("delta counts pass ms", t(lambda: ps.counts([1.05, 1.05 ** 2, 1.05 ** 3], 
 print("evaluation_metrics ms", t(lambda: depth_b200.evaluation_metrics(pp, tt)))
 print("Gpx/s", EB * H * W / (t(lambda: depth_b200.evaluation_metrics(pp, tt)) / 1e3) / 1e9)
 print("copy (read+write 8B/px) ms", t(lambda: tt.copy_(pp)))
+print("fast_math Gpx/s", EB * H * W / (t(lambda: depth_b200.evaluation_metrics(pp, tt, fast_math=True)) / 1e3) / 1e9)
+print("exact out", depth_b200.evaluation_metrics(pp, tt).tolist())
+print("fast  out", depth_b200.evaluation_metrics(pp, tt, fast_math=True).tolist())

@@ -1,4 +1,5 @@
-"""ncu target: the fused evaluation-metrics kernel at the bench's eval shape (650 x 448 x 576)."""
+"""ncu target: the streaming evaluation-metrics kernel (exact and fast-math) at the bench's eval shape (650 x 448 x 576):
+ncu --set full --clock-control none --import-source on -k regex:eval_stream_kernel -s 4 -c 2 python tools/ncu_eval.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, depth_b200
