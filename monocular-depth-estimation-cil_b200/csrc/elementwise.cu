@@ -32,6 +32,12 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 __device__ __forceinline__ uint4 ld8(const bf16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ void st8(bf16* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+// read-only 16-byte load the compiler may not sink below later loads (keeps a batch of loads in flight together)
+__device__ __forceinline__ uint4 ld8_issue(const bf16* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
 
 inline int grid_for(size_t items, int tpb = 256, int max_waves = 8) {
   size_t b = (items + tpb - 1) / tpb;
@@ -99,30 +105,93 @@ __host__ __device__ inline float resize_scale(int in, int out, int align) {
   return (float)in / (float)out;
 }
 
-__global__ void resize_fwd_kernel(const bf16* __restrict__ src, long long src_ld, int B, int Hi, int Wi, int C,
-                                  bf16* __restrict__ dst, long long dst_ld, int Ho, int Wo, int align) {
-  const int C8 = C / 8;
-  const size_t total = (size_t)B * Ho * Wo * C8;
-  const float sy = resize_scale(Hi, Ho, align), sx = resize_scale(Wi, Wo, align);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % C8);
-    size_t p = i / C8;
-    const int ox = (int)(p % Wo); p /= Wo;
-    const int oy = (int)(p % Ho);
-    const int b = (int)(p / Ho);
-    const float fy = src_coord(oy, sy, align), fx = src_coord(ox, sx, align);
-    const int y0 = (int)fy, x0 = (int)fx;
-    const int y1 = y0 + (y0 < Hi - 1 ? 1 : 0), x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
-    const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
-    const bf16* s = src + (size_t)b * Hi * Wi * src_ld + c8 * 8;
-    float a[8], bq[8], c[8], d[8], o[8];
-    unpack8(ld8(s + ((size_t)y0 * Wi + x0) * src_ld), a);
-    unpack8(ld8(s + ((size_t)y0 * Wi + x1) * src_ld), bq);
-    unpack8(ld8(s + ((size_t)y1 * Wi + x0) * src_ld), c);
-    unpack8(ld8(s + ((size_t)y1 * Wi + x1) * src_ld), d);
+// One thread = 8 channels of one output column over kRsRows consecutive output rows.  grid: x = ceil(Wo * C/8 / 256),
+// y = ceil(Ho / kRsRows), z = B.  When up-sampling, kRsRows output rows draw on at most four consecutive source rows:
+// those are loaded once (8 loads, all issued before the first use), interpolated horizontally once, and every output
+// row interpolates vertically between two of the four results (a block-uniform pick) - column arithmetic, address
+// arithmetic and half of the interpolation are shared by the rows, the arithmetic per output is unchanged.  Otherwise (down-sampling) each output row is produced on its own.
+constexpr int kRsRows = 4;
+
+template <int K0, int K1>
+__device__ __forceinline__ void vlerp_store(const float (&h)[4][8], float hy, float ly, bf16* dst) {
+  float o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = hy * (hx * a[j] + lx * bq[j]) + ly * (hx * c[j] + lx * d[j]);
-    st8(dst + (((size_t)b * Ho + oy) * Wo + ox) * dst_ld + c8 * 8, pack8(o));
+  for (int j = 0; j < 8; ++j) o[j] = hy * h[K0][j] + ly * h[K1][j];
+  st8(dst, pack8(o));
+}
+
+__global__ void __launch_bounds__(256, 2) resize_fwd_kernel(const bf16* __restrict__ src, long long src_ld, int B, int Hi,
+                                                            int Wi, int C, bf16* __restrict__ dst, long long dst_ld,
+                                                            int Ho, int Wo, int align, float sy, float sx) {
+  const int C8 = C / 8;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Wo * C8) return;
+  const int ox = idx / C8, c8 = idx - ox * C8;
+  const int oy0 = blockIdx.y * kRsRows, b = blockIdx.z;
+  const float fx = src_coord(ox, sx, align);
+  const int x0 = (int)fx;
+  const int x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
+  const float lx = fx - x0, hx = 1.f - lx;
+  const bf16* s = src + (size_t)b * Hi * Wi * src_ld + c8 * 8;
+  bf16* d = dst + (((size_t)b * Ho + oy0) * Wo + ox) * dst_ld + c8 * 8;
+  const int nrows = min(kRsRows, Ho - oy0);
+
+  int y0[kRsRows], y1[kRsRows];
+  float ly[kRsRows];
+#pragma unroll
+  for (int r = 0; r < kRsRows; ++r) {
+    const float fy = src_coord(min(oy0 + r, Ho - 1), sy, align);
+    y0[r] = (int)fy;
+    y1[r] = y0[r] + (y0[r] < Hi - 1 ? 1 : 0);
+    ly[r] = fy - y0[r];
+  }
+  const int yb = y0[0];
+  if (y1[kRsRows - 1] - yb <= 3) {
+    uint4 ua[4], ub[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const size_t row = (size_t)min(yb + k, Hi - 1) * Wi;
+      ua[k] = ld8_issue(s + (row + x0) * src_ld);
+      ub[k] = ld8_issue(s + (row + x1) * src_ld);
+    }
+    float h[4][8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float a[8], bq[8];
+      unpack8(ua[k], a); unpack8(ub[k], bq);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) h[k][j] = hx * a[j] + lx * bq[j];
+    }
+#pragma unroll
+    for (int r = 0; r < kRsRows; ++r) {
+      if (r < nrows) {
+        // a block-uniform branch picks the two source rows, so the arithmetic per output stays exactly the four-corner
+        // formula F.interpolate uses: hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11)
+        bf16* dr = d + (size_t)r * Wo * dst_ld;
+        const float hy = 1.f - ly[r];
+        switch ((y0[r] - yb) * 4 + (y1[r] - yb)) {
+          case 0: vlerp_store<0, 0>(h, hy, ly[r], dr); break;
+          case 1: vlerp_store<0, 1>(h, hy, ly[r], dr); break;
+          case 5: vlerp_store<1, 1>(h, hy, ly[r], dr); break;
+          case 6: vlerp_store<1, 2>(h, hy, ly[r], dr); break;
+          case 10: vlerp_store<2, 2>(h, hy, ly[r], dr); break;
+          case 11: vlerp_store<2, 3>(h, hy, ly[r], dr); break;
+          default: vlerp_store<3, 3>(h, hy, ly[r], dr); break;
+        }
+      }
+    }
+  } else {
+    for (int r = 0; r < nrows; ++r) {
+      const float hy = 1.f - ly[r];
+      float a[8], bq[8], c[8], dd[8], o[8];
+      unpack8(ld8(s + ((size_t)y0[r] * Wi + x0) * src_ld), a);
+      unpack8(ld8(s + ((size_t)y0[r] * Wi + x1) * src_ld), bq);
+      unpack8(ld8(s + ((size_t)y1[r] * Wi + x0) * src_ld), c);
+      unpack8(ld8(s + ((size_t)y1[r] * Wi + x1) * src_ld), dd);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = hy * (hx * a[j] + lx * bq[j]) + ly[r] * (hx * c[j] + lx * dd[j]);
+      st8(d + (size_t)r * Wo * dst_ld, pack8(o));
+    }
   }
 }
 
@@ -145,98 +214,106 @@ __global__ void resize_planes_f32_kernel(const float* __restrict__ src, int plan
   }
 }
 
-// Backward as a gather: input pixel (iy,ix) collects from every output pixel whose 2x2 footprint touches it.
-// The candidate output range is found by inverting the coordinate map with one pixel of slack, then
-// each candidate re-derives its own (y0,y1,ly) exactly as the forward pass did - deterministic, no atomics.
-__device__ __forceinline__ void out_range(int i, int in, int out, float scale, int align, int& lo, int& hi) {
-  // outputs o with floor(src(o)) in {i-1, i}
-  float inv = scale > 0.f ? 1.f / scale : 0.f;
-  float a = align ? (i - 1) * inv : ((i - 1) + 0.5f) * inv - 0.5f;
-  float b = align ? (i + 1) * inv : ((i + 1) + 0.5f) * inv - 0.5f;
-  lo = (int)floorf(a) - 1;
-  hi = (int)ceilf(b) + 1;
-  if (scale <= 0.f) { lo = 0; hi = out - 1; }
-  if (lo < 0) lo = 0;
-  if (hi > out - 1) hi = out - 1;
-  (void)in;
+// Backward as a gather: input pixel (iy,ix) collects from every output pixel whose 2x2 footprint touches it; each
+// candidate re-derives its own (x0, x1, lx) exactly as the forward pass did - deterministic, no atomics.
+// weight of output index o on input index i along one axis (the forward's own (x0, x1, lx), re-derived)
+__device__ __forceinline__ float axis_weight(int o, int i, int in, float scale, int align) {
+  const float f = src_coord(o, scale, align);
+  const int i0 = (int)f;
+  const int i1 = i0 + (i0 < in - 1 ? 1 : 0);
+  const float l = f - i0;
+  float w = 0.f;
+  if (i0 == i) w += 1.f - l;
+  if (i1 == i) w += l;
+  return w;
 }
 
-__global__ void resize_bwd_kernel(const bf16* __restrict__ gout, long long g_ld, int B, int Hi, int Wi, int C,
-                                  bf16* __restrict__ gin, long long gin_ld, int Ho, int Wo, int align) {
+// The run of outputs that contribute to input i along one axis: `first` and the weights of first .. first+RW-1.
+// Output o contributes when its source coordinate lies in (i-1, i+1); inverting the coordinate map gives the first
+// candidate to within one position, the weights themselves are the forward's own (axis_weight).  Returns false when the
+// run is longer than RW (down-sampling): the caller then walks [lo, hi].
+template <int RW>
+__device__ __forceinline__ bool axis_window(int i, int in, int out, float scale, float inv, int align, int& lo, int& hi,
+                                            int& first, float (&w)[RW]) {
+  const float a = align ? (i - 1) * inv : ((i - 1) + 0.5f) * inv - 0.5f;
+  const float bnd = align ? (i + 1) * inv : ((i + 1) + 0.5f) * inv - 0.5f;
+  lo = max(0, (int)floorf(a) - 1);
+  hi = min(out - 1, (int)ceilf(bnd) + 1);
+  if (scale <= 0.f) { lo = 0; hi = out - 1; }
+  int f = lo;
+#pragma unroll
+  for (int t = 0; t < 3; ++t)
+    if (f < hi && axis_weight(f, i, in, scale, align) == 0.f) ++f;
+  first = f;
+#pragma unroll
+  for (int q = 0; q < RW; ++q) w[q] = (f + q <= hi) ? axis_weight(f + q, i, in, scale, align) : 0.f;
+  bool ok = w[0] != 0.f || f >= hi;             // the advances reached the run (or there is none)
+  for (int o = f + RW; o <= hi && ok; ++o) ok = axis_weight(o, i, in, scale, align) == 0.f;
+  return ok;
+}
+
+// grid: x = ceil(Wi * C/8 / 256), y = Hi, z = B.  Up-sampling (every use on the hot path) touches at most a 4x4 window
+// of output pixels per input pixel: the sixteen 16-byte loads are issued unconditionally (zero weight where a slot
+// does not contribute), eight at a time ahead of their use; wider windows (down-sampling) walk the candidate range.
+__global__ void __launch_bounds__(256, 4) resize_bwd_kernel(const bf16* __restrict__ gout, long long g_ld, int B, int Hi,
+                                                            int Wi, int C, bf16* __restrict__ gin, long long gin_ld,
+                                                            int Ho, int Wo, int align, float sy, float sx, float inv_sy,
+                                                            float inv_sx) {
+  constexpr int RW = 4;
   const int C8 = C / 8;
-  const size_t total = (size_t)B * Hi * Wi * C8;
-  const float sy = resize_scale(Hi, Ho, align), sx = resize_scale(Wi, Wo, align);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % C8);
-    size_t p = i / C8;
-    const int ix = (int)(p % Wi); p /= Wi;
-    const int iy = (int)(p % Hi);
-    const int b = (int)(p / Hi);
-    int oy_lo, oy_hi, ox_lo, ox_hi;
-    out_range(iy, Hi, Ho, sy, align, oy_lo, oy_hi);
-    out_range(ix, Wi, Wo, sx, align, ox_lo, ox_hi);
-    float acc[8];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Wi * C8) return;
+  const int ix = idx / C8, c8 = idx - ix * C8;
+  const int iy = blockIdx.y, b = blockIdx.z;
+  float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    const bf16* g = gout + (size_t)b * Ho * Wo * g_ld + c8 * 8;
-    // column weights once per input pixel (the candidate window is at most a few outputs wide); wide windows
-    // (strong down-scaling) fall back to recomputing them per row
-    constexpr int NW = 8;
-    float wxs[NW];
-    const bool small_win = ox_hi - ox_lo < NW;
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const bf16* g = gout + (size_t)b * Ho * Wo * g_ld + c8 * 8;
+  float wx[RW], wy[RW];
+  int oy_lo, oy_hi, ox_lo, ox_hi, fx0, fy0;
+  const bool fx_ok = axis_window<RW>(ix, Wi, Wo, sx, inv_sx, align, ox_lo, ox_hi, fx0, wx);
+  const bool fy_ok = axis_window<RW>(iy, Hi, Ho, sy, inv_sy, align, oy_lo, oy_hi, fy0, wy);
+  if (fx_ok && fy_ok) {
 #pragma unroll
-    for (int k = 0; k < NW; ++k) {
-      const int ox = ox_lo + k;
-      float wx = 0.f;
-      if (small_win && ox <= ox_hi) {
-        const float fx = src_coord(ox, sx, align);
-        const int x0 = (int)fx;
-        const int x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
-        const float lx = fx - x0;
-        if (x0 == ix) wx += 1.f - lx;
-        if (x1 == ix) wx += lx;
+    for (int r0 = 0; r0 < RW; r0 += 2) {      // two rows = eight loads in flight per batch
+      uint4 u[2][RW];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int oy = min(fy0 + r0 + r, Ho - 1);
+#pragma unroll
+        for (int q = 0; q < RW; ++q) {
+          const int ox = min(fx0 + q, Wo - 1);
+          u[r][q] = ld8_issue(g + ((size_t)oy * Wo + ox) * g_ld);   // volatile asm: issued in program order, before the math
+        }
       }
-      wxs[k] = wx;
-    }
-    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
-      const float fy = src_coord(oy, sy, align);
-      const int y0 = (int)fy;
-      const int y1 = y0 + (y0 < Hi - 1 ? 1 : 0);
-      const float ly = fy - y0;
-      float wy = 0.f;
-      if (y0 == iy) wy += 1.f - ly;
-      if (y1 == iy) wy += ly;
-      if (wy == 0.f) continue;
-      if (small_win) {
 #pragma unroll
-        for (int k = 0; k < NW; ++k) {
-          if (wxs[k] == 0.f) continue;
+      for (int r = 0; r < 2; ++r) {
+#pragma unroll
+        for (int q = 0; q < RW; ++q) {
           float v[8];
-          unpack8(ld8(g + ((size_t)oy * Wo + ox_lo + k) * g_ld), v);
-          const float w = wy * wxs[k];
+          unpack8(u[r][q], v);
+          const float w = wy[r0 + r] * wx[q];
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[j] += w * v[j];
         }
-        continue;
       }
+    }
+  } else {
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+      const float wyv = axis_weight(oy, iy, Hi, sy, align);
+      if (wyv == 0.f) continue;
       for (int ox = ox_lo; ox <= ox_hi; ++ox) {
-        const float fx = src_coord(ox, sx, align);
-        const int x0 = (int)fx;
-        const int x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
-        const float lx = fx - x0;
-        float wx = 0.f;
-        if (x0 == ix) wx += 1.f - lx;
-        if (x1 == ix) wx += lx;
-        if (wx == 0.f) continue;
+        const float wxv = axis_weight(ox, ix, Wi, sx, align);
+        if (wxv == 0.f) continue;
         float v[8];
         unpack8(ld8(g + ((size_t)oy * Wo + ox) * g_ld), v);
-        const float w = wy * wx;
+        const float w = wyv * wxv;
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] += w * v[j];
       }
     }
-    st8(gin + (((size_t)b * Hi + iy) * Wi + ix) * gin_ld + c8 * 8, pack8(acc));
   }
+  st8(gin + (((size_t)b * Hi + iy) * Wi + ix) * gin_ld + c8 * 8, pack8(acc));
 }
 
 // ---- per-channel reductions over pixels --------------------------------------------------------------------
@@ -595,9 +672,11 @@ int dp_copy_channels(const void* src, long long src_ld, void* dst, long long dst
 int dp_resize_bilinear_nhwc(const void* src, long long src_ld, int B, int Hi, int Wi, int C, void* dst,
                             long long dst_ld, int Ho, int Wo, int align_corners, cudaStream_t stream) {
   DP_CHECK_ARG(src && dst && C % 8 == 0 && src_ld % 8 == 0 && dst_ld % 8 == 0, "dp_resize_bilinear_nhwc: bad arguments");
-  const size_t items = (size_t)B * Ho * Wo * (C / 8);
-  resize_fwd_kernel<<<grid_for(items), 256, 0, stream>>>((const bf16*)src, src_ld, B, Hi, Wi, C, (bf16*)dst, dst_ld, Ho,
-                                                         Wo, align_corners);
+  DP_CHECK_ARG(B > 0 && B <= 65535 && Ho > 0 && Ho <= 65535, "dp_resize_bilinear_nhwc: B / Ho out of the grid range");
+  const dim3 grid((unsigned)(((size_t)Wo * (C / 8) + 255) / 256), (unsigned)((Ho + kRsRows - 1) / kRsRows), (unsigned)B);
+  resize_fwd_kernel<<<grid, 256, 0, stream>>>((const bf16*)src, src_ld, B, Hi, Wi, C, (bf16*)dst, dst_ld, Ho, Wo,
+                                              align_corners, resize_scale(Hi, Ho, align_corners),
+                                              resize_scale(Wi, Wo, align_corners));
   DP_CHECK_LAUNCH("resize_fwd_kernel");
   return DP_OK;
 }
@@ -605,9 +684,11 @@ int dp_resize_bilinear_nhwc(const void* src, long long src_ld, int B, int Hi, in
 int dp_resize_bilinear_nhwc_bwd(const void* gout, long long g_ld, int B, int Hi, int Wi, int C, void* gin,
                                 long long gin_ld, int Ho, int Wo, int align_corners, cudaStream_t stream) {
   DP_CHECK_ARG(gout && gin && C % 8 == 0 && g_ld % 8 == 0 && gin_ld % 8 == 0, "dp_resize_bilinear_nhwc_bwd: bad arguments");
-  const size_t items = (size_t)B * Hi * Wi * (C / 8);
-  resize_bwd_kernel<<<grid_for(items), 256, 0, stream>>>((const bf16*)gout, g_ld, B, Hi, Wi, C, (bf16*)gin, gin_ld, Ho,
-                                                         Wo, align_corners);
+  DP_CHECK_ARG(B > 0 && B <= 65535 && Hi > 0 && Hi <= 65535, "dp_resize_bilinear_nhwc_bwd: B / Hi out of the grid range");
+  const dim3 grid((unsigned)(((size_t)Wi * (C / 8) + 255) / 256), (unsigned)Hi, (unsigned)B);
+  const float sy = resize_scale(Hi, Ho, align_corners), sx = resize_scale(Wi, Wo, align_corners);
+  resize_bwd_kernel<<<grid, 256, 0, stream>>>((const bf16*)gout, g_ld, B, Hi, Wi, C, (bf16*)gin, gin_ld, Ho, Wo,
+                                              align_corners, sy, sx, sy > 0.f ? 1.f / sy : 0.f, sx > 0.f ? 1.f / sx : 0.f);
   DP_CHECK_LAUNCH("resize_bwd_kernel");
   return DP_OK;
 }

@@ -45,7 +45,8 @@ def test_layout_roundtrip(pkg):
 @pytest.mark.parametrize("B,C,Hi,Wi,Ho,Wo,align", [
     (2, 32, 14, 18, 28, 36, True), (1, 64, 9, 11, 18, 22, False), (2, 16, 16, 20, 224 // 8, 280 // 8, True),
     (1, 8, 28, 35, 56, 72, True), (1, 32, 56, 70, 112, 144, True), (1, 8, 13, 17, 7, 9, True), (1, 8, 6, 6, 6, 6, False),
-    (1, 8, 10, 12, 20, 24, False)])
+    (1, 8, 10, 12, 20, 24, False), (1, 256, 14, 18, 28, 36, True), (1, 64, 32, 40, 56, 70, True),
+    (2, 128, 24, 30, 48, 60, False), (1, 40, 23, 29, 46, 57, True), (1, 16, 31, 33, 9, 11, False)])
 def test_resize_fwd_bwd(pkg, B, C, Hi, Wi, Ho, Wo, align):
     from depth_b200 import ops
     x = rnd(B, C, Hi, Wi, seed=3)
