@@ -181,7 +181,8 @@ int dp_conv2d_wgrad_tc_s2(const void* P, long long p_ld, int Hp, int Wp, int Cp,
 /* ------------------------------------------------------------------------------------------------
  * Layout / dtype boundaries and weight packing (csrc/layout.cu)
  * ---------------------------------------------------------------------------------------------- */
-/* reference modules speak NCHW fp32; (B,C,H,W) fp32 <-> (B,H,W,ld) bf16 */
+/* reference modules speak NCHW fp32; (B,C,H,W) fp32 <-> (B,H,W,ld) bf16.  Channels C..ld-1 of dst are left untouched,
+ * except for C <= 8 with dst_ld == 8 (the RGB input of the stem convolution), where they are written as zeros. */
 int dp_nchw_f32_to_nhwc_bf16(const float* src, int B, int C, int H, int W, void* dst, long long dst_ld, cudaStream_t stream);
 int dp_nhwc_bf16_to_nchw_f32(const void* src, long long src_ld, int B, int C, int H, int W, float* dst, cudaStream_t stream);
 int dp_cast_f32_to_bf16(const float* src, void* dst, size_t n, cudaStream_t stream);

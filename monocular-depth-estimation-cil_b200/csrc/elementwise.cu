@@ -82,14 +82,17 @@ __global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ 
   }
 }
 
-// dst[p][0..C) = src[p][0..C) with independent pixel strides (channel concat / slice copies)
+// dst[p][0..C) = src[p][0..C) with independent pixel strides (channel concat / slice copies).  IDX = unsigned when the
+// vector count fits 32 bits: the per-vector divide is then one multiply-shift sequence instead of a 64-bit division.
+template <typename IDX>
 __global__ void copy_channels_kernel(const bf16* __restrict__ src, long long src_ld, bf16* __restrict__ dst,
                                      long long dst_ld, size_t npix, int C8) {
-  const size_t total = npix * C8;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % C8);
-    const size_t p = i / C8;
-    st8(dst + p * dst_ld + c8 * 8, ld8(src + p * src_ld + c8 * 8));
+  const IDX total = (IDX)(npix * C8);
+  const IDX stride = (IDX)gridDim.x * blockDim.x;
+  for (IDX i = (IDX)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const IDX p = i / (IDX)C8;
+    const int c8 = (int)(i - p * (IDX)C8);
+    st8(dst + (size_t)p * dst_ld + c8 * 8, ld8(src + (size_t)p * src_ld + c8 * 8));
   }
 }
 
@@ -664,7 +667,11 @@ int dp_copy_channels(const void* src, long long src_ld, void* dst, long long dst
                      cudaStream_t stream) {
   DP_CHECK_ARG(src && dst && C % 8 == 0 && src_ld % 8 == 0 && dst_ld % 8 == 0, "dp_copy_channels: bad arguments");
   if (npix == 0) return DP_OK;
-  copy_channels_kernel<<<grid_for(npix * (C / 8)), 256, 0, stream>>>((const bf16*)src, src_ld, (bf16*)dst, dst_ld, npix, C / 8);
+  const size_t items = npix * (C / 8);
+  if (items < (size_t)0x7fffff00u)
+    copy_channels_kernel<unsigned><<<grid_for(items), 256, 0, stream>>>((const bf16*)src, src_ld, (bf16*)dst, dst_ld, npix, C / 8);
+  else
+    copy_channels_kernel<size_t><<<grid_for(items), 256, 0, stream>>>((const bf16*)src, src_ld, (bf16*)dst, dst_ld, npix, C / 8);
   DP_CHECK_LAUNCH("copy_channels_kernel");
   return DP_OK;
 }

@@ -26,6 +26,25 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int C, int HW
   }
 }
 
+// C <= 8 channels into 8-channel pixels (the RGB input of the stem convolution): one thread per pixel, plane reads
+// coalesced across the warp, one 16-byte store per pixel with the pad channels written as zeros
+__global__ void __launch_bounds__(256) nchw_to_nhwc8_kernel(const float* __restrict__ src, int C, int HW,
+                                                            bf16* __restrict__ dst) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  const float* s = src + (size_t)blockIdx.y * C * HW + p;
+  float v[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) v[c] = c < C ? __ldg(s + (size_t)c * HW) : 0.f;
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(dst + ((size_t)blockIdx.y * HW + p) * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 __global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ src, long long ld, int C, int HW, float* __restrict__ dst) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
@@ -76,6 +95,11 @@ int dp_nchw_f32_to_nhwc_bf16(const float* src, int B, int C, int H, int W, void*
                              cudaStream_t stream) {
   DP_CHECK_ARG(src && dst && B > 0 && C > 0 && dst_ld >= C, "dp_nchw_f32_to_nhwc_bf16: bad arguments");
   const int HW = H * W;
+  if (C <= 8 && dst_ld == 8 && B <= 65535 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    nchw_to_nhwc8_kernel<<<dim3(dp::ceil_div(HW, 256), B), 256, 0, stream>>>(src, C, HW, reinterpret_cast<bf16*>(dst));
+    DP_CHECK_LAUNCH("nchw_to_nhwc8_kernel");
+    return DP_OK;
+  }
   dim3 grid(dp::ceil_div(HW, 32), dp::ceil_div(C, 32), B), block(32, 8);
   nchw_to_nhwc_kernel<<<grid, block, 0, stream>>>(src, C, HW, reinterpret_cast<bf16*>(dst), dst_ld);
   DP_CHECK_LAUNCH("nchw_to_nhwc_kernel");

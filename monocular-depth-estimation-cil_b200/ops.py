@@ -550,7 +550,7 @@ class _StemConv(torch.autograd.Function):
         xs = x.detach()
         if xs.dtype != torch.float32 or not xs.is_contiguous():
             xs = xs.float().contiguous()
-        x8 = torch.zeros(B, H, W, 8, dtype=BF16, device=x.device)
+        x8 = torch.empty(B, H, W, 8, dtype=BF16, device=x.device)     # pad channels are zeroed by the converter
         L.check(L.lib().dp_nchw_f32_to_nhwc_bf16(L.ptr(xs), B, Ci, H, W, L.ptr(x8), 8, L.stream()))
         wp = torch.zeros(K * K, O, 8, dtype=BF16, device=x.device)
         wp[:, :, :Ci] = weight.detach().permute(2, 3, 0, 1).reshape(K * K, O, Ci).to(BF16)

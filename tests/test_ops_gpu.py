@@ -42,6 +42,19 @@ def test_layout_roundtrip(pkg):
     assert torch.equal(x.grad, torch.full_like(x, 0.5))
 
 
+@pytest.mark.parametrize("C", [1, 3, 8])
+def test_layout_small_c_into_8_channel_pixels(pkg, C):
+    """the stem's input path: C <= 8 planes into 8-channel NHWC pixels, pad channels written as zeros (the destination
+    starts as NaN), values rounded to bf16 exactly as the tiled converter does."""
+    from depth_b200 import _lib as L
+    x = rnd(2, C, 13, 21, seed=11).cuda()
+    out = torch.full((2, 13, 21, 8), float("nan"), dtype=BF, device="cuda")
+    L.check(L.lib().dp_nchw_f32_to_nhwc_bf16(L.ptr(x), 2, C, 13, 21, L.ptr(out), 8, L.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(out[..., :C].float(), x.permute(0, 2, 3, 1).to(BF).float())
+    assert bool((out[..., C:] == 0).all())
+
+
 @pytest.mark.parametrize("B,C,Hi,Wi,Ho,Wo,align", [
     (2, 32, 14, 18, 28, 36, True), (1, 64, 9, 11, 18, 22, False), (2, 16, 16, 20, 224 // 8, 280 // 8, True),
     (1, 8, 28, 35, 56, 72, True), (1, 32, 56, 70, 112, 144, True), (1, 8, 13, 17, 7, 9, True), (1, 8, 6, 6, 6, 6, False),
