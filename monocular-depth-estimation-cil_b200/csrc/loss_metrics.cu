@@ -969,16 +969,12 @@ struct EvalPlan {
   size_t dyn;
 };
 
-// Pure function of the shape (and the device's shared memory / SM count), shared by the workspace query and the launch:
-// one CTA per SM, kEvSlots slices resident per CTA, and the CTAs-per-sample count G that wastes the fewest thread
-// slots (slices that are whole chunks) and SMs (groups * G close to the SM count).
-inline EvalPlan eval_plan(long long n, int B) {
+// Pure function of the shape and of the device's shared memory per SM / SM count, shared by the workspace query and
+// the launch: one CTA per SM, kEvSlots slices resident per CTA, and the CTAs-per-sample count G that wastes the fewest
+// thread slots (slices that are whole chunks) and SMs (groups * G close to the SM count).
+inline EvalPlan eval_plan_for(long long n, int B, int smem_sm, int sms) {
   EvalPlan p{};
-  if (n % 4 != 0 || n <= 0) return p;
-  int smem_sm = 0, sms = 0, dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return p;
-  if (cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) != cudaSuccess) return p;
-  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return p;
+  if (n % 4 != 0 || n <= 0 || B <= 0 || sms <= 0) return p;
   const long long budget = ((long long)smem_sm - 1024 - kEvStaticAllowance) / kEvSlots;   // bytes per slot
   if (budget < 4096) return p;
   const long long gmin = (n * 8 + budget - 1) / budget;
@@ -1000,6 +996,14 @@ inline EvalPlan eval_plan(long long n, int B) {
   p.dyn = (size_t)p.per * 8 * kEvSlots;
   p.ok = true;
   return p;
+}
+
+inline EvalPlan eval_plan(long long n, int B) {
+  int smem_sm = 0, sms = 0, dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return EvalPlan{};
+  if (cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) != cudaSuccess) return EvalPlan{};
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return EvalPlan{};
+  return eval_plan_for(n, B, smem_sm, sms);
 }
 
 inline size_t eval_ws_ll_bytes(int B, int G) { return (((size_t)B * G * 2 * sizeof(unsigned long long)) + 255) & ~(size_t)255; }
@@ -1137,6 +1141,17 @@ int dp_metrics_combine(const double* moments, const unsigned long long* counts, 
 static size_t eval_ws_bytes(int B, const EvalPlan& p) {
   return eval_ws_ll_bytes(B, p.G) + (size_t)B * p.G * 4 * sizeof(double) +
          (size_t)B * p.G * DP_MAX_THR * sizeof(unsigned long long) + (size_t)B * (2 + DP_MAX_THR) * sizeof(double);
+}
+
+int dp_eval_metrics_plan(long long pixels, int B, int smem_per_sm, int sms, int* ctas_per_sample, int* groups,
+                         int* slice_pixels, size_t* dynamic_smem) {
+  const EvalPlan p = eval_plan_for(pixels, B, smem_per_sm, sms);
+  if (!p.ok) return 0;
+  if (ctas_per_sample) *ctas_per_sample = p.G;
+  if (groups) *groups = p.ngroups;
+  if (slice_pixels) *slice_pixels = p.per;
+  if (dynamic_smem) *dynamic_smem = p.dyn;
+  return 1;
 }
 
 size_t dp_eval_metrics_workspace(int B, int H, int W) {
