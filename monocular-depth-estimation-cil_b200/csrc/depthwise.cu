@@ -73,9 +73,11 @@ __global__ void __launch_bounds__(TPB, 2) dw_fwd_kernel(DwArgs a) {
   for (int j = 0; j < 8; ++j) { st_s[j] = 0.f; st_q[j] = 0.f; }
   if (active) {
     for (int st = blockIdx.x * nslots + slot; st < nstrips; st += gridDim.x * nslots) {
-      const int sx = st % strips;
-      const int r = st / strips;
-      const int oy = r % a.Ho, b = r / a.Ho;
+      // rows vary fastest: the strip slots of a block (and the blocks next to it) work on vertically adjacent strips
+      // at the same time, so the K-row input windows overlap in L1 / L2 instead of being fetched K times
+      const int oy = st % a.Ho;
+      const int r = st / a.Ho;
+      const int sx = r % strips, b = r / strips;
       const int ox0 = sx * TX;
       float2 acc2[TX][4];            // packed f32x2 accumulators: one FFMA2 does two of the eight channels
 #pragma unroll
