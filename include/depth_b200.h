@@ -124,10 +124,10 @@ int dp_metrics_combine(const double* moments, const unsigned long long* counts, 
  * fast_math = 0: IEEE logf / division (the reference's arithmetic); 1: MUFU lg2 / rcp (within ~1e-6 relative of the exact
  * path; HBM-bound instead of issue-bound). */
 size_t dp_eval_metrics_workspace(int B, int H, int W);
-/* The streaming kernel's decomposition for `pixels` per sample on a device with `smem_per_sm` bytes of shared memory and
- * `sms` SMs (host arithmetic only, no CUDA call): CTAs per sample, sample groups in flight, pixels per CTA slice and
+/* The streaming kernel's decomposition for `pixels` per sample and `nthr` thresholds on a device with `smem_per_sm`
+ * bytes of shared memory and `sms` SMs (host arithmetic only, no CUDA call): CTAs per sample, sample groups in flight, pixels per CTA slice and
  * dynamic shared memory per CTA.  Returns 1, or 0 when the shape goes through the cluster kernel instead. */
-int dp_eval_metrics_plan(long long pixels, int B, int smem_per_sm, int sms, int* ctas_per_sample, int* groups,
+int dp_eval_metrics_plan(long long pixels, int B, int nthr, int smem_per_sm, int sms, int* ctas_per_sample, int* groups,
                          int* slice_pixels, size_t* dynamic_smem);
 int dp_eval_metrics(const float* pred, const float* target, int B, int H, int W, const float* thresholds, int nthr,
                     float eps, int fast_math, double* moments, unsigned long long* counts, float* out,

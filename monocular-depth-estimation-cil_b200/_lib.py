@@ -91,7 +91,7 @@ class _Sig:
                                c_size_t, P])
     dp_metrics_combine = (c_int, [P, P, c_int, c_int, c_int, c_int, P, P])
     dp_eval_metrics_workspace = (c_size_t, [c_int, c_int, c_int])
-    dp_eval_metrics_plan = (c_int, [ctypes.c_longlong, c_int, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int),
+    dp_eval_metrics_plan = (c_int, [ctypes.c_longlong, c_int, c_int, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int),
                                     ctypes.POINTER(c_int), ctypes.POINTER(c_size_t)])
     dp_eval_metrics = (c_int, [P, P, c_int, c_int, c_int, ctypes.POINTER(c_float), c_int, c_float, c_int, P, P, P, P, c_size_t, P])
     dp_conv2d_tc_grid = (c_int, [c_int, c_int, c_int, c_int, c_int, c_int])

@@ -644,7 +644,10 @@ constexpr int kEvThreads = kEvCT + 64;      // + producer warp + exchange warp
 constexpr int kEvChunkPx = kEvCT * 4;       // pixels per chunk: one float4 of each operand per consumer thread
 constexpr int kEvMaxChunks = 8;             // chunks per slot
 constexpr int kEvSlots = 2;                 // shared-memory slots = samples in flight per CTA
-constexpr int kEvStaticAllowance = 3072;    // static shared memory the plan leaves room for
+// static shared memory the plan leaves room for: 2.4 KB in the instantiations with a compile-time threshold count
+// (1 or 3), 3.4 KB with the run-time count (count arrays sized for DP_MAX_THR)
+constexpr int kEvStaticFixed = 3072, kEvStaticRuntime = 4096;
+__host__ inline int eval_static_allowance(int nthr) { return (nthr == 1 || nthr == 3) ? kEvStaticFixed : kEvStaticRuntime; }
 
 struct EvsArgs {
   const float* pred;
@@ -972,10 +975,10 @@ struct EvalPlan {
 // Pure function of the shape and of the device's shared memory per SM / SM count, shared by the workspace query and
 // the launch: one CTA per SM, kEvSlots slices resident per CTA, and the CTAs-per-sample count G that wastes the fewest
 // thread slots (slices that are whole chunks) and SMs (groups * G close to the SM count).
-inline EvalPlan eval_plan_for(long long n, int B, int smem_sm, int sms) {
+inline EvalPlan eval_plan_for(long long n, int B, int smem_sm, int sms, int nthr) {
   EvalPlan p{};
   if (n % 4 != 0 || n <= 0 || B <= 0 || sms <= 0) return p;
-  const long long budget = ((long long)smem_sm - 1024 - kEvStaticAllowance) / kEvSlots;   // bytes per slot
+  const long long budget = ((long long)smem_sm - 1024 - eval_static_allowance(nthr)) / kEvSlots;   // bytes per slot
   if (budget < 4096) return p;
   const long long gmin = (n * 8 + budget - 1) / budget;
   double best = -1.0;
@@ -998,12 +1001,12 @@ inline EvalPlan eval_plan_for(long long n, int B, int smem_sm, int sms) {
   return p;
 }
 
-inline EvalPlan eval_plan(long long n, int B) {
+inline EvalPlan eval_plan(long long n, int B, int nthr) {
   int smem_sm = 0, sms = 0, dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return EvalPlan{};
   if (cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) != cudaSuccess) return EvalPlan{};
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return EvalPlan{};
-  return eval_plan_for(n, B, smem_sm, sms);
+  return eval_plan_for(n, B, smem_sm, sms, nthr);
 }
 
 inline size_t eval_ws_ll_bytes(int B, int G) { return (((size_t)B * G * 2 * sizeof(unsigned long long)) + 255) & ~(size_t)255; }
@@ -1143,9 +1146,9 @@ static size_t eval_ws_bytes(int B, const EvalPlan& p) {
          (size_t)B * p.G * DP_MAX_THR * sizeof(unsigned long long) + (size_t)B * (2 + DP_MAX_THR) * sizeof(double);
 }
 
-int dp_eval_metrics_plan(long long pixels, int B, int smem_per_sm, int sms, int* ctas_per_sample, int* groups,
+int dp_eval_metrics_plan(long long pixels, int B, int nthr, int smem_per_sm, int sms, int* ctas_per_sample, int* groups,
                          int* slice_pixels, size_t* dynamic_smem) {
-  const EvalPlan p = eval_plan_for(pixels, B, smem_per_sm, sms);
+  const EvalPlan p = eval_plan_for(pixels, B, smem_per_sm, sms, nthr);
   if (!p.ok) return 0;
   if (ctas_per_sample) *ctas_per_sample = p.G;
   if (groups) *groups = p.ngroups;
@@ -1156,8 +1159,12 @@ int dp_eval_metrics_plan(long long pixels, int B, int smem_per_sm, int sms, int*
 
 size_t dp_eval_metrics_workspace(int B, int H, int W) {
   if (B <= 0 || H <= 0 || W <= 0) return 256;
-  const EvalPlan p = eval_plan((long long)H * W, B);
-  return p.ok ? eval_ws_bytes(B, p) : 256;
+  size_t need = 256;
+  for (int nthr = 1; nthr <= 2; ++nthr) {      // the two decompositions (compile-time / run-time threshold count)
+    const EvalPlan p = eval_plan((long long)H * W, B, nthr);
+    if (p.ok && eval_ws_bytes(B, p) > need) need = eval_ws_bytes(B, p);
+  }
+  return need;
 }
 
 /* evaluation.py:157-166: a streaming kernel (8 B/px of HBM traffic, pixels classified from shared memory) and the
@@ -1172,7 +1179,7 @@ int dp_eval_metrics(const float* pred, const float* target, int B, int H, int W,
   const long long n = (long long)H * W;
   const bool vec = (n % 4 == 0) && aligned16(pred) && aligned16(target);
 
-  const EvalPlan plan = vec ? eval_plan(n, B) : EvalPlan{};
+  const EvalPlan plan = vec ? eval_plan(n, B, nthr) : EvalPlan{};
   if (plan.ok) {
     DP_CHECK_ARG(workspace, "dp_eval_metrics: null workspace");
     if (workspace_bytes < eval_ws_bytes(B, plan))

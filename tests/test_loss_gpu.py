@@ -159,6 +159,7 @@ def test_fused_eval_counts_match_two_pass_counts(pkg, B, H, W):
     (40, 448, 576, [1.05, 1.05 ** 2, 1.05 ** 3]),      # several samples per CTA group: mbarrier phases, chunk refill
     (5, 426, 560, [1.25]),                             # raw test-set resolution, ragged last slice, one threshold
     (3, 448, 576, [1.1, 1.3]),                         # run-time threshold count, one-division form
+    (20, 448, 576, [1.1, 1.3, 1.5, 2.0, 3.0]),         # run-time count with full-size slices (largest static smem)
     (3, 128, 160, [0.9, 1.0, 1.2, 1.5]),               # thresholds <= 1: both quotients as written in util.py:204
     (2, 896, 1152, [1.05, 1.05 ** 2, 1.05 ** 3]),      # config-5 resolution: more CTAs per sample
 ])

@@ -192,22 +192,23 @@ def test_eval_plan_covers_every_sample_shape():
     import depth_b200
     lib = ctypes.CDLL(depth_b200._lib.LIB_PATH)
     lib.dp_eval_metrics_plan.restype = ctypes.c_int
-    lib.dp_eval_metrics_plan.argtypes = [ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+    lib.dp_eval_metrics_plan.argtypes = [ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
                                          ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_size_t)]
     smem, sms = 233472, 148
     shapes = [(448, 576), (426, 560), (896, 1152), (64, 96), (32, 40), (2, 2), (1080, 1920), (480, 640), (37, 52)]
     for H, W in shapes:
-        for B in (1, 3, 32, 650):
+        for B, nthr in ((1, 3), (3, 1), (32, 2), (650, 3), (650, 8)):
             G, groups, per, dyn = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_size_t()
-            ok = lib.dp_eval_metrics_plan(H * W, B, smem, sms, ctypes.byref(G), ctypes.byref(groups), ctypes.byref(per),
-                                          ctypes.byref(dyn))
+            ok = lib.dp_eval_metrics_plan(H * W, B, nthr, smem, sms, ctypes.byref(G), ctypes.byref(groups),
+                                          ctypes.byref(per), ctypes.byref(dyn))
             assert ok == 1, (H, W, B)
+            static = 2560 if nthr in (1, 3) else 3584      # ptxas: 2432 / 3456 bytes of static shared memory
             n = H * W
             assert per.value % 4 == 0 and per.value * G.value >= n           # slices tile the sample, 16-byte aligned
             assert per.value * (G.value - 1) < n + 4 * G.value                 # no CTA beyond the ragged last one is idle
             assert 1 <= groups.value <= B and groups.value * G.value <= sms    # every CTA of every group is resident
-            assert dyn.value == per.value * 8 * 2 and dyn.value + 4096 <= smem
-    assert lib.dp_eval_metrics_plan(37 * 53, 4, smem, sms, None, None, None, None) == 0      # odd pixel count
-    assert lib.dp_eval_metrics_plan(448 * 576, 4, 16384, sms, None, None, None, None) == 0   # no room for a slot
-    assert lib.dp_eval_metrics_plan(8000 * 8000, 4, smem, sms, None, None, None, None) == 0  # sample larger than the chip's smem
+            assert dyn.value == per.value * 8 * 2 and dyn.value + static + 1024 <= smem   # static + reserved smem fit
+    assert lib.dp_eval_metrics_plan(37 * 53, 4, 3, smem, sms, None, None, None, None) == 0      # odd pixel count
+    assert lib.dp_eval_metrics_plan(448 * 576, 4, 3, 16384, sms, None, None, None, None) == 0   # no room for a slot
+    assert lib.dp_eval_metrics_plan(8000 * 8000, 4, 3, smem, sms, None, None, None, None) == 0  # sample larger than the chip's smem
