@@ -962,22 +962,16 @@ int make_plan(Plan& p, int B, int Hg, int Wg, int Cin, int Cout, const ColSpec* 
   const size_t stats_bytes = want_stats ? ((size_t)kEpiWarps * 2 * Cout * 4 + 15) & ~size_t(15) : 0;
   // TMA-store epilogue: one N block of 16/32/64 columns; two staging tiles per output
   a.epi_tma = (a.n_blocks == 1 && (a.BN == 16 || a.BN == 32 || a.BN == 64) && n_out >= 1) ? 1 : 0;
-  {   // experiment knobs (diagnostics)
-    static const int no_tma = getenv("DP_CONV_NOTMA") != nullptr, niss1 = getenv("DP_CONV_NISS1") != nullptr;
-    if (no_tma) a.epi_tma = 0;
-    if (niss1) a.niss = 1;
-  }
   a.out_tile_bytes = (uint32_t)(128 * a.BN * 2);
   a.nob = n_out >= 2 ? 2 : (a.BN == 64 ? 3 : 4);
   size_t out_bytes = a.epi_tma ? (size_t)a.nob * n_out * a.out_tile_bytes : 0;
   // per-warp mode: two epilogue groups on alternate tiles (needs the two-issuer / four-buffer MMA side: single k-step
   // tiles) and 32-pixel sub-tiles that are whole rows of the tile
-  if (a.epi_tma == 1 && n_out == 1 && (a.BN == 16 || a.BN == 32) && a.nbuf == 4 && a.ncols * a.kchunks == 1 && a.tw <= 32 &&
-      getenv("DP_CONV_NOWARP") == nullptr) {
+  if (a.epi_tma == 1 && n_out == 1 && (a.BN == 16 || a.BN == 32) && a.nbuf == 4 && a.ncols * a.kchunks == 1 && a.tw <= 32) {
     a.epi_tma = 3;
     out_bytes = (size_t)kEpiWarps * 4 * 32 * a.BN * 2;
   }
-  if (!a.epi_tma && n_out == 1 && a.BN > 64 && a.BN % 64 == 0 && getenv("DP_CONV_NOTMA") == nullptr) {
+  if (!a.epi_tma && n_out == 1 && a.BN > 64 && a.BN % 64 == 0) {
     // wide TMA-store epilogue: three (or two) 16 KB staging tiles, as long as the load pipeline keeps >= 3 stages
     const size_t stage_b = a.a_slot_bytes + (a.resident ? 0 : (size_t)a.max_nr * a.b_tap_bytes);
     const size_t base_fixed = 1024 + a.resident_bytes + stats_bytes + sizeof(Barriers) + 64;
