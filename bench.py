@@ -356,7 +356,7 @@ def run_ours(a):
                                          "frac": round(fgbs / hbm, 4)}}}
 
     cpu = None
-    if rank == 0 and not a.no_cpu_baseline:
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:      # reported at N = 1 only (the other ranks would idle on it)
         cpu = cpu_train_step(batch=4, steps=1, warmup=1)
 
     if rank == 0:
