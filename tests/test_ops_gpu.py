@@ -1,6 +1,7 @@
 """Op-level numerics: every hand-written kernel behind ops.py against a plain PyTorch fp32 reference of the same
 op, evaluated on the same bf16-rounded operands.  Tolerances are bf16 output rounding (2^-8 relative) plus
 accumulation-order slack, stated per test."""
+import os
 import pytest
 import torch
 import torch.nn as nn
@@ -75,6 +76,17 @@ def test_resize_fwd_bwd(pkg, B, C, Hi, Wi, Ho, Wo, align):
         assert ok, ("bwd", e, s)
     ok, e, s = close(nchw(out.detach()), ref.detach())
     assert ok, ("fwd", e, s)
+
+
+def test_resize_sweep_small_and_strided(pkg):
+    """tools/resize_sweep.py: tiny and odd shapes (2x3 .. 32x48), both corner conventions, 8 .. 256 channels, dense and
+    channel-slice operands, forward and backward against F.interpolate."""
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "resize_sweep.py")
+    spec = importlib.util.spec_from_file_location("resize_sweep", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.sweep(channels=(8, 32, 256)) == []
 
 
 def test_resize_planes_f32(pkg):
