@@ -150,8 +150,7 @@ class _Sig:
     dp_conv2d_wgrad_tc_s2 = (c_int, [P, c_ll, c_int, c_int, c_int, P, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, P,
                                      c_int, P, c_size_t, P])
     dp_debug_set_buffer = (None, [P])
-    dp_umma_probe = (c_int, [P, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                             c_int, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32), P, c_int, P])
+
 
 
 def check(code):

@@ -49,7 +49,29 @@ def build(verbose=False, force=False):
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
+    build_probe(verbose)
     return LIB
+
+
+def build_probe(verbose=False):
+    """tests/probe/libdepth_b200_probe.so: the single-UMMA descriptor probe used by tests/test_umma_probe_gpu.py.  Test
+    scaffolding - it links the product objects it needs (error string, tensor-map encoder) but is not part of the
+    product library."""
+    pdir = os.path.join(HERE, "..", "tests", "probe")
+    src = os.path.join(pdir, "umma_probe.cu")
+    out = os.path.join(pdir, "libdepth_b200_probe.so")
+    if not os.path.exists(src):
+        return None
+    deps = [os.path.join(OBJ, "dp_core.o"), os.path.join(OBJ, "tmap.o")]
+    hdrs = tuple(glob.glob(os.path.join(CSRC, "*.cuh"))) + (os.path.join(pdir, "probe.h"),)
+    if _newer(src, out, hdrs + tuple(deps)):
+        cmd = [NVCC] + FLAGS + ["-shared", src] + deps + ["-o", out, "-cudart", "static"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError("probe build failed")
+    return out
 
 
 if __name__ == "__main__":

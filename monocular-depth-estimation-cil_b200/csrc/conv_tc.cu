@@ -985,13 +985,24 @@ int make_plan(Plan& p, int B, int Hg, int Wg, int Cin, int Cout, const ColSpec* 
     return dp_set_error(DP_ERR_UNSUPPORTED, "conv_tc: shape needs %zu B of shared memory", fixed + 2 * stage);
   int st = (int)((budget - fixed) / stage);
   a.stages = st > kMaxStages ? kMaxStages : st;
-  // Two issuers alternate tiles.  They are only used when a tile is a single k-step and the ring has an even number
-  // of stages, so that every full/empty barrier is waited on by exactly one issuer for the life of the kernel (issuer
-  // 0 owns the even stages, issuer 1 the odd ones) and the usual one-producer / one-consumer parity reasoning holds.
-  // With several k-steps per tile the two issuers meet on the same barriers in alternating laps; that configuration
-  // faulted intermittently under load (EfficientNet trunk 1x1 layers, Cin 144/192) and is not used.
-  if (a.ncols * a.kchunks != 1) a.niss = 1;
-  if (a.niss == 2 && (a.stages & 1)) a.stages -= 1;
+  // Two issuers alternate tiles (issuer w takes tiles w, w+2, ...).  The stage ring is shared, and an mbarrier parity wait
+  // is only sound for a waiter that observes EVERY phase of the barrier it waits on: `try_wait.parity p` answers "the
+  // phase with parity p has completed", which is also true of the phase two laps back.  With an arbitrary ring depth the
+  // two issuers meet on the same full[] barriers in alternating laps, so an issuer that runs ahead asks for lap L+1 of
+  // a stage whose lap L (the other issuer's) has not landed yet, gets "complete" from lap L-1, and issues UMMAs on a
+  // slot TMA is still writing - the intermittent fault seen in round 1 on the EfficientNet 1x1 layers (Cin 144/192, three
+  // k-steps per tile).  The ring is therefore cut to a multiple of 2 * ksteps stages: tile t then always occupies ring
+  // block t mod (stages / ksteps), even blocks belong to issuer 0 and odd blocks to issuer 1, and every full/empty
+  // barrier has exactly one producer and one consumer for the life of the kernel (the single k-step case is the same
+  // rule with ksteps = 1).  Shapes whose ring cannot hold two tiles run with one issuer.
+  {
+    const int ksteps = a.ncols * a.kchunks;
+    if (a.niss == 2) {
+      const int per = 2 * ksteps;
+      if (ksteps > 4 || a.stages < per) a.niss = 1;
+      else a.stages = (a.stages / per) * per;
+    }
+  }
   p.smem = fixed + (size_t)a.stages * stage;
   a.total_items = (long long)B * a.tiles_y * a.tiles_x * a.n_blocks;
   p.grid = (int)(a.total_items < dp::kNumSMs ? a.total_items : dp::kNumSMs);

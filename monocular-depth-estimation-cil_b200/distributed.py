@@ -46,7 +46,12 @@ class GradientAllReducer:
         self.views = None
 
     def _build(self):
-        self.live = [p for p in self.params if p.grad is not None]
+        keep = getattr(self, "_live_ids", set())
+        self.live = [p for p in self.params if p.grad is not None or id(p) in keep]
+        self._live_ids = {id(p) for p in self.live}
+        if not self.live:
+            self.flat, self.views = None, []
+            return
         n = sum(p.numel() for p in self.live)
         dev = self.live[0].device
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -64,7 +69,16 @@ class GradientAllReducer:
         """call after backward(); averages gradients over ranks (no-op for world 1)."""
         if self.live is None:
             self._build()
-        if self.world == 1:
+        else:
+            # a parameter that starts receiving gradients later (unfrozen layer, conditional branch) must join the
+            # bucket, or the ranks diverge silently
+            late = [p for p in self.params if p.grad is not None and id(p) not in self._live_ids]
+            if late:
+                if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+                    raise RuntimeError("GradientAllReducer: the set of parameters with gradients changed inside a "
+                                       "captured step; re-capture the graph")
+                self._build()
+        if self.world == 1 or not self.live:
             return
         grads, views = [], []
         for p, v in zip(self.live, self.views):

@@ -33,18 +33,47 @@ class GraphedTrainStep:
         self._step = 0
         self._hout = [torch.empty(8, dtype=torch.float32).pin_memory() for _ in range(2)]
         self._done = [torch.cuda.Event(), torch.cuda.Event()]
+        # The warm-up steps below are real optimisation steps (they build the flat gradient bucket, the optimizer state
+        # and the allocator's pools).  Their effect on the model and optimizer is undone before capture, so the caller
+        # gets back exactly the state it handed in (a resumed checkpoint is not perturbed, BN running statistics and
+        # num_batches_tracked included); the reference loop (main.py:125-144) has no such side effect.
+        snap = self._snapshot()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            for _ in range(max(warmup, 2)):          # builds the flat gradient bucket, optimizer state, caches
+            for _ in range(max(warmup, 2)):
                 self._body()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        self._restore(snap)
         ops.PACKS.store.clear()                      # weight re-packs must be part of the captured step
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self._body()
         torch.cuda.synchronize()
+
+    def _snapshot(self):
+        model = {k: v.detach().clone() for k, v in self.model.state_dict().items()}
+        opt = {}
+        for p, st in self.opt.state.items():
+            opt[id(p)] = {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+        return model, opt
+
+    def _restore(self, snap):
+        """in place: the tensors keep their addresses (the captured graph and the optimizer refer to them)"""
+        model, opt = snap
+        with torch.no_grad():
+            for k, v in self.model.state_dict().items():
+                v.copy_(model[k])
+            for p, st in self.opt.state.items():
+                old = opt.get(id(p))
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        if old is not None and k in old:
+                            v.copy_(old[k])
+                        else:
+                            v.zero_()             # state created by the warm-up: back to AdamW's initial zeros
+        self.red.zero()
 
     def _body(self):
         self.red.zero()
@@ -93,6 +122,7 @@ class GraphedTrainStep:
                 self.t.copy_(self._st, non_blocking=True)
             self._consumed.record(main)
         self.graph.replay()
+        ops.PACKS.invalidate()                     # the replay moved the weights without bumping their _version
         slot = self._step & 1
         self._hout[slot].copy_(self.out, non_blocking=True)
         self._done[slot].record(main)
@@ -112,5 +142,5 @@ class GraphedTrainStep:
                 "edge_loss": h[L.L_EDGE]}
 
     def finish(self):
-        """call before going back to eager use of the model: the eager weight-pack cache must not trust versions."""
-        ops.PACKS.store.clear()
+        """kept for round-1 callers; no longer required: every replay invalidates the eager weight-pack cache."""
+        ops.PACKS.invalidate()

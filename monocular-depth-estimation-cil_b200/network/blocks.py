@@ -20,11 +20,12 @@ def _hub(repo, name, **kw):
 
 
 def is_internal(x):
-    return x.dtype == torch.bfloat16
+    """internal NHWC bf16 tensors carry an explicit tag set by `ops` (never inferred from the dtype)"""
+    return ops.is_internal(x)
 
 
 def enter(x):
-    """-> (nhwc bf16 tensor, was_public)"""
+    """-> (nhwc bf16 tensor, was_public).  Public tensors are the reference's NCHW maps (any float dtype)."""
     if is_internal(x):
         return x, False
     return ops.to_nhwc(x), True
@@ -35,7 +36,7 @@ def from_nchw(f):
     NHWC in memory: its permuted view is used as is (autograd routes the gradient back through the view)."""
     if f.dtype == torch.bfloat16:
         t = f.permute(0, 2, 3, 1)
-        return t if t.is_contiguous() else t.contiguous()
+        return ops.mark_internal(t if t.is_contiguous() else t.contiguous())
     return ops.to_nhwc(f)
 
 

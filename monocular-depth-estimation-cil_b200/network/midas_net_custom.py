@@ -50,16 +50,21 @@ class MidasNet_small(BaseModel):
         )
         # run the third-party encoder under bf16 autocast + channels_last (bench); parity tests keep fp32
         self.encoder_autocast = False
-        # run the EfficientNet-Lite3 trunk on the sm_100a kernels (network/encoder_fused.py) when its structure is
-        # recognised; False keeps it on PyTorch (the parity tests compare both)
-        self.fused_encoder = False
+        # run the EfficientNet-Lite3 trunk on the sm_100a kernels (network/encoder_fused.py).  This is the default on a
+        # CUDA device; a trunk whose structure is not gen-efficientnet's raises instead of silently running on PyTorch.
+        # Set it to False explicitly to keep a third-party trunk on PyTorch (the parity tests compare both).
+        self.fused_encoder = True
         if path:
             self.load(path)
 
     # -- pieces shared with MidasNetSemantics ----------------------------------------------------------
     def encoder_features(self, x):
         self._feats_nhwc = False
-        if self.fused_encoder and x.is_cuda and encoder_fused.supported(self.pretrained):
+        if self.fused_encoder and x.is_cuda:
+            if not encoder_fused.supported(self.pretrained):
+                raise NotImplementedError(
+                    "fused_encoder=True but `pretrained` is not a gen-efficientnet EfficientNet-Lite3 trunk "
+                    "(network/encoder_fused.py); set model.fused_encoder = False to run this trunk through PyTorch")
             self._feats_nhwc = True
             return tuple(encoder_fused.forward(self.pretrained, x))      # NHWC bf16 (internal layout)
         if self.encoder_autocast:

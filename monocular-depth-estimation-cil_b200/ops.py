@@ -35,6 +35,31 @@ def _nhwc(B, H, W, C, dev):
     return torch.empty(B, H, W, C, dtype=BF16, device=dev)
 
 
+def mark_internal(t):
+    """Tag a tensor (or each tensor of a tuple) as being in the internal NHWC bf16 layout.  Module boundaries
+    (network.blocks.enter) trust this explicit tag, never the dtype: a caller's own bf16 NCHW tensor is a public tensor
+    and is converted like an fp32 one."""
+    if isinstance(t, tuple):
+        for u in t:
+            mark_internal(u)
+    elif torch.is_tensor(t) and t.dtype == BF16 and t.dim() == 4:
+        t._dp_nhwc = True
+    return t
+
+
+def is_internal(t):
+    return bool(getattr(t, "_dp_nhwc", False))
+
+
+def _internal(fn):
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*a, **k):
+        return mark_internal(fn(*a, **k))
+    return wrapped
+
+
 def _dense(t):
     """gradient tensors arrive with arbitrary strides: make them dense NHWC bf16."""
     if t is None:
@@ -45,14 +70,23 @@ def _dense(t):
 
 
 class _PackCache:
-    """bf16 kernel-layout copies of fp32 parameters, refreshed when the parameter changes in place."""
+    """bf16 kernel-layout copies of fp32 parameters, refreshed when the parameter changes in place.
+
+    `_version` only sees updates made through the dispatcher.  A CUDA-graph replay (graphs.GraphedTrainStep) updates the
+    parameters on the device without touching it, so every replay also bumps `generation`, which is part of the
+    freshness key: the first eager use of a weight after any number of replays repacks it."""
 
     def __init__(self):
         self.store = {}
+        self.generation = 0
+
+    def invalidate(self):
+        """parameters changed behind autograd's back (graph replay, raw device writes)"""
+        self.generation += 1
 
     def get(self, w, swap, flip):
         key = (id(w), swap, flip)
-        ver = (w._version, w.data_ptr(), tuple(w.shape))
+        ver = (w._version, w.data_ptr(), tuple(w.shape), self.generation)
         hit = self.store.get(key)
         if hit is not None and hit[0] == ver and hit[2]() is w:
             return hit[1]
@@ -199,6 +233,7 @@ class _ToNCHW(torch.autograd.Function):
         return out
 
 
+@_internal
 def to_nhwc(x):
     """(B,C,H,W) fp32 -> (B,H,W,C) bf16"""
     return _ToNHWC.apply(x)
@@ -209,6 +244,7 @@ def to_nchw(x):
     return _ToNCHW.apply(x)
 
 
+@_internal
 def tokens_to_nhwc(tok, ph, pw):
     """(B, ph*pw, C) fp32 tokens of the frozen ViT -> (B, ph, pw, C) bf16 (dpt_depth.py:122 without the permute)."""
     B, N, C = tok.shape
@@ -295,6 +331,7 @@ class _ConvTC(torch.autograd.Function):
         return dx, dw, db, dres, dres2, None, None, None
 
 
+@_internal
 def conv_tc(x, weight, bias=None, res=None, res2=None, relu=False, dual=False, stats=False):
     """3x3/s1/p1 or 1x1 conv on tcgen05.  Returns y, or (y, relu(y)) when dual, with BN partials appended when stats."""
     y, y2, st = _ConvTC.apply(x, weight, bias, res, res2, relu, dual, stats)
@@ -448,10 +485,12 @@ class _ConvTransposed(torch.autograd.Function):
         return dx, dw, db, None, None
 
 
+@_internal
 def conv_strided(x, weight, bias, stride, pad):
     return _ConvStrided.apply(x, weight, bias, stride, pad)
 
 
+@_internal
 def conv_transposed(x, weight, bias, stride, pad):
     I, O, KH, KW = weight.shape
     if KH == KW == stride and pad == 0 and I % 8 == 0 and O % 8 == 0:
@@ -533,6 +572,7 @@ class _DwConv(torch.autograd.Function):
         return dx, dw, None, None, None, None, None, None
 
 
+@_internal
 def dwconv(x, weight, stride, pad_t, pad_l, Ho, Wo, stats=False):
     """depthwise conv; returns out or (out, BN partials)"""
     out, st = _DwConv.apply(x, weight, stride, pad_t, pad_l, Ho, Wo, stats)
@@ -569,6 +609,7 @@ class _StemConv(torch.autograd.Function):
         return None, dw, None
 
 
+@_internal
 def stem_conv(x, weight, stats=False):
     out, st = _StemConv.apply(x, weight, stats)
     return (out, st) if stats else out
@@ -634,6 +675,7 @@ class _Resize(torch.autograd.Function):
         return gin, None, None, None
 
 
+@_internal
 def resize(x, size, align_corners):
     Ho, Wo = int(size[0]), int(size[1])
     if (Ho, Wo) == tuple(x.shape[1:3]):
@@ -741,6 +783,7 @@ class _BNAct(torch.autograd.Function):
                 None, None, gmask, None, None)
 
 
+@_internal
 def bn_act(bn, c, stats=None, relu=True, res=None, bn2=None, c2=None, stats2=None):
     """train/eval nn.BatchNorm2d on NHWC bf16 `c` (+ residual, or + a second normalised branch), optional ReLU
     (relu=True / 1) or ReLU6 (relu=2)."""
@@ -793,6 +836,7 @@ class _LNLinear(torch.autograd.Function):
         return dx, dg.to(gamma.dtype), db.to(beta.dtype), dW.to(W.dtype), dbias, None, None
 
 
+@_internal
 def ln_linear(x, ln, lin, out_bf16=False):
     return _LNLinear.apply(x, ln.weight, ln.bias, lin.weight, lin.bias, ln.eps, out_bf16)
 
@@ -871,6 +915,7 @@ def attention(q, k, v, hr, wr, ws, scale):
     return _Attention.apply(q.contiguous(), k.contiguous(), v.contiguous(), items, segs, float(scale))
 
 
+@_internal
 def add(a, b, c=None):
     """elementwise a + b (+ c) on dense NHWC bf16 (autograd: plain fan-out)."""
     return _Add.apply(a, b, c)
@@ -919,6 +964,7 @@ class _Concat(torch.autograd.Function):
         return outs[0], outs[1]
 
 
+@_internal
 def concat_channels(a, b):
     """torch.cat([a, b], dim=1) of the reference, in NHWC."""
     return _Concat.apply(a, b)
@@ -939,5 +985,6 @@ class _Relu(torch.autograd.Function):
         return _mask_grad(None, g, y)
 
 
+@_internal
 def relu(x):
     return _Relu.apply(x)

@@ -30,6 +30,15 @@ class _Pass:
 
     def __init__(self, pred, target, rgb, flags, eps):
         lib = L.lib()
+        # the kernels index every buffer with pred's (B, H, W): a smaller target / rgb would be read out of bounds
+        # where the reference raises a shape / broadcast error
+        assert target.numel() == pred.numel() and target.shape[0] == pred.shape[0] \
+            and target.shape[-2:] == pred.shape[-2:], \
+            "Pred and target must have the same shape, got {} and {}".format(tuple(pred.shape), tuple(target.shape))
+        if rgb is not None:
+            assert rgb.dim() == 4 and rgb.shape[0] == pred.shape[0] and rgb.shape[1] == 3 \
+                and rgb.shape[-2:] == pred.shape[-2:], \
+                "rgb must be (B,3,H,W) matching pred {}, got {}".format(tuple(pred.shape), tuple(rgb.shape))
         self.p, self.t = _prep(pred), _prep(target)
         self.rgb = _prep(rgb) if rgb is not None else None
         self.B, self.H, self.W = _bhw(self.p)

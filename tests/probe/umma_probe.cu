@@ -1,10 +1,11 @@
 // Diagnostic entry point: one CTA, one UMMA chain with fully host-specified descriptors, full TMEM dump.
+// Test scaffolding: built into tests/probe/libdepth_b200_probe.so (NOT part of the product library).
 // Used by tests/test_umma_probe_gpu.py to pin the shared-memory descriptor conventions (K-major and
 // MN-major, every swizzle mode, sub-tile start offsets) and the TMEM accumulator layouts (M=128, M=64)
 // the convolution kernels rely on.  Not on the hot path.
-#include "common.cuh"
-#include "tc.cuh"
-#include "../../include/depth_b200.h"
+#include "../../monocular-depth-estimation-cil_b200/csrc/common.cuh"
+#include "../../monocular-depth-estimation-cil_b200/csrc/tc.cuh"
+#include "probe.h"
 
 namespace {
 

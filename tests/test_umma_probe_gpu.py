@@ -8,15 +8,34 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+_PROBE = None
+
+
+def _probe_lib():
+    """tests/probe/libdepth_b200_probe.so (built by build.py next to the product library, not part of it)"""
+    global _PROBE
+    if _PROBE is None:
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "probe", "libdepth_b200_probe.so")
+        lib = ctypes.CDLL(path)
+        P, I = ctypes.c_void_p, ctypes.c_int
+        lib.dp_umma_probe.restype = I
+        lib.dp_umma_probe.argtypes = [P, I, I, I, I, P, I, I, I, I, I, I, I, I, I, ctypes.POINTER(ctypes.c_uint32),
+                                      ctypes.POINTER(ctypes.c_uint32), P, I, P]
+        _PROBE = lib
+    return _PROBE
+
+
 def _probe(pkg, A, a_box, B, b_box, M, N, nk, a_mn, b_mn, adesc, bdesc, ncols=None):
     L = pkg._lib
     ncols = ncols or max(16, N)
     out = torch.full((128, ncols), float("nan"), device="cuda", dtype=torch.float32)
     ad = (ctypes.c_uint32 * 6)(*(list(adesc) + [0] * (6 - len(adesc))))
     bd = (ctypes.c_uint32 * 5)(*bdesc)
-    L.check(L.lib().dp_umma_probe(L.ptr(A), A.shape[0], A.shape[1], a_box[0], a_box[1], L.ptr(B), B.shape[0],
+    rc = (_probe_lib().dp_umma_probe(L.ptr(A), A.shape[0], A.shape[1], a_box[0], a_box[1], L.ptr(B), B.shape[0],
                                   B.shape[1], b_box[0], b_box[1], M, N, nk, a_mn, b_mn, ad, bd, L.ptr(out), ncols,
                                   L.stream()))
+    assert rc == 0, f"dp_umma_probe returned {rc}"
     torch.cuda.synchronize()
     return out
 
