@@ -9,7 +9,7 @@ the fp32 reference.  (compute-sanitizer is closed on this GPU pool, so the evide
 import pytest
 import torch
 
-from test_conv_tc_gpu import pack_w, ref_conv
+from tests.test_conv_tc_gpu import pack_w, ref_conv
 
 pytestmark = pytest.mark.gpu
 
