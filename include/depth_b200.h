@@ -28,7 +28,7 @@ extern "C" {
 typedef struct CUstream_st* cudaStream_t;
 #endif
 
-#define DP_ABI_VERSION 2
+#define DP_ABI_VERSION 3
 
 int dp_abi_version(void);
 const char* dp_last_error(void);
@@ -153,6 +153,33 @@ int dp_conv2d_tc(const void* x, long long x_ld, int B, int H, int W, int Cin, co
                  long long res2_ld, int relu, void* out, long long out_ld, void* out2, long long out2_ld, int relu2,
                  float* stats_partials, cudaStream_t stream);
 
+/* The same convolution with BatchNorm fused on either side of the GEMM (reference conv -> BN -> ReLU -> conv chains:
+ * midas_semantics.py:132-150 ResidualBlock, :195-203 fusion_head / depth_head).
+ *   prologue: the A operand is act(x * scale[c] + shift[c]) - the train/eval BatchNorm2d + ReLU / ReLU6 that precedes
+ *     the conv in the reference - applied to every TMA-landed tile in shared memory by two transform warps before the
+ *     tensor core reads it; pixels outside the image stay exactly zero (nn.Conv2d pads the ACTIVATED tensor).  The
+ *     activated tensor is never written to HBM.
+ *   backward mask: for a data-gradient launch whose output is the gradient w.r.t. a = act(c * scale + shift), the
+ *     epilogue recomputes the activation from c (mask_x, the pre-activation tensor, (B,H,W,Cout) bf16), zeroes the
+ *     clamped positions, and stats_partials receives [grid][2][Cout] = (sum g, sum g * c) over the stored values: the two
+ *     batch reductions of BatchNorm's backward, which therefore needs no reduction pass of its own.
+ * dp_conv2d_tc_caps: bit mask of what this shape supports (the mask epilogue needs a single N block of <= 64 columns). */
+#define DP_CONV_CAP_PROLOGUE 1
+#define DP_CONV_CAP_BN_BACKWARD 2
+typedef struct dp_conv_fuse {
+  const float* pre_scale_shift;   /* [2][Cin] fp32 (dp_bn_finalize / dp_bn_eval_coeffs layout) or NULL */
+  int pre_act;                    /* 0 affine only, 1 ReLU, 2 ReLU6 */
+  const void* mask_x;             /* NULL or pre-activation tensor c, NHWC bf16, Cout channels */
+  long long mask_ld;
+  const float* mask_scale_shift;  /* [2][Cout] */
+  int mask_act;                   /* 1 ReLU, 2 ReLU6 */
+} dp_conv_fuse_t;
+int dp_conv2d_tc_caps(int B, int H, int W, int Cin, int Cout, int KS);
+int dp_conv2d_tc_fused(const void* x, long long x_ld, int B, int H, int W, int Cin, const void* w_packed, int Cin_p,
+                       int Cout, int KS, const float* bias, const void* residual, long long res_ld, const void* residual2,
+                       long long res2_ld, int relu, void* out, long long out_ld, void* out2, long long out2_ld, int relu2,
+                       float* stats_partials, const dp_conv_fuse_t* fuse, cudaStream_t stream);
+
 /* Stride-2 convolution (conv rule i = 2*o - pad + k, K x K taps) on the tensor cores, reading the four parity planes
  * of the input as strided TMA tensors: nn.Conv2d(k3,s2,p1) forward (midas_semantics.py:39-45, dpt_depth.py:63-68) and
  * the data gradient of nn.ConvTranspose2d(k4,s2,p1) (midas_semantics.py:52-58).
@@ -174,6 +201,13 @@ size_t dp_conv2d_wgrad_tc_workspace(int B, int H, int W, int Cin, int Cout, int 
 int dp_conv2d_wgrad_tc(const void* x, long long x_ld, const void* dy, long long dy_ld, int B, int H, int W, int Cin,
                        int Cout, int KS, float* grad_oihw, int accumulate, void* workspace, size_t workspace_bytes,
                        cudaStream_t stream);
+
+/* Same, with x = act(c * scale[ci] + shift[ci]) computed on the fly from the pre-BatchNorm tensor c passed as `x`
+ * (pre_scale_shift [2][Cin] fp32, pre_act 0 / 1 ReLU / 2 ReLU6; zero padding applies to the activated tensor): the weight
+ * gradient of the second conv of a conv -> BN -> ReLU -> conv chain without the activated tensor ever being stored. */
+int dp_conv2d_wgrad_tc_fused(const void* x, long long x_ld, const void* dy, long long dy_ld, int B, int H, int W, int Cin,
+                             int Cout, int KS, float* grad_oihw, int accumulate, void* workspace, size_t workspace_bytes,
+                             const float* pre_scale_shift, int pre_act, cudaStream_t stream);
 
 /* grad[cp][ct][ky][kx] (+)= sum over plain-grid pixels p of P[p][cp] * T[2p - pad + k][ct]  (K x K taps, stride 2):
  *   nn.Conv2d(k3,s2,p1):          P = dY (B,Ho,Wo,O), T = X  (B,Hi,Wi,I)  -> weight.grad [O][I][3][3]

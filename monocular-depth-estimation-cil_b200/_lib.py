@@ -35,7 +35,7 @@ def lib():
         _declare(_lib)
         if os.environ.get("DP_TRACE"):
             _lib = _Traced(_lib)
-        if _lib.dp_abi_version() != 2:
+        if _lib.dp_abi_version() != 3:
             raise DepthB200Error("libdepth_b200.so ABI version mismatch")
     return _lib
 
@@ -97,6 +97,11 @@ class _Sig:
     dp_conv2d_tc_grid = (c_int, [c_int, c_int, c_int, c_int, c_int, c_int])
     dp_conv2d_tc = (c_int, [P, c_ll, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, P, P, c_ll, P, c_ll, c_int, P,
                             c_ll, P, c_ll, c_int, P, P])
+    dp_conv2d_tc_caps = (c_int, [c_int, c_int, c_int, c_int, c_int, c_int])
+    dp_conv2d_tc_fused = (c_int, [P, c_ll, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, P, P, c_ll, P, c_ll, c_int,
+                                  P, c_ll, P, c_ll, c_int, P, P, P])
+    dp_conv2d_wgrad_tc_fused = (c_int, [P, c_ll, P, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_size_t,
+                                        P, c_int, P])
     dp_conv2d_tc_down2_grid = (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int])
     dp_conv2d_tc_down2 = (c_int, [P, c_ll, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, P, c_int, P, c_ll,
                                   c_int, c_int, P, P])
@@ -151,6 +156,15 @@ class _Sig:
                                      c_int, P, c_size_t, P])
     dp_debug_set_buffer = (None, [P])
 
+
+
+class ConvFuse(ctypes.Structure):
+    """dp_conv_fuse_t (include/depth_b200.h)"""
+    _fields_ = [("pre_scale_shift", c_void_p), ("pre_act", c_int), ("mask_x", c_void_p), ("mask_ld", c_ll),
+                ("mask_scale_shift", c_void_p), ("mask_act", c_int)]
+
+
+CAP_PROLOGUE, CAP_BN_BACKWARD = 1, 2
 
 
 def check(code):

@@ -28,6 +28,7 @@
 #include <cstdlib>
 #include "common.cuh"
 #include "tc.cuh"
+#include "bn_fuse.cuh"
 #include "../../include/depth_b200.h"
 
 extern unsigned long long* g_wg_dbg;
@@ -92,6 +93,13 @@ struct ConvArgs {
   const bf16* resb; long long resb_ld;
   int relu, relu2;
   float* stats;  // [gridDim.x][2][Cout] or null
+  // fused BatchNorm prologue (warps 2 and 3 rewrite every landed A box in place before the MMAs read it):
+  //   A = act(x * pre_ss[c] + pre_ss[pre_c + c]), and exactly 0 outside the image (the conv pads the ACTIVATED tensor)
+  const float* pre_ss; int pre_act, pre_c, pre_pad;   // pre_pad = kchunks * KB (table length per row in smem)
+  int pH[kMaxCols], pW[kMaxCols];                     // extent of source plane `map` (pixels outside are padding)
+  // fused BatchNorm-backward epilogue: `resb` is the pre-activation tensor c of the BN + activation whose output
+  // gradient this launch produces; out = acc * [0 < c*aux_ss[n] + aux_ss[Cout+n] < aux_hi]; stats = (sum out, sum out*c)
+  const float* aux_ss; float aux_hi; int aux_mode;
   unsigned long long* dbg;
 };
 
@@ -101,6 +109,7 @@ struct __align__(8) Barriers {
   uint64_t tmem_full[4];
   uint64_t tmem_empty[4];
   uint64_t resident_full;
+  uint64_t ready[kMaxStages];   // prologue mode: A box transformed (two arrivals: warps 2 and 3)
   uint32_t tmem_base;
 };
 
@@ -128,12 +137,10 @@ struct TileIter {
   }
 };
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+using dpf::pack_bf16x2;
+using dpf::bf16_lo;
+using dpf::bf16_hi;
+using dpf::transform_box;
 
 // column sums of a 32 (lanes) x 16 (registers) tile: after the call, lane L holds the sum of column col_of(L)
 // (lanes L and L^1 hold the same column).  16 shuffles instead of 80.
@@ -170,6 +177,28 @@ __device__ __forceinline__ int transpose_reduce16_col(int lane) {
   return ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
 }
 
+// BatchNorm-backward epilogue helper: v8 are 8 consecutive output columns (gradient w.r.t. the activated tensor), cw the
+// matching 8 bf16 values of the pre-activation tensor c.  The activation is recomputed as in the forward pass
+// (m = c * scale + shift in fp32) and the gradient is zeroed where it was clamped; c is returned for the sum of g * c.
+__device__ __forceinline__ void aux_mask8(float* v8, const uint4& cw, const float* s_aux, int Cout, int col, float hi,
+                                          float (&cx)[8]) {
+  const uint32_t w[4] = {cw.x, cw.y, cw.z, cw.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { cx[2 * k] = bf16_lo(w[k]); cx[2 * k + 1] = bf16_hi(w[k]); }
+  if (col < Cout) {                               // Cout is a multiple of 8
+    const float4 a0 = *reinterpret_cast<const float4*>(s_aux + col), a1 = *reinterpret_cast<const float4*>(s_aux + col + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(s_aux + Cout + col);
+    const float4 b1 = *reinterpret_cast<const float4*>(s_aux + Cout + col + 4);
+    const float sc[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float sh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float m = fmaf(cx[e], sc[e], sh[e]);
+      v8[e] = (m > 0.f && m < hi) ? v8[e] : 0.f;
+    }
+  }
+}
+
 // ---- epilogue A: BN = 2*CW in {16, 32, 64}.  Each of the eight warps owns 32 pixels x CW columns of the tile: one
 // tcgen05.ld, TMEM released at once, math in registers, bf16 rows written to a swizzled shared-memory tile that one
 // thread hands to TMA (the store clips tile overhang, so no per-pixel predicates and fully coalesced HBM writes).
@@ -177,7 +206,7 @@ __device__ __forceinline__ int transpose_reduce16_col(int lane) {
 // column slice) and are reduced once at the end.
 template <int CW>
 __device__ __forceinline__ void epilogue_tma(const Maps& tm, const ConvArgs& a, Barriers* bars, uint8_t* s_out,
-                                             float* s_stats, uint32_t tmem, int warp, int lane) {
+                                             float* s_stats, const float* s_aux, uint32_t tmem, int warp, int lane) {
   const int e = warp - 4, ew = e & 3, half = e >> 2;
   const int m = ew * 32 + lane;
   const int py = m / a.tw, px = m - py * a.tw;
@@ -250,7 +279,7 @@ __device__ __forceinline__ void epilogue_tma(const Maps& tm, const ConvArgs& a, 
         for (int k = 0; k < 4; ++k) { v[j * 8 + 2 * k] += bf16_lo(rr[k]); v[j * 8 + 2 * k + 1] += bf16_hi(rr[k]); }
       }
     }
-    if (a.resb) {
+    if (a.resb && !a.aux_mode) {
 #pragma unroll
       for (int j = 0; j < CW / 8; ++j) {
         const uint32_t rr[4] = {r2[j].x, r2[j].y, r2[j].z, r2[j].w};
@@ -263,6 +292,8 @@ __device__ __forceinline__ void epilogue_tma(const Maps& tm, const ConvArgs& a, 
 #pragma unroll
     for (int j = 0; j < CW / 8; ++j) {
       uint32_t q[4], q2[4];
+      float cx[8];                      // aux mode: the pre-activation values c of this thread's 8 columns
+      if (a.aux_mode) aux_mask8(&v[j * 8], r2[j], s_aux, a.Cout, col0 + j * 8, a.aux_hi, cx);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float x0v = v[j * 8 + 2 * k], x1v = v[j * 8 + 2 * k + 1];
@@ -274,9 +305,9 @@ __device__ __forceinline__ void epilogue_tma(const Maps& tm, const ConvArgs& a, 
           // statistics of the value as stored (bf16-rounded), so mean/var describe the tensor the consumer reads
           const float f0 = valid ? bf16_lo(plain) : 0.f, f1 = valid ? bf16_hi(plain) : 0.f;
           acc_s[j * 8 + 2 * k] += f0;
-          acc_q[j * 8 + 2 * k] = fmaf(f0, f0, acc_q[j * 8 + 2 * k]);
+          acc_q[j * 8 + 2 * k] = fmaf(f0, a.aux_mode ? cx[2 * k] : f0, acc_q[j * 8 + 2 * k]);
           acc_s[j * 8 + 2 * k + 1] += f1;
-          acc_q[j * 8 + 2 * k + 1] = fmaf(f1, f1, acc_q[j * 8 + 2 * k + 1]);
+          acc_q[j * 8 + 2 * k + 1] = fmaf(f1, a.aux_mode ? cx[2 * k + 1] : f1, acc_q[j * 8 + 2 * k + 1]);
         }
       }
       tc::st_shared_v4(st + soff[j], q[0], q[1], q[2], q[3]);
@@ -320,7 +351,7 @@ __device__ __forceinline__ void epilogue_tma(const Maps& tm, const ConvArgs& a, 
 // them in its own swizzled ring slot and issues its own TMA store of a (32 / tw) x tw pixel box: no inter-warp barrier.
 template <int BNT>
 __device__ __forceinline__ void epilogue_tma_warp(const Maps& tm, const ConvArgs& a, Barriers* bars, uint8_t* s_out,
-                                                  float* s_stats, uint32_t tmem, int warp, int lane) {
+                                                  float* s_stats, const float* s_aux, uint32_t tmem, int warp, int lane) {
   const int e = warp - 4, ew = e & 3, grp = e >> 2;
   const int m = ew * 32 + lane;
   const int py = m / a.tw, px = m - py * a.tw;
@@ -394,7 +425,7 @@ __device__ __forceinline__ void epilogue_tma_warp(const Maps& tm, const ConvArgs
         for (int k = 0; k < 4; ++k) { v[j * 8 + 2 * k] += bf16_lo(rr[k]); v[j * 8 + 2 * k + 1] += bf16_hi(rr[k]); }
       }
     }
-    if (a.resb) {
+    if (a.resb && !a.aux_mode) {
 #pragma unroll
       for (int j = 0; j < BNT / 8; ++j) {
         const uint32_t rr[4] = {r2[j].x, r2[j].y, r2[j].z, r2[j].w};
@@ -406,6 +437,8 @@ __device__ __forceinline__ void epilogue_tma_warp(const Maps& tm, const ConvArgs
 #pragma unroll
     for (int j = 0; j < BNT / 8; ++j) {
       uint32_t q[4];
+      float cx[8];
+      if (a.aux_mode) aux_mask8(&v[j * 8], r2[j], s_aux, a.Cout, j * 8, a.aux_hi, cx);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float x0v = v[j * 8 + 2 * k], x1v = v[j * 8 + 2 * k + 1];
@@ -414,9 +447,9 @@ __device__ __forceinline__ void epilogue_tma_warp(const Maps& tm, const ConvArgs
         if (want_stats) {
           const float f0 = valid ? bf16_lo(plain) : 0.f, f1 = valid ? bf16_hi(plain) : 0.f;
           acc_s[j * 8 + 2 * k] += f0;
-          acc_q[j * 8 + 2 * k] = fmaf(f0, f0, acc_q[j * 8 + 2 * k]);
+          acc_q[j * 8 + 2 * k] = fmaf(f0, a.aux_mode ? cx[2 * k] : f0, acc_q[j * 8 + 2 * k]);
           acc_s[j * 8 + 2 * k + 1] += f1;
-          acc_q[j * 8 + 2 * k + 1] = fmaf(f1, f1, acc_q[j * 8 + 2 * k + 1]);
+          acc_q[j * 8 + 2 * k + 1] = fmaf(f1, a.aux_mode ? cx[2 * k + 1] : f1, acc_q[j * 8 + 2 * k + 1]);
         }
       }
       tc::st_shared_v4(st + soff[j], q[0], q[1], q[2], q[3]);
@@ -689,7 +722,11 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
   const uint32_t stage_bytes = a.a_slot_bytes + (a.resident ? 0u : (uint32_t)a.max_nr * a.b_tap_bytes);
   float* s_stats = reinterpret_cast<float*>(s_stage + (size_t)a.stages * stage_bytes);
   const int stats_floats = a.stats ? kEpiWarps * 2 * a.Cout : 0;
-  Barriers* bars = reinterpret_cast<Barriers*>(reinterpret_cast<uint8_t*>(s_stats) + ((stats_floats * 4 + 15) & ~15));
+  float* s_pre = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_stats) + ((stats_floats * 4 + 15) & ~15));
+  const int pre_floats = a.pre_ss ? 2 * a.pre_pad : 0;
+  float* s_aux = s_pre + pre_floats;              // pre_pad is a multiple of 16: s_aux stays 16-byte aligned
+  const int aux_floats = a.aux_mode ? 2 * a.Cout : 0;
+  Barriers* bars = reinterpret_cast<Barriers*>(reinterpret_cast<uint8_t*>(s_aux) + ((aux_floats * 4 + 15) & ~15));
 
   const int warp = tc::warp_idx_uniform();
   const int lane = threadIdx.x & 31;
@@ -701,6 +738,7 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
       tc::mbar_init(&bars->tmem_empty[i], a.epi_tma == 3 ? kEpiWarps / 2 : kEpiWarps);   // per-warp mode: one group per buffer
     }
     tc::mbar_init(&bars->resident_full, 1);
+    for (int i = 0; i < a.stages; ++i) tc::mbar_init(&bars->ready[i], 2);
     tc::fence_barrier_init();
     tc::prefetch_tmap(&tm.a[0]);
     tc::prefetch_tmap(&tm.b);
@@ -708,6 +746,11 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
   }
   if (warp == 2) tc::tmem_alloc(&bars->tmem_base, kTmemCols);
   for (int i = threadIdx.x; i < stats_floats; i += kThreads) s_stats[i] = 0.f;
+  for (int i = threadIdx.x; i < pre_floats; i += kThreads) {      // [scale | shift], zero beyond the real channels
+    const int which = i / a.pre_pad, c = i - which * a.pre_pad;
+    s_pre[i] = c < a.pre_c ? __ldg(a.pre_ss + which * a.pre_c + c) : 0.f;
+  }
+  for (int i = threadIdx.x; i < aux_floats; i += kThreads) s_aux[i] = __ldg(a.aux_ss + i);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -787,7 +830,7 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
         const ColLoad& col = a.cols[c];
         for (int kc = 0; kc < a.kchunks; ++kc) {
           DP_T(const long long q1 = clock64();)
-          tc::mbar_wait(&bars->full[stage], phase);
+          tc::mbar_wait(a.pre_ss ? &bars->ready[stage] : &bars->full[stage], phase);
           tc::fence_after_sync();
           DP_T(const long long q2 = clock64(); dbg_wf += q2 - q1;)
           const uint32_t a_base = tc::smem_u32(s_stage + (size_t)stage * stage_bytes);
@@ -839,17 +882,48 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
     }
     DP_T(if (a.dbg && blockIdx.x == 0 && wiss == 0) { a.dbg[0] = dbg_te; a.dbg[1] = dbg_wf; a.dbg[2] = dbg_is; a.dbg[4] = it; })
     }
+  } else if (a.pre_ss && (warp == 2 || warp == 3)) {
+    // ================= prologue transform (BatchNorm + activation on the landed A boxes) =================
+    const int t64 = (warp - 2) * 32 + lane;
+    uint32_t stage = 0, phase = 0;
+    TileIter ti;
+    ti.init(a, blockIdx.x);
+    for (long long item = blockIdx.x; item < a.total_items; item += gridDim.x, ti.step(a)) {
+      const int y0 = ti.ty * a.th, x0 = ti.tx * a.tw;
+      for (int c = 0; c < a.ncols; ++c) {
+        const ColLoad& col = a.cols[c];
+        const int boxW = a.halo ? a.tw + 2 : a.tw;
+        const int npx = (a.halo ? a.th + 2 : a.th + col.nr - 1) * boxW;
+        for (int kc = 0; kc < a.kchunks; ++kc) {
+          tc::mbar_wait(&bars->full[stage], phase);
+          const uint32_t base = tc::smem_u32(s_stage + (size_t)stage * stage_bytes);
+          if (a.row_bytes == 128)
+            transform_box<128, 64>(base, npx, boxW, x0 + col.dx, y0 + col.dy, a.pW[col.map], a.pH[col.map], s_pre, a.pre_pad,
+                               kc * a.KB, a.pre_act, t64);
+          else if (a.row_bytes == 64)
+            transform_box<64, 64>(base, npx, boxW, x0 + col.dx, y0 + col.dy, a.pW[col.map], a.pH[col.map], s_pre, a.pre_pad,
+                              kc * a.KB, a.pre_act, t64);
+          else
+            transform_box<32, 64>(base, npx, boxW, x0 + col.dx, y0 + col.dy, a.pW[col.map], a.pH[col.map], s_pre, a.pre_pad,
+                              kc * a.KB, a.pre_act, t64);
+          tc::fence_proxy_async();              // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&bars->ready[stage]);
+          if (++stage == (uint32_t)a.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
   } else if (warp >= 4) {
     // ================= epilogue: TMEM -> registers -> (smem -> TMA store | global) =================
     if (a.epi_tma == 3) {
-      if (a.BN == 32) epilogue_tma_warp<32>(tm, a, bars, s_out, s_stats, tmem, warp, lane);
-      else epilogue_tma_warp<16>(tm, a, bars, s_out, s_stats, tmem, warp, lane);
+      if (a.BN == 32) epilogue_tma_warp<32>(tm, a, bars, s_out, s_stats, s_aux, tmem, warp, lane);
+      else epilogue_tma_warp<16>(tm, a, bars, s_out, s_stats, s_aux, tmem, warp, lane);
     } else if (a.epi_tma == 2) {
       epilogue_tma_wide(tm, a, bars, s_out, s_stats, tmem, warp, lane);
     } else if (a.epi_tma) {
-      if (a.BN == 64) epilogue_tma<32>(tm, a, bars, s_out, s_stats, tmem, warp, lane);
-      else if (a.BN == 32) epilogue_tma<16>(tm, a, bars, s_out, s_stats, tmem, warp, lane);
-      else epilogue_tma<8>(tm, a, bars, s_out, s_stats, tmem, warp, lane);
+      if (a.BN == 64) epilogue_tma<32>(tm, a, bars, s_out, s_stats, s_aux, tmem, warp, lane);
+      else if (a.BN == 32) epilogue_tma<16>(tm, a, bars, s_out, s_stats, s_aux, tmem, warp, lane);
+      else epilogue_tma<8>(tm, a, bars, s_out, s_stats, s_aux, tmem, warp, lane);
     } else {
       epilogue_direct(a, bars, s_stats, tmem, warp, lane);
     }
@@ -884,6 +958,9 @@ struct Epilogue {
   const void* res2; long long res2_ld;
   int relu; void* out; long long out_ld; void* out2; long long out2_ld; int relu2;
   float* stats;
+  // fused BatchNorm (dp_conv_fuse_t): prologue scale/shift/activation of the input, backward mask + sums of the output
+  const float* pre_ss = nullptr; int pre_act = 0;
+  const void* mask_x = nullptr; long long mask_ld = 0; const float* mask_ss = nullptr; int mask_act = 0;
 };
 
 struct Plan {
@@ -894,7 +971,7 @@ struct Plan {
 
 // geometry that does not depend on pointers: tile shape, K/N blocking, stages, grid
 int make_plan(Plan& p, int B, int Hg, int Wg, int Cin, int Cout, const ColSpec* cols, int ncols, int want_stats,
-              int allow_halo = 0, int n_out = 1) {
+              int allow_halo = 0, int n_out = 1, int pre = 0, int aux = 0) {
   ConvArgs& a = p.a;
   if (ncols < 1 || ncols > kMaxCols) return dp_set_error(DP_ERR_UNSUPPORTED, "conv_tc: %d column loads", ncols);
   a.B = B; a.H = Hg; a.W = Wg; a.Cout = Cout;
@@ -959,7 +1036,9 @@ int make_plan(Plan& p, int B, int Hg, int Wg, int Cin, int Cout, const ColSpec* 
   const size_t all_w = (size_t)a.nslots * a.kchunks * a.b_tap_bytes;
   a.resident = (a.n_blocks == 1 && all_w <= 100 * 1024) ? 1 : 0;
   a.resident_bytes = a.resident ? (uint32_t)all_w : 0u;
-  const size_t stats_bytes = want_stats ? ((size_t)kEpiWarps * 2 * Cout * 4 + 15) & ~size_t(15) : 0;
+  a.pre_pad = a.kchunks * a.KB;
+  const size_t stats_bytes = (want_stats ? ((size_t)kEpiWarps * 2 * Cout * 4 + 15) & ~size_t(15) : 0) +
+                             (pre ? (size_t)2 * a.pre_pad * 4 : 0) + (aux ? ((size_t)2 * Cout * 4 + 15) & ~size_t(15) : 0);
   // TMA-store epilogue: one N block of 16/32/64 columns; two staging tiles per output
   a.epi_tma = (a.n_blocks == 1 && (a.BN == 16 || a.BN == 32 || a.BN == 64) && n_out >= 1) ? 1 : 0;
   a.out_tile_bytes = (uint32_t)(128 * a.BN * 2);
@@ -995,6 +1074,7 @@ int make_plan(Plan& p, int B, int Hg, int Wg, int Cin, int Cout, const ColSpec* 
   // block t mod (stages / ksteps), even blocks belong to issuer 0 and odd blocks to issuer 1, and every full/empty
   // barrier has exactly one producer and one consumer for the life of the kernel (the single k-step case is the same
   // rule with ksteps = 1).  Shapes whose ring cannot hold two tiles run with one issuer.
+  if (pre) a.niss = 1;      // warps 2 and 3 run the prologue transform
   {
     const int ksteps = a.ncols * a.kchunks;
     if (a.niss == 2) {
@@ -1021,8 +1101,13 @@ int launch(const Plane* planes, const ColSpec* cols, int ncols, int B, int Hg, i
            int Cin_p, int ntaps, int Cout, const Epilogue& ep, const OutMap& om, cudaStream_t stream, int allow_halo = 0) {
   Plan p;
   int rc = make_plan(p, B, Hg, Wg, Cin, Cout, cols, ncols, ep.stats != nullptr, allow_halo,
-                     ep.out ? (ep.out2 ? 2 : 1) : 0);
+                     ep.out ? (ep.out2 ? 2 : 1) : 0, ep.pre_ss != nullptr, ep.mask_x != nullptr);
   if (rc) return rc;
+  if (ep.mask_x && !(p.a.epi_tma == 1 || p.a.epi_tma == 3))
+    return dp_set_error(DP_ERR_UNSUPPORTED, "conv_tc: the BatchNorm-backward epilogue needs a single 16/32/64-column N block "
+                        "(Cout %d)", Cout);
+  if (ep.mask_x && (ep.res2 || ep.relu || ep.out2))
+    return dp_set_error(DP_ERR_INVALID, "conv_tc: the BatchNorm-backward epilogue excludes residual2 / relu / dual output");
   if (p.a.halo) ncols = 1;
   ConvArgs& a = p.a;
   a.Ho = om.Ho; a.Wo = om.Wo; a.osy = om.osy; a.osx = om.osx; a.oay = om.oay; a.oax = om.oax;
@@ -1033,6 +1118,12 @@ int launch(const Plane* planes, const ColSpec* cols, int ncols, int B, int Hg, i
   a.resb = reinterpret_cast<const bf16*>(ep.res2); a.resb_ld = ep.res2_ld;
   a.relu = ep.relu; a.relu2 = ep.relu2;
   a.stats = ep.stats;
+  a.pre_ss = ep.pre_ss; a.pre_act = ep.pre_act; a.pre_c = Cin;
+  for (int c = 0; c < kMaxCols; ++c) { a.pH[c] = planes[cols[c < ncols ? c : 0].plane].Hp; a.pW[c] = planes[cols[c < ncols ? c : 0].plane].Wp; }
+  a.aux_mode = ep.mask_x ? 1 : 0;
+  a.aux_ss = ep.mask_ss;
+  a.aux_hi = ep.mask_act == 2 ? 6.f : __builtin_inff();
+  if (ep.mask_x) { a.resb = reinterpret_cast<const bf16*>(ep.mask_x); a.resb_ld = ep.mask_ld; }
   a.dbg = g_wg_dbg;
   Maps tm;
   for (int c = 0; c < ncols; ++c) {
@@ -1161,6 +1252,22 @@ int dp_conv2d_tc(const void* x, long long x_ld, int B, int H, int W, int Cin, co
                  int Cout, int KS, const float* bias, const void* residual, long long res_ld, const void* residual2,
                  long long res2_ld, int relu, void* out, long long out_ld, void* out2, long long out2_ld, int relu2,
                  float* stats_partials, cudaStream_t stream) {
+  return dp_conv2d_tc_fused(x, x_ld, B, H, W, Cin, w_packed, Cin_p, Cout, KS, bias, residual, res_ld, residual2, res2_ld,
+                            relu, out, out_ld, out2, out2_ld, relu2, stats_partials, nullptr, stream);
+}
+
+int dp_conv2d_tc_caps(int B, int H, int W, int Cin, int Cout, int KS) {
+  Plan p;
+  ColSpec cols[kMaxCols];
+  const int n = plain_cols(cols, KS);
+  if (make_plan(p, B, H, W, Cin, Cout, cols, n, 1, KS == 3, 1, 1, 1)) return 0;
+  return DP_CONV_CAP_PROLOGUE | ((p.a.epi_tma == 1 || p.a.epi_tma == 3) ? DP_CONV_CAP_BN_BACKWARD : 0);
+}
+
+int dp_conv2d_tc_fused(const void* x, long long x_ld, int B, int H, int W, int Cin, const void* w_packed, int Cin_p,
+                       int Cout, int KS, const float* bias, const void* residual, long long res_ld, const void* residual2,
+                       long long res2_ld, int relu, void* out, long long out_ld, void* out2, long long out2_ld, int relu2,
+                       float* stats_partials, const dp_conv_fuse_t* fuse, cudaStream_t stream) {
   DP_CHECK_ARG(x && w_packed && (out || out2), "dp_conv2d_tc: null pointer");
   DP_CHECK_ARG(KS == 3 || KS == 1, "dp_conv2d_tc: kernel size %d (only 1 and 3, stride 1)", KS);
   DP_CHECK_ARG(Cin % 8 == 0 && Cout % 8 == 0 && Cin_p % 8 == 0 && Cin_p >= Cin,
@@ -1173,6 +1280,12 @@ int dp_conv2d_tc(const void* x, long long x_ld, int B, int H, int W, int Cin, co
   ColSpec cols[kMaxCols];
   const int n = plain_cols(cols, KS);
   Epilogue ep{bias, residual, res_ld, residual2, res2_ld, relu, out, out_ld, out2, out2_ld, relu2, stats_partials};
+  if (fuse) {
+    DP_CHECK_ARG(!fuse->mask_x || (fuse->mask_scale_shift && stats_partials && fuse->mask_ld % 8 == 0),
+                 "dp_conv2d_tc_fused: mask_x needs mask_scale_shift, stats_partials and a 16-byte aligned pixel stride");
+    ep.pre_ss = fuse->pre_scale_shift; ep.pre_act = fuse->pre_act;
+    ep.mask_x = fuse->mask_x; ep.mask_ld = fuse->mask_ld; ep.mask_ss = fuse->mask_scale_shift; ep.mask_act = fuse->mask_act;
+  }
   OutMap om{H, W, 1, 1, 0, 0};
   return launch(&pl, cols, n, B, H, W, Cin, w_packed, Cin_p, KS * KS, Cout, ep, om, stream, KS == 3);
 }

@@ -13,6 +13,7 @@
 // (no atomics) by wgrad_reduce_kernel, which also un-packs to the OIHW fp32 layout of param.grad.
 #include "common.cuh"
 #include "tc.cuh"
+#include "bn_fuse.cuh"
 #include "../../include/depth_b200.h"
 
 #ifdef DP_CONV_TIMING
@@ -53,6 +54,10 @@ struct WgArgs {
   long long tiles_total;
   uint32_t a_box_bytes, a_slot_bytes, stage_bytes;
   uint32_t rowA, rowB, layoutA, layoutB, idesc, a_lbo;
+  // fused BatchNorm prologue on the tapped operand: X = act(c * pre_ss[ci] + pre_ss[Cin + ci]), zero outside the plane
+  // (the epilogue warps, idle until the accumulators are complete, rewrite every landed X box in place)
+  const float* pre_ss; int pre_act;
+  int pH[kMaxKW * 2], pW[kMaxKW * 2];
   float* partial;  // [psplit][KH*KW][Cout][Cin]
   unsigned long long* dbg;  // optional cycle counters (diagnostics): [0]=producer wait, [1]=mma wait, [2]=mma issue, [3]=total, [4]=tiles
 };
@@ -61,7 +66,9 @@ struct __align__(8) WgBars {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
   uint64_t done;
+  uint64_t ready[kMaxStages];     // prologue mode: X boxes transformed (four arrivals: warps 2..5)
   uint32_t tmem_base;
+  __align__(16) float pre[2][64]; // this CTA's scale / shift slice (NC <= 64 channels)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -80,11 +87,17 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps tm, const __grid_constant__ WgArg
   if (threadIdx.x == 0) {
     for (int i = 0; i < a.stages; ++i) { tc::mbar_init(&bars->full[i], 1); tc::mbar_init(&bars->empty[i], 1); }
     tc::mbar_init(&bars->done, 1);
+    for (int i = 0; i < a.stages; ++i) tc::mbar_init(&bars->ready[i], 4);
     tc::fence_barrier_init();
     tc::prefetch_tmap(&tm.p);
     tc::prefetch_tmap(&tm.t[0]);
   }
   if (warp == 1) tc::tmem_alloc(&bars->tmem_base, 512);
+  if (a.pre_ss && threadIdx.x >= 64) {
+    const int i = threadIdx.x - 64;                 // 128 threads: [scale | shift] x 64 channels
+    const int which = i >> 6, c = cc * a.NC + (i & 63);
+    bars->pre[which][i & 63] = ((i & 63) < a.NC && c < a.Cin) ? __ldg(a.pre_ss + which * a.Cin + c) : 0.f;
+  }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -136,7 +149,7 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps tm, const __grid_constant__ WgArg
     const uint32_t a_step = (16u * a.rowA) >> 4, b_step = (16u * a.rowB) >> 4;   // 16 pixel rows per UMMA K-step
     for (long long t = ps; t < a.tiles_total; t += a.psplit) {
       DP_T(const long long c0 = clock64();)
-      tc::mbar_wait(&bars->full[stage], phase);
+      tc::mbar_wait(a.pre_ss ? &bars->ready[stage] : &bars->full[stage], phase);
       tc::fence_after_sync();
       DP_T(const long long c1 = clock64(); w_acc += c1 - c0; ++ntile;)
       const uint32_t a_base = tc::smem_u32(smem + (size_t)stage * a.stage_bytes);
@@ -180,6 +193,41 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps tm, const __grid_constant__ WgArg
     DP_T(if (a.dbg && blockIdx.x == 0) { a.dbg[1] = (unsigned long long)w_acc; a.dbg[2] = (unsigned long long)i_acc; a.dbg[4] = (unsigned long long)ntile; })
     }
   } else if (warp >= 2) {
+    if (a.pre_ss) {
+      // prologue transform of the tapped operand, tile by tile behind the producer
+      const int t128 = threadIdx.x - 64;
+      uint32_t stage = 0, phase = 0;
+      int tx, ty;
+      {
+        unsigned m = (unsigned)ps;
+        tx = (int)(m % (unsigned)a.tiles_x); m /= (unsigned)a.tiles_x;
+        ty = (int)(m % (unsigned)a.tiles_y);
+      }
+      for (long long t = ps; t < a.tiles_total; t += a.psplit) {
+        const int y0 = ty * a.th, x0 = tx * a.tw;
+        tc::mbar_wait(&bars->full[stage], phase);
+        const uint32_t x_base = tc::smem_u32(smem + (size_t)stage * a.stage_bytes) + (uint32_t)real_chunks * a.a_slot_bytes;
+        for (int g = 0; g < a.ngrp[s]; ++g) {
+          const WgGroup& G = a.grp[s][g];
+          const int boxW = a.halo ? a.pitch : a.tw;
+          const int npx = (a.halo ? a.th + 2 : a.th + G.nr - 1) * boxW;
+          const uint32_t base = x_base + G.slot_off;
+          if (a.rowB == 128)
+            dpf::transform_box<128, 128>(base, npx, boxW, x0 + G.dx, y0 + G.dy, a.pW[G.map], a.pH[G.map], &bars->pre[0][0], 64, 0, a.pre_act, t128);
+          else if (a.rowB == 64)
+            dpf::transform_box<64, 128>(base, npx, boxW, x0 + G.dx, y0 + G.dy, a.pW[G.map], a.pH[G.map], &bars->pre[0][0], 64, 0, a.pre_act, t128);
+          else
+            dpf::transform_box<32, 128>(base, npx, boxW, x0 + G.dx, y0 + G.dy, a.pW[G.map], a.pH[G.map], &bars->pre[0][0], 64, 0, a.pre_act, t128);
+        }
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bars->ready[stage]);
+        if (++stage == (uint32_t)a.stages) { stage = 0; phase ^= 1; }
+        tx += a.step_tx; ty += a.step_ty;
+        if (tx >= a.tiles_x) { tx -= a.tiles_x; ++ty; }
+        if (ty >= a.tiles_y) ty -= a.tiles_y;
+      }
+    }
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     tc::mbar_wait(&bars->done, 0);
     tc::fence_after_sync();
@@ -376,13 +424,16 @@ int wg_plan(WgPlan& p, int B, int Hg, int Wg, int Cp, int Ct, int K, int pad, in
 }
 
 int wg_launch(WgPlan& p, const void* P, long long p_ld, const WgPlaneT* planes /*[kMaxKW*2], indexed by map id*/, int B,
-              float* grad, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+              float* grad, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream,
+              const float* pre_ss = nullptr, int pre_act = 0) {
   WgArgs& a = p.a;
+  a.pre_ss = pre_ss; a.pre_act = pre_act;
   const int K = a.KH;
   const size_t need = (size_t)a.psplit * K * K * a.Cout * a.Cin * sizeof(float);
   if (workspace_bytes < need) return dp_set_error(DP_ERR_WORKSPACE, "wgrad_tc: workspace %zu < %zu", workspace_bytes, need);
   a.partial = reinterpret_cast<float*>(workspace);
   a.dbg = g_wg_dbg;
+  for (int i = 0; i < kMaxKW * 2; ++i) { a.pH[i] = planes[i].Hp; a.pW[i] = planes[i].Wp; }
   WgMaps tm;
   {
     uint64_t dims[4] = {(uint64_t)a.Cout, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)B};
@@ -439,6 +490,13 @@ size_t dp_conv2d_wgrad_tc_workspace(int B, int H, int W, int Cin, int Cout, int 
 int dp_conv2d_wgrad_tc(const void* x, long long x_ld, const void* dy, long long dy_ld, int B, int H, int W, int Cin,
                        int Cout, int KS, float* grad_oihw, int accumulate, void* workspace, size_t workspace_bytes,
                        cudaStream_t stream) {
+  return dp_conv2d_wgrad_tc_fused(x, x_ld, dy, dy_ld, B, H, W, Cin, Cout, KS, grad_oihw, accumulate, workspace,
+                                  workspace_bytes, nullptr, 0, stream);
+}
+
+int dp_conv2d_wgrad_tc_fused(const void* x, long long x_ld, const void* dy, long long dy_ld, int B, int H, int W, int Cin,
+                             int Cout, int KS, float* grad_oihw, int accumulate, void* workspace, size_t workspace_bytes,
+                             const float* pre_scale_shift, int pre_act, cudaStream_t stream) {
   DP_CHECK_ARG(x && dy && grad_oihw && workspace, "dp_conv2d_wgrad_tc: null pointer");
   DP_CHECK_ARG(KS == 3 || KS == 1, "dp_conv2d_wgrad_tc: kernel size %d", KS);
   DP_CHECK_ARG(Cin % 8 == 0 && Cout % 8 == 0 && x_ld % 8 == 0 && dy_ld % 8 == 0,
@@ -448,7 +506,8 @@ int dp_conv2d_wgrad_tc(const void* x, long long x_ld, const void* dy, long long 
   if (rc) return rc;
   WgPlaneT planes[kMaxKW * 2];
   for (int i = 0; i < kMaxKW * 2; ++i) planes[i] = WgPlaneT{x, x_ld, (long long)W * x_ld, (long long)H * W * x_ld, H, W};
-  return wg_launch(p, dy, dy_ld, planes, B, grad_oihw, accumulate, workspace, workspace_bytes, stream);
+  return wg_launch(p, dy, dy_ld, planes, B, grad_oihw, accumulate, workspace, workspace_bytes, stream, pre_scale_shift,
+                   pre_act);
 }
 
 /* grad[cp][ct][ky][kx] (+)= sum over plain-grid pixels p of P[p][cp] * T[2p - pad + k][ct]  (K x K taps, stride 2):

@@ -90,17 +90,12 @@ class ResidualBlock(nn.Module):
                 nn.BatchNorm2d(out_channels))
 
     def fused(self, x):
-        tr = self.training
-        r = ops.conv_tc(x, self.conv1.weight, None, stats=tr)
-        c1, st1 = r if tr else (r, None)
-        a1 = ops.bn_act(self.bn1, c1, st1, relu=True)
-        r = ops.conv_tc(a1, self.conv2.weight, None, stats=tr)
-        c2, st2 = r if tr else (r, None)
-        if len(self.shortcut) == 0:
-            return ops.bn_act(self.bn2, c2, st2, relu=True, res=x)
-        r = ops.conv_tc(x, self.shortcut[0].weight, None, stats=tr)
-        cs, sts = r if tr else (r, None)
-        return ops.bn_act(self.bn2, c2, st2, relu=True, bn2=self.shortcut[1], c2=cs, stats2=sts)
+        """one autograd node (ops.res_block): bn1 + ReLU live in conv2's operand path and in the epilogue of its data
+        gradient, the shortcut's gradient rides in conv1's data-gradient epilogue"""
+        if self.conv1.weight.shape[0] % 8 or self.conv1.weight.shape[1] % 8:
+            raise NotImplementedError("ResidualBlock on the tensor-core path needs channel counts that are multiples of 8")
+        sc = None if len(self.shortcut) == 0 else (self.shortcut[0], self.shortcut[1])
+        return ops.res_block(x, self.conv1, self.bn1, self.conv2, self.bn2, sc)
 
     def forward(self, x):
         t, pub = enter(x)

@@ -105,6 +105,16 @@ class _PackCache:
 
 PACKS = _PackCache()
 
+# Fused / capturable optimizers (torch.optim.AdamW(fused=True)) update parameters WITHOUT bumping `_version`
+# (measured: `_version` stays 0 across AdamW(fused=True).step()), so an eager training loop would keep convolving with
+# the packs of step 0.  Every optimizer step, of any optimizer, therefore invalidates the cache.
+try:
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_post_hook
+    _reg_post_hook(lambda _opt, _args, _kwargs: PACKS.invalidate())
+except ImportError:  # pragma: no cover - very old torch: fall back to never trusting the cache across calls
+    _PackCache.get = (lambda orig: (lambda self, w, swap, flip: (self.invalidate(), orig(self, w, swap, flip))[1]))(
+        _PackCache.get)
+
 
 # --------------------------------------------------------------------------------------------------
 # weight gradients on a side stream (opt-in: graphs.GraphedTrainStep)
@@ -794,6 +804,181 @@ def bn_act(bn, c, stats=None, relu=True, res=None, bn2=None, c2=None, stats2=Non
         ss2, save2, _ = _bn_coeffs(bn2, c2, stats2, bn2.training)
         g2, b2 = bn2.weight, bn2.bias
     return _BNAct.apply(c, bn.weight, bn.bias, ss, save, c2, g2, b2, ss2, save2, res, relu, used_batch)
+
+
+# --------------------------------------------------------------------------------------------------
+# ResidualBlock as ONE autograd node: BatchNorm folded into the neighbouring convolutions
+# --------------------------------------------------------------------------------------------------
+import ctypes as _ct
+
+
+def _conv_raw(x, wp, Cout, KS, res=None, stats=False, pre=None, mask=None):
+    """plain launch of the tcgen05 convolution (no autograd): returns (out, stats partials | None).
+    pre = (scale_shift [2][Cin], act): BatchNorm + activation of the input fused into the operand path;
+    mask = (c, scale_shift [2][Cout], act): BatchNorm-backward epilogue (masked gradient + its two batch sums)."""
+    B, H, W, Cin = x.shape
+    lib = L.lib()
+    out = _nhwc(B, H, W, Cout, x.device)
+    st = None
+    if stats or mask is not None:
+        st = torch.empty(lib.dp_conv2d_tc_grid(B, H, W, Cin, Cout, KS), 2, Cout, dtype=torch.float32, device=x.device)
+    fuse = None
+    if pre is not None or mask is not None:
+        fuse = L.ConvFuse(L.ptr(pre[0]) if pre is not None else None, int(pre[1]) if pre is not None else 0,
+                          L.ptr(mask[0]) if mask is not None else None, _ld(mask[0]) if mask is not None else 0,
+                          L.ptr(mask[1]) if mask is not None else None, int(mask[2]) if mask is not None else 0)
+    L.check(lib.dp_conv2d_tc_fused(L.ptr(x), _ld(x), B, H, W, Cin, L.ptr(wp), wp.shape[2], Cout, KS, None,
+                                   L.ptr(res), _ld(res) if res is not None else 0, None, 0, 0, L.ptr(out), Cout, None, 0, 0,
+                                   L.ptr(st), _ct.byref(fuse) if fuse is not None else None, L.stream()))
+    return out, st
+
+
+def _wgrad_raw(x, g, Cin, Cout, KS, pre=None):
+    B, H, W, _ = x.shape
+    lib = L.lib()
+    nb = lib.dp_conv2d_wgrad_tc_workspace(B, H, W, Cin, Cout, KS)
+    ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
+    dw = torch.empty(Cout, Cin, KS, KS, dtype=torch.float32, device=x.device)
+    L.check(lib.dp_conv2d_wgrad_tc_fused(L.ptr(x), _ld(x), L.ptr(g), _ld(g), B, H, W, Cin, Cout, KS, L.ptr(dw), 0, L.ptr(ws),
+                                         nb, L.ptr(pre[0]) if pre is not None else None, int(pre[1]) if pre is not None else 0,
+                                         L.stream()))
+    return dw
+
+
+def _bn_reduce(cx, gy, mask, mss, act):
+    """red[2][C] = (sum g, sum g*c) with g = gy * [activation passed]; the activation is recomputed from c (mss, mask =
+    residual added before it) or read from the stored output (mask = y, mss None)."""
+    lib = L.lib()
+    C = cx.shape[-1]
+    npix = cx.numel() // C
+    nb = lib.dp_chan_reduce_blocks()
+    part = torch.empty(nb, 2, C, dtype=torch.float32, device=cx.device)
+    L.check(lib.dp_chan_reduce(3 if act == 2 else 2, L.ptr(cx), _ld(cx), L.ptr(gy), _ld(gy), L.ptr(mask),
+                               _ld(mask) if mask is not None else 0, L.ptr(mss), npix, C, L.ptr(part), L.stream()))
+    return _fold_partials(part, C)
+
+
+def _fold_partials(part, C):
+    red = torch.empty(2, C, dtype=torch.float32, device=part.device)
+    L.check(L.lib().dp_sum_partials(L.ptr(part), part.shape[0], 2, C, L.ptr(red), 0, L.stream()))
+    return red
+
+
+def _bn_bwd(gy, mask, mss, cx, red, save, gamma, train, act, want_gmask=False, want_dx=True):
+    """BatchNorm backward apply: returns (dc, dgamma, dbeta, gmask)"""
+    lib = L.lib()
+    B, H, W, C = cx.shape
+    npix = B * H * W
+    dev = cx.device
+    dx = _nhwc(B, H, W, C, dev) if want_dx else None
+    gmask = _nhwc(B, H, W, C, dev) if want_gmask else None
+    dg = torch.empty(C, dtype=torch.float32, device=dev)
+    db = torch.empty(C, dtype=torch.float32, device=dev)
+    L.check(lib.dp_bn_bwd_apply(L.ptr(gy), _ld(gy), L.ptr(mask), _ld(mask) if mask is not None else 0, L.ptr(mss),
+                                L.ptr(cx), _ld(cx), L.ptr(red), L.ptr(save), L.ptr(_f32(gamma)), float(npix),
+                                int(train) | (2 if act == 2 else 0), npix, C, L.ptr(dx), C, L.ptr(gmask), C, L.ptr(dg),
+                                L.ptr(db), 0, L.stream()))
+    return dx, dg, db, gmask
+
+
+def _bn_apply_raw(c, ss, act, res=None, c2=None, ss2=None):
+    B, H, W, C = c.shape
+    y = _nhwc(B, H, W, C, c.device)
+    L.check(L.lib().dp_bn_apply(L.ptr(c), _ld(c), L.ptr(ss), L.ptr(c2), _ld(c2) if c2 is not None else 0, L.ptr(ss2),
+                                L.ptr(res), _ld(res) if res is not None else 0, B * H * W, C, int(act), L.ptr(y), C,
+                                L.stream()))
+    return y
+
+
+class _ResBlock(torch.autograd.Function):
+    """relu(bn2(conv2(relu(bn1(conv1(x))))) + shortcut(x))  (reference midas_semantics.py:129-151) as one autograd node.
+
+    forward:  conv1 (+ BN partial sums in its epilogue) -> conv2 whose operand path applies bn1 + ReLU to the landed
+              tiles (the activated tensor never reaches HBM; its BN partial sums again come from the epilogue) ->
+              one pass for bn2 + shortcut + ReLU.
+    backward: bn2 backward (reduce + apply) -> conv2 data gradient whose epilogue masks with bn1's ReLU and produces bn1's
+              two batch sums -> bn1 backward apply -> conv1 data gradient with the shortcut's gradient added in its
+              epilogue (no autograd accumulation kernel); the weight gradient of conv2 re-creates relu(bn1(c1)) in its
+              own operand path."""
+
+    @staticmethod
+    def forward(ctx, x, w1, g1, b1, w2, g2, b2, ws, gs, bs, bn1, bn2, bns):
+        C1, Cin = w1.shape[0], w1.shape[1]
+        C2 = w2.shape[0]
+        train = bn1.training
+        c1, st1 = _conv_raw(x, PACKS.get(w1, 0, 0), C1, 3, stats=train)
+        ss1, save1, tr1 = _bn_coeffs(bn1, c1, st1, train)
+        c2, st2 = _conv_raw(c1, PACKS.get(w2, 0, 0), C2, 3, stats=bn2.training, pre=(ss1, 1))
+        ss2, save2, tr2 = _bn_coeffs(bn2, c2, st2, bn2.training)
+        cs = sss = saves = None
+        trs = False
+        if ws is None:
+            y = _bn_apply_raw(c2, ss2, 1, res=x)
+        else:
+            cs, sts = _conv_raw(x, PACKS.get(ws, 0, 0), C2, 1, stats=bns.training)
+            sss, saves, trs = _bn_coeffs(bns, cs, sts, bns.training)
+            y = _bn_apply_raw(c2, ss2, 1, c2=cs, ss2=sss)
+        ctx.save_for_backward(x, w1, g1, w2, g2, ws, gs, c1, c2, cs, y if ws is not None else None, ss1, save1, ss2, save2,
+                              sss, saves)
+        ctx.trains = (tr1, tr2, trs)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w1, g1, w2, g2, ws, gs, c1, c2, cs, y, ss1, save1, ss2, save2, sss, saves = ctx.saved_tensors
+        tr1, tr2, trs = ctx.trains
+        C1, Cin = w1.shape[0], w1.shape[1]
+        C2 = w2.shape[0]
+        B, H, W, _ = x.shape
+        gy = _dense(gy)
+        need_x = ctx.needs_input_grad[0]
+        # ---- bn2 (+ shortcut bn) ----
+        gskip = dcs = dgs = dbs = None
+        if ws is None:
+            red2 = _bn_reduce(c2, gy, x, ss2, 1)
+            dc2, dg2, db2, gskip = _bn_bwd(gy, x, ss2, c2, red2, save2, g2, tr2, 1, want_gmask=need_x)
+        else:
+            red2 = _bn_reduce(c2, gy, y, None, 1)
+            dc2, dg2, db2, _ = _bn_bwd(gy, y, None, c2, red2, save2, g2, tr2, 1)
+            reds = _bn_reduce(cs, gy, y, None, 1)
+            dcs, dgs, dbs, _ = _bn_bwd(gy, y, None, cs, reds, saves, gs, trs, 1)
+        # ---- conv2: data gradient with bn1's ReLU mask and batch sums in the epilogue ----
+        wd2 = PACKS.get(w2, 1, 1)
+        if L.lib().dp_conv2d_tc_caps(B, H, W, C2, C1, 3) & L.CAP_BN_BACKWARD:
+            dz1, part = _conv_raw(dc2, wd2, C1, 3, mask=(c1, ss1, 1))
+            red1 = _fold_partials(part, C1)
+            dc1, dg1, db1, _ = _bn_bwd(dz1, None, None, c1, red1, save1, g1, tr1, 0)
+        else:
+            da1, _ = _conv_raw(dc2, wd2, C1, 3)
+            red1 = _bn_reduce(c1, da1, None, ss1, 1)
+            dc1, dg1, db1, _ = _bn_bwd(da1, None, ss1, c1, red1, save1, g1, tr1, 1)
+        dw2 = None
+        if ctx.needs_input_grad[4]:
+            dw2 = _on_side(w2, lambda: _wgrad_raw(c1, dc2, C1, C2, 3, pre=(ss1, 1)).to(w2.dtype), (c1, dc2))
+        # ---- conv1 (+ shortcut): the skip gradient rides in the data-gradient epilogue ----
+        dx = dw1 = dws = None
+        if need_x:
+            if ws is not None:
+                gskip, _ = _conv_raw(dcs, PACKS.get(ws, 1, 1), Cin, 1)
+            dx, _ = _conv_raw(dc1, PACKS.get(w1, 1, 1), Cin, 3, res=gskip)
+        if ctx.needs_input_grad[1]:
+            dw1 = _on_side(w1, lambda: _wgrad_raw(x, dc1, Cin, C1, 3).to(w1.dtype), (x, dc1))
+        if ws is not None and ctx.needs_input_grad[7]:
+            dws = _on_side(ws, lambda: _wgrad_raw(x, dcs, Cin, C2, 1).to(ws.dtype), (x, dcs))
+        cast = lambda t, ref: t.to(ref.dtype) if t is not None else None
+        return (dx, dw1, cast(dg1, g1), cast(db1, g1), dw2, cast(dg2, g2), cast(db2, g2), dws,
+                cast(dgs, gs) if gs is not None else None, cast(dbs, gs) if gs is not None else None, None, None, None)
+
+
+@_internal
+def res_block(x, conv1, bn1, conv2, bn2, shortcut):
+    """fused ResidualBlock (stride 1, bias-free convs); shortcut = None (identity) or (conv1x1, bn)."""
+    ws = gs = bs = bns = None
+    if shortcut is not None:
+        ws, bns = shortcut[0].weight, shortcut[1]
+        gs, bs = bns.weight, bns.bias
+    return _ResBlock.apply(x, conv1.weight, bn1.weight, bn1.bias, conv2.weight, bn2.weight, bn2.bias, ws, gs, bs,
+                           bn1, bn2, bns)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -89,7 +89,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(depth_b200._lib.LIB_PATH)
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
-    assert lib.dp_abi_version() == 2
+    assert lib.dp_abi_version() == 3
 
 
 def test_no_cpu_fallback():
