@@ -134,6 +134,8 @@ def run_ours(a):
     xh, th = xh.pin_memory(), th.pin_memory()
     xd, td = xh.to(dev), th.to(dev)
     # The whole step (forward, combined_loss, backward, NCCL gradient all-reduce, AdamW) is one CUDA graph.
+    if os.environ.get("DP_NO_BN_FUSION"):
+        ops.Fusion.prologue = ops.Fusion.backward = False
     gstep = depth_b200.GraphedTrainStep(model, opt, cfg, xd, td, use_rgb=True, world=world, warmup=max(a.warmup, 3),
                                         side_wgrad=not a.no_side_wgrad)
     red = gstep.red

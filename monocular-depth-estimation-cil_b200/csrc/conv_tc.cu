@@ -708,7 +708,11 @@ __device__ __forceinline__ void epilogue_direct(const ConvArgs& a, Barriers* bar
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+// kPre: the BatchNorm-prologue variant adds a fourth warpgroup (warps 12..15) that transforms the landed A boxes; the
+// register file is re-balanced with setmaxnreg so that the epilogue warpgroups keep their 168 registers at 512 threads.
+constexpr int kPreThreads = kThreads + 128;
+template <bool kPre>
+__global__ void __launch_bounds__(kPre ? kPreThreads : kThreads, 1)
 conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -738,26 +742,28 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
       tc::mbar_init(&bars->tmem_empty[i], a.epi_tma == 3 ? kEpiWarps / 2 : kEpiWarps);   // per-warp mode: one group per buffer
     }
     tc::mbar_init(&bars->resident_full, 1);
-    for (int i = 0; i < a.stages; ++i) tc::mbar_init(&bars->ready[i], 2);
+    for (int i = 0; i < a.stages; ++i) tc::mbar_init(&bars->ready[i], 4);
     tc::fence_barrier_init();
     tc::prefetch_tmap(&tm.a[0]);
     tc::prefetch_tmap(&tm.b);
     if (a.epi_tma) tc::prefetch_tmap(a.epi_tma == 3 ? &tm.o2 : &tm.o);
   }
   if (warp == 2) tc::tmem_alloc(&bars->tmem_base, kTmemCols);
-  for (int i = threadIdx.x; i < stats_floats; i += kThreads) s_stats[i] = 0.f;
-  for (int i = threadIdx.x; i < pre_floats; i += kThreads) {      // [scale | shift], zero beyond the real channels
+  for (int i = threadIdx.x; i < stats_floats; i += blockDim.x) s_stats[i] = 0.f;
+  for (int i = threadIdx.x; i < pre_floats; i += blockDim.x) {      // [scale | shift], zero beyond the real channels
     const int which = i / a.pre_pad, c = i - which * a.pre_pad;
     s_pre[i] = c < a.pre_c ? __ldg(a.pre_ss + which * a.pre_c + c) : 0.f;
   }
-  for (int i = threadIdx.x; i < aux_floats; i += kThreads) s_aux[i] = __ldg(a.aux_ss + i);
+  for (int i = threadIdx.x; i < aux_floats; i += blockDim.x) s_aux[i] = __ldg(a.aux_ss + i);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = bars->tmem_base;
   DP_T(const long long t_start = clock64();)
-
+  // kPre: 512 threads x 128 registers at launch; each role branch re-sizes its warpgroup's share first thing:
+  // (56 + 168 + 168 + 104) x 128 threads = 63488 <= 65536
   if (warp == 0) {
+    if constexpr (kPre) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     // ================= TMA producer (one elected lane) =================
     if (tc::elect_one_sync()) {
     if (a.resident) {
@@ -799,6 +805,7 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
     }
     }
   } else if (warp == 1 || (warp == 3 && a.niss == 2)) {
+    if constexpr (kPre) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (tc::elect_one_sync()) {
     // ================= MMA issuers (one thread each; two warps alternate tiles) =================
     // A lone thread needs ~50 cycles of scalar work per tcgen05.mma, more than a 128xNx16 UMMA with N <= 64 takes on
@@ -830,7 +837,7 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
         const ColLoad& col = a.cols[c];
         for (int kc = 0; kc < a.kchunks; ++kc) {
           DP_T(const long long q1 = clock64();)
-          tc::mbar_wait(a.pre_ss ? &bars->ready[stage] : &bars->full[stage], phase);
+          tc::mbar_wait(kPre ? &bars->ready[stage] : &bars->full[stage], phase);
           tc::fence_after_sync();
           DP_T(const long long q2 = clock64(); dbg_wf += q2 - q1;)
           const uint32_t a_base = tc::smem_u32(s_stage + (size_t)stage * stage_bytes);
@@ -882,9 +889,12 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
     }
     DP_T(if (a.dbg && blockIdx.x == 0 && wiss == 0) { a.dbg[0] = dbg_te; a.dbg[1] = dbg_wf; a.dbg[2] = dbg_is; a.dbg[4] = it; })
     }
-  } else if (a.pre_ss && (warp == 2 || warp == 3)) {
+  } else if (warp < 4) {
+    if constexpr (kPre) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");     // idle warps of the role warpgroup
+  } else if (kPre && warp >= 12) {
     // ================= prologue transform (BatchNorm + activation on the landed A boxes) =================
-    const int t64 = (warp - 2) * 32 + lane;
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+    const int t64 = (warp - 12) * 32 + lane;
     uint32_t stage = 0, phase = 0;
     TileIter ti;
     ti.init(a, blockIdx.x);
@@ -898,13 +908,13 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
           tc::mbar_wait(&bars->full[stage], phase);
           const uint32_t base = tc::smem_u32(s_stage + (size_t)stage * stage_bytes);
           if (a.row_bytes == 128)
-            transform_box<128, 64>(base, npx, boxW, x0 + col.dx, y0 + col.dy, a.pW[col.map], a.pH[col.map], s_pre, a.pre_pad,
+            transform_box<128, 128>(base, npx, boxW, x0 + col.dx, y0 + col.dy, a.pW[col.map], a.pH[col.map], s_pre, a.pre_pad,
                                kc * a.KB, a.pre_act, t64);
           else if (a.row_bytes == 64)
-            transform_box<64, 64>(base, npx, boxW, x0 + col.dx, y0 + col.dy, a.pW[col.map], a.pH[col.map], s_pre, a.pre_pad,
+            transform_box<64, 128>(base, npx, boxW, x0 + col.dx, y0 + col.dy, a.pW[col.map], a.pH[col.map], s_pre, a.pre_pad,
                               kc * a.KB, a.pre_act, t64);
           else
-            transform_box<32, 64>(base, npx, boxW, x0 + col.dx, y0 + col.dy, a.pW[col.map], a.pH[col.map], s_pre, a.pre_pad,
+            transform_box<32, 128>(base, npx, boxW, x0 + col.dx, y0 + col.dy, a.pW[col.map], a.pH[col.map], s_pre, a.pre_pad,
                               kc * a.KB, a.pre_act, t64);
           tc::fence_proxy_async();              // generic-proxy writes -> visible to the tensor core's async-proxy reads
           __syncwarp();
@@ -913,8 +923,9 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 12) {
     // ================= epilogue: TMEM -> registers -> (smem -> TMA store | global) =================
+    if constexpr (kPre) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
     if (a.epi_tma == 3) {
       if (a.BN == 32) epilogue_tma_warp<32>(tm, a, bars, s_out, s_stats, s_aux, tmem, warp, lane);
       else epilogue_tma_warp<16>(tm, a, bars, s_out, s_stats, s_aux, tmem, warp, lane);
@@ -1074,12 +1085,12 @@ int make_plan(Plan& p, int B, int Hg, int Wg, int Cin, int Cout, const ColSpec* 
   // block t mod (stages / ksteps), even blocks belong to issuer 0 and odd blocks to issuer 1, and every full/empty
   // barrier has exactly one producer and one consumer for the life of the kernel (the single k-step case is the same
   // rule with ksteps = 1).  Shapes whose ring cannot hold two tiles run with one issuer.
-  if (pre) a.niss = 1;      // warps 2 and 3 run the prologue transform
   {
     const int ksteps = a.ncols * a.kchunks;
+    static const int multi_ok = []() { const char* e = getenv("DP_TWO_ISSUER_MULTI"); return e ? atoi(e) : 1; }();
     if (a.niss == 2) {
       const int per = 2 * ksteps;
-      if (ksteps > 4 || a.stages < per) a.niss = 1;
+      if (ksteps > 4 || a.stages < per || (ksteps > 1 && !multi_ok)) a.niss = 1;
       else a.stages = (a.stages / per) * per;
     }
   }
@@ -1169,9 +1180,10 @@ int launch(const Plane* planes, const ColSpec* cols, int ncols, int B, int Hg, i
       if (rc) return rc;
     }
   }
-  cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+  auto kern = a.pre_ss ? conv_tc_kernel<true> : conv_tc_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
   if (e != cudaSuccess) return dp_set_error(DP_ERR_CUDA, "cudaFuncSetAttribute(%zu): %s", p.smem, cudaGetErrorString(e));
-  conv_tc_kernel<<<p.grid, kThreads, p.smem, stream>>>(tm, a);
+  kern<<<p.grid, a.pre_ss ? kPreThreads : kThreads, p.smem, stream>>>(tm, a);
   DP_CHECK_LAUNCH("conv_tc_kernel");
   return DP_OK;
 }

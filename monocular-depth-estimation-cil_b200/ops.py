@@ -890,6 +890,13 @@ def _bn_apply_raw(c, ss, act, res=None, c2=None, ss2=None):
     return y
 
 
+class Fusion:
+    """which BatchNorm fusions the block-level autograd nodes use (all on by default; the switches exist so that the
+    parity tests and tools/fused_micro.py can compare each fused launch with its unfused pipeline)"""
+    prologue = True       # bn + ReLU of the input inside the consumer conv's operand path (forward and weight gradient)
+    backward = True       # ReLU mask + BatchNorm-backward batch sums in the data-gradient epilogue
+
+
 class _ResBlock(torch.autograd.Function):
     """relu(bn2(conv2(relu(bn1(conv1(x))))) + shortcut(x))  (reference midas_semantics.py:129-151) as one autograd node.
 
@@ -908,7 +915,12 @@ class _ResBlock(torch.autograd.Function):
         train = bn1.training
         c1, st1 = _conv_raw(x, PACKS.get(w1, 0, 0), C1, 3, stats=train)
         ss1, save1, tr1 = _bn_coeffs(bn1, c1, st1, train)
-        c2, st2 = _conv_raw(c1, PACKS.get(w2, 0, 0), C2, 3, stats=bn2.training, pre=(ss1, 1))
+        a1 = None
+        if Fusion.prologue:
+            c2, st2 = _conv_raw(c1, PACKS.get(w2, 0, 0), C2, 3, stats=bn2.training, pre=(ss1, 1))
+        else:
+            a1 = _bn_apply_raw(c1, ss1, 1)
+            c2, st2 = _conv_raw(a1, PACKS.get(w2, 0, 0), C2, 3, stats=bn2.training)
         ss2, save2, tr2 = _bn_coeffs(bn2, c2, st2, bn2.training)
         cs = sss = saves = None
         trs = False
@@ -919,13 +931,13 @@ class _ResBlock(torch.autograd.Function):
             sss, saves, trs = _bn_coeffs(bns, cs, sts, bns.training)
             y = _bn_apply_raw(c2, ss2, 1, c2=cs, ss2=sss)
         ctx.save_for_backward(x, w1, g1, w2, g2, ws, gs, c1, c2, cs, y if ws is not None else None, ss1, save1, ss2, save2,
-                              sss, saves)
+                              sss, saves, a1)
         ctx.trains = (tr1, tr2, trs)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, w1, g1, w2, g2, ws, gs, c1, c2, cs, y, ss1, save1, ss2, save2, sss, saves = ctx.saved_tensors
+        x, w1, g1, w2, g2, ws, gs, c1, c2, cs, y, ss1, save1, ss2, save2, sss, saves, a1 = ctx.saved_tensors
         tr1, tr2, trs = ctx.trains
         C1, Cin = w1.shape[0], w1.shape[1]
         C2 = w2.shape[0]
@@ -944,7 +956,7 @@ class _ResBlock(torch.autograd.Function):
             dcs, dgs, dbs, _ = _bn_bwd(gy, y, None, cs, reds, saves, gs, trs, 1)
         # ---- conv2: data gradient with bn1's ReLU mask and batch sums in the epilogue ----
         wd2 = PACKS.get(w2, 1, 1)
-        if L.lib().dp_conv2d_tc_caps(B, H, W, C2, C1, 3) & L.CAP_BN_BACKWARD:
+        if Fusion.backward and L.lib().dp_conv2d_tc_caps(B, H, W, C2, C1, 3) & L.CAP_BN_BACKWARD:
             dz1, part = _conv_raw(dc2, wd2, C1, 3, mask=(c1, ss1, 1))
             red1 = _fold_partials(part, C1)
             dc1, dg1, db1, _ = _bn_bwd(dz1, None, None, c1, red1, save1, g1, tr1, 0)
@@ -954,7 +966,10 @@ class _ResBlock(torch.autograd.Function):
             dc1, dg1, db1, _ = _bn_bwd(da1, None, ss1, c1, red1, save1, g1, tr1, 1)
         dw2 = None
         if ctx.needs_input_grad[4]:
-            dw2 = _on_side(w2, lambda: _wgrad_raw(c1, dc2, C1, C2, 3, pre=(ss1, 1)).to(w2.dtype), (c1, dc2))
+            if a1 is None:
+                dw2 = _on_side(w2, lambda: _wgrad_raw(c1, dc2, C1, C2, 3, pre=(ss1, 1)).to(w2.dtype), (c1, dc2))
+            else:
+                dw2 = _on_side(w2, lambda: _wgrad_raw(a1, dc2, C1, C2, 3).to(w2.dtype), (a1, dc2))
         # ---- conv1 (+ shortcut): the skip gradient rides in the data-gradient epilogue ----
         dx = dw1 = dws = None
         if need_x:

@@ -143,3 +143,28 @@ def evaluate_metric_sums(outputs, targets):
     for k in (1, 2, 3):
         res[f"d{k}"] = int((r < 1.25 ** k).sum().item())
     return res
+
+
+def evaluate_model(model, val_loader, device="cpu"):
+    """reference src/main.py:254-392 `evaluate_model`: the whole loop (eval mode, no grad, resize to the target size,
+    per-batch sums, per-image numpy siRMSE, final normalisation by N * C * H * W) -> dict MAE, RMSE, siRMSE, REL,
+    Delta1..3.  Pinned against the reference's own function by oracle/make_golden.py (identity model, two batches,
+    prediction resolution != target resolution)."""
+    import math
+    model.eval()
+    acc = {"abs": 0.0, "sq": 0.0, "rel": 0.0, "sirmse": 0.0, "d1": 0.0, "d2": 0.0, "d3": 0.0}
+    total_samples, target_shape = 0, None
+    with torch.no_grad():
+        for inputs, targets, _names in val_loader:
+            inputs, targets = inputs.to(device), targets.to(device)
+            total_samples += inputs.size(0)
+            if target_shape is None:
+                target_shape = targets.shape
+            outputs = model(inputs).unsqueeze(1)
+            sums = evaluate_metric_sums(outputs, targets)
+            for k in acc:
+                acc[k] += sums[k]
+    total_pixels = target_shape[1] * target_shape[2] * target_shape[3]
+    n = total_samples * total_pixels
+    return {"MAE": acc["abs"] / n, "RMSE": math.sqrt(acc["sq"] / n), "siRMSE": acc["sirmse"] / total_samples,
+            "REL": acc["rel"] / n, "Delta1": acc["d1"] / n, "Delta2": acc["d2"] / n, "Delta3": acc["d3"] / n}

@@ -121,13 +121,51 @@ def do_losses(ref_util):
             for k, v in g_ref.items():
                 small_store[f"{name}.grad_{k}"] = v.numpy()
         print("loss case", name, {k: round(v, 6) for k, v in r_ref.items()})
-    # main.evaluate_model metric set is inline code in the reference loop (main.py:254-392); record the oracle's
-    # restatement on the small case as a regression vector (checked by hand against the formulae).
+    # main.evaluate_model (main.py:254-392): run the REFERENCE's own function (imported with kornia / omegaconf / wandb
+    # stubs) on an identity model over two batches whose prediction resolution differs from the target's, and require
+    # the oracle's restatement to reproduce its dict; the inputs and the reference's dict are stored as golden vectors.
+    ref_main = ref_import.import_reference_main()
+    ev_batches = evaluate_model_case()
+    ident = IdentityDepth()
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        m_ref = ref_main.evaluate_model(ident, ev_batches, "cpu")
+    m_ora = ol.evaluate_model(ident, ev_batches, "cpu")
+    for k, v in m_ref.items():
+        assert abs(float(v) - float(m_ora[k])) <= 1e-6 * max(abs(float(v)), 1e-12), f"evaluate_model {k}: {v} vs {m_ora[k]}"
+    gold["evaluate_model"] = {k: float(v) for k, v in m_ref.items()}
+    for i, (x, t, _n) in enumerate(ev_batches):
+        small_store[f"evaluate_model.inputs{i}"] = x.numpy()
+        small_store[f"evaluate_model.targets{i}"] = t.numpy()
+    print("evaluate_model (reference)", {k: round(float(v), 6) for k, v in m_ref.items()})
     p, t, rgb = loss_cases()["small_zeros"]()
     gold["small_zeros"]["evaluate_model_sums"] = ol.evaluate_metric_sums(p, t)
     with open(os.path.join(GOLD, "loss_metric_golden.json"), "w") as f:
         json.dump(gold, f, indent=1, sort_keys=True)
     np.savez_compressed(os.path.join(GOLD, "loss_small_inputs.npz"), **small_store)
+
+
+class IdentityDepth(nn.Module):
+    """'model' whose prediction is channel 0 of its input: drives main.evaluate_model with known depth maps"""
+
+    def forward(self, x):
+        return x[:, 0]
+
+
+def evaluate_model_case():
+    """two batches (3 + 2 samples) of (inputs (B,3,30,44) carrying the prediction in channel 0, targets (B,1,24,36), names):
+    exact zeros in both prediction and target, values across the 1.25^k thresholds"""
+    out = []
+    for i, b in enumerate((3, 2)):
+        g = torch.Generator().manual_seed(9100 + i)
+        t = torch.rand(b, 1, 24, 36, generator=g) * 9.9 + 0.1
+        p = torch.nn.functional.interpolate(t, size=(30, 44), mode="bilinear", align_corners=True)
+        p = p * torch.exp(0.35 * torch.randn(p.shape, generator=g)) * 1.2
+        p[:, :, :2, :5] = 0.0
+        t[:, :, 5:7, 3:9] = 0.0
+        x = torch.cat([p, torch.rand(b, 2, 30, 44, generator=g)], dim=1)
+        out.append((x, t, [f"s{i}_{j}" for j in range(b)]))
+    return out
 
 
 def build_reference(kind, kw, ref_blocks, ref_dpt, ref_sem):

@@ -55,3 +55,18 @@ def offline_hub(hub_load):
         yield
     finally:
         torch.hub.load = real
+
+
+def import_reference_main():
+    """the reference's src/main.py (evaluate_model, combined_loss live there).  kornia / omegaconf are absent from this
+    image and wandb must not start a session: inert stubs stand in for them (none is touched by evaluate_model)."""
+    import_reference()
+    for name in ("kornia", "kornia.augmentation", "kornia.geometry", "omegaconf", "wandb"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["kornia"].augmentation = sys.modules["kornia.augmentation"]
+    sys.modules["kornia"].geometry = sys.modules["kornia.geometry"]
+    if not hasattr(sys.modules["omegaconf"], "OmegaConf"):
+        sys.modules["omegaconf"].OmegaConf = type("OmegaConf", (), {})
+    import main as ref_main                                   # noqa
+    return ref_main

@@ -235,3 +235,25 @@ def test_evaluation_loop_matches_reference_arithmetic(pkg):
     assert abs(got["si_rmse"] - want[0]) <= 1e-5 * abs(want[0])
     assert abs(got["abs_rel"] - want[1]) <= 1e-5 * abs(want[1])
     assert all(abs(a - b) <= 1e-4 for a, b in zip(got["delta"], want[2:]))
+
+
+def test_evaluate_model_matches_reference_golden(pkg, golden_loss):
+    """M4 end to end: depth_b200.evaluation.evaluate_model (fused moments + counting kernels) against the dict produced by
+    the reference's own main.evaluate_model on the stored inputs.  Scalars within 1e-5 relative; the delta fractions
+    within 0.01 % of pixels."""
+    import os
+    import numpy as np
+    store = np.load(os.path.join(os.path.dirname(__file__), "golden", "loss_small_inputs.npz"))
+
+    class Ident(torch.nn.Module):
+        def forward(self, x):
+            return x[:, 0]
+
+    batches = [(torch.from_numpy(store[f"evaluate_model.inputs{i}"]), torch.from_numpy(store[f"evaluate_model.targets{i}"]), None)
+               for i in range(2)]
+    got = pkg.evaluation.evaluate_model(Ident(), batches, torch.device("cuda"))
+    ref = golden_loss["evaluate_model"]
+    for k in ("MAE", "RMSE", "siRMSE", "REL"):
+        assert abs(got[k] - ref[k]) <= 1e-5 * abs(ref[k]), (k, got[k], ref[k])
+    for k in ("Delta1", "Delta2", "Delta3"):
+        assert abs(got[k] - ref[k]) <= 1e-4, (k, got[k], ref[k])

@@ -212,3 +212,24 @@ def test_eval_plan_covers_every_sample_shape():
     assert lib.dp_eval_metrics_plan(37 * 53, 4, 3, smem, sms, None, None, None, None) == 0      # odd pixel count
     assert lib.dp_eval_metrics_plan(448 * 576, 4, 3, 16384, sms, None, None, None, None) == 0   # no room for a slot
     assert lib.dp_eval_metrics_plan(8000 * 8000, 4, 3, smem, sms, None, None, None, None) == 0  # sample larger than the chip's smem
+
+
+def test_evaluate_model_oracle_reproduces_reference_golden(golden_loss):
+    """M4: oracle.losses.evaluate_model vs the dict the REFERENCE's main.evaluate_model produced on the stored inputs
+    (oracle/make_golden.py runs the reference's own function: identity model, two batches, 30x44 predictions against
+    24x36 targets)."""
+    import os
+    import numpy as np
+    import torch
+    from oracle import losses as ol
+    store = np.load(os.path.join(os.path.dirname(__file__), "golden", "loss_small_inputs.npz"))
+
+    class Ident(torch.nn.Module):
+        def forward(self, x):
+            return x[:, 0]
+
+    batches = [(torch.from_numpy(store[f"evaluate_model.inputs{i}"]), torch.from_numpy(store[f"evaluate_model.targets{i}"]), None)
+               for i in range(2)]
+    got = ol.evaluate_model(Ident(), batches, "cpu")
+    for k, v in golden_loss["evaluate_model"].items():
+        assert abs(got[k] - v) <= 1e-6 * max(abs(v), 1e-12), (k, got[k], v)

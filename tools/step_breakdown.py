@@ -10,6 +10,9 @@ from depth_b200 import config as fx
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=32)
 a = ap.parse_args()
+if os.environ.get("DP_NO_BN_FUSION"):
+    from depth_b200 import ops as _ops
+    _ops.Fusion.prologue = _ops.Fusion.backward = False
 dev = torch.device("cuda", 0)
 model = bench.build_model(dev)
 cfg = fx.loss_config()
