@@ -121,8 +121,11 @@ int dp_metrics_combine(const double* moments, const unsigned long long* counts, 
  * thresholds: HOST pointer.  moments: device double[B][DP_NMOM] (S1, S2, AR filled).  counts: device u64[B][nthr].
  * out: device float[2+nthr] = SI-RMSE, AbsRel, delta_k (batch means).
  * workspace: device, >= dp_eval_metrics_workspace(B,H,W) bytes (contents irrelevant on entry).
- * fast_math = 0: IEEE logf / division (the reference's arithmetic); 1: MUFU lg2 / rcp (within ~1e-6 relative of the exact
- * path; HBM-bound instead of issue-bound). */
+ * fast_math = 0: IEEE logf / division (the reference's arithmetic, kept as the checker); 1: MUFU lg2 / rcp per operand;
+ * 2: the lean arithmetic - one shared reciprocal and one lg2 per pixel in the moments sweep, division-free
+ * classification hi < thr * lo in the counting sweep, exact two-quotient code for slices that hold a negative value or
+ * a non-finite scale.  Modes 1 and 2 differ from mode 0 by rounding only (SI-RMSE / AbsRel ~1e-7 relative, delta counts
+ * a few pixels per million; contract 1e-5 relative / 0.01 % of pixels). */
 size_t dp_eval_metrics_workspace(int B, int H, int W);
 /* The streaming kernel's decomposition for `pixels` per sample and `nthr` thresholds on a device with `smem_per_sm`
  * bytes of shared memory and `sms` SMs (host arithmetic only, no CUDA call): CTAs per sample, sample groups in flight, pixels per CTA slice and

@@ -185,6 +185,15 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def build_id():
+    """source hash of the library that was built (build.py writes it next to the .so)"""
+    try:
+        with open(os.path.join(_HERE, "build_id.txt")) as f:
+            return f.read().strip()
+    except OSError:
+        return "unknown"
+
+
 def launch_count():
     return int(lib().dp_launch_count())
 

@@ -50,7 +50,23 @@ def build(verbose=False, force=False):
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
     build_probe(verbose)
+    with open(os.path.join(HERE, "build_id.txt"), "w") as f:
+        f.write(source_id() + "\n")
     return LIB
+
+
+def source_id():
+    """sha1 over the kernel sources: profiles/*.json captured with ncu carry it, and bench.py pairs a timing with a
+    `traffic` figure only when the capture was taken from the same sources"""
+    import hashlib
+    h = hashlib.sha1()
+    files = sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")) +
+                   glob.glob(os.path.join(HERE, "..", "include", "*.h")))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:12]
 
 
 def build_probe(verbose=False):

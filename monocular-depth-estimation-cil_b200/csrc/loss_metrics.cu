@@ -643,16 +643,24 @@ constexpr int kEvCT = kEvCW * 32;           // consumer threads
 constexpr int kEvThreads = kEvCT + 64;      // + producer warp + exchange warp
 constexpr int kEvChunkPx = kEvCT * 4;       // pixels per chunk: one float4 of each operand per consumer thread
 constexpr int kEvMaxChunks = 8;             // chunks per slot
-constexpr int kEvSlots = 2;                 // shared-memory slots = samples in flight per CTA
+constexpr int kEvSlots = 2;                 // shared-memory slots = samples in flight per CTA (exact / MUFU arithmetic)
+// The lean arithmetic is no longer issue-bound, and with two slots the kernel is then bound by the latency of one
+// sample's round trip (load -> sweep 1 -> scale exchange through global memory -> sweep 2): two slots x 86 KB in flight
+// per 7 us is 55 % of an SM's HBM share.  It therefore runs with four smaller slots and classifies TWO samples behind the
+// moments sweep, so the exchange has two sweeps' time to complete and the producer stays two samples ahead.
+constexpr int kEvSlotsLean = 4, kEvLagLean = 2;
+constexpr int kEvCWLean = 14, kEvVPTLean = 2;   // 14 consumer warps x 2 float4 per chunk (measured: 28 x 1 -> 395, 14 x 2 -> 460, 7 x 4 -> 390 Gpx/s)
+constexpr int kEvPrefetch = 1;                  // samples of L2 prefetch beyond the slot ring (measured: 0 -> 398, 1 -> 404, 3 -> 390 Gpx/s)
 // static shared memory the plan leaves room for: 2.4 KB in the instantiations with a compile-time threshold count
 // (1 or 3), 3.4 KB with the run-time count (count arrays sized for DP_MAX_THR)
-constexpr int kEvStaticFixed = 3072, kEvStaticRuntime = 4096;
+constexpr int kEvStaticFixed = 5120, kEvStaticRuntime = 6144;
 __host__ inline int eval_static_allowance(int nthr) { return (nthr == 1 || nthr == 3) ? kEvStaticFixed : kEvStaticRuntime; }
 
 struct EvsArgs {
   const float* pred;
   const float* target;
   int B, nthr, G, ngroups, per;  // per: pixels per slice (multiple of 4)
+  int pf_dist;                   // L2 prefetch distance in samples (0 = off)
   long long n;
   float eps;
   float thr[DP_MAX_THR];
@@ -665,6 +673,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(tc::smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(tc::smem_u32(bar))
                : "memory");
+}
+// L2 prefetch of a contiguous range (no shared-memory slot, no completion to wait for): lets HBM stream several samples
+// ahead of the slot ring, so the slot loads themselves are served from L2 (bytes in flight are bounded by the L2, not
+// by the 223 KB of shared memory; DRAM traffic stays the algorithmic 8 B/px - every line is fetched once).
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(src)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(kEvCT) : "memory"); }
 __device__ __forceinline__ float lg2_approx(float x) {
@@ -684,27 +698,22 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // S1 travels as two 8-byte words {flag = 1 : 32 bits of the double}: an aligned 8-byte store is a single transaction, so
 // data and flag land together - no fence, no counter, one round trip to post and one polling read to collect.  The
 // words are zeroed by the entry point before the launch.
-template <bool LOG2_UNITS>
+template <bool LOG2_UNITS, int RB, int LAG, int NTS, int CW>
 __device__ __forceinline__ void exchange_loop(unsigned long long* ll, double* mom_part, int G, int ngroups, int group,
                                               int rank, int nit, long long n, uint64_t* red_full, uint64_t* scale_full,
-                                              const double* s_red /*[2][3*kEvCW]*/, float* s_scale /*[2]*/) {
+                                              const double* s_red /*[RB][3*kEvCW]*/, float* s_scale /*[RB]*/,
+                                              const unsigned* s_neg /*[RB][kEvCW]*/, unsigned* s_flag /*[RB]*/,
+                                              unsigned* s_cnt /*[RB][NTS]*/, uint64_t* done_bar,
+                                              unsigned long long* cnt_part, int nthr) {
+  // The warp is software-pipelined: iteration `it` folds and POSTS this CTA's partials of sample it, then COLLECTS the
+  // group's partials of sample it - 1, which every CTA posted one sample-time ago - so the poll normally succeeds on its
+  // first read and the warp's time per sample is one global round trip, not two.  The warp's per-sample time bounds the
+  // whole kernel (throughput = groups x pixels per sample / exchange time), so the folds are butterflies over lanes
+  // (fixed order: the same bits in every CTA of the group), not serial chains on one lane.
   const int lane = threadIdx.x & 31;
-  for (int it = 0; it < nit; ++it) {
+  auto collect = [&](int it) {
     const int b = group + it * ngroups;
-    if (lane == 0) {
-      tc::mbar_wait(&red_full[it & 1], (it >> 1) & 1);
-      double m0 = 0.0, m1 = 0.0, m2 = 0.0;
-      const double* r = s_red + (it & 1) * 3 * kEvCW;
-      for (int w = 0; w < kEvCW; ++w) { m0 += r[w]; m1 += r[kEvCW + w]; m2 += r[2 * kEvCW + w]; }
-      if (LOG2_UNITS) { m0 *= 0.6931471805599453; m1 *= 0.6931471805599453 * 0.6931471805599453; }
-      unsigned long long* w = ll + ((size_t)b * G + rank) * 2;
-      const unsigned long long w0 = (1ull << 32) | (unsigned)__double2hiint(m0);
-      const unsigned long long w1 = (1ull << 32) | (unsigned)__double2loint(m0);
-      asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(w), "l"(w0), "l"(w1) : "memory");
-      double* mp = mom_part + ((size_t)b * G + rank) * 4;      // for eval_gather_kernel
-      __stcg(mp + 0, m0); __stcg(mp + 1, m1); __stcg(mp + 2, m2);
-    }
-    __syncwarp();
+    const int rb = it % RB;
     double S1 = 0.0;
     const unsigned long long* gw = ll + (size_t)b * G * 2;
     for (int g0 = 0; g0 < G; g0 += 32) {
@@ -724,15 +733,58 @@ __device__ __forceinline__ void exchange_loop(unsigned long long* ll, double* mo
         }
       }
       const double v = g < G ? __hiloint2double((int)(unsigned)w0, (int)(unsigned)w1) : 0.0;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) S1 += __shfl_sync(0xffffffffu, v, i);
+      S1 += warp_sum(v);                    // xor butterfly: every lane of every CTA adds the same pairs in the same order
     }
     if (lane == 0) {
-      s_scale[it & 1] = expf((float)(-S1 / (double)n));
-      tc::mbar_arrive(&scale_full[it & 1]);
+      s_scale[rb] = expf((float)(-S1 / (double)n));
+      tc::mbar_arrive(&scale_full[rb]);
     }
     __syncwarp();
+  };
+  // Per-sample delta counts: every consumer warp adds its count to s_cnt[sample % RB] (shared-memory atomics, no CTA
+  // barrier).  A warp starts sweep 1 of sample `it` only after its sweep 2 of sample it - 1 - LAG, so once red_full[it]
+  // has completed the counts of that older sample are final: they are flushed here, and the ring slot is zeroed before
+  // scale_full of the sample that will reuse it is signalled.
+  int flushed = 0;
+  auto flush = [&](int j) {
+    const int b = group + j * ngroups;
+    if (lane < NTS) {
+      const unsigned v = s_cnt[(j % RB) * NTS + lane];
+      s_cnt[(j % RB) * NTS + lane] = 0u;
+      if (lane < nthr) cnt_part[((size_t)b * G + rank) * DP_MAX_THR + lane] = v;
+    }
+    __syncwarp();
+  };
+  for (int it = 0; it < nit; ++it) {
+    const int b = group + it * ngroups;
+    const int rb = it % RB, rph = (it / RB) & 1;
+    tc::mbar_wait(&red_full[rb], rph);
+    while (flushed <= it - 1 - LAG) flush(flushed++);
+    {
+      const unsigned nb = __reduce_or_sync(0xffffffffu, lane < CW ? s_neg[rb * CW + lane] : 0u);
+      if (lane == 0) s_flag[rb] = nb >> 31;      // a negative operand somewhere in this CTA's slice of the sample
+    }
+    const double* r = s_red + rb * 3 * CW;
+    double m0 = lane < CW ? r[lane] : 0.0, m1 = lane < CW ? r[CW + lane] : 0.0, m2 = lane < CW ? r[2 * CW + lane] : 0.0;
+    m0 = warp_sum(m0); m1 = warp_sum(m1); m2 = warp_sum(m2);
+    if (lane == 0) {
+      if (LOG2_UNITS) { m0 *= 0.6931471805599453; m1 *= 0.6931471805599453 * 0.6931471805599453; }
+      unsigned long long* w = ll + ((size_t)b * G + rank) * 2;
+      const unsigned long long w0 = (1ull << 32) | (unsigned)__double2hiint(m0);
+      const unsigned long long w1 = (1ull << 32) | (unsigned)__double2loint(m0);
+      asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(w), "l"(w0), "l"(w1) : "memory");
+      double* mp = mom_part + ((size_t)b * G + rank) * 4;      // for eval_gather_kernel
+      __stcg(mp + 0, m0); __stcg(mp + 1, m1); __stcg(mp + 2, m2);
+    }
+    __syncwarp();
+    // classification lags two samples (RB = 3): collect one sample late, off the critical path.  With a lag of one the
+    // consumers need this sample's scale as soon as their next sweep 1 ends: collect at once.
+    if (RB > 2) { if (it >= 1) collect(it - 1); }
+    else collect(it);
   }
+  if (RB > 2 && nit >= 1) collect(nit - 1);
+  tc::mbar_wait(done_bar, 0);                    // every consumer warp has finished its last sweep 2
+  while (flushed < nit) flush(flushed++);
 }
 
 // util.py:204-205 for one pixel, both quotients as written there
@@ -748,17 +800,37 @@ __device__ __forceinline__ void delta_px_generic(float al, float t, const float*
 // ONEDIV : every threshold is > 1, so of the two quotients al/t and t/al only the one with the larger numerator can
 //          reach a threshold (the other is <= 1 by monotonicity of rounding): one division per pixel, same counts.
 //          Needs both operands non-negative or of mixed sign; a pixel group with a negative pair takes the generic path.
-template <bool FAST, bool ONEDIV, int NT>
-__global__ void __launch_bounds__(kEvThreads, 1) eval_stream_kernel(EvsArgs a) {
-  constexpr int NS = kEvSlots;
+// LEAN   : the default arithmetic.  Algebraically the same quantities with the transcendental work halved:
+//            sweep 1  r = rcp(t + eps);  d = lg2((p + eps) * r)  [= lg2(p + eps) - lg2(t + eps)],  |t - p| * r  (AbsRel shares
+//                     the reciprocal: both epsilons are 1e-6), ~10 instructions per pixel;
+//            sweep 2  with hi = max(p*s, t), lo = min(p*s, t):  max(a/t, t/a) < thr  <=>  hi < thr * lo  for non-negative
+//                     operands (thr <= 1 gives false on both sides; 0/0, x/0 give false on both sides): no division at
+//                     all, ~12 instructions per pixel.
+//            A CTA whose slice holds a negative value (sign bits OR-ed during sweep 1) or whose sample scale is not finite
+//            classifies that slice with the exact two-quotient code, so the semantics of util.py:204-205 hold for any
+//            input; what differs from the exact arithmetic is rounding only (measured: SI-RMSE / AbsRel ~1e-7 relative,
+//            counts a few pixels per million - contract: 1e-5 / 0.01 % of pixels).
+// CW consumer warps, each thread taking VPT float4 of each operand per chunk (CW * VPT = 28: the chunk stays 3584 pixels).
+// The per-sample bookkeeping (barrier waits, cross-lane folds, count atomics) is paid per THREAD, so the lean arithmetic -
+// whose pixel work is down to ~36 instructions - runs 14 fatter warps (two float4 per chunk) instead of 28.
+template <bool FAST, bool ONEDIV, int NT, bool LEAN = false, int NS_ = kEvSlots, int LAG_ = 1, int CW = kEvCW, int VPT = 1>
+__global__ void __launch_bounds__((CW + 2) * 32, 1) eval_stream_kernel(EvsArgs a) {
+  static_assert(CW * VPT * 128 == kEvChunkPx, "chunk size is fixed");
+  constexpr int CT = CW * 32;                      // consumer threads
+  constexpr int NS = NS_;
+  constexpr int LAG = LAG_;                        // sweep 2 runs LAG samples behind sweep 1
+  constexpr int RB = LAG + 1;                      // ring of per-sample reduction / scale buffers
   constexpr int NTS = NT ? NT : DP_MAX_THR;
   constexpr int CH = kEvChunkPx;
   extern __shared__ __align__(128) unsigned char ev_smem[];
   __shared__ uint64_t full[NS][kEvMaxChunks], empty[NS][kEvMaxChunks];
-  __shared__ uint64_t red_full[2], scale_full[2];
-  __shared__ double s_red[2][3 * kEvCW];
-  __shared__ unsigned s_cred[2][NTS * kEvCW];
-  __shared__ float s_scale[2];
+  __shared__ uint64_t red_full[RB], scale_full[RB];
+  __shared__ double s_red[RB][3 * CW];
+  __shared__ float s_scale[RB];
+  __shared__ unsigned s_neg[RB][CW];        // LEAN: OR of the operands' bit patterns per consumer warp (sign bit = negative seen)
+  __shared__ unsigned s_flag[RB];              // ... folded by the exchange warp: 1 = the slice holds a negative operand
+  __shared__ unsigned s_cnt[RB][NTS];          // per-sample delta counts of this CTA (atomics from the consumer warps)
+  __shared__ uint64_t done_bar;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int group = blockIdx.x / a.G, rank = blockIdx.x - group * a.G;
@@ -772,19 +844,34 @@ __global__ void __launch_bounds__(kEvThreads, 1) eval_stream_kernel(EvsArgs a) {
 
   if (tid == 0) {
     for (int s = 0; s < NS; ++s)
-      for (int c = 0; c < kEvMaxChunks; ++c) { tc::mbar_init(&full[s][c], 1); tc::mbar_init(&empty[s][c], kEvCW); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&red_full[i], kEvCW); tc::mbar_init(&scale_full[i], 1); }
+      for (int c = 0; c < kEvMaxChunks; ++c) { tc::mbar_init(&full[s][c], 1); tc::mbar_init(&empty[s][c], CW); }
+    for (int i = 0; i < RB; ++i) { tc::mbar_init(&red_full[i], CW); tc::mbar_init(&scale_full[i], 1); }
+    tc::mbar_init(&done_bar, CW);
     tc::fence_barrier_init();
   }
+  if (tid < RB * NTS) (&s_cnt[0][0])[tid] = 0u;
+  if (tid < RB * CW) (&s_neg[0][0])[tid] = 0u;
   __syncthreads();
 
-  if (warp == kEvCW) {   // ---- producer warp: one lane streams the slices in ----
+  if (warp == CW) {   // ---- producer warp: one lane streams the slices in ----
     if (lane == 0) {
       int slot = 0, ph = 0;
+      const int pfd = a.pf_dist;                   // samples of L2 prefetch distance beyond the slot ring
+      if (pfd > 0 && len > 0)
+        for (int k = 0; k < NS + pfd && k < nit; ++k) {
+          const int bk = group + k * a.ngroups;
+          bulk_prefetch_l2(a.pred + (size_t)bk * n + px0, (uint32_t)len * 4u);
+          bulk_prefetch_l2(a.target + (size_t)bk * n + px0, (uint32_t)len * 4u);
+        }
       for (int it = 0; it < nit; ++it) {
         const int b = group + it * a.ngroups;
         const float* P = a.pred + (size_t)b * n + px0;
         const float* T = a.target + (size_t)b * n + px0;
+        if (pfd > 0 && len > 0 && it + NS + pfd < nit) {
+          const int bk = group + (it + NS + pfd) * a.ngroups;
+          bulk_prefetch_l2(a.pred + (size_t)bk * n + px0, (uint32_t)len * 4u);
+          bulk_prefetch_l2(a.target + (size_t)bk * n + px0, (uint32_t)len * 4u);
+        }
         float* Ps = reinterpret_cast<float*>(ev_smem) + slot * slot_floats;
         float* Ts = Ps + a.per;
         for (int c = 0; c < nch; ++c) {
@@ -800,8 +887,10 @@ __global__ void __launch_bounds__(kEvThreads, 1) eval_stream_kernel(EvsArgs a) {
     return;
   }
 
-  if (warp == kEvCW + 1) {   // ---- exchange warp: per-sample scale through global memory, off the consumers' path ----
-    exchange_loop<FAST>(a.ll, a.mom_part, a.G, a.ngroups, group, rank, nit, n, red_full, scale_full, &s_red[0][0], s_scale);
+  if (warp == CW + 1) {   // ---- exchange warp: per-sample scale through global memory, off the consumers' path ----
+    exchange_loop<FAST || LEAN, RB, LAG, NTS, CW>(a.ll, a.mom_part, a.G, a.ngroups, group, rank, nit, n, red_full, scale_full,
+                                              &s_red[0][0], s_scale, &s_neg[0][0], s_flag, &s_cnt[0][0], &done_bar, a.cnt_part,
+                                              NT ? NT : a.nthr);
     return;
   }
 
@@ -809,22 +898,31 @@ __global__ void __launch_bounds__(kEvThreads, 1) eval_stream_kernel(EvsArgs a) {
   const int len4 = len >> 2;
   const float eps = a.eps;
   int slot1 = 0, ph1 = 0, slot2 = 0;
-  for (int it = 0; it <= nit; ++it) {
+  for (int it = 0; it < nit + LAG; ++it) {
     if (it < nit) {
       // sweep 1 of sample `it`: moments (fp32 over 4 pixels, fp64 beyond) as the slice lands
       const float4* P4 = reinterpret_cast<const float4*>(reinterpret_cast<float*>(ev_smem) + slot1 * slot_floats) + tid;
       const float4* T4 = reinterpret_cast<const float4*>(reinterpret_cast<float*>(ev_smem) + slot1 * slot_floats + a.per) + tid;
       double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+      float f0 = 0.f, f1 = 0.f, f2 = 0.f;          // LEAN: fp32 over this thread's <= 32 pixels, fp64 across lanes / warps / CTAs
+      unsigned negbits = 0;
       for (int c = 0; c < nch; ++c) {
         tc::mbar_wait(&full[slot1][c], ph1);
-        if (c * kEvCT + tid < len4) {   // one float4 of each operand per thread per chunk
-          const float4 p4 = P4[c * kEvCT], t4 = T4[c * kEvCT];
+#pragma unroll
+        for (int v = 0; v < VPT; ++v)
+        if ((c * VPT + v) * CT + tid < len4) {   // VPT float4 of each operand per thread per chunk
+          const float4 p4 = P4[(c * VPT + v) * CT], t4 = T4[(c * VPT + v) * CT];
           const float pv[4] = {p4.x, p4.y, p4.z, p4.w}, tv[4] = {t4.x, t4.y, t4.z, t4.w};
           float s1 = 0.f, s2 = 0.f, ar = 0.f;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float d, e;
-            if (FAST) {   // d in log2 units; scaled by ln 2 once per CTA
+            if (LEAN) {   // one reciprocal serves the log ratio and AbsRel; d in log2 units
+              const float r = rcp_approx(tv[q] + eps);
+              d = lg2_approx((pv[q] + eps) * r);
+              e = fabsf(tv[q] - pv[q]) * r;
+              negbits |= __float_as_uint(pv[q]) | __float_as_uint(tv[q]);
+            } else if (FAST) {   // d in log2 units; scaled by ln 2 once per CTA
               d = lg2_approx(pv[q] + eps) - lg2_approx(tv[q] + eps);
               e = fabsf(tv[q] - pv[q]) * rcp_approx(tv[q] + 1e-6f);
             } else {
@@ -835,34 +933,57 @@ __global__ void __launch_bounds__(kEvThreads, 1) eval_stream_kernel(EvsArgs a) {
             s2 += d * d;
             ar += e;
           }
-          acc0 += s1; acc1 += s2; acc2 += ar;
+          if (LEAN) { f0 += s1; f1 += s2; f2 += ar; }
+          else { acc0 += s1; acc1 += s2; acc2 += ar; }
         }
       }
+      if (LEAN) { acc0 = f0; acc1 = f1; acc2 = f2; }
       acc0 = warp_sum(acc0); acc1 = warp_sum(acc1); acc2 = warp_sum(acc2);
+      if (LEAN) negbits = __reduce_or_sync(0xffffffffu, negbits);
       if (lane == 0) {
-        double* r = s_red[it & 1];
-        r[warp] = acc0; r[kEvCW + warp] = acc1; r[2 * kEvCW + warp] = acc2;
-        tc::mbar_arrive(&red_full[it & 1]);
+        double* r = s_red[it % RB];
+        r[warp] = acc0; r[CW + warp] = acc1; r[2 * CW + warp] = acc2;
+        // published with the moments: the consumers read it after scale_full, which the exchange warp signals only
+        // after every warp's arrival here (release / acquire chain through the two mbarriers)
+        if (LEAN) s_neg[it % RB][warp] = negbits;
+        tc::mbar_arrive(&red_full[it % RB]);
       }
       if (++slot1 == NS) { slot1 = 0; ph1 ^= 1; }
     }
-    if (it >= 1) {
-      // sweep 2 of sample `it - 1`: scale-aligned delta counts from shared memory; finished chunks go back to the producer
-      const int j = it - 1;
+    if (it >= LAG) {
+      // sweep 2 of sample `it - LAG`: scale-aligned delta counts from shared memory; finished chunks go back to the producer
+      const int j = it - LAG;
       const int b = group + j * a.ngroups;
-      tc::mbar_wait(&scale_full[j & 1], (j >> 1) & 1);
-      const float s = s_scale[j & 1];
+      tc::mbar_wait(&scale_full[j % RB], (j / RB) & 1);
+      const float s = s_scale[j % RB];
       const float4* P4 = reinterpret_cast<const float4*>(reinterpret_cast<float*>(ev_smem) + slot2 * slot_floats) + tid;
       const float4* T4 = reinterpret_cast<const float4*>(reinterpret_cast<float*>(ev_smem) + slot2 * slot_floats + a.per) + tid;
       unsigned cnt[NTS];
 #pragma unroll
       for (int k = 0; k < NTS; ++k) cnt[k] = 0;
+      // LEAN: a negative operand in this CTA's slice, or a NaN / inf scale -> exact two-quotient classification
+      const bool lean_ok = LEAN && s_flag[j % RB] == 0u && (s - s == 0.f);
       for (int c = 0; c < nch; ++c) {
-        if (c * kEvCT + tid < len4) {
-          const float4 p4 = P4[c * kEvCT], t4 = T4[c * kEvCT];
+#pragma unroll
+        for (int v = 0; v < VPT; ++v)
+        if ((c * VPT + v) * CT + tid < len4) {
+          const float4 p4 = P4[(c * VPT + v) * CT], t4 = T4[(c * VPT + v) * CT];
           const float al[4] = {p4.x * s, p4.y * s, p4.z * s, p4.w * s}, tv[4] = {t4.x, t4.y, t4.z, t4.w};
           bool generic = !ONEDIV;
-          if (ONEDIV) {
+          if (LEAN && lean_ok) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              // hi < thr * lo  <=>  fma(-thr, lo, hi) < 0: one FFMA, and the count is the sign bit (a NaN from
+              // inf - inf is the canonical positive NaN: counted as "not below", like the reference's comparison)
+              const float hi = fmaxf(al[q], tv[q]), lo = fminf(al[q], tv[q]);
+#pragma unroll
+              for (int k = 0; k < NTS; ++k)
+                if (NT || k < a.nthr) cnt[k] += __float_as_uint(fmaf(-a.thr[k], lo, hi)) >> 31;
+            }
+            generic = false;
+          } else if (LEAN) {
+            generic = true;
+          } else if (ONEDIV) {
             const float mx = fminf(fminf(fmaxf(al[0], tv[0]), fmaxf(al[1], tv[1])),
                                    fminf(fmaxf(al[2], tv[2]), fmaxf(al[3], tv[3])));
             generic = mx < 0.f;   // some pair is negative in both operands
@@ -870,7 +991,7 @@ __global__ void __launch_bounds__(kEvThreads, 1) eval_stream_kernel(EvsArgs a) {
           if (generic) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) delta_px_generic<NTS, NT == 0>(al[q], tv[q], a.thr, a.nthr, cnt);
-          } else {
+          } else if (!LEAN) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const bool sel = al[q] > tv[q];
@@ -885,21 +1006,17 @@ __global__ void __launch_bounds__(kEvThreads, 1) eval_stream_kernel(EvsArgs a) {
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&empty[slot2][c]);
       }
-      unsigned* cr = s_cred[j & 1];
 #pragma unroll
       for (int k = 0; k < NTS; ++k) {
         const unsigned v = __reduce_add_sync(0xffffffffu, cnt[k]);
-        if (lane == 0) cr[k * kEvCW + warp] = v;
+        if (lane == 0 && (NT || k < a.nthr)) atomicAdd(&s_cnt[j % RB][k], v);    // flushed by the exchange warp
       }
-      bar_consumers();   // also orders the reuse of s_cred[j & 1] two samples later
-      if (tid < NTS && (NT || tid < a.nthr)) {
-        unsigned long long tot = 0;
-        for (int w = 0; w < kEvCW; ++w) tot += cr[tid * kEvCW + w];
-        a.cnt_part[((size_t)b * a.G + rank) * DP_MAX_THR + tid] = tot;
-      }
+      (void)b;
       if (++slot2 == NS) slot2 = 0;
     }
   }
+  __syncwarp();
+  if (lane == 0) tc::mbar_arrive(&done_bar);     // this warp's counts are all in s_cnt
 }
 
 // partials of the streaming kernels -> per-sample moments / counts and the per-sample terms of evaluation.py:157-166.
@@ -975,10 +1092,10 @@ struct EvalPlan {
 // Pure function of the shape and of the device's shared memory per SM / SM count, shared by the workspace query and
 // the launch: one CTA per SM, kEvSlots slices resident per CTA, and the CTAs-per-sample count G that wastes the fewest
 // thread slots (slices that are whole chunks) and SMs (groups * G close to the SM count).
-inline EvalPlan eval_plan_for(long long n, int B, int smem_sm, int sms, int nthr) {
+inline EvalPlan eval_plan_for(long long n, int B, int smem_sm, int sms, int nthr, int slots = kEvSlots) {
   EvalPlan p{};
   if (n % 4 != 0 || n <= 0 || B <= 0 || sms <= 0) return p;
-  const long long budget = ((long long)smem_sm - 1024 - eval_static_allowance(nthr)) / kEvSlots;   // bytes per slot
+  const long long budget = ((long long)smem_sm - 1024 - eval_static_allowance(nthr)) / slots;   // bytes per slot
   if (budget < 4096) return p;
   const long long gmin = (n * 8 + budget - 1) / budget;
   double best = -1.0;
@@ -996,17 +1113,17 @@ inline EvalPlan eval_plan_for(long long n, int B, int smem_sm, int sms, int nthr
     }
   }
   if (best < 0.0) return p;
-  p.dyn = (size_t)p.per * 8 * kEvSlots;
+  p.dyn = (size_t)p.per * 8 * slots;
   p.ok = true;
   return p;
 }
 
-inline EvalPlan eval_plan(long long n, int B, int nthr) {
+inline EvalPlan eval_plan(long long n, int B, int nthr, int slots = kEvSlots) {
   int smem_sm = 0, sms = 0, dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return EvalPlan{};
   if (cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) != cudaSuccess) return EvalPlan{};
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return EvalPlan{};
-  return eval_plan_for(n, B, smem_sm, sms, nthr);
+  return eval_plan_for(n, B, smem_sm, sms, nthr, slots);
 }
 
 inline size_t eval_ws_ll_bytes(int B, int G) { return (((size_t)B * G * 2 * sizeof(unsigned long long)) + 255) & ~(size_t)255; }
@@ -1160,10 +1277,11 @@ int dp_eval_metrics_plan(long long pixels, int B, int nthr, int smem_per_sm, int
 size_t dp_eval_metrics_workspace(int B, int H, int W) {
   if (B <= 0 || H <= 0 || W <= 0) return 256;
   size_t need = 256;
-  for (int nthr = 1; nthr <= 2; ++nthr) {      // the two decompositions (compile-time / run-time threshold count)
-    const EvalPlan p = eval_plan((long long)H * W, B, nthr);
-    if (p.ok && eval_ws_bytes(B, p) > need) need = eval_ws_bytes(B, p);
-  }
+  for (int nthr = 1; nthr <= 2; ++nthr)        // the two decompositions (compile-time / run-time threshold count) ...
+    for (int slots : {kEvSlots, kEvSlotsLean}) {   // ... of the two slot counts (exact / lean arithmetic)
+      const EvalPlan p = eval_plan((long long)H * W, B, nthr, slots);
+      if (p.ok && eval_ws_bytes(B, p) > need) need = eval_ws_bytes(B, p);
+    }
   return need;
 }
 
@@ -1179,7 +1297,10 @@ int dp_eval_metrics(const float* pred, const float* target, int B, int H, int W,
   const long long n = (long long)H * W;
   const bool vec = (n % 4 == 0) && aligned16(pred) && aligned16(target);
 
-  const EvalPlan plan = vec ? eval_plan(n, B, nthr) : EvalPlan{};
+  const bool lean = fast_math == 2 && eps == 1e-6f;
+  EvalPlan plan = vec ? eval_plan(n, B, nthr, lean ? kEvSlotsLean : kEvSlots) : EvalPlan{};
+  bool lean_plan = lean && plan.ok;
+  if (vec && lean && !plan.ok) plan = eval_plan(n, B, nthr);      // shapes too small / odd for four slots: MUFU path
   if (plan.ok) {
     DP_CHECK_ARG(workspace, "dp_eval_metrics: null workspace");
     if (workspace_bytes < eval_ws_bytes(B, plan))
@@ -1192,6 +1313,7 @@ int dp_eval_metrics(const float* pred, const float* target, int B, int H, int W,
     EvsArgs a;
     a.pred = pred; a.target = target; a.B = B; a.nthr = nthr; a.G = plan.G; a.ngroups = plan.ngroups; a.per = plan.per;
     a.n = n; a.eps = eps; a.ll = ll; a.mom_part = mom_part; a.cnt_part = cnt_part;
+    a.pf_dist = kEvPrefetch;
     bool onediv = true;
     for (int k = 0; k < DP_MAX_THR; ++k) {
       a.thr[k] = k < nthr ? thresholds[k] : 0.f;
@@ -1200,21 +1322,29 @@ int dp_eval_metrics(const float* pred, const float* target, int B, int H, int W,
 #define DP_EVS_PICK(F, O)                                                                       \
   (nthr == 3 ? (const void*)eval_stream_kernel<F, O, 3>                                         \
              : (nthr == 1 ? (const void*)eval_stream_kernel<F, O, 1> : (const void*)eval_stream_kernel<F, O, 0>))
+#define DP_EVS_LEAN                                                                                                  \
+  (nthr == 3 ? (const void*)eval_stream_kernel<false, false, 3, true, kEvSlotsLean, kEvLagLean, kEvCWLean, kEvVPTLean>       \
+             : (nthr == 1 ? (const void*)eval_stream_kernel<false, false, 1, true, kEvSlotsLean, kEvLagLean, kEvCWLean, kEvVPTLean> \
+                          : (const void*)eval_stream_kernel<false, false, 0, true, kEvSlotsLean, kEvLagLean, kEvCWLean, kEvVPTLean>))
     const void* fn;
-    if (fast_math) fn = onediv ? DP_EVS_PICK(true, true) : DP_EVS_PICK(true, false);
+    // mode 2 shares one reciprocal between the SI term (eps) and AbsRel (1e-6, util.py:218): needs eps == 1e-6
+    if (lean_plan) fn = DP_EVS_LEAN;
+    else if (fast_math) fn = onediv ? DP_EVS_PICK(true, true) : DP_EVS_PICK(true, false);
     else fn = onediv ? DP_EVS_PICK(false, true) : DP_EVS_PICK(false, false);
+#undef DP_EVS_LEAN
 #undef DP_EVS_PICK
     void* kargs[1] = {&a};
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.dyn);
     int resident = 0;
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, fn, kEvThreads, plan.dyn);
+    const int ev_threads = lean_plan ? (kEvCWLean + 2) * 32 : kEvThreads;
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, fn, ev_threads, plan.dyn);
     if (e != cudaSuccess)
       return dp_set_error(DP_ERR_CUDA, "dp_eval_metrics: launch setup failed: %s", cudaGetErrorString(e));
     if (resident < 1)
       return dp_set_error(DP_ERR_UNSUPPORTED, "dp_eval_metrics: a CTA with %zu B of shared memory is not resident", plan.dyn);
     e = cudaMemsetAsync(ll, 0, (size_t)B * plan.G * 2 * sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return dp_set_error(DP_ERR_CUDA, "dp_eval_metrics: memset failed: %s", cudaGetErrorString(e));
-    e = cudaLaunchCooperativeKernel(fn, dim3(plan.ngroups * plan.G), dim3(kEvThreads), kargs, plan.dyn, stream);
+    e = cudaLaunchCooperativeKernel(fn, dim3(plan.ngroups * plan.G), dim3(ev_threads), kargs, plan.dyn, stream);
     dp_count_launch(1);
     if (e != cudaSuccess)
       return dp_set_error(DP_ERR_CUDA, "eval_stream_kernel launch failed: %s", cudaGetErrorString(e));

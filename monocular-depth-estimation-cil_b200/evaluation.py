@@ -16,13 +16,16 @@ BASE_THRES = 1.05        # evaluation.py:27
 N_DELTA = 3              # evaluation.py:28
 
 
-def evaluate_batches(model, batches, device, n_samples=None, base_thres=BASE_THRES, n_delta=N_DELTA, fast_math=False):
+def evaluate_batches(model, batches, device, n_samples=None, base_thres=BASE_THRES, n_delta=N_DELTA, fast_math=None,
+                     local_shard=False):
     """`batches` yields (rgb, depth_gt, ...) like the reference's DataLoader (evaluation.py:143).  Returns a dict with the
     reference's three printed quantities: 'si_rmse', 'abs_rel', 'delta' (list of n_delta) and 'samples'.
 
     Every rank walks the whole iterable and keeps the batches whose index is congruent to its rank (shard by batch);
     n_samples clips the total exactly as evaluation.py:169-177 does (a partially used last batch is weighted by the
-    number of samples taken from it, with the batch-level metric values - the reference's arithmetic)."""
+    number of samples taken from it, with the batch-level metric values - the reference's arithmetic).
+    local_shard=True: `batches` already holds only this rank's samples (a DistributedSampler-style loader): nothing is
+    skipped, and n_samples clips the local stream."""
     world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
     rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
     thr = [base_thres ** j for j in range(1, n_delta + 1)]
@@ -38,7 +41,7 @@ def evaluate_batches(model, batches, device, n_samples=None, base_thres=BASE_THR
             seen += b
             if take == 0:
                 break
-            if idx % world != rank:
+            if not local_shard and idx % world != rank:
                 continue
             pred = model(rgb.to(device, non_blocking=True))
             if pred.dim() == 3:

@@ -141,6 +141,16 @@ class GraphedTrainStep:
         return {"total": h[L.L_TOTAL], "si_loss": h[L.L_SI], "silog_loss": h[L.L_SILOG], "grad_loss": h[L.L_GRAD],
                 "edge_loss": h[L.L_EDGE]}
 
+    def close(self):
+        """release the captured graph (and with it the NCCL collectives it recorded).  Call before
+        torch.distributed.destroy_process_group(): tearing the process group down while a graph that captured its
+        collectives is alive hung at interpreter exit (round 1, N = 2)."""
+        torch.cuda.synchronize()
+        if self.graph is not None:
+            self.graph.reset()
+            self.graph = None
+        self.out = None
+
     def finish(self):
         """kept for round-1 callers; no longer required: every replay invalidates the eager weight-pack cache."""
         ops.PACKS.invalidate()

@@ -270,23 +270,29 @@ def tokens_to_nhwc(tok, ph, pw):
 # --------------------------------------------------------------------------------------------------
 # tensor-core convolution (3x3 s1 p1 / 1x1)
 # --------------------------------------------------------------------------------------------------
-def _conv_tc_launch(x, wp, Cout, KS, bias, res, res2, relu, out, out2, relu2, stats):
+def _conv_tc_launch(x, wp, Cout, KS, bias, res, res2, relu, out, out2, relu2, stats, fuse=None):
+    """the one place a tcgen05 forward / data-gradient convolution is launched (bench.py times this call);
+    fuse: an _lib.ConvFuse (BatchNorm prologue / backward-mask epilogue) or None"""
+    import ctypes
     B, H, W, Cin = x.shape
-    L.check(L.lib().dp_conv2d_tc(
+    L.check(L.lib().dp_conv2d_tc_fused(
         L.ptr(x), _ld(x), B, H, W, Cin, L.ptr(wp), wp.shape[2], Cout, KS, L.ptr(bias),
         L.ptr(res), _ld(res) if res is not None else 0, L.ptr(res2), _ld(res2) if res2 is not None else 0,
         int(relu), L.ptr(out), _ld(out) if out is not None else 0, L.ptr(out2), _ld(out2) if out2 is not None else 0,
-        int(relu2), L.ptr(stats), L.stream()))
+        int(relu2), L.ptr(stats), ctypes.byref(fuse) if fuse is not None else None, L.stream()))
 
 
-def _wgrad_tc(x, g, Cin, Cout, KS):
+def _wgrad_tc(x, g, Cin, Cout, KS, pre=None):
+    """the one place a tcgen05 weight gradient is launched (bench.py times this call); pre = (scale_shift, act): x is
+    the pre-BatchNorm tensor and the activated operand is produced in the kernel's operand path"""
     B, H, W, _ = x.shape
     lib = L.lib()
     nb = lib.dp_conv2d_wgrad_tc_workspace(B, H, W, Cin, Cout, KS)
     ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
     dw = torch.empty(Cout, Cin, KS, KS, dtype=torch.float32, device=x.device)
-    L.check(lib.dp_conv2d_wgrad_tc(L.ptr(x), _ld(x), L.ptr(g), _ld(g), B, H, W, Cin, Cout, KS, L.ptr(dw), 0, L.ptr(ws),
-                                   nb, L.stream()))
+    L.check(lib.dp_conv2d_wgrad_tc_fused(L.ptr(x), _ld(x), L.ptr(g), _ld(g), B, H, W, Cin, Cout, KS, L.ptr(dw), 0, L.ptr(ws),
+                                         nb, L.ptr(pre[0]) if pre is not None else None,
+                                         int(pre[1]) if pre is not None else 0, L.stream()))
     return dw
 
 
@@ -809,9 +815,6 @@ def bn_act(bn, c, stats=None, relu=True, res=None, bn2=None, c2=None, stats2=Non
 # --------------------------------------------------------------------------------------------------
 # ResidualBlock as ONE autograd node: BatchNorm folded into the neighbouring convolutions
 # --------------------------------------------------------------------------------------------------
-import ctypes as _ct
-
-
 def _conv_raw(x, wp, Cout, KS, res=None, stats=False, pre=None, mask=None):
     """plain launch of the tcgen05 convolution (no autograd): returns (out, stats partials | None).
     pre = (scale_shift [2][Cin], act): BatchNorm + activation of the input fused into the operand path;
@@ -827,22 +830,12 @@ def _conv_raw(x, wp, Cout, KS, res=None, stats=False, pre=None, mask=None):
         fuse = L.ConvFuse(L.ptr(pre[0]) if pre is not None else None, int(pre[1]) if pre is not None else 0,
                           L.ptr(mask[0]) if mask is not None else None, _ld(mask[0]) if mask is not None else 0,
                           L.ptr(mask[1]) if mask is not None else None, int(mask[2]) if mask is not None else 0)
-    L.check(lib.dp_conv2d_tc_fused(L.ptr(x), _ld(x), B, H, W, Cin, L.ptr(wp), wp.shape[2], Cout, KS, None,
-                                   L.ptr(res), _ld(res) if res is not None else 0, None, 0, 0, L.ptr(out), Cout, None, 0, 0,
-                                   L.ptr(st), _ct.byref(fuse) if fuse is not None else None, L.stream()))
+    _conv_tc_launch(x, wp, Cout, KS, None, res, None, False, out, None, False, st, fuse)
     return out, st
 
 
 def _wgrad_raw(x, g, Cin, Cout, KS, pre=None):
-    B, H, W, _ = x.shape
-    lib = L.lib()
-    nb = lib.dp_conv2d_wgrad_tc_workspace(B, H, W, Cin, Cout, KS)
-    ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
-    dw = torch.empty(Cout, Cin, KS, KS, dtype=torch.float32, device=x.device)
-    L.check(lib.dp_conv2d_wgrad_tc_fused(L.ptr(x), _ld(x), L.ptr(g), _ld(g), B, H, W, Cin, Cout, KS, L.ptr(dw), 0, L.ptr(ws),
-                                         nb, L.ptr(pre[0]) if pre is not None else None, int(pre[1]) if pre is not None else 0,
-                                         L.stream()))
-    return dw
+    return _wgrad_tc(x, g, Cin, Cout, KS, pre)
 
 
 def _bn_reduce(cx, gy, mask, mss, act):

@@ -146,7 +146,7 @@ def test_fused_eval_counts_match_two_pass_counts(pkg, B, H, W):
     p = (t.cpu() * torch.exp(0.1 * torch.randn(B, 1, H, W, generator=g)) * 1.3).cuda()
     p[:, :, 3:9, 5:17] = 0.0
     thr = [1.05, 1.05 ** 2, 1.05 ** 3]
-    out = pkg.evaluation_metrics(p, t, thresholds=thr).double().cpu()
+    out = pkg.evaluation_metrics(p, t, thresholds=thr, fast_math=False).double().cpu()
     cnt = pkg.delta_counts(p, t, thr, aligned=True).cpu()
     n = H * W
     want = (cnt.double() / n).float().double().mean(0)
@@ -174,7 +174,7 @@ def test_streaming_eval_counts_exact(pkg, B, H, W, thr):
     t[:, :, 20:23, 40:47] = 0.0
     p[0, :, 21, 41] = 0.0           # 0 / 0
     p, t = p.cuda(), t.cuda()
-    out = pkg.evaluation_metrics(p, t, thresholds=thr).double().cpu()
+    out = pkg.evaluation_metrics(p, t, thresholds=thr, fast_math=False).double().cpu()
     cnt = pkg.delta_counts(p, t, thr, aligned=True).cpu()
     n = H * W
     want = (cnt.double() / n).float().double().mean(0)
@@ -185,8 +185,12 @@ def test_streaming_eval_counts_exact(pkg, B, H, W, thr):
     assert abs(fast[0] - out[0]) <= 1e-5 * abs(out[0])
     assert float((fast[2:] - out[2:]).abs().max()) <= 1e-4
     # same call again: the arrival counters are reset by the entry point, results are deterministic
-    again = pkg.evaluation_metrics(p, t, thresholds=thr).double().cpu()
+    again = pkg.evaluation_metrics(p, t, thresholds=thr, fast_math=False).double().cpu()
     assert torch.equal(again, out)
+    # the default (lean) arithmetic on the same inputs, zeros and 0/0 included: inside the contract
+    lean = pkg.evaluation_metrics(p, t, thresholds=thr).double().cpu()
+    assert abs(lean[0] - out[0]) <= 1e-5 * abs(out[0]) and abs(lean[1] - out[1]) <= 1e-5 * abs(out[1])
+    assert float((lean[2:] - out[2:]).abs().max()) <= 1e-4
 
 
 def test_fused_eval_fast_math_within_contract(pkg):
@@ -198,7 +202,7 @@ def test_fused_eval_fast_math_within_contract(pkg):
     p = (t.cpu() * torch.exp(0.1 * torch.randn(B, 1, H, W, generator=g)) * 1.3).cuda()
     p[:, :, 100:140, 200:300] = 0.0
     thr = [1.05, 1.05 ** 2, 1.05 ** 3]
-    exact = pkg.evaluation_metrics(p, t, thresholds=thr).double().cpu()
+    exact = pkg.evaluation_metrics(p, t, thresholds=thr, fast_math=False).double().cpu()
     fast = pkg.evaluation_metrics(p, t, thresholds=thr, fast_math=True).double().cpu()
     assert abs(fast[0] - exact[0]) <= 1e-5 * abs(exact[0])
     assert abs(fast[1] - exact[1]) <= 1e-5 * abs(exact[1])
@@ -257,3 +261,38 @@ def test_evaluate_model_matches_reference_golden(pkg, golden_loss):
         assert abs(got[k] - ref[k]) <= 1e-5 * abs(ref[k]), (k, got[k], ref[k])
     for k in ("Delta1", "Delta2", "Delta3"):
         assert abs(got[k] - ref[k]) <= 1e-4, (k, got[k], ref[k])
+
+
+@pytest.mark.parametrize("case", ["positive", "zeros", "negative", "nan", "thr_le_1"])
+def test_default_eval_arithmetic_within_contract(pkg, case):
+    """The default (lean) arithmetic of evaluation_metrics - one shared reciprocal + one lg2 per pixel, division-free
+    threshold test - against the exact IEEE path (the reference's arithmetic) at the evaluation size: SI-RMSE / AbsRel
+    within 1e-5 relative, delta fractions within 0.01 % of pixels (the north-star contract), for ordinary depth maps, exact
+    zeros in either operand (x/0, 0/0), negative values (the slice falls back to the two-quotient code: sign semantics of
+    util.py:204-205), NaNs (the sample's scale is NaN: every count 0, SI-RMSE NaN, as in the reference) and thresholds
+    <= 1 (never reached)."""
+    B, H, W = 6, 448, 576
+    g = torch.Generator().manual_seed(321)
+    t = torch.rand(B, 1, H, W, generator=g) * 9.9 + 0.1
+    p = t * torch.exp(0.1 * torch.randn(B, 1, H, W, generator=g)) * 1.3
+    thr = [1.05, 1.05 ** 2, 1.05 ** 3]
+    if case == "zeros":
+        p[:, :, 50:90, 100:300] = 0.0
+        t[:, :, 200:230, 40:470] = 0.0
+        p[:, :, 210:215, 50:60] = 0.0
+    elif case == "negative":
+        p[1, :, 17, 33] = -0.5          # log of a negative number: that sample's metrics are NaN in the reference too
+        t[3, :, 100:110, 200:260] = -1e-7   # inside (-eps, 0): finite logs, negative quotients
+    elif case == "nan":
+        p[2, :, 5, 5] = float("nan")
+    elif case == "thr_le_1":
+        thr = [0.9, 1.0, 1.2]
+    p, t = p.cuda(), t.cuda()
+    exact = pkg.evaluation_metrics(p, t, thresholds=thr, fast_math=False).double().cpu()
+    lean = pkg.evaluation_metrics(p, t, thresholds=thr).double().cpu()
+    for i in range(2):
+        if torch.isnan(exact[i]):
+            assert torch.isnan(lean[i]), (case, i, lean, exact)
+        else:
+            assert abs(lean[i] - exact[i]) <= 1e-5 * abs(exact[i]), (case, i, lean, exact)
+    assert float((lean[2:] - exact[2:]).abs().max()) <= 1e-4, (case, lean, exact)

@@ -26,9 +26,9 @@ def t(fn, reps=10):
 ps = util._Pass(pp, tt, None, L.F_SI | L.F_ABSREL, 1e-6)
 print("moments pass      ms", t(lambda: util._Pass(pp, tt, None, L.F_SI | L.F_ABSREL, 1e-6)))
 print("delta counts pass ms", t(lambda: ps.counts([1.05, 1.05 ** 2, 1.05 ** 3], aligned=True)))
-print("evaluation_metrics ms", t(lambda: depth_b200.evaluation_metrics(pp, tt)))
-print("Gpx/s", EB * H * W / (t(lambda: depth_b200.evaluation_metrics(pp, tt)) / 1e3) / 1e9)
-print("copy (read+write 8B/px) ms", t(lambda: tt.copy_(pp)))
-print("fast_math Gpx/s", EB * H * W / (t(lambda: depth_b200.evaluation_metrics(pp, tt, fast_math=True)) / 1e3) / 1e9)
-print("exact out", depth_b200.evaluation_metrics(pp, tt).tolist())
-print("fast  out", depth_b200.evaluation_metrics(pp, tt, fast_math=True).tolist())
+px = EB * H * W
+for name, fm in (("default (lean)", None), ("exact IEEE", False), ("MUFU", True)):
+    ms = t(lambda: depth_b200.evaluation_metrics(pp, tt, fast_math=fm))
+    print(f"evaluation_metrics {name:15s} {ms:.4f} ms  {px / ms / 1e6:7.1f} Gpx/s  {8 * px / ms / 1e6:7.1f} GB/s  out {[round(v, 7) for v in depth_b200.evaluation_metrics(pp, tt, fast_math=fm).tolist()]}")
+scratch = torch.empty_like(tt)
+print("copy (read+write 8B/px) ms", t(lambda: scratch.copy_(pp)))
