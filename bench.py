@@ -355,7 +355,7 @@ def run_ours(a):
     B = a.batch
     build = depth_b200._lib.build_id()
     if os.environ.get("DP_NO_BN_FUSION"):
-        ops.Fusion.prologue = ops.Fusion.backward = False
+        ops.Fusion.prologue, ops.Fusion.backward = False, False
     model = build_model(dev, fused_encoder=not a.torch_encoder)
     cfg = fx.loss_config()                                # config.yaml:34-42 -> 1 / 0 / 0 / 0
     opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=1e-4, fused=True,
@@ -447,7 +447,9 @@ def run_ours(a):
         s.record(); r = orig_conv(x, wp, Cout, KS, *rest, **kw); e.record()
         Bq, Hq, Wq, Cin = x.shape
         fuse = rest[8] if len(rest) > 8 else kw.get("fuse")
-        tag = "conv" if fuse is None else ("conv+bn_prologue" if fuse.pre_scale_shift else "conv+bn_backward")
+        has_res = len(rest) > 1 and (rest[1] is not None or rest[2] is not None)
+        tag = ("conv+residual" if has_res else "conv") if fuse is None else \
+              ("conv+bn_prologue" if fuse.pre_scale_shift else "conv+bn_backward")
         rec.append((tag, (Hq, Wq, Cin, Cout, KS), 2.0 * Bq * Hq * Wq * Cin * Cout * KS * KS, s, e))
         return r
 

@@ -100,6 +100,7 @@ struct ConvArgs {
   // fused BatchNorm-backward epilogue: `resb` is the pre-activation tensor c of the BN + activation whose output
   // gradient this launch produces; out = acc * [0 < c*aux_ss[n] + aux_ss[Cout+n] < aux_hi]; stats = (sum out, sum out*c)
   const float* aux_ss; float aux_hi; int aux_mode;
+  int epi_pipe;                   // software-pipeline a single epilogue operand one tile ahead (epilogue_tma)
   unsigned long long* dbg;
 };
 
@@ -186,17 +187,37 @@ __device__ __forceinline__ void aux_mask8(float* v8, const uint4& cw, const floa
 #pragma unroll
   for (int k = 0; k < 4; ++k) { cx[2 * k] = bf16_lo(w[k]); cx[2 * k + 1] = bf16_hi(w[k]); }
   if (col < Cout) {                               // Cout is a multiple of 8
-    const float4 a0 = *reinterpret_cast<const float4*>(s_aux + col), a1 = *reinterpret_cast<const float4*>(s_aux + col + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(s_aux + Cout + col);
-    const float4 b1 = *reinterpret_cast<const float4*>(s_aux + Cout + col + 4);
-    const float sc[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float sh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    // explicit shared-space loads: through the generic pointer ptxas emitted LD.E (generic) and the epilogue sat on
+    // the long scoreboard (31 % of its stall samples)
+    float sc[8], sh[8];
+    const uint32_t ta = tc::smem_u32(s_aux) + (uint32_t)col * 4u, tb = ta + (uint32_t)Cout * 4u;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc[0]), "=f"(sc[1]), "=f"(sc[2]), "=f"(sc[3]) : "r"(ta));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc[4]), "=f"(sc[5]), "=f"(sc[6]), "=f"(sc[7]) : "r"(ta + 16u));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sh[0]), "=f"(sh[1]), "=f"(sh[2]), "=f"(sh[3]) : "r"(tb));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sh[4]), "=f"(sh[5]), "=f"(sh[6]), "=f"(sh[7]) : "r"(tb + 16u));
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float m = fmaf(cx[e], sc[e], sh[e]);
       v8[e] = (m > 0.f && m < hi) ? v8[e] : 0.f;
     }
   }
+}
+
+// The epilogue's residual / BatchNorm-backward operands are read per tile straight from global memory by the thread
+// that owns the pixel.  Issued at the top of a tile they would expose a full DRAM round trip on the epilogue's critical
+// path every tile (measured: 64->64 @448x576 0.60 -> 1.32 ms with one operand), so the lines of the tile kPfTiles ahead are
+// pulled into L2 first: the loads at the top of a tile then cost an L2 hit.
+constexpr int kPfTiles = 2;
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<uint64_t>(p)));
+}
+__device__ __forceinline__ void prefetch_tile_operands(const ConvArgs& a, const TileIter& tp, int py, int px, int col0) {
+  const int y = tp.ty * a.th + py, x = tp.tx * a.tw + px;
+  const int oy = y * a.osy + a.oay, ox = x * a.osx + a.oax;
+  if (!((y < a.H) && (x < a.W) && (oy < a.Ho) && (ox < a.Wo)) || col0 >= a.Cout) return;
+  const long long pix = ((long long)tp.n * a.Ho + oy) * a.Wo + ox;
+  if (a.res) prefetch_l2(a.res + pix * a.res_ld + col0);
+  if (a.resb) prefetch_l2(a.resb + pix * a.resb_ld + col0);
 }
 
 // ---- epilogue A: BN = 2*CW in {16, 32, 64}.  Each of the eight warps owns 32 pixels x CW columns of the tile: one
@@ -230,24 +251,63 @@ __device__ __forceinline__ void epilogue_tma(const Maps& tm, const ConvArgs& a, 
   int it = 0, ring = 0;
   TileIter ti;
   ti.init(a, blockIdx.x);
-  for (long long item = blockIdx.x; item < a.total_items; item += gridDim.x, ++it, ti.step(a)) {
+  // Epilogue operands (residuals, or the pre-activation tensor of the BatchNorm-backward mode) are read by the thread
+  // that owns the pixel.  Loaded at the top of their own tile they put a full memory round trip on the epilogue's
+  // critical path every tile (ncu: 23 % of all stall samples on the first use of the loaded value, 64->64 @448x576
+  // 0.60 -> 0.95 ms).  With a single operand - the common case - the loads are software-pipelined one tile ahead in the
+  // register set the second operand would have used: `r2` receives tile i+1 while `r1` (tile i) is consumed.
+  const bool single = a.epi_pipe && ((a.res != nullptr) != (a.resb != nullptr));
+  const bf16* op = a.res ? a.res : a.resb;
+  const long long op_ld = a.res ? a.res_ld : a.resb_ld;
+  uint4 r1[CW / 8], r2[CW / 8];
+  auto load_operand = [&](const TileIter& t, uint4 (&dst)[CW / 8]) {
+    const int yy = t.ty * a.th + py, xx = t.tx * a.tw + px;
+    const int oyy = yy * a.osy + a.oay, oxx = xx * a.osx + a.oax;
+    const bool ok = (yy < a.H) && (xx < a.W) && (oyy < a.Ho) && (oxx < a.Wo);
+    const uint4* rp = reinterpret_cast<const uint4*>(op + (((long long)t.n * a.Ho + oyy) * a.Wo + oxx) * op_ld + col0);
+#pragma unroll
+    for (int j = 0; j < CW / 8; ++j) dst[j] = (ok && col0 + j * 8 < a.Cout) ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
+  };
+  TileIter tn = ti;                                          // one tile ahead of ti
+  if (single && (long long)blockIdx.x < a.total_items) load_operand(tn, r2);
+  tn.step(a);
+  // operands that are not pipelined through registers (two operands, or plain residuals - for which the register
+  // rotation measured no gain) are pulled into L2 kPfTiles tiles ahead instead (64->64 + residual: 1.12 -> 0.95 ms)
+  const bool pf = !single && (a.res || a.resb);
+  TileIter tp = ti;
+  if (pf) {
+    for (int k = 0; k < kPfTiles; ++k) {
+      if (blockIdx.x + (long long)k * gridDim.x < a.total_items) prefetch_tile_operands(a, tp, py, px, col0);
+      tp.step(a);
+    }
+  }
+  for (long long item = blockIdx.x; item < a.total_items; item += gridDim.x, ++it, ti.step(a), tn.step(a)) {
+    if (pf) {
+      if (item + (long long)kPfTiles * gridDim.x < a.total_items) prefetch_tile_operands(a, tp, py, px, col0);
+      tp.step(a);
+    }
     const int n = ti.n, y0 = ti.ty * a.th, x0 = ti.tx * a.tw;
     const int buf = it & (a.nbuf - 1);
     const int y = y0 + py, x = x0 + px;
     const int oy = y * a.osy + a.oay, ox = x * a.osx + a.oax;
     const bool valid = (y < a.H) && (x < a.W) && (oy < a.Ho) && (ox < a.Wo);
     const long long pix = ((long long)n * a.Ho + oy) * a.Wo + ox;
-    // residual operands do not depend on the accumulator: fetch them before waiting for the MMAs
-    uint4 r1[CW / 8], r2[CW / 8];
-    if (a.res) {
-      const uint4* rp = reinterpret_cast<const uint4*>(a.res + pix * a.res_ld + col0);
+    if (single) {
 #pragma unroll
-      for (int j = 0; j < CW / 8; ++j) r1[j] = (valid && col0 + j * 8 < a.Cout) ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
-    }
-    if (a.resb) {
-      const uint4* rp = reinterpret_cast<const uint4*>(a.resb + pix * a.resb_ld + col0);
+      for (int j = 0; j < CW / 8; ++j) r1[j] = r2[j];        // this tile's operand, requested one tile ago
+      if (item + gridDim.x < a.total_items) load_operand(tn, r2);
+    } else {
+      // two operands: fetched here, before waiting for the MMAs (they do not depend on the accumulator)
+      if (a.res) {
+        const uint4* rp = reinterpret_cast<const uint4*>(a.res + pix * a.res_ld + col0);
 #pragma unroll
-      for (int j = 0; j < CW / 8; ++j) r2[j] = (valid && col0 + j * 8 < a.Cout) ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
+        for (int j = 0; j < CW / 8; ++j) r1[j] = (valid && col0 + j * 8 < a.Cout) ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
+      }
+      if (a.resb) {
+        const uint4* rp = reinterpret_cast<const uint4*>(a.resb + pix * a.resb_ld + col0);
+#pragma unroll
+        for (int j = 0; j < CW / 8; ++j) r2[j] = (valid && col0 + j * 8 < a.Cout) ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
+      }
     }
     DP_T(const long long e0 = clock64();)
     tc::mbar_wait(&bars->tmem_full[buf], (it >> (a.nbuf == 4 ? 2 : 1)) & 1);
@@ -282,7 +342,8 @@ __device__ __forceinline__ void epilogue_tma(const Maps& tm, const ConvArgs& a, 
     if (a.resb && !a.aux_mode) {
 #pragma unroll
       for (int j = 0; j < CW / 8; ++j) {
-        const uint32_t rr[4] = {r2[j].x, r2[j].y, r2[j].z, r2[j].w};
+        const uint4 rv = single ? r1[j] : r2[j];             // pipelined mode keeps the (only) operand in r1
+        const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) { v[j * 8 + 2 * k] += bf16_lo(rr[k]); v[j * 8 + 2 * k + 1] += bf16_hi(rr[k]); }
       }
@@ -293,7 +354,7 @@ __device__ __forceinline__ void epilogue_tma(const Maps& tm, const ConvArgs& a, 
     for (int j = 0; j < CW / 8; ++j) {
       uint32_t q[4], q2[4];
       float cx[8];                      // aux mode: the pre-activation values c of this thread's 8 columns
-      if (a.aux_mode) aux_mask8(&v[j * 8], r2[j], s_aux, a.Cout, col0 + j * 8, a.aux_hi, cx);
+      if (a.aux_mode) aux_mask8(&v[j * 8], single ? r1[j] : r2[j], s_aux, a.Cout, col0 + j * 8, a.aux_hi, cx);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float x0v = v[j * 8 + 2 * k], x1v = v[j * 8 + 2 * k + 1];
@@ -375,6 +436,14 @@ __device__ __forceinline__ void epilogue_tma_warp(const Maps& tm, const ConvArgs
   int it = grp, ring = 0;
   TileIter ti;
   ti.init(a, blockIdx.x + (unsigned)grp * gridDim.x);
+  const bool has_op = a.res || a.resb;
+  TileIter tp = ti;                                         // this group's tile kPfTiles ahead (groups take alternate tiles)
+  if (has_op) {
+    for (int k = 0; k < kPfTiles; ++k) {
+      if (blockIdx.x + (long long)(grp + 2 * k) * gridDim.x < a.total_items) prefetch_tile_operands(a, tp, py, px, 0);
+      tp.step(a); tp.step(a);
+    }
+  }
   for (long long item = blockIdx.x + (long long)grp * gridDim.x; item < a.total_items;
        item += 2LL * gridDim.x, it += 2, ti.step(a), ti.step(a)) {
     const int n = ti.n, y0 = ti.ty * a.th, x0 = ti.tx * a.tw;
@@ -383,6 +452,10 @@ __device__ __forceinline__ void epilogue_tma_warp(const Maps& tm, const ConvArgs
     const int oy = y * a.osy + a.oay, ox = x * a.osx + a.oax;
     const bool valid = (y < a.H) && (x < a.W) && (oy < a.Ho) && (ox < a.Wo);
     const long long pix = ((long long)n * a.Ho + oy) * a.Wo + ox;
+    if (has_op) {
+      if (item + 2LL * kPfTiles * gridDim.x < a.total_items) prefetch_tile_operands(a, tp, py, px, 0);
+      tp.step(a); tp.step(a);
+    }
     uint4 r1[BNT / 8], r2[BNT / 8];
     if (a.res) {
       const uint4* rp = reinterpret_cast<const uint4*>(a.res + pix * a.res_ld);
@@ -1131,6 +1204,7 @@ int launch(const Plane* planes, const ColSpec* cols, int ncols, int B, int Hg, i
   a.stats = ep.stats;
   a.pre_ss = ep.pre_ss; a.pre_act = ep.pre_act; a.pre_c = Cin;
   for (int c = 0; c < kMaxCols; ++c) { a.pH[c] = planes[cols[c < ncols ? c : 0].plane].Hp; a.pW[c] = planes[cols[c < ncols ? c : 0].plane].Wp; }
+  a.epi_pipe = ep.mask_x ? 1 : 0;     // measured: the rotation pays in the BatchNorm-backward mode only (1.34 -> 1.03 ms)
   a.aux_mode = ep.mask_x ? 1 : 0;
   a.aux_ss = ep.mask_ss;
   a.aux_hi = ep.mask_act == 2 ? 6.f : __builtin_inff();

@@ -884,10 +884,25 @@ def _bn_apply_raw(c, ss, act, res=None, c2=None, ss2=None):
 
 
 class Fusion:
-    """which BatchNorm fusions the block-level autograd nodes use (all on by default; the switches exist so that the
-    parity tests and tools/fused_micro.py can compare each fused launch with its unfused pipeline)"""
-    prologue = True       # bn + ReLU of the input inside the consumer conv's operand path (forward and weight gradient)
-    backward = True       # ReLU mask + BatchNorm-backward batch sums in the data-gradient epilogue
+    """which BatchNorm fusions the block-level autograd nodes use.  Policy from tools/fused_micro.py on B200 (B = 32,
+    448x576, ms per launch; profiles/fused_micro_r2.txt):
+
+      backward (ReLU mask + BatchNorm-backward sums in the data-gradient epilogue): 64->64 1.04 vs 0.62 + 0.45 for the
+        separate reduction pass, 32->32 0.49 vs 0.29 + 0.23, 32->64 0.88 vs 0.57 + 0.45: on (break-even to 15 % faster,
+        one launch and one full read of the gradient fewer).
+      prologue (bn + ReLU inside the consumer conv's operand path): 64->64 forward 0.92 vs 0.62 + 0.41 for conv + bn_apply,
+        but the weight gradient then has to re-create the activation in its own operand path (0.95 vs 0.70), and at
+        <= 32 channels the four transform warps cannot keep up with the HBM-bound tile rate (32->32 0.66 vs 0.29 + 0.21).
+        "auto": used where it wins - forward passes that keep no graph (eval / no_grad) with >= 64 input channels;
+        True / False force it (tests compare both paths bit for bit)."""
+    prologue = "auto"
+    backward = True
+
+    @staticmethod
+    def use_prologue(cin, needs_grad):
+        if Fusion.prologue == "auto":
+            return (not needs_grad) and cin >= 64
+        return bool(Fusion.prologue)
 
 
 class _ResBlock(torch.autograd.Function):
@@ -909,7 +924,7 @@ class _ResBlock(torch.autograd.Function):
         c1, st1 = _conv_raw(x, PACKS.get(w1, 0, 0), C1, 3, stats=train)
         ss1, save1, tr1 = _bn_coeffs(bn1, c1, st1, train)
         a1 = None
-        if Fusion.prologue:
+        if Fusion.use_prologue(C1, any(ctx.needs_input_grad)):
             c2, st2 = _conv_raw(c1, PACKS.get(w2, 0, 0), C2, 3, stats=bn2.training, pre=(ss1, 1))
         else:
             a1 = _bn_apply_raw(c1, ss1, 1)

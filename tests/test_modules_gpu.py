@@ -336,3 +336,36 @@ def test_config5_dpt_decoder_at_2x_resolution(pkg):
         else:
             assert p.grad is not None and bool(torch.isfinite(p.grad).all()), k
     assert all(f.grad is not None and bool(torch.isfinite(f.grad).all()) for f in fin)
+
+
+@pytest.mark.parametrize("cin,cout", [(64, 64), (64, 32), (32, 16)])
+def test_resblock_fused_paths_bit_identical(pkg, cin, cout):
+    """ResidualBlock as one autograd node: every combination of the BatchNorm fusions (prologue in conv2 / its weight
+    gradient, mask + batch sums in conv2's data-gradient epilogue) must give bit-identical outputs, input gradients,
+    parameter gradients and BN buffers - the fused launches reproduce the unfused arithmetic exactly."""
+    import copy
+    from depth_b200 import ops
+    from depth_b200.network import midas_semantics
+    torch.manual_seed(3)
+    base = fx.fill_deterministic(midas_semantics.ResidualBlock(cin, cout)).cuda().train()
+    x0 = torch.randn(2, cin, 40, 56, device="cuda")
+    results = []
+    saved = (ops.Fusion.prologue, ops.Fusion.backward)
+    try:
+        for pro, bwd in ((False, False), (True, False), (False, True), (True, True)):
+            ops.Fusion.prologue, ops.Fusion.backward = pro, bwd
+            m = copy.deepcopy(base)
+            x = x0.clone().requires_grad_(True)
+            y = m(x)
+            (y * torch.linspace(0.5, 1.5, y.numel(), device="cuda").view_as(y)).sum().backward()
+            results.append((y.detach(), x.grad, {k: p.grad for k, p in m.named_parameters()},
+                            {k: b.clone() for k, b in m.named_buffers()}))
+    finally:
+        ops.Fusion.prologue, ops.Fusion.backward = saved
+    y0, g0, p0, b0 = results[0]
+    for y, g, pg, bf in results[1:]:
+        assert torch.equal(y, y0) and torch.equal(g, g0)
+        for k in p0:
+            assert torch.equal(pg[k], p0[k]), k
+        for k in b0:
+            assert torch.equal(bf[k], b0[k]), k

@@ -39,10 +39,11 @@ for cin, cout, ks in shapes:
     t_pre = timeit(lambda: ops._conv_raw(x, w, cout, ks, stats=True, pre=(ss, 1)))
     caps = L.lib().dp_conv2d_tc_caps(B, H, W, cin, cout, ks)
     t_mask = timeit(lambda: ops._conv_raw(x, w, cout, ks, mask=(c, ssm, 1))) if caps & 2 else float("nan")
+    t_res = timeit(lambda: ops._conv_raw(x, w, cout, ks, res=c))
     t_bn = timeit(lambda: ops._bn_apply_raw(x, ss, 1))
     t_red = timeit(lambda: ops._bn_reduce(c, g, None, ssm, 1))
     t_wg = timeit(lambda: ops._wgrad_raw(x, g, cin, cout, ks))
     t_wgp = timeit(lambda: ops._wgrad_raw(x, g, cin, cout, ks, pre=(ss, 1)))
     by = 2.0 * B * H * W * (cin + cout)
-    print(f"{cin:3d}->{cout:3d} k{ks}: conv {t_plain:.3f} (floor {by / HBM * 1e3:.3f})  +pre {t_pre:.3f}  +mask {t_mask:.3f} | "
+    print(f"{cin:3d}->{cout:3d} k{ks}: conv {t_plain:.3f} (floor {by / HBM * 1e3:.3f})  +res {t_res:.3f}  +pre {t_pre:.3f}  +mask {t_mask:.3f} | "
           f"bn_apply(in) {t_bn:.3f} reduce(out) {t_red:.3f} | wgrad {t_wg:.3f} +pre {t_wgp:.3f}")
