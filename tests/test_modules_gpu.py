@@ -342,7 +342,8 @@ def test_config5_dpt_decoder_at_2x_resolution(pkg):
 def test_resblock_fused_paths_bit_identical(pkg, cin, cout):
     """ResidualBlock as one autograd node: every combination of the BatchNorm fusions (prologue in conv2 / its weight
     gradient, mask + batch sums in conv2's data-gradient epilogue) must give bit-identical outputs, input gradients,
-    parameter gradients and BN buffers - the fused launches reproduce the unfused arithmetic exactly."""
+    parameter gradients and BN buffers: bit-identical for the prologue (same arithmetic, same rounding), and equal up to
+    the summation order of the two BatchNorm-backward batch sums for the data-gradient epilogue."""
     import copy
     from depth_b200 import ops
     from depth_b200.network import midas_semantics
@@ -362,10 +363,19 @@ def test_resblock_fused_paths_bit_identical(pkg, cin, cout):
                             {k: b.clone() for k, b in m.named_buffers()}))
     finally:
         ops.Fusion.prologue, ops.Fusion.backward = saved
-    y0, g0, p0, b0 = results[0]
-    for y, g, pg, bf in results[1:]:
-        assert torch.equal(y, y0) and torch.equal(g, g0)
-        for k in p0:
-            assert torch.equal(pg[k], p0[k]), k
-        for k in b0:
-            assert torch.equal(bf[k], b0[k]), k
+    def same(a, b, exact):
+        ya, ga, pa, ba = a
+        yb, gb, pb, bb = b
+        assert torch.equal(ya, yb)                      # the forward is bit-identical in every combination
+        for k in ba:
+            assert torch.equal(ba[k], bb[k]), k
+        pairs = [("x.grad", ga, gb)] + [(k, pa[k], pb[k]) for k in pa]
+        for k, u, v in pairs:
+            if exact:
+                assert torch.equal(u, v), k
+            else:       # the batch sums are folded in a different order (epilogue partials vs reduction pass)
+                assert float((u.float() - v.float()).norm()) <= 2e-3 * float(v.float().norm()) + 1e-6, k
+
+    same(results[1], results[0], exact=True)            # prologue on / off
+    same(results[3], results[2], exact=True)            # ... also with the backward epilogue on
+    same(results[2], results[0], exact=False)           # backward epilogue on / off
