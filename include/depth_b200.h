@@ -326,6 +326,9 @@ int dp_attn_bwd(const float* q, const float* k, const float* v, const float* out
 /* K in {3,5}, stride in {1,2}; explicit top/left padding (symmetric or TF-"SAME"); w fp32 [K*K][C] tap-major.
  * stats_partials: null or float[dp_dwconv_fwd_blocks()][2][C] = per-block (sum, sumsq) of the stored output. */
 int dp_dwconv_fwd_blocks(int B, int Ho, int Wo, int C);
+/* rows of the statistics partials for a given stride: stride 1 runs the shared-memory tile kernel (one TMA box per
+ * 8 x TW output tile, persistent blocks per channel chunk), stride 2 the register-window kernel */
+int dp_dwconv_fwd_blocks_s(int B, int Ho, int Wo, int C, int K, int stride);
 int dp_dwconv_fwd(const void* x, long long x_ld, int B, int Hi, int Wi, int C, const float* w, int K, int stride,
                   int pad_t, int pad_l, void* out, long long out_ld, int Ho, int Wo, float* stats_partials,
                   cudaStream_t stream);

@@ -110,6 +110,7 @@ class _Sig:
     dp_conv2d_wgrad_tc_workspace = (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int])
     dp_conv2d_wgrad_tc = (c_int, [P, c_ll, P, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_size_t, P])
     dp_dwconv_fwd_blocks = (c_int, [c_int, c_int, c_int, c_int])
+    dp_dwconv_fwd_blocks_s = (c_int, [c_int, c_int, c_int, c_int, c_int, c_int])
     dp_dwconv_fwd = (c_int, [P, c_ll, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, P, c_ll, c_int, c_int, P, P])
     dp_dwconv_dgrad_s2 = (c_int, [P, c_ll, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, P, c_ll, c_int, c_int, P])
     dp_dwconv_wgrad_workspace = (c_size_t, [c_int, c_int, c_int, c_int, c_int])

@@ -225,7 +225,11 @@ __device__ __forceinline__ void prefetch_tile_operands(const ConvArgs& a, const 
 // thread hands to TMA (the store clips tile overhang, so no per-pixel predicates and fully coalesced HBM writes).
 // BatchNorm partial sums stay in registers across all tiles of the persistent CTA (thread = fixed pixel slot and
 // column slice) and are reduced once at the end.
-template <int CW>
+// MODE (compile time, so that the plain path carries none of the operand code: with run-time switches the common plain
+// launch lost 20 % - 64->64 @448x576 0.50 -> 0.60 ms - to register pressure and instruction-cache misses):
+//   0 no epilogue operand, 1 residual(s) read per tile (L2-prefetched kPfTiles ahead), 2 BatchNorm-backward mode (`resb`
+//   is the pre-activation tensor, software-pipelined one tile ahead through registers)
+template <int CW, int MODE>
 __device__ __forceinline__ void epilogue_tma(const Maps& tm, const ConvArgs& a, Barriers* bars, uint8_t* s_out,
                                              float* s_stats, const float* s_aux, uint32_t tmem, int warp, int lane) {
   const int e = warp - 4, ew = e & 3, half = e >> 2;
@@ -256,9 +260,10 @@ __device__ __forceinline__ void epilogue_tma(const Maps& tm, const ConvArgs& a, 
   // critical path every tile (ncu: 23 % of all stall samples on the first use of the loaded value, 64->64 @448x576
   // 0.60 -> 0.95 ms).  With a single operand - the common case - the loads are software-pipelined one tile ahead in the
   // register set the second operand would have used: `r2` receives tile i+1 while `r1` (tile i) is consumed.
-  const bool single = a.epi_pipe && ((a.res != nullptr) != (a.resb != nullptr));
-  const bf16* op = a.res ? a.res : a.resb;
-  const long long op_ld = a.res ? a.res_ld : a.resb_ld;
+  constexpr bool single = MODE == 2;       // MODE 2: the one operand is `resb` (launch() rejects a residual next to it)
+  constexpr bool HAS_RES = MODE == 1;
+  const bf16* op = a.resb;
+  const long long op_ld = a.resb_ld;
   uint4 r1[CW / 8], r2[CW / 8];
   auto load_operand = [&](const TileIter& t, uint4 (&dst)[CW / 8]) {
     const int yy = t.ty * a.th + py, xx = t.tx * a.tw + px;
@@ -273,7 +278,7 @@ __device__ __forceinline__ void epilogue_tma(const Maps& tm, const ConvArgs& a, 
   tn.step(a);
   // operands that are not pipelined through registers (two operands, or plain residuals - for which the register
   // rotation measured no gain) are pulled into L2 kPfTiles tiles ahead instead (64->64 + residual: 1.12 -> 0.95 ms)
-  const bool pf = !single && (a.res || a.resb);
+  constexpr bool pf = MODE == 1;
   TileIter tp = ti;
   if (pf) {
     for (int k = 0; k < kPfTiles; ++k) {
@@ -298,12 +303,12 @@ __device__ __forceinline__ void epilogue_tma(const Maps& tm, const ConvArgs& a, 
       if (item + gridDim.x < a.total_items) load_operand(tn, r2);
     } else {
       // two operands: fetched here, before waiting for the MMAs (they do not depend on the accumulator)
-      if (a.res) {
+      if (HAS_RES && a.res) {
         const uint4* rp = reinterpret_cast<const uint4*>(a.res + pix * a.res_ld + col0);
 #pragma unroll
         for (int j = 0; j < CW / 8; ++j) r1[j] = (valid && col0 + j * 8 < a.Cout) ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
       }
-      if (a.resb) {
+      if (HAS_RES && a.resb) {
         const uint4* rp = reinterpret_cast<const uint4*>(a.resb + pix * a.resb_ld + col0);
 #pragma unroll
         for (int j = 0; j < CW / 8; ++j) r2[j] = (valid && col0 + j * 8 < a.Cout) ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
@@ -331,7 +336,7 @@ __device__ __forceinline__ void epilogue_tma(const Maps& tm, const ConvArgs& a, 
         }
       }
     }
-    if (a.res) {
+    if (HAS_RES && a.res) {
 #pragma unroll
       for (int j = 0; j < CW / 8; ++j) {
         const uint32_t rr[4] = {r1[j].x, r1[j].y, r1[j].z, r1[j].w};
@@ -339,10 +344,10 @@ __device__ __forceinline__ void epilogue_tma(const Maps& tm, const ConvArgs& a, 
         for (int k = 0; k < 4; ++k) { v[j * 8 + 2 * k] += bf16_lo(rr[k]); v[j * 8 + 2 * k + 1] += bf16_hi(rr[k]); }
       }
     }
-    if (a.resb && !a.aux_mode) {
+    if (HAS_RES && a.resb) {
 #pragma unroll
       for (int j = 0; j < CW / 8; ++j) {
-        const uint4 rv = single ? r1[j] : r2[j];             // pipelined mode keeps the (only) operand in r1
+        const uint4 rv = r2[j];
         const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) { v[j * 8 + 2 * k] += bf16_lo(rr[k]); v[j * 8 + 2 * k + 1] += bf16_hi(rr[k]); }
@@ -354,7 +359,7 @@ __device__ __forceinline__ void epilogue_tma(const Maps& tm, const ConvArgs& a, 
     for (int j = 0; j < CW / 8; ++j) {
       uint32_t q[4], q2[4];
       float cx[8];                      // aux mode: the pre-activation values c of this thread's 8 columns
-      if (a.aux_mode) aux_mask8(&v[j * 8], single ? r1[j] : r2[j], s_aux, a.Cout, col0 + j * 8, a.aux_hi, cx);
+      if (MODE == 2) aux_mask8(&v[j * 8], r1[j], s_aux, a.Cout, col0 + j * 8, a.aux_hi, cx);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float x0v = v[j * 8 + 2 * k], x1v = v[j * 8 + 2 * k + 1];
@@ -366,9 +371,9 @@ __device__ __forceinline__ void epilogue_tma(const Maps& tm, const ConvArgs& a, 
           // statistics of the value as stored (bf16-rounded), so mean/var describe the tensor the consumer reads
           const float f0 = valid ? bf16_lo(plain) : 0.f, f1 = valid ? bf16_hi(plain) : 0.f;
           acc_s[j * 8 + 2 * k] += f0;
-          acc_q[j * 8 + 2 * k] = fmaf(f0, a.aux_mode ? cx[2 * k] : f0, acc_q[j * 8 + 2 * k]);
+          acc_q[j * 8 + 2 * k] = fmaf(f0, MODE == 2 ? cx[2 * k] : f0, acc_q[j * 8 + 2 * k]);
           acc_s[j * 8 + 2 * k + 1] += f1;
-          acc_q[j * 8 + 2 * k + 1] = fmaf(f1, a.aux_mode ? cx[2 * k + 1] : f1, acc_q[j * 8 + 2 * k + 1]);
+          acc_q[j * 8 + 2 * k + 1] = fmaf(f1, MODE == 2 ? cx[2 * k + 1] : f1, acc_q[j * 8 + 2 * k + 1]);
         }
       }
       tc::st_shared_v4(st + soff[j], q[0], q[1], q[2], q[3]);
@@ -410,7 +415,7 @@ __device__ __forceinline__ void epilogue_tma(const Maps& tm, const ConvArgs& a, 
 // (TMEM load -> math -> staging -> store), not by its work, so the eight warps form two independent groups that take
 // alternate tiles (group g <-> MMA issuer g <-> TMEM buffers g, g+2).  Each warp owns 32 pixels x all BN columns, stages
 // them in its own swizzled ring slot and issues its own TMA store of a (32 / tw) x tw pixel box: no inter-warp barrier.
-template <int BNT>
+template <int BNT, int MODE>      // MODE as in epilogue_tma (here both operand modes read per tile, L2-prefetched)
 __device__ __forceinline__ void epilogue_tma_warp(const Maps& tm, const ConvArgs& a, Barriers* bars, uint8_t* s_out,
                                                   float* s_stats, const float* s_aux, uint32_t tmem, int warp, int lane) {
   const int e = warp - 4, ew = e & 3, grp = e >> 2;
@@ -436,7 +441,7 @@ __device__ __forceinline__ void epilogue_tma_warp(const Maps& tm, const ConvArgs
   int it = grp, ring = 0;
   TileIter ti;
   ti.init(a, blockIdx.x + (unsigned)grp * gridDim.x);
-  const bool has_op = a.res || a.resb;
+  constexpr bool has_op = MODE != 0;
   TileIter tp = ti;                                         // this group's tile kPfTiles ahead (groups take alternate tiles)
   if (has_op) {
     for (int k = 0; k < kPfTiles; ++k) {
@@ -457,12 +462,12 @@ __device__ __forceinline__ void epilogue_tma_warp(const Maps& tm, const ConvArgs
       tp.step(a); tp.step(a);
     }
     uint4 r1[BNT / 8], r2[BNT / 8];
-    if (a.res) {
+    if (MODE != 0 && a.res) {
       const uint4* rp = reinterpret_cast<const uint4*>(a.res + pix * a.res_ld);
 #pragma unroll
       for (int j = 0; j < BNT / 8; ++j) r1[j] = (valid && j * 8 < a.Cout) ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
     }
-    if (a.resb) {
+    if (MODE != 0 && a.resb) {
       const uint4* rp = reinterpret_cast<const uint4*>(a.resb + pix * a.resb_ld);
 #pragma unroll
       for (int j = 0; j < BNT / 8; ++j) r2[j] = (valid && j * 8 < a.Cout) ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
@@ -490,7 +495,7 @@ __device__ __forceinline__ void epilogue_tma_warp(const Maps& tm, const ConvArgs
         }
       }
     }
-    if (a.res) {
+    if (MODE != 0 && a.res) {
 #pragma unroll
       for (int j = 0; j < BNT / 8; ++j) {
         const uint32_t rr[4] = {r1[j].x, r1[j].y, r1[j].z, r1[j].w};
@@ -498,7 +503,7 @@ __device__ __forceinline__ void epilogue_tma_warp(const Maps& tm, const ConvArgs
         for (int k = 0; k < 4; ++k) { v[j * 8 + 2 * k] += bf16_lo(rr[k]); v[j * 8 + 2 * k + 1] += bf16_hi(rr[k]); }
       }
     }
-    if (a.resb && !a.aux_mode) {
+    if (MODE == 1 && a.resb) {
 #pragma unroll
       for (int j = 0; j < BNT / 8; ++j) {
         const uint32_t rr[4] = {r2[j].x, r2[j].y, r2[j].z, r2[j].w};
@@ -511,7 +516,7 @@ __device__ __forceinline__ void epilogue_tma_warp(const Maps& tm, const ConvArgs
     for (int j = 0; j < BNT / 8; ++j) {
       uint32_t q[4];
       float cx[8];
-      if (a.aux_mode) aux_mask8(&v[j * 8], r2[j], s_aux, a.Cout, j * 8, a.aux_hi, cx);
+      if (MODE == 2) aux_mask8(&v[j * 8], r2[j], s_aux, a.Cout, j * 8, a.aux_hi, cx);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float x0v = v[j * 8 + 2 * k], x1v = v[j * 8 + 2 * k + 1];
@@ -520,9 +525,9 @@ __device__ __forceinline__ void epilogue_tma_warp(const Maps& tm, const ConvArgs
         if (want_stats) {
           const float f0 = valid ? bf16_lo(plain) : 0.f, f1 = valid ? bf16_hi(plain) : 0.f;
           acc_s[j * 8 + 2 * k] += f0;
-          acc_q[j * 8 + 2 * k] = fmaf(f0, a.aux_mode ? cx[2 * k] : f0, acc_q[j * 8 + 2 * k]);
+          acc_q[j * 8 + 2 * k] = fmaf(f0, MODE == 2 ? cx[2 * k] : f0, acc_q[j * 8 + 2 * k]);
           acc_s[j * 8 + 2 * k + 1] += f1;
-          acc_q[j * 8 + 2 * k + 1] = fmaf(f1, a.aux_mode ? cx[2 * k + 1] : f1, acc_q[j * 8 + 2 * k + 1]);
+          acc_q[j * 8 + 2 * k + 1] = fmaf(f1, MODE == 2 ? cx[2 * k + 1] : f1, acc_q[j * 8 + 2 * k + 1]);
         }
       }
       tc::st_shared_v4(st + soff[j], q[0], q[1], q[2], q[3]);
@@ -999,15 +1004,23 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
   } else if (warp >= 4 && warp < 12) {
     // ================= epilogue: TMEM -> registers -> (smem -> TMA store | global) =================
     if constexpr (kPre) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    const int mode = a.aux_mode ? 2 : ((a.res || a.resb) ? 1 : 0);
+#define DP_EPI(FN, N)                                                                       \
+  do {                                                                                      \
+    if (mode == 0) FN<N, 0>(tm, a, bars, s_out, s_stats, s_aux, tmem, warp, lane);          \
+    else if (mode == 1) FN<N, 1>(tm, a, bars, s_out, s_stats, s_aux, tmem, warp, lane);     \
+    else FN<N, 2>(tm, a, bars, s_out, s_stats, s_aux, tmem, warp, lane);                    \
+  } while (0)
     if (a.epi_tma == 3) {
-      if (a.BN == 32) epilogue_tma_warp<32>(tm, a, bars, s_out, s_stats, s_aux, tmem, warp, lane);
-      else epilogue_tma_warp<16>(tm, a, bars, s_out, s_stats, s_aux, tmem, warp, lane);
+      if (a.BN == 32) DP_EPI(epilogue_tma_warp, 32);
+      else DP_EPI(epilogue_tma_warp, 16);
     } else if (a.epi_tma == 2) {
       epilogue_tma_wide(tm, a, bars, s_out, s_stats, tmem, warp, lane);
     } else if (a.epi_tma) {
-      if (a.BN == 64) epilogue_tma<32>(tm, a, bars, s_out, s_stats, s_aux, tmem, warp, lane);
-      else if (a.BN == 32) epilogue_tma<16>(tm, a, bars, s_out, s_stats, s_aux, tmem, warp, lane);
-      else epilogue_tma<8>(tm, a, bars, s_out, s_stats, s_aux, tmem, warp, lane);
+      if (a.BN == 64) DP_EPI(epilogue_tma, 32);
+      else if (a.BN == 32) DP_EPI(epilogue_tma, 16);
+      else DP_EPI(epilogue_tma, 8);
+#undef DP_EPI
     } else {
       epilogue_direct(a, bars, s_stats, tmem, warp, lane);
     }
@@ -1190,8 +1203,8 @@ int launch(const Plane* planes, const ColSpec* cols, int ncols, int B, int Hg, i
   if (ep.mask_x && !(p.a.epi_tma == 1 || p.a.epi_tma == 3))
     return dp_set_error(DP_ERR_UNSUPPORTED, "conv_tc: the BatchNorm-backward epilogue needs a single 16/32/64-column N block "
                         "(Cout %d)", Cout);
-  if (ep.mask_x && (ep.res2 || ep.relu || ep.out2))
-    return dp_set_error(DP_ERR_INVALID, "conv_tc: the BatchNorm-backward epilogue excludes residual2 / relu / dual output");
+  if (ep.mask_x && (ep.res || ep.res2 || ep.relu || ep.out2))
+    return dp_set_error(DP_ERR_INVALID, "conv_tc: the BatchNorm-backward epilogue excludes residuals / relu / dual output");
   if (p.a.halo) ncols = 1;
   ConvArgs& a = p.a;
   a.Ho = om.Ho; a.Wo = om.Wo; a.osy = om.osy; a.osx = om.osx; a.oay = om.oay; a.oax = om.oax;

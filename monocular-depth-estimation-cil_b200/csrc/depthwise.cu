@@ -9,6 +9,7 @@
 //   * weight gradient: thread = 8 channels x one kernel row, K x 8 fp32 accumulators, fixed-order two-level reduction
 //     (no atomics).
 #include "common.cuh"
+#include "tc.cuh"
 #include "../../include/depth_b200.h"
 
 namespace {
@@ -154,6 +155,181 @@ __global__ void __launch_bounds__(TPB, 2) dw_fwd_kernel(DwArgs a) {
       for (int j = 0; j < 8; ++j) { dst[j] = sacc[j]; dst[a.C + j] = qacc[j]; }
     }
   }
+}
+
+// ---- stride-1 forward / data gradient from a shared-memory tile -----------------------------------------------------
+// The register-window kernel above re-reads every input vector K times through L1 / L2 (10 loads per output at K = 5)
+// and unpacks it for every tap: ~250 instructions per output vector, 13 - 40 % of the HBM floor.  Here a persistent block
+// owns a channel chunk of CG groups (CG * 16 bytes per pixel) and walks 8 x TW output tiles.  The (8+K-1) x (TW+K-1) input
+// tile arrives by ONE TMA box load (zero fill outside the image = the conv padding and the tile overhang), double
+// buffered on mbarriers so the next tile is in flight while this one is computed.  A thread owns one channel group of a
+// 2-row x 4-column output patch: it reads each of the (2+K-1) x (4+K-1) input vectors of its patch from shared memory
+// once and unpacks it once (48 loads + unpacks for 8 outputs at K = 5 instead of 80 + 80), the taps come from shared
+// memory as warp-broadcast loads, the MACs are packed f32x2.  ~175 (K = 5) / ~70 (K = 3) instructions per output vector.
+// Two blocks per SM, one tile buffer each: while one block waits for its TMA box the other computes (the kernel is bound
+// by the FMA pipe - 100 packed FFMA2 per output vector at K = 5 - so what matters is keeping 16 warps issuing).
+// output patch per thread: 4 rows x 2 columns at K = 3 (3 input vectors per output), 2 x 2 at K = 5 (9 per output; the
+// 4 x 2 patch needs 64 + 48 fp32 registers for accumulators and the unpacked row and spilled at 128 registers)
+constexpr int dt_r(int K) { return K == 3 ? 4 : 2; }
+constexpr int DT_TXO = 2;
+
+template <int K, int TW, int CG>
+__global__ void __launch_bounds__(TPB, 2) dw_tile_kernel(const __grid_constant__ CUtensorMap tmx, DwArgs a) {
+  constexpr int DT_R = dt_r(K);
+  constexpr int QX = TW / DT_TXO;                            // column pairs per tile row
+  constexpr int TH = DT_R * (TPB / CG) / QX;                 // output rows per tile
+  static_assert(TH >= DT_R && (TPB / CG) % QX == 0, "thread layout");
+  constexpr int IH = TH + K - 1, IW = TW + K - 1;
+  constexpr int PXB = CG * 16;                               // bytes per pixel of the chunk
+  constexpr uint32_t TILE_BYTES = (uint32_t)IH * IW * PXB;
+  extern __shared__ __align__(128) unsigned char dsm[];
+  unsigned char* tile = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dsm) + 127) & ~uintptr_t(127));
+  float* s_w = reinterpret_cast<float*>(tile + ((TILE_BYTES + 127u) & ~127u));   // [K*K][CG*8]
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_w + K * K * CG * 8);
+  const int C8 = a.C / 8;
+  const int cg = threadIdx.x % CG, pt = threadIdx.x / CG;
+  const int qx = pt % QX, ry = pt / QX;
+  const int c8 = blockIdx.y * CG + cg;
+  const bool chan_ok = c8 < C8;
+  const int tiles_x = (a.Wo + TW - 1) / TW, tiles_y = (a.Ho + TH - 1) / TH;
+  const int ntiles = a.B * tiles_y * tiles_x;
+  for (int i = threadIdx.x; i < K * K * CG * 8; i += TPB) {
+    const int tap = i / (CG * 8), cc = i - tap * (CG * 8);
+    const int ch = blockIdx.y * CG * 8 + cc;
+    s_w[i] = ch < a.C ? __ldg(a.w + (size_t)tap * a.C + ch) : 0.f;
+  }
+  if (threadIdx.x == 0) {
+    tc::mbar_init(full, 1);
+    tc::fence_barrier_init();
+    tc::prefetch_tmap(&tmx);
+  }
+  __syncthreads();
+  auto issue = [&](int t) {                     // thread 0: one box load = the whole input tile of output tile t
+    const int tx = t % tiles_x, r = t / tiles_x;
+    const int ty = r % tiles_y, b = r / tiles_y;
+    tc::mbar_expect_tx(full, TILE_BYTES);
+    tc::tma_load_4d(tile, &tmx, full, blockIdx.y * CG * 8, tx * TW - a.pad_l, ty * TH - a.pad_t, b);
+  };
+  if (threadIdx.x == 0 && (int)blockIdx.x < ntiles) issue(blockIdx.x);
+  float st_s[8], st_q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { st_s[j] = 0.f; st_q[j] = 0.f; }
+  const uint32_t w_base = tc::smem_u32(s_w) + (uint32_t)cg * 32u;
+  const uint32_t tb = tc::smem_u32(tile) + (uint32_t)((DT_R * ry) * IW + DT_TXO * qx) * PXB + (uint32_t)cg * 16u;
+  int it = 0;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    tc::mbar_wait(full, it & 1);
+    const int tx = t % tiles_x, rr = t / tiles_x;
+    const int ty = rr % tiles_y, b = rr / tiles_y;
+    float2 acc[DT_R][DT_TXO][4];
+#pragma unroll
+    for (int r = 0; r < DT_R; ++r)
+#pragma unroll
+      for (int q = 0; q < DT_TXO; ++q)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[r][q][j] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int iy = 0; iy < DT_R + K - 1; ++iy) {
+      float2 rv[DT_TXO + K - 1][4];               // this input row of the patch, unpacked once
+#pragma unroll
+      for (int c = 0; c < DT_TXO + K - 1; ++c) {
+        uint32_t u0, u1, u2, u3;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u0), "=r"(u1), "=r"(u2), "=r"(u3)
+                     : "r"(tb + (uint32_t)(iy * IW + c) * PXB));
+        const uint32_t uw[4] = {u0, u1, u2, u3};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          rv[c][j] = make_float2(__uint_as_float(uw[j] << 16), __uint_as_float(uw[j] & 0xffff0000u));
+      }
+#pragma unroll
+      for (int r = 0; r < DT_R; ++r) {
+        const int ky = iy - r;                     // compile-time after unrolling
+        if (ky < 0 || ky >= K) continue;
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+          float2 w2[4];
+          const uint32_t wa = w_base + (uint32_t)((ky * K + kx) * CG * 8) * 4u;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w2[0].x), "=f"(w2[0].y), "=f"(w2[1].x), "=f"(w2[1].y) : "r"(wa));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w2[2].x), "=f"(w2[2].y), "=f"(w2[3].x), "=f"(w2[3].y) : "r"(wa + 16u));
+#pragma unroll
+          for (int q = 0; q < DT_TXO; ++q)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[r][q][j] = __ffma2_rn(rv[q + kx][j], w2[j], acc[r][q][j]);
+        }
+      }
+    }
+    // every thread is past its reads of the tile: fetch the next one while the results are packed and stored
+    __syncthreads();
+    if (threadIdx.x == 0 && t + (int)gridDim.x < ntiles) issue(t + gridDim.x);
+    if (chan_ok) {
+#pragma unroll
+      for (int r = 0; r < DT_R; ++r) {
+        const int oy = ty * TH + DT_R * ry + r;
+        if (oy >= a.Ho) continue;
+#pragma unroll
+        for (int q = 0; q < DT_TXO; ++q) {
+          const int ox = tx * TW + DT_TXO * qx + q;
+          if (ox >= a.Wo) continue;
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { o[2 * j] = acc[r][q][j].x; o[2 * j + 1] = acc[r][q][j].y; }
+          const uint4 pk = pack8(o);
+          *reinterpret_cast<uint4*>(a.out + (((long long)b * a.Ho + oy) * a.Wo + ox) * a.out_ld + c8 * 8) = pk;
+          if (a.stats) {
+            float f[8];
+            unpack8(pk, f);                        // statistics of the value as stored
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { st_s[j] += f[j]; st_q[j] = fmaf(f[j], f[j], st_q[j]); }
+          }
+        }
+      }
+    }
+  }
+  if (a.stats) {
+    // deterministic block reduction over the pixel threads of each channel group (the tile buffer is free now)
+    __syncthreads();
+    float* s_red = reinterpret_cast<float*>(tile);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s_red[threadIdx.x * 16 + j] = st_s[j]; s_red[threadIdx.x * 16 + 8 + j] = st_q[j]; }
+    __syncthreads();
+    if (threadIdx.x < CG && blockIdx.y * CG + threadIdx.x < C8) {
+      float sacc[8], qacc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sacc[j] = 0.f; qacc[j] = 0.f; }
+      for (int sl = 0; sl < TPB / CG; ++sl) {
+        const int tt = sl * CG + threadIdx.x;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sacc[j] += s_red[tt * 16 + j]; qacc[j] += s_red[tt * 16 + 8 + j]; }
+      }
+      float* dst = a.stats + (size_t)blockIdx.x * 2 * a.C + (size_t)(blockIdx.y * CG + threadIdx.x) * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { dst[j] = sacc[j]; dst[a.C + j] = qacc[j]; }
+    }
+  }
+}
+
+// tile geometry of the stride-1 path: output tile 8 x TW, CG channel groups per block
+struct DwTilePlan { int TW, CG, TH, ny, nx; };
+inline DwTilePlan dw_tile_plan(int B, int Ho, int Wo, int C, int K) {
+  // candidates (TW, CG) -> TH = R * (256 / CG) / (TW / 2) with R = 4 (K = 3) or 2 (K = 5)
+  // Pick the one that computes the fewest padded output vectors (tile overhang in x / y, channel-chunk overhang).
+  const int cand[3][2] = {{16, 8}, {16, 16}, {32, 8}};
+  DwTilePlan best{};
+  long long best_cost = -1;
+  for (int i = 0; i < 3; ++i) {
+    DwTilePlan p;
+    p.TW = cand[i][0]; p.CG = cand[i][1];
+    p.TH = dt_r(K) * (TPB / p.CG) / (p.TW / DT_TXO);
+    p.ny = (C / 8 + p.CG - 1) / p.CG;
+    const long long tx = (Wo + p.TW - 1) / p.TW, ty = (Ho + p.TH - 1) / p.TH;
+    const long long cost = tx * p.TW * ty * p.TH * (long long)p.ny * p.CG;
+    const long long ntiles = (long long)B * tx * ty;
+    long long nx = (2LL * kNumSMs + p.ny - 1) / p.ny;          // two blocks per SM
+    if (nx > ntiles) nx = ntiles;
+    p.nx = (int)(nx < 1 ? 1 : nx);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = p; }
+  }
+  return best;
 }
 
 // stride-2 data gradient: dx[b,iy,ix,c] = sum over taps with (iy + pad_t - ky) even: w[ky*K+kx][c] * dy[b,(iy+pad_t-ky)/2,...]
@@ -323,6 +499,11 @@ extern "C" {
 
 static inline int dw_G(int C) { return C / 8 < 32 ? C / 8 : 32; }
 
+int dp_dwconv_fwd_blocks_s(int B, int Ho, int Wo, int C, int K, int stride) {
+  if (stride == 1) return dw_tile_plan(B, Ho, Wo, C, K).nx;
+  return dp_dwconv_fwd_blocks(B, Ho, Wo, C);
+}
+
 int dp_dwconv_fwd_blocks(int B, int Ho, int Wo, int C) {
   const int G = dw_G(C), ny = (C / 8 + G - 1) / G, nslots = TPB / G;
   const long long nstrips = (long long)B * Ho * ((Wo + TX - 1) / TX);
@@ -347,6 +528,35 @@ int dp_dwconv_fwd(const void* x, long long x_ld, int B, int Hi, int Wi, int C, c
   const int G = dw_G(C);
   DwArgs a{reinterpret_cast<const bf16*>(x), x_ld, B, Hi, Wi, C, w, pad_t, pad_l, reinterpret_cast<bf16*>(out), out_ld,
            Ho, Wo, stats_partials, G};
+  if (stride == 1) {
+    // shared-memory tile path; stats_partials then has dp_dwconv_fwd_blocks_s(..., 1) rows
+    const DwTilePlan p = dw_tile_plan(B, Ho, Wo, C, K);
+    CUtensorMap tm;
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)Wi, (uint64_t)Hi, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)x_ld * 2, (uint64_t)Wi * x_ld * 2, (uint64_t)Hi * Wi * x_ld * 2};
+    const uint32_t box[4] = {(uint32_t)(p.CG * 8), (uint32_t)(p.TW + K - 1), (uint32_t)(p.TH + K - 1), 1};
+    int rc = dp_make_tmap_bf16(&tm, x, 4, dims, str, box, nullptr, 0 /* no swizzle: a thread group reads whole pixel rows */);
+    if (rc) return rc;
+    const size_t tile = (((size_t)(p.TH + K - 1) * (p.TW + K - 1) * p.CG * 16) + 127) & ~size_t(127);
+    size_t smem = 128 + tile + (size_t)K * K * p.CG * 8 * 4 + 64;
+    if (smem < 128 + (size_t)TPB * 16 * 4) smem = 128 + (size_t)TPB * 16 * 4;
+    dim3 grid(p.nx, p.ny);
+#define DP_DW_TILE(KK, TWW, CGG)                                                                          \
+    do {                                                                                                  \
+      cudaError_t e = cudaFuncSetAttribute(dw_tile_kernel<KK, TWW, CGG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (e != cudaSuccess) return dp_set_error(DP_ERR_CUDA, "dw_tile_kernel smem %zu: %s", smem, cudaGetErrorString(e));       \
+      dw_tile_kernel<KK, TWW, CGG><<<grid, TPB, smem, stream>>>(tm, a);                                     \
+    } while (0)
+    if (K == 3 && p.TW == 32) DP_DW_TILE(3, 32, 8);
+    else if (K == 3 && p.CG == 16) DP_DW_TILE(3, 16, 16);
+    else if (K == 3) DP_DW_TILE(3, 16, 8);
+    else if (p.TW == 32) DP_DW_TILE(5, 32, 8);
+    else if (p.CG == 16) DP_DW_TILE(5, 16, 16);
+    else DP_DW_TILE(5, 16, 8);
+#undef DP_DW_TILE
+    DP_CHECK_LAUNCH("dw_tile_kernel");
+    return DP_OK;
+  }
   dim3 grid(dp_dwconv_fwd_blocks(B, Ho, Wo, C), (C / 8 + G - 1) / G);
   const size_t smem = ((size_t)K * K * G * 8 + (stats_partials ? (size_t)TPB * 16 : 0)) * sizeof(float);
   if (K == 3 && stride == 1) dw_fwd_kernel<3, 1><<<grid, TPB, smem, stream>>>(a);

@@ -541,7 +541,7 @@ def _dw_launch(x, wp, K, stride, pad_t, pad_l, Ho, Wo, want_stats):
     out = _nhwc(B, Ho, Wo, C, x.device)
     st = None
     if want_stats:
-        st = torch.empty(lib.dp_dwconv_fwd_blocks(B, Ho, Wo, C), 2, C, dtype=torch.float32, device=x.device)
+        st = torch.empty(lib.dp_dwconv_fwd_blocks_s(B, Ho, Wo, C, K, stride), 2, C, dtype=torch.float32, device=x.device)
     L.check(lib.dp_dwconv_fwd(L.ptr(x), _ld(x), B, Hi, Wi, C, L.ptr(wp), K, stride, pad_t, pad_l, L.ptr(out), C, Ho, Wo,
                               L.ptr(st), L.stream()))
     return out, st

@@ -25,6 +25,23 @@ def _bhw(pred):
     return B, pred.numel() // (B * W), W
 
 
+# Data-parallel training shards the batch by sample.  Two terms of the loss are NOT sums of per-sample terms: SiLog
+# averages d and d^2 over the masked pixels of the WHOLE batch (reference util.py:118-121) and the edge-aware term
+# normalises the RGB gradient magnitude with the min / max over the WHOLE batch (util.py:70).  With torch.distributed
+# initialised those batch-global quantities are exchanged (one 3-double sum, one min/max all-reduce of the per-block
+# partials), so an N-GPU step computes exactly the single-device loss of the global batch; the SiLog gradient is scaled
+# by the world size because the gradient all-reduce averages over ranks.  Set to False for
+# per-replica semantics (nn.DataParallel-style).
+SYNC_BATCH_MOMENTS = True
+
+
+def _world():
+    import torch.distributed as dist
+    if SYNC_BATCH_MOMENTS and dist.is_available() and dist.is_initialized():
+        return dist.get_world_size()
+    return 1
+
+
 class _Pass:
     """One fused moments pass over (pred, target[, rgb])."""
 
@@ -51,9 +68,24 @@ class _Pass:
         if flags & L.F_EDGE:
             self.mm = torch.empty(lib.dp_rgb_minmax_bytes() // 4, dtype=torch.float32, device=dev)
             L.check(lib.dp_rgb_gradmag_minmax(L.ptr(self.rgb), self.B, self.H, self.W, L.ptr(self.mm), L.stream()))
+            if _world() > 1:      # batch-global min / max (util.py:70): the partials are (min, max) pairs
+                import torch.distributed as dist
+                sign = torch.tensor([1.0, -1.0], device=dev)
+                t = (self.mm.view(-1, 2) * sign).contiguous()
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)        # min of mins, min of negated maxes
+                self.mm.copy_((t * sign).view(-1))
         L.check(lib.dp_depth_moments(L.ptr(self.p), L.ptr(self.t), L.ptr(self.rgb), L.ptr(self.mm), self.B, self.H,
                                      self.W, flags, self.eps, L.ptr(self.mom), L.ptr(self.ws), self.ws_bytes,
                                      L.stream()))
+        self.world = _world()
+        if self.world > 1 and (flags & L.F_SILOG):
+            # batch-global SiLog moments (count, sum d, sum d^2 over the masked pixels of every rank's samples): the
+            # combine / backward kernels add the per-sample rows, so the global sums go into row 0 and the rest is zero
+            import torch.distributed as dist
+            tot = self.mom[:, L.M_M0:L.M_M2 + 1].sum(dim=0)
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+            self.mom[:, L.M_M0:L.M_M2 + 1] = 0
+            self.mom[0, L.M_M0:L.M_M2 + 1] = tot
 
     def combine(self, w_si=1.0, w_silog=0.0, vf=0.85, w_grad=0.0, beta=0.0, sqroot=False, per_sample=False):
         out = torch.empty(L.NLOSS, dtype=torch.float32, device=self.p.device)
@@ -65,6 +97,8 @@ class _Pass:
     def backward(self, grad_out, w_si, w_silog, vf, w_grad, beta, si_scale=None):
         g = torch.empty_like(self.p)
         go = grad_out.detach().float().contiguous() if grad_out is not None else None
+        if self.world > 1:
+            w_silog = w_silog * self.world      # the gradient all-reduce averages over ranks; SiLog is already global
         L.check(L.lib().dp_loss_backward(L.ptr(self.p), L.ptr(self.t), L.ptr(self.rgb), L.ptr(self.mm), L.ptr(self.mom),
                                          L.ptr(go), L.ptr(si_scale), self.B, self.H, self.W, self.flags, self.eps, w_si,
                                          w_silog, vf, w_grad, beta, L.ptr(g), L.stream()))

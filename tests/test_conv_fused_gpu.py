@@ -94,12 +94,11 @@ def test_bn_backward_epilogue_matches_reduce_pass(pkg, B, H, W, Cin, Cout, KS, a
     w = (torch.randn(Cout, Cin, KS, KS, generator=g) * (2.0 / (Cin * KS * KS)) ** 0.5).cuda()
     wp = pack_w(w)
     c = (torch.randn(B, H, W, Cout, generator=g) * 2).to(torch.bfloat16).cuda()
-    res = torch.randn(B, H, W, Cout, generator=g).to(torch.bfloat16).cuda()
     ss = _ss(Cout, Cout, positive_bias=2.0 if act == 2 else 0.0)
     assert lib.dp_conv2d_tc_caps(B, H, W, Cin, Cout, KS) & L.CAP_BN_BACKWARD
     npix = B * H * W
-    # unfused: raw gradient (+ an accumulated second gradient through the residual operand), then the masked reduction
-    graw = _conv(L, dy, wp, Cout, KS, res=res)
+    # unfused: raw gradient, then the masked reduction pass
+    graw = _conv(L, dy, wp, Cout, KS)
     nb = lib.dp_chan_reduce_blocks()
     part = torch.empty(nb, 2, Cout, device="cuda")
     L.check(lib.dp_chan_reduce(3 if act == 2 else 2, L.ptr(c), Cout, L.ptr(graw), Cout, None, 0, L.ptr(ss), npix, Cout,
@@ -111,7 +110,7 @@ def test_bn_backward_epilogue_matches_reduce_pass(pkg, B, H, W, Cin, Cout, KS, a
     gsz = lib.dp_conv2d_tc_grid(B, H, W, Cin, Cout, KS)
     st = torch.empty(gsz, 2, Cout, device="cuda")
     fuse = L.ConvFuse(None, 0, L.ptr(c), Cout, L.ptr(ss), act)
-    gout = _conv(L, dy, wp, Cout, KS, fuse=fuse, res=res, stats=st)
+    gout = _conv(L, dy, wp, Cout, KS, fuse=fuse, stats=st)
     torch.cuda.synchronize()
     assert torch.equal(gout, gref), float((gout.float() - gref.float()).abs().max())
     got, want = st.double().sum(0), part.double().sum(0)
