@@ -80,11 +80,13 @@ class GraphedTrainStep:
         pred = self.model(self.x).unsqueeze(1)
         total, out = util.combined_loss_device(pred, self.t, self.cfg, rgb=self.x if self.use_rgb else None)
         ops.side_enable(self.side_wgrad)          # weight gradients overlap the data-gradient chain on a second stream
+        ops._Side.reducer = self.red              # ... and are all-reduced bucket by bucket as they complete
         try:
             total.backward()
             ops.side_join()
         finally:
             ops.side_enable(False)
+            ops._Side.reducer = None
         self.red.reduce()
         self.opt.step()
         self.out = out

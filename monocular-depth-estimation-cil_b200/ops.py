@@ -129,6 +129,7 @@ class _Side:
     pending = []
     pending_bytes = 0
     limit = 6 << 30
+    reducer = None        # distributed.GradientAllReducer of the step being run (graphs.GraphedTrainStep sets it)
 
 
 def side_enable(flag):
@@ -157,7 +158,10 @@ def _on_side(weight, fn, keep):
     side.wait_stream(cur)
     with torch.cuda.stream(side):
         dw = fn()
-        if weight.grad is None:
+        red = _Side.reducer
+        if red is not None and red.side_grad(weight, dw):
+            pass                  # written into its bucket slice; the bucket's all-reduce starts when it is complete
+        elif weight.grad is None:
             weight.grad = dw
         else:
             weight.grad.add_(dw)
