@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--no-config5", action="store_true")
+    ap.add_argument("--overlap-h2d", action="store_true", help="next batch's H2D on a copy stream under the current replay")
     ap.add_argument("--profile-layers", action="store_true", help="print per-shape conv timings to stderr")
     ap.add_argument("--no-side-wgrad", action="store_true", help="keep weight gradients on the main stream")
     ap.add_argument("--torch-encoder", action="store_true", help="run the EfficientNet-Lite3 trunk through PyTorch/cuDNN")
@@ -132,18 +133,24 @@ def _timeit(fn, reps, barrier, dev, world, dist):
     return ms
 
 
-def _profile_traffic(name, build):
-    """`traffic` (DRAM bytes per launch) from a committed ncu --set full summary, only if it was captured from the
-    sources this library was built from (profiles/*.json carry the build id; tools/ncu_summary.py writes them)"""
+def _profile_traffic(name, files, index=0, kernel=None):
+    """`traffic` (DRAM bytes per launch) from a committed ncu --set full summary (tools/ncu_summary.py), paired with a
+    live timing only if the capture was taken from the same kernel sources: the summary carries the sha1 of every csrc
+    file, and the files the kernel is compiled from must match the library that is running."""
+    import depth_b200
     try:
         with open(os.path.join(ROOT, "profiles", name)) as f:
             cap = json.load(f)
     except Exception:
         return None, f"profiles/{name} not found"
-    if cap.get("build_id") != build:
-        return None, f"profiles/{name} was captured from build {cap.get('build_id')}, this library is {build}: not paired"
-    k = cap["launches"][0]
-    return int(k["dram_bytes_read"] + k["dram_bytes_write"]), f"profiles/{name} (dram__bytes_read.sum + dram__bytes_write.sum, one launch, build {build})"
+    now = depth_b200._lib.build_files()
+    stale = [f for f in files if cap.get("source_files", {}).get(f) != now.get(f)]
+    if stale or not now:
+        return None, f"profiles/{name} was captured from other sources ({', '.join(stale) or 'no build record'} changed): not paired"
+    ls = [k for k in cap["launches"] if kernel is None or kernel in k["kernel"]]
+    k = ls[index]
+    return int(k["dram_bytes_read"] + k["dram_bytes_write"]), \
+        f"profiles/{name} launch '{k['kernel'][:40]}' (dram__bytes_read.sum + dram__bytes_write.sum, one launch; sources unchanged since the capture)"
 
 
 def eval_kernel_leg(depth_b200, dev, rank, world, barrier, dist, hbm, build):
@@ -167,7 +174,7 @@ def eval_kernel_leg(depth_b200, dev, rank, world, barrier, dist, hbm, build):
     contract = {"si_rmse_rel_diff": abs(d[0] - e[0]) / abs(e[0]), "abs_rel_rel_diff": abs(d[1] - e[1]) / abs(e[1]),
                 "max_delta_fraction_diff": max(abs(x - y) for x, y in zip(d[2:], e[2:])),
                 "allowed": "1e-5 relative / 1e-4 (0.01 % of pixels)"}
-    traffic, tsrc = _profile_traffic("ncu_eval_lean_r2.json", build)
+    traffic, tsrc = _profile_traffic("ncu_kernels_r2.json", ["loss_metrics.cu", "tc.cuh", "common.cuh"], kernel="eval_stream_kernel")
 
     def roof(ms_):
         gbs = px * 8 / (ms_ / 1e3) / 1e9
@@ -365,7 +372,7 @@ def run_ours(a):
     xd, td = xh.to(dev), th.to(dev)
     # The whole step (forward, combined_loss, backward, NCCL gradient all-reduce, AdamW) is one CUDA graph.
     gstep = depth_b200.GraphedTrainStep(model, opt, cfg, xd, td, use_rgb=True, world=world, warmup=max(a.warmup, 3),
-                                        side_wgrad=not a.no_side_wgrad)
+                                        side_wgrad=not a.no_side_wgrad, overlap_h2d=a.overlap_h2d)
     red = gstep.red
 
     def step(x, t, read_loss):
@@ -494,7 +501,8 @@ def run_ours(a):
         alg_bytes = 2.0 * B * Ht * Wt * (cin_t + cout_t)
         traffic, tsrc = (None, "no capture for this shape")
         if (Ht, Wt, cin_t, cout_t, ks_t, B) == (448, 576, 64, 64, 3, 32):
-            traffic, tsrc = _profile_traffic("ncu_conv_64x64_r2.json", build)
+            # launch 4 of tools/ncu_kernels.py: conv 3x3 64->64 @448x576 (+stats), B = 32
+            traffic, tsrc = _profile_traffic("ncu_kernels_r2.json", ["conv_tc.cu", "tc.cuh", "bn_fuse.cuh", "common.cuh"], index=4)
         roof = {"bound": "tensor",
                 "kernel": f"conv_tc_kernel (tcgen05 implicit GEMM) {ks_t}x{ks_t} {cin_t}->{cout_t} @{Ht}x{Wt}, B={B}: the "
                           "shape with the largest share of the step (fusion-block convs and their data gradients)",

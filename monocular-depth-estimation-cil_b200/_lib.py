@@ -195,6 +195,16 @@ def build_id():
         return "unknown"
 
 
+def build_files():
+    """per-file source hashes of the library that was built"""
+    import json
+    try:
+        with open(os.path.join(_HERE, "build_files.json")) as f:
+            return json.load(f)
+    except OSError:
+        return {}
+
+
 def launch_count():
     return int(lib().dp_launch_count())
 

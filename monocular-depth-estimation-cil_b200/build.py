@@ -52,7 +52,21 @@ def build(verbose=False, force=False):
     build_probe(verbose)
     with open(os.path.join(HERE, "build_id.txt"), "w") as f:
         f.write(source_id() + "\n")
+    import json
+    with open(os.path.join(HERE, "build_files.json"), "w") as f:
+        json.dump(source_ids(), f, indent=1, sort_keys=True)
     return LIB
+
+
+def source_ids():
+    """per-file sha1 of the kernel sources (a capture stays valid for a kernel as long as ITS files are unchanged)"""
+    import hashlib
+    out = {}
+    for f in sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")) +
+                    glob.glob(os.path.join(HERE, "..", "include", "*.h"))):
+        with open(f, "rb") as fh:
+            out[os.path.basename(f)] = hashlib.sha1(fh.read()).hexdigest()[:12]
+    return out
 
 
 def source_id():

@@ -650,7 +650,7 @@ constexpr int kEvSlots = 2;                 // shared-memory slots = samples in 
 // moments sweep, so the exchange has two sweeps' time to complete and the producer stays two samples ahead.
 constexpr int kEvSlotsLean = 4, kEvLagLean = 2;
 constexpr int kEvCWLean = 14, kEvVPTLean = 2;   // 14 consumer warps x 2 float4 per chunk (measured: 28 x 1 -> 395, 14 x 2 -> 460, 7 x 4 -> 390 Gpx/s)
-constexpr int kEvPrefetch = 1;                  // samples of L2 prefetch beyond the slot ring (measured: 0 -> 398, 1 -> 404, 3 -> 390 Gpx/s)
+constexpr int kEvPrefetch = 0;                  // samples of L2 prefetch beyond the slot ring: off (measured 0 -> 398, 1 -> 404, 3 -> 390 Gpx/s, but ncu showed 17 % more DRAM reads with 1: prefetched lines evicted before use)
 // static shared memory the plan leaves room for: 2.4 KB in the instantiations with a compile-time threshold count
 // (1 or 3), 3.4 KB with the run-time count (count arrays sized for DP_MAX_THR)
 constexpr int kEvStaticFixed = 5120, kEvStaticRuntime = 6144;

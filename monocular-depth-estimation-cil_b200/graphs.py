@@ -29,7 +29,7 @@ class GraphedTrainStep:
         # only).  Measured end to end it ranged from +2 % to -7 % against plain main-stream copies across runs on one
         # GPU, and it doubled the step time at N = 4 with NCCL collectives captured in the graph (the H2D bandwidth
         # itself was a full 55 GB/s per rank), so the default is the predictable main-stream copy (+2.6 ms per step).
-        self._overlap_h2d = bool(overlap_h2d) and self.red.world == 1
+        self._overlap_h2d = bool(overlap_h2d)
         self._step = 0
         self._hout = [torch.empty(8, dtype=torch.float32).pin_memory() for _ in range(2)]
         self._done = [torch.cuda.Event(), torch.cuda.Event()]

@@ -45,7 +45,7 @@ def _world():
 class _Pass:
     """One fused moments pass over (pred, target[, rgb])."""
 
-    def __init__(self, pred, target, rgb, flags, eps):
+    def __init__(self, pred, target, rgb, flags, eps, sync_silog=True, sync_edge=True):
         lib = L.lib()
         # the kernels index every buffer with pred's (B, H, W): a smaller target / rgb would be read out of bounds
         # where the reference raises a shape / broadcast error
@@ -68,16 +68,17 @@ class _Pass:
         if flags & L.F_EDGE:
             self.mm = torch.empty(lib.dp_rgb_minmax_bytes() // 4, dtype=torch.float32, device=dev)
             L.check(lib.dp_rgb_gradmag_minmax(L.ptr(self.rgb), self.B, self.H, self.W, L.ptr(self.mm), L.stream()))
-            if _world() > 1:      # batch-global min / max (util.py:70): the partials are (min, max) pairs
+            if sync_edge and _world() > 1:      # batch-global min / max (util.py:70): the partials are (min, max) pairs
                 import torch.distributed as dist
-                sign = torch.tensor([1.0, -1.0], device=dev)
-                t = (self.mm.view(-1, 2) * sign).contiguous()
+                t = self.mm.view(-1, 2).clone()      # device-only arithmetic: the step is captured in a CUDA graph
+                t[:, 1].neg_()
                 dist.all_reduce(t, op=dist.ReduceOp.MIN)        # min of mins, min of negated maxes
-                self.mm.copy_((t * sign).view(-1))
+                t[:, 1].neg_()
+                self.mm.copy_(t.view(-1))
         L.check(lib.dp_depth_moments(L.ptr(self.p), L.ptr(self.t), L.ptr(self.rgb), L.ptr(self.mm), self.B, self.H,
                                      self.W, flags, self.eps, L.ptr(self.mom), L.ptr(self.ws), self.ws_bytes,
                                      L.stream()))
-        self.world = _world()
+        self.world = _world() if sync_silog else 1
         if self.world > 1 and (flags & L.F_SILOG):
             # batch-global SiLog moments (count, sum d, sum d^2 over the masked pixels of every rank's samples): the
             # combine / backward kernels add the per-sample rows, so the global sums go into row 0 and the rest is zero
@@ -119,7 +120,9 @@ class _LossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, pred, target, rgb, flags, eps, w_si, w_silog, vf, w_grad, beta, sqroot, slot):
-        ps = _Pass(pred, target, rgb, flags, eps)
+        # the batch-global exchanges are made for the terms that carry weight; a zero-weight term is only logged
+        # (main.py:85-88) and then reports this rank's shard
+        ps = _Pass(pred, target, rgb, flags, eps, sync_silog=w_silog != 0.0, sync_edge=beta != 0.0)
         out, per = ps.combine(w_si, w_silog, vf, w_grad, beta, sqroot, per_sample=bool(sqroot))
         ctx.ps, ctx.per, ctx.args, ctx.slot = ps, per, (w_si, w_silog, vf, w_grad, beta, sqroot), slot
         ctx.in_shape, ctx.in_dtype = pred.shape, pred.dtype

@@ -41,6 +41,7 @@ for r in data:
     })
 with open(os.path.join(ROOT, "monocular-depth-estimation-cil_b200", "build_id.txt")) as f:
     build = f.read().strip()
-json.dump({"build_id": build, "source": os.path.basename(rep), "command": "ncu --set full --clock-control none --import-source on",
+files = json.load(open(os.path.join(ROOT, "monocular-depth-estimation-cil_b200", "build_files.json")))
+json.dump({"build_id": build, "source_files": files, "source": os.path.basename(rep), "command": "ncu --set full --clock-control none --import-source on",
            "note": note, "launches": launches}, open(out, "w"), indent=1)
 print(out, build, len(launches), "launch(es)")
