@@ -109,6 +109,11 @@ int dp_delta_counts(const float* pred, const float* target, const double* moment
                     const float* thresholds, int nthr, int aligned, float eps_div, unsigned long long* counts,
                     void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+/* util.py:159-181 per_pixel_scale_invariant_loss: out[b][i] = (d_i - mean_b d)^2, d = log p - log t (no epsilon);
+ * `moments` from dp_depth_moments(flags = DP_F_SI, eps = 0).  pred, target, out: fp32 (B,H,W). */
+int dp_per_pixel_si(const float* pred, const float* target, const double* moments, int B, int H, int W, float* out,
+                    cudaStream_t stream);
+
 /* evaluation.py:157-166 for one batch: out[0]=SI-RMSE, out[1]=AbsRel, out[2+k]=delta_k */
 int dp_metrics_combine(const double* moments, const unsigned long long* counts, int B, int H, int W, int nthr,
                        float* out, cudaStream_t stream);

@@ -90,6 +90,7 @@ class _Sig:
     dp_delta_counts = (c_int, [P, P, P, c_int, c_int, c_int, ctypes.POINTER(c_float), c_int, c_int, c_float, P, P,
                                c_size_t, P])
     dp_metrics_combine = (c_int, [P, P, c_int, c_int, c_int, c_int, P, P])
+    dp_per_pixel_si = (c_int, [P, P, P, c_int, c_int, c_int, P, P])
     dp_eval_metrics_workspace = (c_size_t, [c_int, c_int, c_int])
     dp_eval_metrics_plan = (c_int, [ctypes.c_longlong, c_int, c_int, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int),
                                     ctypes.POINTER(c_int), ctypes.POINTER(c_size_t)])

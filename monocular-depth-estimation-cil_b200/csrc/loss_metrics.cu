@@ -1083,6 +1083,20 @@ __global__ void __launch_bounds__(256) eval_means_kernel(const double* __restric
   }
 }
 
+// util.py:159-181 per_pixel_scale_invariant_loss: out = (d - mean d)^2 with d = log p - log t (no epsilon) per image;
+// the mean comes from the moments pass (S1 of dp_depth_moments run with eps = 0).
+__global__ void __launch_bounds__(TPB) per_pixel_si_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                                           const double* __restrict__ mom, long long n, int B,
+                                                           float* __restrict__ out) {
+  const long long total = n * B;
+  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
+    const int b = (int)(i / n);
+    const float mean = (float)(mom[(size_t)b * NMOM + DP_M_S1] / (double)n);
+    const float d = logf(__ldg(pred + i)) - logf(__ldg(target + i));
+    out[i] = (d - mean) * (d - mean);
+  }
+}
+
 struct EvalPlan {
   bool ok;
   int G, ngroups, per;
@@ -1246,6 +1260,17 @@ int dp_delta_counts(const float* pred, const float* target, const double* moment
   DP_CHECK_LAUNCH("delta_counts_kernel");
   counts_finalize_kernel<<<B, 32, 0, stream>>>(a.partials, a.chunks, nthr, counts);
   DP_CHECK_LAUNCH("counts_finalize_kernel");
+  return DP_OK;
+}
+
+int dp_per_pixel_si(const float* pred, const float* target, const double* moments, int B, int H, int W, float* out,
+                    cudaStream_t stream) {
+  DP_CHECK_ARG(pred && target && moments && out && B > 0 && H > 0 && W > 0, "dp_per_pixel_si: bad arguments");
+  const long long n = (long long)H * W;
+  long long blocks = (n * B + TPB - 1) / TPB;
+  if (blocks > 8LL * kNumSMs) blocks = 8LL * kNumSMs;
+  per_pixel_si_kernel<<<(int)blocks, TPB, 0, stream>>>(pred, target, moments, n, B, out);
+  DP_CHECK_LAUNCH("per_pixel_si_kernel");
   return DP_OK;
 }
 

@@ -293,12 +293,20 @@ def evaluate_model_sums(outputs, targets):
 
 
 def per_pixel_scale_invariant_loss(pred, target):
-    """reference util.py:159-181 (visualisation only; single image): plain tensor algebra, not a hot path."""
+    """reference util.py:159-181 (visualisation; single image (H,W) or any (..., H, W) stack treated image by image):
+    (d - mean d)^2 with d = log pred - log target, no epsilon.  One moments pass for the per-image mean and one
+    elementwise kernel (dp_per_pixel_si)."""
     assert pred.shape == target.shape, \
         "Pred and target must have the same shape, got {} and {}".format(pred.shape, target.shape)
+    _check_cuda(pred, target)
     assert (pred > 0).all() and (target > 0).all(), "Pred and target must be positive"
-    d = torch.log(pred) - torch.log(target)
-    return (d - d.mean()) ** 2
+    p, t = _prep(pred), _prep(target)
+    H, W = p.shape[-2], p.shape[-1]
+    B = p.numel() // (H * W)
+    ps = _Pass(p.reshape(B, 1, H, W), t.reshape(B, 1, H, W), None, L.F_SI, 0.0)
+    out = torch.empty_like(p)
+    L.check(L.lib().dp_per_pixel_si(L.ptr(p), L.ptr(t), L.ptr(ps.mom), B, H, W, L.ptr(out), L.stream()))
+    return out
 
 
 def remove_module_prefix(state_dict):

@@ -121,6 +121,15 @@ def do_losses(ref_util):
             for k, v in g_ref.items():
                 small_store[f"{name}.grad_{k}"] = v.numpy()
         print("loss case", name, {k: round(v, 6) for k, v in r_ref.items()})
+    # M5 per_pixel_scale_invariant_loss (util.py:159-181): reference vs restatement on one positive image
+    gp = torch.Generator().manual_seed(4711)
+    t5 = torch.rand(48, 64, generator=gp) * 9.9 + 0.1
+    p5 = t5 * torch.exp(0.2 * torch.randn(48, 64, generator=gp)) * 1.3
+    m_ref, m_ora = ref_util.per_pixel_scale_invariant_loss(p5, t5), ol.per_pixel_scale_invariant_loss(p5, t5)
+    assert torch.equal(m_ref, m_ora), "per_pixel_scale_invariant_loss: oracle != reference"
+    gold["per_pixel_si"] = {"sum": float(m_ref.double().sum()), "max": float(m_ref.max())}
+    small_store["per_pixel_si.pred"], small_store["per_pixel_si.target"] = p5.numpy(), t5.numpy()
+    small_store["per_pixel_si.map"] = m_ref.numpy()
     # main.evaluate_model (main.py:254-392): run the REFERENCE's own function (imported with kornia / omegaconf / wandb
     # stubs) on an identity model over two batches whose prediction resolution differs from the target's, and require
     # the oracle's restatement to reproduce its dict; the inputs and the reference's dict are stored as golden vectors.

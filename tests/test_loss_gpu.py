@@ -296,3 +296,25 @@ def test_default_eval_arithmetic_within_contract(pkg, case):
         else:
             assert abs(lean[i] - exact[i]) <= 1e-5 * abs(exact[i]), (case, i, lean, exact)
     assert float((lean[2:] - exact[2:]).abs().max()) <= 1e-4, (case, lean, exact)
+
+
+def test_per_pixel_scale_invariant_loss(pkg):
+    """M5 (util.py:159-181): the per-pixel map against the oracle's restatement (pinned to the reference in
+    oracle/make_golden.py's loss cases), single image as the reference's visualiser calls it, 1e-5 of the map's maximum."""
+    g = torch.Generator().manual_seed(11)
+    t = torch.rand(448, 576, generator=g) * 9.9 + 0.1
+    p = t * torch.exp(0.2 * torch.randn(448, 576, generator=g)) * 1.3
+    got = pkg.per_pixel_scale_invariant_loss(p.cuda(), t.cuda()).cpu()
+    ref = ol.per_pixel_scale_invariant_loss(p, t)
+    assert got.shape == ref.shape
+    assert float((got - ref).abs().max()) <= 1e-5 * float(ref.max())
+    with pytest.raises(AssertionError):
+        pkg.per_pixel_scale_invariant_loss(-p.cuda(), t.cuda())
+    # the map the REFERENCE's own function produced (tests/golden, written by oracle/make_golden.py)
+    import os
+    import numpy as np
+    store = np.load(os.path.join(os.path.dirname(__file__), "golden", "loss_small_inputs.npz"))
+    got = pkg.per_pixel_scale_invariant_loss(torch.from_numpy(store["per_pixel_si.pred"]).cuda(),
+                                             torch.from_numpy(store["per_pixel_si.target"]).cuda()).cpu()
+    ref = torch.from_numpy(store["per_pixel_si.map"])
+    assert float((got - ref).abs().max()) <= 1e-5 * float(ref.max())
