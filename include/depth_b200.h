@@ -240,6 +240,14 @@ int dp_cast_bf16_to_f32(const void* src, float* dst, size_t n, cudaStream_t stre
  *   gather-form data gradient / transposed-conv forward: swap 1 flip 0;  transposed-conv data gradient: swap 0 flip 0 */
 int dp_pack_conv_weight(const float* w, int D0, int D1, int KH, int KW, int swap, int flip, void* dst, int ld,
                         cudaStream_t stream);
+/* the same for n weights in one launch: `descs_device` is a DEVICE array of n descriptors (fields as the arguments of
+ * dp_pack_conv_weight); blocks_per_weight 256-thread blocks stride over each weight. */
+typedef struct dp_pack_desc {
+  const void* src;      /* fp32 [D0][D1][KH][KW] */
+  void* dst;            /* bf16 [KH*KW][A][ld] */
+  int D0, D1, KH, KW, swap, flip, ld, pad_;
+} dp_pack_desc_t;
+int dp_pack_conv_weights_batched(const dp_pack_desc_t* descs_device, int n, int blocks_per_weight, cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Bandwidth-bound NHWC bf16 kernels (csrc/elementwise.cu)

@@ -122,6 +122,7 @@ class _Sig:
     dp_cast_f32_to_bf16 = (c_int, [P, P, c_size_t, P])
     dp_cast_bf16_to_f32 = (c_int, [P, P, c_size_t, P])
     dp_pack_conv_weight = (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P])
+    dp_pack_conv_weights_batched = (c_int, [P, c_int, c_int, P])
     dp_add_relu_bwd = (c_int, [P, P, P, P, c_size_t, P])
     dp_add_bf16 = (c_int, [P, P, P, P, c_size_t, P])
     dp_relu_bf16 = (c_int, [P, P, c_size_t, P])

@@ -87,9 +87,35 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int D0, int D1, 
   }
 }
 
+// All weight packs of a step in ONE launch (a train step needs ~230: forward and data-gradient layout of every
+// convolution; one tiny kernel each costs more in launch gaps than in work).  blockIdx.y = descriptor.
+__global__ void pack_weights_batched_kernel(const dp_pack_desc_t* __restrict__ descs) {
+  const dp_pack_desc_t d = descs[blockIdx.y];
+  const float* __restrict__ w = reinterpret_cast<const float*>(d.src);
+  bf16* __restrict__ dst = reinterpret_cast<bf16*>(d.dst);
+  const int taps = d.KH * d.KW;
+  const long long total = (long long)d.D0 * d.D1 * taps;
+  const int A = d.swap ? d.D1 : d.D0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % taps);
+    const int d1 = (int)((i / taps) % d.D1);
+    const int d0 = (int)(i / ((long long)taps * d.D1));
+    const int t = d.flip ? taps - 1 - tap : tap;
+    const int ai = d.swap ? d1 : d0, bi = d.swap ? d0 : d1;
+    dst[((size_t)t * A + ai) * d.ld + bi] = __float2bfloat16_rn(__ldg(w + i));
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+int dp_pack_conv_weights_batched(const dp_pack_desc_t* descs_device, int n, int blocks_per_weight, cudaStream_t stream) {
+  DP_CHECK_ARG(descs_device && n > 0 && n <= 65535 && blocks_per_weight > 0, "dp_pack_conv_weights_batched: bad arguments");
+  pack_weights_batched_kernel<<<dim3(blocks_per_weight, n), 256, 0, stream>>>(descs_device);
+  DP_CHECK_LAUNCH("pack_weights_batched_kernel");
+  return DP_OK;
+}
 
 int dp_nchw_f32_to_nhwc_bf16(const float* src, int B, int C, int H, int W, void* dst, long long dst_ld,
                              cudaStream_t stream) {

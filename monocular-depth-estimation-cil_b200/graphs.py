@@ -46,7 +46,7 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self._restore(snap)
-        ops.PACKS.store.clear()                      # weight re-packs must be part of the captured step
+        ops.PACKS.invalidate()                       # weight re-packs must be part of the captured step (one batched launch)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self._body()
@@ -77,6 +77,7 @@ class GraphedTrainStep:
 
     def _body(self):
         self.red.zero()
+        ops.PACKS.repack_all()                    # every weight pack of the step in one launch (no-op in the first step)
         pred = self.model(self.x).unsqueeze(1)
         total, out = util.combined_loss_device(pred, self.t, self.cfg, rgb=self.x if self.use_rgb else None)
         ops.side_enable(self.side_wgrad)          # weight gradients overlap the data-gradient chain on a second stream

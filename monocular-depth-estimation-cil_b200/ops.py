@@ -84,15 +84,24 @@ class _PackCache:
         """parameters changed behind autograd's back (graph replay, raw device writes)"""
         self.generation += 1
 
+    def _ver(self, w):
+        return (w._version, w.data_ptr(), tuple(w.shape), self.generation)
+
     def get(self, w, swap, flip):
         key = (id(w), swap, flip)
-        ver = (w._version, w.data_ptr(), tuple(w.shape), self.generation)
+        ver = self._ver(w)
         hit = self.store.get(key)
         if hit is not None and hit[0] == ver and hit[2]() is w:
             return hit[1]
         D0, D1, KH, KW = w.shape
         A, Bc = (D1, D0) if swap else (D0, D1)
-        dst = torch.empty(KH * KW, A, Bc, dtype=BF16, device=w.device)
+        # the pack buffer of a (weight, layout) pair is kept across refreshes: stable addresses let repack_all() refresh
+        # every pack of a step with one launch from a cached descriptor table
+        if hit is not None and hit[2]() is w and hit[1].shape == (KH * KW, A, Bc) and hit[1].device == w.device:
+            dst = hit[1]
+        else:
+            dst = torch.empty(KH * KW, A, Bc, dtype=BF16, device=w.device)
+            self._table = None
         src = w.detach()
         if src.dtype != torch.float32 or not src.is_contiguous():
             src = src.float().contiguous()
@@ -100,7 +109,40 @@ class _PackCache:
         self.store[key] = (ver, dst, weakref.ref(w))
         if len(self.store) > 4096:
             self.store.clear()
+            self._table = None
         return dst
+
+    _table = None
+
+    def repack_all(self):
+        """refresh every known pack (all weights a previous step asked for, in the layouts it asked for) with ONE launch;
+        the per-weight get() calls of the step that follows then hit the cache.  Used at the head of the captured train
+        step (graphs.GraphedTrainStep): ~230 tiny pack kernels become one."""
+        import struct
+        items = []
+        for key, (ver, dst, ref) in list(self.store.items()):
+            w = ref()
+            # parameters only: temporaries (e.g. the re-viewed weight of a non-overlapping transposed conv) come and go
+            if w is None or not w.is_leaf or not w.is_cuda or w.dtype != torch.float32 or not w.is_contiguous() \
+                    or w.dim() != 4:
+                continue
+            items.append((key, w, dst))
+        if not items:
+            return 0
+        sig = tuple((k, w.data_ptr(), d.data_ptr()) for k, w, d in items)
+        if self._table is None or self._table[0] != sig:
+            if torch.cuda.is_current_stream_capturing():
+                return 0          # the set of packs changed under capture: fall back to the per-weight packs
+            buf = bytearray()
+            for (wid, swap, flip), w, dst in items:
+                D0, D1, KH, KW = w.shape
+                buf += struct.pack("<QQ8i", w.data_ptr(), dst.data_ptr(), D0, D1, KH, KW, int(swap), int(flip), dst.shape[2], 0)
+            host = torch.frombuffer(buf, dtype=torch.uint8).clone().pin_memory()
+            self._table = (sig, host.to(items[0][1].device, non_blocking=False))
+        L.check(L.lib().dp_pack_conv_weights_batched(L.ptr(self._table[1]), len(items), 8, L.stream()))
+        for key, w, dst in items:
+            self.store[key] = (self._ver(w), dst, weakref.ref(w))
+        return len(items)
 
 
 PACKS = _PackCache()
