@@ -160,32 +160,32 @@ __global__ void __launch_bounds__(TPB, 2) dw_fwd_kernel(DwArgs a) {
 // ---- stride-1 forward / data gradient from a shared-memory tile -----------------------------------------------------
 // The register-window kernel above re-reads every input vector K times through L1 / L2 (10 loads per output at K = 5)
 // and unpacks it for every tap: ~250 instructions per output vector, 13 - 40 % of the HBM floor.  Here a persistent block
-// owns a channel chunk of CG groups (CG * 16 bytes per pixel) and walks 8 x TW output tiles.  The (8+K-1) x (TW+K-1) input
-// tile arrives by ONE TMA box load (zero fill outside the image = the conv padding and the tile overhang), double
-// buffered on mbarriers so the next tile is in flight while this one is computed.  A thread owns one channel group of a
-// 2-row x 4-column output patch: it reads each of the (2+K-1) x (4+K-1) input vectors of its patch from shared memory
-// once and unpacks it once (48 loads + unpacks for 8 outputs at K = 5 instead of 80 + 80), the taps come from shared
-// memory as warp-broadcast loads, the MACs are packed f32x2.  ~175 (K = 5) / ~70 (K = 3) instructions per output vector.
-// Two blocks per SM, one tile buffer each: while one block waits for its TMA box the other computes (the kernel is bound
-// by the FMA pipe - 100 packed FFMA2 per output vector at K = 5 - so what matters is keeping 16 warps issuing).
+// owns a channel chunk of CG groups (CG * 16 bytes per pixel) and walks TH x TW output tiles.  The (TH+K-1) x (TW+K-1)
+// input tile arrives by ONE TMA box load (zero fill outside the image = the conv padding and the tile overhang) into one
+// of two buffers, so the next tile is in flight while this one is computed.  A thread owns one channel group of an
+// R-row x XO-column output patch: it reads each of the (R+K-1) x (XO+K-1) input vectors of its patch from shared memory
+// once and unpacks it once, the taps come from shared memory ([tap][half][group][4] so the eight groups of a warp read
+// 128 contiguous bytes), the MACs are packed f32x2.  Two blocks per SM; the grid is the LARGEST multiple of the channel
+// chunks that fits the 2 x 148 resident slots - one block more and a second wave doubles the kernel's time.
 // output patch per thread: 4 rows x 2 columns at K = 3 (3 input vectors per output), 2 x 2 at K = 5 (9 per output; the
 // 4 x 2 patch needs 64 + 48 fp32 registers for accumulators and the unpacked row and spilled at 128 registers)
-constexpr int dt_r(int K) { return K == 3 ? 4 : 2; }
-constexpr int DT_TXO = 2;
+// (measured: 1 x 4 at K = 5 and 2 x 2 at K = 3 are within 2 % of these)
+struct DwPatch { int R, XO; };
+inline DwPatch dw_patch(int K) { return K == 3 ? DwPatch{4, 2} : DwPatch{2, 2}; }
 
-template <int K, int TW, int CG>
+template <int K, int TW, int CG, int DT_R, int DT_TXO>
 __global__ void __launch_bounds__(TPB, 2) dw_tile_kernel(const __grid_constant__ CUtensorMap tmx, DwArgs a) {
-  constexpr int DT_R = dt_r(K);
-  constexpr int QX = TW / DT_TXO;                            // column pairs per tile row
+  constexpr int QX = TW / DT_TXO;                            // patches per tile row
   constexpr int TH = DT_R * (TPB / CG) / QX;                 // output rows per tile
   static_assert(TH >= DT_R && (TPB / CG) % QX == 0, "thread layout");
   constexpr int IH = TH + K - 1, IW = TW + K - 1;
   constexpr int PXB = CG * 16;                               // bytes per pixel of the chunk
   constexpr uint32_t TILE_BYTES = (uint32_t)IH * IW * PXB;
+  constexpr uint32_t TILE_STRIDE = (TILE_BYTES + 127u) & ~127u;
   extern __shared__ __align__(128) unsigned char dsm[];
   unsigned char* tile = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dsm) + 127) & ~uintptr_t(127));
-  float* s_w = reinterpret_cast<float*>(tile + ((TILE_BYTES + 127u) & ~127u));   // [K*K][CG*8]
-  uint64_t* full = reinterpret_cast<uint64_t*>(s_w + K * K * CG * 8);
+  float* s_w = reinterpret_cast<float*>(tile + 2 * TILE_STRIDE);                  // [K*K][2][CG][4]
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_w + K * K * CG * 8);             // [2]
   const int C8 = a.C / 8;
   const int cg = threadIdx.x % CG, pt = threadIdx.x / CG;
   const int qx = pt % QX, ry = pt / QX;
@@ -195,30 +195,35 @@ __global__ void __launch_bounds__(TPB, 2) dw_tile_kernel(const __grid_constant__
   const int ntiles = a.B * tiles_y * tiles_x;
   for (int i = threadIdx.x; i < K * K * CG * 8; i += TPB) {
     const int tap = i / (CG * 8), cc = i - tap * (CG * 8);
+    const int g = cc >> 3, j = cc & 7;
     const int ch = blockIdx.y * CG * 8 + cc;
-    s_w[i] = ch < a.C ? __ldg(a.w + (size_t)tap * a.C + ch) : 0.f;
+    s_w[tap * (CG * 8) + (j >> 2) * (CG * 4) + g * 4 + (j & 3)] = ch < a.C ? __ldg(a.w + (size_t)tap * a.C + ch) : 0.f;
   }
   if (threadIdx.x == 0) {
     tc::mbar_init(full, 1);
+    tc::mbar_init(full + 1, 1);
     tc::fence_barrier_init();
     tc::prefetch_tmap(&tmx);
   }
   __syncthreads();
-  auto issue = [&](int t) {                     // thread 0: one box load = the whole input tile of output tile t
+  auto issue = [&](int t, int buf) {            // thread 0: one box load = the whole input tile of output tile t
     const int tx = t % tiles_x, r = t / tiles_x;
     const int ty = r % tiles_y, b = r / tiles_y;
-    tc::mbar_expect_tx(full, TILE_BYTES);
-    tc::tma_load_4d(tile, &tmx, full, blockIdx.y * CG * 8, tx * TW - a.pad_l, ty * TH - a.pad_t, b);
+    tc::mbar_expect_tx(full + buf, TILE_BYTES);
+    tc::tma_load_4d(tile + buf * TILE_STRIDE, &tmx, full + buf, blockIdx.y * CG * 8, tx * TW - a.pad_l, ty * TH - a.pad_t, b);
   };
-  if (threadIdx.x == 0 && (int)blockIdx.x < ntiles) issue(blockIdx.x);
+  if (threadIdx.x == 0 && (int)blockIdx.x < ntiles) issue(blockIdx.x, 0);
   float st_s[8], st_q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { st_s[j] = 0.f; st_q[j] = 0.f; }
-  const uint32_t w_base = tc::smem_u32(s_w) + (uint32_t)cg * 32u;
-  const uint32_t tb = tc::smem_u32(tile) + (uint32_t)((DT_R * ry) * IW + DT_TXO * qx) * PXB + (uint32_t)cg * 16u;
+  const uint32_t w_base = tc::smem_u32(s_w) + (uint32_t)cg * 16u;
+  const uint32_t tb0 = tc::smem_u32(tile) + (uint32_t)((DT_R * ry) * IW + DT_TXO * qx) * PXB + (uint32_t)cg * 16u;
   int it = 0;
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-    tc::mbar_wait(full, it & 1);
+    // the other buffer was last read in iteration it - 1, and every thread is past that iteration's barrier
+    if (threadIdx.x == 0 && t + (int)gridDim.x < ntiles) issue(t + gridDim.x, (it + 1) & 1);
+    tc::mbar_wait(full + (it & 1), (it >> 1) & 1);
+    const uint32_t tb = tb0 + (uint32_t)(it & 1) * TILE_STRIDE;
     const int tx = t % tiles_x, rr = t / tiles_x;
     const int ty = rr % tiles_y, b = rr / tiles_y;
     float2 acc[DT_R][DT_TXO][4];
@@ -250,7 +255,7 @@ __global__ void __launch_bounds__(TPB, 2) dw_tile_kernel(const __grid_constant__
           float2 w2[4];
           const uint32_t wa = w_base + (uint32_t)((ky * K + kx) * CG * 8) * 4u;
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w2[0].x), "=f"(w2[0].y), "=f"(w2[1].x), "=f"(w2[1].y) : "r"(wa));
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w2[2].x), "=f"(w2[2].y), "=f"(w2[3].x), "=f"(w2[3].y) : "r"(wa + 16u));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w2[2].x), "=f"(w2[2].y), "=f"(w2[3].x), "=f"(w2[3].y) : "r"(wa + (uint32_t)(CG * 16)));
 #pragma unroll
           for (int q = 0; q < DT_TXO; ++q)
 #pragma unroll
@@ -258,9 +263,8 @@ __global__ void __launch_bounds__(TPB, 2) dw_tile_kernel(const __grid_constant__
         }
       }
     }
-    // every thread is past its reads of the tile: fetch the next one while the results are packed and stored
+    // every thread is past its reads of this buffer: the next iteration may refill it
     __syncthreads();
-    if (threadIdx.x == 0 && t + (int)gridDim.x < ntiles) issue(t + gridDim.x);
     if (chan_ok) {
 #pragma unroll
       for (int r = 0; r < DT_R; ++r) {
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(TPB, 2) dw_tile_kernel(const __grid_constant__
     }
   }
   if (a.stats) {
-    // deterministic block reduction over the pixel threads of each channel group (the tile buffer is free now)
+    // deterministic block reduction over the pixel threads of each channel group (the tile buffers are free now)
     __syncthreads();
     float* s_red = reinterpret_cast<float*>(tile);
 #pragma unroll
@@ -308,23 +312,24 @@ __global__ void __launch_bounds__(TPB, 2) dw_tile_kernel(const __grid_constant__
   }
 }
 
-// tile geometry of the stride-1 path: output tile 8 x TW, CG channel groups per block
-struct DwTilePlan { int TW, CG, TH, ny, nx; };
+// tile geometry of the stride-1 path: output tile TH x TW, CG channel groups per block
+struct DwTilePlan { int TW, CG, TH, ny, nx, R, XO; };
 inline DwTilePlan dw_tile_plan(int B, int Ho, int Wo, int C, int K) {
-  // candidates (TW, CG) -> TH = R * (256 / CG) / (TW / 2) with R = 4 (K = 3) or 2 (K = 5)
+  // candidates (TW, CG) -> TH = R * (256 / CG) / (TW / XO)
   // Pick the one that computes the fewest padded output vectors (tile overhang in x / y, channel-chunk overhang).
   const int cand[3][2] = {{16, 8}, {16, 16}, {32, 8}};
+  const DwPatch pp = dw_patch(K);
   DwTilePlan best{};
   long long best_cost = -1;
   for (int i = 0; i < 3; ++i) {
     DwTilePlan p;
-    p.TW = cand[i][0]; p.CG = cand[i][1];
-    p.TH = dt_r(K) * (TPB / p.CG) / (p.TW / DT_TXO);
+    p.TW = cand[i][0]; p.CG = cand[i][1]; p.R = pp.R; p.XO = pp.XO;
+    p.TH = pp.R * (TPB / p.CG) / (p.TW / pp.XO);
     p.ny = (C / 8 + p.CG - 1) / p.CG;
     const long long tx = (Wo + p.TW - 1) / p.TW, ty = (Ho + p.TH - 1) / p.TH;
     const long long cost = tx * p.TW * ty * p.TH * (long long)p.ny * p.CG;
     const long long ntiles = (long long)B * tx * ty;
-    long long nx = (2LL * kNumSMs + p.ny - 1) / p.ny;          // two blocks per SM
+    long long nx = (2LL * kNumSMs) / p.ny;                      // two blocks per SM, never a second wave
     if (nx > ntiles) nx = ntiles;
     p.nx = (int)(nx < 1 ? 1 : nx);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = p; }
@@ -456,6 +461,132 @@ __global__ void __launch_bounds__(TPB) dw_wgrad_kernel(const bf16* __restrict__ 
   }
 }
 
+// ---- stride-1 weight gradient from shared-memory tiles ------------------------------------------------------------
+// The kernel above reads dy K times and x ~K times through L1 / L2 and multiplies with scalar FMAs.  Here a persistent
+// block owns a chunk of WT_CG channel groups and walks TH x 8 output tiles: the dy tile and the (TH+K-1) x (8+K-1) input
+// tile under it arrive as two TMA boxes (zero fill outside either image: out-of-range products vanish, no bounds tests),
+// double buffered.  thread = (channel group, kernel row ky, row slot): it walks its output rows with a K-wide sliding
+// window of unpacked input vectors - per output pixel one dy vector, one new input vector, K x 4 packed f32x2 MACs into
+// the K x 8 accumulators it keeps for the whole launch.  partial[block][tap][c] is folded by dw_wgrad_reduce_kernel.
+constexpr int WT_CG = 8, WT_TW = 8;
+constexpr int wt_th(int K) { return K == 3 ? 10 : 12; }
+
+template <int K>
+__global__ void __launch_bounds__(TPB, 2) dw_wgrad_tile_kernel(const __grid_constant__ CUtensorMap tmx,
+                                                               const __grid_constant__ CUtensorMap tmg, int B, int Ho, int Wo,
+                                                               int C, int pad_t, int pad_l, float* __restrict__ partial) {
+  constexpr int CG = WT_CG, TW = WT_TW, TH = wt_th(K);
+  constexpr int NSLOT = (TPB / CG) / K;                      // row slots: 10 (K = 3) / 6 (K = 5)
+  static_assert(TH % NSLOT == 0, "rows per slot");
+  constexpr int IH = TH + K - 1, IW = TW + K - 1;
+  constexpr int PXB = CG * 16;
+  constexpr uint32_t X_BYTES = (uint32_t)IH * IW * PXB, G_BYTES = (uint32_t)TH * TW * PXB;
+  constexpr uint32_t X_STRIDE = (X_BYTES + 127u) & ~127u, BUF_STRIDE = X_STRIDE + ((G_BYTES + 127u) & ~127u);
+  static_assert(2 * BUF_STRIDE >= (uint32_t)TPB * K * 8 * 4, "reduction scratch fits the tile buffers");
+  extern __shared__ __align__(128) unsigned char dsm[];
+  unsigned char* tile = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dsm) + 127) & ~uintptr_t(127));
+  uint64_t* full = reinterpret_cast<uint64_t*>(tile + 2 * BUF_STRIDE);
+  const int C8 = C / 8;
+  const int cg = threadIdx.x % CG, pt = threadIdx.x / CG;
+  const int ky = pt % K, slot = pt / K;
+  const bool active = slot < NSLOT;
+  const int c8 = blockIdx.y * CG + cg;
+  const int tiles_x = (Wo + TW - 1) / TW, tiles_y = (Ho + TH - 1) / TH;
+  const int ntiles = B * tiles_y * tiles_x;
+  if (threadIdx.x == 0) {
+    tc::mbar_init(full, 1);
+    tc::mbar_init(full + 1, 1);
+    tc::fence_barrier_init();
+    tc::prefetch_tmap(&tmx);
+    tc::prefetch_tmap(&tmg);
+  }
+  __syncthreads();
+  auto issue = [&](int t, int buf) {
+    const int tx = t % tiles_x, r = t / tiles_x;
+    const int ty = r % tiles_y, b = r / tiles_y;
+    tc::mbar_expect_tx(full + buf, X_BYTES + G_BYTES);
+    tc::tma_load_4d(tile + buf * BUF_STRIDE, &tmx, full + buf, blockIdx.y * CG * 8, tx * TW - pad_l, ty * TH - pad_t, b);
+    tc::tma_load_4d(tile + buf * BUF_STRIDE + X_STRIDE, &tmg, full + buf, blockIdx.y * CG * 8, tx * TW, ty * TH, b);
+  };
+  if (threadIdx.x == 0 && (int)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+  float2 acc[K][4];
+#pragma unroll
+  for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[kx][j] = make_float2(0.f, 0.f);
+  const uint32_t tb0 = tc::smem_u32(tile) + (uint32_t)cg * 16u;
+  int it = 0;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    if (threadIdx.x == 0 && t + (int)gridDim.x < ntiles) issue(t + gridDim.x, (it + 1) & 1);
+    tc::mbar_wait(full + (it & 1), (it >> 1) & 1);
+    if (active) {
+      const uint32_t xb = tb0 + (uint32_t)(it & 1) * BUF_STRIDE;
+      const uint32_t gb = xb + X_STRIDE;
+#pragma unroll 1
+      for (int oy = slot; oy < TH; oy += NSLOT) {
+        const uint32_t xrow = xb + (uint32_t)((oy + ky) * IW) * PXB;
+        const uint32_t grow = gb + (uint32_t)(oy * TW) * PXB;
+        float2 win[K][4];                          // sliding window of unpacked input vectors (indices are compile-time)
+        auto ldv = [&](uint32_t addr, float2 (&v)[4]) {
+          uint32_t u0, u1, u2, u3;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u0), "=r"(u1), "=r"(u2), "=r"(u3) : "r"(addr));
+          const uint32_t uw[4] = {u0, u1, u2, u3};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = make_float2(__uint_as_float(uw[j] << 16), __uint_as_float(uw[j] & 0xffff0000u));
+        };
+#pragma unroll
+        for (int c = 0; c < K - 1; ++c) ldv(xrow + (uint32_t)c * PXB, win[c]);
+#pragma unroll
+        for (int ox = 0; ox < TW; ++ox) {
+          ldv(xrow + (uint32_t)(ox + K - 1) * PXB, win[(ox + K - 1) % K]);
+          float2 g[4];
+          ldv(grow + (uint32_t)ox * PXB, g);
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[kx][j] = __ffma2_rn(g[j], win[(ox + kx) % K][j], acc[kx][j]);
+        }
+      }
+    }
+    __syncthreads();                               // this buffer may be refilled by the next iteration's issue
+  }
+  // fixed-order fold over the row slots, one (channel group, ky) row per thread of the first K * CG threads
+  float* s_acc = reinterpret_cast<float*>(tile);   // [TPB][K*8]
+#pragma unroll
+  for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      s_acc[threadIdx.x * (K * 8) + kx * 8 + 2 * j] = acc[kx][j].x;
+      s_acc[threadIdx.x * (K * 8) + kx * 8 + 2 * j + 1] = acc[kx][j].y;
+    }
+  __syncthreads();
+  if (slot == 0 && c8 < C8) {
+#pragma unroll 1
+    for (int kx = 0; kx < K; ++kx) {
+      float sum[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum[j] = 0.f;
+      for (int sl = 0; sl < NSLOT; ++sl) {
+        const int tt = sl * (K * CG) + threadIdx.x;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum[j] += s_acc[tt * (K * 8) + kx * 8 + j];
+      }
+      float* dst = partial + ((size_t)blockIdx.x * K * K + ky * K + kx) * C + c8 * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dst[j] = sum[j];
+    }
+  }
+}
+
+// blocks along x of the tile weight-gradient kernel (= rows of its partials buffer)
+inline int wt_blocks(int B, int Ho, int Wo, int C, int K) {
+  const int ny = (C / 8 + WT_CG - 1) / WT_CG;
+  const long long ntiles = (long long)B * ((Ho + wt_th(K) - 1) / wt_th(K)) * ((Wo + WT_TW - 1) / WT_TW);
+  long long nx = (2LL * kNumSMs) / ny;
+  if (nx > ntiles) nx = ntiles;
+  return (int)(nx < 1 ? 1 : nx);
+}
+
 // grad[c][ky][kx] (OIHW with I = 1) (+)= sum_chunks partial[chunk][tap][c]
 // block = 32 consecutive (tap, c) columns x 32 chunk lanes: coalesced rows of the partials, fixed-order fp64 fold
 __global__ void __launch_bounds__(1024) dw_wgrad_reduce_kernel(const float* __restrict__ partial, int nchunks, int taps, int C,
@@ -538,21 +669,21 @@ int dp_dwconv_fwd(const void* x, long long x_ld, int B, int Hi, int Wi, int C, c
     int rc = dp_make_tmap_bf16(&tm, x, 4, dims, str, box, nullptr, 0 /* no swizzle: a thread group reads whole pixel rows */);
     if (rc) return rc;
     const size_t tile = (((size_t)(p.TH + K - 1) * (p.TW + K - 1) * p.CG * 16) + 127) & ~size_t(127);
-    size_t smem = 128 + tile + (size_t)K * K * p.CG * 8 * 4 + 64;
+    size_t smem = 128 + 2 * tile + (size_t)K * K * p.CG * 8 * 4 + 64;
     if (smem < 128 + (size_t)TPB * 16 * 4) smem = 128 + (size_t)TPB * 16 * 4;
     dim3 grid(p.nx, p.ny);
-#define DP_DW_TILE(KK, TWW, CGG)                                                                          \
+#define DP_DW_TILE(KK, TWW, CGG, RR, XX)                                                                  \
     do {                                                                                                  \
-      cudaError_t e = cudaFuncSetAttribute(dw_tile_kernel<KK, TWW, CGG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      cudaError_t e = cudaFuncSetAttribute(dw_tile_kernel<KK, TWW, CGG, RR, XX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       if (e != cudaSuccess) return dp_set_error(DP_ERR_CUDA, "dw_tile_kernel smem %zu: %s", smem, cudaGetErrorString(e));       \
-      dw_tile_kernel<KK, TWW, CGG><<<grid, TPB, smem, stream>>>(tm, a);                                     \
+      dw_tile_kernel<KK, TWW, CGG, RR, XX><<<grid, TPB, smem, stream>>>(tm, a);                             \
     } while (0)
-    if (K == 3 && p.TW == 32) DP_DW_TILE(3, 32, 8);
-    else if (K == 3 && p.CG == 16) DP_DW_TILE(3, 16, 16);
-    else if (K == 3) DP_DW_TILE(3, 16, 8);
-    else if (p.TW == 32) DP_DW_TILE(5, 32, 8);
-    else if (p.CG == 16) DP_DW_TILE(5, 16, 16);
-    else DP_DW_TILE(5, 16, 8);
+    if (K == 3 && p.TW == 32) DP_DW_TILE(3, 32, 8, 4, 2);
+    else if (K == 3 && p.CG == 16) DP_DW_TILE(3, 16, 16, 4, 2);
+    else if (K == 3) DP_DW_TILE(3, 16, 8, 4, 2);
+    else if (p.TW == 32) DP_DW_TILE(5, 32, 8, 2, 2);
+    else if (p.CG == 16) DP_DW_TILE(5, 16, 16, 2, 2);
+    else DP_DW_TILE(5, 16, 8, 2, 2);
 #undef DP_DW_TILE
     DP_CHECK_LAUNCH("dw_tile_kernel");
     return DP_OK;
@@ -583,7 +714,9 @@ int dp_dwconv_dgrad_s2(const void* dy, long long dy_ld, int B, int Ho, int Wo, i
 }
 
 size_t dp_dwconv_wgrad_workspace(int B, int Ho, int Wo, int C, int K) {
-  return (size_t)wg_chunks(B, Ho, Wo, C) * K * K * C * sizeof(float);
+  int n = wg_chunks(B, Ho, Wo, C);
+  if (K == 3 || K == 5) { const int t = wt_blocks(B, Ho, Wo, C, K); if (t > n) n = t; }
+  return (size_t)n * K * K * C * sizeof(float);
 }
 
 /* weight gradient of the depthwise convolution: grad (fp32, [C][1][K][K]) (+)= sum_p dy[p][c] * x[tap(p)][c] */
@@ -594,10 +727,43 @@ int dp_dwconv_wgrad(const void* x, long long x_ld, int B, int Hi, int Wi, int C,
   DP_CHECK_ARG((K == 3 || K == 5) && (stride == 1 || stride == 2), "dp_dwconv_wgrad: K %d stride %d", K, stride);
   if (workspace_bytes < dp_dwconv_wgrad_workspace(B, Ho, Wo, C, K))
     return dp_set_error(DP_ERR_WORKSPACE, "dp_dwconv_wgrad: workspace too small");
+  float* partial = reinterpret_cast<float*>(workspace);
+  if (stride == 1 && x_ld % 8 == 0 && dy_ld % 8 == 0) {
+    const int TH = wt_th(K);
+    CUtensorMap tmx, tmg;
+    const uint64_t xd[4] = {(uint64_t)C, (uint64_t)Wi, (uint64_t)Hi, (uint64_t)B};
+    const uint64_t xs[3] = {(uint64_t)x_ld * 2, (uint64_t)Wi * x_ld * 2, (uint64_t)Hi * Wi * x_ld * 2};
+    const uint32_t xbox[4] = {(uint32_t)(WT_CG * 8), (uint32_t)(WT_TW + K - 1), (uint32_t)(TH + K - 1), 1};
+    int rc = dp_make_tmap_bf16(&tmx, x, 4, xd, xs, xbox, nullptr, 0);
+    if (rc) return rc;
+    const uint64_t gd[4] = {(uint64_t)C, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)B};
+    const uint64_t gs[3] = {(uint64_t)dy_ld * 2, (uint64_t)Wo * dy_ld * 2, (uint64_t)Ho * Wo * dy_ld * 2};
+    const uint32_t gbox[4] = {(uint32_t)(WT_CG * 8), (uint32_t)WT_TW, (uint32_t)TH, 1};
+    rc = dp_make_tmap_bf16(&tmg, dy, 4, gd, gs, gbox, nullptr, 0);
+    if (rc) return rc;
+    const size_t xb = (((size_t)(TH + K - 1) * (WT_TW + K - 1) * WT_CG * 16) + 127) & ~size_t(127);
+    const size_t gbz = (((size_t)TH * WT_TW * WT_CG * 16) + 127) & ~size_t(127);
+    const size_t smem = 128 + 2 * (xb + gbz) + 64;
+    const int nx = wt_blocks(B, Ho, Wo, C, K);
+    dim3 grid(nx, (C / 8 + WT_CG - 1) / WT_CG);
+    cudaError_t e;
+    if (K == 3) {
+      e = cudaFuncSetAttribute(dw_wgrad_tile_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return dp_set_error(DP_ERR_CUDA, "dw_wgrad_tile_kernel smem %zu: %s", smem, cudaGetErrorString(e));
+      dw_wgrad_tile_kernel<3><<<grid, TPB, smem, stream>>>(tmx, tmg, B, Ho, Wo, C, pad_t, pad_l, partial);
+    } else {
+      e = cudaFuncSetAttribute(dw_wgrad_tile_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return dp_set_error(DP_ERR_CUDA, "dw_wgrad_tile_kernel smem %zu: %s", smem, cudaGetErrorString(e));
+      dw_wgrad_tile_kernel<5><<<grid, TPB, smem, stream>>>(tmx, tmg, B, Ho, Wo, C, pad_t, pad_l, partial);
+    }
+    DP_CHECK_LAUNCH("dw_wgrad_tile_kernel");
+    dw_wgrad_reduce_kernel<<<dp::ceil_div(K * K * C, 32), 1024, 0, stream>>>(partial, nx, K * K, C, grad, accumulate);
+    DP_CHECK_LAUNCH("dw_wgrad_reduce_kernel");
+    return DP_OK;
+  }
   const int nchunks = wg_chunks(B, Ho, Wo, C);
   const int C8 = C / 8;
   dim3 grid((C8 + WG_C8B - 1) / WG_C8B, nchunks);
-  float* partial = reinterpret_cast<float*>(workspace);
   const size_t smem = (size_t)TPB * K * 8 * sizeof(float);
   const bf16* xb = reinterpret_cast<const bf16*>(x);
   const bf16* gb = reinterpret_cast<const bf16*>(dy);

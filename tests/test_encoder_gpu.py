@@ -30,7 +30,9 @@ def close(a, b, rel=2 ** -7, abs_frac=4e-3):
 
 @pytest.mark.parametrize("B,C,H,W,K,S,pad", [
     (2, 32, 20, 28, 3, 1, 1), (2, 144, 31, 45, 3, 2, 1), (1, 192, 28, 37, 5, 2, 2), (1, 816, 14, 18, 5, 1, 2),
-    (1, 1392, 7, 9, 3, 1, 1), (2, 48, 16, 19, 5, 1, 2), (1, 24, 33, 18, 3, 2, 0)])
+    (1, 1392, 7, 9, 3, 1, 1), (2, 48, 16, 19, 5, 1, 2), (1, 24, 33, 18, 3, 2, 0),
+    # several tiles per persistent block (both tile buffers, both barrier phases), ragged tile borders
+    (4, 288, 56, 72, 5, 1, 2), (4, 192, 61, 75, 3, 1, 1), (8, 40, 45, 37, 5, 1, 2)])
 def test_depthwise_fwd_bwd_stats(pkg, B, C, H, W, K, S, pad):
     from depth_b200 import ops
     x = rnd(B, C, H, W, seed=C + K)

@@ -39,8 +39,12 @@ for (B, H, W, C, K, S) in SHAPES:
         e.record(); torch.cuda.synchronize()
         return s.elapsed_time(e) / reps * 1e3
     tf = t(fwd)
-    def fb():
-        yy = fwd(); torch.autograd.grad(yy, (x, w), g)
-    tb = t(fb) - tf
+    def fbx():
+        yy = fwd(); torch.autograd.grad(yy, (x,), g)
+    def fbw():
+        yy = fwd(); torch.autograd.grad(yy, (w,), g)
+    tdx = t(fbx) - tf
+    tdw = t(fbw) - tf
     by = 2.0 * B * (H * W + Ho * Wo) * C
-    print(f"dw k{K} s{S} {H}x{W}x{C}: fwd {tf:7.1f} us (floor {by / HBM * 1e6:5.1f})  bwd(dgrad+wgrad) {tb:7.1f} us (floor {2 * by / HBM * 1e6:5.1f})")
+    print(f"dw k{K} s{S} {H}x{W}x{C}: fwd {tf:7.1f} us (floor {by / HBM * 1e6:5.1f})  dgrad {tdx:7.1f} us  wgrad {tdw:7.1f} us "
+          f"(floor {by / HBM * 1e6:5.1f} each)", flush=True)
