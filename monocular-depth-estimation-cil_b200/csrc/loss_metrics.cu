@@ -649,7 +649,7 @@ constexpr int kEvSlots = 2;                 // shared-memory slots = samples in 
 // per 7 us is 55 % of an SM's HBM share.  It therefore runs with four smaller slots and classifies TWO samples behind the
 // moments sweep, so the exchange has two sweeps' time to complete and the producer stays two samples ahead.
 constexpr int kEvSlotsLean = 4, kEvLagLean = 2;
-constexpr int kEvCWLean = 14, kEvVPTLean = 2;   // 14 consumer warps x 2 float4 per chunk (measured: 28 x 1 -> 395, 14 x 2 -> 460, 7 x 4 -> 390 Gpx/s)
+constexpr int kEvCWLean = 14, kEvVPTLean = 4;   // 14 consumer warps x 4 float4 per chunk = one chunk per slice at 448x576 (measured: 28 x 1 -> 395, 14 x 2 -> 470, 14 x 4 -> 480, 7 x 4 -> 390 Gpx/s)
 constexpr int kEvPrefetch = 0;                  // samples of L2 prefetch beyond the slot ring: off (measured 0 -> 398, 1 -> 404, 3 -> 390 Gpx/s, but ncu showed 17 % more DRAM reads with 1: prefetched lines evicted before use)
 // static shared memory the plan leaves room for: 2.4 KB in the instantiations with a compile-time threshold count
 // (1 or 3), 3.4 KB with the run-time count (count arrays sized for DP_MAX_THR)
@@ -815,13 +815,13 @@ __device__ __forceinline__ void delta_px_generic(float al, float t, const float*
 // whose pixel work is down to ~36 instructions - runs 14 fatter warps (two float4 per chunk) instead of 28.
 template <bool FAST, bool ONEDIV, int NT, bool LEAN = false, int NS_ = kEvSlots, int LAG_ = 1, int CW = kEvCW, int VPT = 1>
 __global__ void __launch_bounds__((CW + 2) * 32, 1) eval_stream_kernel(EvsArgs a) {
-  static_assert(CW * VPT * 128 == kEvChunkPx, "chunk size is fixed");
+  static_assert(CW * VPT * 128 % kEvChunkPx == 0, "chunk size is a multiple of the plan's unit");
   constexpr int CT = CW * 32;                      // consumer threads
   constexpr int NS = NS_;
   constexpr int LAG = LAG_;                        // sweep 2 runs LAG samples behind sweep 1
   constexpr int RB = LAG + 1;                      // ring of per-sample reduction / scale buffers
   constexpr int NTS = NT ? NT : DP_MAX_THR;
-  constexpr int CH = kEvChunkPx;
+  constexpr int CH = CW * VPT * 128;             // pixels per chunk: VPT float4 of each operand per consumer thread
   extern __shared__ __align__(128) unsigned char ev_smem[];
   __shared__ uint64_t full[NS][kEvMaxChunks], empty[NS][kEvMaxChunks];
   __shared__ uint64_t red_full[RB], scale_full[RB];
@@ -1106,7 +1106,8 @@ struct EvalPlan {
 // Pure function of the shape and of the device's shared memory per SM / SM count, shared by the workspace query and
 // the launch: one CTA per SM, kEvSlots slices resident per CTA, and the CTAs-per-sample count G that wastes the fewest
 // thread slots (slices that are whole chunks) and SMs (groups * G close to the SM count).
-inline EvalPlan eval_plan_for(long long n, int B, int smem_sm, int sms, int nthr, int slots = kEvSlots) {
+inline EvalPlan eval_plan_for(long long n, int B, int smem_sm, int sms, int nthr, int slots = kEvSlots,
+                              int chunk_px = kEvChunkPx) {
   EvalPlan p{};
   if (n % 4 != 0 || n <= 0 || B <= 0 || sms <= 0) return p;
   const long long budget = ((long long)smem_sm - 1024 - eval_static_allowance(nthr)) / slots;   // bytes per slot
@@ -1116,11 +1117,11 @@ inline EvalPlan eval_plan_for(long long n, int B, int smem_sm, int sms, int nthr
   for (long long G = gmin; G <= sms && G < gmin + 32; ++G) {
     long long per = (n + G - 1) / G;
     per = (per + 3) & ~3LL;
-    const long long nch = (per + kEvChunkPx - 1) / kEvChunkPx;
+    const long long nch = (per + chunk_px - 1) / chunk_px;
     if (per * 8 > budget || nch > kEvMaxChunks) continue;
     long long groups = sms / G;
     if (groups > B) groups = B;
-    const double eff = (double)n / (double)(nch * kEvChunkPx * G) * (double)(groups * G) / (double)sms;
+    const double eff = (double)n / (double)(nch * chunk_px * G) * (double)(groups * G) / (double)sms;
     if (eff > best + 1e-9) {
       best = eff;
       p.G = (int)G; p.per = (int)per; p.ngroups = (int)groups;
@@ -1132,12 +1133,12 @@ inline EvalPlan eval_plan_for(long long n, int B, int smem_sm, int sms, int nthr
   return p;
 }
 
-inline EvalPlan eval_plan(long long n, int B, int nthr, int slots = kEvSlots) {
+inline EvalPlan eval_plan(long long n, int B, int nthr, int slots = kEvSlots, int chunk_px = kEvChunkPx) {
   int smem_sm = 0, sms = 0, dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return EvalPlan{};
   if (cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) != cudaSuccess) return EvalPlan{};
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return EvalPlan{};
-  return eval_plan_for(n, B, smem_sm, sms, nthr, slots);
+  return eval_plan_for(n, B, smem_sm, sms, nthr, slots, chunk_px);
 }
 
 inline size_t eval_ws_ll_bytes(int B, int G) { return (((size_t)B * G * 2 * sizeof(unsigned long long)) + 255) & ~(size_t)255; }
@@ -1303,10 +1304,11 @@ size_t dp_eval_metrics_workspace(int B, int H, int W) {
   if (B <= 0 || H <= 0 || W <= 0) return 256;
   size_t need = 256;
   for (int nthr = 1; nthr <= 2; ++nthr)        // the two decompositions (compile-time / run-time threshold count) ...
-    for (int slots : {kEvSlots, kEvSlotsLean}) {   // ... of the two slot counts (exact / lean arithmetic)
-      const EvalPlan p = eval_plan((long long)H * W, B, nthr, slots);
-      if (p.ok && eval_ws_bytes(B, p) > need) need = eval_ws_bytes(B, p);
-    }
+    for (int slots : {kEvSlots, kEvSlotsLean})     // ... of the two slot counts (exact / lean arithmetic)
+      for (int vpt : {1, 2, 4}) {
+        const EvalPlan p = eval_plan((long long)H * W, B, nthr, slots, slots == kEvSlots ? kEvChunkPx : kEvCWLean * vpt * 128);
+        if (p.ok && eval_ws_bytes(B, p) > need) need = eval_ws_bytes(B, p);
+      }
   return need;
 }
 
@@ -1323,7 +1325,9 @@ int dp_eval_metrics(const float* pred, const float* target, int B, int H, int W,
   const bool vec = (n % 4 == 0) && aligned16(pred) && aligned16(target);
 
   const bool lean = fast_math == 2 && eps == 1e-6f;
-  EvalPlan plan = vec ? eval_plan(n, B, nthr, lean ? kEvSlotsLean : kEvSlots) : EvalPlan{};
+  static const int lean_vpt = [] { const char* e = getenv("DP_EV_VPT"); const int v = e ? atoi(e) : kEvVPTLean; return v == 4 ? 4 : 2; }();
+  EvalPlan plan = vec ? eval_plan(n, B, nthr, lean ? kEvSlotsLean : kEvSlots, lean ? kEvCWLean * lean_vpt * 128 : kEvChunkPx)
+                      : EvalPlan{};
   bool lean_plan = lean && plan.ok;
   if (vec && lean && !plan.ok) plan = eval_plan(n, B, nthr);      // shapes too small / odd for four slots: MUFU path
   if (plan.ok) {
@@ -1347,13 +1351,13 @@ int dp_eval_metrics(const float* pred, const float* target, int B, int H, int W,
 #define DP_EVS_PICK(F, O)                                                                       \
   (nthr == 3 ? (const void*)eval_stream_kernel<F, O, 3>                                         \
              : (nthr == 1 ? (const void*)eval_stream_kernel<F, O, 1> : (const void*)eval_stream_kernel<F, O, 0>))
-#define DP_EVS_LEAN                                                                                                  \
-  (nthr == 3 ? (const void*)eval_stream_kernel<false, false, 3, true, kEvSlotsLean, kEvLagLean, kEvCWLean, kEvVPTLean>       \
-             : (nthr == 1 ? (const void*)eval_stream_kernel<false, false, 1, true, kEvSlotsLean, kEvLagLean, kEvCWLean, kEvVPTLean> \
-                          : (const void*)eval_stream_kernel<false, false, 0, true, kEvSlotsLean, kEvLagLean, kEvCWLean, kEvVPTLean>))
+#define DP_EVS_LEAN(V)                                                                                               \
+  (nthr == 3 ? (const void*)eval_stream_kernel<false, false, 3, true, kEvSlotsLean, kEvLagLean, kEvCWLean, V>       \
+             : (nthr == 1 ? (const void*)eval_stream_kernel<false, false, 1, true, kEvSlotsLean, kEvLagLean, kEvCWLean, V> \
+                          : (const void*)eval_stream_kernel<false, false, 0, true, kEvSlotsLean, kEvLagLean, kEvCWLean, V>))
     const void* fn;
     // mode 2 shares one reciprocal between the SI term (eps) and AbsRel (1e-6, util.py:218): needs eps == 1e-6
-    if (lean_plan) fn = DP_EVS_LEAN;
+    if (lean_plan) fn = lean_vpt == 4 ? DP_EVS_LEAN(4) : DP_EVS_LEAN(2);
     else if (fast_math) fn = onediv ? DP_EVS_PICK(true, true) : DP_EVS_PICK(true, false);
     else fn = onediv ? DP_EVS_PICK(false, true) : DP_EVS_PICK(false, false);
 #undef DP_EVS_LEAN
