@@ -461,31 +461,162 @@ __global__ void __launch_bounds__(TPB) dw_wgrad_kernel(const bf16* __restrict__ 
   }
 }
 
-// ---- stride-1 weight gradient from shared-memory tiles ------------------------------------------------------------
+// ---- stride-2 data gradient from a shared-memory tile --------------------------------------------------------------
+// dx[iy,ix] = sum over taps with (iy + pad_t - ky) even of w[ky][kx] * dy[(iy + pad_t - ky) / 2, ...].  For the 2 x 2
+// output block at even (iy0, ix0) the dy rows involved are o0 + r, r = 0 .. (K-1)/2, with o0 = ceil((iy0 + pad_t) / 2) -
+// (K-1)/2, and output row iy0 + a meets dy row o0 + r through tap ky = K - 1 - e + a - 2r, e = (pad_t & 1) - every tap is
+// used exactly once per block, and with the two padding parities as template parameters the tap set is compile-time.
+// A persistent block owns a chunk of 8 channel groups and walks 16 x 32 output tiles; the (8 + (K-1)/2) x (16 + (K-1)/2)
+// dy tile arrives as one TMA box (zero fill = out-of-range gradient rows / columns), double buffered; a thread owns two
+// horizontally adjacent blocks (2 x 4 outputs) per pass, unpacks each dy vector once, MACs are packed f32x2.
+constexpr int DG_TH = 16, DG_TW = 32, DG_CG = 8;
+
+template <int K, int EY, int EX>
+__global__ void __launch_bounds__(TPB, 2) dw_dgrad_s2_tile_kernel(const __grid_constant__ CUtensorMap tmg, int B, int Hi, int Wi,
+                                                                  int C, const float* __restrict__ w, int pad_t, int pad_l,
+                                                                  bf16* __restrict__ dx, long long dx_ld) {
+  constexpr int CG = DG_CG, TH = DG_TH, TW = DG_TW;
+  constexpr int WR = (K + 1) / 2;                            // dy rows / columns under one 2 x 2 block
+  constexpr int NR = TH / 2 + (K - 1) / 2, NC = TW / 2 + (K - 1) / 2;
+  constexpr int PXB = CG * 16;
+  constexpr uint32_t TILE_BYTES = (uint32_t)NR * NC * PXB;
+  constexpr uint32_t TILE_STRIDE = (TILE_BYTES + 127u) & ~127u;
+  constexpr int PW = TW / 4;                                 // patches (two blocks) per tile row of blocks
+  constexpr int NPATCH = (TH / 2) * PW;
+  constexpr int NPT = TPB / CG;                              // pixel threads
+  static_assert(NPATCH % NPT == 0, "patches per thread");
+  extern __shared__ __align__(128) unsigned char dsm[];
+  unsigned char* tile = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dsm) + 127) & ~uintptr_t(127));
+  float* s_w = reinterpret_cast<float*>(tile + 2 * TILE_STRIDE);                  // [K*K][2][CG][4]
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_w + K * K * CG * 8);
+  const int C8 = C / 8;
+  const int cg = threadIdx.x % CG, pt = threadIdx.x / CG;
+  const int c8 = blockIdx.y * CG + cg;
+  const bool chan_ok = c8 < C8;
+  const int tiles_x = (Wi + TW - 1) / TW, tiles_y = (Hi + TH - 1) / TH;
+  const int ntiles = B * tiles_y * tiles_x;
+  for (int i = threadIdx.x; i < K * K * CG * 8; i += TPB) {
+    const int tap = i / (CG * 8), cc = i - tap * (CG * 8);
+    const int g = cc >> 3, j = cc & 7;
+    const int ch = blockIdx.y * CG * 8 + cc;
+    s_w[tap * (CG * 8) + (j >> 2) * (CG * 4) + g * 4 + (j & 3)] = ch < C ? __ldg(w + (size_t)tap * C + ch) : 0.f;
+  }
+  if (threadIdx.x == 0) {
+    tc::mbar_init(full, 1);
+    tc::mbar_init(full + 1, 1);
+    tc::fence_barrier_init();
+    tc::prefetch_tmap(&tmg);
+  }
+  __syncthreads();
+  auto issue = [&](int t, int buf) {
+    const int tx = t % tiles_x, r = t / tiles_x;
+    const int ty = r % tiles_y, b = r / tiles_y;
+    const int o0y = ((ty * TH + pad_t + 1) >> 1) - (K - 1) / 2, o0x = ((tx * TW + pad_l + 1) >> 1) - (K - 1) / 2;
+    tc::mbar_expect_tx(full + buf, TILE_BYTES);
+    tc::tma_load_4d(tile + buf * TILE_STRIDE, &tmg, full + buf, blockIdx.y * CG * 8, o0x, o0y, b);
+  };
+  if (threadIdx.x == 0 && (int)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+  const uint32_t w_base = tc::smem_u32(s_w) + (uint32_t)cg * 16u;
+  const uint32_t tb0 = tc::smem_u32(tile) + (uint32_t)cg * 16u;
+  int it = 0;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    if (threadIdx.x == 0 && t + (int)gridDim.x < ntiles) issue(t + gridDim.x, (it + 1) & 1);
+    tc::mbar_wait(full + (it & 1), (it >> 1) & 1);
+    const int tx = t % tiles_x, rr = t / tiles_x;
+    const int ty = rr % tiles_y, b = rr / tiles_y;
+#pragma unroll 1
+    for (int pi = pt; pi < NPATCH; pi += NPT) {
+      const int bm = pi / PW, bn = (pi - bm * PW) * 2;       // block row, first block column of the patch
+      const uint32_t tb = tb0 + (uint32_t)(it & 1) * TILE_STRIDE + (uint32_t)(bm * NC + bn) * PXB;
+      float2 acc[2][4][4];                                   // [output row a][output column 2j + b][channel pair]
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[a][q][j] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < WR; ++r) {
+        float2 v[WR + 1][4];
+#pragma unroll
+        for (int c = 0; c < WR + 1; ++c) {
+          uint32_t u0, u1, u2, u3;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u0), "=r"(u1), "=r"(u2), "=r"(u3)
+                       : "r"(tb + (uint32_t)(r * NC + c) * PXB));
+          const uint32_t uw[4] = {u0, u1, u2, u3};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[c][j] = make_float2(__uint_as_float(uw[j] << 16), __uint_as_float(uw[j] & 0xffff0000u));
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          const int ky = K - 1 - EY + a - 2 * r;             // compile-time after unrolling
+          if (ky < 0 || ky >= K) continue;
+#pragma unroll
+          for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+            for (int cc = 0; cc < WR; ++cc) {
+              const int kx = K - 1 - EX + bb - 2 * cc;
+              if (kx < 0 || kx >= K) continue;
+              float2 w2[4];
+              const uint32_t wa = w_base + (uint32_t)((ky * K + kx) * CG * 8) * 4u;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w2[0].x), "=f"(w2[0].y), "=f"(w2[1].x), "=f"(w2[1].y) : "r"(wa));
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w2[2].x), "=f"(w2[2].y), "=f"(w2[3].x), "=f"(w2[3].y) : "r"(wa + (uint32_t)(CG * 16)));
+#pragma unroll
+              for (int jb = 0; jb < 2; ++jb)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[a][2 * jb + bb][j] = __ffma2_rn(v[jb + cc][j], w2[j], acc[a][2 * jb + bb][j]);
+            }
+        }
+      }
+      if (chan_ok) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          const int iy = ty * TH + 2 * bm + a;
+          if (iy >= Hi) continue;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int ix = tx * TW + 2 * bn + q;
+            if (ix >= Wi) continue;
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { o[2 * j] = acc[a][q][j].x; o[2 * j + 1] = acc[a][q][j].y; }
+            *reinterpret_cast<uint4*>(dx + (((long long)b * Hi + iy) * Wi + ix) * dx_ld + c8 * 8) = pack8(o);
+          }
+        }
+      }
+    }
+    __syncthreads();                               // every thread is past its reads of this buffer
+  }
+}
+
+// ---- weight gradient from shared-memory tiles -----------------------------------------------------------------------
 // The kernel above reads dy K times and x ~K times through L1 / L2 and multiplies with scalar FMAs.  Here a persistent
-// block owns a chunk of WT_CG channel groups and walks TH x 8 output tiles: the dy tile and the (TH+K-1) x (8+K-1) input
-// tile under it arrive as two TMA boxes (zero fill outside either image: out-of-range products vanish, no bounds tests),
-// double buffered.  thread = (channel group, kernel row ky, row slot): it walks its output rows with a K-wide sliding
-// window of unpacked input vectors - per output pixel one dy vector, one new input vector, K x 4 packed f32x2 MACs into
-// the K x 8 accumulators it keeps for the whole launch.  partial[block][tap][c] is folded by dw_wgrad_reduce_kernel.
+// block owns a chunk of WT_CG channel groups and walks TH x 8 output tiles: the dy tile and the input tile under it
+// ((TH-1)*S+K rows x (8-1)*S+K columns) arrive as two TMA boxes (zero fill outside either image: out-of-range products
+// vanish, no bounds tests) - double buffered at stride 1, single buffered at stride 2 (the tile is four times larger;
+// the second block of the SM computes while this one waits).  thread = (channel group, kernel row ky, row slot): it
+// walks its output rows with a K-wide sliding window of unpacked input vectors - per output pixel one dy vector, S new
+// input vectors, K x 4 packed f32x2 MACs into the K x 8 accumulators it keeps for the whole launch.
+// partial[block][tap][c] is folded by dw_wgrad_reduce_kernel.
 constexpr int WT_CG = 8, WT_TW = 8;
 constexpr int wt_th(int K) { return K == 3 ? 10 : 12; }
 
-template <int K>
+template <int K, int S>
 __global__ void __launch_bounds__(TPB, 2) dw_wgrad_tile_kernel(const __grid_constant__ CUtensorMap tmx,
                                                                const __grid_constant__ CUtensorMap tmg, int B, int Ho, int Wo,
                                                                int C, int pad_t, int pad_l, float* __restrict__ partial) {
   constexpr int CG = WT_CG, TW = WT_TW, TH = wt_th(K);
+  constexpr int NBUF = S == 1 ? 2 : 1;
   constexpr int NSLOT = (TPB / CG) / K;                      // row slots: 10 (K = 3) / 6 (K = 5)
   static_assert(TH % NSLOT == 0, "rows per slot");
-  constexpr int IH = TH + K - 1, IW = TW + K - 1;
+  constexpr int IH = (TH - 1) * S + K, IW = (TW - 1) * S + K;
   constexpr int PXB = CG * 16;
   constexpr uint32_t X_BYTES = (uint32_t)IH * IW * PXB, G_BYTES = (uint32_t)TH * TW * PXB;
   constexpr uint32_t X_STRIDE = (X_BYTES + 127u) & ~127u, BUF_STRIDE = X_STRIDE + ((G_BYTES + 127u) & ~127u);
-  static_assert(2 * BUF_STRIDE >= (uint32_t)TPB * K * 8 * 4, "reduction scratch fits the tile buffers");
+  static_assert(NBUF * BUF_STRIDE >= (uint32_t)TPB * K * 8 * 4, "reduction scratch fits the tile buffers");
   extern __shared__ __align__(128) unsigned char dsm[];
   unsigned char* tile = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dsm) + 127) & ~uintptr_t(127));
-  uint64_t* full = reinterpret_cast<uint64_t*>(tile + 2 * BUF_STRIDE);
+  uint64_t* full = reinterpret_cast<uint64_t*>(tile + NBUF * BUF_STRIDE);
   const int C8 = C / 8;
   const int cg = threadIdx.x % CG, pt = threadIdx.x / CG;
   const int ky = pt % K, slot = pt / K;
@@ -505,7 +636,7 @@ __global__ void __launch_bounds__(TPB, 2) dw_wgrad_tile_kernel(const __grid_cons
     const int tx = t % tiles_x, r = t / tiles_x;
     const int ty = r % tiles_y, b = r / tiles_y;
     tc::mbar_expect_tx(full + buf, X_BYTES + G_BYTES);
-    tc::tma_load_4d(tile + buf * BUF_STRIDE, &tmx, full + buf, blockIdx.y * CG * 8, tx * TW - pad_l, ty * TH - pad_t, b);
+    tc::tma_load_4d(tile + buf * BUF_STRIDE, &tmx, full + buf, blockIdx.y * CG * 8, tx * TW * S - pad_l, ty * TH * S - pad_t, b);
     tc::tma_load_4d(tile + buf * BUF_STRIDE + X_STRIDE, &tmg, full + buf, blockIdx.y * CG * 8, tx * TW, ty * TH, b);
   };
   if (threadIdx.x == 0 && (int)blockIdx.x < ntiles) issue(blockIdx.x, 0);
@@ -517,14 +648,15 @@ __global__ void __launch_bounds__(TPB, 2) dw_wgrad_tile_kernel(const __grid_cons
   const uint32_t tb0 = tc::smem_u32(tile) + (uint32_t)cg * 16u;
   int it = 0;
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-    if (threadIdx.x == 0 && t + (int)gridDim.x < ntiles) issue(t + gridDim.x, (it + 1) & 1);
-    tc::mbar_wait(full + (it & 1), (it >> 1) & 1);
+    const int buf = NBUF == 2 ? (it & 1) : 0;
+    if (NBUF == 2 && threadIdx.x == 0 && t + (int)gridDim.x < ntiles) issue(t + gridDim.x, (it + 1) & 1);
+    tc::mbar_wait(full + buf, NBUF == 2 ? ((it >> 1) & 1) : (it & 1));
     if (active) {
-      const uint32_t xb = tb0 + (uint32_t)(it & 1) * BUF_STRIDE;
+      const uint32_t xb = tb0 + (uint32_t)buf * BUF_STRIDE;
       const uint32_t gb = xb + X_STRIDE;
 #pragma unroll 1
       for (int oy = slot; oy < TH; oy += NSLOT) {
-        const uint32_t xrow = xb + (uint32_t)((oy + ky) * IW) * PXB;
+        const uint32_t xrow = xb + (uint32_t)((oy * S + ky) * IW) * PXB;
         const uint32_t grow = gb + (uint32_t)(oy * TW) * PXB;
         float2 win[K][4];                          // sliding window of unpacked input vectors (indices are compile-time)
         auto ldv = [&](uint32_t addr, float2 (&v)[4]) {
@@ -535,20 +667,22 @@ __global__ void __launch_bounds__(TPB, 2) dw_wgrad_tile_kernel(const __grid_cons
           for (int j = 0; j < 4; ++j) v[j] = make_float2(__uint_as_float(uw[j] << 16), __uint_as_float(uw[j] & 0xffff0000u));
         };
 #pragma unroll
-        for (int c = 0; c < K - 1; ++c) ldv(xrow + (uint32_t)c * PXB, win[c]);
+        for (int c = 0; c < K - S; ++c) ldv(xrow + (uint32_t)c * PXB, win[c % K]);
 #pragma unroll
         for (int ox = 0; ox < TW; ++ox) {
-          ldv(xrow + (uint32_t)(ox + K - 1) * PXB, win[(ox + K - 1) % K]);
+#pragma unroll
+          for (int c = ox * S + K - S; c < ox * S + K; ++c) ldv(xrow + (uint32_t)c * PXB, win[c % K]);   // the S new columns
           float2 g[4];
           ldv(grow + (uint32_t)ox * PXB, g);
 #pragma unroll
           for (int kx = 0; kx < K; ++kx)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[kx][j] = __ffma2_rn(g[j], win[(ox + kx) % K][j], acc[kx][j]);
+            for (int j = 0; j < 4; ++j) acc[kx][j] = __ffma2_rn(g[j], win[(ox * S + kx) % K][j], acc[kx][j]);
         }
       }
     }
-    __syncthreads();                               // this buffer may be refilled by the next iteration's issue
+    __syncthreads();                               // this buffer may be refilled now
+    if (NBUF == 1 && threadIdx.x == 0 && t + (int)gridDim.x < ntiles) issue(t + gridDim.x, 0);
   }
   // fixed-order fold over the row slots, one (channel group, ky) row per thread of the first K * CG threads
   float* s_acc = reinterpret_cast<float*>(tile);   // [TPB][K*8]
@@ -702,6 +836,39 @@ int dp_dwconv_fwd(const void* x, long long x_ld, int B, int Hi, int Wi, int C, c
 int dp_dwconv_dgrad_s2(const void* dy, long long dy_ld, int B, int Ho, int Wo, int C, const float* w, int K, int pad_t,
                        int pad_l, void* dx, long long dx_ld, int Hi, int Wi, cudaStream_t stream) {
   DP_CHECK_ARG(dy && w && dx && C % 8 == 0 && (K == 3 || K == 5), "dp_dwconv_dgrad_s2: bad arguments");
+  if (dy_ld % 8 == 0 && dx_ld % 8 == 0) {
+    const int NR = DG_TH / 2 + (K - 1) / 2, NC = DG_TW / 2 + (K - 1) / 2;
+    CUtensorMap tmg;
+    const uint64_t gd[4] = {(uint64_t)C, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)B};
+    const uint64_t gs[3] = {(uint64_t)dy_ld * 2, (uint64_t)Wo * dy_ld * 2, (uint64_t)Ho * Wo * dy_ld * 2};
+    const uint32_t gbox[4] = {(uint32_t)(DG_CG * 8), (uint32_t)NC, (uint32_t)NR, 1};
+    int rc = dp_make_tmap_bf16(&tmg, dy, 4, gd, gs, gbox, nullptr, 0);
+    if (rc) return rc;
+    const size_t tile = (((size_t)NR * NC * DG_CG * 16) + 127) & ~size_t(127);
+    const size_t smem = 128 + 2 * tile + (size_t)K * K * DG_CG * 8 * 4 + 64;
+    const int ny = (C / 8 + DG_CG - 1) / DG_CG;
+    const long long ntiles = (long long)B * ((Hi + DG_TH - 1) / DG_TH) * ((Wi + DG_TW - 1) / DG_TW);
+    long long nx = (2LL * kNumSMs) / ny;
+    if (nx > ntiles) nx = ntiles;
+    if (nx < 1) nx = 1;
+    dim3 grid2((unsigned)nx, ny);
+    bf16* dxb = reinterpret_cast<bf16*>(dx);
+#define DP_DW_DG(KK, EYY, EXX)                                                                                             \
+    do {                                                                                                                   \
+      cudaError_t e = cudaFuncSetAttribute(dw_dgrad_s2_tile_kernel<KK, EYY, EXX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (e != cudaSuccess) return dp_set_error(DP_ERR_CUDA, "dw_dgrad_s2_tile_kernel smem %zu: %s", smem, cudaGetErrorString(e)); \
+      dw_dgrad_s2_tile_kernel<KK, EYY, EXX><<<grid2, TPB, smem, stream>>>(tmg, B, Hi, Wi, C, w, pad_t, pad_l, dxb, dx_ld);  \
+    } while (0)
+    const int ey = pad_t & 1, ex = pad_l & 1;
+    if (K == 3) {
+      if (ey && ex) DP_DW_DG(3, 1, 1); else if (ey) DP_DW_DG(3, 1, 0); else if (ex) DP_DW_DG(3, 0, 1); else DP_DW_DG(3, 0, 0);
+    } else {
+      if (ey && ex) DP_DW_DG(5, 1, 1); else if (ey) DP_DW_DG(5, 1, 0); else if (ex) DP_DW_DG(5, 0, 1); else DP_DW_DG(5, 0, 0);
+    }
+#undef DP_DW_DG
+    DP_CHECK_LAUNCH("dw_dgrad_s2_tile_kernel");
+    return DP_OK;
+  }
   const int grid = dw_grid((long long)B * Hi * Wi * (C / 8));
   if (K == 3)
     dw_dgrad_s2_kernel<3><<<grid, TPB, 0, stream>>>(reinterpret_cast<const bf16*>(dy), dy_ld, B, Ho, Wo, C, w, pad_t, pad_l,
@@ -728,12 +895,13 @@ int dp_dwconv_wgrad(const void* x, long long x_ld, int B, int Hi, int Wi, int C,
   if (workspace_bytes < dp_dwconv_wgrad_workspace(B, Ho, Wo, C, K))
     return dp_set_error(DP_ERR_WORKSPACE, "dp_dwconv_wgrad: workspace too small");
   float* partial = reinterpret_cast<float*>(workspace);
-  if (stride == 1 && x_ld % 8 == 0 && dy_ld % 8 == 0) {
-    const int TH = wt_th(K);
+  if (x_ld % 8 == 0 && dy_ld % 8 == 0) {
+    const int TH = wt_th(K), S = stride;
+    const int IH = (TH - 1) * S + K, IW = (WT_TW - 1) * S + K;
     CUtensorMap tmx, tmg;
     const uint64_t xd[4] = {(uint64_t)C, (uint64_t)Wi, (uint64_t)Hi, (uint64_t)B};
     const uint64_t xs[3] = {(uint64_t)x_ld * 2, (uint64_t)Wi * x_ld * 2, (uint64_t)Hi * Wi * x_ld * 2};
-    const uint32_t xbox[4] = {(uint32_t)(WT_CG * 8), (uint32_t)(WT_TW + K - 1), (uint32_t)(TH + K - 1), 1};
+    const uint32_t xbox[4] = {(uint32_t)(WT_CG * 8), (uint32_t)IW, (uint32_t)IH, 1};
     int rc = dp_make_tmap_bf16(&tmx, x, 4, xd, xs, xbox, nullptr, 0);
     if (rc) return rc;
     const uint64_t gd[4] = {(uint64_t)C, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)B};
@@ -741,21 +909,22 @@ int dp_dwconv_wgrad(const void* x, long long x_ld, int B, int Hi, int Wi, int C,
     const uint32_t gbox[4] = {(uint32_t)(WT_CG * 8), (uint32_t)WT_TW, (uint32_t)TH, 1};
     rc = dp_make_tmap_bf16(&tmg, dy, 4, gd, gs, gbox, nullptr, 0);
     if (rc) return rc;
-    const size_t xb = (((size_t)(TH + K - 1) * (WT_TW + K - 1) * WT_CG * 16) + 127) & ~size_t(127);
+    const size_t xb = (((size_t)IH * IW * WT_CG * 16) + 127) & ~size_t(127);
     const size_t gbz = (((size_t)TH * WT_TW * WT_CG * 16) + 127) & ~size_t(127);
-    const size_t smem = 128 + 2 * (xb + gbz) + 64;
+    const size_t smem = 128 + (S == 1 ? 2 : 1) * (xb + gbz) + 64;
     const int nx = wt_blocks(B, Ho, Wo, C, K);
     dim3 grid(nx, (C / 8 + WT_CG - 1) / WT_CG);
-    cudaError_t e;
-    if (K == 3) {
-      e = cudaFuncSetAttribute(dw_wgrad_tile_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return dp_set_error(DP_ERR_CUDA, "dw_wgrad_tile_kernel smem %zu: %s", smem, cudaGetErrorString(e));
-      dw_wgrad_tile_kernel<3><<<grid, TPB, smem, stream>>>(tmx, tmg, B, Ho, Wo, C, pad_t, pad_l, partial);
-    } else {
-      e = cudaFuncSetAttribute(dw_wgrad_tile_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return dp_set_error(DP_ERR_CUDA, "dw_wgrad_tile_kernel smem %zu: %s", smem, cudaGetErrorString(e));
-      dw_wgrad_tile_kernel<5><<<grid, TPB, smem, stream>>>(tmx, tmg, B, Ho, Wo, C, pad_t, pad_l, partial);
-    }
+#define DP_DW_WT(KK, SS)                                                                                                   \
+    do {                                                                                                                   \
+      cudaError_t e = cudaFuncSetAttribute(dw_wgrad_tile_kernel<KK, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (e != cudaSuccess) return dp_set_error(DP_ERR_CUDA, "dw_wgrad_tile_kernel smem %zu: %s", smem, cudaGetErrorString(e)); \
+      dw_wgrad_tile_kernel<KK, SS><<<grid, TPB, smem, stream>>>(tmx, tmg, B, Ho, Wo, C, pad_t, pad_l, partial);            \
+    } while (0)
+    if (K == 3 && S == 1) DP_DW_WT(3, 1);
+    else if (K == 3) DP_DW_WT(3, 2);
+    else if (S == 1) DP_DW_WT(5, 1);
+    else DP_DW_WT(5, 2);
+#undef DP_DW_WT
     DP_CHECK_LAUNCH("dw_wgrad_tile_kernel");
     dw_wgrad_reduce_kernel<<<dp::ceil_div(K * K * C, 32), 1024, 0, stream>>>(partial, nx, K * K, C, grad, accumulate);
     DP_CHECK_LAUNCH("dw_wgrad_reduce_kernel");

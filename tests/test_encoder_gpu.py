@@ -72,6 +72,34 @@ def test_depthwise_tf_same_padding(pkg):
     assert ok, (e, s)
 
 
+@pytest.mark.parametrize("B,C,H,W,K,S,pt,pl,pb,pr", [
+    # stride-2 data / weight gradients for every parity of the top / left padding (the tap sets are compile-time per parity)
+    (2, 72, 37, 46, 3, 2, 0, 0, 1, 1), (2, 72, 37, 46, 3, 2, 1, 0, 1, 1), (2, 72, 36, 45, 3, 2, 0, 1, 1, 0),
+    (2, 72, 36, 45, 3, 2, 1, 1, 0, 0), (1, 136, 41, 70, 5, 2, 1, 2, 2, 1), (1, 136, 41, 70, 5, 2, 2, 1, 2, 2),
+    (1, 136, 40, 71, 5, 2, 1, 1, 2, 2), (1, 136, 40, 71, 5, 2, 2, 2, 1, 1), (3, 144, 64, 96, 3, 2, 0, 0, 1, 1),
+    # stride 1, asymmetric
+    (2, 48, 30, 41, 5, 1, 1, 3, 3, 1), (2, 48, 30, 41, 3, 1, 0, 2, 2, 0)])
+def test_depthwise_asymmetric_padding_fwd_bwd(pkg, B, C, H, W, K, S, pt, pl, pb, pr):
+    from depth_b200 import ops
+    x = rnd(B, C, H, W, seed=C + K + pt)
+    w = rnd(C, 1, K, K, seed=C + 9, scale=0.3)
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    ref = F.conv2d(F.pad(xr, (pl, pr, pt, pb)), wr, None, S, 0, 1, C)
+    Ho, Wo = ref.shape[-2:]
+    cot = rnd(B, C, Ho, Wo, seed=13)
+    ref.backward(cot)
+    xp = nhwc(x).requires_grad_(True)
+    wp = w.cuda().requires_grad_(True)
+    out = ops.dwconv(xp, wp, S, pt, pl, Ho, Wo)
+    ok, e, s = close(nchw(out), ref.detach())
+    assert ok, (e, s)
+    out.backward(nhwc(cot))
+    ok, e, s = close(nchw(xp.grad), xr.grad)
+    assert ok, ("dgrad", e, s)
+    ok, e, s = close(wp.grad.cpu(), wr.grad, rel=2e-3, abs_frac=2e-3)
+    assert ok, ("wgrad", e, s)
+
+
 @pytest.mark.parametrize("C,res", [(32, False), (192, True), (1392, False)])
 def test_batchnorm_relu6_fwd_bwd(pkg, C, res):
     from depth_b200 import ops
