@@ -315,13 +315,13 @@ __global__ void __launch_bounds__(TPB, 2) dw_tile_kernel(const __grid_constant__
 // tile geometry of the stride-1 path: output tile TH x TW, CG channel groups per block
 struct DwTilePlan { int TW, CG, TH, ny, nx, R, XO; };
 inline DwTilePlan dw_tile_plan(int B, int Ho, int Wo, int C, int K) {
-  // candidates (TW, CG) -> TH = R * (256 / CG) / (TW / XO)
+  // candidates (TW, CG) -> TH = R * (256 / CG) / (TW / XO); (8, 8) is the tall narrow tile for the 14 x 18 / 28 x 36 maps
   // Pick the one that computes the fewest padded output vectors (tile overhang in x / y, channel-chunk overhang).
-  const int cand[3][2] = {{16, 8}, {16, 16}, {32, 8}};
+  const int cand[4][2] = {{16, 8}, {16, 16}, {32, 8}, {8, 8}};
   const DwPatch pp = dw_patch(K);
   DwTilePlan best{};
   long long best_cost = -1;
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < 4; ++i) {
     DwTilePlan p;
     p.TW = cand[i][0]; p.CG = cand[i][1]; p.R = pp.R; p.XO = pp.XO;
     p.TH = pp.R * (TPB / p.CG) / (p.TW / pp.XO);
@@ -812,7 +812,9 @@ int dp_dwconv_fwd(const void* x, long long x_ld, int B, int Hi, int Wi, int C, c
       if (e != cudaSuccess) return dp_set_error(DP_ERR_CUDA, "dw_tile_kernel smem %zu: %s", smem, cudaGetErrorString(e));       \
       dw_tile_kernel<KK, TWW, CGG, RR, XX><<<grid, TPB, smem, stream>>>(tm, a);                             \
     } while (0)
-    if (K == 3 && p.TW == 32) DP_DW_TILE(3, 32, 8, 4, 2);
+    if (K == 3 && p.TW == 8) DP_DW_TILE(3, 8, 8, 4, 2);
+    else if (K == 5 && p.TW == 8) DP_DW_TILE(5, 8, 8, 2, 2);
+    else if (K == 3 && p.TW == 32) DP_DW_TILE(3, 32, 8, 4, 2);
     else if (K == 3 && p.CG == 16) DP_DW_TILE(3, 16, 16, 4, 2);
     else if (K == 3) DP_DW_TILE(3, 16, 8, 4, 2);
     else if (p.TW == 32) DP_DW_TILE(5, 32, 8, 2, 2);

@@ -648,7 +648,7 @@ constexpr int kEvSlots = 2;                 // shared-memory slots = samples in 
 // sample's round trip (load -> sweep 1 -> scale exchange through global memory -> sweep 2): two slots x 86 KB in flight
 // per 7 us is 55 % of an SM's HBM share.  It therefore runs with four smaller slots and classifies TWO samples behind the
 // moments sweep, so the exchange has two sweeps' time to complete and the producer stays two samples ahead.
-constexpr int kEvSlotsLean = 4, kEvLagLean = 2;
+constexpr int kEvSlotsLean = 4, kEvLagLean = 2;   // measured alternatives at 448x576: 5 slots (3 groups of 49) 374, 8 slots (2 groups of 74) 213, lag 1 367 Gpx/s
 constexpr int kEvCWLean = 14, kEvVPTLean = 4;   // 14 consumer warps x 4 float4 per chunk = one chunk per slice at 448x576 (measured: 28 x 1 -> 395, 14 x 2 -> 470, 14 x 4 -> 480, 7 x 4 -> 390 Gpx/s)
 constexpr int kEvPrefetch = 0;                  // samples of L2 prefetch beyond the slot ring: off (measured 0 -> 398, 1 -> 404, 3 -> 390 Gpx/s, but ncu showed 17 % more DRAM reads with 1: prefetched lines evicted before use)
 // static shared memory the plan leaves room for: 2.4 KB in the instantiations with a compile-time threshold count
@@ -815,7 +815,6 @@ __device__ __forceinline__ void delta_px_generic(float al, float t, const float*
 // whose pixel work is down to ~36 instructions - runs 14 fatter warps (two float4 per chunk) instead of 28.
 template <bool FAST, bool ONEDIV, int NT, bool LEAN = false, int NS_ = kEvSlots, int LAG_ = 1, int CW = kEvCW, int VPT = 1>
 __global__ void __launch_bounds__((CW + 2) * 32, 1) eval_stream_kernel(EvsArgs a) {
-  static_assert(CW * VPT * 128 % kEvChunkPx == 0, "chunk size is a multiple of the plan's unit");
   constexpr int CT = CW * 32;                      // consumer threads
   constexpr int NS = NS_;
   constexpr int LAG = LAG_;                        // sweep 2 runs LAG samples behind sweep 1
@@ -1304,11 +1303,10 @@ size_t dp_eval_metrics_workspace(int B, int H, int W) {
   if (B <= 0 || H <= 0 || W <= 0) return 256;
   size_t need = 256;
   for (int nthr = 1; nthr <= 2; ++nthr)        // the two decompositions (compile-time / run-time threshold count) ...
-    for (int slots : {kEvSlots, kEvSlotsLean})     // ... of the two slot counts (exact / lean arithmetic)
-      for (int vpt : {1, 2, 4}) {
-        const EvalPlan p = eval_plan((long long)H * W, B, nthr, slots, slots == kEvSlots ? kEvChunkPx : kEvCWLean * vpt * 128);
-        if (p.ok && eval_ws_bytes(B, p) > need) need = eval_ws_bytes(B, p);
-      }
+    for (int cfg : {0, 1}) {                       // ... of the exact and the lean plan
+      const EvalPlan p = eval_plan((long long)H * W, B, nthr, cfg ? kEvSlotsLean : kEvSlots, cfg ? kEvCWLean * kEvVPTLean * 128 : kEvChunkPx);
+      if (p.ok && eval_ws_bytes(B, p) > need) need = eval_ws_bytes(B, p);
+    }
   return need;
 }
 
@@ -1325,8 +1323,7 @@ int dp_eval_metrics(const float* pred, const float* target, int B, int H, int W,
   const bool vec = (n % 4 == 0) && aligned16(pred) && aligned16(target);
 
   const bool lean = fast_math == 2 && eps == 1e-6f;
-  static const int lean_vpt = [] { const char* e = getenv("DP_EV_VPT"); const int v = e ? atoi(e) : kEvVPTLean; return v == 4 ? 4 : 2; }();
-  EvalPlan plan = vec ? eval_plan(n, B, nthr, lean ? kEvSlotsLean : kEvSlots, lean ? kEvCWLean * lean_vpt * 128 : kEvChunkPx)
+  EvalPlan plan = vec ? eval_plan(n, B, nthr, lean ? kEvSlotsLean : kEvSlots, lean ? kEvCWLean * kEvVPTLean * 128 : kEvChunkPx)
                       : EvalPlan{};
   bool lean_plan = lean && plan.ok;
   if (vec && lean && !plan.ok) plan = eval_plan(n, B, nthr);      // shapes too small / odd for four slots: MUFU path
@@ -1351,13 +1348,13 @@ int dp_eval_metrics(const float* pred, const float* target, int B, int H, int W,
 #define DP_EVS_PICK(F, O)                                                                       \
   (nthr == 3 ? (const void*)eval_stream_kernel<F, O, 3>                                         \
              : (nthr == 1 ? (const void*)eval_stream_kernel<F, O, 1> : (const void*)eval_stream_kernel<F, O, 0>))
-#define DP_EVS_LEAN(V)                                                                                               \
-  (nthr == 3 ? (const void*)eval_stream_kernel<false, false, 3, true, kEvSlotsLean, kEvLagLean, kEvCWLean, V>       \
-             : (nthr == 1 ? (const void*)eval_stream_kernel<false, false, 1, true, kEvSlotsLean, kEvLagLean, kEvCWLean, V> \
-                          : (const void*)eval_stream_kernel<false, false, 0, true, kEvSlotsLean, kEvLagLean, kEvCWLean, V>))
+#define DP_EVS_LEAN                                                                                                  \
+  (nthr == 3 ? (const void*)eval_stream_kernel<false, false, 3, true, kEvSlotsLean, kEvLagLean, kEvCWLean, kEvVPTLean>       \
+             : (nthr == 1 ? (const void*)eval_stream_kernel<false, false, 1, true, kEvSlotsLean, kEvLagLean, kEvCWLean, kEvVPTLean> \
+                          : (const void*)eval_stream_kernel<false, false, 0, true, kEvSlotsLean, kEvLagLean, kEvCWLean, kEvVPTLean>))
     const void* fn;
     // mode 2 shares one reciprocal between the SI term (eps) and AbsRel (1e-6, util.py:218): needs eps == 1e-6
-    if (lean_plan) fn = lean_vpt == 4 ? DP_EVS_LEAN(4) : DP_EVS_LEAN(2);
+    if (lean_plan) fn = DP_EVS_LEAN;
     else if (fast_math) fn = onediv ? DP_EVS_PICK(true, true) : DP_EVS_PICK(true, false);
     else fn = onediv ? DP_EVS_PICK(false, true) : DP_EVS_PICK(false, false);
 #undef DP_EVS_LEAN
