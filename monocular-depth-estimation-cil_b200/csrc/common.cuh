@@ -32,9 +32,34 @@ void dp_count_launch(int n);
 
 typedef __nv_bfloat16 bf16;
 
+int dp_pdl_enabled(void);   // dp_core.cu: programmatic dependent launch on (default) / off (DP_PDL=0)
+
 namespace dp {
 
 constexpr int kNumSMs = 148;  // B200
+
+// ---- programmatic dependent launch ----------------------------------------------------------------------------------
+// The train step is ~1500 short launches in one stream.  Launched with the programmatic-stream-serialization attribute a
+// kernel's blocks may be scheduled while the previous kernel of the stream is still draining (every block of it has
+// executed pdl_trigger(), which all kernels here do first thing), so launch latency, block scheduling and the
+// prologue (barrier init, TMEM allocation, descriptor prefetch) overlap the predecessor's tail.  pdl_wait() returns once
+// the predecessor grid has COMPLETED and its writes are visible: every kernel launched through dp::launch executes it
+// before its first global-memory access, which also makes completion transitive along the stream (a grid cannot
+// complete before its own wait returned).  Both instructions are no-ops in a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() { pdl_trigger(); pdl_wait(); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = dp_pdl_enabled();
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

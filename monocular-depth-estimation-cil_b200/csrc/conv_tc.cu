@@ -792,6 +792,7 @@ constexpr int kPreThreads = kThreads + 128;
 template <bool kPre>
 __global__ void __launch_bounds__(kPre ? kPreThreads : kThreads, 1)
 conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs a) {
+  dp::pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // layout: [resident weights][output staging tiles][stages x (A | B)][stats][barriers]
@@ -828,6 +829,7 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
   }
   if (warp == 2) tc::tmem_alloc(&bars->tmem_base, kTmemCols);
   for (int i = threadIdx.x; i < stats_floats; i += blockDim.x) s_stats[i] = 0.f;
+  dp::pdl_wait();   // everything above overlaps the previous kernel's tail; global memory is touched from here on
   for (int i = threadIdx.x; i < pre_floats; i += blockDim.x) {      // [scale | shift], zero beyond the real channels
     const int which = i / a.pre_pad, c = i - which * a.pre_pad;
     s_pre[i] = c < a.pre_c ? __ldg(a.pre_ss + which * a.pre_c + c) : 0.f;
@@ -1270,7 +1272,7 @@ int launch(const Plane* planes, const ColSpec* cols, int ncols, int B, int Hg, i
   auto kern = a.pre_ss ? conv_tc_kernel<true> : conv_tc_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
   if (e != cudaSuccess) return dp_set_error(DP_ERR_CUDA, "cudaFuncSetAttribute(%zu): %s", p.smem, cudaGetErrorString(e));
-  kern<<<p.grid, a.pre_ss ? kPreThreads : kThreads, p.smem, stream>>>(tm, a);
+  dp::launch(kern, p.grid, a.pre_ss ? kPreThreads : kThreads, p.smem, stream, tm, a);
   DP_CHECK_LAUNCH("conv_tc_kernel");
   return DP_OK;
 }

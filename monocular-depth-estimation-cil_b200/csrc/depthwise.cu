@@ -54,6 +54,7 @@ struct DwArgs {
 // (channel group c8l = tid % G, strip slot = tid / G), so a warp touches G*16 contiguous bytes per pixel.
 template <int K, int S>
 __global__ void __launch_bounds__(TPB, 2) dw_fwd_kernel(DwArgs a) {
+  dp::pdl_prologue();
   extern __shared__ float smem[];            // [K*K][G*8] taps | [TPB][16] statistics scratch
   const int G = a.G, C8 = a.C / 8;
   float* s_w = smem;
@@ -175,6 +176,7 @@ inline DwPatch dw_patch(int K) { return K == 3 ? DwPatch{4, 2} : DwPatch{2, 2}; 
 
 template <int K, int TW, int CG, int DT_R, int DT_TXO>
 __global__ void __launch_bounds__(TPB, 2) dw_tile_kernel(const __grid_constant__ CUtensorMap tmx, DwArgs a) {
+  dp::pdl_prologue();
   constexpr int QX = TW / DT_TXO;                            // patches per tile row
   constexpr int TH = DT_R * (TPB / CG) / QX;                 // output rows per tile
   static_assert(TH >= DT_R && (TPB / CG) % QX == 0, "thread layout");
@@ -342,6 +344,7 @@ template <int K>
 __global__ void __launch_bounds__(TPB) dw_dgrad_s2_kernel(const bf16* __restrict__ dy, long long dy_ld, int B, int Ho, int Wo,
                                                           int C, const float* __restrict__ w, int pad_t, int pad_l,
                                                           bf16* __restrict__ dx, long long dx_ld, int Hi, int Wi) {
+  dp::pdl_prologue();
   const int C8 = C / 8;
   const long long items = (long long)B * Hi * Wi * C8;
   for (long long idx = (long long)blockIdx.x * TPB + threadIdx.x; idx < items; idx += (long long)gridDim.x * TPB) {
@@ -387,6 +390,7 @@ template <int K, int S>
 __global__ void __launch_bounds__(TPB) dw_wgrad_kernel(const bf16* __restrict__ x, long long x_ld, int B, int Hi, int Wi, int C,
                                                        const bf16* __restrict__ dy, long long dy_ld, int Ho, int Wo,
                                                        int pad_t, int pad_l, int nchunks, float* __restrict__ partial) {
+  dp::pdl_prologue();
   extern __shared__ float s_acc[];   // [TPB][K*8]
   const int C8 = C / 8;
   const int c8b = C8 < WG_C8B ? C8 : WG_C8B;
@@ -475,6 +479,7 @@ template <int K, int EY, int EX>
 __global__ void __launch_bounds__(TPB, 2) dw_dgrad_s2_tile_kernel(const __grid_constant__ CUtensorMap tmg, int B, int Hi, int Wi,
                                                                   int C, const float* __restrict__ w, int pad_t, int pad_l,
                                                                   bf16* __restrict__ dx, long long dx_ld) {
+  dp::pdl_prologue();
   constexpr int CG = DG_CG, TH = DG_TH, TW = DG_TW;
   constexpr int WR = (K + 1) / 2;                            // dy rows / columns under one 2 x 2 block
   constexpr int NR = TH / 2 + (K - 1) / 2, NC = TW / 2 + (K - 1) / 2;
@@ -605,6 +610,7 @@ template <int K, int S>
 __global__ void __launch_bounds__(TPB, 2) dw_wgrad_tile_kernel(const __grid_constant__ CUtensorMap tmx,
                                                                const __grid_constant__ CUtensorMap tmg, int B, int Ho, int Wo,
                                                                int C, int pad_t, int pad_l, float* __restrict__ partial) {
+  dp::pdl_prologue();
   constexpr int CG = WT_CG, TW = WT_TW, TH = wt_th(K);
   constexpr int NBUF = S == 1 ? 2 : 1;
   constexpr int NSLOT = (TPB / CG) / K;                      // row slots: 10 (K = 3) / 6 (K = 5)
@@ -725,6 +731,7 @@ inline int wt_blocks(int B, int Ho, int Wo, int C, int K) {
 // block = 32 consecutive (tap, c) columns x 32 chunk lanes: coalesced rows of the partials, fixed-order fp64 fold
 __global__ void __launch_bounds__(1024) dw_wgrad_reduce_kernel(const float* __restrict__ partial, int nchunks, int taps, int C,
                                                                float* __restrict__ grad, int accumulate) {
+  dp::pdl_prologue();
   __shared__ double s_s[32][32];
   const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + cl;
@@ -810,7 +817,7 @@ int dp_dwconv_fwd(const void* x, long long x_ld, int B, int Hi, int Wi, int C, c
     do {                                                                                                  \
       cudaError_t e = cudaFuncSetAttribute(dw_tile_kernel<KK, TWW, CGG, RR, XX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       if (e != cudaSuccess) return dp_set_error(DP_ERR_CUDA, "dw_tile_kernel smem %zu: %s", smem, cudaGetErrorString(e));       \
-      dw_tile_kernel<KK, TWW, CGG, RR, XX><<<grid, TPB, smem, stream>>>(tm, a);                             \
+      dp::launch(dw_tile_kernel<KK, TWW, CGG, RR, XX>, grid, TPB, smem, stream, tm, a);                             \
     } while (0)
     if (K == 3 && p.TW == 8) DP_DW_TILE(3, 8, 8, 4, 2);
     else if (K == 5 && p.TW == 8) DP_DW_TILE(5, 8, 8, 2, 2);
@@ -826,10 +833,10 @@ int dp_dwconv_fwd(const void* x, long long x_ld, int B, int Hi, int Wi, int C, c
   }
   dim3 grid(dp_dwconv_fwd_blocks(B, Ho, Wo, C), (C / 8 + G - 1) / G);
   const size_t smem = ((size_t)K * K * G * 8 + (stats_partials ? (size_t)TPB * 16 : 0)) * sizeof(float);
-  if (K == 3 && stride == 1) dw_fwd_kernel<3, 1><<<grid, TPB, smem, stream>>>(a);
-  else if (K == 3) dw_fwd_kernel<3, 2><<<grid, TPB, smem, stream>>>(a);
-  else if (stride == 1) dw_fwd_kernel<5, 1><<<grid, TPB, smem, stream>>>(a);
-  else dw_fwd_kernel<5, 2><<<grid, TPB, smem, stream>>>(a);
+  if (K == 3 && stride == 1) dp::launch(dw_fwd_kernel<3, 1>, grid, TPB, smem, stream, a);
+  else if (K == 3) dp::launch(dw_fwd_kernel<3, 2>, grid, TPB, smem, stream, a);
+  else if (stride == 1) dp::launch(dw_fwd_kernel<5, 1>, grid, TPB, smem, stream, a);
+  else dp::launch(dw_fwd_kernel<5, 2>, grid, TPB, smem, stream, a);
   DP_CHECK_LAUNCH("dw_fwd_kernel");
   return DP_OK;
 }
@@ -859,7 +866,7 @@ int dp_dwconv_dgrad_s2(const void* dy, long long dy_ld, int B, int Ho, int Wo, i
     do {                                                                                                                   \
       cudaError_t e = cudaFuncSetAttribute(dw_dgrad_s2_tile_kernel<KK, EYY, EXX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       if (e != cudaSuccess) return dp_set_error(DP_ERR_CUDA, "dw_dgrad_s2_tile_kernel smem %zu: %s", smem, cudaGetErrorString(e)); \
-      dw_dgrad_s2_tile_kernel<KK, EYY, EXX><<<grid2, TPB, smem, stream>>>(tmg, B, Hi, Wi, C, w, pad_t, pad_l, dxb, dx_ld);  \
+      dp::launch(dw_dgrad_s2_tile_kernel<KK, EYY, EXX>, grid2, TPB, smem, stream, tmg, B, Hi, Wi, C, w, pad_t, pad_l, dxb, dx_ld);  \
     } while (0)
     const int ey = pad_t & 1, ex = pad_l & 1;
     if (K == 3) {
@@ -873,10 +880,10 @@ int dp_dwconv_dgrad_s2(const void* dy, long long dy_ld, int B, int Ho, int Wo, i
   }
   const int grid = dw_grid((long long)B * Hi * Wi * (C / 8));
   if (K == 3)
-    dw_dgrad_s2_kernel<3><<<grid, TPB, 0, stream>>>(reinterpret_cast<const bf16*>(dy), dy_ld, B, Ho, Wo, C, w, pad_t, pad_l,
+    dp::launch(dw_dgrad_s2_kernel<3>, grid, TPB, 0, stream, reinterpret_cast<const bf16*>(dy), dy_ld, B, Ho, Wo, C, w, pad_t, pad_l,
                                                     reinterpret_cast<bf16*>(dx), dx_ld, Hi, Wi);
   else
-    dw_dgrad_s2_kernel<5><<<grid, TPB, 0, stream>>>(reinterpret_cast<const bf16*>(dy), dy_ld, B, Ho, Wo, C, w, pad_t, pad_l,
+    dp::launch(dw_dgrad_s2_kernel<5>, grid, TPB, 0, stream, reinterpret_cast<const bf16*>(dy), dy_ld, B, Ho, Wo, C, w, pad_t, pad_l,
                                                     reinterpret_cast<bf16*>(dx), dx_ld, Hi, Wi);
   DP_CHECK_LAUNCH("dw_dgrad_s2_kernel");
   return DP_OK;
@@ -920,7 +927,7 @@ int dp_dwconv_wgrad(const void* x, long long x_ld, int B, int Hi, int Wi, int C,
     do {                                                                                                                   \
       cudaError_t e = cudaFuncSetAttribute(dw_wgrad_tile_kernel<KK, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       if (e != cudaSuccess) return dp_set_error(DP_ERR_CUDA, "dw_wgrad_tile_kernel smem %zu: %s", smem, cudaGetErrorString(e)); \
-      dw_wgrad_tile_kernel<KK, SS><<<grid, TPB, smem, stream>>>(tmx, tmg, B, Ho, Wo, C, pad_t, pad_l, partial);            \
+      dp::launch(dw_wgrad_tile_kernel<KK, SS>, grid, TPB, smem, stream, tmx, tmg, B, Ho, Wo, C, pad_t, pad_l, partial);            \
     } while (0)
     if (K == 3 && S == 1) DP_DW_WT(3, 1);
     else if (K == 3) DP_DW_WT(3, 2);
@@ -928,7 +935,7 @@ int dp_dwconv_wgrad(const void* x, long long x_ld, int B, int Hi, int Wi, int C,
     else DP_DW_WT(5, 2);
 #undef DP_DW_WT
     DP_CHECK_LAUNCH("dw_wgrad_tile_kernel");
-    dw_wgrad_reduce_kernel<<<dp::ceil_div(K * K * C, 32), 1024, 0, stream>>>(partial, nx, K * K, C, grad, accumulate);
+    dp::launch(dw_wgrad_reduce_kernel, dp::ceil_div(K * K * C, 32), 1024, 0, stream, partial, nx, K * K, C, grad, accumulate);
     DP_CHECK_LAUNCH("dw_wgrad_reduce_kernel");
     return DP_OK;
   }
@@ -938,12 +945,12 @@ int dp_dwconv_wgrad(const void* x, long long x_ld, int B, int Hi, int Wi, int C,
   const size_t smem = (size_t)TPB * K * 8 * sizeof(float);
   const bf16* xb = reinterpret_cast<const bf16*>(x);
   const bf16* gb = reinterpret_cast<const bf16*>(dy);
-  if (K == 3 && stride == 1) dw_wgrad_kernel<3, 1><<<grid, TPB, smem, stream>>>(xb, x_ld, B, Hi, Wi, C, gb, dy_ld, Ho, Wo, pad_t, pad_l, nchunks, partial);
-  else if (K == 3) dw_wgrad_kernel<3, 2><<<grid, TPB, smem, stream>>>(xb, x_ld, B, Hi, Wi, C, gb, dy_ld, Ho, Wo, pad_t, pad_l, nchunks, partial);
-  else if (stride == 1) dw_wgrad_kernel<5, 1><<<grid, TPB, smem, stream>>>(xb, x_ld, B, Hi, Wi, C, gb, dy_ld, Ho, Wo, pad_t, pad_l, nchunks, partial);
-  else dw_wgrad_kernel<5, 2><<<grid, TPB, smem, stream>>>(xb, x_ld, B, Hi, Wi, C, gb, dy_ld, Ho, Wo, pad_t, pad_l, nchunks, partial);
+  if (K == 3 && stride == 1) dp::launch(dw_wgrad_kernel<3, 1>, grid, TPB, smem, stream, xb, x_ld, B, Hi, Wi, C, gb, dy_ld, Ho, Wo, pad_t, pad_l, nchunks, partial);
+  else if (K == 3) dp::launch(dw_wgrad_kernel<3, 2>, grid, TPB, smem, stream, xb, x_ld, B, Hi, Wi, C, gb, dy_ld, Ho, Wo, pad_t, pad_l, nchunks, partial);
+  else if (stride == 1) dp::launch(dw_wgrad_kernel<5, 1>, grid, TPB, smem, stream, xb, x_ld, B, Hi, Wi, C, gb, dy_ld, Ho, Wo, pad_t, pad_l, nchunks, partial);
+  else dp::launch(dw_wgrad_kernel<5, 2>, grid, TPB, smem, stream, xb, x_ld, B, Hi, Wi, C, gb, dy_ld, Ho, Wo, pad_t, pad_l, nchunks, partial);
   DP_CHECK_LAUNCH("dw_wgrad_kernel");
-  dw_wgrad_reduce_kernel<<<dp::ceil_div(K * K * C, 32), 1024, 0, stream>>>(partial, nchunks, K * K, C, grad, accumulate);
+  dp::launch(dw_wgrad_reduce_kernel, dp::ceil_div(K * K * C, 32), 1024, 0, stream, partial, nchunks, K * K, C, grad, accumulate);
   DP_CHECK_LAUNCH("dw_wgrad_reduce_kernel");
   return DP_OK;
 }

@@ -3,6 +3,7 @@
 #include "../../include/depth_b200.h"
 #include <atomic>
 #include <cstring>
+#include <cstdlib>
 
 static thread_local char g_err[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
@@ -13,6 +14,11 @@ int dp_set_error(int code, const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
+}
+
+int dp_pdl_enabled(void) {
+  static const int on = [] { const char* e = getenv("DP_PDL"); return e ? (atoi(e) != 0) : 1; }();
+  return on;
 }
 
 void dp_count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }

@@ -48,6 +48,7 @@ inline int grid_for(size_t items, int tpb = 256, int max_waves = 8) {
 // out = (ga ? ga : 0) + (gb ? gb * (y > 0) : 0)            (vectors of 8)
 __global__ void add_relu_bwd_kernel(const bf16* __restrict__ ga, const bf16* __restrict__ gb, const bf16* __restrict__ y,
                                     bf16* __restrict__ out, size_t n8) {
+  dp::pdl_prologue();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
     float a[8], b[8], yy[8], o[8];
     if (ga) unpack8(ld8(ga + i * 8), a);
@@ -59,6 +60,7 @@ __global__ void add_relu_bwd_kernel(const bf16* __restrict__ ga, const bf16* __r
 }
 
 __global__ void relu_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, size_t n8) {
+  dp::pdl_prologue();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
     float v[8];
     unpack8(ld8(x + i * 8), v);
@@ -71,6 +73,7 @@ __global__ void relu_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, 
 // out = a + b (+ c)
 __global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, const bf16* __restrict__ c,
                            bf16* __restrict__ out, size_t n8) {
+  dp::pdl_prologue();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
     float x[8], y[8], z[8], o[8];
     unpack8(ld8(a + i * 8), x);
@@ -87,6 +90,7 @@ __global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ 
 template <typename IDX>
 __global__ void copy_channels_kernel(const bf16* __restrict__ src, long long src_ld, bf16* __restrict__ dst,
                                      long long dst_ld, size_t npix, int C8) {
+  dp::pdl_prologue();
   const IDX total = (IDX)(npix * C8);
   const IDX stride = (IDX)gridDim.x * blockDim.x;
   for (IDX i = (IDX)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -126,6 +130,7 @@ __device__ __forceinline__ void vlerp_store(const float (&h)[4][8], float hy, fl
 __global__ void __launch_bounds__(256, 2) resize_fwd_kernel(const bf16* __restrict__ src, long long src_ld, int B, int Hi,
                                                             int Wi, int C, bf16* __restrict__ dst, long long dst_ld,
                                                             int Ho, int Wo, int align, float sy, float sx) {
+  dp::pdl_prologue();
   const int C8 = C / 8;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Wo * C8) return;
@@ -201,6 +206,7 @@ __global__ void __launch_bounds__(256, 2) resize_fwd_kernel(const bf16* __restri
 // fp32 variant for the (B,3,H,W) RGB -> DINOv2 input resize and the (B,1,H,W) prediction resize (NCHW planes)
 __global__ void resize_planes_f32_kernel(const float* __restrict__ src, int planes, int Hi, int Wi,
                                          float* __restrict__ dst, int Ho, int Wo, int align) {
+  dp::pdl_prologue();
   const size_t total = (size_t)planes * Ho * Wo;
   const float sy = resize_scale(Hi, Ho, align), sx = resize_scale(Wi, Wo, align);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -262,6 +268,7 @@ __global__ void __launch_bounds__(256, 4) resize_bwd_kernel(const bf16* __restri
                                                             int Wi, int C, bf16* __restrict__ gin, long long gin_ld,
                                                             int Ho, int Wo, int align, float sy, float sx, float inv_sy,
                                                             float inv_sx) {
+  dp::pdl_prologue();
   constexpr int RW = 4;
   const int C8 = C / 8;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -331,6 +338,7 @@ __global__ void __launch_bounds__(RED_TPB) chan_reduce_kernel(const bf16* __rest
                                                               const bf16* __restrict__ mask, long long m_ld,
                                                               size_t npix, int C, float* __restrict__ partial,
                                                               float mask_hi, const float* __restrict__ mask_ss) {
+  dp::pdl_prologue();
   extern __shared__ float sred[];  // [2][lanes][C]
   const int C8 = C / 8;
   const int lanes = RED_TPB / C8;  // pixel lanes per block (C8 <= 64 -> lanes >= 4); threads beyond lanes*C8 idle
@@ -422,6 +430,7 @@ __global__ void __launch_bounds__(32 * kPartLanes) bn_finalize_kernel(const floa
                                    float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                                    long long* __restrict__ num_batches, float* __restrict__ scale_shift,
                                    float* __restrict__ save) {
+  dp::pdl_prologue();
   // block = 32 channels x kPartLanes partial lanes: coalesced 128-byte rows of the partials, fixed-order fp64 folding
   __shared__ double s_s[kPartLanes][32], s_q[kPartLanes][32];
   const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
@@ -461,6 +470,7 @@ __global__ void __launch_bounds__(32 * kPartLanes) bn_finalize_kernel(const floa
 __global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                       const float* __restrict__ rm, const float* __restrict__ rv, float eps, int C,
                                       float* __restrict__ scale_shift, float* __restrict__ save) {
+  dp::pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float invstd = 1.f / sqrtf(rv[c] + eps);
@@ -478,6 +488,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ 
                                 const bf16* __restrict__ x2, long long x2_ld, const float* __restrict__ ss2,
                                 const bf16* __restrict__ res, long long res_ld, size_t npix, int C, int relu,
                                 bf16* __restrict__ y, long long y_ld) {
+  dp::pdl_prologue();
   const int C8 = C / 8;
   const size_t total = npix * C8;
   const size_t nthreads = (size_t)gridDim.x * blockDim.x;
@@ -533,6 +544,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
                                     bf16* __restrict__ dx, long long dx_ld, bf16* __restrict__ gmask, long long gm_ld,
                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
                                     float mask_hi, const float* __restrict__ mask_ss) {
+  dp::pdl_prologue();
   const int C8 = C / 8;
   if (blockIdx.x == 0 && dgamma) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -614,6 +626,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
 
 __global__ void __launch_bounds__(32 * kPartLanes) sum_partials_kernel(const float* __restrict__ partial, int nparts, int rows, int C,
                                     float* __restrict__ out, int accumulate) {
+  dp::pdl_prologue();
   // block = 32 columns x kPartLanes partial lanes over the flattened [rows*C] vector; partial stride is 2*C per part
   __shared__ double s_s[kPartLanes][32];
   const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
@@ -641,7 +654,7 @@ extern "C" {
 int dp_add_relu_bwd(const void* g_raw, const void* g_relu, const void* y, void* out, size_t n, cudaStream_t stream) {
   DP_CHECK_ARG(out && (g_raw || g_relu) && (!g_relu || y) && n % 8 == 0, "dp_add_relu_bwd: bad arguments");
   if (n == 0) return DP_OK;
-  add_relu_bwd_kernel<<<grid_for(n / 8), 256, 0, stream>>>((const bf16*)g_raw, (const bf16*)g_relu, (const bf16*)y,
+  dp::launch(add_relu_bwd_kernel, grid_for(n / 8), 256, 0, stream, (const bf16*)g_raw, (const bf16*)g_relu, (const bf16*)y,
                                                            (bf16*)out, n / 8);
   DP_CHECK_LAUNCH("add_relu_bwd_kernel");
   return DP_OK;
@@ -650,7 +663,7 @@ int dp_add_relu_bwd(const void* g_raw, const void* g_relu, const void* y, void* 
 int dp_relu_bf16(const void* x, void* out, size_t n, cudaStream_t stream) {
   DP_CHECK_ARG(x && out && n % 8 == 0, "dp_relu_bf16: bad arguments");
   if (n == 0) return DP_OK;
-  relu_kernel<<<grid_for(n / 8), 256, 0, stream>>>((const bf16*)x, (bf16*)out, n / 8);
+  dp::launch(relu_kernel, grid_for(n / 8), 256, 0, stream, (const bf16*)x, (bf16*)out, n / 8);
   DP_CHECK_LAUNCH("relu_kernel");
   return DP_OK;
 }
@@ -658,7 +671,7 @@ int dp_relu_bf16(const void* x, void* out, size_t n, cudaStream_t stream) {
 int dp_add_bf16(const void* a, const void* b, const void* c, void* out, size_t n, cudaStream_t stream) {
   DP_CHECK_ARG(a && b && out && n % 8 == 0, "dp_add_bf16: bad arguments");
   if (n == 0) return DP_OK;
-  add_kernel<<<grid_for(n / 8), 256, 0, stream>>>((const bf16*)a, (const bf16*)b, (const bf16*)c, (bf16*)out, n / 8);
+  dp::launch(add_kernel, grid_for(n / 8), 256, 0, stream, (const bf16*)a, (const bf16*)b, (const bf16*)c, (bf16*)out, n / 8);
   DP_CHECK_LAUNCH("add_kernel");
   return DP_OK;
 }
@@ -669,9 +682,9 @@ int dp_copy_channels(const void* src, long long src_ld, void* dst, long long dst
   if (npix == 0) return DP_OK;
   const size_t items = npix * (C / 8);
   if (items < (size_t)0x7fffff00u)
-    copy_channels_kernel<unsigned><<<grid_for(items), 256, 0, stream>>>((const bf16*)src, src_ld, (bf16*)dst, dst_ld, npix, C / 8);
+    dp::launch(copy_channels_kernel<unsigned>, grid_for(items), 256, 0, stream, (const bf16*)src, src_ld, (bf16*)dst, dst_ld, npix, C / 8);
   else
-    copy_channels_kernel<size_t><<<grid_for(items), 256, 0, stream>>>((const bf16*)src, src_ld, (bf16*)dst, dst_ld, npix, C / 8);
+    dp::launch(copy_channels_kernel<size_t>, grid_for(items), 256, 0, stream, (const bf16*)src, src_ld, (bf16*)dst, dst_ld, npix, C / 8);
   DP_CHECK_LAUNCH("copy_channels_kernel");
   return DP_OK;
 }
@@ -681,7 +694,7 @@ int dp_resize_bilinear_nhwc(const void* src, long long src_ld, int B, int Hi, in
   DP_CHECK_ARG(src && dst && C % 8 == 0 && src_ld % 8 == 0 && dst_ld % 8 == 0, "dp_resize_bilinear_nhwc: bad arguments");
   DP_CHECK_ARG(B > 0 && B <= 65535 && Ho > 0 && Ho <= 65535, "dp_resize_bilinear_nhwc: B / Ho out of the grid range");
   const dim3 grid((unsigned)(((size_t)Wo * (C / 8) + 255) / 256), (unsigned)((Ho + kRsRows - 1) / kRsRows), (unsigned)B);
-  resize_fwd_kernel<<<grid, 256, 0, stream>>>((const bf16*)src, src_ld, B, Hi, Wi, C, (bf16*)dst, dst_ld, Ho, Wo,
+  dp::launch(resize_fwd_kernel, grid, 256, 0, stream, (const bf16*)src, src_ld, B, Hi, Wi, C, (bf16*)dst, dst_ld, Ho, Wo,
                                               align_corners, resize_scale(Hi, Ho, align_corners),
                                               resize_scale(Wi, Wo, align_corners));
   DP_CHECK_LAUNCH("resize_fwd_kernel");
@@ -694,7 +707,7 @@ int dp_resize_bilinear_nhwc_bwd(const void* gout, long long g_ld, int B, int Hi,
   DP_CHECK_ARG(B > 0 && B <= 65535 && Hi > 0 && Hi <= 65535, "dp_resize_bilinear_nhwc_bwd: B / Hi out of the grid range");
   const dim3 grid((unsigned)(((size_t)Wi * (C / 8) + 255) / 256), (unsigned)Hi, (unsigned)B);
   const float sy = resize_scale(Hi, Ho, align_corners), sx = resize_scale(Wi, Wo, align_corners);
-  resize_bwd_kernel<<<grid, 256, 0, stream>>>((const bf16*)gout, g_ld, B, Hi, Wi, C, (bf16*)gin, gin_ld, Ho, Wo,
+  dp::launch(resize_bwd_kernel, grid, 256, 0, stream, (const bf16*)gout, g_ld, B, Hi, Wi, C, (bf16*)gin, gin_ld, Ho, Wo,
                                               align_corners, sy, sx, sy > 0.f ? 1.f / sy : 0.f, sx > 0.f ? 1.f / sx : 0.f);
   DP_CHECK_LAUNCH("resize_bwd_kernel");
   return DP_OK;
@@ -704,7 +717,7 @@ int dp_resize_bilinear_planes_f32(const float* src, int planes, int Hi, int Wi, 
                                   int align_corners, cudaStream_t stream) {
   DP_CHECK_ARG(src && dst && planes > 0, "dp_resize_bilinear_planes_f32: bad arguments");
   const size_t items = (size_t)planes * Ho * Wo;
-  resize_planes_f32_kernel<<<grid_for(items), 256, 0, stream>>>(src, planes, Hi, Wi, dst, Ho, Wo, align_corners);
+  dp::launch(resize_planes_f32_kernel, grid_for(items), 256, 0, stream, src, planes, Hi, Wi, dst, Ho, Wo, align_corners);
   DP_CHECK_LAUNCH("resize_planes_f32_kernel");
   return DP_OK;
 }
@@ -722,11 +735,11 @@ int dp_chan_reduce(int mode, const void* x, long long x_ld, const void* dy, long
   const int lanes = RED_TPB / C8;
   const size_t smem = (size_t)2 * lanes * C * sizeof(float);
   if (mode == 0)
-    chan_reduce_kernel<0><<<kRedBlocks, RED_TPB, smem, stream>>>((const bf16*)x, x_ld, nullptr, 0, nullptr, 0, npix, C, partial, mask_hi, nullptr);
+    dp::launch(chan_reduce_kernel<0>, kRedBlocks, RED_TPB, smem, stream, (const bf16*)x, x_ld, nullptr, 0, nullptr, 0, npix, C, partial, mask_hi, nullptr);
   else if (mode == 1)
-    chan_reduce_kernel<1><<<kRedBlocks, RED_TPB, smem, stream>>>((const bf16*)x, x_ld, nullptr, 0, nullptr, 0, npix, C, partial, mask_hi, nullptr);
+    dp::launch(chan_reduce_kernel<1>, kRedBlocks, RED_TPB, smem, stream, (const bf16*)x, x_ld, nullptr, 0, nullptr, 0, npix, C, partial, mask_hi, nullptr);
   else
-    chan_reduce_kernel<2><<<kRedBlocks, RED_TPB, smem, stream>>>((const bf16*)x, x_ld, (const bf16*)dy, dy_ld,
+    dp::launch(chan_reduce_kernel<2>, kRedBlocks, RED_TPB, smem, stream, (const bf16*)x, x_ld, (const bf16*)dy, dy_ld,
                                                                  (const bf16*)mask, m_ld, npix, C, partial, mask_hi, mask_ss);
   DP_CHECK_LAUNCH("chan_reduce_kernel");
   return DP_OK;
@@ -734,7 +747,7 @@ int dp_chan_reduce(int mode, const void* x, long long x_ld, const void* dy, long
 
 int dp_sum_partials(const float* partial, int nparts, int rows, int C, float* out, int accumulate, cudaStream_t stream) {
   DP_CHECK_ARG(partial && out && rows >= 1 && rows <= 2, "dp_sum_partials: bad arguments");
-  sum_partials_kernel<<<dp::ceil_div(rows * C, 32), 32 * kPartLanes, 0, stream>>>(partial, nparts, rows, C, out, accumulate);
+  dp::launch(sum_partials_kernel, dp::ceil_div(rows * C, 32), 32 * kPartLanes, 0, stream, partial, nparts, rows, C, out, accumulate);
   DP_CHECK_LAUNCH("sum_partials_kernel");
   return DP_OK;
 }
@@ -743,7 +756,7 @@ int dp_bn_finalize(const float* partial, int nparts, int C, double count, const 
                    float eps, float momentum, float* running_mean, float* running_var, long long* num_batches_tracked,
                    float* scale_shift, float* save_mean_invstd, cudaStream_t stream) {
   DP_CHECK_ARG(partial && scale_shift && save_mean_invstd && C > 0 && count > 0, "dp_bn_finalize: bad arguments");
-  bn_finalize_kernel<<<dp::ceil_div(C, 32), 32 * kPartLanes, 0, stream>>>(partial, nparts, C, count, gamma, beta, eps, momentum,
+  dp::launch(bn_finalize_kernel, dp::ceil_div(C, 32), 32 * kPartLanes, 0, stream, partial, nparts, C, count, gamma, beta, eps, momentum,
                                                                running_mean, running_var, num_batches_tracked,
                                                                scale_shift, save_mean_invstd);
   DP_CHECK_LAUNCH("bn_finalize_kernel");
@@ -753,7 +766,7 @@ int dp_bn_finalize(const float* partial, int nparts, int C, double count, const 
 int dp_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                       float eps, int C, float* scale_shift, float* save_mean_invstd, cudaStream_t stream) {
   DP_CHECK_ARG(running_mean && running_var && scale_shift && save_mean_invstd, "dp_bn_eval_coeffs: null pointer");
-  bn_eval_coeffs_kernel<<<dp::ceil_div(C, 128), 128, 0, stream>>>(gamma, beta, running_mean, running_var, eps, C,
+  dp::launch(bn_eval_coeffs_kernel, dp::ceil_div(C, 128), 128, 0, stream, gamma, beta, running_mean, running_var, eps, C,
                                                                   scale_shift, save_mean_invstd);
   DP_CHECK_LAUNCH("bn_eval_coeffs_kernel");
   return DP_OK;
@@ -763,7 +776,7 @@ int dp_bn_apply(const void* x, long long x_ld, const float* scale_shift, const v
                 const float* scale_shift2, const void* res, long long res_ld, size_t npix, int C, int relu, void* y,
                 long long y_ld, cudaStream_t stream) {
   DP_CHECK_ARG(x && scale_shift && y && C % 8 == 0 && (!x2 || scale_shift2), "dp_bn_apply: bad arguments");
-  bn_apply_kernel<<<grid_for(npix * (C / 8)), 256, 0, stream>>>((const bf16*)x, x_ld, scale_shift, (const bf16*)x2, x2_ld,
+  dp::launch(bn_apply_kernel, grid_for(npix * (C / 8)), 256, 0, stream, (const bf16*)x, x_ld, scale_shift, (const bf16*)x2, x2_ld,
                                                                 scale_shift2, (const bf16*)res, res_ld, npix, C, relu,
                                                                 (bf16*)y, y_ld);
   DP_CHECK_LAUNCH("bn_apply_kernel");
@@ -778,7 +791,7 @@ int dp_bn_bwd_apply(const void* dy, long long dy_ld, const void* mask, long long
   DP_CHECK_ARG(!dx || (x && save_mean_invstd && (!train || red)), "dp_bn_bwd_apply: missing statistics");
   DP_CHECK_ARG(!dgamma || (dbeta && red && save_mean_invstd), "dp_bn_bwd_apply: dgamma needs dbeta, red and save");
   // train: bit 0 = batch statistics (train mode); bit 1 = the mask is a ReLU6 output (gradient passes for 0 < mask < 6)
-  bn_bwd_apply_kernel<<<grid_for(npix * (C / 8)), 256, 0, stream>>>(
+  dp::launch(bn_bwd_apply_kernel, grid_for(npix * (C / 8)), 256, 0, stream, 
       (const bf16*)dy, dy_ld, (const bf16*)mask, m_ld, (const bf16*)x, x_ld, red, save_mean_invstd, gamma, count, train & 1,
       npix, C, (bf16*)dx, dx_ld, (bf16*)gmask, gm_ld, dgamma, dbeta, accumulate, (train & 2) ? 6.f : INFINITY, mask_ss);
   DP_CHECK_LAUNCH("bn_bwd_apply_kernel");

@@ -10,6 +10,7 @@ namespace {
 
 // (B,C,H,W) fp32 -> (B,H,W,ld) bf16: 32 pixels x 32 channels tiles through shared memory
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int C, int HW, bf16* __restrict__ dst, long long ld) {
+  dp::pdl_prologue();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -30,6 +31,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int C, int HW
 // coalesced across the warp, one 16-byte store per pixel with the pad channels written as zeros
 __global__ void __launch_bounds__(256) nchw_to_nhwc8_kernel(const float* __restrict__ src, int C, int HW,
                                                             bf16* __restrict__ dst) {
+  dp::pdl_prologue();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= HW) return;
   const float* s = src + (size_t)blockIdx.y * C * HW + p;
@@ -46,6 +48,7 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc8_kernel(const float* __restr
 }
 
 __global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ src, long long ld, int C, int HW, float* __restrict__ dst) {
+  dp::pdl_prologue();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -63,10 +66,12 @@ __global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ src, long long ld, 
 }
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n) {
+  dp::pdl_prologue();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     dst[i] = __float2bfloat16_rn(__ldg(src + i));
 }
 __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, size_t n) {
+  dp::pdl_prologue();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     dst[i] = __bfloat162float(src[i]);
 }
@@ -74,6 +79,7 @@ __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __rest
 // weight [D0][D1][KH][KW] fp32 -> bf16 [tap'][A][ld], (A, b) = swap ? (D1, d0) : (D0, d1); tap' reversed when flip
 __global__ void pack_weight_kernel(const float* __restrict__ w, int D0, int D1, int KH, int KW, int swap, int flip,
                                    bf16* __restrict__ dst, int ld) {
+  dp::pdl_prologue();
   const long long total = (long long)D0 * D1 * KH * KW;
   const int taps = KH * KW;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -90,6 +96,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int D0, int D1, 
 // All weight packs of a step in ONE launch (a train step needs ~230: forward and data-gradient layout of every
 // convolution; one tiny kernel each costs more in launch gaps than in work).  blockIdx.y = descriptor.
 __global__ void pack_weights_batched_kernel(const dp_pack_desc_t* __restrict__ descs) {
+  dp::pdl_prologue();
   const dp_pack_desc_t d = descs[blockIdx.y];
   const float* __restrict__ w = reinterpret_cast<const float*>(d.src);
   bf16* __restrict__ dst = reinterpret_cast<bf16*>(d.dst);
@@ -112,7 +119,7 @@ extern "C" {
 
 int dp_pack_conv_weights_batched(const dp_pack_desc_t* descs_device, int n, int blocks_per_weight, cudaStream_t stream) {
   DP_CHECK_ARG(descs_device && n > 0 && n <= 65535 && blocks_per_weight > 0, "dp_pack_conv_weights_batched: bad arguments");
-  pack_weights_batched_kernel<<<dim3(blocks_per_weight, n), 256, 0, stream>>>(descs_device);
+  dp::launch(pack_weights_batched_kernel, dim3(blocks_per_weight, n), 256, 0, stream, descs_device);
   DP_CHECK_LAUNCH("pack_weights_batched_kernel");
   return DP_OK;
 }
@@ -122,12 +129,12 @@ int dp_nchw_f32_to_nhwc_bf16(const float* src, int B, int C, int H, int W, void*
   DP_CHECK_ARG(src && dst && B > 0 && C > 0 && dst_ld >= C, "dp_nchw_f32_to_nhwc_bf16: bad arguments");
   const int HW = H * W;
   if (C <= 8 && dst_ld == 8 && B <= 65535 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-    nchw_to_nhwc8_kernel<<<dim3(dp::ceil_div(HW, 256), B), 256, 0, stream>>>(src, C, HW, reinterpret_cast<bf16*>(dst));
+    dp::launch(nchw_to_nhwc8_kernel, dim3(dp::ceil_div(HW, 256), B), 256, 0, stream, src, C, HW, reinterpret_cast<bf16*>(dst));
     DP_CHECK_LAUNCH("nchw_to_nhwc8_kernel");
     return DP_OK;
   }
   dim3 grid(dp::ceil_div(HW, 32), dp::ceil_div(C, 32), B), block(32, 8);
-  nchw_to_nhwc_kernel<<<grid, block, 0, stream>>>(src, C, HW, reinterpret_cast<bf16*>(dst), dst_ld);
+  dp::launch(nchw_to_nhwc_kernel, grid, block, 0, stream, src, C, HW, reinterpret_cast<bf16*>(dst), dst_ld);
   DP_CHECK_LAUNCH("nchw_to_nhwc_kernel");
   return DP_OK;
 }
@@ -137,7 +144,7 @@ int dp_nhwc_bf16_to_nchw_f32(const void* src, long long src_ld, int B, int C, in
   DP_CHECK_ARG(src && dst && B > 0 && C > 0 && src_ld >= C, "dp_nhwc_bf16_to_nchw_f32: bad arguments");
   const int HW = H * W;
   dim3 grid(dp::ceil_div(HW, 32), dp::ceil_div(C, 32), B), block(32, 8);
-  nhwc_to_nchw_kernel<<<grid, block, 0, stream>>>(reinterpret_cast<const bf16*>(src), src_ld, C, HW, dst);
+  dp::launch(nhwc_to_nchw_kernel, grid, block, 0, stream, reinterpret_cast<const bf16*>(src), src_ld, C, HW, dst);
   DP_CHECK_LAUNCH("nhwc_to_nchw_kernel");
   return DP_OK;
 }
@@ -147,7 +154,7 @@ int dp_cast_f32_to_bf16(const float* src, void* dst, size_t n, cudaStream_t stre
   if (n == 0) return DP_OK;
   int blocks = (int)((n + 255) / 256);
   if (blocks > 8 * dp::kNumSMs) blocks = 8 * dp::kNumSMs;
-  cast_f32_bf16_kernel<<<blocks, 256, 0, stream>>>(src, reinterpret_cast<bf16*>(dst), n);
+  dp::launch(cast_f32_bf16_kernel, blocks, 256, 0, stream, src, reinterpret_cast<bf16*>(dst), n);
   DP_CHECK_LAUNCH("cast_f32_bf16_kernel");
   return DP_OK;
 }
@@ -157,7 +164,7 @@ int dp_cast_bf16_to_f32(const void* src, float* dst, size_t n, cudaStream_t stre
   if (n == 0) return DP_OK;
   int blocks = (int)((n + 255) / 256);
   if (blocks > 8 * dp::kNumSMs) blocks = 8 * dp::kNumSMs;
-  cast_bf16_f32_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const bf16*>(src), dst, n);
+  dp::launch(cast_bf16_f32_kernel, blocks, 256, 0, stream, reinterpret_cast<const bf16*>(src), dst, n);
   DP_CHECK_LAUNCH("cast_bf16_f32_kernel");
   return DP_OK;
 }
@@ -169,7 +176,7 @@ int dp_pack_conv_weight(const float* w, int D0, int D1, int KH, int KW, int swap
   const long long total = (long long)D0 * D1 * KH * KW;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 8 * dp::kNumSMs) blocks = 8 * dp::kNumSMs;
-  pack_weight_kernel<<<blocks, 256, 0, stream>>>(w, D0, D1, KH, KW, swap, flip, reinterpret_cast<bf16*>(dst), ld);
+  dp::launch(pack_weight_kernel, blocks, 256, 0, stream, w, D0, D1, KH, KW, swap, flip, reinterpret_cast<bf16*>(dst), ld);
   DP_CHECK_LAUNCH("pack_weight_kernel");
   return DP_OK;
 }

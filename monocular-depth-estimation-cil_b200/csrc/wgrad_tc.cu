@@ -73,6 +73,7 @@ struct __align__(8) WgBars {
 
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ WgMaps tm, const __grid_constant__ WgArgs a) {
+  dp::pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   WgBars* bars = reinterpret_cast<WgBars*>(smem + (size_t)a.stages * a.stage_bytes);
@@ -93,6 +94,7 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps tm, const __grid_constant__ WgArg
     tc::prefetch_tmap(&tm.t[0]);
   }
   if (warp == 1) tc::tmem_alloc(&bars->tmem_base, 512);
+  dp::pdl_wait();   // global memory is touched from here on
   if (a.pre_ss && threadIdx.x >= 64) {
     const int i = threadIdx.x - 64;                 // 128 threads: [scale | shift] x 64 channels
     const int which = i >> 6, c = cc * a.NC + (i & 63);
@@ -267,6 +269,7 @@ wgrad_tc_kernel(const __grid_constant__ WgMaps tm, const __grid_constant__ WgArg
 // sum the split-K partials and write OIHW fp32: grad[co][ci][r][s] (+)= sum_ps partial[ps][tap][co][ci]
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int psplit, int taps, int Cout, int Cin,
                                     float* __restrict__ grad, int accumulate) {
+  dp::pdl_prologue();
   const long long total = (long long)taps * Cout * Cin;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     float s = 0.f;
@@ -464,12 +467,12 @@ int wg_launch(WgPlan& p, const void* P, long long p_ld, const WgPlaneT* planes /
   }
   cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
   if (e != cudaSuccess) return dp_set_error(DP_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  wgrad_tc_kernel<<<p.grid, kThreads, p.smem, stream>>>(tm, a);
+  dp::launch(wgrad_tc_kernel, p.grid, kThreads, p.smem, stream, tm, a);
   DP_CHECK_LAUNCH("wgrad_tc_kernel");
   const long long total = (long long)K * K * a.Cout * a.Cin;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 4 * dp::kNumSMs) blocks = 4 * dp::kNumSMs;
-  wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(a.partial, a.psplit, K * K, a.Cout, a.Cin, grad, accumulate);
+  dp::launch(wgrad_reduce_kernel, blocks, 256, 0, stream, a.partial, a.psplit, K * K, a.Cout, a.Cin, grad, accumulate);
   DP_CHECK_LAUNCH("wgrad_reduce_kernel");
   return DP_OK;
 }
