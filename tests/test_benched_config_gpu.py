@@ -130,12 +130,123 @@ def test_forward_backward_at_448x576(pkg):
     ratio = float(np.median([e / max(sa, 1e-9) for e, sa in rest.values()]))
     print(f"train-mode SI gradients, remaining {len(rest)} tensors: median drift ratio ours / stock autocast {ratio:.3f}")
     assert not bad, bad[:5]
-    # BatchNorm running statistics against the oracle after the FIRST step (one forward on identical weights): in-scope
-    # layers 5e-3, the PyTorch-run trunk 3e-2.  Later steps are not comparable layer by layer: AdamW's first updates are
-    # +-lr per weight whatever the gradient's size, so every weight whose (tiny) gradient changes sign between the fp32
-    # and the bf16 path moves the other way, and this random-init network has activations of magnitude ~100 entering
-    # cross_attention.spatial_reduction - measured (tools/diag_bnstats.py): its running_mean agrees to 2.5e-4 after step
-    # 1 and differs by 22 % on single channels after step 2 while the loss trajectories stay within 0.5 %.
+    bo = dict(ora.named_buffers())
+    for k, b in prod.named_buffers():
+        if k.startswith("dinov2."):
+            continue
+        if k.endswith("num_batches_tracked"):
+            assert int(b) == int(bo[k]), k
+        else:
+            assert rel_max(b.float(), bo[k].float()) <= 2e-3, (k, rel_max(b.float(), bo[k].float()))
+
+
+def test_eval_mode_gradients_absolute(pkg):
+    """The well-conditioned gradient check at the benched resolution: eval-mode BatchNorm (no batch-mean cancellation) and
+    a positive linear functional of the depth map.  Every in-scope parameter tensor within 5e-2 relative L2 of the fp32
+    oracle (measured worst 3.3e-2 in the DINOv2 head, most layers 1e-3), median <= 1e-2."""
+    ora, prod = _pair(pkg)
+    prod.fused_encoder = False
+    ora.eval(); prod.eval()
+    x, _ = _batch(4)
+    w = (torch.rand(4, H, W, generator=torch.Generator().manual_seed(5)) + 0.5).cuda()
+    (ora(x) * w).mean().backward()
+    (prod(x) * w).mean().backward()
+    go = dict(ora.named_parameters())
+    gmax = max(float(p.grad.norm()) for p in go.values() if p.grad is not None)
+    errs = {}
+    for k, p in prod.named_parameters():
+        if k.startswith(("dinov2.", "pretrained.")) or go[k].grad is None:
+            continue
+        if float(go[k].grad.norm()) < 1e-6 * gmax:
+            continue
+        errs[k] = rel_l2(p.grad, go[k].grad)
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:3]
+    med = float(np.median(list(errs.values())))
+    print(f"eval-mode gradients: {len(errs)} tensors, median {med:.4f}, worst {worst}")
+    assert worst[0][1] <= 5e-2 and med <= 1e-2, worst
+
+
+def test_fused_trunk_drift_not_worse_than_stock_autocast(pkg):
+    ora, prod = _pair(pkg)
+    x, t = _batch(4)
+    with torch.no_grad():
+        ref = ora(x)
+        out = prod(x)                                  # default path: fused trunk
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            auto = ora(x).float()
+    d_ours, d_auto = rel_l2(out, ref), rel_l2(auto, ref)
+    l_ref = ol.scale_invariant_loss(ref.unsqueeze(1), t).item()
+    l_ours = pkg.scale_invariant_loss(out.unsqueeze(1), t).item()
+    print(f"output drift from fp32: ours {d_ours:.4f}, stock bf16 autocast {d_auto:.4f}; loss {l_ours:.5f} vs {l_ref:.5f}")
+    assert d_ours <= 1.1 * d_auto
+    assert abs(l_ours - l_ref) <= 2e-2 * abs(l_ref)
+
+
+def _opt(model):
+    return torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=1e-4, fused=True,
+                             capturable=True)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_five_steps_graph_vs_eager_vs_oracle(pkg, fused):
+    """reference loop main.py:125-144: zero_grad, forward, combined_loss, backward, AdamW step - five times."""
+    ora, prod = _pair(pkg)
+    prod.fused_encoder = fused
+    eager = copy.deepcopy(prod)
+    cfg = fx.loss_config()
+    B, steps = 2, 5
+    batches = [_batch(B, seed=100 + i) for i in range(steps)]
+    # --- oracle (fp32) ---
+    opt_o = torch.optim.AdamW([p for p in ora.parameters() if p.requires_grad], lr=1e-4, weight_decay=1e-4)
+    loss_o = []
+    bo1 = None
+    for x, t in batches:
+        opt_o.zero_grad(set_to_none=True)
+        l = ol.scale_invariant_loss(ora(x).unsqueeze(1), t)
+        l.backward()
+        opt_o.step()
+        loss_o.append(l.item())
+        if bo1 is None:
+            bo1 = {k: v.detach().clone() for k, v in ora.named_buffers()}
+    # --- eager product steps (same body the graph captures, dispatched kernel by kernel) ---
+    opt_e = _opt(eager)
+    loss_e = []
+    for x, t in batches:
+        for p in eager.parameters():
+            p.grad = None
+        total, out = pkg.util.combined_loss_device(eager(x).unsqueeze(1), t, cfg, rgb=x)
+        total.backward()
+        opt_e.step()
+        loss_e.append(out[pkg._lib.L_TOTAL].item())
+    # --- graph replays ---
+    opt_g = _opt(prod)
+    before = {k: v.detach().clone() for k, v in prod.state_dict().items()}
+    gstep = pkg.GraphedTrainStep(prod, opt_g, cfg, batches[0][0], batches[0][1], use_rgb=True, world=1, warmup=2)
+    for k, v in prod.state_dict().items():        # the warm-up steps must leave no trace (ADVICE r1)
+        assert torch.equal(v, before[k]), f"GraphedTrainStep construction changed {k}"
+    loss_g = []
+    bg1 = None
+    for x, t in batches:
+        gstep(x, t)
+        loss_g.append(gstep.loss_dict()["total"])
+        if bg1 is None:
+            torch.cuda.synchronize()
+            bg1 = {k: v.detach().clone() for k, v in prod.named_buffers()}
+    torch.cuda.synchronize()
+    print("loss oracle", loss_o, "\nloss eager ", loss_e, "\nloss graph ", loss_g)
+    se, sg = eager.state_dict(), prod.state_dict()
+    if fused:
+        assert loss_g == loss_e, "graph replay must reproduce the eager step exactly"
+        for k in se:
+            assert torch.equal(se[k], sg[k]), f"graph vs eager: {k} differs after {steps} steps"
+    else:
+        # the PyTorch-run trunk is not bit-reproducible between eager dispatch and graph capture (cuDNN picks its
+        # algorithms per call): and the random-init network amplifies the
+        # last-bit differences step by step: the two trajectories agree to 5e-3 instead of bit for bit
+        for a, b in zip(loss_g, loss_e):
+            assert abs(a - b) <= 5e-3 * abs(b), (loss_g, loss_e)
+    for a, b in zip(loss_g, loss_o):
+        assert abs(a - b) <= 2e-2 * abs(b), (loss_g, loss_o)
     bo = dict(ora.named_buffers())
     for k, b in prod.named_buffers():
         if k.startswith("dinov2."):
@@ -143,6 +254,13 @@ def test_forward_backward_at_448x576(pkg):
         if k.endswith("num_batches_tracked"):
             assert int(b) == int(bo[k]), (k, int(b), int(bo[k]))
         elif not fused:
+            # BatchNorm running statistics against the oracle after the FIRST step (one forward on identical weights):
+            # in-scope layers 5e-3, the PyTorch-run trunk 3e-2 (run-to-run spread of the cuDNN trunk alone is ~1e-2).
+            # Later steps are not comparable layer by layer: AdamW's first updates are +-lr per weight whatever the
+            # gradient's size, so every weight whose (tiny) gradient changes sign between the fp32 and the bf16 path
+            # moves the other way, and this random-init network feeds activations of magnitude ~100 into
+            # cross_attention.spatial_reduction - measured (tools/diag_bnstats.py): its running_mean agrees to 2.5e-4
+            # after step 1 and differs by 22 % on single channels after step 2 while the losses stay within 0.5 %.
             tol = 3e-2 if k.startswith("pretrained.") else 5e-3
             assert rel_max(bg1[k].float(), bo1[k].float()) <= tol, (k, rel_max(bg1[k].float(), bo1[k].float()))
     assert int(prod.cross_attention.spatial_reduction[1].num_batches_tracked) == 2 * steps

@@ -41,6 +41,13 @@ conv_case("conv 3x3 32->32 @448x576 +stats", B, H, W, 32, 32, 3, stats=True)
 conv_case("conv 3x3 64->64 @448x576 +residual", B, H, W, 64, 64, 3, res=True)
 conv_case("conv 3x3 64->64 @448x576 +bn_prologue", B, H, W, 64, 64, 3, stats=True, pre=True)
 conv_case("conv 3x3 64->64 @448x576 +bn_backward", B, H, W, 64, 64, 3, mask=True)
+# EfficientNet-Lite3 trunk pointwise layers (expand / project) with BatchNorm statistics, and their weight gradients
+conv_case("conv 1x1 136->816 @28x36 +stats", B, 28, 36, 136, 816, 1, stats=True)
+conv_case("conv 1x1 816->136 @28x36 +stats", B, 28, 36, 816, 136, 1, stats=True)
+conv_case("conv 1x1 232->1392 @14x18 +stats", B, 14, 18, 232, 1392, 1, stats=True)
+conv_case("conv 1x1 32->192 @112x144 +stats", B, 112, 144, 32, 192, 1, stats=True)
+wgrad_case("wgrad 1x1 232->1392 @14x18", B, 14, 18, 232, 1392, 1)
+wgrad_case("wgrad 1x1 136->816 @28x36", B, 28, 36, 136, 816, 1)
 wgrad_case("wgrad 3x3 64->64 @448x576", B, H, W, 64, 64, 3)
 wgrad_case("wgrad 3x3 64->64 @448x576 +bn_prologue", B, H, W, 64, 64, 3, pre=True)
 
@@ -58,6 +65,16 @@ cases.append(("dwconv k5 s1 56x72x288", lambda: ops._dw_launch(xd, wd, 5, 1, 2, 
 xd3 = torch.randn(B, 112, 144, 192, device=dev).to(torch.bfloat16)
 wd3 = torch.randn(9, 192, device=dev)
 cases.append(("dwconv k3 s1 112x144x192", lambda: ops._dw_launch(xd3, wd3, 3, 1, 1, 1, 112, 144, True)))
+gd = torch.randn(B, 56, 72, 288, device=dev).to(torch.bfloat16)
+wsd = torch.empty(L.lib().dp_dwconv_wgrad_workspace(B, 56, 72, 288, 5), dtype=torch.uint8, device=dev)
+gwd = torch.empty(288, 1, 5, 5, device=dev)
+cases.append(("dw wgrad k5 s1 56x72x288", lambda: L.check(L.lib().dp_dwconv_wgrad(
+    L.ptr(xd), 288, B, 56, 72, 288, L.ptr(gd), 288, 56, 72, 5, 1, 2, 2, L.ptr(gwd), 0, L.ptr(wsd), wsd.numel(), L.stream()))))
+gs2 = torch.randn(B, 112, 144, 144, device=dev).to(torch.bfloat16)
+ws2 = torch.randn(9, 144, device=dev)
+dxs2 = torch.empty(B, 224, 288, 144, device=dev, dtype=torch.bfloat16)
+cases.append(("dw dgrad k3 s2 224x288x144", lambda: L.check(L.lib().dp_dwconv_dgrad_s2(
+    L.ptr(gs2), 144, B, 112, 144, 144, L.ptr(ws2), 3, 1, 1, L.ptr(dxs2), 144, 224, 288, L.stream()))))
 # bilinear resize backward (x2, 64 channels, 224x288 -> 112x144 gradient)
 gr = torch.randn(B, 224, 288, 64, device=dev).to(torch.bfloat16)
 gin = torch.empty(B, 112, 144, 64, device=dev, dtype=torch.bfloat16)
@@ -68,7 +85,10 @@ tt = torch.rand(650, 1, H, W, device=dev) * 9.9 + 0.1
 pp = tt * torch.exp(0.1 * torch.randn(650, 1, H, W, device=dev)) * 1.3
 cases.append(("evaluation_metrics default, 650 x 448x576", lambda: util.evaluation_metrics(pp, tt)))
 
+ONLY = os.environ.get("CASES")          # substring filter: capture a single case (source-level pages stay small)
 for name, fn in cases:
+    if ONLY and ONLY not in name:
+        continue
     fn(); fn()
     torch.cuda.synchronize()
     if PROFILE:
