@@ -566,6 +566,7 @@ __device__ __forceinline__ void epilogue_tma_wide(const Maps& tm, const ConvArgs
   const int m = ew * 32 + lane;
   const int py = m / a.tw, px = m - py * a.tw;
   const bool store_thread = threadIdx.x == kRoleThreads;
+  const int et = threadIdx.x - kRoleThreads;                  // 0 .. kEpiThreads - 1
   uint32_t soff[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -574,6 +575,11 @@ __device__ __forceinline__ void epilogue_tma_wide(const Maps& tm, const ConvArgs
   }
   const uint32_t s_base = tc::smem_u32(s_out);
   const int nsub = a.BN / 64;
+  float* grow = a.stats ? a.stats + (size_t)blockIdx.x * 2 * a.Cout : nullptr;    // this CTA's row of the partials
+  if (a.stats) {
+    for (int i = et; i < 2 * a.Cout; i += kEpiThreads) grow[i] = 0.f;
+    tc::named_bar_sync(1, kEpiThreads);
+  }
   int it = 0, ring = 0;
   TileIter ti;
   ti.init(a, blockIdx.x);
@@ -584,21 +590,32 @@ __device__ __forceinline__ void epilogue_tma_wide(const Maps& tm, const ConvArgs
     const int oy = y * a.osy + a.oay, ox = x * a.osx + a.oax;
     const bool valid = (y < a.H) && (x < a.W) && (oy < a.Ho) && (ox < a.Wo);
     const long long pix = ((long long)n * a.Ho + oy) * a.Wo + ox;
+    // sub-blocks that hold real output channels (the last N block of e.g. Cout = 816 = 3 x 256 + 48 has one of four)
+    int nsv = (a.Cout - nb * a.BN + 63) / 64;
+    nsv = nsv < 0 ? 0 : (nsv > nsub ? nsub : nsv);
+    const uint32_t t_base = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * a.BN + half * 32);
     tc::mbar_wait(&bars->tmem_full[buf], (it >> (a.nbuf == 4 ? 2 : 1)) & 1);
     tc::fence_after_sync();
-    for (int sb = 0; sb < nsub; ++sb) {
+    uint32_t raw[32];
+    if (nsv > 0) tc::tmem_ld_issue<32>(t_base, raw);
+    else {
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bars->tmem_empty[buf]);
+    }
+    for (int sb = 0; sb < nsv; ++sb) {
       const int n0 = nb * a.BN + sb * 64 + half * 32;       // first output channel of this thread's 32 columns
-      uint32_t raw[32];
-      tc::tmem_ld_issue<32>(tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * a.BN + sb * 64 + half * 32), raw);
       tc::tmem_ld_wait();
-      if (sb == nsub - 1) {
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+      // the next sub-block's accumulator columns travel while this one is packed, staged, stored and summed
+      if (sb + 1 < nsv) tc::tmem_ld_issue<32>(t_base + (uint32_t)((sb + 1) * 64), raw);
+      else {
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&bars->tmem_empty[buf]);
       }
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
       if (n0 < a.Cout) {                                        // warp-uniform; Cout is a multiple of 8
         if (a.bias) {
 #pragma unroll
@@ -673,15 +690,26 @@ __device__ __forceinline__ void epilogue_tma_wide(const Maps& tm, const ConvArgs
           s0 += f0; s1 += f1;
           q0 = fmaf(f0, f0, q0); q1 = fmaf(f1, f1, q1);
         }
-        const int col = nb * a.BN + sb * 64 + 2 * lane;
-        if (col < a.Cout) {      // Cout is even
-          s_stats[(e * 2 + 0) * a.Cout + col] += s0;
-          s_stats[(e * 2 + 0) * a.Cout + col + 1] += s1;
-          s_stats[(e * 2 + 1) * a.Cout + col] += q0;
-          s_stats[(e * 2 + 1) * a.Cout + col + 1] += q1;
-        }
+        const int col = sb * 64 + 2 * lane;                     // column within the N block
+        s_stats[(e * 2 + 0) * a.BN + col] += s0;
+        s_stats[(e * 2 + 0) * a.BN + col + 1] += s1;
+        s_stats[(e * 2 + 1) * a.BN + col] += q0;
+        s_stats[(e * 2 + 1) * a.BN + col + 1] += q1;
       }
       if (++ring == a.nob) ring = 0;
+    }
+    if (a.stats) {
+      // fold the eight warps' sums of this tile into the CTA's row of the partials (fixed order; the row has one owner)
+      tc::named_bar_sync(1, kEpiThreads);
+      for (int i = et; i < 2 * a.BN; i += kEpiThreads) {
+        const int which = i / a.BN, c = i - which * a.BN;
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < kEpiWarps; ++w) { sum += s_stats[(w * 2 + which) * a.BN + c]; s_stats[(w * 2 + which) * a.BN + c] = 0.f; }
+        const int gcol = nb * a.BN + c;
+        if (gcol < a.Cout) grow[which * a.Cout + gcol] += sum;
+      }
+      tc::named_bar_sync(1, kEpiThreads);
     }
   }
   if (store_thread) tc::bulk_wait_read<0>();
@@ -804,7 +832,7 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
   uint8_t* s_stage = s_out + out_bytes;
   const uint32_t stage_bytes = a.a_slot_bytes + (a.resident ? 0u : (uint32_t)a.max_nr * a.b_tap_bytes);
   float* s_stats = reinterpret_cast<float*>(s_stage + (size_t)a.stages * stage_bytes);
-  const int stats_floats = a.stats ? kEpiWarps * 2 * a.Cout : 0;
+  const int stats_floats = a.stats ? kEpiWarps * 2 * (a.epi_tma == 2 ? a.BN : a.Cout) : 0;   // wide epilogue: per N block, flushed per tile
   float* s_pre = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_stats) + ((stats_floats * 4 + 15) & ~15));
   const int pre_floats = a.pre_ss ? 2 * a.pre_pad : 0;
   float* s_aux = s_pre + pre_floats;              // pre_pad is a multiple of 16: s_aux stays 16-byte aligned
@@ -1026,7 +1054,7 @@ conv_tc_kernel(const __grid_constant__ Maps tm, const __grid_constant__ ConvArgs
     } else {
       epilogue_direct(a, bars, s_stats, tmem, warp, lane);
     }
-    if (a.stats) {
+    if (a.stats && a.epi_tma != 2) {       // (the wide epilogue has flushed its sums tile by tile)
       tc::named_bar_sync(1, kEpiThreads);  // the epilogue warps only
       float* dst = a.stats + (size_t)blockIdx.x * 2 * a.Cout;
       for (int i = threadIdx.x - kRoleThreads; i < 2 * a.Cout; i += kEpiThreads) {
@@ -1136,8 +1164,11 @@ int make_plan(Plan& p, int B, int Hg, int Wg, int Cin, int Cout, const ColSpec* 
   a.resident = (a.n_blocks == 1 && all_w <= 100 * 1024) ? 1 : 0;
   a.resident_bytes = a.resident ? (uint32_t)all_w : 0u;
   a.pre_pad = a.kchunks * a.KB;
-  const size_t stats_bytes = (want_stats ? ((size_t)kEpiWarps * 2 * Cout * 4 + 15) & ~size_t(15) : 0) +
-                             (pre ? (size_t)2 * a.pre_pad * 4 : 0) + (aux ? ((size_t)2 * Cout * 4 + 15) & ~size_t(15) : 0);
+  const size_t side_bytes = (pre ? (size_t)2 * a.pre_pad * 4 : 0) + (aux ? ((size_t)2 * Cout * 4 + 15) & ~size_t(15) : 0);
+  size_t stats_bytes = (want_stats ? ((size_t)kEpiWarps * 2 * Cout * 4 + 15) & ~size_t(15) : 0) + side_bytes;
+  // the wide epilogue keeps BatchNorm partial sums for one N block only and adds them to the CTA's row of the global
+  // partials after every tile ([8 warps][2][Cout] floats would be 52 KB at Cout = 816 and push those layers off it)
+  const size_t stats_bytes_wide = (want_stats ? (size_t)kEpiWarps * 2 * a.BN * 4 : 0) + side_bytes;
   // TMA-store epilogue: one N block of 16/32/64 columns; two staging tiles per output
   a.epi_tma = (a.n_blocks == 1 && (a.BN == 16 || a.BN == 32 || a.BN == 64) && n_out >= 1) ? 1 : 0;
   a.out_tile_bytes = (uint32_t)(128 * a.BN * 2);
@@ -1152,9 +1183,10 @@ int make_plan(Plan& p, int B, int Hg, int Wg, int Cin, int Cout, const ColSpec* 
   if (!a.epi_tma && n_out == 1 && a.BN > 64 && a.BN % 64 == 0) {
     // wide TMA-store epilogue: three (or two) 16 KB staging tiles, as long as the load pipeline keeps >= 3 stages
     const size_t stage_b = a.a_slot_bytes + (a.resident ? 0 : (size_t)a.max_nr * a.b_tap_bytes);
-    const size_t base_fixed = 1024 + a.resident_bytes + stats_bytes + sizeof(Barriers) + 64;
+    const size_t base_fixed = 1024 + a.resident_bytes + stats_bytes_wide + sizeof(Barriers) + 64;
     for (int nob = 3; nob >= 2 && !a.epi_tma; --nob)
       if (base_fixed + (size_t)nob * 16384 + 3 * stage_b <= 220 * 1024) { a.epi_tma = 2; a.nob = nob; out_bytes = (size_t)nob * 16384; }
+    if (a.epi_tma == 2) stats_bytes = stats_bytes_wide;
   }
   const size_t fixed = 1024 + a.resident_bytes + out_bytes + stats_bytes + sizeof(Barriers) + 64;
   const size_t budget = 220 * 1024;

@@ -1026,6 +1026,7 @@ __global__ void __launch_bounds__(1024) eval_gather_kernel(const double* __restr
                                                            double n, int nthr, double* __restrict__ moments,
                                                            unsigned long long* __restrict__ counts,
                                                            double* __restrict__ terms /*[B][2 + DP_MAX_THR]*/) {
+  dp::pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -1064,6 +1065,7 @@ __global__ void __launch_bounds__(1024) eval_gather_kernel(const double* __restr
 // per-sample terms -> the batch means evaluation.py:157-166 reports (one block, fixed order)
 __global__ void __launch_bounds__(256) eval_means_kernel(const double* __restrict__ terms, int B, double n, int nthr,
                                                          float* __restrict__ out) {
+  dp::pdl_prologue();
   __shared__ double red[(2 + DP_MAX_THR) * 32];
   double v[2 + DP_MAX_THR];
 #pragma unroll
@@ -1375,9 +1377,9 @@ int dp_eval_metrics(const float* pred, const float* target, int B, int H, int W,
     if (e != cudaSuccess)
       return dp_set_error(DP_ERR_CUDA, "eval_stream_kernel launch failed: %s", cudaGetErrorString(e));
     double* terms = reinterpret_cast<double*>(cnt_part + (size_t)B * plan.G * DP_MAX_THR);
-    eval_gather_kernel<<<(B + 31) / 32, 1024, 0, stream>>>(mom_part, cnt_part, B, plan.G, (double)n, nthr, moments, counts, terms);
+    dp::launch(eval_gather_kernel, (B + 31) / 32, 1024, 0, stream, mom_part, cnt_part, B, plan.G, (double)n, nthr, moments, counts, terms);
     DP_CHECK_LAUNCH("eval_gather_kernel");
-    eval_means_kernel<<<1, 256, 0, stream>>>(terms, B, (double)n, nthr, out);
+    dp::launch(eval_means_kernel, 1, 256, 0, stream, terms, B, (double)n, nthr, out);
     DP_CHECK_LAUNCH("eval_means_kernel");
     return DP_OK;
   }
