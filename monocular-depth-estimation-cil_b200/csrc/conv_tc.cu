@@ -580,11 +580,29 @@ __device__ __forceinline__ void epilogue_tma_wide(const Maps& tm, const ConvArgs
     for (int i = et; i < 2 * a.Cout; i += kEpiThreads) grow[i] = 0.f;
     tc::named_bar_sync(1, kEpiThreads);
   }
+  // s_stats holds the sums of ONE N block: when the CTA moves to another N block (and at the end) the eight warps' sums
+  // are folded into the CTA's row of the partials (fixed order; every global slot has one owner thread).  With 1, 2 or 4
+  // N blocks a CTA's tiles all share one (148 is a multiple), so the fold runs once.
+  auto flush = [&](int fnb) {
+    tc::named_bar_sync(1, kEpiThreads);
+    for (int i = et; i < 2 * a.BN; i += kEpiThreads) {
+      const int which = i / a.BN, c = i - which * a.BN;
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < kEpiWarps; ++w) { sum += s_stats[(w * 2 + which) * a.BN + c]; s_stats[(w * 2 + which) * a.BN + c] = 0.f; }
+      const int gcol = fnb * a.BN + c;
+      if (gcol < a.Cout) grow[which * a.Cout + gcol] += sum;
+    }
+    tc::named_bar_sync(1, kEpiThreads);
+  };
+  int cur_nb = -1;
   int it = 0, ring = 0;
   TileIter ti;
   ti.init(a, blockIdx.x);
   for (long long item = blockIdx.x; item < a.total_items; item += gridDim.x, ++it, ti.step(a)) {
     const int n = ti.n, y0 = ti.ty * a.th, x0 = ti.tx * a.tw, nb = ti.nb;
+    if (a.stats && cur_nb >= 0 && nb != cur_nb) flush(cur_nb);
+    cur_nb = nb;
     const int buf = it & (a.nbuf - 1);
     const int y = y0 + py, x = x0 + px;
     const int oy = y * a.osy + a.oay, ox = x * a.osx + a.oax;
@@ -698,20 +716,8 @@ __device__ __forceinline__ void epilogue_tma_wide(const Maps& tm, const ConvArgs
       }
       if (++ring == a.nob) ring = 0;
     }
-    if (a.stats) {
-      // fold the eight warps' sums of this tile into the CTA's row of the partials (fixed order; the row has one owner)
-      tc::named_bar_sync(1, kEpiThreads);
-      for (int i = et; i < 2 * a.BN; i += kEpiThreads) {
-        const int which = i / a.BN, c = i - which * a.BN;
-        float sum = 0.f;
-#pragma unroll
-        for (int w = 0; w < kEpiWarps; ++w) { sum += s_stats[(w * 2 + which) * a.BN + c]; s_stats[(w * 2 + which) * a.BN + c] = 0.f; }
-        const int gcol = nb * a.BN + c;
-        if (gcol < a.Cout) grow[which * a.Cout + gcol] += sum;
-      }
-      tc::named_bar_sync(1, kEpiThreads);
-    }
   }
+  if (a.stats && cur_nb >= 0) flush(cur_nb);
   if (store_thread) tc::bulk_wait_read<0>();
 }
 
@@ -1304,6 +1310,12 @@ int launch(const Plane* planes, const ColSpec* cols, int ncols, int B, int Hg, i
   auto kern = a.pre_ss ? conv_tc_kernel<true> : conv_tc_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
   if (e != cudaSuccess) return dp_set_error(DP_ERR_CUDA, "cudaFuncSetAttribute(%zu): %s", p.smem, cudaGetErrorString(e));
+  {
+    const double px = (double)B * Hg * Wg;
+    const double bytes = 2.0 * px * (Cin + Cout * (1 + (ep.res ? 1 : 0) + (ep.res2 || ep.mask_x ? 1 : 0) + (ep.out2 ? 1 : 0)));
+    const double flops = 2.0 * px * Cin * Cout * ntaps;
+    dp::pdl_work(bytes > flops / 200.0 ? bytes : flops / 200.0);
+  }
   dp::launch(kern, p.grid, a.pre_ss ? kPreThreads : kThreads, p.smem, stream, tm, a);
   DP_CHECK_LAUNCH("conv_tc_kernel");
   return DP_OK;

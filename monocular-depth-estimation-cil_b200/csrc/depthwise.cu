@@ -800,6 +800,7 @@ int dp_dwconv_fwd(const void* x, long long x_ld, int B, int Hi, int Wi, int C, c
   const int G = dw_G(C);
   DwArgs a{reinterpret_cast<const bf16*>(x), x_ld, B, Hi, Wi, C, w, pad_t, pad_l, reinterpret_cast<bf16*>(out), out_ld,
            Ho, Wo, stats_partials, G};
+  const double dw_work = 8.0 * (double)B * C * ((double)Hi * Wi + (double)Ho * Wo);   // ~4x the bytes: FMA-bound kernels
   if (stride == 1) {
     // shared-memory tile path; stats_partials then has dp_dwconv_fwd_blocks_s(..., 1) rows
     const DwTilePlan p = dw_tile_plan(B, Ho, Wo, C, K);
@@ -817,7 +818,7 @@ int dp_dwconv_fwd(const void* x, long long x_ld, int B, int Hi, int Wi, int C, c
     do {                                                                                                  \
       cudaError_t e = cudaFuncSetAttribute(dw_tile_kernel<KK, TWW, CGG, RR, XX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       if (e != cudaSuccess) return dp_set_error(DP_ERR_CUDA, "dw_tile_kernel smem %zu: %s", smem, cudaGetErrorString(e));       \
-      dp::launch(dw_tile_kernel<KK, TWW, CGG, RR, XX>, grid, TPB, smem, stream, tm, a);                             \
+      dp::pdl_work(dw_work); dp::launch(dw_tile_kernel<KK, TWW, CGG, RR, XX>, grid, TPB, smem, stream, tm, a);                             \
     } while (0)
     if (K == 3 && p.TW == 8) DP_DW_TILE(3, 8, 8, 4, 2);
     else if (K == 5 && p.TW == 8) DP_DW_TILE(5, 8, 8, 2, 2);
@@ -833,6 +834,7 @@ int dp_dwconv_fwd(const void* x, long long x_ld, int B, int Hi, int Wi, int C, c
   }
   dim3 grid(dp_dwconv_fwd_blocks(B, Ho, Wo, C), (C / 8 + G - 1) / G);
   const size_t smem = ((size_t)K * K * G * 8 + (stats_partials ? (size_t)TPB * 16 : 0)) * sizeof(float);
+  dp::pdl_work(dw_work);
   if (K == 3 && stride == 1) dp::launch(dw_fwd_kernel<3, 1>, grid, TPB, smem, stream, a);
   else if (K == 3) dp::launch(dw_fwd_kernel<3, 2>, grid, TPB, smem, stream, a);
   else if (stride == 1) dp::launch(dw_fwd_kernel<5, 1>, grid, TPB, smem, stream, a);
@@ -866,7 +868,7 @@ int dp_dwconv_dgrad_s2(const void* dy, long long dy_ld, int B, int Ho, int Wo, i
     do {                                                                                                                   \
       cudaError_t e = cudaFuncSetAttribute(dw_dgrad_s2_tile_kernel<KK, EYY, EXX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       if (e != cudaSuccess) return dp_set_error(DP_ERR_CUDA, "dw_dgrad_s2_tile_kernel smem %zu: %s", smem, cudaGetErrorString(e)); \
-      dp::launch(dw_dgrad_s2_tile_kernel<KK, EYY, EXX>, grid2, TPB, smem, stream, tmg, B, Hi, Wi, C, w, pad_t, pad_l, dxb, dx_ld);  \
+      dp::pdl_work(4.0 * (double)B * C * ((double)Hi * Wi + (double)Ho * Wo)); dp::launch(dw_dgrad_s2_tile_kernel<KK, EYY, EXX>, grid2, TPB, smem, stream, tmg, B, Hi, Wi, C, w, pad_t, pad_l, dxb, dx_ld);  \
     } while (0)
     const int ey = pad_t & 1, ex = pad_l & 1;
     if (K == 3) {
@@ -927,7 +929,7 @@ int dp_dwconv_wgrad(const void* x, long long x_ld, int B, int Hi, int Wi, int C,
     do {                                                                                                                   \
       cudaError_t e = cudaFuncSetAttribute(dw_wgrad_tile_kernel<KK, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       if (e != cudaSuccess) return dp_set_error(DP_ERR_CUDA, "dw_wgrad_tile_kernel smem %zu: %s", smem, cudaGetErrorString(e)); \
-      dp::launch(dw_wgrad_tile_kernel<KK, SS>, grid, TPB, smem, stream, tmx, tmg, B, Ho, Wo, C, pad_t, pad_l, partial);            \
+      dp::pdl_work(8.0 * (double)B * C * ((double)Hi * Wi + (double)Ho * Wo)); dp::launch(dw_wgrad_tile_kernel<KK, SS>, grid, TPB, smem, stream, tmx, tmg, B, Ho, Wo, C, pad_t, pad_l, partial);            \
     } while (0)
     if (K == 3 && S == 1) DP_DW_WT(3, 1);
     else if (K == 3) DP_DW_WT(3, 2);

@@ -21,6 +21,15 @@ int dp_pdl_enabled(void) {
   return on;
 }
 
+static thread_local double g_pdl_hint = 0.0;
+void dp_pdl_hint(double bytes_equivalent) { g_pdl_hint = bytes_equivalent; }
+int dp_pdl_take(void) {
+  static const double max_bytes = [] { const char* e = getenv("DP_PDL_MAX_MB"); return (e ? atof(e) : 256.0) * 1e6; }();
+  const double h = g_pdl_hint;
+  g_pdl_hint = 0.0;                      // one launch per hint; launches without a hint are short helper kernels
+  return dp_pdl_enabled() && h <= max_bytes;
+}
+
 void dp_count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 extern "C" {

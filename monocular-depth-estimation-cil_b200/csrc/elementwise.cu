@@ -654,6 +654,7 @@ extern "C" {
 int dp_add_relu_bwd(const void* g_raw, const void* g_relu, const void* y, void* out, size_t n, cudaStream_t stream) {
   DP_CHECK_ARG(out && (g_raw || g_relu) && (!g_relu || y) && n % 8 == 0, "dp_add_relu_bwd: bad arguments");
   if (n == 0) return DP_OK;
+  dp::pdl_work(8.0 * (double)n);
   dp::launch(add_relu_bwd_kernel, grid_for(n / 8), 256, 0, stream, (const bf16*)g_raw, (const bf16*)g_relu, (const bf16*)y,
                                                            (bf16*)out, n / 8);
   DP_CHECK_LAUNCH("add_relu_bwd_kernel");
@@ -663,6 +664,7 @@ int dp_add_relu_bwd(const void* g_raw, const void* g_relu, const void* y, void* 
 int dp_relu_bf16(const void* x, void* out, size_t n, cudaStream_t stream) {
   DP_CHECK_ARG(x && out && n % 8 == 0, "dp_relu_bf16: bad arguments");
   if (n == 0) return DP_OK;
+  dp::pdl_work(4.0 * (double)n);
   dp::launch(relu_kernel, grid_for(n / 8), 256, 0, stream, (const bf16*)x, (bf16*)out, n / 8);
   DP_CHECK_LAUNCH("relu_kernel");
   return DP_OK;
@@ -671,6 +673,7 @@ int dp_relu_bf16(const void* x, void* out, size_t n, cudaStream_t stream) {
 int dp_add_bf16(const void* a, const void* b, const void* c, void* out, size_t n, cudaStream_t stream) {
   DP_CHECK_ARG(a && b && out && n % 8 == 0, "dp_add_bf16: bad arguments");
   if (n == 0) return DP_OK;
+  dp::pdl_work(8.0 * (double)n);
   dp::launch(add_kernel, grid_for(n / 8), 256, 0, stream, (const bf16*)a, (const bf16*)b, (const bf16*)c, (bf16*)out, n / 8);
   DP_CHECK_LAUNCH("add_kernel");
   return DP_OK;
@@ -681,6 +684,7 @@ int dp_copy_channels(const void* src, long long src_ld, void* dst, long long dst
   DP_CHECK_ARG(src && dst && C % 8 == 0 && src_ld % 8 == 0 && dst_ld % 8 == 0, "dp_copy_channels: bad arguments");
   if (npix == 0) return DP_OK;
   const size_t items = npix * (C / 8);
+  dp::pdl_work(4.0 * (double)npix * C);
   if (items < (size_t)0x7fffff00u)
     dp::launch(copy_channels_kernel<unsigned>, grid_for(items), 256, 0, stream, (const bf16*)src, src_ld, (bf16*)dst, dst_ld, npix, C / 8);
   else
@@ -694,6 +698,7 @@ int dp_resize_bilinear_nhwc(const void* src, long long src_ld, int B, int Hi, in
   DP_CHECK_ARG(src && dst && C % 8 == 0 && src_ld % 8 == 0 && dst_ld % 8 == 0, "dp_resize_bilinear_nhwc: bad arguments");
   DP_CHECK_ARG(B > 0 && B <= 65535 && Ho > 0 && Ho <= 65535, "dp_resize_bilinear_nhwc: B / Ho out of the grid range");
   const dim3 grid((unsigned)(((size_t)Wo * (C / 8) + 255) / 256), (unsigned)((Ho + kRsRows - 1) / kRsRows), (unsigned)B);
+  dp::pdl_work(2.0 * (double)B * C * ((double)Hi * Wi + (double)Ho * Wo));
   dp::launch(resize_fwd_kernel, grid, 256, 0, stream, (const bf16*)src, src_ld, B, Hi, Wi, C, (bf16*)dst, dst_ld, Ho, Wo,
                                               align_corners, resize_scale(Hi, Ho, align_corners),
                                               resize_scale(Wi, Wo, align_corners));
@@ -707,6 +712,7 @@ int dp_resize_bilinear_nhwc_bwd(const void* gout, long long g_ld, int B, int Hi,
   DP_CHECK_ARG(B > 0 && B <= 65535 && Hi > 0 && Hi <= 65535, "dp_resize_bilinear_nhwc_bwd: B / Hi out of the grid range");
   const dim3 grid((unsigned)(((size_t)Wi * (C / 8) + 255) / 256), (unsigned)Hi, (unsigned)B);
   const float sy = resize_scale(Hi, Ho, align_corners), sx = resize_scale(Wi, Wo, align_corners);
+  dp::pdl_work(2.0 * (double)B * C * ((double)Hi * Wi + (double)Ho * Wo));
   dp::launch(resize_bwd_kernel, grid, 256, 0, stream, (const bf16*)gout, g_ld, B, Hi, Wi, C, (bf16*)gin, gin_ld, Ho, Wo,
                                               align_corners, sy, sx, sy > 0.f ? 1.f / sy : 0.f, sx > 0.f ? 1.f / sx : 0.f);
   DP_CHECK_LAUNCH("resize_bwd_kernel");
@@ -734,6 +740,7 @@ int dp_chan_reduce(int mode, const void* x, long long x_ld, const void* dy, long
   const int C8 = C / 8;
   const int lanes = RED_TPB / C8;
   const size_t smem = (size_t)2 * lanes * C * sizeof(float);
+  dp::pdl_work((mode >= 2 ? 4.0 : 2.0) * (double)npix * C);
   if (mode == 0)
     dp::launch(chan_reduce_kernel<0>, kRedBlocks, RED_TPB, smem, stream, (const bf16*)x, x_ld, nullptr, 0, nullptr, 0, npix, C, partial, mask_hi, nullptr);
   else if (mode == 1)
@@ -776,6 +783,7 @@ int dp_bn_apply(const void* x, long long x_ld, const float* scale_shift, const v
                 const float* scale_shift2, const void* res, long long res_ld, size_t npix, int C, int relu, void* y,
                 long long y_ld, cudaStream_t stream) {
   DP_CHECK_ARG(x && scale_shift && y && C % 8 == 0 && (!x2 || scale_shift2), "dp_bn_apply: bad arguments");
+  dp::pdl_work((x2 || res ? 6.0 : 4.0) * (double)npix * C);
   dp::launch(bn_apply_kernel, grid_for(npix * (C / 8)), 256, 0, stream, (const bf16*)x, x_ld, scale_shift, (const bf16*)x2, x2_ld,
                                                                 scale_shift2, (const bf16*)res, res_ld, npix, C, relu,
                                                                 (bf16*)y, y_ld);
@@ -791,6 +799,7 @@ int dp_bn_bwd_apply(const void* dy, long long dy_ld, const void* mask, long long
   DP_CHECK_ARG(!dx || (x && save_mean_invstd && (!train || red)), "dp_bn_bwd_apply: missing statistics");
   DP_CHECK_ARG(!dgamma || (dbeta && red && save_mean_invstd), "dp_bn_bwd_apply: dgamma needs dbeta, red and save");
   // train: bit 0 = batch statistics (train mode); bit 1 = the mask is a ReLU6 output (gradient passes for 0 < mask < 6)
+  dp::pdl_work(6.0 * (double)npix * C);
   dp::launch(bn_bwd_apply_kernel, grid_for(npix * (C / 8)), 256, 0, stream, 
       (const bf16*)dy, dy_ld, (const bf16*)mask, m_ld, (const bf16*)x, x_ld, red, save_mean_invstd, gamma, count, train & 1,
       npix, C, (bf16*)dx, dx_ld, (bf16*)gmask, gm_ld, dgamma, dbeta, accumulate, (train & 2) ? 6.f : INFINITY, mask_ss);

@@ -467,6 +467,11 @@ int wg_launch(WgPlan& p, const void* P, long long p_ld, const WgPlaneT* planes /
   }
   cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
   if (e != cudaSuccess) return dp_set_error(DP_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  {
+    const double px = (double)B * a.H * a.W;
+    const double bytes = 2.0 * px * (a.Cin + a.Cout), flops = 2.0 * px * a.Cin * a.Cout * K * K;
+    dp::pdl_work(bytes > flops / 200.0 ? bytes : flops / 200.0);
+  }
   dp::launch(wgrad_tc_kernel, p.grid, kThreads, p.smem, stream, tm, a);
   DP_CHECK_LAUNCH("wgrad_tc_kernel");
   const long long total = (long long)K * K * a.Cout * a.Cin;
