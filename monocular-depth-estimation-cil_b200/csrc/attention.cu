@@ -126,6 +126,30 @@ __global__ void lnl_reduce_kernel(const float* __restrict__ partial, int nblocks
 // items: int4 {q0, nq (<=32), k_lo, k_hi}; block = 8 warps (warp = head), lane = query
 constexpr int KCH = 128;  // keys staged per chunk
 
+// The three attention kernels are issue-bound (head dim 4: ~15-25 instructions per (query, key, head) score), so the
+// arithmetic is packed: dot products and accumulations as f32x2 FMAs, scores kept in log2 units (the softmax scale and
+// log2(e) are folded into the query once per thread) so that every exponential is a bare MUFU.EX2.
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+struct F4 { float2 lo, hi; };                              // a float4 as two packed pairs: (x, y), (z, w)
+__device__ __forceinline__ F4 ld4(const float* p) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  return F4{make_float2(t.x, t.y), make_float2(t.z, t.w)};
+}
+__device__ __forceinline__ float dot4(const F4& a, const F4& b) {
+  const float2 t = __ffma2_rn(a.hi, b.hi, __fmul2_rn(a.lo, b.lo));
+  return t.x + t.y;
+}
+__device__ __forceinline__ void axpy4(F4& acc, float s, const F4& v) {
+  const float2 ss = make_float2(s, s);
+  acc.lo = __ffma2_rn(ss, v.lo, acc.lo);
+  acc.hi = __ffma2_rn(ss, v.hi, acc.hi);
+}
+
 __global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                        const float* __restrict__ v, int N, float scale,
                                                        const int4* __restrict__ items, float* __restrict__ out,
@@ -138,11 +162,14 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__
   const size_t base = (size_t)b * N;
   const bool active = lane < it.y;
   const int qi = it.x + lane;
-  float4 qv = make_float4(0, 0, 0, 0);
-  if (active) qv = *reinterpret_cast<const float4*>(q + (base + qi) * D + h * HD);
-  qv.x *= scale; qv.y *= scale; qv.z *= scale; qv.w *= scale;
+  F4 qv{make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+  if (active) qv = ld4(q + (base + qi) * D + h * HD);
+  {
+    const float2 sc2 = make_float2(scale * kLog2e, scale * kLog2e);   // scores in log2 units
+    qv.lo = __fmul2_rn(qv.lo, sc2); qv.hi = __fmul2_rn(qv.hi, sc2);
+  }
   float m = -INFINITY, l = 0.f;
-  float4 acc = make_float4(0, 0, 0, 0);
+  F4 acc{make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
   for (int k0 = it.z; k0 < it.w; k0 += KCH) {
     const int nk = min(KCH, it.w - k0);
     __syncthreads();
@@ -156,32 +183,34 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__
     // by the MUFU rate (two exponentials per score otherwise)
     for (int j = 0; j < nk; j += 4) {
       float sc[4];
-      float4 vv[4];
+      F4 vv[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int jj = j + u < nk ? j + u : nk - 1;
-        const float4 kk = *reinterpret_cast<const float4*>(&sK[jj][h * HD]);
-        vv[u] = *reinterpret_cast<const float4*>(&sV[jj][h * HD]);
-        const float s = qv.x * kk.x + qv.y * kk.y + qv.z * kk.z + qv.w * kk.w;
+        const F4 kk = ld4(&sK[jj][h * HD]);
+        vv[u] = ld4(&sV[jj][h * HD]);
+        const float s = dot4(qv, kk);
         sc[u] = j + u < nk ? s : -INFINITY;
       }
       const float mn = fmaxf(fmaxf(m, fmaxf(sc[0], sc[1])), fmaxf(sc[2], sc[3]));
-      const float corr = __expf(m - mn);
+      const float corr = ex2(m - mn);
       l *= corr;
-      acc.x *= corr; acc.y *= corr; acc.z *= corr; acc.w *= corr;
+      const float2 c2 = make_float2(corr, corr);
+      acc.lo = __fmul2_rn(acc.lo, c2); acc.hi = __fmul2_rn(acc.hi, c2);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const float p = __expf(sc[u] - mn);
+        const float p = ex2(sc[u] - mn);
         l += p;
-        acc.x += p * vv[u].x; acc.y += p * vv[u].y; acc.z += p * vv[u].z; acc.w += p * vv[u].w;
+        axpy4(acc, p, vv[u]);
       }
       m = mn;
     }
   }
   if (active) {
     const float inv = 1.f / l;
-    *reinterpret_cast<float4*>(out + (base + qi) * D + h * HD) = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
-    lse[(base + qi) * NH + h] = m + __logf(l);
+    *reinterpret_cast<float4*>(out + (base + qi) * D + h * HD) =
+        make_float4(acc.lo.x * inv, acc.lo.y * inv, acc.hi.x * inv, acc.hi.y * inv);
+    lse[(base + qi) * NH + h] = (m + __log2f(l)) * kLn2;      // natural-log units, as before
   }
 }
 
@@ -199,16 +228,18 @@ __global__ void __launch_bounds__(256) attn_bwd_q_kernel(const float* __restrict
   const size_t base = (size_t)b * N;
   const bool active = lane < it.y;
   const int qi = it.x + lane;
-  float4 qv = make_float4(0, 0, 0, 0), go = qv, ov = qv;
+  F4 qv{make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, go = qv, ov = qv;
   float L = 0.f;
   if (active) {
-    qv = *reinterpret_cast<const float4*>(q + (base + qi) * D + h * HD);
-    go = *reinterpret_cast<const float4*>(dout + (base + qi) * D + h * HD);
-    ov = *reinterpret_cast<const float4*>(out + (base + qi) * D + h * HD);
-    L = lse[(base + qi) * NH + h];
+    qv = ld4(q + (base + qi) * D + h * HD);
+    go = ld4(dout + (base + qi) * D + h * HD);
+    ov = ld4(out + (base + qi) * D + h * HD);
+    L = lse[(base + qi) * NH + h] * kLog2e;                   // log2 units
   }
-  const float dl = go.x * ov.x + go.y * ov.y + go.z * ov.z + go.w * ov.w;
-  float4 acc = make_float4(0, 0, 0, 0);
+  const float dl = dot4(go, ov);
+  const float2 sc2 = make_float2(scale * kLog2e, scale * kLog2e);
+  const F4 q2{__fmul2_rn(qv.lo, sc2), __fmul2_rn(qv.hi, sc2)};   // scores in log2 units
+  F4 acc{make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
   for (int k0 = it.z; k0 < it.w; k0 += KCH) {
     const int nk = min(KCH, it.w - k0);
     __syncthreads();
@@ -218,18 +249,18 @@ __global__ void __launch_bounds__(256) attn_bwd_q_kernel(const float* __restrict
       reinterpret_cast<float4*>(&sV[j][0])[c4] = __ldg(reinterpret_cast<const float4*>(v + (base + k0 + j) * D) + c4);
     }
     __syncthreads();
+#pragma unroll 4
     for (int j = 0; j < nk; ++j) {
-      const float4 kk = *reinterpret_cast<const float4*>(&sK[j][h * HD]);
-      const float4 vv = *reinterpret_cast<const float4*>(&sV[j][h * HD]);
-      const float s = (qv.x * kk.x + qv.y * kk.y + qv.z * kk.z + qv.w * kk.w) * scale;
-      const float p = __expf(s - L);
-      const float dp = go.x * vv.x + go.y * vv.y + go.z * vv.z + go.w * vv.w;
-      const float ds = p * (dp - dl) * scale;
-      acc.x += ds * kk.x; acc.y += ds * kk.y; acc.z += ds * kk.z; acc.w += ds * kk.w;
+      const F4 kk = ld4(&sK[j][h * HD]);
+      const F4 vv = ld4(&sV[j][h * HD]);
+      const float p = ex2(dot4(q2, kk) - L);
+      const float ds = p * (dot4(go, vv) - dl);              // the softmax scale is applied once, after the loop
+      axpy4(acc, ds, kk);
     }
   }
   if (active) {
-    *reinterpret_cast<float4*>(dq + (base + qi) * D + h * HD) = acc;
+    *reinterpret_cast<float4*>(dq + (base + qi) * D + h * HD) =
+        make_float4(acc.lo.x * scale, acc.lo.y * scale, acc.hi.x * scale, acc.hi.y * scale);
     delta[(base + qi) * NH + h] = dl;
   }
 }
@@ -251,12 +282,14 @@ __global__ void __launch_bounds__(256) attn_bwd_kv_kernel(const float* __restric
   const size_t base = (size_t)b * N;
   const int j0 = blockIdx.x * 32, j = j0 + lane;
   const bool kvalid = j < N;
-  float4 kk = make_float4(0, 0, 0, 0), vv = kk;
+  F4 kk{make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, vv = kk;
   if (kvalid) {
-    kk = *reinterpret_cast<const float4*>(k + (base + j) * D + h * HD);
-    vv = *reinterpret_cast<const float4*>(v + (base + j) * D + h * HD);
+    kk = ld4(k + (base + j) * D + h * HD);
+    vv = ld4(v + (base + j) * D + h * HD);
   }
-  float4 adk = make_float4(0, 0, 0, 0), adv = adk;
+  const float2 sc2 = make_float2(scale * kLog2e, scale * kLog2e);
+  const F4 k2{__fmul2_rn(kk.lo, sc2), __fmul2_rn(kk.hi, sc2)};   // scores in log2 units
+  F4 adk{make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, adv = adk;
   for (int sidx = 0; sidx < nseg; ++sidx) {
     const int4 sg = segs[sidx];
     if (sg.w <= j0 || sg.z >= j0 + 32) continue;  // block-uniform: key ranges do not meet
@@ -270,27 +303,27 @@ __global__ void __launch_bounds__(256) attn_bwd_kv_kernel(const float* __restric
         reinterpret_cast<float4*>(&sG[i][0])[c4] = __ldg(reinterpret_cast<const float4*>(dout + (base + q0 + i) * D) + c4);
       }
       for (int e = threadIdx.x; e < nq * NH; e += blockDim.x) {
-        sL[e / NH][e % NH] = lse[(base + q0) * NH + e];
+        sL[e / NH][e % NH] = lse[(base + q0) * NH + e] * kLog2e;     // log2 units
         sDl[e / NH][e % NH] = delta[(base + q0) * NH + e];
       }
       __syncthreads();
       if (mine) {
+#pragma unroll 4
         for (int i = 0; i < nq; ++i) {
-          const float4 qq = *reinterpret_cast<const float4*>(&sQ[i][h * HD]);
-          const float4 gg = *reinterpret_cast<const float4*>(&sG[i][h * HD]);
-          const float s = (qq.x * kk.x + qq.y * kk.y + qq.z * kk.z + qq.w * kk.w) * scale;
-          const float p = __expf(s - sL[i][h]);
-          const float dp = gg.x * vv.x + gg.y * vv.y + gg.z * vv.z + gg.w * vv.w;
-          const float ds = p * (dp - sDl[i][h]) * scale;
-          adv.x += p * gg.x; adv.y += p * gg.y; adv.z += p * gg.z; adv.w += p * gg.w;
-          adk.x += ds * qq.x; adk.y += ds * qq.y; adk.z += ds * qq.z; adk.w += ds * qq.w;
+          const F4 qq = ld4(&sQ[i][h * HD]);
+          const F4 gg = ld4(&sG[i][h * HD]);
+          const float p = ex2(dot4(qq, k2) - sL[i][h]);
+          const float ds = p * (dot4(gg, vv) - sDl[i][h]);    // the softmax scale is applied once, after the loops
+          axpy4(adv, p, gg);
+          axpy4(adk, ds, qq);
         }
       }
     }
   }
   if (kvalid) {
-    *reinterpret_cast<float4*>(dk + (base + j) * D + h * HD) = adk;
-    *reinterpret_cast<float4*>(dv + (base + j) * D + h * HD) = adv;
+    *reinterpret_cast<float4*>(dk + (base + j) * D + h * HD) =
+        make_float4(adk.lo.x * scale, adk.lo.y * scale, adk.hi.x * scale, adk.hi.y * scale);
+    *reinterpret_cast<float4*>(dv + (base + j) * D + h * HD) = make_float4(adv.lo.x, adv.lo.y, adv.hi.x, adv.hi.y);
   }
 }
 
