@@ -383,6 +383,226 @@ __global__ void __launch_bounds__(256) head_conv_wgrad_rows_kernel(const float* 
   }
 }
 
+// ---- the depth head proper: 16 -> 1, 3x3, pad 1 (midas_semantics.py:203-204) at full resolution ---------------------
+// The generic kernels above spend most of their time on 64-bit index divisions, a 144-long dependent FMA chain (forward)
+// and scalar gradient loads behind bounds branches (backward): 370 / 410 / 490 us at 32 x 448 x 576 against HBM floors of
+// 45 / 50 / 45 us.  These three keep 32-bit indices, packed f32x2 MACs on independent accumulators and unpack / load
+// every operand once per thread.
+__device__ __forceinline__ void unpack8f2(const uint4& u, float2 (&f)[4]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) f[i] = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
+}
+
+// forward: thread = 4 consecutive output pixels of a row; the 3 x 6 input vectors under them are loaded and unpacked
+// once, each tap's 16 weights (shared memory, [tap][16]) serve the four outputs
+__global__ void __launch_bounds__(256) head16_fwd_kernel(const bf16* __restrict__ x, long long x_ld, int B, int H, int W,
+                                                         const float* __restrict__ w /*[16][3][3]*/,
+                                                         const float* __restrict__ bias, int relu, float* __restrict__ out) {
+  __shared__ __align__(16) float sw[9 * 16];
+  if (threadIdx.x < 144) sw[threadIdx.x] = w[(threadIdx.x % 16) * 9 + threadIdx.x / 16];
+  __syncthreads();
+  const int strips = (W + 3) >> 2;
+  const int total = B * H * strips;
+  const float b0 = bias ? __ldg(bias) : 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int sx = i % strips, row = i / strips;
+    const int y = row % H;
+    const int x0 = sx * 4;
+    float2 acc[4][2];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { acc[t][0] = make_float2(0.f, 0.f); acc[t][1] = make_float2(0.f, 0.f); }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int iy = y + r - 1;
+      if (iy < 0 || iy >= H) continue;                         // warp-uniform except at strip rows: rows are uniform
+      const bf16* prow = x + ((long long)(row - y + iy) * W) * x_ld;
+      float2 wt[3][8];
+#pragma unroll
+      for (int s2 = 0; s2 < 3; ++s2)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 t4 = *reinterpret_cast<const float4*>(&sw[(r * 3 + s2) * 16 + q * 4]);
+          wt[s2][2 * q] = make_float2(t4.x, t4.y);
+          wt[s2][2 * q + 1] = make_float2(t4.z, t4.w);
+        }
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const int ix = x0 - 1 + c;
+        float2 v[8];
+        if (ix >= 0 && ix < W) {
+          const uint4* pp = reinterpret_cast<const uint4*>(prow + (long long)ix * x_ld);
+          float2 a[4], b2[4];
+          unpack8f2(__ldg(pp), a);
+          unpack8f2(__ldg(pp + 1), b2);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { v[q] = a[q]; v[4 + q] = b2[q]; }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[q] = make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int s2 = c - t;                                // tap column for output t (compile-time)
+          if (s2 < 0 || s2 > 2) continue;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[t][q & 1] = __ffma2_rn(v[q], wt[s2][q], acc[t][q & 1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (x0 + t >= W) continue;
+      const float2 s2 = __fadd2_rn(acc[t][0], acc[t][1]);
+      const float r = b0 + (s2.x + s2.y);
+      out[(long long)row * W + x0 + t] = relu ? fmaxf(r, 0.f) : r;
+    }
+  }
+}
+
+// data gradient: thread = one pixel, all 16 channels; the nine masked upstream gradients are loaded first
+__global__ void __launch_bounds__(256) head16_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                                                           int relu, int B, int H, int W, const float* __restrict__ w,
+                                                           bf16* __restrict__ dx, long long dx_ld) {
+  __shared__ __align__(16) float sw[9 * 16];
+  if (threadIdx.x < 144) sw[threadIdx.x] = w[(threadIdx.x % 16) * 9 + threadIdx.x / 16];
+  __syncthreads();
+  const int total = B * H * W;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int xx = i % W, row = i / W;
+    const int yy = row % H;
+    float g[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s2 = 0; s2 < 3; ++s2) {
+        const int oy = yy - (r - 1), ox = xx - (s2 - 1);
+        const bool ok = oy >= 0 && oy < H && ox >= 0 && ox < W;
+        const int o = ok ? i - (r - 1) * W - (s2 - 1) : i;     // clamped: the load is unconditional
+        float gv = __ldg(dout + o);
+        if (relu && !(__ldg(out + o) > 0.f)) gv = 0.f;
+        g[r * 3 + s2] = ok ? gv : 0.f;
+      }
+    float2 acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float2 gg = make_float2(g[t], g[t]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 t4 = *reinterpret_cast<const float4*>(&sw[t * 16 + q * 4]);
+        acc[2 * q] = __ffma2_rn(gg, make_float2(t4.x, t4.y), acc[2 * q]);
+        acc[2 * q + 1] = __ffma2_rn(gg, make_float2(t4.z, t4.w), acc[2 * q + 1]);
+      }
+    }
+    uint4 o0, o1;
+    {
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[0].x, acc[0].y), h1 = __floats2bfloat162_rn(acc[1].x, acc[1].y);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[2].x, acc[2].y), h3 = __floats2bfloat162_rn(acc[3].x, acc[3].y);
+      o0 = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1), *reinterpret_cast<uint32_t*>(&h2),
+                      *reinterpret_cast<uint32_t*>(&h3));
+      __nv_bfloat162 h4 = __floats2bfloat162_rn(acc[4].x, acc[4].y), h5 = __floats2bfloat162_rn(acc[5].x, acc[5].y);
+      __nv_bfloat162 h6 = __floats2bfloat162_rn(acc[6].x, acc[6].y), h7 = __floats2bfloat162_rn(acc[7].x, acc[7].y);
+      o1 = make_uint4(*reinterpret_cast<uint32_t*>(&h4), *reinterpret_cast<uint32_t*>(&h5), *reinterpret_cast<uint32_t*>(&h6),
+                      *reinterpret_cast<uint32_t*>(&h7));
+    }
+    uint4* dst = reinterpret_cast<uint4*>(dx + (long long)i * dx_ld);
+    dst[0] = o0;
+    dst[1] = o1;
+  }
+}
+
+// weight + bias gradient partials: part[block][9*16 + 1].  A block owns a contiguous run of image rows and keeps the
+// masked upstream gradient of rows y-1 .. y+1 in a rolling shared-memory window (one new row per step, zero borders), so
+// a thread = (pixel column, 8-channel group) loads its activation vector once and reads its nine gradients from shared
+// memory; 9 x 8 fp32 accumulators as packed pairs; fixed-order shuffle + shared-memory fold at the end.
+constexpr int H16_MAXW = 1024;
+__global__ void __launch_bounds__(256) head16_wgrad_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                                                           int relu, const bf16* __restrict__ x, long long x_ld, int B,
+                                                           int H, int W, int rows_per_block, float* __restrict__ part) {
+  extern __shared__ __align__(16) float h16_smem[];          // [3][W + 2] gradient rows | reduction scratch
+  const int SW = W + 2;
+  float* s_g = h16_smem;
+  float (*s_red)[2][9 * 8 + 1] = reinterpret_cast<float (*)[2][9 * 8 + 1]>(h16_smem + 3 * SW + 2);
+  const int c8 = threadIdx.x & 1, px0 = threadIdx.x >> 1;
+  float2 acc[9][4];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[t][q] = make_float2(0.f, 0.f);
+  float bsum = 0.f;
+  const int rows = B * H;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  auto stage = [&](int slot, int row, bool valid) {            // masked gradient row -> s_g[slot][1 .. W], zero if invalid
+    float* dst = s_g + slot * SW;
+    for (int xx = threadIdx.x; xx < SW; xx += 256) {
+      float gv = 0.f;
+      if (valid && xx >= 1 && xx <= W) {
+        const long long o = (long long)row * W + xx - 1;
+        gv = __ldg(dout + o);
+        if (relu && !(__ldg(out + o) > 0.f)) gv = 0.f;
+      }
+      dst[xx] = gv;
+    }
+  };
+  for (int row = r0; row < r1; ++row) {
+    const int y = row % H;
+    // window slots: gradient row (y + d) lives in slot (row + d + 3) % 3; rows of other images / outside are zero
+    if (row == r0 || y == 0) {
+      __syncthreads();
+      stage((row + 2) % 3, row - 1, y > 0);
+      stage(row % 3, row, true);
+    }
+    __syncthreads();                                           // (previous row's reads of the slot being replaced are done)
+    stage((row + 1) % 3, row + 1, y + 1 < H);
+    __syncthreads();
+    const float* gm = s_g + ((row + 2) % 3) * SW;              // gradient row y - 1
+    const float* g0 = s_g + (row % 3) * SW;
+    const float* gp = s_g + ((row + 1) % 3) * SW;              // gradient row y + 1
+    for (int xx = px0; xx < W; xx += 128) {
+      float2 v[4];
+      unpack8f2(__ldg(reinterpret_cast<const uint4*>(x + ((long long)row * W + xx) * x_ld + c8 * 8)), v);
+      // dw[r][s] += g[y - (r-1)][x - (s-1)] * v : tap (r, s) pairs with gradient row y + 1 - r, column xx + 1 - s (+1 border)
+      const float* grow[3] = {gp, g0, gm};
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s2 = 0; s2 < 3; ++s2) {
+          const float gv = grow[r][xx + 2 - s2];
+          if (r == 1 && s2 == 1 && c8 == 0) bsum += gv;
+          const float2 gg = make_float2(gv, gv);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[r * 3 + s2][q] = __ffma2_rn(gg, v[q], acc[r * 3 + s2][q]);
+        }
+    }
+  }
+  // lanes with equal parity hold the same channel group: fold them with xor shuffles down to lanes 0 / 1
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float a = acc[t][q].x, b2 = acc[t][q].y;
+      for (int o = 16; o >= 2; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b2 += __shfl_xor_sync(0xffffffffu, b2, o); }
+      if (lane < 2) { s_red[warp][lane][t * 8 + 2 * q] = a; s_red[warp][lane][t * 8 + 2 * q + 1] = b2; }
+    }
+  for (int o = 16; o >= 1; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+  if (lane == 0) s_red[warp][0][72] = bsum;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 145; i += 256) {
+    float sum = 0.f;
+    if (i == 144) {
+      for (int wq = 0; wq < 8; ++wq) sum += s_red[wq][0][72];
+    } else {
+      const int t = i / 16, c = i % 16;                        // output index order: tap-major, channel-minor
+      for (int wq = 0; wq < 8; ++wq) sum += s_red[wq][c / 8][t * 8 + (c % 8)];
+    }
+    part[(size_t)blockIdx.x * 145 + i] = sum;
+  }
+}
+
 __global__ void head_conv_wgrad_reduce_kernel(const float* __restrict__ part, int nblocks, int C, int KS,
                                               float* __restrict__ dw /*[C][KS][KS]*/, float* __restrict__ db,
                                               int accumulate) {
@@ -472,6 +692,12 @@ int dp_conv_wgrad_direct(const void* P, long long p_ld, int Hp, int Wp, int Cp, 
 int dp_head_conv_fwd(const void* x, long long x_ld, int B, int H, int W, int C, int KS, const float* w,
                      const float* bias, int relu, float* out, cudaStream_t stream) {
   DP_CHECK_ARG(x && w && out && C % 8 == 0 && (KS == 1 || KS == 3), "dp_head_conv_fwd: bad arguments");
+  if (C == 16 && KS == 3 && x_ld % 8 == 0 && (long long)B * H * W < (1LL << 31)) {
+    const int strips = (W + 3) / 4;
+    head16_fwd_kernel<<<grid_for((size_t)B * H * strips), 256, 0, stream>>>((const bf16*)x, x_ld, B, H, W, w, bias, relu, out);
+    DP_CHECK_LAUNCH("head16_fwd_kernel");
+    return DP_OK;
+  }
   head_conv_fwd_kernel<<<grid_for((size_t)B * H * W), 256, KS * KS * C * sizeof(float), stream>>>(
       (const bf16*)x, x_ld, B, H, W, C, KS, w, bias, relu, out);
   DP_CHECK_LAUNCH("head_conv_fwd_kernel");
@@ -488,10 +714,26 @@ int dp_head_conv_bwd(const float* dout, const float* out, int relu, const void* 
   DP_CHECK_ARG(KS * KS * (C / 8) <= 72, "dp_head_conv_bwd: C too large for the head kernel");
   if (workspace_bytes < dp_head_conv_bwd_workspace(C, KS))
     return dp_set_error(DP_ERR_WORKSPACE, "dp_head_conv_bwd: workspace too small");
-  if (dx) {
+  const bool fast16 = C == 16 && KS == 3 && x_ld % 8 == 0 && dx_ld % 8 == 0 && W <= H16_MAXW &&
+                      (long long)B * H * W < (1LL << 31);
+  if (dx && fast16) {
+    head16_dgrad_kernel<<<grid_for((size_t)B * H * W), 256, 0, stream>>>(dout, out, relu, B, H, W, w, (bf16*)dx, dx_ld);
+    DP_CHECK_LAUNCH("head16_dgrad_kernel");
+  } else if (dx) {
     head_conv_dgrad_kernel<<<grid_for((size_t)B * H * W * (C / 8)), 256, KS * KS * C * sizeof(float), stream>>>(
         dout, out, relu, B, H, W, C, KS, w, (bf16*)dx, dx_ld);
     DP_CHECK_LAUNCH("head_conv_dgrad_kernel");
+  }
+  if (dw && fast16) {
+    const int rows = B * H;
+    const int rpb = (rows + kHeadWgBlocks - 1) / kHeadWgBlocks;
+    const int nblk = (rows + rpb - 1) / rpb;                        // <= kHeadWgBlocks: the partials buffer has room
+    const size_t smem = ((size_t)3 * (W + 2) + 2 + 8 * 2 * 73) * sizeof(float);
+    head16_wgrad_kernel<<<nblk, 256, smem, stream>>>(dout, out, relu, (const bf16*)x, x_ld, B, H, W, rpb, (float*)workspace);
+    DP_CHECK_LAUNCH("head16_wgrad_kernel");
+    head_conv_wgrad_reduce_kernel<<<ceil_div(KS * KS * C + 1, 128), 128, 0, stream>>>((const float*)workspace, nblk, C, KS, dw, db, accumulate);
+    DP_CHECK_LAUNCH("head_conv_wgrad_reduce_kernel");
+    return DP_OK;
   }
   if (dw) {
     const int nacc = KS * KS * C + 1;

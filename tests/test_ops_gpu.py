@@ -135,10 +135,11 @@ def test_strided_and_transposed_conv(pkg, kind, Cin, Cout, k, stride, pad, B, H,
         assert ok, (nm, e, s)
 
 
-@pytest.mark.parametrize("C,KS,relu", [(16, 3, True), (32, 1, True), (32, 1, False), (64, 3, True)])
-def test_head_conv(pkg, C, KS, relu):
+@pytest.mark.parametrize("H,W", [(20, 28), (11, 37), (3, 5)])       # ragged strips / single-row images for the 16 -> 1 fast path
+@pytest.mark.parametrize("C,KS,relu", [(16, 3, True), (16, 3, False), (32, 1, True), (32, 1, False), (64, 3, True)])
+def test_head_conv(pkg, C, KS, relu, H, W):
     from depth_b200 import ops
-    B, H, W = 2, 20, 28
+    B = 3
     x = rnd(B, C, H, W, seed=9)
     m = nn.Conv2d(C, 1, KS, 1, KS // 2)
     with torch.no_grad():
