@@ -187,7 +187,7 @@ def eval_kernel_leg(depth_b200, dev, rank, world, barrier, dist, hbm, build):
             "value": round(world * px / (ms / 1e3) / 1e9, 2), "unit": "Gpx/s", "batch_per_gpu": EB,
             "inputs": f"{px * 8 / 1e6:.0f} MB per GPU per call (> 126 MB L2)",
             "kernel": "eval_stream_kernel: one CTA per SM, groups of CTAs own a sample, slices staged in shared memory by "
-                      "cp.async.bulk (4 slots, L2 prefetch one sample ahead), per-sample scale exchanged through global memory "
+                      "cp.async.bulk (4 slots of one chunk each), per-sample scale exchanged through global memory "
                       "by a pipelined warp, classification two samples behind the moments sweep, from shared memory",
             "arithmetic": "default path of evaluation_metrics: one shared reciprocal + one lg2 per pixel, division-free "
                           "threshold test (exact code for slices with negative values / non-finite scales)",

@@ -278,6 +278,9 @@ __global__ void __launch_bounds__(256, 4) resize_bwd_kernel(const bf16* __restri
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  float2 acc2[4];                               // the 4 x 4 window path accumulates packed pairs (same fma per element)
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc2[j] = make_float2(0.f, 0.f);
   const bf16* g = gout + (size_t)b * Ho * Wo * g_ld + c8 * 8;
   float wx[RW], wy[RW];
   int oy_lo, oy_hi, ox_lo, ox_hi, fx0, fy0;
@@ -300,14 +303,17 @@ __global__ void __launch_bounds__(256, 4) resize_bwd_kernel(const bf16* __restri
       for (int r = 0; r < 2; ++r) {
 #pragma unroll
         for (int q = 0; q < RW; ++q) {
-          float v[8];
-          unpack8(u[r][q], v);
+          const uint32_t uw[4] = {u[r][q].x, u[r][q].y, u[r][q].z, u[r][q].w};
           const float w = wy[r0 + r] * wx[q];
+          const float2 w2 = make_float2(w, w);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] += w * v[j];
+          for (int j = 0; j < 4; ++j)
+            acc2[j] = __ffma2_rn(w2, make_float2(__uint_as_float(uw[j] << 16), __uint_as_float(uw[j] & 0xffff0000u)), acc2[j]);
         }
       }
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[2 * j] = acc2[j].x; acc[2 * j + 1] = acc2[j].y; }
   } else {
     for (int oy = oy_lo; oy <= oy_hi; ++oy) {
       const float wyv = axis_weight(oy, iy, Hi, sy, align);

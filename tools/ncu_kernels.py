@@ -75,6 +75,20 @@ ws2 = torch.randn(9, 144, device=dev)
 dxs2 = torch.empty(B, 224, 288, 144, device=dev, dtype=torch.bfloat16)
 cases.append(("dw dgrad k3 s2 224x288x144", lambda: L.check(L.lib().dp_dwconv_dgrad_s2(
     L.ptr(gs2), 144, B, 112, 144, 144, L.ptr(ws2), 3, 1, 1, L.ptr(dxs2), 144, 224, 288, L.stream()))))
+# the 16 -> 1 depth head at full resolution: forward, then data gradient + weight gradient + reduce
+xh = torch.randn(B, H, W, 16, device=dev).to(torch.bfloat16)
+wh = torch.randn(1, 16, 3, 3, device=dev) * 0.1
+bh = torch.full((1,), 0.5, device=dev)
+oh = torch.empty(B, H, W, device=dev)
+gh = torch.rand(B, H, W, device=dev)
+dxh = torch.empty(B, H, W, 16, device=dev, dtype=torch.bfloat16)
+dwh, dbh = torch.empty(1, 16, 3, 3, device=dev), torch.empty(1, device=dev)
+wsh = torch.empty(L.lib().dp_head_conv_bwd_workspace(16, 3), dtype=torch.uint8, device=dev)
+cases.append(("head conv 16->1 3x3 fwd @448x576", lambda: L.check(L.lib().dp_head_conv_fwd(
+    L.ptr(xh), 16, B, H, W, 16, 3, L.ptr(wh), L.ptr(bh), 1, L.ptr(oh), L.stream()))))
+cases.append(("head conv 16->1 3x3 bwd @448x576", lambda: L.check(L.lib().dp_head_conv_bwd(
+    L.ptr(gh), L.ptr(oh), 1, L.ptr(xh), 16, B, H, W, 16, 3, L.ptr(wh), L.ptr(dxh), 16, L.ptr(dwh), L.ptr(dbh), 0, L.ptr(wsh),
+    wsh.numel(), L.stream()))))
 # bilinear resize backward (x2, 64 channels, 224x288 -> 112x144 gradient)
 gr = torch.randn(B, 224, 288, 64, device=dev).to(torch.bfloat16)
 gin = torch.empty(B, 112, 144, 64, device=dev, dtype=torch.bfloat16)
