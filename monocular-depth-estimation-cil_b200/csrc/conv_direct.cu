@@ -394,69 +394,59 @@ __device__ __forceinline__ void unpack8f2(const uint4& u, float2 (&f)[4]) {
   for (int i = 0; i < 4; ++i) f[i] = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
 }
 
-// forward: thread = 4 consecutive output pixels of a row; the 3 x 6 input vectors under them are loaded and unpacked
-// once, each tap's 16 weights (shared memory, [tap][16]) serve the four outputs
+// forward: thread = one output pixel (adjacent lanes read adjacent 32-byte pixels: a warp load touches 8 cache lines; a
+// 4-pixel strip per thread put every lane on its own line and the kernel ran at the L1 tag rate, 293 us); four
+// independent packed accumulators, each tap's 16 weights from shared memory ([tap][16])
 __global__ void __launch_bounds__(256) head16_fwd_kernel(const bf16* __restrict__ x, long long x_ld, int B, int H, int W,
                                                          const float* __restrict__ w /*[16][3][3]*/,
                                                          const float* __restrict__ bias, int relu, float* __restrict__ out) {
   __shared__ __align__(16) float sw[9 * 16];
   if (threadIdx.x < 144) sw[threadIdx.x] = w[(threadIdx.x % 16) * 9 + threadIdx.x / 16];
   __syncthreads();
-  const int strips = (W + 3) >> 2;
-  const int total = B * H * strips;
+  const int total = B * H * W;
   const float b0 = bias ? __ldg(bias) : 0.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int sx = i % strips, row = i / strips;
+    const int xx = i % W, row = i / W;
     const int y = row % H;
-    const int x0 = sx * 4;
-    float2 acc[4][2];
+    float2 acc[4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) { acc[t][0] = make_float2(0.f, 0.f); acc[t][1] = make_float2(0.f, 0.f); }
+    for (int q = 0; q < 4; ++q) acc[q] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int iy = y + r - 1;
-      if (iy < 0 || iy >= H) continue;                         // warp-uniform except at strip rows: rows are uniform
-      const bf16* prow = x + ((long long)(row - y + iy) * W) * x_ld;
-      float2 wt[3][8];
+      const bool rok = iy >= 0 && iy < H;
+      uint4 u[3][2];
 #pragma unroll
-      for (int s2 = 0; s2 < 3; ++s2)
+      for (int s2 = 0; s2 < 3; ++s2) {                          // the row's six loads are issued before any is used
+        const int ix = xx + s2 - 1;
+        const bool ok = rok && ix >= 0 && ix < W;
+        const uint4* pp = reinterpret_cast<const uint4*>(x + (long long)(ok ? i + (r - 1) * W + (s2 - 1) : i) * x_ld);
+        u[s2][0] = __ldg(pp);
+        u[s2][1] = __ldg(pp + 1);
+        if (!ok) { u[s2][0] = make_uint4(0, 0, 0, 0); u[s2][1] = make_uint4(0, 0, 0, 0); }
+      }
+#pragma unroll
+      for (int s2 = 0; s2 < 3; ++s2) {
+        float2 v[8];
+        {
+          float2 a2[4], b2[4];
+          unpack8f2(u[s2][0], a2);
+          unpack8f2(u[s2][1], b2);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { v[q] = a2[q]; v[4 + q] = b2[q]; }
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 t4 = *reinterpret_cast<const float4*>(&sw[(r * 3 + s2) * 16 + q * 4]);
-          wt[s2][2 * q] = make_float2(t4.x, t4.y);
-          wt[s2][2 * q + 1] = make_float2(t4.z, t4.w);
-        }
-#pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        const int ix = x0 - 1 + c;
-        float2 v[8];
-        if (ix >= 0 && ix < W) {
-          const uint4* pp = reinterpret_cast<const uint4*>(prow + (long long)ix * x_ld);
-          float2 a[4], b2[4];
-          unpack8f2(__ldg(pp), a);
-          unpack8f2(__ldg(pp + 1), b2);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) { v[q] = a[q]; v[4 + q] = b2[q]; }
-        } else {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) v[q] = make_float2(0.f, 0.f);
-        }
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int s2 = c - t;                                // tap column for output t (compile-time)
-          if (s2 < 0 || s2 > 2) continue;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) acc[t][q & 1] = __ffma2_rn(v[q], wt[s2][q], acc[t][q & 1]);
+          acc[q] = __ffma2_rn(v[2 * q], make_float2(t4.x, t4.y), acc[q]);
+          acc[q] = __ffma2_rn(v[2 * q + 1], make_float2(t4.z, t4.w), acc[q]);
         }
       }
     }
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      if (x0 + t >= W) continue;
-      const float2 s2 = __fadd2_rn(acc[t][0], acc[t][1]);
-      const float r = b0 + (s2.x + s2.y);
-      out[(long long)row * W + x0 + t] = relu ? fmaxf(r, 0.f) : r;
-    }
+    const float2 s01 = __fadd2_rn(acc[0], acc[1]), s23 = __fadd2_rn(acc[2], acc[3]);
+    const float2 st = __fadd2_rn(s01, s23);
+    const float rr = b0 + (st.x + st.y);
+    out[i] = relu ? fmaxf(rr, 0.f) : rr;
   }
 }
 
@@ -513,18 +503,20 @@ __global__ void __launch_bounds__(256) head16_dgrad_kernel(const float* __restri
   }
 }
 
-// weight + bias gradient partials: part[block][9*16 + 1].  A block owns a contiguous run of image rows and keeps the
-// masked upstream gradient of rows y-1 .. y+1 in a rolling shared-memory window (one new row per step, zero borders), so
-// a thread = (pixel column, 8-channel group) loads its activation vector once and reads its nine gradients from shared
-// memory; 9 x 8 fp32 accumulators as packed pairs; fixed-order shuffle + shared-memory fold at the end.
-constexpr int H16_MAXW = 1024;
+// weight + bias gradient partials: part[block][9*16 + 1].  A block owns a contiguous run of image rows and walks it in
+// tiles of up to 8 rows of one image: the masked upstream gradient of the tile's rows and of the row above / below
+// (zero outside the image) is staged in shared memory with zero borders, so a thread = (pixel column, 8-channel group)
+// loads its activation vector once and reads its nine gradients from shared memory - two barriers per tile, the
+// activation loads of a whole tile in flight; 9 x 8 fp32 accumulators as packed pairs; fixed-order shuffle +
+// shared-memory fold at the end.
+constexpr int H16_MAXW = 1024, H16_R = 8;
 __global__ void __launch_bounds__(256) head16_wgrad_kernel(const float* __restrict__ dout, const float* __restrict__ out,
                                                            int relu, const bf16* __restrict__ x, long long x_ld, int B,
                                                            int H, int W, int rows_per_block, float* __restrict__ part) {
-  extern __shared__ __align__(16) float h16_smem[];          // [3][W + 2] gradient rows | reduction scratch
+  extern __shared__ __align__(16) float h16_smem[];          // [H16_R + 2][W + 2] gradient rows | reduction scratch
   const int SW = W + 2;
   float* s_g = h16_smem;
-  float (*s_red)[2][9 * 8 + 1] = reinterpret_cast<float (*)[2][9 * 8 + 1]>(h16_smem + 3 * SW + 2);
+  float (*s_red)[2][9 * 8 + 1] = reinterpret_cast<float (*)[2][9 * 8 + 1]>(h16_smem + (H16_R + 2) * SW + 2);
   const int c8 = threadIdx.x & 1, px0 = threadIdx.x >> 1;
   float2 acc[9][4];
 #pragma unroll
@@ -534,48 +526,44 @@ __global__ void __launch_bounds__(256) head16_wgrad_kernel(const float* __restri
   float bsum = 0.f;
   const int rows = B * H;
   const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
-  auto stage = [&](int slot, int row, bool valid) {            // masked gradient row -> s_g[slot][1 .. W], zero if invalid
-    float* dst = s_g + slot * SW;
-    for (int xx = threadIdx.x; xx < SW; xx += 256) {
+  for (int row0 = r0; row0 < r1;) {
+    const int y0 = row0 % H;
+    const int nr = min(min(H16_R, H - y0), r1 - row0);         // rows of this tile: one image, this block's run
+    __syncthreads();                                           // the previous tile's reads are done
+    for (int e = threadIdx.x; e < (nr + 2) * SW; e += 256) {   // slot k holds gradient row row0 - 1 + k
+      const int k = e / SW, xs = e - k * SW;
+      const bool valid = (k >= 1 && k <= nr) || (k == 0 && y0 > 0) || (k == nr + 1 && y0 + nr < H);
       float gv = 0.f;
-      if (valid && xx >= 1 && xx <= W) {
-        const long long o = (long long)row * W + xx - 1;
+      if (valid && xs >= 1 && xs <= W) {
+        const long long o = (long long)(row0 - 1 + k) * W + xs - 1;
         gv = __ldg(dout + o);
         if (relu && !(__ldg(out + o) > 0.f)) gv = 0.f;
       }
-      dst[xx] = gv;
+      s_g[e] = gv;
     }
-  };
-  for (int row = r0; row < r1; ++row) {
-    const int y = row % H;
-    // window slots: gradient row (y + d) lives in slot (row + d + 3) % 3; rows of other images / outside are zero
-    if (row == r0 || y == 0) {
-      __syncthreads();
-      stage((row + 2) % 3, row - 1, y > 0);
-      stage(row % 3, row, true);
-    }
-    __syncthreads();                                           // (previous row's reads of the slot being replaced are done)
-    stage((row + 1) % 3, row + 1, y + 1 < H);
     __syncthreads();
-    const float* gm = s_g + ((row + 2) % 3) * SW;              // gradient row y - 1
-    const float* g0 = s_g + (row % 3) * SW;
-    const float* gp = s_g + ((row + 1) % 3) * SW;              // gradient row y + 1
-    for (int xx = px0; xx < W; xx += 128) {
-      float2 v[4];
-      unpack8f2(__ldg(reinterpret_cast<const uint4*>(x + ((long long)row * W + xx) * x_ld + c8 * 8)), v);
-      // dw[r][s] += g[y - (r-1)][x - (s-1)] * v : tap (r, s) pairs with gradient row y + 1 - r, column xx + 1 - s (+1 border)
+    for (int rr = 0; rr < nr; ++rr) {
+      const float* gm = s_g + rr * SW;                         // gradient row y - 1
+      const float* g0 = gm + SW;
+      const float* gp = g0 + SW;                               // gradient row y + 1
       const float* grow[3] = {gp, g0, gm};
+      for (int xx = px0; xx < W; xx += 128) {
+        float2 v[4];
+        unpack8f2(__ldg(reinterpret_cast<const uint4*>(x + ((long long)(row0 + rr) * W + xx) * x_ld + c8 * 8)), v);
+        // dw[r][s] += g[y - (r-1)][x - (s-1)] * v : tap (r, s) pairs with gradient row y + 1 - r, column xx + 1 - s (+1 border)
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
+        for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int s2 = 0; s2 < 3; ++s2) {
-          const float gv = grow[r][xx + 2 - s2];
-          if (r == 1 && s2 == 1 && c8 == 0) bsum += gv;
-          const float2 gg = make_float2(gv, gv);
+          for (int s2 = 0; s2 < 3; ++s2) {
+            const float gv = grow[r][xx + 2 - s2];
+            if (r == 1 && s2 == 1 && c8 == 0) bsum += gv;
+            const float2 gg = make_float2(gv, gv);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) acc[r * 3 + s2][q] = __ffma2_rn(gg, v[q], acc[r * 3 + s2][q]);
-        }
+            for (int q = 0; q < 4; ++q) acc[r * 3 + s2][q] = __ffma2_rn(gg, v[q], acc[r * 3 + s2][q]);
+          }
+      }
     }
+    row0 += nr;
   }
   // lanes with equal parity hold the same channel group: fold them with xor shuffles down to lanes 0 / 1
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -606,11 +594,14 @@ __global__ void __launch_bounds__(256) head16_wgrad_kernel(const float* __restri
 __global__ void head_conv_wgrad_reduce_kernel(const float* __restrict__ part, int nblocks, int C, int KS,
                                               float* __restrict__ dw /*[C][KS][KS]*/, float* __restrict__ db,
                                               int accumulate) {
+  // one warp per output: lanes stride the per-block partials (fixed order), fp64 butterfly
   const int nacc = KS * KS * C + 1;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= nacc) return;
   double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += (double)part[(size_t)b * nacc + i];
+  for (int b = lane; b < nblocks; b += 32) s += (double)part[(size_t)b * nacc + i];
+  s = dp::warp_sum(s);
+  if (lane != 0) return;
   if (i == nacc - 1) {
     if (db) db[0] = accumulate ? db[0] + (float)s : (float)s;
   } else {
@@ -693,8 +684,7 @@ int dp_head_conv_fwd(const void* x, long long x_ld, int B, int H, int W, int C, 
                      const float* bias, int relu, float* out, cudaStream_t stream) {
   DP_CHECK_ARG(x && w && out && C % 8 == 0 && (KS == 1 || KS == 3), "dp_head_conv_fwd: bad arguments");
   if (C == 16 && KS == 3 && x_ld % 8 == 0 && (long long)B * H * W < (1LL << 31)) {
-    const int strips = (W + 3) / 4;
-    head16_fwd_kernel<<<grid_for((size_t)B * H * strips), 256, 0, stream>>>((const bf16*)x, x_ld, B, H, W, w, bias, relu, out);
+    head16_fwd_kernel<<<grid_for((size_t)B * H * W), 256, 0, stream>>>((const bf16*)x, x_ld, B, H, W, w, bias, relu, out);
     DP_CHECK_LAUNCH("head16_fwd_kernel");
     return DP_OK;
   }
@@ -728,10 +718,10 @@ int dp_head_conv_bwd(const float* dout, const float* out, int relu, const void* 
     const int rows = B * H;
     const int rpb = (rows + kHeadWgBlocks - 1) / kHeadWgBlocks;
     const int nblk = (rows + rpb - 1) / rpb;                        // <= kHeadWgBlocks: the partials buffer has room
-    const size_t smem = ((size_t)3 * (W + 2) + 2 + 8 * 2 * 73) * sizeof(float);
+    const size_t smem = ((size_t)(H16_R + 2) * (W + 2) + 2 + 8 * 2 * 73) * sizeof(float);
     head16_wgrad_kernel<<<nblk, 256, smem, stream>>>(dout, out, relu, (const bf16*)x, x_ld, B, H, W, rpb, (float*)workspace);
     DP_CHECK_LAUNCH("head16_wgrad_kernel");
-    head_conv_wgrad_reduce_kernel<<<ceil_div(KS * KS * C + 1, 128), 128, 0, stream>>>((const float*)workspace, nblk, C, KS, dw, db, accumulate);
+    head_conv_wgrad_reduce_kernel<<<ceil_div((KS * KS * C + 1) * 32, 256), 256, 0, stream>>>((const float*)workspace, nblk, C, KS, dw, db, accumulate);
     DP_CHECK_LAUNCH("head_conv_wgrad_reduce_kernel");
     return DP_OK;
   }
@@ -753,7 +743,7 @@ int dp_head_conv_bwd(const float* dout, const float* out, int relu, const void* 
                                                                       H, W, C, KS, (float*)workspace);
       DP_CHECK_LAUNCH("head_conv_wgrad_kernel");
     }
-    head_conv_wgrad_reduce_kernel<<<dp::ceil_div(nacc, 128), 128, 0, stream>>>((const float*)workspace, kHeadWgBlocks, C,
+    head_conv_wgrad_reduce_kernel<<<dp::ceil_div(nacc * 32, 256), 256, 0, stream>>>((const float*)workspace, kHeadWgBlocks, C,
                                                                                KS, dw, db, accumulate);
     DP_CHECK_LAUNCH("head_conv_wgrad_reduce_kernel");
   }
