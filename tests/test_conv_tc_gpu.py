@@ -138,6 +138,24 @@ def test_conv_bn_statistics_with_bias_small_n(pkg, Cin, Cout, KS):
     assert torch.allclose(s[1], (y * y).sum(0), rtol=1e-4, atol=1e-2)
 
 
+@pytest.mark.parametrize("Cin,Cout", [(96, 576), (136, 816), (232, 1392), (32, 192)])
+def test_conv_bn_statistics_wide_many_tiles(pkg, Cin, Cout):
+    """wide (64-column sub-block) epilogue with several tiles per persistent CTA: the per-N-block sums are folded into
+    the CTA's row of the partials whenever the N block changes (3 and 6 N blocks: every tile; 1 and 4: once), and the
+    last N block of 816 / 1392 holds sub-blocks without real channels."""
+    B, H, W = 8, 45, 52
+    g = torch.Generator().manual_seed(Cin + Cout)
+    x = torch.randn(B, H, W, Cin, generator=g).to(torch.bfloat16).cuda()
+    w = (torch.randn(Cout, Cin, 1, 1, generator=g) * 0.1).cuda()
+    out, _, st = run_conv(pkg, x, pack_w(w), Cout, 1, stats=True)
+    ref = ref_conv(x, w, None, None, 1)
+    assert bool(((out.float() - ref).abs() <= 2 ** -7 * ref.abs() + 2e-3).all())
+    s = st.double().sum(dim=0)
+    y = out.double().reshape(-1, Cout)
+    assert torch.allclose(s[0], y.sum(0), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(s[1], (y * y).sum(0), rtol=1e-4, atol=1e-2)
+
+
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 40, 48, 64, 64), (3, 24, 40, 64, 32), (1, 50, 70, 32, 16)])
 def test_conv_bn_statistics(pkg, B, H, W, Cin, Cout):
     g = torch.Generator().manual_seed(9)
