@@ -25,10 +25,11 @@ class GraphedTrainStep:
         self.red = D.GradientAllReducer(model.parameters(), world)
         self.out = None
         self._copy = self._sx = self._st = self._consumed = None
-        # Optional copy-stream overlap of the next batch's H2D with the current replay (overlap_h2d=True, single rank
-        # only).  Measured end to end it ranged from +2 % to -7 % against plain main-stream copies across runs on one
-        # GPU, and it doubled the step time at N = 4 with NCCL collectives captured in the graph (the H2D bandwidth
-        # itself was a full 55 GB/s per rank), so the default is the predictable main-stream copy (+2.6 ms per step).
+        # Optional copy-stream overlap of the next batch's H2D with the current replay (overlap_h2d=True).  Measured
+        # end to end on one GPU (round 2, six runs of 16 steps): 60.1 / 60.4 ms per step when it works (= the device time,
+        # against 61.9 with main-stream copies) but 62.2 / 62.3 / 66.0 / 67.2 in the other runs - bimodal per process, also
+        # with a high-priority copy stream - and 94.9 vs 68.3 ms at N = 2 with the NCCL collectives captured in the graph.
+        # The default is therefore the predictable main-stream copy (+2.2 ms per step).
         self._overlap_h2d = bool(overlap_h2d)
         self._step = 0
         self._hout = [torch.empty(8, dtype=torch.float32).pin_memory() for _ in range(2)]
