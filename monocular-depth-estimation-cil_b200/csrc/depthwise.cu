@@ -1,13 +1,18 @@
 // Depthwise convolutions of the EfficientNet-Lite3 encoder trunk (the hub model consumed at
 // reference src/network/blocks.py:166-186): k3 / k5, stride 1 / 2, NHWC bf16, fp32 accumulation.
-// All three passes are bandwidth-bound (9..25 MAC per element), so the design goal is to touch HBM once per tensor:
-//   * forward (and, with flipped taps, the stride-1 data gradient): each thread owns 8 channels (one 16-byte vector) of
-//     a strip of 4 output pixels and slides the K x (3*S+K) input window through registers; the BatchNorm batch
-//     statistics (sum, sum of squares of the stored bf16 value) of the layer that follows are accumulated on the fly
-//     and reduced deterministically per block, so the BN needs no extra pass over the output;
-//   * stride-2 data gradient: gather over the taps whose parity matches;
-//   * weight gradient: thread = 8 channels x one kernel row, K x 8 fp32 accumulators, fixed-order two-level reduction
-//     (no atomics).
+// By bytes all passes are bandwidth-bound (9..25 MAC per element); in practice the k5 layers are FMA / issue-bound (100
+// packed FFMA2 per 16-byte output vector), so the design touches HBM once per tensor AND unpacks every operand once:
+//   * stride-1 forward and (flipped taps) stride-1 data gradient: dw_tile_kernel - persistent blocks, one TMA box per
+//     (TH+K-1) x (TW+K-1) input tile into one of two shared-memory buffers, R x XO output patch per thread, packed MACs,
+//     BatchNorm batch statistics (sum, sum of squares of the stored bf16 value) accumulated on the fly and reduced
+//     deterministically per block, so the BN that follows needs no extra pass over the output;
+//   * stride-2 forward: dw_fwd_kernel (register window, 75 % of its HBM floor);
+//   * stride-2 data gradient: dw_dgrad_s2_tile_kernel - 2 x 2 output blocks from a TMA tile of dy, tap sets compile-time
+//     per parity of the top / left padding;
+//   * weight gradient (both strides): dw_wgrad_tile_kernel - dy tile and input tile by TMA, thread = (channel group,
+//     kernel row, row slot) with a sliding window, fixed-order two-level reduction (no atomics).
+// dw_dgrad_s2_kernel / dw_wgrad_kernel are the round-1 gather forms, kept for operands whose pixel stride is not a
+// multiple of 8 channels (TMA needs 16-byte strides).
 #include "common.cuh"
 #include "tc.cuh"
 #include "../../include/depth_b200.h"

@@ -933,12 +933,12 @@ class Fusion:
     """which BatchNorm fusions the block-level autograd nodes use.  Policy from tools/fused_micro.py on B200 (B = 32,
     448x576, ms per launch; profiles/fused_micro_r2.txt):
 
-      backward (ReLU mask + BatchNorm-backward sums in the data-gradient epilogue): 64->64 1.04 vs 0.62 + 0.45 for the
-        separate reduction pass, 32->32 0.49 vs 0.29 + 0.23, 32->64 0.88 vs 0.57 + 0.45: on (break-even to 15 % faster,
+      backward (ReLU mask + BatchNorm-backward sums in the data-gradient epilogue): 64->64 0.89 vs 0.52 + 0.45 for the
+        separate reduction pass, 32->32 0.45 vs 0.23 + 0.23, 32->64 0.78 vs 0.37 + 0.45: on (break-even to 8 % faster,
         one launch and one full read of the gradient fewer).
-      prologue (bn + ReLU inside the consumer conv's operand path): 64->64 forward 0.92 vs 0.62 + 0.41 for conv + bn_apply,
-        but the weight gradient then has to re-create the activation in its own operand path (0.95 vs 0.70), and at
-        <= 32 channels the four transform warps cannot keep up with the HBM-bound tile rate (32->32 0.66 vs 0.29 + 0.21).
+      prologue (bn + ReLU inside the consumer conv's operand path): 64->64 forward 0.76 vs 0.52 + 0.41 for conv + bn_apply,
+        but the weight gradient then has to re-create the activation in its own operand path (0.99 vs 0.68), and at
+        <= 32 channels the four transform warps cannot keep up with the HBM-bound tile rate (32->32 0.53 vs 0.23 + 0.21).
         "auto": used where it wins - forward passes that keep no graph (eval / no_grad) with >= 64 input channels;
         True / False force it (tests compare both paths bit for bit)."""
     prologue = "auto"
