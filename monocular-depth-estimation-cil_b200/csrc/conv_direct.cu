@@ -394,39 +394,52 @@ __device__ __forceinline__ void unpack8f2(const uint4& u, float2 (&f)[4]) {
   for (int i = 0; i < 4; ++i) f[i] = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
 }
 
-// forward: thread = one output pixel (adjacent lanes read adjacent 32-byte pixels: a warp load touches 8 cache lines; a
-// 4-pixel strip per thread put every lane on its own line and the kernel ran at the L1 tag rate, 293 us); four
-// independent packed accumulators, each tap's 16 weights from shared memory ([tap][16])
-__global__ void __launch_bounds__(256) head16_fwd_kernel(const bf16* __restrict__ x, long long x_ld, int B, int H, int W,
+// forward: thread = 4 vertically adjacent output pixels of one column.  Adjacent lanes sit on adjacent 32-byte pixels
+// (a warp load touches 8 cache lines - a horizontal 4-pixel strip per thread put every lane on its own line and ran at the
+// L1 tag rate), and the 6 x 3 input vectors under the strip are loaded and unpacked once for the four outputs (4.5
+// vectors per output instead of 9); two independent packed accumulators per output, weights from shared memory.
+__global__ void __launch_bounds__(256, 2) head16_fwd_kernel(const bf16* __restrict__ x, long long x_ld, int B, int H, int W,
                                                          const float* __restrict__ w /*[16][3][3]*/,
                                                          const float* __restrict__ bias, int relu, float* __restrict__ out) {
   __shared__ __align__(16) float sw[9 * 16];
   if (threadIdx.x < 144) sw[threadIdx.x] = w[(threadIdx.x % 16) * 9 + threadIdx.x / 16];
   __syncthreads();
-  const int total = B * H * W;
+  const int HG = (H + 3) >> 2;
+  const int total = B * HG * W;
   const float b0 = bias ? __ldg(bias) : 0.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int xx = i % W, row = i / W;
-    const int y = row % H;
-    float2 acc[4];
+    const int xx = i % W, rg = i / W;
+    const int yg = rg % HG, b = rg / HG;
+    const int y0 = yg * 4;
+    const long long img = (long long)b * H;
+    float2 acc[4][2];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) acc[q] = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int iy = y + r - 1;
+    for (int t = 0; t < 4; ++t) { acc[t][0] = make_float2(0.f, 0.f); acc[t][1] = make_float2(0.f, 0.f); }
+    // the six loads of input row rin + 1 are issued before row rin is consumed (the kernel is bound by load latency)
+    auto load_row = [&](int rin, uint4 (&u)[3][2]) {
+      const int iy = y0 - 1 + rin;
       const bool rok = iy >= 0 && iy < H;
-      uint4 u[3][2];
-#pragma unroll
-      for (int s2 = 0; s2 < 3; ++s2) {                          // the row's six loads are issued before any is used
-        const int ix = xx + s2 - 1;
-        const bool ok = rok && ix >= 0 && ix < W;
-        const uint4* pp = reinterpret_cast<const uint4*>(x + (long long)(ok ? i + (r - 1) * W + (s2 - 1) : i) * x_ld);
-        u[s2][0] = __ldg(pp);
-        u[s2][1] = __ldg(pp + 1);
-        if (!ok) { u[s2][0] = make_uint4(0, 0, 0, 0); u[s2][1] = make_uint4(0, 0, 0, 0); }
-      }
 #pragma unroll
       for (int s2 = 0; s2 < 3; ++s2) {
+        const int ix = xx + s2 - 1;
+        const bool ok = rok && ix >= 0 && ix < W;
+        const uint4* pp = reinterpret_cast<const uint4*>(x + ((img + (ok ? iy : y0)) * W + (ok ? ix : xx)) * x_ld);
+        u[s2][0] = __ldg(pp);
+        u[s2][1] = __ldg(pp + 1);
+      }
+    };
+    uint4 ua[3][2], ub[3][2];
+    load_row(0, ua);
+#pragma unroll
+    for (int rin = 0; rin < 6; ++rin) {
+      uint4 (&u)[3][2] = (rin & 1) ? ub : ua;
+      if (rin + 1 < 6) load_row(rin + 1, (rin & 1) ? ua : ub);
+      const int iy = y0 - 1 + rin;
+      const bool rok = iy >= 0 && iy < H;
+#pragma unroll
+      for (int s2 = 0; s2 < 3; ++s2) {
+        const int ix = xx + s2 - 1;
+        if (!(rok && ix >= 0 && ix < W)) continue;             // zero padding: the tap contributes nothing
         float2 v[8];
         {
           float2 a2[4], b2[4];
@@ -436,17 +449,25 @@ __global__ void __launch_bounds__(256) head16_fwd_kernel(const bf16* __restrict_
           for (int q = 0; q < 4; ++q) { v[q] = a2[q]; v[4 + q] = b2[q]; }
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 t4 = *reinterpret_cast<const float4*>(&sw[(r * 3 + s2) * 16 + q * 4]);
-          acc[q] = __ffma2_rn(v[2 * q], make_float2(t4.x, t4.y), acc[q]);
-          acc[q] = __ffma2_rn(v[2 * q + 1], make_float2(t4.z, t4.w), acc[q]);
+        for (int t = 0; t < 4; ++t) {
+          const int r = rin - t;                                // tap row of output t under input row rin (compile-time)
+          if (r < 0 || r > 2) continue;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 t4 = *reinterpret_cast<const float4*>(&sw[(r * 3 + s2) * 16 + q * 4]);
+            acc[t][q & 1] = __ffma2_rn(v[2 * q], make_float2(t4.x, t4.y), acc[t][q & 1]);
+            acc[t][q & 1] = __ffma2_rn(v[2 * q + 1], make_float2(t4.z, t4.w), acc[t][q & 1]);
+          }
         }
       }
     }
-    const float2 s01 = __fadd2_rn(acc[0], acc[1]), s23 = __fadd2_rn(acc[2], acc[3]);
-    const float2 st = __fadd2_rn(s01, s23);
-    const float rr = b0 + (st.x + st.y);
-    out[i] = relu ? fmaxf(rr, 0.f) : rr;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (y0 + t >= H) continue;
+      const float2 st = __fadd2_rn(acc[t][0], acc[t][1]);
+      const float rr = b0 + (st.x + st.y);
+      out[((img + y0 + t) * W) + xx] = relu ? fmaxf(rr, 0.f) : rr;
+    }
   }
 }
 
@@ -510,7 +531,7 @@ __global__ void __launch_bounds__(256) head16_dgrad_kernel(const float* __restri
 // activation loads of a whole tile in flight; 9 x 8 fp32 accumulators as packed pairs; fixed-order shuffle +
 // shared-memory fold at the end.
 constexpr int H16_MAXW = 1024, H16_R = 8;
-__global__ void __launch_bounds__(256) head16_wgrad_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+__global__ void __launch_bounds__(256, 2) head16_wgrad_kernel(const float* __restrict__ dout, const float* __restrict__ out,
                                                            int relu, const bf16* __restrict__ x, long long x_ld, int B,
                                                            int H, int W, int rows_per_block, float* __restrict__ part) {
   extern __shared__ __align__(16) float h16_smem[];          // [H16_R + 2][W + 2] gradient rows | reduction scratch
@@ -530,36 +551,56 @@ __global__ void __launch_bounds__(256) head16_wgrad_kernel(const float* __restri
     const int y0 = row0 % H;
     const int nr = min(min(H16_R, H - y0), r1 - row0);         // rows of this tile: one image, this block's run
     __syncthreads();                                           // the previous tile's reads are done
-    for (int e = threadIdx.x; e < (nr + 2) * SW; e += 256) {   // slot k holds gradient row row0 - 1 + k
-      const int k = e / SW, xs = e - k * SW;
-      const bool valid = (k >= 1 && k <= nr) || (k == 0 && y0 > 0) || (k == nr + 1 && y0 + nr < H);
-      float gv = 0.f;
-      if (valid && xs >= 1 && xs <= W) {
-        const long long o = (long long)(row0 - 1 + k) * W + xs - 1;
-        gv = __ldg(dout + o);
-        if (relu && !(__ldg(out + o) > 0.f)) gv = 0.f;
+    for (int e0 = threadIdx.x; e0 < (nr + 2) * SW; e0 += 4 * 256) {   // slot k holds gradient row row0 - 1 + k
+      float gd[4], go[4];
+      bool live[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {                                   // four elements per thread, all loads first
+        const int e = e0 + q * 256;
+        const int k = e / SW, xs = e - k * SW;
+        const bool valid = e < (nr + 2) * SW && ((k >= 1 && k <= nr) || (k == 0 && y0 > 0) || (k == nr + 1 && y0 + nr < H));
+        live[q] = valid && xs >= 1 && xs <= W;
+        const long long o = live[q] ? (long long)(row0 - 1 + k) * W + xs - 1 : (long long)row0 * W;
+        gd[q] = __ldg(dout + o);
+        go[q] = relu ? __ldg(out + o) : 1.f;
       }
-      s_g[e] = gv;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int e = e0 + q * 256;
+        if (e < (nr + 2) * SW) s_g[e] = (live[q] && go[q] > 0.f) ? gd[q] : 0.f;
+      }
     }
     __syncthreads();
-    for (int rr = 0; rr < nr; ++rr) {
-      const float* gm = s_g + rr * SW;                         // gradient row y - 1
-      const float* g0 = gm + SW;
-      const float* gp = g0 + SW;                               // gradient row y + 1
-      const float* grow[3] = {gp, g0, gm};
-      for (int xx = px0; xx < W; xx += 128) {
+    // this thread's items of the tile: (row rr, column px0 + 128 k); eight activation loads in flight at a time (the
+    // kernel is bound by the latency of these loads, not by their bytes)
+    const int nk = px0 < W ? (W - px0 + 127) / 128 : 0;
+    const int nitems = nr * nk;
+    for (int j0 = 0; j0 < nitems; j0 += 8) {
+      uint4 u[8];
+      int rrs[8], xxs[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int j = min(j0 + q, nitems - 1);
+        rrs[q] = j / nk;
+        xxs[q] = px0 + (j - rrs[q] * nk) * 128;
+        u[q] = __ldg(reinterpret_cast<const uint4*>(x + ((long long)(row0 + rrs[q]) * W + xxs[q]) * x_ld + c8 * 8));
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (j0 + q >= nitems) break;
         float2 v[4];
-        unpack8f2(__ldg(reinterpret_cast<const uint4*>(x + ((long long)(row0 + rr) * W + xx) * x_ld + c8 * 8)), v);
-        // dw[r][s] += g[y - (r-1)][x - (s-1)] * v : tap (r, s) pairs with gradient row y + 1 - r, column xx + 1 - s (+1 border)
+        unpack8f2(u[q], v);
+        const float* gm = s_g + rrs[q] * SW + xxs[q];          // gradient row y - 1 (slot rr), column xx - 1 (+1 border)
+        // dw[r][s] += g[y - (r-1)][x - (s-1)] * v : tap (r, s) pairs with gradient row y + 1 - r, column xx + 1 - s
 #pragma unroll
         for (int r = 0; r < 3; ++r)
 #pragma unroll
           for (int s2 = 0; s2 < 3; ++s2) {
-            const float gv = grow[r][xx + 2 - s2];
+            const float gv = gm[(2 - r) * SW + 2 - s2];
             if (r == 1 && s2 == 1 && c8 == 0) bsum += gv;
             const float2 gg = make_float2(gv, gv);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) acc[r * 3 + s2][q] = __ffma2_rn(gg, v[q], acc[r * 3 + s2][q]);
+            for (int t = 0; t < 4; ++t) acc[r * 3 + s2][t] = __ffma2_rn(gg, v[t], acc[r * 3 + s2][t]);
           }
       }
     }
@@ -684,7 +725,7 @@ int dp_head_conv_fwd(const void* x, long long x_ld, int B, int H, int W, int C, 
                      const float* bias, int relu, float* out, cudaStream_t stream) {
   DP_CHECK_ARG(x && w && out && C % 8 == 0 && (KS == 1 || KS == 3), "dp_head_conv_fwd: bad arguments");
   if (C == 16 && KS == 3 && x_ld % 8 == 0 && (long long)B * H * W < (1LL << 31)) {
-    head16_fwd_kernel<<<grid_for((size_t)B * H * W), 256, 0, stream>>>((const bf16*)x, x_ld, B, H, W, w, bias, relu, out);
+    head16_fwd_kernel<<<grid_for((size_t)B * ((H + 3) / 4) * W), 256, 0, stream>>>((const bf16*)x, x_ld, B, H, W, w, bias, relu, out);
     DP_CHECK_LAUNCH("head16_fwd_kernel");
     return DP_OK;
   }
