@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--no-config5", action="store_true")
-    ap.add_argument("--overlap-h2d", action="store_true", help="next batch's H2D on a copy stream under the current replay")
+    ap.add_argument("--no-overlap-h2d", action="store_true", help="copy each batch on the main stream instead of under the previous replay")
     ap.add_argument("--profile-layers", action="store_true", help="print per-shape conv timings to stderr")
     ap.add_argument("--no-side-wgrad", action="store_true", help="keep weight gradients on the main stream")
     ap.add_argument("--torch-encoder", action="store_true", help="run the EfficientNet-Lite3 trunk through PyTorch/cuDNN")
@@ -382,7 +382,7 @@ def run_ours(a):
     xd, td = xh.to(dev), th.to(dev)
     # The whole step (forward, combined_loss, backward, NCCL gradient all-reduce, AdamW) is one CUDA graph.
     gstep = depth_b200.GraphedTrainStep(model, opt, cfg, xd, td, use_rgb=True, world=world, warmup=max(a.warmup, 3),
-                                        side_wgrad=not a.no_side_wgrad, overlap_h2d=a.overlap_h2d)
+                                        side_wgrad=not a.no_side_wgrad, overlap_h2d=not a.no_overlap_h2d)
     red = gstep.red
 
     def step(x, t, read_loss):

@@ -16,7 +16,7 @@ from . import distributed as D
 
 class GraphedTrainStep:
     def __init__(self, model, optimizer, config, example_inputs, example_targets, use_rgb=True, world=None,
-                 warmup=3, side_wgrad=True, overlap_h2d=False):
+                 warmup=3, side_wgrad=True, overlap_h2d=True):
         assert example_inputs.is_cuda and example_targets.is_cuda
         self.model, self.opt, self.cfg, self.use_rgb = model, optimizer, config, use_rgb
         self.side_wgrad = side_wgrad
@@ -25,12 +25,19 @@ class GraphedTrainStep:
         self.red = D.GradientAllReducer(model.parameters(), world)
         self.out = None
         self._copy = self._sx = self._st = self._consumed = None
-        # Optional copy-stream overlap of the next batch's H2D with the current replay (overlap_h2d=True).  Measured
-        # end to end on one GPU (round 2, six runs of 16 steps): 60.1 / 60.4 ms per step when it works (= the device time,
-        # against 61.9 with main-stream copies) but 62.2 / 62.3 / 66.0 / 67.2 in the other runs - bimodal per process, also
-        # with a high-priority copy stream - and 94.9 vs 68.3 ms at N = 2 with the NCCL collectives captured in the graph.
-        # The default is therefore the predictable main-stream copy (+2.2 ms per step).
+        # Copy-stream overlap of the next batch's H2D with the current replay: host batches travel on a copy stream into
+        # staging buffers while the previous replay runs, and a device copy (0.1 ms) moves them into the graph's static
+        # inputs.  The copy stream and the staging buffers are created HERE: created lazily in the first call they cost a
+        # one-time 30 - 130 ms (two fresh 88 / 44 MB cudaMallocs next to a 45 GB graph pool), which earlier measurements
+        # of 8 - 16 steps mistook for a slow mode of the overlap itself (62 - 68 ms per step; 94.9 at N = 2).  In steady
+        # state the end-to-end step equals the device step (tools/overlap_probe.py: 59.8 - 60.1 ms in 12 of 12 processes
+        # against 61.9 with main-stream copies).  Needs the host to run one step ahead: read losses with loss_dict(lag=1).
         self._overlap_h2d = bool(overlap_h2d)
+        if self._overlap_h2d:
+            self._copy = torch.cuda.Stream()
+            self._sx, self._st = torch.empty_like(self.x), torch.empty_like(self.t)
+            self._consumed = torch.cuda.Event()
+            self._consumed.record(torch.cuda.current_stream())
         self._step = 0
         self._hout = [torch.empty(8, dtype=torch.float32).pin_memory() for _ in range(2)]
         self._done = [torch.cuda.Event(), torch.cuda.Event()]
@@ -97,33 +104,25 @@ class GraphedTrainStep:
         """one optimisation step; inputs/targets may be (pinned) host or device tensors, or None to reuse the static
         batch.  Returns the device tensor of loss scalars (index with depth_b200._lib.L_*); no host sync.
 
-        Host batches are copied into the graph's static inputs on the main stream (asynchronously from pinned memory);
-        with overlap_h2d=True (single rank) they travel on a copy stream into a staging buffer instead, so the H2D
-        transfer of step i can overlap the graph replay of step i-1.  The loss scalars of every step are copied to pinned host memory asynchronously (`loss_dict`)."""
+        With overlap_h2d=False host batches are copied into the graph's static inputs on the main stream;
+        with overlap_h2d=True (the default) they travel on a copy stream into a staging buffer instead, so the H2D
+        transfer of step i overlaps the graph replay of step i-1.  The loss scalars of every step are copied to pinned host memory asynchronously (`loss_dict`)."""
         main = torch.cuda.current_stream()
-        if (inputs is not None or targets is not None) and not self._overlap_h2d:
-            if inputs is not None:                 # copies on the main stream (no overlap with the previous replay)
-                self.x.copy_(inputs, non_blocking=True)
-            if targets is not None:
-                self.t.copy_(targets, non_blocking=True)
-        elif inputs is not None or targets is not None:
-            if self._copy is None:
-                self._copy = torch.cuda.Stream()
-                self._sx, self._st = torch.empty_like(self.x), torch.empty_like(self.t)
-                self._consumed = torch.cuda.Event()
-                self._consumed.record(main)
+        host = [(dst, stg, src) for dst, stg, src in ((self.x, self._sx, inputs), (self.t, self._st, targets))
+                if src is not None and self._overlap_h2d and not src.is_cuda]
+        for dst, src in ((self.x, inputs), (self.t, targets)):
+            if src is not None and not (self._overlap_h2d and not src.is_cuda):
+                dst.copy_(src, non_blocking=True)      # device tensors (ordered after their producer on this stream),
+                                                       # or host tensors with the overlap switched off
+        if host:
             cs = self._copy
-            cs.wait_event(self._consumed)                 # the previous step has finished reading the staging buffers
+            cs.wait_event(self._consumed)              # the previous step has finished reading the staging buffers
             with torch.cuda.stream(cs):
-                if inputs is not None:
-                    self._sx.copy_(inputs, non_blocking=True)
-                if targets is not None:
-                    self._st.copy_(targets, non_blocking=True)
+                for _, stg, src in host:
+                    stg.copy_(src, non_blocking=True)
             main.wait_stream(cs)
-            if inputs is not None:
-                self.x.copy_(self._sx, non_blocking=True)
-            if targets is not None:
-                self.t.copy_(self._st, non_blocking=True)
+            for dst, stg, _ in host:
+                dst.copy_(stg, non_blocking=True)
             self._consumed.record(main)
         self.graph.replay()
         ops.PACKS.invalidate()                     # the replay moved the weights without bumping their _version
