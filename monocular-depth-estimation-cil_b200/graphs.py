@@ -11,6 +11,7 @@ import os
 import torch
 
 from . import ops, util
+from .network import frozen_cast
 from . import distributed as D
 
 
@@ -124,6 +125,7 @@ class GraphedTrainStep:
             for dst, stg, _ in host:
                 dst.copy_(stg, non_blocking=True)
             self._consumed.record(main)
+        frozen_cast.refresh_all()                  # frozen-encoder bf16 weight copies the graph reads (version check only)
         self.graph.replay()
         ops.PACKS.invalidate()                     # the replay moved the weights without bumping their _version
         slot = self._step & 1

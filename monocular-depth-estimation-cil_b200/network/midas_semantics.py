@@ -4,6 +4,7 @@ import torch.nn as nn
 
 from .. import ops
 from . import blocks as _blocks
+from . import frozen_cast
 from .blocks import enter, leave
 from .dpt_depth import Dinov2Head
 from .midas_net_custom import MidasNet_small
@@ -133,6 +134,7 @@ class MidasNetSemantics(MidasNet_small):
     def dino_tokens(self, x):
         x_dinov2 = ops.resize_planes_f32(x, self.DINOv2_IMAGE_SIZE, True)
         if self.encoder_autocast:
+            frozen_cast.enable(self.dinov2)       # the frozen branch keeps bf16 copies of its Linear weights
             with torch.autocast("cuda", dtype=torch.bfloat16):
                 return self.dinov2.get_intermediate_layers(x_dinov2, 4, return_class_token=False)
         return self.dinov2.get_intermediate_layers(x_dinov2, 4, return_class_token=False)
