@@ -233,3 +233,28 @@ def test_evaluate_model_oracle_reproduces_reference_golden(golden_loss):
     got = ol.evaluate_model(Ident(), batches, "cpu")
     for k, v in golden_loss["evaluate_model"].items():
         assert abs(got[k] - v) <= 1e-6 * max(abs(v), 1e-12), (k, got[k], v)
+
+
+def test_frozen_cast_is_transparent_on_the_host():
+    """network/frozen_cast.py on the CPU side: only frozen nn.Linear modules get the caching forward, the state_dict and
+    deepcopy keep working, and without CUDA autocast the forward is the plain fp32 F.linear (no copies are made)."""
+    import copy
+    import torch
+    import torch.nn as nn
+    import depth_b200  # noqa: F401
+    from depth_b200.network import frozen_cast
+    torch.manual_seed(0)
+    m = nn.Sequential(nn.Linear(8, 16), nn.LayerNorm(16), nn.Linear(16, 4, bias=False), nn.Linear(4, 4))
+    for p in list(m[0].parameters()) + list(m[2].parameters()):
+        p.requires_grad_(False)
+    ref = copy.deepcopy(m)
+    keys = list(m.state_dict().keys())
+    frozen_cast.enable(m)
+    assert "forward" in m[0].__dict__ and "forward" in m[2].__dict__ and "forward" not in m[3].__dict__
+    x = torch.randn(5, 8)
+    assert torch.equal(m(x), ref(x))
+    assert "_dp_cast" not in m[0].__dict__                      # no autocast, no CUDA: nothing cached
+    assert list(m.state_dict().keys()) == keys
+    m2 = copy.deepcopy(m)
+    assert m2[0].forward.__self__ is m2[0] and torch.equal(m2(x), ref(x))
+    frozen_cast.refresh_all()                                   # nothing to refresh; must not raise
